@@ -1,0 +1,156 @@
+/*
+ * monai_b200 C ABI -- the drop-in boundary of the B200-native sliding-window / spatial-transform hot path.
+ *
+ * The reference (Project-MONAI/MONAI) has NO native boundary for this path: the seam is Python
+ * (monai/inferers/utils.py, monai/networks/blocks/convolutions.py, monai/transforms/spatial/array.py), and
+ * its only native module, monai._C (monai/csrc/ext.cpp:21-75), is a pybind11/ATen extension.  This header is
+ * the plain-C equivalent a maintainer would bind with ctypes: raw device pointers,
+ * sizes and an opaque CUDA stream handle -- no torch types.  Every function
+ *   - returns 0 on success, non-zero on failure (b200_last_error() gives the thread-local message),
+ *   - launches asynchronously on `stream` (a cudaStream_t / CUstream cast to void*),
+ *   - never allocates, frees or retains caller memory beyond the call (tensor maps are built per call).
+ *
+ * dtype codes: 0 = float32, 1 = float16.
+ */
+#ifndef MONAI_B200_H_
+#define MONAI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int b200_abi_version(void);
+const char* b200_last_error(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches evidence). */
+long long b200_launch_count(void);
+
+/* ---- sliding-window inference: gather + blend -------------------------------------------------------- */
+/* replaces monai/inferers/utils.py:217-224 -- copy n_win windows (win_tab[n_win][4] = {batch, d0, h0, w0},
+ * device int32) out of vol[B,C,D,H,W] into out[n_win,C,rd,rh,rw]; dtype conversion allowed. */
+int b200_sw_gather(const void* vol, int in_dtype, void* out, int out_dtype, const int32_t* win_tab, int n_win,
+                   int C, int D, int H, int W, int rd, int rh, int rw, void* stream);
+
+typedef struct b200_blend_desc {
+  const void* preds;        /* resident window predictions, windows [win_begin, win_end) */
+  int pred_dtype;
+  long long pred_stride[5]; /* element strides of preds: window, channel, d, h, w */
+  int win_begin, win_end;   /* flat window ids: batch-major, then meshgrid("ij") of the per-axis starts */
+  int B, C, D, H, W;        /* blended (padded) volume */
+  int rd, rh, rw;           /* roi */
+  const int32_t* starts_d; int nd;  /* device: per-axis window starts (dense_patch_slices, data/utils.py:166-206) */
+  const int32_t* starts_h; int nh;
+  const int32_t* starts_w; int nw;
+  const float* gd; const float* gh; const float* gw; /* device: 1-D importance factors (data/utils.py:1122-1127) */
+  float clamp_min;          /* max(min(map), 1e-3) (data/utils.py:1132-1133) */
+  const float* wmap;        /* optional device dense weight map [rd,rh,rw]; overrides gd/gh/gw when non-null */
+  void* out;                /* mode 0/2: [B,C,D,H,W] in out_dtype; mode 1: fp32 accumulators (+=) */
+  int out_dtype;
+  const float* acc;         /* mode 2: fp32 accumulators */
+  int box[4];               /* rows to visit: d in [box0,box1), h in [box2,box3); all-zero = whole volume */
+} b200_blend_desc;
+
+/* replaces monai/inferers/utils.py:264-275, 286-288, 297-298, 351-360.
+ * mode 0: all windows resident -> out = sum(w*pred)/sum(w);  mode 1: acc += sum over resident windows;
+ * mode 2: out = acc / sum(w) (the count map is evaluated analytically, never stored). */
+int b200_sw_blend(const b200_blend_desc* desc, int mode, void* stream);
+
+/* ---- convolution / normalisation / activation (NCDHW, CUDA-core path) --------------------------------- */
+typedef struct b200_conv_desc {
+  int N, Cin, Cout;
+  int Di, Hi, Wi;           /* input spatial */
+  int Do, Ho, Wo;           /* output spatial */
+  int kd, kh, kw;
+  int sd, sh, sw;           /* stride */
+  int pd, ph, pw;           /* padding */
+  int transposed;           /* 0: Conv3d (weight [Cout,Cin,k]), 1: ConvTranspose3d (weight [Cin,Cout,k]) */
+  int in_dtype, out_dtype;  /* weights and bias are always float32 */
+  long long in_stride_n;    /* element stride between samples of x (lets x be a slice of a concat buffer) */
+  long long out_stride_n;   /* element stride between samples of y */
+} b200_conv_desc;
+
+/* replaces nn.Conv3d / nn.ConvTranspose3d as used by monai/networks/blocks/convolutions.py:131-152.
+ * fp32 accumulation on CUDA cores; exact-parity path for fp32 models and odd channel counts. */
+int b200_conv3d_direct(const b200_conv_desc* desc, const void* x, const float* weight, const float* bias, void* y,
+                       void* stream);
+
+/* per-(n,c) sum and sum of squares over S = D*H*W elements of x[N,C,S] -> stats[N*C][2] (float32, overwritten).
+ * x_stride_n = element stride between samples. */
+int b200_instnorm_stats(const void* x, int dtype, int N, int C, long long S, long long x_stride_n, float* stats,
+                        void* stream);
+
+/* y = act( (x - mean) * rstd * gamma + beta  [+ res] ) with mean/rstd from stats (biased variance, eps);
+ * stats == NULL skips the normalisation.  replaces InstanceNorm3d + PReLU/LeakyReLU (ADN,
+ * monai/networks/blocks/acti_norm.py:19-101) and the residual add of UnetResBlock (dynunet_block.py:97-111).
+ * res_stats != NULL additionally instance-normalises the residual branch (norm3 of UnetResBlock).
+ * act: 0 none, 1 leaky-relu(slope), 2 prelu (slope_ptr[c % n_slope]), 3 relu, 4 gelu(erf). */
+int b200_norm_act(const void* x, int dtype, int N, int C, long long S, long long x_stride_n, const float* stats,
+                  float eps, const float* gamma, const float* beta, const void* res, long long res_stride_n,
+                  const float* res_stats, int act, float slope, const float* slope_ptr, int n_slope, void* y,
+                  long long y_stride_n, void* stream);
+
+/* MaxPool3d(kernel=2, stride=2) on [N,C,D,H,W] (basic_unet.py:61-89). */
+int b200_maxpool3d_2(const void* x, int dtype, int NC, int D, int H, int W, void* y, void* stream);
+
+/* replicate-pad / copy x[N,C,Di,Hi,Wi] into the channel slice of y (zero-copy concat helper, basic_unet.py:165-172):
+ * y[n, c_off + c, d, h, w] = x[n, c, min(d,Di-1), ...]. */
+int b200_copy_channels(const void* x, int dtype, int N, int C, int Di, int Hi, int Wi, void* y, int Ctot, int c_off,
+                       int Do, int Ho, int Wo, void* stream);
+
+/* ---- spatial transforms ----------------------------------------------------------------------------- */
+/* out[c, i,j,k] = sample(src[c], M * (i,j,k,1)) for a 3x4 row-major double matrix M that maps OUTPUT voxel
+ * indices to INPUT voxel indices (the composition the reference reaches through AffineTransform /
+ * affine_grid + grid_sample: monai/networks/layers/spatial_transforms.py:502-592, spatial/array.py:2015-2117).
+ * interp: 0 nearest, 1 trilinear.  pad: 0 zeros, 1 border, 2 reflection (align_corners flag selects the
+ * reflection bounds and matches grid_sample's unnormalisation: coordinates are unnormalised by the caller). */
+int b200_resample_affine(const void* src, int src_dtype, int C, int Di, int Hi, int Wi, void* dst, int dst_dtype,
+                         int Do, int Ho, int Wo, const double* mat3x4, int interp, int pad, int align_corners,
+                         void* stream);
+
+/* zero-padded separable 3-D filter (GaussianFilter, monai/networks/layers/simplelayers.py:170-249, 542-595):
+ * taps_* are float32 device arrays of odd length n_*; src/dst [C,D,H,W]; tmp is a float32 scratch buffer of
+ * 2*C*D*H*W elements (the two intermediate passes stay fp32). */
+int b200_separable_filter3d(const void* src, int dtype, int C, int D, int H, int W, const float* taps_d, int n_d,
+                            const float* taps_h, int n_h, const float* taps_w, int n_w, float* tmp, void* dst,
+                            void* stream);
+
+/* ---- tensor-core path (tcgen05 / TMEM / TMA), channel-blocked fp16 activations -------------------------- */
+/* Activation layout "NC8": [N][C/8][D][H][W][8] float16 (C % 8 == 0).  */
+
+/* NCDHW (f16/f32) <-> NC8 (f16) repack; c_off/Ctot address a channel slice of a concat buffer. */
+int b200_pack_nc8(const void* x, int dtype, int N, int C, long long S, void* y, int Ctot, int c_off, void* stream);
+int b200_unpack_nc8(const void* x, int Ctot, int c_off, int N, int C, long long S, void* y, int dtype, void* stream);
+
+/* bytes needed for the packed weight image of b200_conv3x3x3_tc (depends on Cin, Cout only). */
+long long b200_conv3x3x3_tc_weight_bytes(int Cin, int Cout);
+/* pack Conv3d weight [Cout,Cin,3,3,3] float32 (device) into the UMMA B-operand image (device, fp16). */
+int b200_conv3x3x3_tc_pack_weight(const float* w, int Cin, int Cout, void* packed, void* stream);
+
+typedef struct b200_conv_tc_desc {
+  int N, Cin, Cout, D, H, W;
+  int in_ctot, in_coff;     /* x is channels [in_coff, in_coff+Cin) of an NC8 buffer with in_ctot channels */
+  int out_ctot, out_coff;   /* y likewise */
+} b200_conv_tc_desc;
+
+/* 3x3x3, stride 1, zero padding 1 implicit-GEMM convolution on tcgen05 tensor cores: halo tile staged once
+ * into shared memory by TMA, 27 taps issued as shifted UMMA shared-memory descriptors, fp32 accumulators in
+ * TMEM.  stats (optional) receives per-(n,cout) {sum, sumsq} of the fp32 results (atomically accumulated:
+ * zero it first) so InstanceNorm needs no extra pass.  replaces the Conv3d inside UnetResBlock
+ * (monai/networks/blocks/dynunet_block.py:25-111) for SwinUNETR / DynUNet-style blocks. */
+int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
+                      void* y, float* stats, void* stream);
+
+/* NC8 variant of b200_norm_act: y = act(instnorm(x) [+ instnorm?(res)]); act: 0 none, 1 leaky-relu(slope), 3 relu.
+ * x / res / y are channel slices [coff, coff+C) of NC8 buffers with ctot channels. */
+int b200_norm_act_nc8(const void* x, int x_ctot, int x_coff, int N, int C, long long S, const float* stats, float eps,
+                      const void* res, int res_ctot, int res_coff, const float* res_stats, int act, float slope,
+                      void* y, int y_ctot, int y_coff, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONAI_B200_H_ */

@@ -1,0 +1,220 @@
+// Direct 3-D convolution / transposed convolution on CUDA cores, fp32 accumulation.
+//
+// This is the exact-parity path: it serves fp32 models (config C1, BasicUNet fp32) and the layers whose
+// channel counts cannot feed a tensor-core tile (Cin = 1 stems, Cout = 2 heads, stride-2 UNet layers).
+// Semantics follow nn.Conv3d / nn.ConvTranspose3d as instantiated by
+// monai/networks/blocks/convolutions.py:131-152 (padding from same_padding, layers/convutils.py:22-43,
+// output_padding = stride - 1, convutils.py:46-53): zero padding, dilation 1, groups 1.
+#include "common.cuh"
+#include "../../include/monai_b200.h"
+
+namespace b200 {
+
+struct ConvP {
+  b200_conv_desc d;
+  const void* x; const float* w; const float* bias; void* y;
+  int ntaps;
+  int cls;          // number of parity classes (transposed: sd*sh*sw, else 1)
+  int Dc, Hc, Wc;   // coarse output extent per parity class
+};
+
+constexpr int kCiT = 8;
+
+// Each thread owns one output voxel and CO_T output channels.  Weights for (CO_T couts x kCiT cins x taps)
+// are staged in shared memory as [tap][ci][co] so the inner product reads them as broadcast vectors.
+template <typename TI, typename TO, int CO_T>
+__global__ void __launch_bounds__(128) conv3d_direct_kernel(ConvP p) {
+  extern __shared__ float s_wt[];  // [ntaps][kCiT][CO_T]
+  const b200_conv_desc& d = p.d;
+  const int co_blocks = (d.Cout + CO_T - 1) / CO_T;
+  const int cob = blockIdx.y % co_blocks;
+  const int cls = blockIdx.y / co_blocks;
+  const int n = blockIdx.z;
+  const int co0 = cob * CO_T;
+  // parity class offsets (transposed conv only; 0 otherwise)
+  int pz = 0, py = 0, px = 0;
+  if (d.transposed) { px = cls % d.sw; py = (cls / d.sw) % d.sh; pz = cls / (d.sw * d.sh); }
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ncoarse = (long long)p.Dc * p.Hc * p.Wc;
+  const bool active = t < ncoarse;
+  int oz = 0, oy = 0, ox = 0;
+  if (active) {
+    const int cx = (int)(t % p.Wc), cy = (int)((t / p.Wc) % p.Hc), cz = (int)(t / ((long long)p.Wc * p.Hc));
+    if (d.transposed) { ox = cx * d.sw + px; oy = cy * d.sh + py; oz = cz * d.sd + pz; }
+    else { ox = cx; oy = cy; oz = cz; }
+  }
+  const bool inb = active && oz < d.Do && oy < d.Ho && ox < d.Wo;
+
+  float acc[CO_T];
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) acc[c] = 0.f;
+
+  const long long in_cs = (long long)d.Di * d.Hi * d.Wi;
+  const TI* xin = (const TI*)p.x + (long long)n * d.in_stride_n;
+  const int khw = d.kh * d.kw;
+
+  for (int ci0 = 0; ci0 < d.Cin; ci0 += kCiT) {
+    const int cin = min(kCiT, d.Cin - ci0);
+    __syncthreads();
+    // stage weights
+    for (int i = threadIdx.x; i < p.ntaps * kCiT * CO_T; i += blockDim.x) {
+      const int co = i % CO_T, ci = (i / CO_T) % kCiT, tap = i / (CO_T * kCiT);
+      float v = 0.f;
+      if (ci < cin && co0 + co < d.Cout) {
+        const long long widx = d.transposed
+            ? ((long long)(ci0 + ci) * d.Cout + (co0 + co)) * p.ntaps + tap
+            : ((long long)(co0 + co) * d.Cin + (ci0 + ci)) * p.ntaps + tap;
+        v = p.w[widx];
+      }
+      s_wt[i] = v;
+    }
+    __syncthreads();
+    if (!inb) continue;
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+      const int kz = tap / khw, ky = (tap / d.kw) % d.kh, kx = tap % d.kw;
+      int iz, iy, ix;
+      if (d.transposed) {
+        const int tz = oz + d.pd - kz, ty = oy + d.ph - ky, tx = ox + d.pw - kx;
+        if (tz < 0 || ty < 0 || tx < 0) continue;
+        if (tz % d.sd || ty % d.sh || tx % d.sw) continue;  // uniform across the block (parity classes)
+        iz = tz / d.sd; iy = ty / d.sh; ix = tx / d.sw;
+      } else {
+        iz = oz * d.sd - d.pd + kz; iy = oy * d.sh - d.ph + ky; ix = ox * d.sw - d.pw + kx;
+      }
+      if (iz < 0 || iz >= d.Di || iy < 0 || iy >= d.Hi || ix < 0 || ix >= d.Wi) continue;
+      const TI* xp = xin + (long long)ci0 * in_cs + ((long long)iz * d.Hi + iy) * d.Wi + ix;
+      const float* wp = s_wt + tap * kCiT * CO_T;
+#pragma unroll 4
+      for (int ci = 0; ci < cin; ++ci) {
+        const float xv = io<TI>::ld(xp + (long long)ci * in_cs);
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c) acc[c] = fmaf(xv, wp[ci * CO_T + c], acc[c]);
+      }
+    }
+  }
+  if (!inb) return;
+  const long long out_cs = (long long)d.Do * d.Ho * d.Wo;
+  TO* yo = (TO*)p.y + (long long)n * d.out_stride_n + ((long long)oz * d.Ho + oy) * d.Wo + ox;
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c)
+    if (co0 + c < d.Cout) io<TO>::st(yo + (long long)(co0 + c) * out_cs, acc[c] + (p.bias ? p.bias[co0 + c] : 0.f));
+}
+
+template <typename T>
+__global__ void maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int NC, int D, int H, int W) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)NC * Do * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho), oz = (int)((i / ((long long)Wo * Ho)) % Do);
+    const long long nc = i / ((long long)Wo * Ho * Do);
+    const T* p = x + ((nc * D + 2 * oz) * H + 2 * oy) * (long long)W + 2 * ox;
+    float m = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) m = fmaxf(m, io<T>::ld(p + ((long long)a * H + b) * W + c));
+    io<T>::st(y + i, m);
+  }
+}
+
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int C, int Di, int Hi, int Wi,
+                                     int Ctot, int c_off, int Do, int Ho, int Wo) {
+  const long long total = (long long)N * C * Do * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho), oz = (int)((i / ((long long)Wo * Ho)) % Do);
+    const int c = (int)((i / ((long long)Wo * Ho * Do)) % C);
+    const int n = (int)(i / ((long long)Wo * Ho * Do * C));
+    const int iz = min(oz, Di - 1), iy = min(oy, Hi - 1), ix = min(ox, Wi - 1);
+    const T v = x[((((long long)n * C + c) * Di + iz) * Hi + iy) * Wi + ix];
+    y[((((long long)n * Ctot + c_off + c) * Do + oz) * Ho + oy) * Wo + ox] = v;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+template <int CO_T>
+static int launch_conv(const ConvP& p, cudaStream_t st) {
+  const b200_conv_desc& d = p.d;
+  const long long ncoarse = (long long)p.Dc * p.Hc * p.Wc;
+  const int co_blocks = (d.Cout + CO_T - 1) / CO_T;
+  dim3 block(128), grid(ceil_div(ncoarse, 128), co_blocks * p.cls, d.N);
+  B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d_direct: grid too large");
+  const size_t smem = (size_t)p.ntaps * kCiT * CO_T * sizeof(float);
+  B200_REQUIRE(smem <= 48 * 1024, "conv3d_direct: kernel volume too large (%d taps)", p.ntaps);
+#define LC(TI, TO) conv3d_direct_kernel<TI, TO, CO_T><<<grid, block, smem, st>>>(p)
+  if (d.in_dtype == B200_DT_F16 && d.out_dtype == B200_DT_F16) LC(__half, __half);
+  else if (d.in_dtype == B200_DT_F16 && d.out_dtype == B200_DT_F32) LC(__half, float);
+  else if (d.in_dtype == B200_DT_F32 && d.out_dtype == B200_DT_F16) LC(float, __half);
+  else if (d.in_dtype == B200_DT_F32 && d.out_dtype == B200_DT_F32) LC(float, float);
+  else return set_err(B200_ERR_INVALID, "conv3d_direct: bad dtype");
+#undef LC
+  B200_LAUNCH_CHECK("conv3d_direct_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_conv3d_direct(const b200_conv_desc* desc, const void* x, const float* weight, const float* bias,
+                                  void* y, void* stream) {
+  B200_REQUIRE(desc && x && weight && y, "conv3d_direct: null pointer");
+  const b200_conv_desc& d = *desc;
+  B200_REQUIRE(d.N > 0 && d.Cin > 0 && d.Cout > 0, "conv3d_direct: empty problem");
+  B200_REQUIRE(d.sd > 0 && d.sh > 0 && d.sw > 0 && d.kd > 0 && d.kh > 0 && d.kw > 0, "conv3d_direct: bad kernel/stride");
+  // shape consistency (same formulas as torch)
+  if (!d.transposed) {
+    B200_REQUIRE(d.Do == (d.Di + 2 * d.pd - d.kd) / d.sd + 1 && d.Ho == (d.Hi + 2 * d.ph - d.kh) / d.sh + 1 &&
+                 d.Wo == (d.Wi + 2 * d.pw - d.kw) / d.sw + 1, "conv3d_direct: output shape does not match conv arithmetic");
+  } else {
+    const int lo_d = (d.Di - 1) * d.sd - 2 * d.pd + d.kd, lo_h = (d.Hi - 1) * d.sh - 2 * d.ph + d.kh,
+              lo_w = (d.Wi - 1) * d.sw - 2 * d.pw + d.kw;
+    B200_REQUIRE(d.Do >= lo_d && d.Do < lo_d + d.sd && d.Ho >= lo_h && d.Ho < lo_h + d.sh && d.Wo >= lo_w && d.Wo < lo_w + d.sw,
+                 "conv3d_direct: output shape does not match transposed-conv arithmetic");
+  }
+  ConvP p;
+  p.d = d; p.x = x; p.w = weight; p.bias = bias; p.y = y;
+  p.ntaps = d.kd * d.kh * d.kw;
+  if (d.transposed) {
+    p.cls = d.sd * d.sh * d.sw;
+    p.Dc = ceil_div(d.Do, d.sd); p.Hc = ceil_div(d.Ho, d.sh); p.Wc = ceil_div(d.Wo, d.sw);
+  } else {
+    p.cls = 1; p.Dc = d.Do; p.Hc = d.Ho; p.Wc = d.Wo;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d.Cout <= 2) return launch_conv<2>(p, st);
+  if (d.Cout <= 4) return launch_conv<4>(p, st);
+  if (d.Cout <= 8 || d.Cout % 16) return launch_conv<8>(p, st);
+  return launch_conv<16>(p, st);
+}
+
+extern "C" int b200_maxpool3d_2(const void* x, int dtype, int NC, int D, int H, int W, void* y, void* stream) {
+  B200_REQUIRE(x && y, "maxpool3d_2: null pointer");
+  const long long total = (long long)NC * (D / 2) * (H / 2) * (W / 2);
+  if (total == 0) return B200_OK;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_DT_F16) maxpool2_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, (__half*)y, NC, D, H, W);
+  else if (dtype == B200_DT_F32) maxpool2_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, NC, D, H, W);
+  else return set_err(B200_ERR_INVALID, "maxpool3d_2: bad dtype");
+  B200_LAUNCH_CHECK("maxpool2_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_copy_channels(const void* x, int dtype, int N, int C, int Di, int Hi, int Wi, void* y, int Ctot,
+                                  int c_off, int Do, int Ho, int Wo, void* stream) {
+  B200_REQUIRE(x && y, "copy_channels: null pointer");
+  B200_REQUIRE(c_off >= 0 && c_off + C <= Ctot, "copy_channels: channel slice outside the destination");
+  const long long total = (long long)N * C * Do * Ho * Wo;
+  if (total == 0) return B200_OK;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_DT_F16)
+    copy_channels_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, (__half*)y, N, C, Di, Hi, Wi, Ctot, c_off, Do, Ho, Wo);
+  else if (dtype == B200_DT_F32)
+    copy_channels_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, N, C, Di, Hi, Wi, Ctot, c_off, Do, Ho, Wo);
+  else return set_err(B200_ERR_INVALID, "copy_channels: bad dtype");
+  B200_LAUNCH_CHECK("copy_channels_kernel");
+  return B200_OK;
+}

@@ -1,0 +1,479 @@
+// 3x3x3 stride-1 implicit-GEMM convolution on tcgen05 tensor cores.
+//
+// Replaces the nn.Conv3d inside UnetResBlock / Convolution (monai/networks/blocks/dynunet_block.py:25-111,
+// monai/networks/blocks/convolutions.py:131-152) for kernel 3, stride 1, zero padding 1.
+//
+// Data layout in HBM ("NC8"): activations are fp16 [N][C/8][D][H][W][8]: eight channels of one voxel are 16
+// contiguous bytes and voxels run along W.  A shared-memory image of a (D,H,W) box of one 8-channel chunk is
+// then exactly a column of UMMA "core matrices" (8 rows x 16 B) for the K-major / no-swizzle operand layout:
+//   rows = 8 consecutive voxels along W, K = 8 channels.
+//
+// GEMM view: M = 128 output voxels (one 16(H) x 8(W) patch of one D-plane), N = NT output channels, K = 27*Cin.
+// Per K-slice of 16 input channels the CTA stages ONE halo tile (BD+2) x 18 x 10 voxels with a single 5-D TMA
+// box load (out-of-bounds => zero fill == the convolution's zero padding) and issues the 27 taps as 27 UMMA
+// instructions whose A descriptors merely start at a shifted voxel of that tile (start += ((kd*18+kh)*10+kw)*16 B,
+// SBO = 10*16 B between the 16 row groups, LBO = chunk stride).  Weights are pre-packed into the exact B-operand
+// image and arrive by 1-D bulk copies.  fp32 accumulators live in TMEM (BD planes x NT columns); the epilogue
+// reads them back with tcgen05.ld, adds bias, reduces InstanceNorm partial sums and stores fp16 NC8.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "../../include/monai_b200.h"
+#include <mutex>
+
+namespace b200 {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// NC8 pack / unpack
+// ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pack_nc8_kernel(const T* __restrict__ x, __half* __restrict__ y, int C, long long S,
+                                                       int Ctot, int c_off) {
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  const T* xs = x + ((long long)n * C + chunk * 8) * S;
+  __half* yd = y + (((long long)n * (Ctot / 8) + c_off / 8 + chunk) * S) * 8;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __float2half_rn(io<T>::ld(xs + (long long)j * S + s));
+    *reinterpret_cast<uint4*>(yd + s * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_nc8_kernel(const __half* __restrict__ x, T* __restrict__ y, int C, long long S,
+                                                         int Ctot, int c_off) {
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  const __half* xs = x + (((long long)n * (Ctot / 8) + c_off / 8 + chunk) * S) * 8;
+  T* yd = y + ((long long)n * C + chunk * 8) * S;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+    __align__(16) __half v[8];
+    *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(xs + s * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) io<T>::st(yd + (long long)j * S + s, __half2float(v[j]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// weight packing: Conv3d weight [Cout][Cin][27] fp32 -> [nt][kc][kd][tap9][khalf][NT/8][8 cout][8 k] fp16
+// ----------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int conv_tc_nt(int Cout) {
+  if (Cout <= 128) return Cout;
+  for (int nt = 128; nt >= 16; nt -= 16)
+    if (Cout % nt == 0) return nt;
+  return 16;
+}
+
+__global__ void conv_tc_pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cin, int Cout, int NT) {
+  const long long total = (long long)Cout * Cin * 27;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int kk = (int)(r % 8); r /= 8;
+    const int row = (int)(r % 8); r /= 8;
+    const int g = (int)(r % (NT / 8)); r /= (NT / 8);
+    const int khalf = (int)(r % 2); r /= 2;
+    const int t9 = (int)(r % 9); r /= 9;
+    const int kd = (int)(r % 3); r /= 3;
+    const int kc = (int)(r % (Cin / 16)); r /= (Cin / 16);
+    const int nt = (int)r;
+    const int cout = nt * NT + g * 8 + row;
+    const int cin = kc * 16 + khalf * 8 + kk;
+    const int tap = kd * 9 + t9;
+    out[i] = __float2half_rn(w[((long long)cout * Cin + cin) * 27 + tap]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// the convolution kernel
+// ----------------------------------------------------------------------------------------------------------
+constexpr int kTH = 16, kTW = 8;                 // output patch per D-plane: 16 (H) x 8 (W) = 128 GEMM rows
+constexpr int kHH = kTH + 2, kHW = kTW + 2;      // halo patch
+constexpr int kSA = 2, kSB = 3;                  // pipeline depths (A halo tiles, B weight slabs)
+
+template <int NT, int BD>
+struct ConvTcCfg {
+  static constexpr int kPlanes = BD + 2;
+  static constexpr int kChunkBytes = kPlanes * kHH * kHW * 16;   // one 8-channel chunk of the halo tile
+  static constexpr int kABytes = 2 * kChunkBytes;                // 16 input channels
+  static constexpr int kBTapBytes = NT * 32;                     // one tap: NT x 16 fp16
+  static constexpr int kBBytes = 9 * kBTapBytes;                 // one kd slab
+  static constexpr int kTmemCols = (BD * NT <= 32) ? 32 : (BD * NT <= 64) ? 64 : (BD * NT <= 128) ? 128 : (BD * NT <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + 256 /*barriers*/ + 2 * NT * 4 /*stats*/ + 128 /*align slack*/;
+  static_assert(BD * NT <= 512, "accumulators exceed TMEM");
+  static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "invalid UMMA N");
+};
+
+struct ConvTcParams {
+  b200_conv_tc_desc d;
+  const __half* w;      // packed
+  const float* bias;
+  __half* y;
+  float* stats;
+  int tiles_w, tiles_h, tiles_d;
+};
+
+template <int NT, int BD>
+__global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
+  using Cfg = ConvTcCfg<NT, BD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kSA * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSB * Cfg::kBBytes);
+  uint64_t* full_a = bars;            // [kSA]
+  uint64_t* empty_a = bars + kSA;     // [kSA]
+  uint64_t* full_b = bars + 2 * kSA;  // [kSB]
+  uint64_t* empty_b = full_b + kSB;   // [kSB]
+  uint64_t* acc_full = empty_b + kSB; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* s_stats = reinterpret_cast<float*>(bars + 32);  // [2*NT]
+
+  const b200_conv_tc_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th = tile % p.tiles_h; tile /= p.tiles_h;
+  const int td = tile;
+  const int w0 = tw * kTW, h0 = th * kTH, d0 = td * BD;
+  const int nt = blockIdx.y, n = blockIdx.z;
+  const int num_kc = d.Cin / 16;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < kSB; ++i) { tc::mbar_init(&full_b[i], 1); tc::mbar_init(&empty_b[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+  if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmap);
+      const __half* wbase = p.w + (long long)nt * num_kc * 3 * (Cfg::kBBytes / 2);
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        tc::mbar_wait(&empty_a[sa], pa ^ 1);
+        tc::mbar_arrive_expect_tx(&full_a[sa], Cfg::kABytes);
+        tc::tma_load_5d(smem_a + sa * Cfg::kABytes, &tmap, &full_a[sa], (w0 - 1) * 8, h0 - 1, d0 - 1,
+                        (d.in_coff + kc * 16) / 8, n);
+        if (++sa == kSA) { sa = 0; pa ^= 1; }
+        for (int kd = 0; kd < 3; ++kd) {
+          tc::mbar_wait(&empty_b[sb], pb ^ 1);
+          tc::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBBytes);
+          tc::bulk_load(smem_b + sb * Cfg::kBBytes, wbase + ((long long)kc * 3 + kd) * (Cfg::kBBytes / 2), Cfg::kBBytes,
+                        &full_b[sb]);
+          if (++sb == kSB) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_f16(128, NT);
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        tc::mbar_wait(&full_a[sa], pa);
+        const uint32_t a_base = tc::smem_u32(smem_a + sa * Cfg::kABytes);
+        for (int kd = 0; kd < 3; ++kd) {
+          tc::mbar_wait(&full_b[sb], pb);
+          tc::fence_after_sync();
+          const uint32_t b_base = tc::smem_u32(smem_b + sb * Cfg::kBBytes);
+#pragma unroll
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int kh = t9 / 3, kw = t9 % 3;
+            const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_base + t9 * Cfg::kBTapBytes, NT * 16, 128);
+#pragma unroll
+            for (int sub = 0; sub < BD; ++sub) {
+              const uint32_t a_addr = a_base + (((sub + kd) * kHH + kh) * kHW + kw) * 16;
+              const uint64_t adesc = tc::make_desc_kmajor_noswz(a_addr, Cfg::kChunkBytes, kHW * 16);
+              tc::mma_f16_ss(tmem_base + sub * NT, adesc, bdesc, idesc, (kc | kd | t9) != 0 ? 1u : 0u);
+            }
+          }
+          tc::mma_commit(&empty_b[sb]);
+          if (++sb == kSB) { sb = 0; pb ^= 1; }
+        }
+        tc::mma_commit(&empty_a[sa]);
+        if (++sa == kSA) { sa = 0; pa ^= 1; }
+      }
+      tc::mma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int h = h0 + (row >> 3), w = w0 + (row & 7);
+    const bool hw_ok = h < d.H && w < d.W;
+    tc::mbar_wait(acc_full, 0);
+    tc::fence_after_sync();
+    const int co0 = nt * NT;
+    const long long S = (long long)d.D * d.H * d.W;
+    __half* ybase = p.y + (((long long)n * (d.out_ctot / 8) + (d.out_coff + co0) / 8) * S) * 8;
+#pragma unroll 1
+    for (int cc = 0; cc < NT / 8; ++cc) {
+      float bsum[8], bsq[8], bias8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = p.bias ? p.bias[co0 + cc * 8 + j] : 0.f; }
+#pragma unroll
+      for (int sub = 0; sub < BD; ++sub) {
+        uint32_t v[8];
+        tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + sub * NT + cc * 8, v);
+        tc::tmem_ld_wait();
+        const int dz = d0 + sub;
+        const bool ok = hw_ok && dz < d.D;
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f = __uint_as_float(v[j]) + bias8[j];
+          hv[j] = __float2half_rn(f);
+          if (ok) { bsum[j] += f; bsq[j] = fmaf(f, f, bsq[j]); }
+        }
+        if (ok) *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * d.H + h) * d.W + w) * 8) =
+                    *reinterpret_cast<const uint4*>(hv);
+      }
+      if (p.stats) {
+        // transpose-reduce 8 columns over the 32 lanes: 4+2+1 exchange steps, then 2 plain steps
+        float a4[4], b4[4];
+        const bool hi16 = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float send = hi16 ? bsum[j] : bsum[j + 4], keep = hi16 ? bsum[j + 4] : bsum[j];
+          a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          const float send2 = hi16 ? bsq[j] : bsq[j + 4], keep2 = hi16 ? bsq[j + 4] : bsq[j];
+          b4[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
+        }
+        float a2[2], b2[2];
+        const bool hi8 = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float send = hi8 ? a4[j] : a4[j + 2], keep = hi8 ? a4[j + 2] : a4[j];
+          a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          const float send2 = hi8 ? b4[j] : b4[j + 2], keep2 = hi8 ? b4[j + 2] : b4[j];
+          b2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
+        }
+        const bool hi4 = lane & 4;
+        float a1 = (hi4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? a2[0] : a2[1], 4);
+        float b1 = (hi4 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? b2[0] : b2[1], 4);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 2); b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+        if ((lane & 3) == 0) {
+          const int col = cc * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+          atomicAdd(&s_stats[2 * col], a1);
+          atomicAdd(&s_stats[2 * col + 1], b1);
+        }
+      }
+    }
+    tc::fence_before_sync();
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;
+      for (int i = t; i < 2 * NT; i += 128) atomicAdd(&p.stats[((long long)n * d.Cout + co0) * 2 + i], s_stats[i]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// NC8 normalise + activation (same math as norm_act_kernel, 8 channels per 16-byte vector)
+struct NormActNc8P {
+  const __half* x; __half* y; const __half* res;
+  int C, x_ctot, x_coff, y_ctot, y_coff, r_ctot, r_coff;
+  long long S;
+  const float* stats; const float* res_stats; float eps;
+  int act; float slope;
+};
+
+__global__ void __launch_bounds__(256) norm_act_nc8_kernel(NormActNc8P p) {
+  const int chunk = blockIdx.y, n = blockIdx.z;
+  float sc[8], sh[8], rsc[8], rsh[8];
+  const float invS = 1.f / (float)p.S;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = chunk * 8 + j;
+    sc[j] = 1.f; sh[j] = 0.f; rsc[j] = 1.f; rsh[j] = 0.f;
+    if (p.stats) {
+      const float s = p.stats[2 * (n * p.C + c)], q = p.stats[2 * (n * p.C + c) + 1];
+      const float mean = s * invS, var = fmaxf(q * invS - mean * mean, 0.f), rstd = 1.f / sqrtf(var + p.eps);
+      sc[j] = rstd; sh[j] = -mean * rstd;
+    }
+    if (p.res_stats) {
+      const float s = p.res_stats[2 * (n * p.C + c)], q = p.res_stats[2 * (n * p.C + c) + 1];
+      const float mean = s * invS, var = fmaxf(q * invS - mean * mean, 0.f), rstd = 1.f / sqrtf(var + p.eps);
+      rsc[j] = rstd; rsh[j] = -mean * rstd;
+    }
+  }
+  const __half* x = p.x + (((long long)n * (p.x_ctot / 8) + p.x_coff / 8 + chunk) * p.S) * 8;
+  __half* y = p.y + (((long long)n * (p.y_ctot / 8) + p.y_coff / 8 + chunk) * p.S) * 8;
+  const __half* r = p.res ? p.res + (((long long)n * (p.r_ctot / 8) + p.r_coff / 8 + chunk) * p.S) * 8 : nullptr;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < p.S; s += (long long)gridDim.x * blockDim.x) {
+    __align__(16) __half v[8], rv[8];
+    *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(x + s * 8);
+    if (r) *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(r + s * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = fmaf(__half2float(v[j]), sc[j], sh[j]);
+      if (r) f += fmaf(__half2float(rv[j]), rsc[j], rsh[j]);
+      if (p.act == 1) f = f >= 0.f ? f : f * p.slope;
+      else if (p.act == 3) f = fmaxf(f, 0.f);
+      v[j] = __float2half_rn(f);
+    }
+    *reinterpret_cast<uint4*>(y + s * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_pack_nc8(const void* x, int dtype, int N, int C, long long S, void* y, int Ctot, int c_off, void* stream) {
+  B200_REQUIRE(x && y, "pack_nc8: null pointer");
+  B200_REQUIRE(C % 8 == 0 && Ctot % 8 == 0 && c_off % 8 == 0 && c_off + C <= Ctot, "pack_nc8: channel counts must be multiples of 8");
+  if ((long long)N * C * S == 0) return B200_OK;
+  dim3 grid((unsigned)std::min<long long>((S + 255) / 256, 1024), C / 8, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_DT_F16) pack_nc8_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, C, S, Ctot, c_off);
+  else if (dtype == B200_DT_F32) pack_nc8_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (__half*)y, C, S, Ctot, c_off);
+  else return set_err(B200_ERR_INVALID, "pack_nc8: bad dtype");
+  B200_LAUNCH_CHECK("pack_nc8_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_unpack_nc8(const void* x, int Ctot, int c_off, int N, int C, long long S, void* y, int dtype, void* stream) {
+  B200_REQUIRE(x && y, "unpack_nc8: null pointer");
+  B200_REQUIRE(C % 8 == 0 && Ctot % 8 == 0 && c_off % 8 == 0 && c_off + C <= Ctot, "unpack_nc8: channel counts must be multiples of 8");
+  if ((long long)N * C * S == 0) return B200_OK;
+  dim3 grid((unsigned)std::min<long long>((S + 255) / 256, 1024), C / 8, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_DT_F16) unpack_nc8_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, C, S, Ctot, c_off);
+  else if (dtype == B200_DT_F32) unpack_nc8_kernel<float><<<grid, 256, 0, st>>>((const __half*)x, (float*)y, C, S, Ctot, c_off);
+  else return set_err(B200_ERR_INVALID, "unpack_nc8: bad dtype");
+  B200_LAUNCH_CHECK("unpack_nc8_kernel");
+  return B200_OK;
+}
+
+extern "C" long long b200_conv3x3x3_tc_weight_bytes(int Cin, int Cout) {
+  if (Cin <= 0 || Cout <= 0 || Cin % 16 || Cout % 16) return -1;
+  return (long long)Cin * Cout * 27 * 2;
+}
+
+extern "C" int b200_conv3x3x3_tc_pack_weight(const float* w, int Cin, int Cout, void* packed, void* stream) {
+  B200_REQUIRE(w && packed, "conv3x3x3_tc_pack_weight: null pointer");
+  B200_REQUIRE(Cin > 0 && Cout > 0 && Cin % 16 == 0 && Cout % 16 == 0, "conv3x3x3_tc: Cin and Cout must be multiples of 16 (got %d, %d)", Cin, Cout);
+  const long long total = (long long)Cin * Cout * 27;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
+  conv_tc_pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed, Cin, Cout, conv_tc_nt(Cout));
+  B200_LAUNCH_CHECK("conv_tc_pack_weight_kernel");
+  return B200_OK;
+}
+
+template <int NT, int BD>
+static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats,
+                          cudaStream_t st) {
+  using Cfg = ConvTcCfg<NT, BD>;
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_REQUIRE(enc != nullptr, "conv3x3x3_tc: cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap tmap;
+  const cuuint64_t S = (cuuint64_t)d.D * d.H * d.W;
+  cuuint64_t gdim[5] = {(cuuint64_t)d.W * 8, (cuuint64_t)d.H, (cuuint64_t)d.D, (cuuint64_t)(d.in_ctot / 8), (cuuint64_t)d.N};
+  cuuint64_t gstr[4] = {(cuuint64_t)d.W * 16, (cuuint64_t)d.H * d.W * 16, S * 16, S * 16 * (cuuint64_t)(d.in_ctot / 8)};
+  cuuint32_t box[5] = {(cuuint32_t)kHW * 8, (cuuint32_t)kHH, (cuuint32_t)(BD + 2), 2, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "conv3x3x3_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  ConvTcParams p;
+  p.d = d; p.w = (const __half*)w; p.bias = bias; p.y = (__half*)y; p.stats = stats;
+  p.tiles_w = ceil_div(d.W, kTW); p.tiles_h = ceil_div(d.H, kTH); p.tiles_d = ceil_div(d.D, BD);
+  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * p.tiles_d), d.Cout / NT, d.N);
+  B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3x3x3_tc: grid too large");
+  auto kern = conv3x3x3_tc_kernel<NT, BD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmap, p);
+  B200_LAUNCH_CHECK("conv3x3x3_tc_kernel");
+  return B200_OK;
+}
+
+template <int NT>
+static int dispatch_bd(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats,
+                       cudaStream_t st) {
+  // deeper CTA tiles amortise the halo and the weight slab; TMEM (BD*NT <= 512) and the plane count bound BD
+  if constexpr (NT * 4 <= 512) {
+    if (d.D % 4 == 0 || d.D >= 16) return launch_conv_tc<NT, 4>(d, x, w, bias, y, stats, st);
+  }
+  if constexpr (NT * 2 <= 512) {
+    if (d.D >= 2) return launch_conv_tc<NT, 2>(d, x, w, bias, y, stats, st);
+  }
+  return launch_conv_tc<NT, 1>(d, x, w, bias, y, stats, st);
+}
+
+extern "C" int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
+                                 void* y, float* stats, void* stream) {
+  B200_REQUIRE(desc && x && packed_w && y, "conv3x3x3_tc: null pointer");
+  const b200_conv_tc_desc& d = *desc;
+  B200_REQUIRE(d.N > 0 && d.D > 0 && d.H > 0 && d.W > 0, "conv3x3x3_tc: empty problem");
+  B200_REQUIRE(d.Cin > 0 && d.Cin % 16 == 0 && d.Cout > 0 && d.Cout % 16 == 0,
+               "conv3x3x3_tc: Cin and Cout must be multiples of 16 (got %d, %d)", d.Cin, d.Cout);
+  B200_REQUIRE(d.in_ctot % 8 == 0 && d.in_coff % 8 == 0 && d.in_coff + d.Cin <= d.in_ctot, "conv3x3x3_tc: bad input channel slice");
+  B200_REQUIRE(d.out_ctot % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + d.Cout <= d.out_ctot, "conv3x3x3_tc: bad output channel slice");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(packed_w) & 15) == 0, "conv3x3x3_tc: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (conv_tc_nt(d.Cout)) {
+    case 16: return dispatch_bd<16>(d, x, packed_w, bias, y, stats, st);
+    case 32: return dispatch_bd<32>(d, x, packed_w, bias, y, stats, st);
+    case 48: return dispatch_bd<48>(d, x, packed_w, bias, y, stats, st);
+    case 64: return dispatch_bd<64>(d, x, packed_w, bias, y, stats, st);
+    case 80: return dispatch_bd<80>(d, x, packed_w, bias, y, stats, st);
+    case 96: return dispatch_bd<96>(d, x, packed_w, bias, y, stats, st);
+    case 112: return dispatch_bd<112>(d, x, packed_w, bias, y, stats, st);
+    case 128: return dispatch_bd<128>(d, x, packed_w, bias, y, stats, st);
+    default: return set_err(B200_ERR_UNSUPPORTED, "conv3x3x3_tc: unsupported Cout %d", d.Cout);
+  }
+}
+
+extern "C" int b200_norm_act_nc8(const void* x, int x_ctot, int x_coff, int N, int C, long long S, const float* stats,
+                                 float eps, const void* res, int res_ctot, int res_coff, const float* res_stats, int act,
+                                 float slope, void* y, int y_ctot, int y_coff, void* stream) {
+  B200_REQUIRE(x && y, "norm_act_nc8: null pointer");
+  B200_REQUIRE(C % 8 == 0 && x_ctot % 8 == 0 && x_coff % 8 == 0 && y_ctot % 8 == 0 && y_coff % 8 == 0, "norm_act_nc8: channels must be multiples of 8");
+  B200_REQUIRE(act == 0 || act == 1 || act == 3, "norm_act_nc8: activation must be none, leaky-relu or relu");
+  if ((long long)N * C * S == 0) return B200_OK;
+  NormActNc8P p;
+  p.x = (const __half*)x; p.y = (__half*)y; p.res = (const __half*)res; p.C = C;
+  p.x_ctot = x_ctot; p.x_coff = x_coff; p.y_ctot = y_ctot; p.y_coff = y_coff; p.r_ctot = res_ctot; p.r_coff = res_coff;
+  p.S = S; p.stats = stats; p.res_stats = res_stats; p.eps = eps; p.act = act; p.slope = slope;
+  long long want = (long long)num_sms() * 16 / ((long long)N * (C / 8)) + 1;
+  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(want, (S + 255) / 256)), C / 8, N);
+  norm_act_nc8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  B200_LAUNCH_CHECK("norm_act_nc8_kernel");
+  return B200_OK;
+}
