@@ -1,0 +1,305 @@
+"""Tensor-level wrappers around the C ABI (include/monai_b200.h).
+
+PyTorch only supplies device memory and the current stream here; every computation below is a hand-written
+sm_100a kernel reached through ctypes.  All functions require CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _t3(v) -> tuple[int, int, int]:
+    if isinstance(v, int):
+        return (v, v, v)
+    v = tuple(int(i) for i in v)
+    if len(v) != 3:
+        raise ValueError(f"expected 3 values, got {v}")
+    return v  # type: ignore[return-value]
+
+
+# ------------------------------------------------------------------------------------------- convolution (direct)
+def conv_out_shape(in_sp, k, s, p, transposed=False, output_padding=(0, 0, 0)):
+    if transposed:
+        return tuple((i - 1) * st - 2 * pd + kk + op for i, kk, st, pd, op in zip(in_sp, k, s, p, output_padding))
+    return tuple((i + 2 * pd - kk) // st + 1 for i, kk, st, pd in zip(in_sp, k, s, p))
+
+
+def conv3d_direct(
+    x: torch.Tensor,
+    weight: torch.Tensor,
+    bias: torch.Tensor | None = None,
+    stride=1,
+    padding=0,
+    transposed: bool = False,
+    output_padding=0,
+    out: torch.Tensor | None = None,
+    out_dtype: torch.dtype | None = None,
+) -> torch.Tensor:
+    """Conv3d / ConvTranspose3d (groups=1, dilation=1) with fp32 accumulation.  x: [N,Cin,D,H,W] contiguous per sample
+    (a channel slice of a larger buffer is allowed); `out` may be a channel slice of a concat buffer."""
+    L.require_cuda(x, weight)
+    lib = L.load()
+    s, p, op = _t3(stride), _t3(padding), _t3(output_padding)
+    N, Cin, Di, Hi, Wi = x.shape
+    k = tuple(weight.shape[2:])
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    wc = weight.shape[0] if transposed else weight.shape[1]
+    if wc != Cin:
+        raise ValueError(f"weight expects {wc} input channels, input has {Cin}")
+    Do, Ho, Wo = conv_out_shape((Di, Hi, Wi), k, s, p, transposed, op)
+    if out is None:
+        out = torch.empty((N, Cout, Do, Ho, Wo), device=x.device, dtype=out_dtype or x.dtype)
+    if tuple(out.shape) != (N, Cout, Do, Ho, Wo):
+        raise ValueError(f"out has shape {tuple(out.shape)}, expected {(N, Cout, Do, Ho, Wo)}")
+    for t, nm in ((x, "x"), (out, "out")):
+        if not t[0].is_contiguous():
+            raise ValueError(f"{nm} must be contiguous within each sample")
+    w32 = weight.detach().to(torch.float32).contiguous()
+    b32 = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    d = L.ConvDesc(
+        N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], int(transposed),
+        L.dt(x), L.dt(out), x.stride(0) if N > 1 else Cin * Di * Hi * Wi, out.stride(0) if N > 1 else Cout * Do * Ho * Wo,
+    )
+    L.check(lib.b200_conv3d_direct(C.byref(d), L.ptr(x), L.ptr(w32), L.ptr(b32), L.ptr(out), L.stream_ptr(x.device)), "conv3d_direct")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- norm / activation
+def instnorm_stats(x: torch.Tensor) -> torch.Tensor:
+    """Per-(n,c) {sum, sumsq} of x[N,C,*spatial] -> float32 [N*C, 2]."""
+    L.require_cuda(x)
+    N, Cc = x.shape[:2]
+    S = x[0, 0].numel()
+    stats = torch.empty((N * Cc, 2), device=x.device, dtype=torch.float32)
+    L.check(L.load().b200_instnorm_stats(L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), L.stream_ptr(x.device)), "instnorm_stats")
+    return stats
+
+
+def norm_act(
+    x: torch.Tensor,
+    stats: torch.Tensor | None = None,
+    eps: float = 1e-5,
+    gamma: torch.Tensor | None = None,
+    beta: torch.Tensor | None = None,
+    res: torch.Tensor | None = None,
+    res_stats: torch.Tensor | None = None,
+    act: int = L.ACT_NONE,
+    slope: float = 0.0,
+    slope_t: torch.Tensor | None = None,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    L.require_cuda(x)
+    N, Cc = x.shape[:2]
+    S = x[0, 0].numel()
+    if out is None:
+        out = torch.empty_like(x)
+    g = None if gamma is None else gamma.detach().float().contiguous()
+    b = None if beta is None else beta.detach().float().contiguous()
+    sl = None if slope_t is None else slope_t.detach().float().contiguous()
+    L.check(
+        L.load().b200_norm_act(
+            L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), eps, L.ptr(g), L.ptr(b), L.ptr(res),
+            (res.stride(0) if N > 1 else Cc * S) if res is not None else 0, L.ptr(res_stats), act, float(slope), L.ptr(sl),
+            0 if sl is None else sl.numel(), L.ptr(out), out.stride(0) if N > 1 else Cc * S, L.stream_ptr(x.device),
+        ),
+        "norm_act",
+    )
+    return out
+
+
+def maxpool3d_2(x: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(x)
+    N, Cc, D, H, W = x.shape
+    x = x.contiguous()
+    y = torch.empty((N, Cc, D // 2, H // 2, W // 2), device=x.device, dtype=x.dtype)
+    L.check(L.load().b200_maxpool3d_2(L.ptr(x), L.dt(x), N * Cc, D, H, W, L.ptr(y), L.stream_ptr(x.device)), "maxpool3d_2")
+    return y
+
+
+def copy_channels(x: torch.Tensor, dst: torch.Tensor, c_off: int) -> None:
+    """dst[:, c_off:c_off+C] = replicate_pad(x) (dst spatial >= x spatial, padding on the high side only)."""
+    L.require_cuda(x, dst)
+    x = x.contiguous()
+    N, Cc, Di, Hi, Wi = x.shape
+    _, Ct, Do, Ho, Wo = dst.shape
+    if not dst.is_contiguous():
+        raise ValueError("dst must be contiguous")
+    L.check(L.load().b200_copy_channels(L.ptr(x), L.dt(x), N, Cc, Di, Hi, Wi, L.ptr(dst), Ct, c_off, Do, Ho, Wo, L.stream_ptr(x.device)), "copy_channels")
+
+
+# ------------------------------------------------------------------------------------------------ sliding window
+def sw_gather(vol: torch.Tensor, win_tab: torch.Tensor, roi: Sequence[int], out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """vol [B,C,D,H,W] -> [n_win,C,*roi]; win_tab int32 device [n_win,4] = (batch, d0, h0, w0)."""
+    L.require_cuda(vol, win_tab)
+    vol = vol.contiguous()
+    B, Cc, D, H, W = vol.shape
+    n = win_tab.shape[0]
+    out = torch.empty((n, Cc, *roi), device=vol.device, dtype=out_dtype or vol.dtype)
+    L.check(L.load().b200_sw_gather(L.ptr(vol), L.dt(vol), L.ptr(out), L.dt(out), L.ptr(win_tab), n, Cc, D, H, W, roi[0], roi[1], roi[2], L.stream_ptr(vol.device)), "sw_gather")
+    return out
+
+
+def sw_blend(
+    mode: int,
+    preds: torch.Tensor | None,
+    win_begin: int,
+    win_end: int,
+    vol_shape: Sequence[int],
+    roi: Sequence[int],
+    starts: Sequence[torch.Tensor],
+    g: Sequence[torch.Tensor] | None,
+    clamp_min: float,
+    wmap: torch.Tensor | None,
+    out: torch.Tensor,
+    acc: torch.Tensor | None = None,
+    box: Sequence[int] = (0, 0, 0, 0),
+) -> None:
+    d = L.BlendDesc()
+    B, Cc, D, H, W = vol_shape
+    if preds is not None:
+        L.require_cuda(preds)
+        d.preds, d.pred_dtype = L.ptr(preds), L.dt(preds)
+        st = preds.stride()
+        for i in range(5):
+            d.pred_stride[i] = st[i]
+    d.win_begin, d.win_end = win_begin, win_end
+    d.B, d.C, d.D, d.H, d.W = B, Cc, D, H, W
+    d.rd, d.rh, d.rw = roi
+    d.starts_d, d.nd = L.ptr(starts[0]), starts[0].numel()
+    d.starts_h, d.nh = L.ptr(starts[1]), starts[1].numel()
+    d.starts_w, d.nw = L.ptr(starts[2]), starts[2].numel()
+    if g is not None:
+        d.gd, d.gh, d.gw = L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2])
+    d.clamp_min = clamp_min
+    d.wmap = L.ptr(wmap)
+    d.out, d.out_dtype = L.ptr(out), L.dt(out)
+    d.acc = L.ptr(acc)
+    for i in range(4):
+        d.box[i] = box[i]
+    L.check(L.load().b200_sw_blend(C.byref(d), mode, L.stream_ptr(out.device)), "sw_blend")
+
+
+# ---------------------------------------------------------------------------------------------------- transforms
+def resample_affine(
+    src: torch.Tensor, out_shape: Sequence[int], mat: "Sequence[float]", interp: int, pad: int, align_corners: bool,
+    out_dtype: torch.dtype = torch.float32,
+) -> torch.Tensor:
+    """src [C,D,H,W]; mat = 12 doubles (3x4 row-major) mapping output voxel index -> source voxel index."""
+    L.require_cuda(src)
+    src = src.contiguous()
+    Cc, Di, Hi, Wi = src.shape
+    dst = torch.empty((Cc, *out_shape), device=src.device, dtype=out_dtype)
+    m = (C.c_double * 12)(*[float(v) for v in mat])
+    L.check(L.load().b200_resample_affine(L.ptr(src), L.dt(src), Cc, Di, Hi, Wi, L.ptr(dst), L.dt(dst), out_shape[0], out_shape[1], out_shape[2], m, interp, pad, int(bool(align_corners)), L.stream_ptr(src.device)), "resample_affine")
+    return dst
+
+
+def separable_filter3d(src: torch.Tensor, taps: Sequence[torch.Tensor]) -> torch.Tensor:
+    """src [C,D,H,W]; taps = three float32 device vectors of odd length; zero padding."""
+    L.require_cuda(src)
+    src = src.contiguous()
+    Cc, D, H, W = src.shape
+    dst = torch.empty_like(src)
+    tmp = torch.empty((2, Cc, D, H, W), device=src.device, dtype=torch.float32)
+    t = [x.detach().to(device=src.device, dtype=torch.float32).contiguous() for x in taps]
+    L.check(L.load().b200_separable_filter3d(L.ptr(src), L.dt(src), Cc, D, H, W, L.ptr(t[0]), t[0].numel(), L.ptr(t[1]), t[1].numel(), L.ptr(t[2]), t[2].numel(), L.ptr(tmp), L.ptr(dst), L.stream_ptr(src.device)), "separable_filter3d")
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core path
+class NC8:
+    """fp16 activation buffer in the channel-blocked layout [N][C/8][D][H][W][8] used by the tcgen05 kernels."""
+
+    __slots__ = ("buf", "N", "C", "sp")
+
+    def __init__(self, N: int, C_: int, sp: Sequence[int], device, buf: torch.Tensor | None = None):
+        if C_ % 8:
+            raise ValueError("NC8 needs a channel count divisible by 8")
+        self.N, self.C, self.sp = N, C_, tuple(int(s) for s in sp)
+        self.buf = buf if buf is not None else torch.empty((N, C_ // 8, *self.sp, 8), device=device, dtype=torch.float16)
+
+    @property
+    def S(self) -> int:
+        return self.sp[0] * self.sp[1] * self.sp[2]
+
+
+def pack_nc8(x: torch.Tensor, dst: NC8 | None = None, c_off: int = 0) -> NC8:
+    L.require_cuda(x)
+    x = x.contiguous()
+    N, Cc = x.shape[:2]
+    if dst is None:
+        dst = NC8(N, Cc, x.shape[2:], x.device)
+    L.check(L.load().b200_pack_nc8(L.ptr(x), L.dt(x), N, Cc, dst.S, L.ptr(dst.buf), dst.C, c_off, L.stream_ptr(x.device)), "pack_nc8")
+    return dst
+
+
+def unpack_nc8(src: NC8, C_: int | None = None, c_off: int = 0, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    C_ = C_ or src.C
+    y = torch.empty((src.N, C_, *src.sp), device=src.buf.device, dtype=dtype)
+    L.check(L.load().b200_unpack_nc8(L.ptr(src.buf), src.C, c_off, src.N, C_, src.S, L.ptr(y), L.dt(y), L.stream_ptr(y.device)), "unpack_nc8")
+    return y
+
+
+def conv3x3x3_tc_pack_weight(weight: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(weight)
+    Cout, Cin = weight.shape[:2]
+    nbytes = L.load().b200_conv3x3x3_tc_weight_bytes(Cin, Cout)
+    if nbytes < 0:
+        raise ValueError(f"conv3x3x3_tc needs Cin, Cout multiples of 16, got {Cin}, {Cout}")
+    w32 = weight.detach().float().contiguous()
+    packed = torch.empty(nbytes // 2, device=weight.device, dtype=torch.float16)
+    L.check(L.load().b200_conv3x3x3_tc_pack_weight(L.ptr(w32), Cin, Cout, L.ptr(packed), L.stream_ptr(weight.device)), "conv3x3x3_tc_pack_weight")
+    return packed
+
+
+def conv3x3x3_tc(
+    x: NC8, packed_w: torch.Tensor, Cin: int, Cout: int, in_coff: int = 0, bias: torch.Tensor | None = None,
+    out: NC8 | None = None, out_coff: int = 0, want_stats: bool = False,
+) -> tuple[NC8, torch.Tensor | None]:
+    if out is None:
+        out = NC8(x.N, Cout, x.sp, x.buf.device)
+    stats = torch.zeros((x.N * Cout, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff)
+    L.check(L.load().b200_conv3x3x3_tc(C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.stream_ptr(x.buf.device)), "conv3x3x3_tc")
+    return out, stats
+
+
+def norm_act_nc8(
+    x: NC8, C_: int, stats: torch.Tensor | None, x_coff: int = 0, res: NC8 | None = None, res_coff: int = 0,
+    res_stats: torch.Tensor | None = None, act: int = L.ACT_NONE, slope: float = 0.0, out: NC8 | None = None,
+    out_coff: int = 0, eps: float = 1e-5,
+) -> NC8:
+    if out is None:
+        out = NC8(x.N, C_, x.sp, x.buf.device)
+    L.check(
+        L.load().b200_norm_act_nc8(
+            L.ptr(x.buf), x.C, x_coff, x.N, C_, x.S, L.ptr(stats), eps, L.ptr(res.buf) if res is not None else None,
+            res.C if res is not None else 0, res_coff, L.ptr(res_stats), act, float(slope), L.ptr(out.buf), out.C, out_coff,
+            L.stream_ptr(x.buf.device),
+        ),
+        "norm_act_nc8",
+    )
+    return out
+
+
+def cat_channels(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """torch.cat(tensors, dim=1) for [N,C_i,*spatial] tensors of one dtype, done by the channel-copy kernel."""
+    t0 = tensors[0]
+    N, sp = t0.shape[0], tuple(t0.shape[2:])
+    lift = 3 - len(sp)
+    sp3 = (1,) * lift + sp
+    ctot = sum(int(t.shape[1]) for t in tensors)
+    out = torch.empty((N, ctot, *sp3), device=t0.device, dtype=t0.dtype)
+    off = 0
+    for t in tensors:
+        if tuple(t.shape[2:]) != sp or t.dtype != t0.dtype:
+            raise ValueError("cat_channels needs equal spatial shapes and dtypes")
+        copy_channels(t.reshape(N, t.shape[1], *sp3), out, off)
+        off += int(t.shape[1])
+    return out.reshape(N, ctot, *sp)

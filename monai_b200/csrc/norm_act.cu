@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActP p) {
     const float rstd = 1.f / sqrtf(var + p.eps);
     const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
     scale = rstd * g; shift = b - mean * rstd * g;
+  } else {  // pre-folded per-channel affine (e.g. eval-mode BatchNorm)
+    scale = p.gamma ? p.gamma[c] : 1.f; shift = p.beta ? p.beta[c] : 0.f;
   }
   if (p.res_stats) {
     const float s = p.res_stats[2 * (n * p.C + c)], q = p.res_stats[2 * (n * p.C + c) + 1];

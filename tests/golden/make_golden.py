@@ -1,0 +1,153 @@
+"""Generate the golden fixtures in this directory from the REAL reference (Project-MONAI/MONAI at /root/reference).
+
+Run in the build container only (the reference does not exist on the GPU box):
+    PYTHONPATH=/root/reference python tests/golden/make_golden.py
+Everything is seeded; fixtures are small .npz files that are committed.
+"""
+from __future__ import annotations
+
+import itertools
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, "/root/reference")
+import monai  # noqa: E402
+from monai.data.utils import compute_importance_map, dense_patch_slices, get_valid_patch_size  # noqa: E402
+from monai.inferers import sliding_window_inference  # noqa: E402
+from monai.inferers.utils import _get_scan_interval  # noqa: E402
+from monai.networks.nets import BasicUNet, SwinUNETR, UNet  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def save(name, **arrays):
+    np.savez_compressed(os.path.join(HERE, name), **arrays)
+    print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrays.items() if not k.startswith("sd.")})
+
+
+def sd_arrays(net):
+    return {"sd." + k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+
+
+def planner():
+    cases = []
+    for image, roi, ov in [
+        ((64, 64, 64), (32, 32, 32), 0.25), ((256, 256, 256), (96, 96, 96), 0.5), ((512, 512, 1024), (96, 96, 96), 0.5),
+        ((33, 47, 21), (16, 16, 16), 0.6), ((20, 20, 20), (32, 16, 8), 0.0), ((50, 17, 9), (7, 17, 4), 0.9),
+        ((100, 100), (33, 44), (0.1, 0.7)), ((7,), (3,), 0.5), ((96, 96, 96), (96, 96, 96), 0.5),
+    ]:
+        image_p = tuple(max(i, r) for i, r in zip(image, roi))
+        ovt = ov if isinstance(ov, tuple) else (ov,) * len(image)
+        interval = _get_scan_interval(image_p, roi, len(image), ovt)
+        sl = dense_patch_slices(image_p, roi, interval)
+        starts = np.array([[s.start for s in w] for w in sl], dtype=np.int64)
+        cases.append((np.array(image), np.array(roi), np.array(ovt), np.array(interval), starts))
+    out = {}
+    for i, (im, roi, ov, iv, st) in enumerate(cases):
+        out[f"c{i}.image"], out[f"c{i}.roi"], out[f"c{i}.overlap"], out[f"c{i}.interval"], out[f"c{i}.starts"] = im, roi, ov, iv, st
+    out["n"] = np.array(len(cases))
+    for j, (ps, mode, sig) in enumerate([((96, 96, 96), "gaussian", 0.125), ((8, 5, 3), "gaussian", (0.2, 0.125, 0.5)), ((4, 4), "constant", 0.125), ((32, 32, 32), "gaussian", 0.125)]):
+        out[f"imp{j}.map"] = compute_importance_map(ps, mode=mode, sigma_scale=sig).numpy()
+        out[f"imp{j}.patch"] = np.array(ps)
+        out[f"imp{j}.sigma"] = np.atleast_1d(np.array(sig, dtype=np.float64))
+        out[f"imp{j}.mode"] = np.array(mode)
+    out["n_imp"] = np.array(4)
+    save("planner.npz", **out)
+
+
+def _cheap_predictor(x):
+    """deterministic, resolution-preserving, 2 output channels: depends on values and on the window-local position."""
+    ramp = torch.arange(x.shape[-1], dtype=x.dtype, device=x.device) * 0.01
+    a = x.mean(dim=1, keepdim=True) * 1.5 + ramp
+    b = torch.tanh(x[:, :1]) - 0.25
+    return torch.cat([a, b], dim=1)
+
+
+def sliding():
+    torch.manual_seed(0)
+    out = {}
+    cases = [
+        # name, shape, roi, sw_bs, overlap, mode, padding_mode, cval
+        ("a", (1, 1, 64, 64, 64), (32, 32, 32), 4, 0.25, "constant", "constant", 0.0),
+        ("b", (2, 2, 30, 26, 34), (12, 16, 10), 3, 0.5, "gaussian", "constant", 0.0),
+        ("c", (1, 1, 20, 20, 20), (32, 16, 24), 2, 0.25, "gaussian", "constant", -1.0),
+        ("d", (1, 3, 30, 30), (16, 16), 4, (0.5, 0.25), "gaussian", "replicate", 0.0),
+        ("e", (1, 1, 50), (16,), 5, 0.6, "constant", "constant", 0.0),
+        ("f", (1, 1, 24, 40, 40), (-1, 16, 24), 8, 0.5, "gaussian", "constant", 0.0),
+    ]
+    for name, shape, roi, bs, ov, mode, pm, cval in cases:
+        x = torch.randn(shape)
+        y = sliding_window_inference(x, roi, bs, _cheap_predictor, ov, mode, 0.125, pm, cval)
+        out[f"{name}.x"], out[f"{name}.y"] = x.numpy(), y.numpy()
+        out[f"{name}.roi"], out[f"{name}.bs"] = np.array(roi), np.array(bs)
+        out[f"{name}.overlap"] = np.atleast_1d(np.array(ov, dtype=np.float64))
+        out[f"{name}.mode"], out[f"{name}.pad"], out[f"{name}.cval"] = np.array(mode), np.array(pm), np.array(cval)
+    out["names"] = np.array([c[0] for c in cases])
+
+    # multi-resolution tuple / dict outputs (test_multioutput, tests/inferers/test_sliding_window_inference.py:314-377)
+    def multi(x):
+        return {"1": x + 1.0, "2": torch.nn.functional.avg_pool3d(x, 2) * 2.0, "3": x[..., ::4, ::4, ::4] - 3.0}
+
+    x = torch.randn(1, 1, 32, 32, 32)
+    r = sliding_window_inference(x, (16, 16, 16), 3, multi, 0.5, "gaussian")
+    out["multi.x"] = x.numpy()
+    for k, v in r.items():
+        out[f"multi.y{k}"] = v.numpy()
+    save("sliding_window.npz", **out)
+
+
+def _load_named(net, seed):
+    from weights import fill_state_dict
+
+    net.load_state_dict(fill_state_dict(net.state_dict(), seed))
+    return net.eval()
+
+
+def nets():
+    import contextlib
+    import io
+
+    sys.path.insert(0, HERE)
+    net = _load_named(UNet(3, 1, 2, (4, 8, 16), (2, 2)), 0)
+    x = torch.randn(2, 1, 16, 16, 16, generator=torch.Generator().manual_seed(10))
+    with torch.no_grad():
+        y = net(x)
+    save("unet_tiny.npz", x=x.numpy(), y=y.numpy())
+
+    net = _load_named(UNet(3, 1, 2, (16, 32, 64, 128, 256), (2, 2, 2, 2)), 1)  # config C2 topology
+    x = torch.randn(1, 1, 32, 32, 32, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        y = net(x)
+    save("unet_c2_32.npz", x=x.numpy(), y=y.numpy())
+
+    net = _load_named(UNet(3, 2, 3, (4, 8, 8), (2, 1), num_res_units=2), 2)
+    x = torch.randn(1, 2, 12, 10, 8, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        y = net(x)
+    save("unet_res.npz", x=x.numpy(), y=y.numpy())
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = _load_named(BasicUNet(3, 1, 2, features=(4, 4, 8, 8, 16, 4)), 3)
+    x = torch.randn(1, 1, 32, 32, 32, generator=torch.Generator().manual_seed(13))
+    with torch.no_grad():
+        y = net(x)
+    save("basic_unet_tiny.npz", x=x.numpy(), y=y.numpy())
+
+    net = _load_named(SwinUNETR(in_channels=1, out_channels=2, feature_size=12), 4)
+    # 64^3 is the smallest input: InstanceNorm at the 1/32 scale needs more than one spatial element
+    x = torch.randn(1, 1, 64, 64, 64, generator=torch.Generator().manual_seed(15)).half().float()
+    with torch.no_grad():
+        hs = net.swinViT(x, True)
+        y = net(x)
+    save("swin_unetr_fs12_64.npz", x=x.numpy().astype(np.float16), y_sub=y.numpy()[..., ::4, ::4, ::4], h0_sub=hs[0].numpy()[..., ::4, ::4, ::4],
+         h2=hs[2].numpy(), h4=hs[4].numpy(), y_mean=np.array(float(y.double().mean())), y_absmean=np.array(float(y.double().abs().mean())))
+
+
+if __name__ == "__main__":
+    print("reference monai", monai.__version__, "torch", torch.__version__)
+    which = sys.argv[1:] or ["planner", "sliding", "nets"]
+    for w in which:
+        globals()[w]()

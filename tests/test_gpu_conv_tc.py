@@ -1,0 +1,63 @@
+"""GPU parity of the tcgen05 implicit-GEMM 3x3x3 convolution against a torch fp32 reference of the same op.
+
+Inputs and weights are rounded to fp16 first (the kernel's storage type), so the only differences left are the
+fp32 accumulation order and the final fp16 rounding of the output: tolerance 2e-3 relative to the output scale.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from monai_b200 import _kernels as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run(N, Cin, Cout, sp, bias, seed=0, in_pad=0, out_pad=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((N, Cin, *sp), generator=g).half()
+    w = (torch.randn((Cout, Cin, 3, 3, 3), generator=g) / (27 * Cin) ** 0.5).half()
+    b = torch.randn(Cout, generator=g) if bias else None
+    ref = F.conv3d(x.float(), w.float(), b, padding=1)
+    # optionally embed the input / output in wider concat buffers (channel offsets)
+    xin = K.NC8(N, Cin + in_pad, sp, DEV)
+    xin.buf.fill_(float("nan")) if in_pad else None
+    K.pack_nc8(x.to(DEV), xin, c_off=in_pad)
+    out = K.NC8(N, Cout + out_pad, sp, DEV)
+    out.buf.zero_()
+    pw = K.conv3x3x3_tc_pack_weight(w.float().to(DEV))
+    y, stats = K.conv3x3x3_tc(xin, pw, Cin, Cout, in_coff=in_pad, bias=None if b is None else b.to(DEV), out=out, out_coff=out_pad, want_stats=True)
+    torch.cuda.synchronize()
+    got = K.unpack_nc8(y, Cout, c_off=out_pad, dtype=torch.float32).cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, f"max err {err} (scale {scale}) for N={N} Cin={Cin} Cout={Cout} sp={sp}"
+    S = sp[0] * sp[1] * sp[2]
+    torch.testing.assert_close(stats[:, 0].cpu() / S, ref.mean(dim=(2, 3, 4)).reshape(-1), rtol=1e-2, atol=2e-3 * scale)
+    torch.testing.assert_close(stats[:, 1].cpu() / S, (ref * ref).mean(dim=(2, 3, 4)).reshape(-1), rtol=1e-2, atol=1e-3 * scale * scale)
+    if out_pad:
+        assert float(out.buf[:, : out_pad // 8].abs().max()) == 0.0  # neighbouring channels untouched
+
+
+@pytest.mark.parametrize(
+    "N,Cin,Cout,sp",
+    [
+        (1, 16, 16, (4, 16, 8)),      # exactly one CTA tile, one K slice
+        (1, 16, 16, (5, 19, 11)),     # ragged edges in all three axes
+        (2, 48, 48, (8, 32, 16)),     # SwinUNETR encoder shapes (NT=48)
+        (1, 96, 48, (12, 24, 24)),    # decoder1.conv1 shape class
+        (1, 32, 128, (6, 12, 12)),    # NT=128
+        (1, 64, 192, (3, 6, 6)),      # Cout tiled 2 x 96, tiny volume
+        (1, 384, 32, (2, 3, 3)),      # deep K loop on a volume smaller than one tile
+    ],
+)
+def test_conv3x3x3_tc(N, Cin, Cout, sp):
+    _run(N, Cin, Cout, sp, bias=False)
+
+
+def test_conv3x3x3_tc_bias_and_channel_slices():
+    _run(2, 32, 48, (7, 20, 13), bias=True, seed=3, in_pad=16, out_pad=8)
+
+
+def test_conv3x3x3_tc_full_window_shape():
+    _run(1, 48, 48, (96, 96, 96), bias=False, seed=5)

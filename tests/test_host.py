@@ -1,0 +1,92 @@
+"""CPU-only checks of the host side: planner arithmetic (bit-exact vs the reference fixtures), the C-ABI library
+loads and exports every symbol include/monai_b200.h declares, and argument validation of the drop-in API."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from monai_b200 import _lib
+from monai_b200.data import utils as du
+from monai_b200.inferers import SlidingWindowInferer, sliding_window_inference
+from monai_b200.inferers.utils import _get_scan_interval
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_planner_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "planner.npz"))
+    for i in range(int(g["n"])):
+        image, roi, ov = tuple(g[f"c{i}.image"]), tuple(g[f"c{i}.roi"]), tuple(g[f"c{i}.overlap"])
+        image_p = tuple(int(max(a, b)) for a, b in zip(image, roi))
+        interval = _get_scan_interval(image_p, roi, len(image), ov)
+        assert interval == tuple(g[f"c{i}.interval"])
+        sl = du.dense_patch_slices(image_p, roi, interval)
+        np.testing.assert_array_equal(np.array([[s.start for s in w] for w in sl]), g[f"c{i}.starts"])
+        assert all(w[d].stop - w[d].start == min(roi[d], image_p[d]) for w in sl for d in range(len(roi)))
+
+
+def test_importance_factors_reproduce_the_dense_map(golden_dir):
+    g = np.load(os.path.join(golden_dir, "planner.npz"))
+    for j in range(int(g["n_imp"])):
+        sig = g[f"imp{j}.sigma"].tolist()
+        sig = sig[0] if len(sig) == 1 else tuple(sig)
+        patch, mode = tuple(int(v) for v in g[f"imp{j}.patch"]), str(g[f"imp{j}.mode"])
+        dense = du.compute_importance_map(patch, mode, sig).numpy()
+        np.testing.assert_array_equal(dense, g[f"imp{j}.map"])
+        f, clamp = du.importance_factors(patch, mode, sig)
+        m = f[0].numpy()
+        for i, v in enumerate(f[1:], start=1):
+            m = (m[..., None] * v.numpy()[(None,) * i]).astype(np.float32)
+        np.testing.assert_array_equal(np.maximum(m, np.float32(clamp)), g[f"imp{j}.map"])
+
+
+def test_get_valid_patch_size_follows_reference_code():
+    assert du.get_valid_patch_size((10, 20, 30), 5) == (5, 20, 30)
+    assert du.get_valid_patch_size((10, 20, 30), (5, 0)) == (5, 20, 30)
+    assert du.get_valid_patch_size((10, 20, 30), (50, None, 7)) == (10, 20, 7)
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "monai_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert os.path.exists(_lib.LIB_PATH), f"{_lib.LIB_PATH} missing: run python -m monai_b200._build"
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"symbols declared in include/monai_b200.h but not exported: {missing}"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.load().b200_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # sanity: ctypes mirrors must be at least as large as the packed field sum and 8-byte aligned
+    assert ctypes.sizeof(_lib.BlendDesc) % 8 == 0
+    assert ctypes.sizeof(_lib.ConvDesc) == 21 * 4 + 4 + 16
+    assert ctypes.sizeof(_lib.ConvTcDesc) == 40
+
+
+def test_argument_validation_matches_reference():
+    x = torch.zeros(1, 1, 8, 8, 8)
+    with pytest.raises(ValueError, match="overlap must be >= 0 and < 1"):
+        sliding_window_inference(x, (4, 4, 4), 1, lambda t: t, overlap=1.0)
+    with pytest.raises(ValueError, match="overlap must be >= 0 and < 1"):
+        sliding_window_inference(x, (4, 4, 4), 1, lambda t: t, overlap=(0.5, -0.1, 0.5))
+    with pytest.raises(ValueError, match="buffer_dim must be in"):
+        sliding_window_inference(x, (4, 4, 4), 1, lambda t: t, buffer_steps=2, buffer_dim=7)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sliding_window_inference(x, (4, 4, 4), 1, lambda t: t)  # CPU tensors: no silent fallback
+    with pytest.raises(ValueError):
+        SlidingWindowInferer((4, 4, 4), mode="nonsense")
+
+
+def test_kernels_refuse_cpu_tensors():
+    from monai_b200 import _kernels as K
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        K.instnorm_stats(torch.zeros(1, 2, 4, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        K.conv3d_direct(torch.zeros(1, 1, 4, 4, 4), torch.zeros(2, 1, 3, 3, 3))
