@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the monai_b200 hot path (sliding-window inference, voxels/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload unet_c2|swin_c3] [--impl b200|reference]
+
+One "step" = one full `SlidingWindowInferer(...)(volume, network)` pass over one synthetic volume.
+  value : voxels/s with the volume already resident in HBM (CUDA-event timed, max over ranks)
+  e2e   : the same call with a pinned HOST volume: H2D copy + inference + D2H copy of the logits inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md "Measurement"
+`--impl reference` times the reference algorithm's CPU path (the oracle port: torch-CPU restatement, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "unet_c2": dict(
+        desc="UNet(16,32,64,128,256; strides 2,2,2,2) sliding-window 256^3 fp16, roi 96^3, overlap 0.5, gaussian",
+        vol=(256, 256, 256), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=25, net="unet_c2", windows=125,
+        flop_per_window=2.96e9,
+    ),
+    # BASELINE.json configs[2]
+    "swin_c3": dict(
+        desc="SwinUNETR(feature_size=48) sliding-window 512^3 fp16, roi 96^3, overlap 0.5, gaussian",
+        vol=(512, 512, 512), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=4, net="swin48", windows=1000,
+        flop_per_window=636e9,
+    ),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf=d.get("bf16_tflops", 1590.0), tf_sustained=d.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def build_net(kind: str, device, half: bool):
+    from weights import fill_state_dict
+
+    if kind == "unet_c2":
+        from monai_b200.networks.nets import UNet
+
+        net = UNet(3, 1, 2, (16, 32, 64, 128, 256), (2, 2, 2, 2))
+    elif kind == "swin48":
+        from monai_b200.networks.nets import SwinUNETR
+
+        net = SwinUNETR(in_channels=1, out_channels=2, feature_size=48)
+    else:
+        raise ValueError(kind)
+    net.load_state_dict(fill_state_dict(net.state_dict(), 1))  # random-init weights of the named architecture
+    net = net.eval().to(device)
+    return net.half() if half else net
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=self.f, stderr=subprocess.DEVNULL,
+            )
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, wl):
+    """CPU arm: the reference algorithm's CPU path (oracle port), all host threads, fp32."""
+    from oracle import networks as onet
+    from oracle import sliding_window as osw
+    from weights import fill_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if wl["net"] == "unet_c2":
+        from monai_b200.networks.nets import UNet
+
+        sd = fill_state_dict(UNet(3, 1, 2, (16, 32, 64, 128, 256), (2, 2, 2, 2)).state_dict(), 1)
+        vol = wl["vol"]
+        fwd = lambda a: onet.unet_forward(sd, torch.from_numpy(a), (2, 2, 2, 2)).numpy()  # noqa: E731
+        sample = f"full {vol[0]}x{vol[1]}x{vol[2]} volume ({wl['windows']} windows) per step, fp32"
+        scale = 1.0
+    else:
+        from monai_b200.networks.nets import SwinUNETR
+
+        sd = fill_state_dict(SwinUNETR(in_channels=1, out_channels=2, feature_size=48).state_dict(), 1)
+        vol = (144, 144, 96)  # 2x2x1 = 4 windows; cost is linear in windows
+        fwd = lambda a: onet.swin_unetr_forward(sd, torch.from_numpy(a)).numpy()  # noqa: E731
+        sample = "144x144x96 sub-volume (4 windows) per step, extrapolated linearly to 1000 windows, fp32"
+        scale = 4.0 / wl["windows"]
+    x = np.random.default_rng(0).standard_normal((1, 1, *vol)).astype(np.float32)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            osw.sliding_window_inference(x, wl["roi"], 4, fwd, wl["overlap"], wl["mode"])
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    full_vox = float(np.prod(wl["vol"]))
+    sec_full = statistics.mean(times) / scale
+    v = full_vox / sec_full
+    line = {
+        "impl": "reference", "metric": "voxels/sec sliding-window inference", "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
+        "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(wl, budget_s: float = 20.0) -> dict:
+    from oracle import networks as onet
+    from oracle import sliding_window as osw
+    from weights import fill_state_dict
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if wl["net"] == "unet_c2":
+        from monai_b200.networks.nets import UNet
+
+        sd = fill_state_dict(UNet(3, 1, 2, (16, 32, 64, 128, 256), (2, 2, 2, 2)).state_dict(), 1)
+        vol, nwin = (144, 144, 144), 8
+        fwd = lambda a: onet.unet_forward(sd, torch.from_numpy(a), (2, 2, 2, 2)).numpy()  # noqa: E731
+    else:
+        from monai_b200.networks.nets import SwinUNETR
+
+        sd = fill_state_dict(SwinUNETR(in_channels=1, out_channels=2, feature_size=48).state_dict(), 1)
+        vol, nwin = (144, 144, 96), 4
+        fwd = lambda a: onet.swin_unetr_forward(sd, torch.from_numpy(a)).numpy()  # noqa: E731
+    x = np.random.default_rng(0).standard_normal((1, 1, *vol)).astype(np.float32)
+    times = []
+    t_all = time.perf_counter()
+    with torch.no_grad():
+        while len(times) < 2 or (time.perf_counter() - t_all < budget_s and len(times) < 6):
+            t0 = time.perf_counter()
+            osw.sliding_window_inference(x, wl["roi"], 4, fwd, wl["overlap"], wl["mode"])
+            times.append(time.perf_counter() - t0)
+    per_win = min(times[1:] or times) / nwin
+    v = float(np.prod(wl["vol"])) / (per_win * wl["windows"])
+    return {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
+            "sample": f"{vol[0]}x{vol[1]}x{vol[2]} sub-volume ({nwin} windows, fp32, torch-CPU oracle) x{len(times)} passes, seconds/window extrapolated to {wl['windows']} windows"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("B200_WORKLOAD", "unet_c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    from monai_b200 import _kernels as K
+    from monai_b200 import _lib
+    from monai_b200.inferers import SlidingWindowInferer
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    net = build_net(wl["net"], dev, half=True)
+    vol = wl["vol"]
+    host = torch.randn((1, 1, *vol), generator=torch.Generator().manual_seed(0)).half().pin_memory()
+    x_dev = host.to(dev)
+    inferer = SlidingWindowInferer(wl["roi"], wl["sw_batch"], wl["overlap"], wl["mode"])
+    if world > 1:
+        from monai_b200.parallel import ShardedSlidingWindowInferer
+
+        inferer = ShardedSlidingWindowInferer(wl["roi"], wl["sw_batch"], wl["overlap"], wl["mode"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        return inferer(x_dev, net)
+
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        xd = host.to(dev, non_blocking=True)
+        y = inferer(xd, net)
+        if out_host is None:
+            out_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        out_host.copy_(y, non_blocking=True)
+        return y
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    launches = (_lib.launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if sampler else {}
+    ms_e2e = timed(step_e2e, args.steps, 1)
+
+    # per-kernel device time (CUDA events around every C-ABI launch, one extra untimed-for-value pass)
+    K.profile_start()
+    step_resident()
+    prof = K.profile_stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    nvox = float(np.prod(vol))
+    ms_step = ms_total / args.steps
+    pk = peaks()
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    roofline = None
+    if top[0] is not None:
+        name, st = top
+        flops, byts = st.get("flops", 0.0), st.get("bytes", 0.0)
+        avg_ms = st["ms"] / max(1, st["n"])
+        if flops and (flops / pk["tf"] / 1e12) >= (byts / pk["hbm"] / 1e9):
+            ach = flops / max(1, st["n"]) / (avg_ms * 1e-3) / 1e12
+            roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None}
+        else:
+            ach = byts / max(1, st["n"]) / (avg_ms * 1e-3) / 1e9
+            roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None}
+        roofline.update({"peak_source": pk["src"], "launches": st["n"], "avg_launch_ms": avg_ms, "share_of_kernel_time": st["ms"] / total_kernel_ms})
+    line = {
+        "metric": "voxels/sec sliding-window inference", "value": nvox / (ms_step * 1e-3), "unit": "voxels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sw_batch_size": wl["sw_batch"], "windows": wl["windows"], "l2": "256 MiB flush write between timed steps",
+                   "accumulate": "fp32", "parallelism": f"depth-shard x{world}" if world > 1 else "single GPU"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": nvox / (ms_e2e / args.steps * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
+                "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()) if out_host is not None else 0},
+        "model_tflops": wl["flop_per_window"] * wl["windows"] / (ms_step * 1e-3) / 1e12,
+        "roofline": roofline,
+        "kernels": {k: {"ms": round(v["ms"], 4), "n": v["n"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_leg(wl)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,59 @@ typedef struct b200_conv_tc_desc {
 int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
                       void* y, float* stats, void* stream);
 
+typedef struct b200_gemm_tc_desc {
+  int Nb;                   /* batch items (each with its own S rows) */
+  int S;                    /* GEMM rows per batch item (tokens / voxels of x) */
+  int K, N;                 /* reduction size (input channels) and GEMM columns */
+  int in_ctot, in_coff;     /* x = channels [in_coff, in_coff+K) of an NC8 buffer with in_ctot channels */
+  int out_ctot, out_coff;   /* destination channel slice */
+  int res_ctot, res_coff;   /* residual (added before the store), indexed like the destination */
+  long long S_out;          /* rows per batch item of the destination (== S unless mode 1/2) */
+  int mode;                 /* 0: row r -> r; 1: row r -> row_map[n*S + r] (-1 = drop); 2: ConvTranspose k2 s2 scatter */
+  int act;                  /* 0 none, 4 GELU(erf) */
+  int D, H, W;              /* mode 2: source grid (S == D*H*W); destination grid is (2D,2H,2W) */
+} b200_gemm_tc_desc;
+
+long long b200_gemm_tc_weight_bytes(int N, int K);
+/* pack W[n,k] = w[n*stride_n + k*stride_k] (float32 device) into the UMMA B-operand image (fp16 device). */
+int b200_gemm_tc_pack_weight(const float* w, int N, int K, long long stride_n, long long stride_k, void* packed,
+                             void* stream);
+/* y = [res +] act(x * W^T + bias) on tcgen05: nn.Linear (swin_unetr.py:509-532, blocks/mlp.py:75-80, PatchMerging
+ * 749-773), 1x1x1 Conv3d (dynunet_block.py:75-87) and ConvTranspose3d k2 s2 (unetr_block.py:56-64, mode 2 with
+ * GEMM columns ordered [tap = kd*4+kh*2+kw][cout]).  stats (optional, zero-initialised by the caller) accumulates
+ * per-(batch, column) {sum, sumsq} of the stored values for InstanceNorm. */
+int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const void* packed_w, const float* bias, const void* res,
+                 const int32_t* row_map, void* y, float* stats, void* stream);
+
+/* LayerNorm over channels of NC8 tokens with an optional row gather (window partition + cyclic shift + zero pad of
+ * swin_unetr.py:596-625): y[n, :, r] = LN(x[n, :, src[r]]) (src[r] < 0 -> zeros; src == NULL -> identity).
+ * gamma/beta NULL = no affine (SwinTransformer.proj_out, swin_unetr.py:1040-1053).  src is shared by all batch items. */
+int b200_layernorm_nc8(const void* x, int N, int C, long long S_in, const int32_t* src, long long S_out,
+                       const float* gamma, const float* beta, float eps, void* y, void* stream);
+
+/* PatchMerging gather + LayerNorm (swin_unetr.py:749-773): x NC8 [N][C/8][D][H][W][8] -> y NC8 [N][8C/8][D/2*H/2*W/2][8],
+ * channel blocks in the reference order x0..x7 = (0,0,0),(1,0,0),(0,1,0),(0,0,1),(1,1,0),(1,0,1),(0,1,1),(1,1,1)
+ * (v2 = 0) or itertools.product order (v2 = 1); odd sizes are zero padded. */
+int b200_patch_merge_ln_nc8(const void* x, int N, int C, int D, int H, int W, const float* gamma, const float* beta,
+                            float eps, int v2, void* y, void* stream);
+
+/* Windowed multi-head self-attention (WindowAttention.forward, swin_unetr.py:509-532) on NC8 tokens in window order:
+ * qkv NC8 [N][3C/8][nW*n][8] (channels = [q | k | v], head h = channels [16h, 16h+16) of each third; head_dim 16),
+ * bias float32 [heads][n][n] (relative position bias already gathered), region int32 [nW][n] or NULL (shift mask:
+ * -100 where regions differ, swin_unetr.py:779-816), out NC8 [N][C/8][nW*n][8]. */
+int b200_window_attention_nc8(const void* qkv, int N, int C, int heads, int nW, int n, float scale, const float* bias,
+                              const int32_t* region, void* out, void* stream);
+
+/* Convolution with ONE input channel straight from an NCDHW volume to NC8 (patch embedding k2 s2, the 3x3x3 stem of
+ * UnetrBasicBlock and its 1x1x1 residual conv): weight float32 [Cout][1][k][k][k]; stats optional {sum,sumsq}. */
+int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H, int W, const float* weight, const float* bias,
+                       int Cout, int k, int stride, int pad, void* y, int out_ctot, int out_coff, float* stats,
+                       void* stream);
+
+/* 1x1x1 output head (UnetOutBlock, dynunet_block.py:247-267): NC8 fp16 [N][C/8][S][8] -> NCDHW [N][Cout][S]. */
+int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,
+                       void* y, int out_dtype, void* stream);
+
 /* NC8 variant of b200_norm_act: y = act(instnorm(x) [+ instnorm?(res)]); act: 0 none, 1 leaky-relu(slope), 3 relu.
  * x / res / y are channel slices [coff, coff+C) of NC8 buffers with ctot channels. */
 int b200_norm_act_nc8(const void* x, int x_ctot, int x_coff, int N, int C, long long S, const float* stats, float eps,

@@ -13,6 +13,48 @@ import torch
 from . import _lib as L
 
 
+class _Prof:
+    on = False
+    events: list = []
+
+
+def profile_start() -> None:
+    """Record a CUDA-event pair around every C-ABI launch until profile_stop() (used by bench.py for the roofline)."""
+    _Prof.on, _Prof.events = True, []
+
+
+def profile_stop() -> dict:
+    torch.cuda.synchronize()
+    _Prof.on = False
+    out: dict = {}
+    for name, e0, e1, flops, nbytes in _Prof.events:
+        d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["n"] += 1
+        d["flops"] += flops
+        d["bytes"] += nbytes
+    _Prof.events = []
+    return out
+
+
+def _call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    """Launch one C-ABI entry point (b200_<name>) and raise on a non-zero status."""
+    fn = getattr(L.load(), "b200_" + name)
+    if _Prof.on:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _Prof.events.append((name, e0, e1, flops, nbytes))
+    else:
+        rc = fn(*args)
+    L.check(rc, name)
+
+
+def _nb(*tensors) -> float:
+    return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
+
+
 def _t3(v) -> tuple[int, int, int]:
     if isinstance(v, int):
         return (v, v, v)
@@ -65,7 +107,10 @@ def conv3d_direct(
         N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], int(transposed),
         L.dt(x), L.dt(out), x.stride(0) if N > 1 else Cin * Di * Hi * Wi, out.stride(0) if N > 1 else Cout * Do * Ho * Wo,
     )
-    L.check(lib.b200_conv3d_direct(C.byref(d), L.ptr(x), L.ptr(w32), L.ptr(b32), L.ptr(out), L.stream_ptr(x.device)), "conv3d_direct")
+    taps = k[0] * k[1] * k[2]
+    macs = float(N) * (Di * Hi * Wi if transposed else Do * Ho * Wo) * Cin * Cout * taps
+    _call("conv3d_direct", C.byref(d), L.ptr(x), L.ptr(w32), L.ptr(b32), L.ptr(out), L.stream_ptr(x.device),
+          flops=2.0 * macs, nbytes=_nb(x, out, w32))
     return out
 
 
@@ -76,7 +121,7 @@ def instnorm_stats(x: torch.Tensor) -> torch.Tensor:
     N, Cc = x.shape[:2]
     S = x[0, 0].numel()
     stats = torch.empty((N * Cc, 2), device=x.device, dtype=torch.float32)
-    L.check(L.load().b200_instnorm_stats(L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), L.stream_ptr(x.device)), "instnorm_stats")
+    _call("instnorm_stats", L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), L.stream_ptr(x.device), nbytes=_nb(x))
     return stats
 
 
@@ -101,14 +146,9 @@ def norm_act(
     g = None if gamma is None else gamma.detach().float().contiguous()
     b = None if beta is None else beta.detach().float().contiguous()
     sl = None if slope_t is None else slope_t.detach().float().contiguous()
-    L.check(
-        L.load().b200_norm_act(
-            L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), eps, L.ptr(g), L.ptr(b), L.ptr(res),
+    _call("norm_act", L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), eps, L.ptr(g), L.ptr(b), L.ptr(res),
             (res.stride(0) if N > 1 else Cc * S) if res is not None else 0, L.ptr(res_stats), act, float(slope), L.ptr(sl),
-            0 if sl is None else sl.numel(), L.ptr(out), out.stride(0) if N > 1 else Cc * S, L.stream_ptr(x.device),
-        ),
-        "norm_act",
-    )
+            0 if sl is None else sl.numel(), L.ptr(out), out.stride(0) if N > 1 else Cc * S, L.stream_ptr(x.device))
     return out
 
 
@@ -117,7 +157,7 @@ def maxpool3d_2(x: torch.Tensor) -> torch.Tensor:
     N, Cc, D, H, W = x.shape
     x = x.contiguous()
     y = torch.empty((N, Cc, D // 2, H // 2, W // 2), device=x.device, dtype=x.dtype)
-    L.check(L.load().b200_maxpool3d_2(L.ptr(x), L.dt(x), N * Cc, D, H, W, L.ptr(y), L.stream_ptr(x.device)), "maxpool3d_2")
+    _call("maxpool3d_2", L.ptr(x), L.dt(x), N * Cc, D, H, W, L.ptr(y), L.stream_ptr(x.device))
     return y
 
 
@@ -129,7 +169,7 @@ def copy_channels(x: torch.Tensor, dst: torch.Tensor, c_off: int) -> None:
     _, Ct, Do, Ho, Wo = dst.shape
     if not dst.is_contiguous():
         raise ValueError("dst must be contiguous")
-    L.check(L.load().b200_copy_channels(L.ptr(x), L.dt(x), N, Cc, Di, Hi, Wi, L.ptr(dst), Ct, c_off, Do, Ho, Wo, L.stream_ptr(x.device)), "copy_channels")
+    _call("copy_channels", L.ptr(x), L.dt(x), N, Cc, Di, Hi, Wi, L.ptr(dst), Ct, c_off, Do, Ho, Wo, L.stream_ptr(x.device))
 
 
 # ------------------------------------------------------------------------------------------------ sliding window
@@ -140,7 +180,7 @@ def sw_gather(vol: torch.Tensor, win_tab: torch.Tensor, roi: Sequence[int], out_
     B, Cc, D, H, W = vol.shape
     n = win_tab.shape[0]
     out = torch.empty((n, Cc, *roi), device=vol.device, dtype=out_dtype or vol.dtype)
-    L.check(L.load().b200_sw_gather(L.ptr(vol), L.dt(vol), L.ptr(out), L.dt(out), L.ptr(win_tab), n, Cc, D, H, W, roi[0], roi[1], roi[2], L.stream_ptr(vol.device)), "sw_gather")
+    _call("sw_gather", L.ptr(vol), L.dt(vol), L.ptr(out), L.dt(out), L.ptr(win_tab), n, Cc, D, H, W, roi[0], roi[1], roi[2], L.stream_ptr(vol.device))
     return out
 
 
@@ -181,7 +221,8 @@ def sw_blend(
     d.acc = L.ptr(acc)
     for i in range(4):
         d.box[i] = box[i]
-    L.check(L.load().b200_sw_blend(C.byref(d), mode, L.stream_ptr(out.device)), "sw_blend")
+    nb = _nb(preds) + (_nb(out) if mode == 0 else 0.0) + (2.0 * _nb(out) if mode == 1 else 0.0) + (_nb(out, acc) if mode == 2 else 0.0)
+    _call("sw_blend", C.byref(d), mode, L.stream_ptr(out.device), nbytes=nb)
 
 
 # ---------------------------------------------------------------------------------------------------- transforms
@@ -195,7 +236,7 @@ def resample_affine(
     Cc, Di, Hi, Wi = src.shape
     dst = torch.empty((Cc, *out_shape), device=src.device, dtype=out_dtype)
     m = (C.c_double * 12)(*[float(v) for v in mat])
-    L.check(L.load().b200_resample_affine(L.ptr(src), L.dt(src), Cc, Di, Hi, Wi, L.ptr(dst), L.dt(dst), out_shape[0], out_shape[1], out_shape[2], m, interp, pad, int(bool(align_corners)), L.stream_ptr(src.device)), "resample_affine")
+    _call("resample_affine", L.ptr(src), L.dt(src), Cc, Di, Hi, Wi, L.ptr(dst), L.dt(dst), out_shape[0], out_shape[1], out_shape[2], m, interp, pad, int(bool(align_corners)), L.stream_ptr(src.device))
     return dst
 
 
@@ -207,7 +248,7 @@ def separable_filter3d(src: torch.Tensor, taps: Sequence[torch.Tensor]) -> torch
     dst = torch.empty_like(src)
     tmp = torch.empty((2, Cc, D, H, W), device=src.device, dtype=torch.float32)
     t = [x.detach().to(device=src.device, dtype=torch.float32).contiguous() for x in taps]
-    L.check(L.load().b200_separable_filter3d(L.ptr(src), L.dt(src), Cc, D, H, W, L.ptr(t[0]), t[0].numel(), L.ptr(t[1]), t[1].numel(), L.ptr(t[2]), t[2].numel(), L.ptr(tmp), L.ptr(dst), L.stream_ptr(src.device)), "separable_filter3d")
+    _call("separable_filter3d", L.ptr(src), L.dt(src), Cc, D, H, W, L.ptr(t[0]), t[0].numel(), L.ptr(t[1]), t[1].numel(), L.ptr(t[2]), t[2].numel(), L.ptr(tmp), L.ptr(dst), L.stream_ptr(src.device))
     return dst
 
 
@@ -234,14 +275,14 @@ def pack_nc8(x: torch.Tensor, dst: NC8 | None = None, c_off: int = 0) -> NC8:
     N, Cc = x.shape[:2]
     if dst is None:
         dst = NC8(N, Cc, x.shape[2:], x.device)
-    L.check(L.load().b200_pack_nc8(L.ptr(x), L.dt(x), N, Cc, dst.S, L.ptr(dst.buf), dst.C, c_off, L.stream_ptr(x.device)), "pack_nc8")
+    _call("pack_nc8", L.ptr(x), L.dt(x), N, Cc, dst.S, L.ptr(dst.buf), dst.C, c_off, L.stream_ptr(x.device))
     return dst
 
 
 def unpack_nc8(src: NC8, C_: int | None = None, c_off: int = 0, dtype: torch.dtype = torch.float16) -> torch.Tensor:
     C_ = C_ or src.C
     y = torch.empty((src.N, C_, *src.sp), device=src.buf.device, dtype=dtype)
-    L.check(L.load().b200_unpack_nc8(L.ptr(src.buf), src.C, c_off, src.N, C_, src.S, L.ptr(y), L.dt(y), L.stream_ptr(y.device)), "unpack_nc8")
+    _call("unpack_nc8", L.ptr(src.buf), src.C, c_off, src.N, C_, src.S, L.ptr(y), L.dt(y), L.stream_ptr(y.device))
     return y
 
 
@@ -253,7 +294,7 @@ def conv3x3x3_tc_pack_weight(weight: torch.Tensor) -> torch.Tensor:
         raise ValueError(f"conv3x3x3_tc needs Cin, Cout multiples of 16, got {Cin}, {Cout}")
     w32 = weight.detach().float().contiguous()
     packed = torch.empty(nbytes // 2, device=weight.device, dtype=torch.float16)
-    L.check(L.load().b200_conv3x3x3_tc_pack_weight(L.ptr(w32), Cin, Cout, L.ptr(packed), L.stream_ptr(weight.device)), "conv3x3x3_tc_pack_weight")
+    _call("conv3x3x3_tc_pack_weight", L.ptr(w32), Cin, Cout, L.ptr(packed), L.stream_ptr(weight.device))
     return packed
 
 
@@ -266,7 +307,8 @@ def conv3x3x3_tc(
     stats = torch.zeros((x.N * Cout, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
     b32 = None if bias is None else bias.detach().float().contiguous()
     d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff)
-    L.check(L.load().b200_conv3x3x3_tc(C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.stream_ptr(x.buf.device)), "conv3x3x3_tc")
+    _call("conv3x3x3_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.stream_ptr(x.buf.device),
+          flops=2.0 * x.N * x.S * Cin * Cout * 27, nbytes=float(x.N * x.S * (Cin + Cout) * 2) + _nb(packed_w))
     return out, stats
 
 
@@ -277,14 +319,9 @@ def norm_act_nc8(
 ) -> NC8:
     if out is None:
         out = NC8(x.N, C_, x.sp, x.buf.device)
-    L.check(
-        L.load().b200_norm_act_nc8(
-            L.ptr(x.buf), x.C, x_coff, x.N, C_, x.S, L.ptr(stats), eps, L.ptr(res.buf) if res is not None else None,
+    _call("norm_act_nc8", L.ptr(x.buf), x.C, x_coff, x.N, C_, x.S, L.ptr(stats), eps, L.ptr(res.buf) if res is not None else None,
             res.C if res is not None else 0, res_coff, L.ptr(res_stats), act, float(slope), L.ptr(out.buf), out.C, out_coff,
-            L.stream_ptr(x.buf.device),
-        ),
-        "norm_act_nc8",
-    )
+            L.stream_ptr(x.buf.device))
     return out
 
 

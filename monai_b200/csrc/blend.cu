@@ -64,6 +64,11 @@ __global__ void __launch_bounds__(256) sw_blend_kernel(BlendParams p) {
     const int cn = min(CMAX, p.C - c0);
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) accv[c] = 0.f;
+    if (MODE == 1) {  // continue the running sums so the addition order stays "one window after the other"
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < cn) accv[c] = *((const float*)p.out + ((long long)b * p.C + c0 + c) * vol + voff);
+    }
     cnt = 0.f;
     for (int a = 0; a < s_ndc; ++a) {
       const int id = s_did[a];
@@ -99,10 +104,7 @@ __global__ void __launch_bounds__(256) sw_blend_kernel(BlendParams p) {
     } else if (MODE == 1) {
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
-        if (c < cn) {
-          float* o = (float*)p.out + ((long long)b * p.C + c0 + c) * vol + voff;
-          *o = __fadd_rn(*o, accv[c]);
-        }
+        if (c < cn) *((float*)p.out + ((long long)b * p.C + c0 + c) * vol + voff) = accv[c];
     }
   }
   if (MODE == 2) {

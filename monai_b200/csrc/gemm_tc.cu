@@ -1,0 +1,259 @@
+// Y = epilogue( X * W^T ) on tcgen05 tensor cores for channel-blocked (NC8) activations.
+//
+// One kernel serves every GEMM-shaped layer of SwinUNETR outside the 3x3x3 convolutions:
+//   * nn.Linear of WindowAttention.qkv / proj, MLPBlock.linear1 / linear2, PatchMerging.reduction
+//     (monai/networks/nets/swin_unetr.py:509-532, 596-648, 749-773; monai/networks/blocks/mlp.py:75-80),
+//   * 1x1x1 Conv3d (UnetResBlock.conv3, dynunet_block.py:75-87),
+//   * ConvTranspose3d(kernel 2, stride 2) of UnetrUpBlock (unetr_block.py:56-64): a GEMM with N = 8*Cout followed by a
+//     scatter of each (tap, cout) group to the 2x-upsampled voxel.
+//
+// Operands: X is NC8 [Nb][K/8][S][8] fp16 (rows = S tokens/voxels); a 128-row A tile of one 8-channel chunk is 2 KB
+// contiguous in HBM and lands in shared memory as the UMMA K-major / no-swizzle core-matrix column
+// (LBO = 128*16 B between K chunks, SBO = 128 B between 8-row groups).  W is pre-packed into the B image
+// [nt][k16][khalf][NT/8][8][8] and streamed with 1-D bulk copies.  fp32 accumulators live in TMEM.
+// Epilogue (4 warps, one TMEM lane quarter each): + bias, GELU(erf), + residual, InstanceNorm partial sums, and a
+// row map (identity / index table / 2x upsample scatter) before the fp16 NC8 store.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "../../include/monai_b200.h"
+
+namespace b200 {
+
+constexpr int kGemmStages = 4;
+constexpr int kGemmK16PerStage = 4;                 // 64 K elements per pipeline stage
+constexpr int kGemmAStage = kGemmK16PerStage * 2 * 128 * 16;  // 16 KB
+
+__host__ __device__ inline int gemm_tc_nt(int N) {
+  for (int nt = 256; nt >= 16; nt -= 16)
+    if (N % nt == 0) return nt;
+  return 16;
+}
+
+struct GemmTcParams {
+  b200_gemm_tc_desc d;
+  const __half* w; const float* bias; __half* y; const __half* res; float* stats; const int32_t* row_map;
+  int NT, tmem_cols;
+};
+
+__global__ void gemm_tc_pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int N, int K, int NT,
+                                           long long w_stride_n, long long w_stride_k) {
+  // out index: [nt][k16][khalf][g][row][kk]
+  const long long total = (long long)N * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int kk = (int)(r % 8); r /= 8;
+    const int row = (int)(r % 8); r /= 8;
+    const int g = (int)(r % (NT / 8)); r /= (NT / 8);
+    const int khalf = (int)(r % 2); r /= 2;
+    const int k16 = (int)(r % (K / 16)); r /= (K / 16);
+    const int nt = (int)r;
+    const int n = nt * NT + g * 8 + row, k = k16 * 16 + khalf * 8 + kk;
+    out[i] = __float2half_rn(w[n * w_stride_n + k * w_stride_k]);
+  }
+}
+
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap, GemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int NT = p.NT;
+  const int b_stage = kGemmK16PerStage * NT * 32;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kGemmStages * kGemmAStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kGemmStages * b_stage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kGemmStages;
+  uint64_t* acc_full = bars + 2 * kGemmStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* s_stats = reinterpret_cast<float*>(bars + 16);  // [2*NT]
+
+  const b200_gemm_tc_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 128, nt = blockIdx.y, n = blockIdx.z;
+  const int num_k16 = d.K / 16;
+  const int num_stages = (num_k16 + kGemmK16PerStage - 1) / kGemmK16PerStage;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGemmStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+  if (warp == 1) tc::tmem_alloc(tmem_slot, p.tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmap);
+      const __half* wbase = p.w + (long long)nt * num_k16 * (NT * 16);
+      int s = 0; uint32_t ph = 0;
+      for (int st = 0; st < num_stages; ++st) {
+        const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&full[s], kGemmAStage + steps * NT * 32);
+        tc::tma_load_4d(smem_a + s * kGemmAStage, &tmap, &full[s], 0, row0, (d.in_coff / 8) + st * kGemmK16PerStage * 2, n);
+        tc::bulk_load(smem_b + s * b_stage, wbase + (long long)st * kGemmK16PerStage * (NT * 16), steps * NT * 32, &full[s]);
+        if (++s == kGemmStages) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(128, NT);
+      int s = 0; uint32_t ph = 0;
+      for (int st = 0; st < num_stages; ++st) {
+        const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
+        tc::mbar_wait(&full[s], ph);
+        tc::fence_after_sync();
+        const uint32_t a_base = tc::smem_u32(smem_a + s * kGemmAStage), b_base = tc::smem_u32(smem_b + s * b_stage);
+        for (int k = 0; k < steps; ++k) {
+          const uint64_t adesc = tc::make_desc_kmajor_noswz(a_base + k * 2 * 2048, 2048, 128);
+          const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_base + k * NT * 32, NT * 16, 128);
+          tc::mma_f16_ss(tmem_base, adesc, bdesc, idesc, (st | k) != 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&empty[s]);
+        if (++s == kGemmStages) { s = 0; ph ^= 1; }
+      }
+      tc::mma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = row0 + q * 32 + lane;
+    const bool row_ok = row < d.S;
+    // destination row (identity, table lookup, or 2x-upsample scatter computed per tap below)
+    long long drow = row;
+    if (row_ok && p.row_map) drow = p.row_map[(long long)n * d.S + row];
+    const bool dst_ok = row_ok && drow >= 0;
+    int vz = 0, vy = 0, vx = 0;
+    if (d.mode == 2 && row_ok) { vx = row % d.W; vy = (row / d.W) % d.H; vz = row / (d.W * d.H); }
+    tc::mbar_wait(acc_full, 0);
+    tc::fence_after_sync();
+    const int co0 = nt * NT;
+    const int cout = d.mode == 2 ? d.N / 8 : d.N;  // channels of the destination tensor written by this GEMM
+    __half* ybase = p.y + ((long long)n * (d.out_ctot / 8)) * d.S_out * 8;
+    const __half* rbase = p.res ? p.res + ((long long)n * (d.res_ctot / 8)) * d.S_out * 8 : nullptr;
+#pragma unroll 1
+    for (int cc = 0; cc < NT / 8; ++cc) {
+      uint32_t v[8];
+      tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 8, v);
+      tc::tmem_ld_wait();
+      const int nc = co0 + cc * 8;  // first GEMM column of this chunk
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[d.mode == 2 ? (nc + j) % cout : nc + j] : 0.f);
+      if (d.act == 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+      }
+      long long orow = drow; int ochunk;
+      if (d.mode == 2) {
+        const int tap = nc / cout;  // GEMM columns are ordered [tap][cout]
+        ochunk = (d.out_coff + (nc % cout)) / 8;
+        orow = ((long long)(2 * vz + (tap >> 2)) * (2 * d.H) + (2 * vy + ((tap >> 1) & 1))) * (2 * d.W) + (2 * vx + (tap & 1));
+      } else {
+        ochunk = (d.out_coff + nc) / 8;
+      }
+      if (dst_ok) {
+        if (rbase) {
+          __align__(16) __half rv[8];
+          *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(rbase + (((long long)(d.res_coff + nc) / 8) * d.S_out + orow) * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += __half2float(rv[j]);
+        }
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(f[j]);
+        *reinterpret_cast<uint4*>(ybase + ((long long)ochunk * d.S_out + orow) * 8) = *reinterpret_cast<const uint4*>(hv);
+      }
+      if (p.stats) {
+        float a1[8], b1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a1[j] = dst_ok ? f[j] : 0.f; b1[j] = a1[j] * a1[j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a1[j] = warp_sum(a1[j]); b1[j] = warp_sum(b1[j]); }
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { atomicAdd(&s_stats[2 * (cc * 8 + j)], a1[j]); atomicAdd(&s_stats[2 * (cc * 8 + j) + 1], b1[j]); }
+        }
+      }
+    }
+    tc::fence_before_sync();
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;
+      for (int i = t; i < 2 * NT; i += 128) atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" long long b200_gemm_tc_weight_bytes(int N, int K) {
+  if (N <= 0 || K <= 0 || N % 16 || K % 16) return -1;
+  return (long long)N * K * 2;
+}
+
+extern "C" int b200_gemm_tc_pack_weight(const float* w, int N, int K, long long stride_n, long long stride_k, void* packed,
+                                        void* stream) {
+  B200_REQUIRE(w && packed, "gemm_tc_pack_weight: null pointer");
+  B200_REQUIRE(N > 0 && K > 0 && N % 16 == 0 && K % 16 == 0, "gemm_tc: N and K must be multiples of 16 (got %d, %d)", N, K);
+  const long long total = (long long)N * K;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
+  gemm_tc_pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed, N, K, gemm_tc_nt(N), stride_n, stride_k);
+  B200_LAUNCH_CHECK("gemm_tc_pack_weight_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
+                            const void* res, const int32_t* row_map, void* y, float* stats, void* stream) {
+  B200_REQUIRE(desc && x && packed_w && y, "gemm_tc: null pointer");
+  const b200_gemm_tc_desc& d = *desc;
+  B200_REQUIRE(d.Nb > 0 && d.S > 0 && d.S_out > 0, "gemm_tc: empty problem");
+  B200_REQUIRE(d.K > 0 && d.K % 16 == 0 && d.N > 0 && d.N % 16 == 0, "gemm_tc: N and K must be multiples of 16 (got %d, %d)", d.N, d.K);
+  B200_REQUIRE(d.in_ctot % 8 == 0 && d.in_coff % 8 == 0 && d.in_coff + d.K <= d.in_ctot, "gemm_tc: bad input channel slice");
+  B200_REQUIRE(d.mode >= 0 && d.mode <= 2, "gemm_tc: mode must be 0 (rows), 1 (row map) or 2 (2x upsample scatter)");
+  B200_REQUIRE(d.mode != 1 || row_map, "gemm_tc: mode 1 needs a row map");
+  const int cout = d.mode == 2 ? d.N / 8 : d.N;
+  B200_REQUIRE(d.mode != 2 || (d.N % 8 == 0 && cout % 8 == 0 && (long long)d.D * d.H * d.W == d.S && d.S_out == 8LL * d.S),
+               "gemm_tc: upsample scatter needs N = 8*Cout, S = D*H*W and S_out = 8*S");
+  B200_REQUIRE(d.out_ctot % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + cout <= d.out_ctot, "gemm_tc: bad output channel slice");
+  B200_REQUIRE(!res || (d.res_ctot % 8 == 0 && d.res_coff % 8 == 0 && d.res_coff + cout <= d.res_ctot), "gemm_tc: bad residual channel slice");
+  B200_REQUIRE(d.act == 0 || d.act == 4, "gemm_tc: activation must be 0 (none) or 4 (gelu)");
+  const int NT = gemm_tc_nt(d.N);
+  EncodeTiledFn enc = get_encode_tiled();
+  B200_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap tmap;
+  cuuint64_t gdim[4] = {8, (cuuint64_t)d.S, (cuuint64_t)(d.in_ctot / 8), (cuuint64_t)d.Nb};
+  cuuint64_t gstr[3] = {16, (cuuint64_t)d.S * 16, (cuuint64_t)d.S * 16 * (cuuint64_t)(d.in_ctot / 8)};
+  cuuint32_t box[4] = {8, 128, (cuuint32_t)(kGemmK16PerStage * 2), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  GemmTcParams p;
+  p.d = d; p.w = (const __half*)packed_w; p.bias = bias; p.y = (__half*)y; p.res = (const __half*)res; p.stats = stats;
+  p.row_map = row_map; p.NT = NT;
+  p.tmem_cols = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
+  const int smem = kGemmStages * (kGemmAStage + kGemmK16PerStage * NT * 32) + 128 + 2 * NT * 4 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(d.S, 128), d.N / NT, d.Nb);
+  B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_tc: grid too large");
+  gemm_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmap, p);
+  B200_LAUNCH_CHECK("gemm_tc_kernel");
+  return B200_OK;
+}

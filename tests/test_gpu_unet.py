@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from monai_b200.inferers import sliding_window_inference
-from monai_b200.networks.nets import UNet
+from monai_b200.networks.nets import BasicUNet, UNet
 from oracle import networks as onet
 from oracle import sliding_window as osw
 from weights import fill_state_dict
@@ -60,3 +60,16 @@ def test_config_c1_style_sliding_window_unet_fp32_vs_oracle():
     got = sliding_window_inference(x.to(DEV), (32, 32, 32), 4, net, 0.25, "constant")
     err = np.abs(got.cpu().numpy() - want).max() / np.abs(want).max()
     assert err < 1e-3, err
+
+
+def test_basic_unet_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "basic_unet_tiny.npz"))
+    net = _build(lambda: BasicUNet(3, 1, 2, features=(4, 4, 8, 8, 16, 4)), 3)
+    y = net(torch.from_numpy(g["x"]).to(DEV))
+    err = np.abs(y.cpu().numpy() - g["y"]).max() / np.abs(g["y"]).max()
+    assert err < 1e-3, err
+    # odd input size exercises the replicate-pad branch of UpCat (basic_unet.py:165-170)
+    x = torch.randn(1, 1, 36, 40, 44, generator=torch.Generator().manual_seed(9))
+    ref = onet.basic_unet_forward({k: v.float().cpu() for k, v in net.state_dict().items()}, x).numpy()
+    y = net(x.to(DEV)).cpu().numpy()
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-3

@@ -136,3 +136,12 @@ def test_unet_oracle_matches_reference_fixture(golden_dir):
         sd = _my_state_dict(factory, seed)
         y = onet.unet_forward(sd, torch.from_numpy(g["x"]), strides)
         np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-4, atol=1e-5, err_msg=name)
+
+
+def test_basic_unet_oracle_matches_reference_fixture(golden_dir):
+    from monai_b200.networks.nets import BasicUNet
+
+    g = _npz(golden_dir, "basic_unet_tiny.npz")
+    sd = _my_state_dict(lambda: BasicUNet(3, 1, 2, features=(4, 4, 8, 8, 16, 4)), 3)
+    y = onet.basic_unet_forward(sd, torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-4, atol=1e-5)
