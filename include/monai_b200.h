@@ -152,7 +152,7 @@ typedef struct b200_gemm_tc_desc {
   int out_ctot, out_coff;   /* destination channel slice */
   int res_ctot, res_coff;   /* residual (added before the store), indexed like the destination */
   long long S_out;          /* rows per batch item of the destination (== S unless mode 1/2) */
-  int mode;                 /* 0: row r -> r; 1: row r -> row_map[n*S + r] (-1 = drop); 2: ConvTranspose k2 s2 scatter */
+  int mode;                 /* 0: row r -> r; 1: row r -> row_map[r] (-1 = drop; shared by batch items); 2: ConvTranspose k2 s2 scatter */
   int act;                  /* 0 none, 4 GELU(erf) */
   int D, H, W;              /* mode 2: source grid (S == D*H*W); destination grid is (2D,2H,2W) */
 } b200_gemm_tc_desc;

@@ -340,3 +340,93 @@ def cat_channels(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
         copy_channels(t.reshape(N, t.shape[1], *sp3), out, off)
         off += int(t.shape[1])
     return out.reshape(N, ctot, *sp)
+
+
+def gemm_tc_pack_weight(w2d: torch.Tensor) -> torch.Tensor:
+    """Pack W[N,K] (any float dtype, device) into the UMMA B-operand image used by gemm_tc."""
+    L.require_cuda(w2d)
+    w32 = w2d.detach().float().contiguous()
+    N, Kd = w32.shape
+    nbytes = L.load().b200_gemm_tc_weight_bytes(N, Kd)
+    if nbytes < 0:
+        raise ValueError(f"gemm_tc needs N and K multiples of 16, got {N}, {Kd}")
+    packed = torch.empty(nbytes // 2, device=w32.device, dtype=torch.float16)
+    _call("gemm_tc_pack_weight", L.ptr(w32), N, Kd, Kd, 1, L.ptr(packed), L.stream_ptr(w32.device))
+    return packed
+
+
+def gemm_tc(
+    x: NC8, packed_w: torch.Tensor, Kd: int, N: int, bias: torch.Tensor | None = None, in_coff: int = 0,
+    out: NC8 | None = None, out_coff: int = 0, res: NC8 | None = None, res_coff: int = 0, row_map: torch.Tensor | None = None,
+    out_sp: Sequence[int] | None = None, mode: int = 0, act: int = L.ACT_NONE, want_stats: bool = False,
+) -> tuple[NC8, torch.Tensor | None]:
+    """y = [res +] act(x W^T + b).  mode 0: rows map to rows; mode 1: rows scattered through row_map into a
+    destination with spatial shape out_sp; mode 2: ConvTranspose k2 s2 (N = 8*Cout, destination 2x upsampled)."""
+    cout = N // 8 if mode == 2 else N
+    if out is None:
+        sp = tuple(out_sp) if out_sp is not None else (tuple(2 * s for s in x.sp) if mode == 2 else x.sp)
+        out = NC8(x.N, cout, sp, x.buf.device)
+    stats = torch.zeros((x.N * N, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    d = L.GemmTcDesc(
+        x.N, x.S, Kd, N, x.C, in_coff, out.C, out_coff, res.C if res is not None else 0, res_coff, out.S, mode, act,
+        x.sp[0], x.sp[1], x.sp[2],
+    )
+    _call("gemm_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(res.buf) if res is not None else None,
+          L.ptr(row_map), L.ptr(out.buf), L.ptr(stats), L.stream_ptr(x.buf.device),
+          flops=2.0 * x.N * x.S * Kd * N, nbytes=float(x.N * x.S * (Kd + N) * 2) + _nb(packed_w))
+    return out, stats
+
+
+def layernorm_nc8(x: NC8, gamma: torch.Tensor | None, beta: torch.Tensor | None, eps: float = 1e-5, src: torch.Tensor | None = None,
+                  out_sp: Sequence[int] | None = None, out: NC8 | None = None) -> NC8:
+    """LayerNorm over channels; with `src` (int32 [S_out]) the output rows are gathered (−1 = zero row)."""
+    if out is None:
+        out = NC8(x.N, x.C, tuple(out_sp) if out_sp is not None else x.sp, x.buf.device)
+    g = None if gamma is None else gamma.detach().float().contiguous()
+    b = None if beta is None else beta.detach().float().contiguous()
+    _call("layernorm_nc8", L.ptr(x.buf), x.N, x.C, x.S, L.ptr(src), out.S, L.ptr(g), L.ptr(b), float(eps), L.ptr(out.buf), L.stream_ptr(x.buf.device),
+          nbytes=float(x.N * x.C * (x.S + out.S) * 2))
+    return out
+
+
+def patch_merge_ln_nc8(x: NC8, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, v2: bool = False) -> NC8:
+    sp2 = tuple((s + 1) // 2 for s in x.sp)
+    out = NC8(x.N, 8 * x.C, sp2, x.buf.device)
+    g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+    _call("patch_merge_ln_nc8", L.ptr(x.buf), x.N, x.C, x.sp[0], x.sp[1], x.sp[2], L.ptr(g), L.ptr(b), float(eps), int(v2), L.ptr(out.buf), L.stream_ptr(x.buf.device))
+    return out
+
+
+def window_attention_nc8(qkv: NC8, Cc: int, heads: int, nW: int, n: int, scale: float, biasT: torch.Tensor, region: torch.Tensor | None) -> NC8:
+    out = NC8(qkv.N, Cc, qkv.sp, qkv.buf.device)
+    _call("window_attention_nc8", L.ptr(qkv.buf), qkv.N, Cc, heads, nW, n, float(scale), L.ptr(biasT), L.ptr(region), L.ptr(out.buf), L.stream_ptr(qkv.buf.device),
+          flops=4.0 * qkv.N * nW * heads * n * n * 16)
+    return out
+
+
+def conv_cin1_nc8(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, k: int, stride: int, pad: int,
+                  out: NC8 | None = None, out_coff: int = 0, want_stats: bool = False) -> tuple[NC8, torch.Tensor | None]:
+    """x [N,1,D,H,W] (f16/f32) -> NC8 with Cout channels."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    N, _, D, H, W = x.shape
+    Cout = weight.shape[0]
+    sp = tuple((s + 2 * pad - k) // stride + 1 for s in (D, H, W))
+    if out is None:
+        out = NC8(N, Cout, sp, x.device)
+    w32 = weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    stats = torch.zeros((N * Cout, 2), device=x.device, dtype=torch.float32) if want_stats else None
+    _call("conv_cin1_nc8", L.ptr(x), L.dt(x), N, D, H, W, L.ptr(w32), L.ptr(b32), Cout, k, stride, pad, L.ptr(out.buf), out.C, out_coff, L.ptr(stats), L.stream_ptr(x.device),
+          flops=2.0 * N * sp[0] * sp[1] * sp[2] * Cout * k**3)
+    return out, stats
+
+
+def head_conv_nc8(x: NC8, weight: torch.Tensor, bias: torch.Tensor | None, out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    Cout = weight.shape[0]
+    w32 = weight.detach().float().reshape(Cout, -1).contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    y = torch.empty((x.N, Cout, *x.sp), device=x.buf.device, dtype=out_dtype)
+    _call("head_conv_nc8", L.ptr(x.buf), x.N, x.C, x.S, L.ptr(w32), L.ptr(b32), Cout, L.ptr(y), L.dt(y), L.stream_ptr(x.buf.device))
+    return y

@@ -50,6 +50,14 @@ class ConvTcDesc(C.Structure):
     ]
 
 
+class GemmTcDesc(C.Structure):
+    _fields_ = [
+        ("Nb", i32), ("S", i32), ("K", i32), ("N", i32), ("in_ctot", i32), ("in_coff", i32), ("out_ctot", i32),
+        ("out_coff", i32), ("res_ctot", i32), ("res_coff", i32), ("S_out", i64), ("mode", i32), ("act", i32),
+        ("D", i32), ("H", i32), ("W", i32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/monai_b200.h declares (tests check this).
 SIGNATURES = {
     "b200_abi_version": (i32, []),
@@ -69,6 +77,14 @@ SIGNATURES = {
     "b200_conv3x3x3_tc_weight_bytes": (i64, [i32, i32]),
     "b200_conv3x3x3_tc_pack_weight": (i32, [vp, i32, i32, vp, vp]),
     "b200_conv3x3x3_tc": (i32, [C.POINTER(ConvTcDesc), vp, vp, vp, vp, vp, vp]),
+    "b200_gemm_tc_weight_bytes": (i64, [i32, i32]),
+    "b200_gemm_tc_pack_weight": (i32, [vp, i32, i32, i64, i64, vp, vp]),
+    "b200_gemm_tc": (i32, [C.POINTER(GemmTcDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b200_layernorm_nc8": (i32, [vp, i32, i32, i64, vp, i64, vp, vp, f32, vp, vp]),
+    "b200_patch_merge_ln_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp]),
+    "b200_window_attention_nc8": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
+    "b200_conv_cin1_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "b200_head_conv_nc8": (i32, [vp, i32, i32, i64, vp, vp, i32, vp, i32, vp]),
     "b200_norm_act_nc8": (i32, [vp, i32, i32, i32, i32, i64, vp, f32, vp, i32, i32, vp, i32, f32, vp, i32, i32, vp]),
 }
 

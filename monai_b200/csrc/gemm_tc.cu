@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     const bool row_ok = row < d.S;
     // destination row (identity, table lookup, or 2x-upsample scatter computed per tap below)
     long long drow = row;
-    if (row_ok && p.row_map) drow = p.row_map[(long long)n * d.S + row];
+    if (row_ok && p.row_map) drow = p.row_map[row];  // the map is shared by all batch items
     const bool dst_ok = row_ok && drow >= 0;
     int vz = 0, vy = 0, vx = 0;
     if (d.mode == 2 && row_ok) { vx = row % d.W; vy = (row / d.W) % d.H; vz = row / (d.W * d.H); }

@@ -1,0 +1,2 @@
+from .meta_tensor import MetaTensor
+from .utils import compute_importance_map, dense_patch_slices, get_valid_patch_size

@@ -1,0 +1,85 @@
+"""Minimal MetaTensor: a torch.Tensor subclass carrying `.affine` (4x4 float64), `.meta` and `.applied_operations`.
+
+The reference's MetaTensor (monai/data/meta_tensor.py:52) is part of the drop-in *boundary*, not of the hot path: when
+MONAI itself is importable its MetaTensor can be passed to every monai_b200 transform / inferer (they duck-type on
+`.affine`, `.meta`, `copy_meta_from`).  This class exists so the package is usable stand-alone (e.g. on the GPU box).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any
+
+import torch
+
+__all__ = ["MetaTensor", "is_meta", "get_affine", "rewrap"]
+
+
+class MetaTensor(torch.Tensor):
+    @staticmethod
+    def __new__(cls, x, affine=None, meta: dict | None = None, applied_operations: list | None = None, *args, **kwargs):
+        t = torch.as_tensor(x, *args, **kwargs)
+        return t.as_subclass(cls)
+
+    def __init__(self, x, affine=None, meta: dict | None = None, applied_operations: list | None = None, *args, **kwargs) -> None:
+        self.meta: dict[str, Any] = dict(meta) if meta is not None else dict(getattr(x, "meta", {}) or {})
+        self.applied_operations: list = list(applied_operations) if applied_operations is not None else list(getattr(x, "applied_operations", []) or [])
+        if affine is not None:
+            self.affine = affine
+        elif "affine" not in self.meta:
+            self.affine = torch.eye(4, dtype=torch.float64)
+
+    @property
+    def affine(self) -> torch.Tensor:
+        return self.meta.get("affine", torch.eye(4, dtype=torch.float64))
+
+    @affine.setter
+    def affine(self, d) -> None:
+        self.meta["affine"] = torch.as_tensor(d, dtype=torch.float64, device="cpu")
+
+    def as_tensor(self) -> torch.Tensor:
+        return self.as_subclass(torch.Tensor)
+
+    def copy_meta_from(self, other, copy_attr: bool = True):
+        self.meta = copy.deepcopy(other.meta) if copy_attr else dict(other.meta)
+        self.applied_operations = copy.deepcopy(other.applied_operations) if copy_attr else list(getattr(other, "applied_operations", []))
+        return self
+
+    def peek_pending_shape(self):
+        return tuple(self.shape[1:])
+
+    def peek_pending_affine(self):
+        return self.affine
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        # metadata does not propagate through arbitrary torch ops here: results are plain tensors unless re-wrapped
+        ret = super().__torch_function__(func, types, args, kwargs or {})
+        return ret
+
+    def __repr__(self, **kw) -> str:  # pragma: no cover
+        return f"MetaTensor({self.as_tensor()!r}, affine={self.affine.tolist()})"
+
+
+def is_meta(x) -> bool:
+    return hasattr(x, "meta") and hasattr(x, "copy_meta_from")
+
+
+def get_affine(x):
+    """4x4 (or (r+1)x(r+1)) float64 affine of a MetaTensor-like object, or None for plain tensors."""
+    if not is_meta(x):
+        return None
+    a = x.peek_pending_affine() if hasattr(x, "peek_pending_affine") else x.affine
+    return torch.as_tensor(a, dtype=torch.float64).cpu()
+
+
+def rewrap(out: torch.Tensor, like, affine=None, applied=None):
+    """Wrap `out` with the metadata of `like` (same class as `like`), optionally replacing the affine."""
+    if not is_meta(like):
+        return out
+    w = type(like)(out)
+    w.copy_meta_from(like, copy_attr=True)
+    if affine is not None:
+        w.affine = torch.as_tensor(affine, dtype=torch.float64)
+    if applied is not None:
+        w.applied_operations = list(w.applied_operations) + [applied]
+    return w

@@ -1,2 +1,3 @@
 from .basic_unet import BasicUNet, BasicUnet, Basicunet, basicunet
 from .unet import UNet, Unet
+from .swin_unetr import SwinUNETR

@@ -1,0 +1,476 @@
+"""`SwinUNETR` (monai/networks/nets/swin_unetr.py:45-330, 919-1075) on tcgen05 tensor cores.
+
+The module tree only holds parameters under the reference's names (159 state_dict keys for the default config:
+`swinViT.layers1.0.blocks.0.attn.qkv.weight`, `encoder1.layer.conv1.conv.weight`, `decoder5.transp_conv.conv.weight`,
+`out.conv.conv.bias`, ...), so reference checkpoints load unchanged.  `forward` never calls a torch op on activations:
+the whole network runs on fp16 channel-blocked ("NC8") buffers through the C ABI --
+
+  * 3x3x3 convolutions: implicit GEMM on tcgen05 (`b200_conv3x3x3_tc`), InstanceNorm partial sums in the epilogue;
+  * Linear / 1x1x1 conv / ConvTranspose k2 s2: `b200_gemm_tc` (bias, GELU, residual, window-reverse scatter,
+    2x upsample scatter fused in the epilogue);
+  * LayerNorm + pad + cyclic shift + window partition: one gather kernel (`b200_layernorm_nc8`);
+  * windowed attention with relative-position bias and shift mask: `b200_window_attention_nc8`;
+  * PatchMerging gather + LayerNorm, the single-channel stems and the output head: dedicated kernels.
+
+Skip concatenations are zero-copy: producers write straight into channel slices of the decoder's input buffer.
+
+Supported on this path: spatial_dims=3, feature_size % 48 == 0 with head_dim 16 (the default num_heads for
+feature_size 48), norm_name="instance" (non-affine), downsample "merging"/"mergingv2", use_v2=False, inference only.
+"""
+from __future__ import annotations
+
+import itertools
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import _kernels as K
+from ... import _lib as L
+from ..blocks.convolutions import Convolution
+
+__all__ = ["SwinUNETR", "PatchMerging", "PatchMergingV2", "window_plan"]
+
+
+def _rep(v, n):
+    return tuple(v) if isinstance(v, (list, tuple)) else (v,) * n
+
+
+# ----------------------------------------------------------------------------------------- parameter containers
+class PatchEmbed(nn.Module):
+    """monai/networks/blocks/patchembedding.py:141-219 (Conv3d k=s=patch_size, optional LayerNorm)."""
+
+    def __init__(self, patch_size, in_chans: int, embed_dim: int, norm_layer=None):
+        super().__init__()
+        self.patch_size = patch_size
+        self.embed_dim = embed_dim
+        self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+
+class MLPBlock(nn.Module):
+    """monai/networks/blocks/mlp.py:25-80 with dropout_mode="swin": linear1 -> GELU -> linear2."""
+
+    def __init__(self, hidden_size: int, mlp_dim: int):
+        super().__init__()
+        self.linear1 = nn.Linear(hidden_size, mlp_dim)
+        self.linear2 = nn.Linear(mlp_dim, hidden_size)
+        self.fn = nn.GELU()
+
+
+class WindowAttention(nn.Module):
+    """swin_unetr.py:426-532 (parameters + the relative_position_index buffer)."""
+
+    def __init__(self, dim: int, num_heads: int, window_size: Sequence[int], qkv_bias: bool = False):
+        super().__init__()
+        self.dim, self.window_size, self.num_heads = dim, tuple(window_size), num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        ws = self.window_size
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws[0] - 1) * (2 * ws[1] - 1) * (2 * ws[2] - 1), num_heads))
+        coords = torch.stack(torch.meshgrid(torch.arange(ws[0]), torch.arange(ws[1]), torch.arange(ws[2]), indexing="ij")).flatten(1)
+        rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += ws[0] - 1
+        rel[:, :, 1] += ws[1] - 1
+        rel[:, :, 2] += ws[2] - 1
+        rel[:, :, 0] *= (2 * ws[1] - 1) * (2 * ws[2] - 1)
+        rel[:, :, 1] *= 2 * ws[2] - 1
+        self.register_buffer("relative_position_index", rel.sum(-1))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+
+class SwinTransformerBlock(nn.Module):
+    def __init__(self, dim, num_heads, window_size, shift_size, mlp_ratio=4.0, qkv_bias=True, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim, self.num_heads, self.window_size, self.shift_size = dim, num_heads, tuple(window_size), tuple(shift_size)
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, num_heads, window_size, qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = MLPBlock(dim, int(dim * mlp_ratio))
+
+
+class PatchMergingV2(nn.Module):
+    """swin_unetr.py:701-746 (itertools.product slice order)."""
+
+    v2 = True
+
+    def __init__(self, dim: int, norm_layer=nn.LayerNorm, spatial_dims: int = 3):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(8 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(8 * dim)
+
+
+class PatchMerging(PatchMergingV2):
+    """swin_unetr.py:749-773 (the v0.9.0 slice order x0..x7)."""
+
+    v2 = False
+
+
+MERGING_MODE = {"merging": PatchMerging, "mergingv2": PatchMergingV2}
+
+
+class BasicLayer(nn.Module):
+    def __init__(self, dim, depth, num_heads, window_size, mlp_ratio, qkv_bias, norm_layer, downsample):
+        super().__init__()
+        self.window_size = tuple(window_size)
+        self.shift_size = tuple(i // 2 for i in window_size)
+        self.no_shift = tuple(0 for _ in window_size)
+        self.depth = depth
+        self.blocks = nn.ModuleList(
+            [
+                SwinTransformerBlock(dim, num_heads, self.window_size, self.no_shift if i % 2 == 0 else self.shift_size, mlp_ratio, qkv_bias, norm_layer)
+                for i in range(depth)
+            ]
+        )
+        self.downsample = downsample(dim=dim, norm_layer=norm_layer, spatial_dims=3) if downsample is not None else None
+
+
+class SwinTransformer(nn.Module):
+    def __init__(self, in_chans, embed_dim, window_size, patch_size, depths, num_heads, mlp_ratio=4.0, qkv_bias=True,
+                 norm_layer=nn.LayerNorm, patch_norm=False, downsample="merging"):
+        super().__init__()
+        self.num_layers = len(depths)
+        self.embed_dim, self.patch_norm, self.window_size, self.patch_size = embed_dim, patch_norm, tuple(window_size), tuple(patch_size)
+        self.patch_embed = PatchEmbed(self.patch_size, in_chans, embed_dim, norm_layer if patch_norm else None)
+        self.pos_drop = nn.Dropout(p=0.0)
+        self.layers1, self.layers2, self.layers3, self.layers4 = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        down = MERGING_MODE[downsample] if isinstance(downsample, str) else downsample
+        for i in range(self.num_layers):
+            layer = BasicLayer(int(embed_dim * 2**i), depths[i], num_heads[i], self.window_size, mlp_ratio, qkv_bias, norm_layer, down)
+            (self.layers1, self.layers2, self.layers3, self.layers4)[i].append(layer)
+        self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
+
+
+class UnetResBlock(nn.Module):
+    """monai/networks/blocks/dynunet_block.py:25-111 (containers; kernel 3, stride 1, instance norm, LeakyReLU 0.01)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        kw = dict(strides=1, act=None, norm=None, dropout=None, bias=False, conv_only=False)
+        self.conv1 = Convolution(3, in_channels, out_channels, kernel_size=3, padding=1, **kw)
+        self.conv2 = Convolution(3, out_channels, out_channels, kernel_size=3, padding=1, **kw)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.01, inplace=True)
+        self.norm1 = nn.InstanceNorm3d(out_channels)
+        self.norm2 = nn.InstanceNorm3d(out_channels)
+        self.downsample = in_channels != out_channels
+        if self.downsample:
+            self.conv3 = Convolution(3, in_channels, out_channels, kernel_size=1, padding=0, **kw)
+            self.norm3 = nn.InstanceNorm3d(out_channels)
+
+
+class UnetrBasicBlock(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.layer = UnetResBlock(in_channels, out_channels)
+
+
+class UnetrUpBlock(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.transp_conv = Convolution(3, in_channels, out_channels, strides=2, kernel_size=2, act=None, norm=None, dropout=None,
+                                       bias=False, conv_only=True, is_transposed=True, padding=0, output_padding=0)
+        self.conv_block = UnetResBlock(out_channels + out_channels, out_channels)
+
+
+class UnetOutBlock(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.conv = Convolution(3, in_channels, out_channels, strides=1, kernel_size=1, act=None, norm=None, dropout=None, bias=True,
+                                conv_only=False, padding=0)
+
+
+# --------------------------------------------------------------------------------------------- host-side planning
+def _get_window_size(x_size, window_size, shift_size):
+    """swin_unetr.py:399-423: clamp the window to the feature map and drop the shift on clamped axes."""
+    ws, ss = list(window_size), list(shift_size)
+    for i in range(len(x_size)):
+        if x_size[i] <= window_size[i]:
+            ws[i] = x_size[i]
+            ss[i] = 0
+    return tuple(ws), tuple(ss)
+
+
+def window_plan(dims, window_size, shift_size):
+    """Index tables for pad + roll(-shift) + window_partition (swin_unetr.py:596-625) and compute_mask (779-816).
+
+    Returns (src int32 [nW*n] with -1 for zero-padded tokens, region int32 [nW, n] or None, nW, n).
+    Row r of the windowed tensor is token src[r] of the (d,h,w) grid; window_reverse + roll(+shift) + crop is the
+    inverse of the same table, so the projection GEMM scatters through it."""
+    ws, ss = _get_window_size(dims, window_size, shift_size)
+    pdims = [int(np.ceil(d / w)) * w for d, w in zip(dims, ws)]
+    grids = []
+    for ax in range(3):
+        p = np.arange(pdims[ax])                       # coordinate in the shifted, padded volume
+        o = (p + ss[ax]) % pdims[ax]                   # coordinate in the padded volume before the roll
+        grids.append((p, o))
+    P = np.stack(np.meshgrid(grids[0][0], grids[1][0], grids[2][0], indexing="ij"), -1)
+    O = np.stack(np.meshgrid(grids[0][1], grids[1][1], grids[2][1], indexing="ij"), -1)
+    valid = (O[..., 0] < dims[0]) & (O[..., 1] < dims[1]) & (O[..., 2] < dims[2])
+    lin = (O[..., 0] * dims[1] + O[..., 1]) * dims[2] + O[..., 2]
+    lin = np.where(valid, lin, -1)
+
+    def part(a):  # window_partition on a (dp,hp,wp) array
+        a = a.reshape(pdims[0] // ws[0], ws[0], pdims[1] // ws[1], ws[1], pdims[2] // ws[2], ws[2])
+        return a.transpose(0, 2, 4, 1, 3, 5).reshape(-1, ws[0] * ws[1] * ws[2])
+
+    src = part(lin).astype(np.int32)
+    region = None
+    if any(s > 0 for s in ss):
+        lab = np.zeros(pdims, dtype=np.int32)
+        for ax in range(3):
+            p = P[..., ax]
+            if ss[ax] > 0:
+                a = np.where(p < pdims[ax] - ws[ax], 0, np.where(p < pdims[ax] - ss[ax], 1, 2))
+            else:
+                a = np.zeros_like(p)  # all three slices collapse onto the whole axis: a single label
+            lab = lab * 3 + a
+        region = part(lab).astype(np.int32)
+    return src.reshape(-1), region, src.shape[0], src.shape[1]
+
+
+class _Cache:
+    """Packed weights and index tables keyed by (name, device); invalidated when a parameter is modified."""
+
+    def __init__(self):
+        self.store: dict = {}
+
+    def get(self, key, params: Sequence[torch.Tensor], build):
+        ver = tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+        hit = self.store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = build()
+        self.store[key] = (ver, val)
+        return val
+
+
+class SwinUNETR(nn.Module):
+    patch_size: int = 2
+
+    def __init__(
+        self,
+        in_channels: int,
+        out_channels: int,
+        patch_size: int = 2,
+        depths: Sequence[int] = (2, 2, 2, 2),
+        num_heads: Sequence[int] = (3, 6, 12, 24),
+        window_size: Sequence[int] | int = 7,
+        qkv_bias: bool = True,
+        mlp_ratio: float = 4.0,
+        feature_size: int = 24,
+        norm_name: tuple | str = "instance",
+        drop_rate: float = 0.0,
+        attn_drop_rate: float = 0.0,
+        dropout_path_rate: float = 0.0,
+        normalize: bool = True,
+        norm_layer: type[nn.LayerNorm] = nn.LayerNorm,
+        patch_norm: bool = False,
+        use_checkpoint: bool = False,
+        spatial_dims: int = 3,
+        downsample: str | nn.Module = "merging",
+        use_v2: bool = False,
+        img_size: Sequence[int] | int | None = None,  # accepted and ignored (older bundles pass it)
+    ) -> None:
+        super().__init__()
+        if spatial_dims not in (2, 3):
+            raise ValueError("spatial dimension should be 2 or 3.")
+        for name, v in (("dropout rate", drop_rate), ("attention dropout rate", attn_drop_rate), ("drop path rate", dropout_path_rate)):
+            if not (0 <= v <= 1):
+                raise ValueError(f"{name} should be between 0 and 1.")
+        if feature_size % 12 != 0:
+            raise ValueError("feature_size should be divisible by 12.")
+        if spatial_dims != 3 or use_v2:
+            raise NotImplementedError("monai_b200 SwinUNETR implements spatial_dims=3, use_v2=False")
+        if feature_size % 48 != 0:
+            raise NotImplementedError("monai_b200 SwinUNETR needs feature_size % 48 == 0 (tensor-core tiles need 16-channel multiples)")
+        if any((feature_size * 2**i) // h != 16 for i, h in enumerate(num_heads)):
+            raise NotImplementedError("monai_b200 window attention is specialised for head_dim 16 (num_heads = feature_size/16 * 2**stage)")
+        nn_name = norm_name if isinstance(norm_name, str) else norm_name[0]
+        if str(nn_name).lower() != "instance" or (not isinstance(norm_name, str) and norm_name[1].get("affine")):
+            raise NotImplementedError("monai_b200 SwinUNETR implements norm_name='instance' (non-affine)")
+        if patch_size != 2:
+            raise NotImplementedError("monai_b200 SwinUNETR implements patch_size=2")
+        self.patch_size = patch_size
+        self.normalize = normalize
+        self.feature_size = feature_size
+        self.out_channels = out_channels
+        self.in_channels = in_channels
+        if in_channels != 1:
+            raise NotImplementedError("monai_b200 SwinUNETR implements in_channels=1 (the configured workloads)")
+        ws = _rep(window_size, 3)
+        self.swinViT = SwinTransformer(in_channels, feature_size, ws, _rep(patch_size, 3), depths, num_heads, mlp_ratio, qkv_bias,
+                                       norm_layer, patch_norm, downsample)
+        fs = feature_size
+        self.encoder1 = UnetrBasicBlock(in_channels, fs)
+        self.encoder2 = UnetrBasicBlock(fs, fs)
+        self.encoder3 = UnetrBasicBlock(2 * fs, 2 * fs)
+        self.encoder4 = UnetrBasicBlock(4 * fs, 4 * fs)
+        self.encoder10 = UnetrBasicBlock(16 * fs, 16 * fs)
+        self.decoder5 = UnetrUpBlock(16 * fs, 8 * fs)
+        self.decoder4 = UnetrUpBlock(8 * fs, 4 * fs)
+        self.decoder3 = UnetrUpBlock(4 * fs, 2 * fs)
+        self.decoder2 = UnetrUpBlock(2 * fs, fs)
+        self.decoder1 = UnetrUpBlock(fs, fs)
+        self.out = UnetOutBlock(fs, out_channels)
+        self._cache = _Cache()
+
+    def _check_input_size(self, spatial_shape):
+        img_size = np.array(spatial_shape)
+        remainder = (img_size % np.power(self.patch_size, 5)) > 0
+        if remainder.any():
+            wrong_dims = (np.where(remainder)[0] + 2).tolist()
+            raise ValueError(
+                f"spatial dimensions {wrong_dims} of input image (spatial shape: {spatial_shape})"
+                f" must be divisible by {self.patch_size}**5."
+            )
+
+    # ----------------------------------------------------------------------------------------------- weight prep
+    def _w3(self, conv: nn.Conv3d, key: str):
+        return self._cache.get(("w3", key, conv.weight.device), [conv.weight], lambda: K.conv3x3x3_tc_pack_weight(conv.weight))
+
+    def _wlin(self, w: torch.Tensor, key: str):
+        return self._cache.get(("lin", key, w.device), [w], lambda: K.gemm_tc_pack_weight(w.reshape(w.shape[0], -1)))
+
+    def _wup(self, conv: nn.ConvTranspose3d, key: str):
+        # ConvTranspose3d weight [Cin, Cout, 2,2,2] -> GEMM W[(tap, cout), cin]
+        def build():
+            w = conv.weight.detach().float()
+            return K.gemm_tc_pack_weight(w.permute(2, 3, 4, 1, 0).reshape(8 * w.shape[1], w.shape[0]).contiguous())
+
+        return self._cache.get(("up", key, conv.weight.device), [conv.weight], build)
+
+    def _attn_tables(self, blk: SwinTransformerBlock, key: str, n: int, dev):
+        attn = blk.attn
+
+        def build():
+            idx = attn.relative_position_index[:n, :n].reshape(-1).to(attn.relative_position_bias_table.device)
+            bias = attn.relative_position_bias_table.detach().float()[idx].reshape(n, n, -1)  # [i, j, h]
+            return bias.permute(2, 1, 0).contiguous().to(dev)  # [h, j, i]: coalesced over queries i
+
+        return self._cache.get(("bias", key, n, dev), [attn.relative_position_bias_table], build)
+
+    def _plan(self, dims, ws, ss, dev):
+        def build():
+            src, region, nW, n = window_plan(dims, ws, ss)
+            return (torch.from_numpy(src).to(dev), None if region is None else torch.from_numpy(region).to(dev), nW, n)
+
+        return self._cache.get(("plan", tuple(dims), tuple(ws), tuple(ss), dev), [], build)
+
+    # ------------------------------------------------------------------------------------------------- sub-graphs
+    def _res_block(self, x: K.NC8, cin: int, in_coff: int, blk: UnetResBlock, key: str, out: K.NC8 | None = None, out_coff: int = 0,
+                   x_in_raw: torch.Tensor | None = None) -> K.NC8:
+        """UnetResBlock.forward (dynunet_block.py:97-111) on NC8 buffers; `out` may be a slice of a concat buffer."""
+        cout = blk.conv1.conv.out_channels
+        if x_in_raw is not None:  # single input channel: direct stem kernels read the raw NCDHW window
+            y1, st1 = K.conv_cin1_nc8(x_in_raw, blk.conv1.conv.weight, None, 3, 1, 1, want_stats=True)
+        else:
+            y1, st1 = K.conv3x3x3_tc(x, self._w3(blk.conv1.conv, key + ".c1"), cin, cout, in_coff=in_coff, want_stats=True)
+        K.norm_act_nc8(y1, cout, st1, act=L.ACT_LEAKY, slope=0.01, out=y1)
+        y2, st2 = K.conv3x3x3_tc(y1, self._w3(blk.conv2.conv, key + ".c2"), cout, cout, want_stats=True)
+        if out is None:
+            out = K.NC8(y2.N, cout, y2.sp, y2.buf.device)
+        if hasattr(blk, "conv3"):
+            if x_in_raw is not None:
+                y3, st3 = K.conv_cin1_nc8(x_in_raw, blk.conv3.conv.weight, None, 1, 1, 0, want_stats=True)
+            else:
+                y3, st3 = K.gemm_tc(x, self._wlin(blk.conv3.conv.weight, key + ".c3"), cin, cout, in_coff=in_coff, want_stats=True)
+            K.norm_act_nc8(y2, cout, st2, res=y3, res_stats=st3, act=L.ACT_LEAKY, slope=0.01, out=out, out_coff=out_coff)
+        else:
+            K.norm_act_nc8(y2, cout, st2, res=x, res_coff=in_coff, act=L.ACT_LEAKY, slope=0.01, out=out, out_coff=out_coff)
+        return out
+
+    def _swin_stage(self, cur: K.NC8, layer: BasicLayer, key: str) -> K.NC8:
+        dims, C = cur.sp, cur.C
+        dev = cur.buf.device
+        for bi, blk in enumerate(layer.blocks):
+            ws, ss = _get_window_size(dims, blk.window_size, blk.shift_size)
+            src, region, nW, n = self._plan(dims, ws, ss, dev)
+            bkey = f"{key}.b{bi}"
+            xw = K.layernorm_nc8(cur, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, src=src, out_sp=(1, nW, n))
+            qkv, _ = K.gemm_tc(xw, self._wlin(blk.attn.qkv.weight, bkey + ".qkv"), C, 3 * C, bias=blk.attn.qkv.bias)
+            att = K.window_attention_nc8(qkv, C, blk.num_heads, nW, n, blk.attn.scale, self._attn_tables(blk, bkey, n, dev), region if any(s > 0 for s in ss) else None)
+            # x = shortcut + window_reverse(proj(att)): scattered back through the same table, residual fused
+            x1, _ = K.gemm_tc(att, self._wlin(blk.attn.proj.weight, bkey + ".proj"), C, C, bias=blk.attn.proj.bias, res=cur, row_map=src, out_sp=dims, mode=1)
+            y = K.layernorm_nc8(x1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+            h, _ = K.gemm_tc(y, self._wlin(blk.mlp.linear1.weight, bkey + ".fc1"), C, blk.mlp.linear1.out_features, bias=blk.mlp.linear1.bias, act=L.ACT_GELU)
+            cur, _ = K.gemm_tc(h, self._wlin(blk.mlp.linear2.weight, bkey + ".fc2"), blk.mlp.linear1.out_features, C, bias=blk.mlp.linear2.bias, res=x1)
+        if layer.downsample is not None:
+            ds = layer.downsample
+            m = K.patch_merge_ln_nc8(cur, ds.norm.weight, ds.norm.bias, ds.norm.eps, v2=ds.v2)
+            cur, _ = K.gemm_tc(m, self._wlin(ds.reduction.weight, key + ".red"), 8 * C, 2 * C)
+        return cur
+
+    def _proj_out(self, t: K.NC8, out: K.NC8 | None = None, out_coff: int = 0) -> K.NC8:
+        """SwinTransformer.proj_out (swin_unetr.py:1040-1053): channel LayerNorm without affine when normalize=True."""
+        if not self.normalize:
+            if out is None:
+                return t
+            return K.norm_act_nc8(t, t.C, None, out=out, out_coff=out_coff)
+        if out is None:
+            return K.layernorm_nc8(t, None, None, 1e-5)
+        # LayerNorm into a private buffer, then place into the concat slice (layernorm writes whole buffers)
+        tmp = K.layernorm_nc8(t, None, None, 1e-5)
+        return K.norm_act_nc8(tmp, t.C, None, out=out, out_coff=out_coff)
+
+    def forward(self, x_in: torch.Tensor) -> torch.Tensor:
+        if not x_in.is_cuda:
+            raise RuntimeError("monai_b200.SwinUNETR runs on CUDA tensors only (there is no CPU fallback)")
+        self._check_input_size(x_in.shape[2:])
+        if x_in.shape[1] != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channel(s), got {x_in.shape[1]}")
+        if x_in.dtype not in (torch.float16, torch.float32):
+            raise TypeError(f"SwinUNETR takes float16/float32 inputs, got {x_in.dtype}")
+        with torch.no_grad():
+            x_in = x_in.contiguous()
+            n = x_in.shape[0]
+            dev = x_in.device
+            fs = self.feature_size
+            sp0 = tuple(int(s) for s in x_in.shape[2:])
+            sp = [tuple(s // (2 ** (i + 1)) for s in sp0) for i in range(5)]  # resolutions of hidden states 0..4
+            vit = self.swinViT
+
+            # decoder input buffers: [upsampled | skip] channel slices, written in place by their producers
+            cat1 = K.NC8(n, 2 * fs, sp0, dev)       # decoder1: [up(dec0) | enc0]
+            cat2 = K.NC8(n, 2 * fs, sp[0], dev)     # decoder2: [up(dec1) | enc1]
+            cat3 = K.NC8(n, 4 * fs, sp[1], dev)     # decoder3: [up(dec2) | enc2]
+            cat4 = K.NC8(n, 8 * fs, sp[2], dev)     # decoder4: [up(dec3) | enc3]
+            cat5 = K.NC8(n, 16 * fs, sp[3], dev)    # decoder5: [up(dec4) | hidden3]
+
+            # ---- Swin transformer encoder (swin_unetr.py:1055-1075)
+            pe = vit.patch_embed
+            t0, _ = K.conv_cin1_nc8(x_in, pe.proj.weight, pe.proj.bias, 2, 2, 0)
+            if pe.norm is not None:
+                t0 = K.layernorm_nc8(t0, pe.norm.weight, pe.norm.bias, pe.norm.eps)
+            h0 = self._proj_out(t0)
+            t1 = self._swin_stage(t0, vit.layers1[0], "l1")
+            h1 = self._proj_out(t1)
+            t2 = self._swin_stage(t1, vit.layers2[0], "l2")
+            h2 = self._proj_out(t2)
+            t3 = self._swin_stage(t2, vit.layers3[0], "l3")
+            self._proj_out(t3, out=cat5, out_coff=8 * fs)
+            t4 = self._swin_stage(t3, vit.layers4[0], "l4")
+            h4 = self._proj_out(t4)
+
+            # ---- CNN encoders on the hidden states (swin_unetr.py:319-324)
+            self._res_block(None, 1, 0, self.encoder1.layer, "enc1", out=cat1, out_coff=fs, x_in_raw=x_in)
+            self._res_block(h0, fs, 0, self.encoder2.layer, "enc2", out=cat2, out_coff=fs)
+            self._res_block(h1, 2 * fs, 0, self.encoder3.layer, "enc3", out=cat3, out_coff=2 * fs)
+            self._res_block(h2, 4 * fs, 0, self.encoder4.layer, "enc4", out=cat4, out_coff=4 * fs)
+            dec4 = self._res_block(h4, 16 * fs, 0, self.encoder10.layer, "enc10")
+
+            # ---- decoders: ConvTranspose k2 s2 scatter into the concat buffer, then the residual block
+            def up(dec_in: K.NC8, cin: int, block: UnetrUpBlock, cat: K.NC8, key: str) -> K.NC8:
+                cout = block.transp_conv.conv.out_channels
+                K.gemm_tc(dec_in, self._wup(block.transp_conv.conv, key), cin, 8 * cout, out=cat, out_coff=0, mode=2)
+                return self._res_block(cat, 2 * cout, 0, block.conv_block, key + ".rb")
+
+            dec3 = up(dec4, 16 * fs, self.decoder5, cat5, "dec5")
+            dec2 = up(dec3, 8 * fs, self.decoder4, cat4, "dec4")
+            dec1 = up(dec2, 4 * fs, self.decoder3, cat3, "dec3")
+            dec0 = up(dec1, 2 * fs, self.decoder2, cat2, "dec2")
+            outb = up(dec0, fs, self.decoder1, cat1, "dec1")
+            oc = self.out.conv.conv
+            return K.head_conv_nc8(outb, oc.weight, oc.bias, out_dtype=x_in.dtype)

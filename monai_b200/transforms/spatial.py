@@ -1,0 +1,467 @@
+"""Spatial transforms with the reference's operator surface (monai/transforms/spatial/array.py, dictionary.py):
+`SpatialResample`, `Spacing`, `Spacingd`, `Resample`, `AffineGrid`, `RandAffineGrid`, `Affine`, `RandAffine`, `RandAffined`.
+
+Every resampling step is ONE launch of `b200_resample_affine`: sampling coordinates are an affine function of the
+output voxel index, so the dense coordinate grid the reference materialises (F.affine_grid, create_grid @ affine;
+3-4 x voxels x 8 bytes) and its float64 image copy never exist.  Host-side algebra (output shape, affines, RNG draw
+order) follows the reference exactly (see transforms/utils.py); metadata (`.affine`, `applied_operations`) is kept.
+Outputs are float32 like the reference (spatial/array.py:2116, functional.py:183).
+"""
+from __future__ import annotations
+
+from collections.abc import Hashable, Mapping, Sequence
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import _kernels as K
+from .. import _lib as L
+from ..data.meta_tensor import get_affine, is_meta, rewrap
+from . import utils as U
+from .transform import MapTransform, Randomizable, RandomizableTransform, Transform
+
+__all__ = ["SpatialResample", "Spacing", "Spacingd", "Resample", "AffineGrid", "RandAffineGrid", "Affine", "RandAffine", "RandAffined"]
+
+_INTERP = {"bilinear": L.INTERP_LINEAR, "linear": L.INTERP_LINEAR, "trilinear": L.INTERP_LINEAR, "nearest": L.INTERP_NEAREST, 1: L.INTERP_LINEAR, 0: L.INTERP_NEAREST}
+_PAD = {"zeros": L.PAD_ZEROS, "border": L.PAD_BORDER, "reflection": L.PAD_REFLECTION, "constant": L.PAD_ZEROS, "nearest": L.PAD_BORDER, "reflect": L.PAD_REFLECTION}
+
+
+def _mode(v) -> int:
+    key = getattr(v, "value", v)
+    key = key.lower() if isinstance(key, str) else key
+    if key not in _INTERP:
+        raise NotImplementedError(f"monai_b200 resampling implements nearest and (bi/tri)linear interpolation, got {v!r}")
+    return _INTERP[key]
+
+
+def _pad(v) -> int:
+    key = str(getattr(v, "value", v)).lower()
+    if key not in _PAD:
+        raise NotImplementedError(f"monai_b200 resampling implements zeros / border / reflection padding, got {v!r}")
+    return _PAD[key]
+
+
+def _fall_back(user, default) -> tuple[int, ...]:
+    if user is None:
+        return tuple(int(d) for d in default)
+    if not isinstance(user, (list, tuple, np.ndarray, torch.Tensor)):
+        user = (user,) * len(default)
+    return tuple(int(u) if (u is not None and u > 0) else int(d) for u, d in zip(user, default))
+
+
+def _resample(img: torch.Tensor, mat: np.ndarray, r: int, out_shape: Sequence[int], mode, padding_mode, align_corners: bool) -> torch.Tensor:
+    """img [C, *spatial(r)] (CUDA) -> float32 [C, *out_shape] through the 3-D kernel (leading singleton axes for r < 3)."""
+    if not img.is_cuda:
+        raise RuntimeError("monai_b200 spatial transforms run on CUDA tensors only (there is no CPU fallback)")
+    t = img.as_subclass(torch.Tensor) if type(img) is not torch.Tensor else img
+    if t.dtype not in (torch.float16, torch.float32):
+        t = t.float()
+    lift = 3 - r
+    extra = tuple(t.shape[1 + r:])  # additional (non-spatial) trailing dims are folded into channels
+    if extra:
+        t = t.reshape(t.shape[0], *t.shape[1 : 1 + r], -1).movedim(-1, 1).reshape(-1, *t.shape[1 : 1 + r])
+    t3 = t.reshape(t.shape[0], *([1] * lift), *t.shape[1:])
+    out3 = K.resample_affine(t3, (1,) * lift + tuple(int(s) for s in out_shape), U.lift_to_3d(mat, r).reshape(-1), _mode(mode), _pad(padding_mode), bool(align_corners))
+    out = out3.reshape(out3.shape[0], *out_shape)
+    if extra:
+        out = out.reshape(img.shape[0], -1, *out_shape).movedim(1, -1).reshape(img.shape[0], *out_shape, *extra)
+    return out
+
+
+class SpatialResample(Transform):
+    """Resample to a destination affine / shape (spatial/array.py:122-253; functional.py:68-184)."""
+
+    def __init__(self, mode="bilinear", padding_mode="border", align_corners: bool = False, dtype=np.float64, lazy: bool = False):
+        if lazy:
+            raise NotImplementedError("lazy resampling is not part of the monai_b200 hot path yet")
+        self.mode, self.padding_mode, self.align_corners, self.dtype = mode, padding_mode, align_corners, dtype
+
+    def __call__(self, img, dst_affine=None, spatial_size=None, mode=None, padding_mode=None, align_corners=None, dtype=None, lazy=None):
+        align = self.align_corners if align_corners is None else align_corners
+        src_affine_full = get_affine(img)
+        if src_affine_full is None:
+            src_affine_full = torch.eye(4, dtype=torch.float64)
+        original_shape = tuple(img.shape[1:])
+        rank = min(len(img.shape) - 1, src_affine_full.shape[0] - 1, 3)
+        if (not isinstance(spatial_size, int) or spatial_size != -1) and spatial_size is not None:
+            rank = min(len(tuple(spatial_size)), 3)
+        src_affine = U.to_affine_nd(rank, src_affine_full)
+        dst = U.to_affine_nd(rank, dst_affine) if dst_affine is not None else src_affine
+        in_size = np.asarray(original_shape[:rank])
+        if isinstance(spatial_size, int) and spatial_size == -1:
+            spatial_size = in_size
+        elif spatial_size is None and rank > 1:
+            spatial_size, _ = U.compute_shape_offset(in_size, src_affine, dst)
+        sp = np.asarray([int(s) if s >= 0 else int(d) for s, d in zip(tuple(spatial_size)[:rank], in_size)])
+        try:
+            xform = np.eye(rank + 1) if rank < 2 else np.linalg.solve(src_affine, dst)
+        except np.linalg.LinAlgError as e:
+            raise ValueError(f"src affine is not invertible {src_affine}, {dst}.") from e
+        xform = U.to_affine_nd(rank, xform)
+        unchanged = (np.allclose(src_affine, dst, atol=U.AFFINE_TOL) and np.allclose(sp, in_size)) or (
+            np.allclose(xform, np.eye(len(xform)), atol=U.AFFINE_TOL) and np.allclose(sp, in_size)
+        )
+        info = {"class": type(self).__name__, "orig_size": original_shape, "extra_info": {"src_affine": src_affine, "align_corners": align,
+                "mode": getattr(mode or self.mode, "value", mode or self.mode), "padding_mode": getattr(padding_mode or self.padding_mode, "value", padding_mode or self.padding_mode)}}
+        new_affine = None
+        if is_meta(img):
+            # track_transform_meta: affine <- affine @ xform (the voxel->world map of the resampled grid)
+            new_affine = U.to_affine_nd(len(src_affine_full) - 1, src_affine_full.numpy().copy())
+            full = np.eye(len(src_affine_full))
+            full[:rank, :rank], full[:rank, -1] = xform[:rank, :rank], xform[:rank, -1]
+            new_affine = src_affine_full.numpy() @ full if not unchanged else src_affine_full.numpy()
+        if unchanged:
+            out = (img.as_subclass(torch.Tensor) if type(img) is not torch.Tensor else img).to(torch.float32)
+            return rewrap(out, img, new_affine, info)
+        mat = U.sample_matrix_from_xform(xform, original_shape[:rank], sp, align)
+        out = _resample(img, mat, rank, tuple(int(s) for s in sp), mode or self.mode, padding_mode or self.padding_mode, align)
+        return rewrap(out, img, new_affine, info)
+
+
+class Spacing(Transform):
+    """Resample to the given voxel spacing (spatial/array.py:338-546)."""
+
+    def __init__(self, pixdim, diagonal: bool = False, mode="bilinear", padding_mode="border", align_corners: bool = False, dtype=np.float64,
+                 scale_extent: bool = False, recompute_affine: bool = False, min_pixdim=None, max_pixdim=None, lazy: bool = False):
+        self.pixdim = np.array(pixdim if isinstance(pixdim, (list, tuple, np.ndarray)) else (pixdim,), dtype=np.float64)
+        self.min_pixdim = np.array(min_pixdim if isinstance(min_pixdim, (list, tuple, np.ndarray)) else (min_pixdim,), dtype=np.float64) if min_pixdim is not None else np.array([np.nan])
+        self.max_pixdim = np.array(max_pixdim if isinstance(max_pixdim, (list, tuple, np.ndarray)) else (max_pixdim,), dtype=np.float64) if max_pixdim is not None else np.array([np.nan])
+        if min_pixdim is None:
+            self.min_pixdim = np.full(len(self.pixdim), np.nan)
+        if max_pixdim is None:
+            self.max_pixdim = np.full(len(self.pixdim), np.nan)
+        self.diagonal, self.scale_extent, self.recompute_affine = diagonal, scale_extent, recompute_affine
+        for mn, mx in zip(self.min_pixdim, self.max_pixdim):
+            if (not np.isnan(mn)) and (not np.isnan(mx)) and ((mx < mn) or (mn < 0)):
+                raise ValueError(f"min_pixdim {self.min_pixdim} must be positive, smaller than max {self.max_pixdim}.")
+        self.sp_resample = SpatialResample(mode=mode, padding_mode=padding_mode, align_corners=align_corners, dtype=dtype, lazy=lazy)
+
+    def __call__(self, data_array, mode=None, padding_mode=None, align_corners=None, dtype=None, scale_extent=None, output_spatial_shape=None, lazy=None):
+        original_shape = tuple(data_array.shape[1:])
+        sr = len(original_shape)
+        if sr <= 0:
+            raise ValueError(f"data_array must have at least one spatial dimension, got {original_shape}.")
+        input_affine = get_affine(data_array)
+        if input_affine is None:
+            import warnings
+
+            warnings.warn("`data_array` is not of type MetaTensor, assuming affine to be identity.")
+            input_affine = np.eye(sr + 1, dtype=np.float64)
+        affine_ = U.to_affine_nd(sr, input_affine)
+        out_d = self.pixdim[:sr].copy()
+        if out_d.size < sr:
+            out_d = np.append(out_d, [out_d[-1]] * (sr - out_d.size))
+        orig_d = U.affine_to_spacing(affine_, sr)
+        mins = list(self.min_pixdim[:sr]) + [np.nan] * sr
+        maxs = list(self.max_pixdim[:sr]) + [np.nan] * sr
+        for idx, _d in enumerate(orig_d):
+            target = out_d[idx]
+            mn = target if np.isnan(mins[idx]) else min(mins[idx], target)
+            mx = target if np.isnan(maxs[idx]) else max(maxs[idx], target)
+            if mn > mx:
+                raise ValueError(f"min_pixdim is larger than max_pixdim at dim {idx}: min {mn} max {mx} out {target}.")
+            out_d[idx] = _d if (mn - U.AFFINE_TOL) <= _d <= (mx + U.AFFINE_TOL) else target
+        new_affine = U.zoom_affine(affine_, out_d, diagonal=self.diagonal)
+        scale_extent = self.scale_extent if scale_extent is None else scale_extent
+        output_shape, offset = U.compute_shape_offset(original_shape, affine_, new_affine, scale_extent)
+        new_affine[:sr, -1] = offset[:sr]
+        actual_shape = list(output_shape) if output_spatial_shape is None else output_spatial_shape
+        out = self.sp_resample(data_array, dst_affine=new_affine, spatial_size=actual_shape, mode=mode, padding_mode=padding_mode,
+                               align_corners=align_corners, dtype=dtype)
+        if self.recompute_affine and is_meta(out):
+            # scale_affine(original, actual) (monai/transforms/utils.py): centre-preserving rescale of the index grid
+            r = len(original_shape)
+            scale = np.asarray([o / max(a, 1) for o, a in zip(original_shape, actual_shape)], dtype=np.float64)
+            a = np.diag(np.append(scale, 1.0))
+            a[:r, -1] = (scale - 1) / 2.0
+            out.affine = torch.as_tensor(affine_ @ a)
+        return out
+
+
+class Spacingd(MapTransform):
+    """Dictionary version (spatial/dictionary.py:365-531): every key is resampled; with `ensure_same_shape` later keys
+    whose input shape equals the first key's reuse the first key's output shape."""
+
+    def __init__(self, keys, pixdim, diagonal: bool = False, mode="bilinear", padding_mode="border", align_corners=False, dtype=np.float64,
+                 scale_extent: bool = False, recompute_affine: bool = False, min_pixdim=None, max_pixdim=None, ensure_same_shape: bool = True,
+                 allow_missing_keys: bool = False, lazy: bool = False):
+        super().__init__(keys, allow_missing_keys)
+        self.spacing_transform = Spacing(pixdim, diagonal=diagonal, recompute_affine=recompute_affine, min_pixdim=min_pixdim, max_pixdim=max_pixdim, lazy=lazy)
+        n = len(self.keys)
+        rep = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * n  # noqa: E731
+        self.mode, self.padding_mode, self.align_corners, self.dtype, self.scale_extent = rep(mode), rep(padding_mode), rep(align_corners), rep(dtype), rep(scale_extent)
+        self.ensure_same_shape = ensure_same_shape
+
+    def __call__(self, data: Mapping[Hashable, Any], lazy=None) -> dict:
+        d = dict(data)
+        _init_shape, _pixdim, should_match = None, None, False
+        output_shape_k = None
+        for i, key in enumerate(self.key_iterator(d)):
+            idx = self.keys.index(key)
+            if self.ensure_same_shape and is_meta(d[key]):
+                if _init_shape is None:
+                    _init_shape, _pixdim = tuple(d[key].shape[1:]), d[key].meta.get("pixdim") if hasattr(d[key], "meta") else None
+                else:
+                    should_match = tuple(d[key].shape[1:]) == _init_shape
+            d[key] = self.spacing_transform(
+                d[key], mode=self.mode[idx], padding_mode=self.padding_mode[idx], align_corners=self.align_corners[idx], dtype=self.dtype[idx],
+                scale_extent=self.scale_extent[idx], output_spatial_shape=output_shape_k if should_match else None,
+            )
+            if output_shape_k is None:
+                output_shape_k = tuple(d[key].shape[1:])
+        return d
+
+
+class AffineGrid(Transform):
+    """Affine matrix builder (spatial/array.py:1662-1783).  The dense grid is only materialised on request
+    (`__call__(..., grid=None)` returns (grid, affine) like the reference); the resamplers use the matrix alone."""
+
+    def __init__(self, rotate_params=None, shear_params=None, translate_params=None, scale_params=None, device=None, dtype=np.float32,
+                 align_corners: bool = False, affine=None, lazy: bool = False):
+        self.rotate_params, self.shear_params, self.translate_params, self.scale_params = rotate_params, shear_params, translate_params, scale_params
+        self.device, self.dtype, self.align_corners, self.affine = device, dtype, align_corners, affine
+
+    def matrix(self, spatial_dims: int) -> np.ndarray:
+        if self.affine is not None:
+            return U.to_affine_nd(spatial_dims, self.affine)
+        affine = np.eye(spatial_dims + 1, dtype=np.float32)
+        if self.rotate_params:
+            affine = affine @ U.create_rotate(spatial_dims, self.rotate_params)
+        if self.shear_params:
+            affine = affine @ U.create_shear(spatial_dims, self.shear_params)
+        if self.translate_params:
+            affine = affine @ U.create_translate(spatial_dims, self.translate_params)
+        if self.scale_params:
+            affine = affine @ U.create_scale(spatial_dims, self.scale_params)
+        return U.to_affine_nd(spatial_dims, affine.astype(np.float32))
+
+    def __call__(self, spatial_size=None, grid=None, lazy=None):
+        if grid is None and spatial_size is None:
+            raise ValueError("Incompatible values: grid=None and spatial_size=None.")
+        if grid is None:
+            r = len(spatial_size)
+            axes = [torch.linspace(-(d - 1.0) / 2.0, (d - 1.0) / 2.0, int(d), dtype=torch.float32) for d in spatial_size]
+            coords = torch.meshgrid(*axes, indexing="ij")
+            grid = torch.stack([*coords, torch.ones_like(coords[0])])
+        r = grid.shape[0] - 1
+        affine = torch.as_tensor(self.matrix(r), dtype=grid.dtype, device=grid.device)
+        a = affine
+        if self.align_corners:
+            sc = torch.as_tensor(U.create_scale(r, [max(d, 2) / (max(d, 2) - 1) for d in grid.shape[1:]], dtype=np.float64), dtype=grid.dtype, device=grid.device)
+            a = affine @ sc
+        out = (a @ grid.reshape(grid.shape[0], -1)).reshape(-1, *grid.shape[1:])
+        return out, affine
+
+
+class RandAffineGrid(Randomizable, Transform):
+    """Random affine parameters with the reference's draw order (spatial/array.py:1786-1915): rotate, shear,
+    translate, scale (+1.0); each entry `uniform(-f, f)` or `uniform(f[0], f[1])`."""
+
+    def __init__(self, rotate_range=None, shear_range=None, translate_range=None, scale_range=None, device=None, dtype=np.float32, lazy: bool = False):
+        _t = lambda v: () if v is None else (tuple(v) if isinstance(v, (list, tuple, np.ndarray)) else (v,))  # noqa: E731
+        self.rotate_range, self.shear_range, self.translate_range, self.scale_range = _t(rotate_range), _t(shear_range), _t(translate_range), _t(scale_range)
+        self.rotate_params = self.shear_params = self.translate_params = self.scale_params = None
+        self.device, self.dtype = device, dtype
+        self.affine = torch.eye(4, dtype=torch.float64)
+
+    def _get_rand_param(self, param_range, add_scalar: float = 0.0):
+        out = []
+        for f in param_range:
+            if isinstance(f, (list, tuple, np.ndarray)):
+                if len(f) != 2:
+                    raise ValueError(f"If giving range as [min,max], should have 2 elements per dim, got {f}.")
+                out.append(self.R.uniform(f[0], f[1]) + add_scalar)
+            elif f is not None:
+                out.append(self.R.uniform(-f, f) + add_scalar)
+        return out
+
+    def randomize(self, data=None) -> None:
+        self.rotate_params = self._get_rand_param(self.rotate_range)
+        self.shear_params = self._get_rand_param(self.shear_range)
+        self.translate_params = self._get_rand_param(self.translate_range)
+        self.scale_params = self._get_rand_param(self.scale_range, 1.0)
+
+    def matrix(self, spatial_dims: int, randomize: bool = True) -> np.ndarray:
+        if randomize:
+            self.randomize()
+        ag = AffineGrid(self.rotate_params, self.shear_params, self.translate_params, self.scale_params)
+        m = ag.matrix(spatial_dims)
+        self.affine = torch.as_tensor(m, dtype=torch.float32)
+        return m
+
+    def __call__(self, spatial_size=None, grid=None, randomize: bool = True, lazy=None):
+        if randomize:
+            self.randomize()
+        ag = AffineGrid(self.rotate_params, self.shear_params, self.translate_params, self.scale_params)
+        g, self.affine = ag(spatial_size, grid)
+        return g
+
+    def get_transformation_matrix(self):
+        return self.affine
+
+
+class Resample(Transform):
+    """Resample with an explicit grid (spatial/array.py:1962-2117).  Affine grids produced by this package are resolved
+    to their matrix (no dense grid traffic); arbitrary dense grids are not implemented on this path."""
+
+    def __init__(self, mode="bilinear", padding_mode="border", norm_coords: bool = True, device=None, align_corners: bool = False, dtype=np.float64):
+        self.mode, self.padding_mode, self.norm_coords, self.device, self.align_corners, self.dtype = mode, padding_mode, norm_coords, device, align_corners, dtype
+
+    def __call__(self, img, grid=None, mode=None, padding_mode=None, dtype=None, align_corners=None):
+        if grid is None:
+            return img
+        if not isinstance(grid, AffineSpec):
+            raise NotImplementedError("monai_b200 Resample takes the affine grids of AffineGrid/RandAffineGrid (AffineSpec); dense deformation grids are not implemented")
+        if not self.norm_coords:
+            raise NotImplementedError("norm_coords=False is not implemented")
+        align = self.align_corners if align_corners is None else align_corners
+        r = len(grid.spatial_size)
+        mat = U.sample_matrix_from_centered_affine(grid.affine if not (grid.grid_align_corners) else grid.affine, tuple(img.shape[1 : 1 + r]), grid.spatial_size, align)
+        out = _resample(img, mat, r, grid.spatial_size, self.mode if mode is None else mode, self.padding_mode if padding_mode is None else padding_mode, align)
+        return rewrap(out, img)
+
+
+class AffineSpec:
+    """An affine sampling grid in closed form: `affine` acts on the centred index grid of `spatial_size`."""
+
+    def __init__(self, affine: np.ndarray, spatial_size: Sequence[int], grid_align_corners: bool = False):
+        self.affine, self.spatial_size, self.grid_align_corners = np.asarray(affine, dtype=np.float64), tuple(int(s) for s in spatial_size), grid_align_corners
+
+
+def _update_affine(img, affine_centered: np.ndarray, src_shape, dst_shape):
+    """metadata update of affine_func (spatial/functional.py:548-613): new = old @ (T_src_center @ A @ T_dst_center^-1)."""
+    if not is_meta(img):
+        return None
+    r = len(dst_shape)
+    old = get_affine(img).numpy()
+    t_src, t_dst = np.eye(r + 1), np.eye(r + 1)
+    t_src[:r, -1] = (np.asarray(src_shape[:r], dtype=np.float64) - 1) / 2.0
+    t_dst[:r, -1] = -(np.asarray(dst_shape, dtype=np.float64) - 1) / 2.0
+    m = t_src @ U.to_affine_nd(r, affine_centered) @ t_dst
+    full = np.eye(len(old))
+    full[:r, :r], full[:r, -1] = m[:r, :r], m[:r, -1]
+    return old @ full
+
+
+class Affine(Transform):
+    """Deterministic affine transform (spatial/array.py:2120-2316)."""
+
+    def __init__(self, rotate_params=None, shear_params=None, translate_params=None, scale_params=None, affine=None, spatial_size=None, mode="bilinear",
+                 padding_mode="reflection", normalized: bool = False, device=None, dtype=np.float32, align_corners: bool = False, image_only: bool = False, lazy: bool = False):
+        if normalized:
+            raise NotImplementedError("Affine(normalized=True) is not implemented")
+        self.affine_grid = AffineGrid(rotate_params, shear_params, translate_params, scale_params, affine=affine, dtype=dtype, align_corners=align_corners)
+        self.image_only, self.spatial_size, self.mode, self.padding_mode, self.align_corners = image_only, spatial_size, mode, padding_mode, align_corners
+
+    def __call__(self, img, spatial_size=None, mode=None, padding_mode=None, lazy=None):
+        ori = tuple(img.shape[1:])
+        r = min(len(ori), 3)
+        sp = _fall_back(self.spatial_size if spatial_size is None else spatial_size, ori[:r])
+        a = self.affine_grid.matrix(r)
+        a_eff = a
+        if self.align_corners:
+            n = np.asarray(sp, dtype=np.float64)
+            a_eff = a @ np.diag(np.append(np.maximum(n, 2) / (np.maximum(n, 2) - 1), 1.0))
+        n_s = np.asarray(ori[:r], dtype=np.float64)
+        norm = np.diag(np.append(2.0 / np.maximum(2.0, n_s), 1.0))
+        center = np.eye(r + 1)
+        center[:-1, -1] = -(np.asarray(sp, dtype=np.float64) - 1) / 2.0
+        mat = U._unnormalize(ori[:r], self.align_corners) @ norm @ a_eff @ center
+        out = _resample(img, mat, r, sp, self.mode if mode is None else mode, self.padding_mode if padding_mode is None else padding_mode, self.align_corners)
+        out = rewrap(out, img, _update_affine(img, a, ori, sp), {"class": "Affine", "affine": a})
+        return out if self.image_only else (out, torch.as_tensor(a))
+
+
+class RandAffine(RandomizableTransform):
+    """Random affine transform (spatial/array.py:2317-2577)."""
+
+    def __init__(self, prob: float = 0.1, rotate_range=None, shear_range=None, translate_range=None, scale_range=None, spatial_size=None, mode="bilinear",
+                 padding_mode="reflection", cache_grid: bool = False, device=None, lazy: bool = False):
+        RandomizableTransform.__init__(self, prob)
+        self.rand_affine_grid = RandAffineGrid(rotate_range, shear_range, translate_range, scale_range, device=device)
+        self.resampler = Resample(device=device)
+        self.spatial_size, self.mode, self.padding_mode, self.cache_grid = spatial_size, mode, padding_mode, cache_grid
+
+    def set_random_state(self, seed=None, state=None):
+        self.rand_affine_grid.set_random_state(seed, state)
+        super().set_random_state(seed, state)
+        return self
+
+    def randomize(self, data=None) -> None:
+        super().randomize(None)
+        if not self._do_transform:
+            return None
+        self.rand_affine_grid.randomize()
+
+    def get_identity_grid(self, spatial_size, lazy: bool = False) -> AffineSpec:
+        return AffineSpec(np.eye(len(spatial_size) + 1), spatial_size)
+
+    def __call__(self, img, spatial_size=None, mode=None, padding_mode=None, randomize: bool = True, grid=None, lazy=None):
+        if randomize:
+            self.randomize()
+        ori = tuple(img.shape[1:])
+        r = min(len(ori), 3)
+        sp = _fall_back(self.spatial_size if spatial_size is None else spatial_size, ori[:r])
+        do_resampling = self._do_transform or (sp != tuple(ori[:r]))
+        _mode_ = self.mode if mode is None else mode
+        _pad_ = self.padding_mode if padding_mode is None else padding_mode
+        if grid is None or not isinstance(grid, AffineSpec):
+            grid = self.get_identity_grid(sp)
+            if self._do_transform:
+                grid = AffineSpec(self.rand_affine_grid.matrix(r, randomize=randomize), sp)
+        affine = self.rand_affine_grid.get_transformation_matrix()
+        if not do_resampling:
+            t = img.as_subclass(torch.Tensor) if type(img) is not torch.Tensor else img
+            return rewrap(t.to(torch.float32), img)
+        out = self.resampler(img, grid=grid, mode=_mode_, padding_mode=_pad_)
+        a = np.asarray(grid.affine)
+        return rewrap(out.as_subclass(torch.Tensor) if type(out) is not torch.Tensor else out, img, _update_affine(img, a, ori, sp),
+                      {"class": "RandAffine", "affine": a, "rand_affine_matrix": affine})
+
+
+class RandAffined(RandomizableTransform, MapTransform):
+    """Dictionary version (spatial/dictionary.py:1001-1175): one set of random parameters shared by all keys."""
+
+    def __init__(self, keys, spatial_size=None, prob: float = 0.1, rotate_range=None, shear_range=None, translate_range=None, scale_range=None,
+                 mode="bilinear", padding_mode="reflection", cache_grid: bool = False, device=None, allow_missing_keys: bool = False, lazy: bool = False):
+        MapTransform.__init__(self, keys, allow_missing_keys)
+        RandomizableTransform.__init__(self, prob)
+        self.rand_affine = RandAffine(prob=1.0, rotate_range=rotate_range, shear_range=shear_range, translate_range=translate_range, scale_range=scale_range,
+                                      spatial_size=spatial_size, cache_grid=cache_grid, device=device)
+        n = len(self.keys)
+        rep = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * n  # noqa: E731
+        self.mode, self.padding_mode = rep(mode), rep(padding_mode)
+
+    def set_random_state(self, seed=None, state=None):
+        self.rand_affine.set_random_state(seed, state)
+        super().set_random_state(seed, state)
+        return self
+
+    def __call__(self, data: Mapping[Hashable, Any], lazy=None) -> dict:
+        d = dict(data)
+        keys = [k for k in self.key_iterator(d)]
+        if not keys:
+            return d
+        self.randomize(None)
+        self.rand_affine.randomize()  # all the keys share the same random affine factor
+        item = d[keys[0]]
+        ori = tuple(item.shape[1:])
+        r = min(len(ori), 3)
+        sp = _fall_back(self.rand_affine.spatial_size, ori[:r])
+        do_resampling = self._do_transform or (sp != tuple(ori[:r]))
+        grid = None
+        if do_resampling:
+            grid = self.rand_affine.get_identity_grid(sp)
+            if self._do_transform:
+                grid = AffineSpec(self.rand_affine.rand_affine_grid.matrix(r, randomize=True), sp)
+        for key in keys:
+            idx = self.keys.index(key)
+            if do_resampling:
+                # the reference passes randomize=True here too (dictionary.py:1156): the per-key redraw only consumes
+                # RNG state, the shared grid is what is applied
+                d[key] = self.rand_affine(d[key], None, self.mode[idx], self.padding_mode[idx], True, grid)
+            else:
+                t = d[key].as_subclass(torch.Tensor) if type(d[key]) is not torch.Tensor else d[key]
+                d[key] = rewrap(t.to(torch.float32), d[key])
+        return d

@@ -136,18 +136,57 @@ def nets():
         y = net(x)
     save("basic_unet_tiny.npz", x=x.numpy(), y=y.numpy())
 
-    net = _load_named(SwinUNETR(in_channels=1, out_channels=2, feature_size=12), 4)
-    # 64^3 is the smallest input: InstanceNorm at the 1/32 scale needs more than one spatial element
-    x = torch.randn(1, 1, 64, 64, 64, generator=torch.Generator().manual_seed(15)).half().float()
-    with torch.no_grad():
-        hs = net.swinViT(x, True)
-        y = net(x)
-    save("swin_unetr_fs12_64.npz", x=x.numpy().astype(np.float16), y_sub=y.numpy()[..., ::4, ::4, ::4], h0_sub=hs[0].numpy()[..., ::4, ::4, ::4],
-         h2=hs[2].numpy(), h4=hs[4].numpy(), y_mean=np.array(float(y.double().mean())), y_absmean=np.array(float(y.double().abs().mean())))
+    # feature_size=48 (config C3 architecture); 64^3 is the smallest legal input (InstanceNorm at 1/32 scale needs >1 voxel)
+    net = _load_named(SwinUNETR(in_channels=1, out_channels=2, feature_size=48), 4)
+    for tag, shape, seed in (("64", (64, 64, 64), 15), ("96x64x64", (96, 64, 64), 16)):
+        x = torch.randn(1, 1, *shape, generator=torch.Generator().manual_seed(seed)).half().float()
+        with torch.no_grad():
+            hs = net.swinViT(x, True)
+            y = net(x)
+        save(f"swin_unetr_fs48_{tag}.npz", x=x.numpy().astype(np.float16), y_sub=y.numpy()[..., ::4, ::4, ::4],
+             h0_sub=hs[0].numpy()[..., ::4, ::4, ::4], h1_sub=hs[1].numpy()[..., ::2, ::2, ::2], h2=hs[2].numpy()[:, ::4],
+             h4=hs[4].numpy()[:, ::8], y_mean=np.array(float(y.double().mean())), y_absmean=np.array(float(y.double().abs().mean())))
+
+
+def transforms():
+    from monai.data import MetaTensor
+    from monai.transforms import GaussianSmooth, RandAffined, Spacing, Spacingd
+
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    img = torch.rand((1, 20, 24, 18), generator=g)
+    for tag, aff, pixdim, kw in [
+        ("s0", np.diag([1.25, 1.25, 1.25, 1.0]), (1.0, 1.0, 1.0), {}),
+        ("s1", np.diag([0.8, 1.5, 1.1, 1.0]), (1.0, 1.2, 0.7), {"mode": "nearest"}),
+        ("s2", np.array([[0.0, -1.3, 0.0, 10.0], [1.1, 0.0, 0.0, -5.0], [0.0, 0.0, 2.0, 3.0], [0, 0, 0, 1.0]]), (1.0, 1.0, 1.5), {"padding_mode": "zeros"}),
+        ("s3", np.diag([1.25, 1.25, 1.25, 1.0]), (1.0, 1.0, 1.0), {"align_corners": True}),
+        ("s4", np.diag([1.5, 1.5, 1.5, 1.0]), (1.0, 1.0, 1.0), {"diagonal": True, "padding_mode": "reflection"}),
+    ]:
+        m = MetaTensor(img.clone(), affine=torch.as_tensor(aff))
+        r = Spacing(pixdim=pixdim, **kw)(m)
+        out[f"{tag}.affine"], out[f"{tag}.pixdim"], out[f"{tag}.y"], out[f"{tag}.new_affine"] = aff, np.array(pixdim), r.numpy(), r.affine.numpy()
+        out[f"{tag}.kw"] = np.array(repr(kw))
+    out["img"] = img.numpy()
+    # RandAffined, seeded as in SURVEY.md section 8(d) config C4
+    img2 = torch.rand((2, 24, 20, 16), generator=g)
+    for tag, kw in [
+        ("r0", dict(prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border")),
+        ("r1", dict(prob=1.0, rotate_range=(0.3, 0.0, 0.1), shear_range=(0.05,) * 6, mode="nearest", padding_mode="zeros")),
+        ("r2", dict(prob=1.0, rotate_range=((0.1, 0.4),), scale_range=(0.2,), spatial_size=(16, 28, 12), mode="bilinear", padding_mode="reflection")),
+    ]:
+        t = RandAffined(keys=["image"], **kw)
+        t.set_random_state(seed=0)
+        r = t({"image": MetaTensor(img2.clone(), affine=torch.eye(4))})["image"]
+        out[f"{tag}.y"], out[f"{tag}.kw"], out[f"{tag}.new_affine"] = r.numpy(), np.array(repr(kw)), r.affine.numpy()
+    out["img2"] = img2.numpy()
+    for tag, sigma in [("g0", 1.0), ("g1", (1.5, 0.5, 1.0)), ("g2", 0.3)]:
+        out[f"{tag}.y"] = GaussianSmooth(sigma=sigma)(img2).numpy()
+        out[f"{tag}.sigma"] = np.atleast_1d(np.array(sigma, dtype=np.float64))
+    save("transforms.npz", **out)
 
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms"]
     for w in which:
         globals()[w]()

@@ -1,0 +1,165 @@
+"""GPU parity of the SwinUNETR path (tcgen05 convs / GEMMs, window attention, LayerNorm / merging kernels) against the
+reference fixtures (real MONAI outputs) and the torch-CPU oracle.  The network computes in fp16 with fp32
+accumulation, the oracle in fp32: tolerances are stated relative to the output scale."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from monai_b200 import _kernels as K
+from monai_b200 import _lib as L
+from monai_b200.networks.nets import SwinUNETR
+from monai_b200.networks.nets.swin_unetr import window_plan
+from oracle import networks as onet
+from weights import fill_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(1e-6, np.abs(b).max()))
+
+
+def _to_nc8(x):  # [N,C,*sp] float -> NC8
+    return K.pack_nc8(x.to(DEV).half())
+
+
+def test_gemm_tc_linear_bias_gelu_residual():
+    g = torch.Generator().manual_seed(0)
+    for (S, Kd, N) in [(300, 48, 144), (1000, 192, 48), (129, 768, 3072), (64, 3072, 768)]:
+        x = torch.randn((2, Kd, 1, 1, S), generator=g).half()
+        w = (torch.randn((N, Kd), generator=g) / Kd**0.5).half()
+        b = torch.randn(N, generator=g)
+        r = torch.randn((2, N, 1, 1, S), generator=g).half()
+        ref = F.linear(x.float().reshape(2, Kd, S).transpose(1, 2), w.float(), b)  # [2,S,N]
+        y, _ = K.gemm_tc(_to_nc8(x), K.gemm_tc_pack_weight(w.to(DEV)), Kd, N, bias=b.to(DEV))
+        got = K.unpack_nc8(y, dtype=torch.float32).cpu().reshape(2, N, S).transpose(1, 2)
+        assert _rel(got.numpy(), ref.numpy()) < 3e-3, (S, Kd, N)
+        y, _ = K.gemm_tc(_to_nc8(x), K.gemm_tc_pack_weight(w.to(DEV)), Kd, N, bias=b.to(DEV), act=L.ACT_GELU, res=_to_nc8(r))
+        got = K.unpack_nc8(y, dtype=torch.float32).cpu().reshape(2, N, S).transpose(1, 2)
+        ref2 = F.gelu(ref) + r.float().reshape(2, N, S).transpose(1, 2)
+        assert _rel(got.numpy(), ref2.numpy()) < 3e-3, (S, Kd, N)
+
+
+def test_gemm_tc_conv_transpose_k2s2_and_1x1_stats():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((2, 96, 3, 5, 6), generator=g).half()
+    w = (torch.randn((96, 48, 2, 2, 2), generator=g) / 10).half()
+    ref = F.conv_transpose3d(x.float(), w.float(), stride=2)
+    wg = w.float().permute(2, 3, 4, 1, 0).reshape(8 * 48, 96).contiguous()
+    cat = K.NC8(2, 96, (6, 10, 12), DEV)
+    cat.buf.zero_()
+    K.gemm_tc(_to_nc8(x), K.gemm_tc_pack_weight(wg.to(DEV)), 96, 8 * 48, out=cat, out_coff=48, mode=2)
+    got = K.unpack_nc8(cat, 48, c_off=48, dtype=torch.float32).cpu()
+    assert _rel(got.numpy(), ref.numpy()) < 3e-3
+    assert float(cat.buf[:, :6].abs().max()) == 0.0
+    w1 = (torch.randn((48, 96, 1, 1, 1), generator=g) / 10).half()
+    ref1 = F.conv3d(x.float(), w1.float())
+    y, st = K.gemm_tc(_to_nc8(x), K.gemm_tc_pack_weight(w1.reshape(48, 96).to(DEV)), 96, 48, want_stats=True)
+    assert _rel(K.unpack_nc8(y, dtype=torch.float32).cpu().numpy(), ref1.numpy()) < 3e-3
+    torch.testing.assert_close(st[:, 0].cpu(), ref1.sum(dim=(2, 3, 4)).reshape(-1), rtol=2e-2, atol=2e-2)
+
+
+def test_layernorm_gather_and_patch_merging():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((2, 48, 6, 9, 10), generator=g).half()
+    gamma, beta = torch.rand(48, generator=g) + 0.5, torch.randn(48, generator=g)
+    ref = F.layer_norm(x.float().permute(0, 2, 3, 4, 1), (48,), gamma, beta).permute(0, 4, 1, 2, 3)
+    got = K.unpack_nc8(K.layernorm_nc8(_to_nc8(x), gamma.to(DEV), beta.to(DEV)), dtype=torch.float32).cpu()
+    assert _rel(got.numpy(), ref.numpy()) < 2e-3
+    # gather with the window plan (shifted, padded): compare against pad + roll + window_partition
+    src, region, nW, n = window_plan((6, 9, 10), (7, 7, 7), (3, 3, 3))
+    xw = K.layernorm_nc8(_to_nc8(x), gamma.to(DEV), beta.to(DEV), src=torch.from_numpy(src).to(DEV), out_sp=(1, nW, n))
+    got = K.unpack_nc8(xw, dtype=torch.float32).cpu().reshape(2, 48, nW, n).permute(0, 2, 3, 1).reshape(-1, n, 48)
+    t = ref.permute(0, 2, 3, 4, 1)
+    t = F.pad(t, (0, 0, 0, 4, 0, 5, 0, 0))  # to (6->6 [window clamps to 6], 9->14, 10->14)
+    ws, ss = (6, 7, 7), (0, 3, 3)
+    t = torch.roll(t, shifts=(-ss[0], -ss[1], -ss[2]), dims=(1, 2, 3))
+    want = onet._window_partition(t, ws)
+    assert _rel(got.numpy(), want.numpy()) < 2e-3
+    want_mask = onet._compute_mask([6, 14, 14], ws, ss)
+    reg = torch.from_numpy(region)
+    got_mask = torch.where(reg[:, None, :] != reg[:, :, None], -100.0, 0.0)
+    torch.testing.assert_close(got_mask, want_mask.float(), rtol=0, atol=0)
+    # patch merging (both slice orders), odd sizes padded
+    sd = {"p.norm.weight": torch.rand(384, generator=g) + 0.5, "p.norm.bias": torch.randn(384, generator=g), "p.reduction.weight": torch.eye(96, 384)}
+    for v2 in (False, True):
+        m = K.patch_merge_ln_nc8(_to_nc8(x), sd["p.norm.weight"].to(DEV), sd["p.norm.bias"].to(DEV), v2=v2)
+        got = K.unpack_nc8(m, dtype=torch.float32).cpu()
+        xt = F.pad(x.float().permute(0, 2, 3, 4, 1), (0, 0, 0, 0, 0, 1, 0, 0))
+        order = list(__import__("itertools").product(range(2), range(2), range(2))) if v2 else [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)]
+        cat = torch.cat([xt[:, i::2, j::2, k::2, :] for i, j, k in order], -1)
+        want = F.layer_norm(cat, (384,), sd["p.norm.weight"], sd["p.norm.bias"]).permute(0, 4, 1, 2, 3)
+        assert _rel(got.numpy(), want.numpy()) < 2e-3, v2
+
+
+def test_window_attention_matches_reference_math():
+    g = torch.Generator().manual_seed(3)
+    heads, C, nW, n, B = 3, 48, 5, 343, 2
+    qkv = torch.randn((B, nW, n, 3 * C), generator=g).half()
+    bias = torch.randn((heads, n, n), generator=g)
+    region = torch.randint(0, 3, (nW, n), generator=g, dtype=torch.int32)
+    q, k, v = qkv.float().reshape(B, nW, n, 3, heads, 16).permute(3, 0, 1, 4, 2, 5)
+    attn = (q * 0.25) @ k.transpose(-2, -1) + bias[None, None]
+    mask = torch.where(region[:, None, :] != region[:, :, None], -100.0, 0.0)  # [nW, i, j]
+    attn = (attn + mask[None, :, None]).softmax(-1)
+    ref = (attn @ v).permute(0, 1, 3, 2, 4).reshape(B, nW, n, C)
+    x = K.pack_nc8(qkv.permute(0, 3, 1, 2).reshape(B, 3 * C, 1, nW, n).contiguous().to(DEV))
+    out = K.window_attention_nc8(x, C, heads, nW, n, 0.25, bias.permute(0, 2, 1).contiguous().to(DEV), region.to(DEV))
+    got = K.unpack_nc8(out, dtype=torch.float32).cpu().reshape(B, C, nW, n).permute(0, 2, 3, 1)
+    assert _rel(got.numpy(), ref.numpy()) < 3e-3
+
+
+def test_cin1_stem_and_head():
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((2, 1, 8, 10, 12), generator=g)
+    for k, s, p in [(3, 1, 1), (2, 2, 0), (1, 1, 0)]:
+        w, b = torch.randn((48, 1, k, k, k), generator=g) / k**1.5, torch.randn(48, generator=g)
+        ref = F.conv3d(x, w, b, stride=s, padding=p)
+        y, st = K.conv_cin1_nc8(x.to(DEV), w.to(DEV), b.to(DEV), k, s, p, want_stats=True)
+        assert _rel(K.unpack_nc8(y, dtype=torch.float32).cpu().numpy(), ref.numpy()) < 2e-3
+        torch.testing.assert_close(st[:, 0].cpu(), ref.sum(dim=(2, 3, 4)).reshape(-1), rtol=1e-3, atol=1e-2)
+    h = torch.randn((2, 48, 4, 5, 6), generator=g).half()
+    w, b = torch.randn((2, 48, 1, 1, 1), generator=g) / 7, torch.randn(2, generator=g)
+    ref = F.conv3d(h.float(), w, b)
+    got = K.head_conv_nc8(_to_nc8(h), w.to(DEV), b.to(DEV), out_dtype=torch.float32)
+    assert _rel(got.cpu().numpy(), ref.numpy()) < 1e-3
+
+
+def _build():
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = SwinUNETR(in_channels=1, out_channels=2, feature_size=48)
+    net.load_state_dict(fill_state_dict(net.state_dict(), 4))
+    return net.eval().to(DEV)
+
+
+@pytest.mark.parametrize("tag", ["64", "96x64x64"])
+def test_swin_unetr_matches_reference_fixture(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, f"swin_unetr_fs48_{tag}.npz"))
+    net = _build()
+    x = torch.from_numpy(g["x"]).to(DEV)  # fp16 input
+    y = net(x).float().cpu().numpy()
+    assert y.shape[2:] == g["x"].shape[2:]
+    err = _rel(y[..., ::4, ::4, ::4], g["y_sub"])
+    assert err < 3e-2, f"rel err {err}"  # fp16 activations through ~40 layers vs the fp32 reference
+    assert abs(float(y.mean()) - float(g["y_mean"])) < 2e-2 * float(g["y_absmean"])
+    agree = (y[..., ::4, ::4, ::4].argmax(1) == g["y_sub"].argmax(1)).mean()
+    assert agree > 0.98, agree
+
+
+def test_swin_unetr_batch_and_fp32_input_vs_oracle():
+    net = _build()
+    x = torch.randn(2, 1, 64, 64, 64, generator=torch.Generator().manual_seed(8))
+    sd = {k: v.float().cpu() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        ref = onet.swin_unetr_forward(sd, x).numpy()
+    y = net(x.to(DEV))  # fp32 in -> fp32 logits (internals fp16)
+    assert y.dtype == torch.float32
+    assert _rel(y.cpu().numpy(), ref) < 3e-2
+    with pytest.raises(ValueError, match="must be divisible by 2\\*\\*5"):
+        net(torch.zeros(1, 1, 48, 64, 64, device=DEV))

@@ -1,0 +1,91 @@
+"""GPU parity of the transform operator surface (Spacing / Spacingd / RandAffined / GaussianSmooth) vs the reference
+fixtures and the torch-CPU oracle.  fp32 resample tolerance 1e-3 relative (north star); measured errors are ~1e-5."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from monai_b200.data import MetaTensor
+from monai_b200.transforms import Compose, GaussianSmooth, GaussianSmoothd, RandAffine, RandAffined, Spacing, Spacingd
+from oracle import transforms as otr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _kw(g, tag):
+    return ast.literal_eval(str(g[f"{tag}.kw"]))
+
+
+def test_spacing_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "transforms.npz"))
+    for tag in ("s0", "s1", "s2", "s3", "s4"):
+        kw = _kw(g, tag)
+        m = MetaTensor(torch.from_numpy(g["img"]).to(DEV), affine=torch.as_tensor(g[f"{tag}.affine"]))
+        r = Spacing(pixdim=tuple(g[f"{tag}.pixdim"]), **kw)(m)
+        assert tuple(r.shape) == g[f"{tag}.y"].shape and r.dtype == torch.float32, tag  # shapes are bit-exact host arithmetic
+        np.testing.assert_allclose(r.affine.numpy(), g[f"{tag}.new_affine"], rtol=1e-9, atol=1e-9, err_msg=tag)
+        if kw.get("mode") == "nearest":
+            assert (r.cpu().numpy() != g[f"{tag}.y"]).mean() < 2e-3, tag
+        else:
+            np.testing.assert_allclose(r.cpu().numpy(), g[f"{tag}.y"], rtol=1e-3, atol=1e-4, err_msg=tag)
+
+
+def test_rand_affined_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "transforms.npz"))
+    for tag in ("r0", "r1", "r2"):
+        kw = _kw(g, tag)
+        t = RandAffined(keys=["image"], **kw)
+        t.set_random_state(seed=0)
+        r = t({"image": MetaTensor(torch.from_numpy(g["img2"]).to(DEV), affine=torch.eye(4))})["image"]
+        assert tuple(r.shape) == g[f"{tag}.y"].shape, tag
+        if kw["mode"] == "nearest":
+            assert (r.cpu().numpy() != g[f"{tag}.y"]).mean() < 2e-3, tag
+        else:
+            np.testing.assert_allclose(r.cpu().numpy(), g[f"{tag}.y"], rtol=1e-3, atol=2e-4, err_msg=tag)
+        np.testing.assert_allclose(r.affine.numpy(), g[f"{tag}.new_affine"], rtol=1e-5, atol=1e-5, err_msg=tag)
+
+
+def test_gaussian_smooth_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "transforms.npz"))
+    img = torch.from_numpy(g["img2"]).to(DEV)
+    for tag in ("g0", "g1", "g2"):
+        s = g[f"{tag}.sigma"].tolist()
+        y = GaussianSmooth(sigma=s[0] if len(s) == 1 else s)(img)
+        np.testing.assert_allclose(y.cpu().numpy(), g[f"{tag}.y"], rtol=1e-4, atol=1e-5)
+    # the 2-D golden of tests/transforms/test_gaussian_smooth.py
+    img2 = torch.tensor([[[1, 1, 1], [2, 2, 2], [3, 3, 3]], [[4, 4, 4], [5, 5, 5], [6, 6, 6]]], dtype=torch.float32, device=DEV)
+    exp = [[[0.59167546, 0.69312394, 0.59167546], [0.7956997, 0.93213004, 0.7956997], [0.7668002, 0.8982755, 0.7668002]],
+           [[1.6105323, 1.8866735, 1.6105323], [1.9892492, 2.3303251, 1.9892492], [1.7856569, 2.091825, 1.7856569]]]
+    np.testing.assert_allclose(GaussianSmooth(sigma=1.5)(img2).cpu().numpy(), np.array(exp), rtol=1e-4, atol=1e-4)
+
+
+def test_config_c4_pipeline_vs_oracle():
+    """Spacingd -> RandAffined -> GaussianSmoothd on a small volume vs the CPU oracle."""
+    gen = torch.Generator().manual_seed(5)
+    img = torch.rand((1, 40, 36, 44), generator=gen)
+    aff = np.diag([1.25, 1.25, 1.25, 1.0])
+    pipe = Compose([
+        Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear"),
+        RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border"),
+        GaussianSmoothd(keys=["image"], sigma=1.0),
+    ])
+    pipe.transforms[1].set_random_state(seed=0)
+    got = pipe({"image": MetaTensor(img.to(DEV), affine=torch.as_tensor(aff))})["image"]
+    a, _ = otr.spacing(img, aff, (1.0, 1.0, 1.0))
+    b, _ = otr.rand_affine(a, 0, (0.2,) * 3, (), (5,) * 3, (0.1,) * 3, None, "bilinear", "border")
+    want = otr.gaussian_smooth(b, 1.0)
+    assert tuple(got.shape) == tuple(want.shape) == (1, 50, 45, 55)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-3, atol=2e-4)
+
+
+def test_rand_affine_without_transform_and_plain_tensor():
+    x = torch.rand((1, 8, 9, 10), device=DEV)
+    t = RandAffine(prob=0.0, rotate_range=(0.5,))
+    t.set_random_state(seed=1)
+    y = t(x)
+    torch.testing.assert_close(y, x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Spacing(pixdim=(2.0, 2.0, 2.0))(torch.rand(1, 4, 4, 4))

@@ -1,0 +1,66 @@
+"""CPU checks of the transform host algebra: the closed-form index->coordinate matrix the CUDA resampler consumes must
+equal the dense coordinates the reference generates (F.affine_grid + grid_sample un-normalisation / create_grid @ affine)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from monai_b200.transforms import utils as U
+from oracle import transforms as otr
+
+
+def _dense_coords_from_affine_grid(xform, src_shape, dst_shape, align):
+    r = len(src_shape)
+    theta = torch.as_tensor(xform, dtype=torch.float64)[None]
+    theta = otr._normalize_transform(src_shape, False) @ theta @ torch.linalg.inv(otr._normalize_transform(dst_shape, False))
+    rev = list(range(r - 1, -1, -1))
+    t2 = theta.clone(); t2[:, :r] = theta[:, rev]
+    t3 = t2.clone(); t3[:, :, :r] = t2[:, :, rev]
+    grid = F.affine_grid(t3[:, :r], [1, 1, *dst_shape], align_corners=align)[0]  # (..., xyz) normalised
+    g = grid.flip(-1)
+    s = torch.tensor(src_shape, dtype=torch.float64)
+    return ((g + 1) / 2 * (s - 1)) if align else (((g + 1) * s - 1) / 2)
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_sample_matrix_from_xform_equals_affine_grid(align):
+    rng = np.random.default_rng(0)
+    xform = np.eye(4)
+    xform[:3, :3] += rng.normal(0, 0.2, (3, 3))
+    xform[:3, 3] = rng.normal(0, 3, 3)
+    src, dst = (9, 11, 13), (7, 12, 10)
+    want = _dense_coords_from_affine_grid(xform, src, dst, align).numpy()
+    m = U.sample_matrix_from_xform(xform, src, dst, align)
+    idx = np.stack(np.meshgrid(*[np.arange(d) for d in dst], indexing="ij"), -1)
+    got = idx @ m[:3, :3].T + m[:3, 3]
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
+
+
+def test_host_helpers_match_oracle():
+    rng = np.random.default_rng(1)
+    a = np.eye(4)
+    a[:3, :3] = np.diag([1.3, 0.7, 2.1]) @ np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    a[:3, 3] = [4, -2, 7]
+    np.testing.assert_allclose(U.affine_to_spacing(a), otr.affine_to_spacing(a))
+    for diag in (True, False):
+        np.testing.assert_allclose(U.zoom_affine(a, (1.0, 1.0, 1.5), diag), otr.zoom_affine(a, (1.0, 1.0, 1.5), diag))
+    na = U.zoom_affine(a, (1.0, 1.0, 1.5), False)
+    s1, o1 = U.compute_shape_offset((20, 24, 18), a, na)
+    s2, o2 = otr.compute_shape_offset((20, 24, 18), a, na)
+    assert tuple(s1) == tuple(s2)
+    np.testing.assert_allclose(o1, o2)
+    rot = U.create_rotate(3, (0.3, -0.2, 0.1))
+    np.testing.assert_array_equal(rot, otr._create_rotate3((0.3, -0.2, 0.1)).numpy())
+
+
+def test_rand_affine_draw_order():
+    from monai_b200.transforms import RandAffined
+
+    t = RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3)
+    t.set_random_state(seed=0)
+    t.randomize(None)
+    t.rand_affine.randomize()
+    t.rand_affine.rand_affine_grid.matrix(3, randomize=True)
+    g = t.rand_affine.rand_affine_grid
+    rot, shear, trans, scale = otr.rand_affine_params(0, (0.2,) * 3, (), (5,) * 3, (0.1,) * 3)
+    assert g.rotate_params == rot and g.translate_params == trans and g.scale_params == scale
