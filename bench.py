@@ -118,7 +118,8 @@ def run_reference(args, wl):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(min(cores, int(os.environ.get("B200_REF_THREADS", "32"))))
+    cores = torch.get_num_threads()
     if wl["net"] == "unet_c2":
         from monai_b200.networks.nets import UNet
 
@@ -163,7 +164,6 @@ def cpu_baseline_leg(wl, budget_s: float = 20.0) -> dict:
     from weights import fill_state_dict
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     if wl["net"] == "unet_c2":
         from monai_b200.networks.nets import UNet
 
@@ -177,17 +177,26 @@ def cpu_baseline_leg(wl, budget_s: float = 20.0) -> dict:
         vol, nwin = (144, 144, 96), 4
         fwd = lambda a: onet.swin_unetr_forward(sd, torch.from_numpy(a)).numpy()  # noqa: E731
     x = np.random.default_rng(0).standard_normal((1, 1, *vol)).astype(np.float32)
-    times = []
+    best, best_threads, passes = None, cores, 0
     t_all = time.perf_counter()
     with torch.no_grad():
-        while len(times) < 2 or (time.perf_counter() - t_all < budget_s and len(times) < 6):
-            t0 = time.perf_counter()
-            osw.sliding_window_inference(x, wl["roi"], 4, fwd, wl["overlap"], wl["mode"])
-            times.append(time.perf_counter() - t0)
-    per_win = min(times[1:] or times) / nwin
+        # oneDNN/ATen on many-core hosts can lose to a smaller pool on these small windows: take the best thread count
+        for threads in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+            torch.set_num_threads(threads)
+            for rep in range(2):
+                t0 = time.perf_counter()
+                osw.sliding_window_inference(x, wl["roi"], 4, fwd, wl["overlap"], wl["mode"])
+                dt = time.perf_counter() - t0
+                passes += 1
+                if rep == 1 and (best is None or dt < best):
+                    best, best_threads = dt, threads
+            if time.perf_counter() - t_all > budget_s:
+                break
+    per_win = best / nwin
     v = float(np.prod(wl["vol"])) / (per_win * wl["windows"])
-    return {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
-            "sample": f"{vol[0]}x{vol[1]}x{vol[2]} sub-volume ({nwin} windows, fp32, torch-CPU oracle) x{len(times)} passes, seconds/window extrapolated to {wl['windows']} windows"}
+    return {"value": v, "unit": "voxels/s", "cores": best_threads, "host_cores": cores, "kind": "port",
+            "sample": f"{vol[0]}x{vol[1]}x{vol[2]} sub-volume ({nwin} windows, fp32, torch-CPU oracle), {passes} passes over thread counts, best "
+                      f"seconds/window extrapolated to {wl['windows']} windows"}
 
 
 def main():

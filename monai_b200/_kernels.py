@@ -51,6 +51,27 @@ def _call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
     L.check(rc, name)
 
 
+_F32_CACHE: dict = {}
+
+
+def _f32c(t: torch.Tensor | None) -> torch.Tensor | None:
+    """float32 contiguous view of a (parameter) tensor, cached per (storage, version) so fp16 models do not re-convert
+    their weights on every forward."""
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
+    key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype, t.device)
+    hit = _F32_CACHE.get(key)
+    if hit is None:
+        if len(_F32_CACHE) > 4096:
+            _F32_CACHE.clear()
+        hit = t.to(torch.float32).contiguous()
+        _F32_CACHE[key] = hit
+    return hit
+
+
 def _nb(*tensors) -> float:
     return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
 
@@ -101,8 +122,8 @@ def conv3d_direct(
     for t, nm in ((x, "x"), (out, "out")):
         if not t[0].is_contiguous():
             raise ValueError(f"{nm} must be contiguous within each sample")
-    w32 = weight.detach().to(torch.float32).contiguous()
-    b32 = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    w32 = _f32c(weight)
+    b32 = _f32c(bias)
     d = L.ConvDesc(
         N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], int(transposed),
         L.dt(x), L.dt(out), x.stride(0) if N > 1 else Cin * Di * Hi * Wi, out.stride(0) if N > 1 else Cout * Do * Ho * Wo,
@@ -143,9 +164,7 @@ def norm_act(
     S = x[0, 0].numel()
     if out is None:
         out = torch.empty_like(x)
-    g = None if gamma is None else gamma.detach().float().contiguous()
-    b = None if beta is None else beta.detach().float().contiguous()
-    sl = None if slope_t is None else slope_t.detach().float().contiguous()
+    g, b, sl = _f32c(gamma), _f32c(beta), _f32c(slope_t)
     _call("norm_act", L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), eps, L.ptr(g), L.ptr(b), L.ptr(res),
             (res.stride(0) if N > 1 else Cc * S) if res is not None else 0, L.ptr(res_stats), act, float(slope), L.ptr(sl),
             0 if sl is None else sl.numel(), L.ptr(out), out.stride(0) if N > 1 else Cc * S, L.stream_ptr(x.device))
@@ -305,7 +324,7 @@ def conv3x3x3_tc(
     if out is None:
         out = NC8(x.N, Cout, x.sp, x.buf.device)
     stats = torch.zeros((x.N * Cout, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
-    b32 = None if bias is None else bias.detach().float().contiguous()
+    b32 = _f32c(bias)
     d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff)
     _call("conv3x3x3_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.stream_ptr(x.buf.device),
           flops=2.0 * x.N * x.S * Cin * Cout * 27, nbytes=float(x.N * x.S * (Cin + Cout) * 2) + _nb(packed_w))
@@ -367,7 +386,7 @@ def gemm_tc(
         sp = tuple(out_sp) if out_sp is not None else (tuple(2 * s for s in x.sp) if mode == 2 else x.sp)
         out = NC8(x.N, cout, sp, x.buf.device)
     stats = torch.zeros((x.N * N, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
-    b32 = None if bias is None else bias.detach().float().contiguous()
+    b32 = _f32c(bias)
     d = L.GemmTcDesc(
         x.N, x.S, Kd, N, x.C, in_coff, out.C, out_coff, res.C if res is not None else 0, res_coff, out.S, mode, act,
         x.sp[0], x.sp[1], x.sp[2],
@@ -383,8 +402,7 @@ def layernorm_nc8(x: NC8, gamma: torch.Tensor | None, beta: torch.Tensor | None,
     """LayerNorm over channels; with `src` (int32 [S_out]) the output rows are gathered (−1 = zero row)."""
     if out is None:
         out = NC8(x.N, x.C, tuple(out_sp) if out_sp is not None else x.sp, x.buf.device)
-    g = None if gamma is None else gamma.detach().float().contiguous()
-    b = None if beta is None else beta.detach().float().contiguous()
+    g, b = _f32c(gamma), _f32c(beta)
     _call("layernorm_nc8", L.ptr(x.buf), x.N, x.C, x.S, L.ptr(src), out.S, L.ptr(g), L.ptr(b), float(eps), L.ptr(out.buf), L.stream_ptr(x.buf.device),
           nbytes=float(x.N * x.C * (x.S + out.S) * 2))
     return out
@@ -393,7 +411,7 @@ def layernorm_nc8(x: NC8, gamma: torch.Tensor | None, beta: torch.Tensor | None,
 def patch_merge_ln_nc8(x: NC8, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, v2: bool = False) -> NC8:
     sp2 = tuple((s + 1) // 2 for s in x.sp)
     out = NC8(x.N, 8 * x.C, sp2, x.buf.device)
-    g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+    g, b = _f32c(gamma), _f32c(beta)
     _call("patch_merge_ln_nc8", L.ptr(x.buf), x.N, x.C, x.sp[0], x.sp[1], x.sp[2], L.ptr(g), L.ptr(b), float(eps), int(v2), L.ptr(out.buf), L.stream_ptr(x.buf.device))
     return out
 
@@ -415,8 +433,8 @@ def conv_cin1_nc8(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | No
     sp = tuple((s + 2 * pad - k) // stride + 1 for s in (D, H, W))
     if out is None:
         out = NC8(N, Cout, sp, x.device)
-    w32 = weight.detach().float().contiguous()
-    b32 = None if bias is None else bias.detach().float().contiguous()
+    w32 = _f32c(weight)
+    b32 = _f32c(bias)
     stats = torch.zeros((N * Cout, 2), device=x.device, dtype=torch.float32) if want_stats else None
     _call("conv_cin1_nc8", L.ptr(x), L.dt(x), N, D, H, W, L.ptr(w32), L.ptr(b32), Cout, k, stride, pad, L.ptr(out.buf), out.C, out_coff, L.ptr(stats), L.stream_ptr(x.device),
           flops=2.0 * N * sp[0] * sp[1] * sp[2] * Cout * k**3)
@@ -425,8 +443,8 @@ def conv_cin1_nc8(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | No
 
 def head_conv_nc8(x: NC8, weight: torch.Tensor, bias: torch.Tensor | None, out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
     Cout = weight.shape[0]
-    w32 = weight.detach().float().reshape(Cout, -1).contiguous()
-    b32 = None if bias is None else bias.detach().float().contiguous()
+    w32 = _f32c(weight)
+    b32 = _f32c(bias)
     y = torch.empty((x.N, Cout, *x.sp), device=x.buf.device, dtype=out_dtype)
     _call("head_conv_nc8", L.ptr(x.buf), x.N, x.C, x.S, L.ptr(w32), L.ptr(b32), Cout, L.ptr(y), L.dt(y), L.stream_ptr(x.buf.device))
     return y

@@ -1,0 +1,171 @@
+"""Depth-sharded sliding-window inference over the GPUs of one node (BASELINE.json configs[4]).
+
+The reference has no single-volume sharding; its result on one device is the oracle.  Here the
+window set is partitioned by *start layer* along the first spatial axis ("depth"): rank k runs the windows of a
+contiguous group of layers and accumulates fp32 numerators for its slab only.  The only coupling between ranks is
+the overlap-add at slab boundaries, so exactly one exchange step follows: every rank sends each peer the part of its
+slab that the peer *owns* (NCCL P2P over NVLink; gloo in the CPU tests), adds what it receives, normalises its owned
+rows with the analytic count map (no count-map exchange) and the slabs are all-gathered.
+
+`make_shard_plan` / `exchange_partials` are device-agnostic and are unit-tested with gloo on CPU (world_size 2, 3).
+"""
+from __future__ import annotations
+
+from collections.abc import Callable, Sequence
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["ShardPlan", "make_shard_plan", "exchange_partials", "ShardedSlidingWindowInferer"]
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    layers: list[tuple[int, int]]      # per rank: [first, last) start-layer indices along depth
+    slab: list[tuple[int, int]]        # per rank: depth rows covered by its windows [lo, hi)
+    owned: list[tuple[int, int]]       # per rank: depth rows it finalises [lo, hi); a partition of [0, D)
+
+
+def make_shard_plan(starts_d: Sequence[int], roi_d: int, D: int, world: int) -> ShardPlan:
+    """Contiguous, balanced partition of the depth start-layers; ownership cuts sit mid-way through each overlap."""
+    nl = len(starts_d)
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    base, extra = divmod(nl, world)
+    layers, lo = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        layers.append((lo, lo + n))
+        lo += n
+    slab = []
+    for a, b in layers:
+        slab.append((int(starts_d[a]), int(starts_d[b - 1]) + roi_d) if b > a else (0, 0))
+    active = [r for r in range(world) if layers[r][1] > layers[r][0]]
+    owned = [(0, 0)] * world
+    cuts = [0]
+    for i in range(1, len(active)):
+        prev, cur = active[i - 1], active[i]
+        ov_lo, ov_hi = slab[cur][0], slab[prev][1]          # overlap of neighbouring slabs (may be empty)
+        cuts.append((ov_lo + ov_hi) // 2 if ov_hi > ov_lo else ov_lo)
+    cuts.append(D)
+    for i, r in enumerate(active):
+        owned[r] = (cuts[i], cuts[i + 1])
+    return ShardPlan(world, layers, slab, owned)
+
+
+def _intersect(a, b):
+    lo, hi = max(a[0], b[0]), min(a[1], b[1])
+    return (lo, hi) if hi > lo else None
+
+
+def exchange_partials(acc: torch.Tensor, plan: ShardPlan, rank: int, group=None) -> None:
+    """acc [B, C, D, H, W] fp32 holds this rank's partial numerators on its slab rows (zeros elsewhere).  After the
+    call the rows this rank OWNS hold the complete sums.  Sends: my slab ∩ peer's owned rows; receives the converse."""
+    world = plan.world
+    if world == 1:
+        return
+    ops, recv_bufs = [], []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        s = _intersect(plan.slab[rank], plan.owned[peer])
+        if s is not None:
+            buf = acc[:, :, s[0] : s[1]].contiguous()
+            ops.append(dist.P2POp(dist.isend, buf, peer, group=group))
+        r = _intersect(plan.slab[peer], plan.owned[rank])
+        if r is not None:
+            buf = torch.empty_like(acc[:, :, r[0] : r[1]])
+            recv_bufs.append((r, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, peer, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for r, buf in recv_bufs:
+        acc[:, :, r[0] : r[1]] += buf
+
+
+class ShardedSlidingWindowInferer:
+    """`SlidingWindowInferer` whose windows are partitioned over the ranks of the default process group.
+
+    Every rank passes the SAME full volume (or a tensor whose slab rows are valid) and receives the SAME full result.
+    Constructor arguments match `SlidingWindowInferer` (roi_size, sw_batch_size, overlap, mode, sigma_scale).
+    """
+
+    def __init__(self, roi_size, sw_batch_size: int = 1, overlap=0.25, mode="constant", sigma_scale=0.125, gather: bool = True):
+        self.roi_size, self.sw_batch_size, self.overlap, self.mode, self.sigma_scale, self.gather = roi_size, sw_batch_size, overlap, mode, sigma_scale, gather
+
+    def __call__(self, inputs: torch.Tensor, network: Callable[..., torch.Tensor], *args: Any, **kwargs: Any) -> torch.Tensor:
+        from .. import _kernels as K
+        from ..data.utils import dense_patch_starts, importance_factors
+        from ..inferers.utils import _ensure_tuple_rep, _fall_back_tuple, _get_scan_interval
+
+        if inputs.dim() != 5 or not inputs.is_cuda:
+            raise RuntimeError("ShardedSlidingWindowInferer takes CUDA tensors [B, C, D, H, W]")
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        B, _, D, H, W = inputs.shape
+        roi = _fall_back_tuple(self.roi_size, (D, H, W))
+        if any(r > s for r, s in zip(roi, (D, H, W))):
+            raise NotImplementedError("sharded inference expects the volume to be at least one roi in every axis")
+        overlap = _ensure_tuple_rep(self.overlap, 3)
+        interval = _get_scan_interval((D, H, W), roi, 3, overlap)
+        starts = dense_patch_starts((D, H, W), roi, interval)
+        plan = make_shard_plan(starts[0], roi[0], D, world)
+        la, lb = plan.layers[rank]
+        nh, nw = len(starts[1]), len(starts[2])
+        num_win = len(starts[0]) * nh * nw
+        dev = inputs.device
+        mode_s = str(getattr(self.mode, "value", self.mode)).lower()
+        factors, clamp = importance_factors(roi, mode_s, self.sigma_scale)
+        factors = [f.to(dev) for f in factors]
+        starts_t = [torch.tensor(s, dtype=torch.int32, device=dev) for s in starts]
+        x = inputs.detach()
+        x = x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x
+        acc = None
+        out_c = None
+        for b in range(B):
+            ids = [b * num_win + i for i in range(la * nh * nw, lb * nh * nw)]
+            tab = torch.tensor([(b, starts[0][(i % num_win) // (nh * nw)], starts[1][((i % num_win) // nw) % nh], starts[2][(i % num_win) % nw]) for i in ids],
+                               dtype=torch.int32, device=dev).reshape(-1, 4)
+            for g in range(0, len(ids), self.sw_batch_size):
+                win = K.sw_gather(x, tab[g : g + self.sw_batch_size], roi)
+                seg = network(win, *args, **kwargs)
+                if not isinstance(seg, torch.Tensor) or tuple(seg.shape[2:]) != tuple(roi):
+                    raise NotImplementedError("sharded inference supports single-tensor predictors at the input resolution")
+                seg = seg.detach()
+                if acc is None:
+                    out_c = seg.shape[1]
+                    acc = torch.zeros((B, out_c, D, H, W), device=dev, dtype=torch.float32)
+                first = ids[g]
+                n = seg.shape[0]
+                d_lo = int(tab[g, 1])
+                d_hi = int(tab[min(g + n, len(ids)) - 1, 1]) + roi[0]
+                K.sw_blend(1, seg, first, first + n, (B, out_c, D, H, W), roi, starts_t, factors, clamp, None, acc, box=(d_lo, d_hi, 0, 0))
+        if acc is None:  # a rank without windows still takes part in the exchange
+            cshape = torch.zeros(1, dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(cshape, op=dist.ReduceOp.MAX)
+            raise RuntimeError("rank without windows: use fewer ranks than depth start-layers")
+        exchange_partials(acc, plan, rank)
+        o_lo, o_hi = plan.owned[rank]
+        out = torch.empty((B, out_c, D, H, W), device=dev, dtype=inputs.dtype if inputs.dtype in (torch.float16, torch.float32) else torch.float32)
+        K.sw_blend(2, None, 0, B * num_win, (B, out_c, D, H, W), roi, starts_t, factors, clamp, None, out, acc=acc, box=(o_lo, o_hi, 0, 0))
+        if world > 1 and self.gather:
+            ops = []
+            for peer in range(world):
+                lo, hi = plan.owned[peer]
+                if hi <= lo:
+                    continue
+                slab = out[:, :, lo:hi]
+                if slab.is_contiguous():
+                    dist.broadcast(slab, src=peer)
+                else:
+                    buf = slab.contiguous()
+                    dist.broadcast(buf, src=peer)
+                    if peer != rank:
+                        slab.copy_(buf)
+        return out
