@@ -33,8 +33,30 @@ constexpr int kMaxStarts = 512;
 
 // MODE 0: all windows resident -> write normalised result.  MODE 1: accumulate numerators (+=) for the
 // resident window range.  MODE 2: divide accumulators by the analytic count (all windows).
-template <typename TP, typename TO, int MODE>
-__global__ void __launch_bounds__(256) sw_blend_kernel(BlendParams p) {
+//
+// Each thread owns VEC (1 or 2) consecutive voxels along W.  It first lists the covering windows (at most kMaxCover,
+// ascending window index = the reference's accumulation order) with their weights, then streams the predictions in
+// groups of four independent loads so that ~16 requests per thread are in flight (the kernel is HBM-bound: every
+// prediction is read exactly once, the output is written exactly once).
+
+template <typename TP, int VEC> struct PredVec;
+template <> struct PredVec<__half, 1> { static __device__ __forceinline__ void ld(const __half* p, float* v) { v[0] = __half2float(__ldg(p)); } };
+template <> struct PredVec<float, 1> { static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); } };
+template <> struct PredVec<__half, 2> {
+  static __device__ __forceinline__ void ld(const __half* p, float* v) {
+    const __half2 h = __ldg(reinterpret_cast<const __half2*>(p));
+    v[0] = __low2float(h); v[1] = __high2float(h);
+  }
+};
+template <> struct PredVec<float, 2> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    const float2 h = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = h.x; v[1] = h.y;
+  }
+};
+
+template <typename TP, typename TO, int MODE, int VEC>
+__global__ void __launch_bounds__(128) sw_blend_kernel(BlendParams p) {
   __shared__ int s_w[kMaxStarts];
   __shared__ int s_did[32], s_hid[32];
   __shared__ int s_ndc, s_nhc;
@@ -50,26 +72,30 @@ __global__ void __launch_bounds__(256) sw_blend_kernel(BlendParams p) {
     s_nhc = n;
   }
   __syncthreads();
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (w >= p.W) return;
   const int num_win = p.nd * p.nh * p.nw;
   const long long vol = (long long)p.D * p.H * p.W;
   const long long voff = ((long long)d * p.H + h) * p.W + w;
 
-  float cnt = 0.f;
-  float accv[8];
-  constexpr int CMAX = 8;
-  // channels are processed in groups of CMAX so the weight walk is shared between channels
-  for (int c0 = 0; c0 < (MODE == 2 ? 1 : p.C); c0 += CMAX) {
-    const int cn = min(CMAX, p.C - c0);
+  // covering windows along W form a contiguous index range [iw_lo, iw_lo + nwc) because the starts are sorted
+  int iw_lo = 0, nwc = 0;
+  for (int iw = 0; iw < p.nw; ++iw) {
+    const int lw = w - s_w[iw];
+    if (lw >= 0 && lw < p.rw) { if (nwc == 0) iw_lo = iw; ++nwc; }
+  }
+  const TP* preds = (const TP*)p.preds;
+  float cnt[VEC];
+  // channels are walked in pairs so that up to 8 independent loads are in flight per (d,h) window pair
+  for (int c0 = 0; c0 < (MODE == 2 ? 1 : p.C); c0 += 2) {
+    const bool two = (MODE != 2) && (c0 + 1 < p.C);
+    float acc0[VEC], acc1[VEC];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) accv[c] = 0.f;
-    if (MODE == 1) {  // continue the running sums so the addition order stays "one window after the other"
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < cn) accv[c] = *((const float*)p.out + ((long long)b * p.C + c0 + c) * vol + voff);
+    for (int v = 0; v < VEC; ++v) {
+      cnt[v] = 0.f;
+      acc0[v] = (MODE == 1) ? *((const float*)p.out + ((long long)b * p.C + c0) * vol + voff + v) : 0.f;
+      acc1[v] = (MODE == 1 && two) ? *((const float*)p.out + ((long long)b * p.C + c0 + 1) * vol + voff + v) : 0.f;
     }
-    cnt = 0.f;
     for (int a = 0; a < s_ndc; ++a) {
       const int id = s_did[a];
       const int ld = d - p.starts_d[id];
@@ -77,40 +103,62 @@ __global__ void __launch_bounds__(256) sw_blend_kernel(BlendParams p) {
         const int ih = s_hid[e];
         const int lh = h - p.starts_h[ih];
         const float gdh = p.wmap ? 0.f : __fmul_rn(p.gd[ld], p.gh[lh]);
-        for (int iw = 0; iw < p.nw; ++iw) {
-          const int lw = w - s_w[iw];
-          if (lw < 0 || lw >= p.rw) continue;
-          float wt;
-          if (p.wmap) wt = p.wmap[((long long)ld * p.rh + lh) * p.rw + lw];
-          else wt = fmaxf(__fmul_rn(gdh, p.gw[lw]), p.clamp_min);
-          cnt = __fadd_rn(cnt, wt);
-          if (MODE != 2) {
-            const int widx = b * num_win + (id * p.nh + ih) * p.nw + iw;
-            if (widx < p.win_begin || widx >= p.win_end) continue;
-            const TP* pp = (const TP*)p.preds + (long long)(widx - p.win_begin) * p.ps_n +
-                           (long long)ld * p.ps_d + (long long)lh * p.ps_h + (long long)lw * p.ps_w +
-                           (long long)c0 * p.ps_c;
+        const long long rowoff = (long long)ld * p.ps_d + (long long)lh * p.ps_h + (long long)c0 * p.ps_c;
+        const int wbase = b * num_win + (id * p.nh + ih) * p.nw;
+        for (int k0 = 0; k0 < nwc; k0 += 4) {
+          float wt[4][VEC], v0[4][VEC], v1[4][VEC];
+          bool res[4];
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-              if (c < cn) accv[c] = __fadd_rn(accv[c], __fmul_rn(io<TP>::ld(pp + c * p.ps_c), wt));
+          for (int q = 0; q < 4; ++q) {
+            const int iw = iw_lo + k0 + q;
+            const bool in = k0 + q < nwc;
+            const int lw = in ? w - s_w[iw] : 0;
+            const int widx = wbase + iw;
+            res[q] = in && (MODE != 2) && widx >= p.win_begin && widx < p.win_end;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              float t = 0.f;
+              if (in) t = p.wmap ? p.wmap[((long long)ld * p.rh + lh) * p.rw + lw + v] : fmaxf(__fmul_rn(gdh, p.gw[lw + v]), p.clamp_min);
+              wt[q][v] = t; v0[q][v] = 0.f; v1[q][v] = 0.f;
+            }
+            if (res[q]) {
+              const TP* pp = preds + (long long)(widx - p.win_begin) * p.ps_n + rowoff + (long long)lw * p.ps_w;
+              PredVec<TP, VEC>::ld(pp, v0[q]);
+              if (two) PredVec<TP, VEC>::ld(pp + p.ps_c, v1[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              if (k0 + q < nwc) cnt[v] = __fadd_rn(cnt[v], wt[q][v]);
+              if (res[q]) {
+                acc0[v] = __fadd_rn(acc0[v], __fmul_rn(v0[q][v], wt[q][v]));
+                if (two) acc1[v] = __fadd_rn(acc1[v], __fmul_rn(v1[q][v], wt[q][v]));
+              }
+            }
           }
         }
       }
     }
-    if (MODE == 0) {
+    if (MODE == 2) break;
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < cn) io<TO>::st((TO*)p.out + ((long long)b * p.C + c0 + c) * vol + voff, __fdiv_rn(accv[c], cnt));
-    } else if (MODE == 1) {
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < cn) *((float*)p.out + ((long long)b * p.C + c0 + c) * vol + voff) = accv[c];
+    for (int v = 0; v < VEC; ++v) {
+      const long long o0 = ((long long)b * p.C + c0) * vol + voff + v;
+      if (MODE == 0) {
+        io<TO>::st((TO*)p.out + o0, __fdiv_rn(acc0[v], cnt[v]));
+        if (two) io<TO>::st((TO*)p.out + o0 + vol, __fdiv_rn(acc1[v], cnt[v]));
+      } else {
+        *((float*)p.out + o0) = acc0[v];
+        if (two) *((float*)p.out + o0 + vol) = acc1[v];
+      }
     }
   }
   if (MODE == 2) {
     for (int c = 0; c < p.C; ++c) {
       const long long o = ((long long)b * p.C + c) * vol + voff;
-      io<TO>::st((TO*)p.out + o, __fdiv_rn(p.acc[o], cnt));
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) io<TO>::st((TO*)p.out + o + v, __fdiv_rn(p.acc[o + v], cnt[v]));
     }
   }
 }
@@ -133,13 +181,14 @@ __global__ void __launch_bounds__(256) sw_gather_kernel(const TI* __restrict__ v
 
 using namespace b200;
 
-template <int MODE>
-static int launch_blend(const BlendParams& p, int pred_dtype, int out_dtype, cudaStream_t st) {
-  dim3 block(p.W >= 192 ? 256 : (p.W >= 96 ? 128 : 64));
-  dim3 grid(ceil_div(p.W, block.x), p.h1 - p.h0, (p.d1 - p.d0) * p.B);
+template <int MODE, int VEC>
+static int launch_blend_v(const BlendParams& p, int pred_dtype, int out_dtype, cudaStream_t st) {
+  const int wq = (p.W + VEC - 1) / VEC;
+  dim3 block(wq >= 128 ? 128 : (wq >= 64 ? 64 : 32));
+  dim3 grid(ceil_div(wq, block.x), p.h1 - p.h0, (p.d1 - p.d0) * p.B);
   if (grid.y == 0 || grid.z == 0) return B200_OK;
   B200_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "sw_blend: volume too large for the launch grid");
-#define LB(TP, TO) sw_blend_kernel<TP, TO, MODE><<<grid, block, 0, st>>>(p)
+#define LB(TP, TO) sw_blend_kernel<TP, TO, MODE, VEC><<<grid, block, 0, st>>>(p)
   if (MODE == 1) {
     if (pred_dtype == B200_DT_F16) LB(__half, float); else LB(float, float);
   } else if (MODE == 2) {
@@ -153,6 +202,11 @@ static int launch_blend(const BlendParams& p, int pred_dtype, int out_dtype, cud
 #undef LB
   B200_LAUNCH_CHECK("sw_blend_kernel");
   return B200_OK;
+}
+
+template <int MODE>
+static int launch_blend(const BlendParams& p, int pred_dtype, int out_dtype, bool vec2, cudaStream_t st) {
+  return vec2 ? launch_blend_v<MODE, 2>(p, pred_dtype, out_dtype, st) : launch_blend_v<MODE, 1>(p, pred_dtype, out_dtype, st);
 }
 
 extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream) {
@@ -179,9 +233,15 @@ extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream)
   if (p.h1 <= 0) { p.h0 = 0; p.h1 = p.H; }
   B200_REQUIRE(p.d0 >= 0 && p.d1 <= p.D && p.h0 >= 0 && p.h1 <= p.H, "sw_blend: box outside the volume");
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == 0) return launch_blend<0>(p, dsc->pred_dtype, dsc->out_dtype, st);
-  if (mode == 1) return launch_blend<1>(p, dsc->pred_dtype, dsc->out_dtype, st);
-  return launch_blend<2>(p, dsc->pred_dtype, dsc->out_dtype, st);
+  // two voxels per thread when every window start, the roi and W are even and predictions are contiguous along W
+  bool vec2 = (p.W % 2 == 0) && (p.rw % 2 == 0) && (mode == 2 || p.ps_w == 1) && dsc->starts_w_all_even;
+  if (vec2 && mode != 2) {
+    const int esz = dsc->pred_dtype == B200_DT_F16 ? 2 : 4;
+    vec2 = (reinterpret_cast<uintptr_t>(p.preds) % (2 * esz) == 0) && p.ps_n % 2 == 0 && p.ps_c % 2 == 0 && p.ps_d % 2 == 0 && p.ps_h % 2 == 0;
+  }
+  if (mode == 0) return launch_blend<0>(p, dsc->pred_dtype, dsc->out_dtype, vec2, st);
+  if (mode == 1) return launch_blend<1>(p, dsc->pred_dtype, dsc->out_dtype, vec2, st);
+  return launch_blend<2>(p, dsc->pred_dtype, dsc->out_dtype, vec2, st);
 }
 
 extern "C" int b200_sw_gather(const void* vol, int in_dtype, void* out, int out_dtype, const int32_t* win_tab,

@@ -22,27 +22,47 @@ constexpr int kCiT = 8;
 
 // Each thread owns one output voxel and CO_T output channels.  Weights for (CO_T couts x kCiT cins x taps)
 // are staged in shared memory as [tap][ci][co] so the inner product reads them as broadcast vectors.
+// A per-block tap table (valid flag + input offset per axis) removes every division from the inner loops: for a
+// forward conv  i = o*stride + (k - pad); for a transposed conv all voxels of a block share one parity class, so
+// i = o_coarse + (parity + pad - k)/stride for the taps whose numerator is divisible (the others contribute nothing).
 template <typename TI, typename TO, int CO_T>
 __global__ void __launch_bounds__(128) conv3d_direct_kernel(ConvP p) {
   extern __shared__ float s_wt[];  // [ntaps][kCiT][CO_T]
+  __shared__ int s_tap[128][4];    // tap id, dz, dy, dx of the taps that are live for this block
+  __shared__ int s_ntap;
   const b200_conv_desc& d = p.d;
   const int co_blocks = (d.Cout + CO_T - 1) / CO_T;
   const int cob = blockIdx.y % co_blocks;
   const int cls = blockIdx.y / co_blocks;
   const int n = blockIdx.z;
   const int co0 = cob * CO_T;
-  // parity class offsets (transposed conv only; 0 otherwise)
   int pz = 0, py = 0, px = 0;
   if (d.transposed) { px = cls % d.sw; py = (cls / d.sw) % d.sh; pz = cls / (d.sw * d.sh); }
+  if (threadIdx.x == 0) {
+    int nt = 0;
+    for (int tap = 0; tap < p.ntaps && nt < 128; ++tap) {
+      const int kz = tap / (d.kh * d.kw), ky = (tap / d.kw) % d.kh, kx = tap % d.kw;
+      int dz, dy, dx;
+      if (d.transposed) {
+        const int tz = pz + d.pd - kz, ty = py + d.ph - ky, tx = px + d.pw - kx;
+        // floor-division-safe divisibility test (numerators may be negative)
+        if (((tz % d.sd) + d.sd) % d.sd || ((ty % d.sh) + d.sh) % d.sh || ((tx % d.sw) + d.sw) % d.sw) continue;
+        dz = (tz - (((tz % d.sd) + d.sd) % d.sd)) / d.sd; dy = (ty - (((ty % d.sh) + d.sh) % d.sh)) / d.sh; dx = (tx - (((tx % d.sw) + d.sw) % d.sw)) / d.sw;
+      } else {
+        dz = kz - d.pd; dy = ky - d.ph; dx = kx - d.pw;
+      }
+      s_tap[nt][0] = tap; s_tap[nt][1] = dz; s_tap[nt][2] = dy; s_tap[nt][3] = dx;
+      ++nt;
+    }
+    s_ntap = nt;
+  }
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ncoarse = (long long)p.Dc * p.Hc * p.Wc;
   const bool active = t < ncoarse;
-  int oz = 0, oy = 0, ox = 0;
-  if (active) {
-    const int cx = (int)(t % p.Wc), cy = (int)((t / p.Wc) % p.Hc), cz = (int)(t / ((long long)p.Wc * p.Hc));
-    if (d.transposed) { ox = cx * d.sw + px; oy = cy * d.sh + py; oz = cz * d.sd + pz; }
-    else { ox = cx; oy = cy; oz = cz; }
-  }
+  int cz = 0, cy = 0, cx = 0;
+  if (active) { cx = (int)(t % p.Wc); cy = (int)((t / p.Wc) % p.Hc); cz = (int)(t / ((long long)p.Wc * p.Hc)); }
+  const int oz = d.transposed ? cz * d.sd + pz : cz, oy = d.transposed ? cy * d.sh + py : cy, ox = d.transposed ? cx * d.sw + px : cx;
+  const int bz = d.transposed ? cz : cz * d.sd, by = d.transposed ? cy : cy * d.sh, bx = d.transposed ? cx : cx * d.sw;
   const bool inb = active && oz < d.Do && oy < d.Ho && ox < d.Wo;
 
   float acc[CO_T];
@@ -51,12 +71,10 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(ConvP p) {
 
   const long long in_cs = (long long)d.Di * d.Hi * d.Wi;
   const TI* xin = (const TI*)p.x + (long long)n * d.in_stride_n;
-  const int khw = d.kh * d.kw;
 
   for (int ci0 = 0; ci0 < d.Cin; ci0 += kCiT) {
     const int cin = min(kCiT, d.Cin - ci0);
     __syncthreads();
-    // stage weights
     for (int i = threadIdx.x; i < p.ntaps * kCiT * CO_T; i += blockDim.x) {
       const int co = i % CO_T, ci = (i / CO_T) % kCiT, tap = i / (CO_T * kCiT);
       float v = 0.f;
@@ -70,25 +88,27 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(ConvP p) {
     }
     __syncthreads();
     if (!inb) continue;
-    for (int tap = 0; tap < p.ntaps; ++tap) {
-      const int kz = tap / khw, ky = (tap / d.kw) % d.kh, kx = tap % d.kw;
-      int iz, iy, ix;
-      if (d.transposed) {
-        const int tz = oz + d.pd - kz, ty = oy + d.ph - ky, tx = ox + d.pw - kx;
-        if (tz < 0 || ty < 0 || tx < 0) continue;
-        if (tz % d.sd || ty % d.sh || tx % d.sw) continue;  // uniform across the block (parity classes)
-        iz = tz / d.sd; iy = ty / d.sh; ix = tx / d.sw;
-      } else {
-        iz = oz * d.sd - d.pd + kz; iy = oy * d.sh - d.ph + ky; ix = ox * d.sw - d.pw + kx;
-      }
+    const int nt = s_ntap;
+    for (int q = 0; q < nt; ++q) {
+      const int iz = bz + s_tap[q][1], iy = by + s_tap[q][2], ix = bx + s_tap[q][3];
       if (iz < 0 || iz >= d.Di || iy < 0 || iy >= d.Hi || ix < 0 || ix >= d.Wi) continue;
       const TI* xp = xin + (long long)ci0 * in_cs + ((long long)iz * d.Hi + iy) * d.Wi + ix;
-      const float* wp = s_wt + tap * kCiT * CO_T;
-#pragma unroll 4
-      for (int ci = 0; ci < cin; ++ci) {
-        const float xv = io<TI>::ld(xp + (long long)ci * in_cs);
+      const float* wp = s_wt + s_tap[q][0] * kCiT * CO_T;
+      if (cin == kCiT) {
+        float xv[kCiT];
 #pragma unroll
-        for (int c = 0; c < CO_T; ++c) acc[c] = fmaf(xv, wp[ci * CO_T + c], acc[c]);
+        for (int ci = 0; ci < kCiT; ++ci) xv[ci] = io<TI>::ld(xp + (long long)ci * in_cs);
+#pragma unroll
+        for (int ci = 0; ci < kCiT; ++ci) {
+#pragma unroll
+          for (int c = 0; c < CO_T; ++c) acc[c] = fmaf(xv[ci], wp[ci * CO_T + c], acc[c]);
+        }
+      } else {
+        for (int ci = 0; ci < cin; ++ci) {
+          const float xv = io<TI>::ld(xp + (long long)ci * in_cs);
+#pragma unroll
+          for (int c = 0; c < CO_T; ++c) acc[c] = fmaf(xv, wp[ci * CO_T + c], acc[c]);
+        }
       }
     }
   }
@@ -145,7 +165,7 @@ static int launch_conv(const ConvP& p, cudaStream_t st) {
   dim3 block(128), grid(ceil_div(ncoarse, 128), co_blocks * p.cls, d.N);
   B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d_direct: grid too large");
   const size_t smem = (size_t)p.ntaps * kCiT * CO_T * sizeof(float);
-  B200_REQUIRE(smem <= 48 * 1024, "conv3d_direct: kernel volume too large (%d taps)", p.ntaps);
+  B200_REQUIRE(smem <= 40 * 1024 && p.ntaps <= 128, "conv3d_direct: kernel volume too large (%d taps)", p.ntaps);
 #define LC(TI, TO) conv3d_direct_kernel<TI, TO, CO_T><<<grid, block, smem, st>>>(p)
   if (d.in_dtype == B200_DT_F16 && d.out_dtype == B200_DT_F16) LC(__half, __half);
   else if (d.in_dtype == B200_DT_F16 && d.out_dtype == B200_DT_F32) LC(__half, float);

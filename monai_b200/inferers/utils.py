@@ -114,7 +114,9 @@ class _OutputPlan:
         self.roi = seg_shape
         self.vol = tuple(int(i * s) for i, s in zip(image_size, z)) if self.z_scale else tuple(image_size)
         # window starts in output space: int(start * z) exactly as _compute_coords (utils.py:351-360)
-        self.starts = [torch.tensor([int(s * zz) for s in ax], dtype=torch.int32, device=device) for ax, zz in zip(starts, z)]
+        out_starts = [[int(s * zz) for s in ax] for ax, zz in zip(starts, z)]
+        self.starts = [torch.tensor(ax, dtype=torch.int32, device=device) for ax in out_starts]
+        self.starts[2]._all_even = all(v % 2 == 0 for v in out_starts[2])  # enables the 2-voxels-per-thread blend path
         self.batch_size = batch_size
         self.total = total
         per_win = self.chns * int(np.prod(seg_shape))

@@ -123,6 +123,7 @@ class ShardedSlidingWindowInferer:
         factors, clamp = importance_factors(roi, mode_s, self.sigma_scale)
         factors = [f.to(dev) for f in factors]
         starts_t = [torch.tensor(s, dtype=torch.int32, device=dev) for s in starts]
+        starts_t[2]._all_even = all(v % 2 == 0 for v in starts[2])
         x = inputs.detach()
         x = x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x
         acc = None
