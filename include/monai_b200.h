@@ -183,10 +183,12 @@ int b200_patch_merge_ln_nc8(const void* x, int N, int C, int D, int H, int W, co
 
 /* Windowed multi-head self-attention (WindowAttention.forward, swin_unetr.py:509-532) on NC8 tokens in window order:
  * qkv NC8 [N][3C/8][nW*n][8] (channels = [q | k | v], head h = channels [16h, 16h+16) of each third; head_dim 16),
- * bias float32 [heads][n][n] (relative position bias already gathered), region int32 [nW][n] or NULL (shift mask:
- * -100 where regions differ, swin_unetr.py:779-816), out NC8 [N][C/8][nW*n][8]. */
-int b200_window_attention_nc8(const void* qkv, int N, int C, int heads, int nW, int n, float scale, const float* bias,
-                              const int32_t* region, void* out, void* stream);
+ * table float32 [(2ws0-1)(2ws1-1)(2ws2-1)][heads] = relative_position_bias_table of the MODULE window (ws0,ws1,ws2)
+ * (tokens keep base-window coordinates when the window is clamped, as relative_position_index[:n,:n] does),
+ * region int32 [nW][n] or NULL (shift mask: -100 where regions differ, swin_unetr.py:779-816),
+ * out NC8 [N][C/8][nW*n][8]. */
+int b200_window_attention_nc8(const void* qkv, int N, int C, int heads, int nW, int n, float scale, const float* table,
+                              int ws0, int ws1, int ws2, const int32_t* region, void* out, void* stream);
 
 /* Convolution with ONE input channel straight from an NCDHW volume to NC8 (patch embedding k2 s2, the 3x3x3 stem of
  * UnetrBasicBlock and its 1x1x1 residual conv): weight float32 [Cout][1][k][k][k]; stats optional {sum,sumsq}. */

@@ -417,10 +417,14 @@ def patch_merge_ln_nc8(x: NC8, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def window_attention_nc8(qkv: NC8, Cc: int, heads: int, nW: int, n: int, scale: float, biasT: torch.Tensor, region: torch.Tensor | None) -> NC8:
+def window_attention_nc8(qkv: NC8, Cc: int, heads: int, nW: int, n: int, scale: float, table: torch.Tensor, window: Sequence[int],
+                         region: torch.Tensor | None) -> NC8:
+    """table: relative_position_bias_table [(2w0-1)(2w1-1)(2w2-1), heads] of the module window `window`."""
     out = NC8(qkv.N, Cc, qkv.sp, qkv.buf.device)
-    _call("window_attention_nc8", L.ptr(qkv.buf), qkv.N, Cc, heads, nW, n, float(scale), L.ptr(biasT), L.ptr(region), L.ptr(out.buf), L.stream_ptr(qkv.buf.device),
-          flops=4.0 * qkv.N * nW * heads * n * n * 16)
+    tab = _f32c(table)
+    _call("window_attention_nc8", L.ptr(qkv.buf), qkv.N, Cc, heads, nW, n, float(scale), L.ptr(tab), int(window[0]), int(window[1]), int(window[2]),
+          L.ptr(region), L.ptr(out.buf), L.stream_ptr(qkv.buf.device), flops=4.0 * qkv.N * nW * heads * n * n * 16,
+          nbytes=float(qkv.N * 4 * Cc * nW * n * 2))
     return out
 
 

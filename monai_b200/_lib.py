@@ -82,7 +82,7 @@ SIGNATURES = {
     "b200_gemm_tc": (i32, [C.POINTER(GemmTcDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200_layernorm_nc8": (i32, [vp, i32, i32, i64, vp, i64, vp, vp, f32, vp, vp]),
     "b200_patch_merge_ln_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp]),
-    "b200_window_attention_nc8": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
+    "b200_window_attention_nc8": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, i32, i32, i32, vp, vp, vp]),
     "b200_conv_cin1_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
     "b200_head_conv_nc8": (i32, [vp, i32, i32, i64, vp, vp, i32, vp, i32, vp]),
     "b200_norm_act_nc8": (i32, [vp, i32, i32, i32, i32, i64, vp, f32, vp, i32, i32, vp, i32, f32, vp, i32, i32, vp]),

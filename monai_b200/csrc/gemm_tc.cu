@@ -52,6 +52,8 @@ __global__ void gemm_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
   }
 }
 
+// Persistent, warp-specialised: each CTA loops over (batch, row tile, N tile) work items.  Two TMEM accumulator
+// buffers let the epilogue of tile i overlap the MMAs of tile i+1; the shared-memory ring runs across tile boundaries.
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap, GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -62,19 +64,21 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kGemmStages * b_stage);
   uint64_t* full = bars;
   uint64_t* empty = bars + kGemmStages;
-  uint64_t* acc_full = bars + 2 * kGemmStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = bars + 2 * kGemmStages;       // [2]
+  uint64_t* acc_empty = acc_full + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_stats = reinterpret_cast<float*>(bars + 16);  // [2*NT]
 
   const b200_gemm_tc_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * 128, nt = blockIdx.y, n = blockIdx.z;
   const int num_k16 = d.K / 16;
   const int num_stages = (num_k16 + kGemmK16PerStage - 1) / kGemmK16PerStage;
+  const int n_tiles = d.N / NT, row_tiles = (d.S + 127) / 128;
+  const long long total_tiles = (long long)d.Nb * row_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    tc::mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
@@ -87,15 +91,20 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmap);
-      const __half* wbase = p.w + (long long)nt * num_k16 * (NT * 16);
       int s = 0; uint32_t ph = 0;
-      for (int st = 0; st < num_stages; ++st) {
-        const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
-        tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&full[s], kGemmAStage + steps * NT * 32);
-        tc::tma_load_4d(smem_a + s * kGemmAStage, &tmap, &full[s], 0, row0, (d.in_coff / 8) + st * kGemmK16PerStage * 2, n);
-        tc::bulk_load(smem_b + s * b_stage, wbase + (long long)st * kGemmK16PerStage * (NT * 16), steps * NT * 32, &full[s]);
-        if (++s == kGemmStages) { s = 0; ph ^= 1; }
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % n_tiles);
+        const int rt = (int)((tile / n_tiles) % row_tiles);
+        const int n = (int)(tile / ((long long)n_tiles * row_tiles));
+        const __half* wbase = p.w + (long long)nt * num_k16 * (NT * 16);
+        for (int st = 0; st < num_stages; ++st) {
+          const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
+          tc::mbar_wait(&empty[s], ph ^ 1);
+          tc::mbar_arrive_expect_tx(&full[s], kGemmAStage + steps * NT * 32);
+          tc::tma_load_4d(smem_a + s * kGemmAStage, &tmap, &full[s], 0, rt * 128, (d.in_coff / 8) + st * kGemmK16PerStage * 2, n);
+          tc::bulk_load(smem_b + s * b_stage, wbase + (long long)st * kGemmK16PerStage * (NT * 16), steps * NT * 32, &full[s]);
+          if (++s == kGemmStages) { s = 0; ph ^= 1; }
+        }
       }
     }
     __syncwarp();
@@ -103,88 +112,107 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_f16(128, NT);
       int s = 0; uint32_t ph = 0;
-      for (int st = 0; st < num_stages; ++st) {
-        const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
-        tc::mbar_wait(&full[s], ph);
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t aph = (uint32_t)((it >> 1) & 1);
+        tc::mbar_wait(&acc_empty[buf], aph ^ 1);     // epilogue has drained this accumulator buffer
         tc::fence_after_sync();
-        const uint32_t a_base = tc::smem_u32(smem_a + s * kGemmAStage), b_base = tc::smem_u32(smem_b + s * b_stage);
-        for (int k = 0; k < steps; ++k) {
-          const uint64_t adesc = tc::make_desc_kmajor_noswz(a_base + k * 2 * 2048, 2048, 128);
-          const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_base + k * NT * 32, NT * 16, 128);
-          tc::mma_f16_ss(tmem_base, adesc, bdesc, idesc, (st | k) != 0 ? 1u : 0u);
+        const uint32_t tacc = tmem_base + buf * NT;
+        for (int st = 0; st < num_stages; ++st) {
+          const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
+          tc::mbar_wait(&full[s], ph);
+          tc::fence_after_sync();
+          const uint32_t a_base = tc::smem_u32(smem_a + s * kGemmAStage), b_base = tc::smem_u32(smem_b + s * b_stage);
+          for (int k = 0; k < steps; ++k) {
+            const uint64_t adesc = tc::make_desc_kmajor_noswz(a_base + k * 2 * 2048, 2048, 128);
+            const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_base + k * NT * 32, NT * 16, 128);
+            tc::mma_f16_ss(tacc, adesc, bdesc, idesc, (st | k) != 0 ? 1u : 0u);
+          }
+          tc::mma_commit(&empty[s]);
+          if (++s == kGemmStages) { s = 0; ph ^= 1; }
         }
-        tc::mma_commit(&empty[s]);
-        if (++s == kGemmStages) { s = 0; ph ^= 1; }
+        tc::mma_commit(&acc_full[buf]);
       }
-      tc::mma_commit(acc_full);
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int row = row0 + q * 32 + lane;
-    const bool row_ok = row < d.S;
-    // destination row (identity, table lookup, or 2x-upsample scatter computed per tap below)
-    long long drow = row;
-    if (row_ok && p.row_map) drow = p.row_map[row];  // the map is shared by all batch items
-    const bool dst_ok = row_ok && drow >= 0;
-    int vz = 0, vy = 0, vx = 0;
-    if (d.mode == 2 && row_ok) { vx = row % d.W; vy = (row / d.W) % d.H; vz = row / (d.W * d.H); }
-    tc::mbar_wait(acc_full, 0);
-    tc::fence_after_sync();
-    const int co0 = nt * NT;
     const int cout = d.mode == 2 ? d.N / 8 : d.N;  // channels of the destination tensor written by this GEMM
-    __half* ybase = p.y + ((long long)n * (d.out_ctot / 8)) * d.S_out * 8;
-    const __half* rbase = p.res ? p.res + ((long long)n * (d.res_ctot / 8)) * d.S_out * 8 : nullptr;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = (int)(tile % n_tiles);
+      const int rt = (int)((tile / n_tiles) % row_tiles);
+      const int n = (int)(tile / ((long long)n_tiles * row_tiles));
+      const int buf = it & 1;
+      const uint32_t aph = (uint32_t)((it >> 1) & 1);
+      const int row = rt * 128 + q * 32 + lane;
+      const bool row_ok = row < d.S;
+      long long drow = row;
+      if (row_ok && p.row_map) drow = p.row_map[row];  // the map is shared by all batch items
+      const bool dst_ok = row_ok && drow >= 0;
+      int vz = 0, vy = 0, vx = 0;
+      if (d.mode == 2 && row_ok) { vx = row % d.W; vy = (row / d.W) % d.H; vz = row / (d.W * d.H); }
+      const int co0 = nt * NT;
+      __half* ybase = p.y + ((long long)n * (d.out_ctot / 8)) * d.S_out * 8;
+      const __half* rbase = p.res ? p.res + ((long long)n * (d.res_ctot / 8)) * d.S_out * 8 : nullptr;
+      tc::mbar_wait(&acc_full[buf], aph);
+      tc::fence_after_sync();
+      const uint32_t tacc = tmem_base + buf * NT + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int cc = 0; cc < NT / 8; ++cc) {
-      uint32_t v[8];
-      tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 8, v);
-      tc::tmem_ld_wait();
-      const int nc = co0 + cc * 8;  // first GEMM column of this chunk
-      float f[8];
+      for (int cc = 0; cc < NT / 8; ++cc) {
+        uint32_t v[8];
+        tc::tmem_ld8(tacc + cc * 8, v);
+        tc::tmem_ld_wait();
+        const int nc = co0 + cc * 8;  // first GEMM column of this chunk
+        float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[d.mode == 2 ? (nc + j) % cout : nc + j] : 0.f);
-      if (d.act == 4) {
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[d.mode == 2 ? (nc + j) % cout : nc + j] : 0.f);
+        if (d.act == 4) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
-      }
-      long long orow = drow; int ochunk;
-      if (d.mode == 2) {
-        const int tap = nc / cout;  // GEMM columns are ordered [tap][cout]
-        ochunk = (d.out_coff + (nc % cout)) / 8;
-        orow = ((long long)(2 * vz + (tap >> 2)) * (2 * d.H) + (2 * vy + ((tap >> 1) & 1))) * (2 * d.W) + (2 * vx + (tap & 1));
-      } else {
-        ochunk = (d.out_coff + nc) / 8;
-      }
-      if (dst_ok) {
-        if (rbase) {
-          __align__(16) __half rv[8];
-          *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(rbase + (((long long)(d.res_coff + nc) / 8) * d.S_out + orow) * 8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] += __half2float(rv[j]);
+          for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
         }
-        __align__(16) __half hv[8];
+        long long orow = drow; int ochunk;
+        if (d.mode == 2) {
+          const int tap = nc / cout;  // GEMM columns are ordered [tap][cout]
+          ochunk = (d.out_coff + (nc % cout)) / 8;
+          orow = ((long long)(2 * vz + (tap >> 2)) * (2 * d.H) + (2 * vy + ((tap >> 1) & 1))) * (2 * d.W) + (2 * vx + (tap & 1));
+        } else {
+          ochunk = (d.out_coff + nc) / 8;
+        }
+        if (dst_ok) {
+          if (rbase) {
+            __align__(16) __half rv[8];
+            *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(rbase + (((long long)(d.res_coff + nc) / 8) * d.S_out + orow) * 8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(f[j]);
-        *reinterpret_cast<uint4*>(ybase + ((long long)ochunk * d.S_out + orow) * 8) = *reinterpret_cast<const uint4*>(hv);
+            for (int j = 0; j < 8; ++j) f[j] += __half2float(rv[j]);
+          }
+          __align__(16) __half hv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(f[j]);
+          *reinterpret_cast<uint4*>(ybase + ((long long)ochunk * d.S_out + orow) * 8) = *reinterpret_cast<const uint4*>(hv);
+        }
+        if (p.stats) {
+          float a1[8], b1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a1[j] = dst_ok ? f[j] : 0.f; b1[j] = a1[j] * a1[j]; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a1[j] = warp_sum(a1[j]); b1[j] = warp_sum(b1[j]); }
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { atomicAdd(&s_stats[2 * (cc * 8 + j)], a1[j]); atomicAdd(&s_stats[2 * (cc * 8 + j) + 1], b1[j]); }
+          }
+        }
       }
+      // this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
+      tc::fence_before_sync();
+      tc::mbar_arrive(&acc_empty[buf]);
       if (p.stats) {
-        float a1[8], b1[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { a1[j] = dst_ok ? f[j] : 0.f; b1[j] = a1[j] * a1[j]; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { a1[j] = warp_sum(a1[j]); b1[j] = warp_sum(b1[j]); }
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { atomicAdd(&s_stats[2 * (cc * 8 + j)], a1[j]); atomicAdd(&s_stats[2 * (cc * 8 + j) + 1], b1[j]); }
-        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t = threadIdx.x - 64;
+        for (int i = t; i < 2 * NT; i += 128) { atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-    }
-    tc::fence_before_sync();
-    if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;
-      for (int i = t; i < 2 * NT; i += 128) atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]);
     }
   }
   __syncthreads();
@@ -244,15 +272,15 @@ extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const 
   GemmTcParams p;
   p.d = d; p.w = (const __half*)packed_w; p.bias = bias; p.y = (__half*)y; p.res = (const __half*)res; p.stats = stats;
   p.row_map = row_map; p.NT = NT;
-  p.tmem_cols = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
+  p.tmem_cols = 2 * NT <= 32 ? 32 : 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;  // two accumulator buffers
   const int smem = kGemmStages * (kGemmAStage + kGemmK16PerStage * NT * 32) + 128 + 2 * NT * 4 + 128;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  dim3 grid(ceil_div(d.S, 128), d.N / NT, d.Nb);
-  B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm_tc: grid too large");
+  const long long total_tiles = (long long)ceil_div(d.S, 128) * (d.N / NT) * d.Nb;
+  dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
   gemm_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmap, p);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   return B200_OK;

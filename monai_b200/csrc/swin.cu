@@ -124,88 +124,161 @@ __global__ void __launch_bounds__(128) patch_merge_ln_nc8_kernel(const __half* _
 }
 
 // ---------------------------------------------------------------------------------------------- window attention
-// one block = one (window, head, batch item); K and V of the head are staged in shared memory as fp32.
-__global__ void __launch_bounds__(128) window_attention_nc8_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int C,
-                                                                   int nW, int n, float scale, const float* __restrict__ biasT,
-                                                                   const int* __restrict__ region) {
-  extern __shared__ float s_kv[];  // K[n][16], V[n][16], region[n]
-  float* sK = s_kv;
-  float* sV = s_kv + (size_t)n * 16;
-  int* sR = reinterpret_cast<int*>(sV + (size_t)n * 16);
+// Flash-style attention for one (window, head, batch item) per block: K and V^T of the head are staged in shared
+// memory once; each warp owns 16 query rows at a time and walks the keys 16 at a time:
+//   S = Q K^T (2 x mma.m16n8k16, K = head_dim = 16 is a single MMA step), + relative-position bias + shift mask,
+//   online softmax in the accumulator registers, O += P V (2 x mma.m16n8k16, P re-used from the S fragments).
+// The relative-position bias is looked up in the (2w-1)^3-entry table held in shared memory:
+//   index(i, j) = lin(i) - lin(j) + const,  lin(t) = d*(2w1-1)(2w2-1) + h*(2w2-1) + w  with the token's coordinates in
+// the MODULE window (the reference slices relative_position_index[:n, :n], swin_unetr.py:514-516, so clamped windows
+// keep base-`window_size` coordinates).  With head_dim 16 the kernel is bound by exp/softmax issue, not by the MMAs,
+// which is why the legacy warp-level mma.sync path is used here instead of a tcgen05 + TMEM round trip.
+constexpr int kAttKStride = 24;   // halfs per K row in smem (48 B: conflict-free b-fragment loads)
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256) window_attention_nc8_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int C,
+                                                                   int heads, int nW, int n, float scale,
+                                                                   const float* __restrict__ table, int tab_len, int ws0, int ws1,
+                                                                   int ws2, const int* __restrict__ region) {
+  extern __shared__ __align__(16) uint8_t s_att[];
+  const int npad = (n + 15) / 16 * 16;
+  const int vstride = npad + 8;                       // halfs per V^T row (conflict-free b-fragment loads)
+  __half* sK = reinterpret_cast<__half*>(s_att);      // [npad][kAttKStride]
+  __half* sVt = sK + (size_t)npad * kAttKStride;      // [16][vstride]
+  float* sTab = reinterpret_cast<float*>(sVt + 16 * vstride);  // [tab_len]
+  short* sLin = reinterpret_cast<short*>(sTab + tab_len);      // [npad]
+  unsigned char* sReg = reinterpret_cast<unsigned char*>(sLin + npad);  // [npad]
   const int w = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int C8 = C / 8;
   const long long T = (long long)nW * n;
   const __half* base = qkv + (long long)b * (3 * C8) * T * 8;
   const long long row0 = (long long)w * n;
-  for (int i = threadIdx.x; i < n * 2; i += blockDim.x) {
-    const int t = i >> 1, half_ = i & 1;
-    float f[8];
-    ld8(base + ((long long)(C8 + 2 * h + half_) * T + row0 + t) * 8, f);
+  const int s1 = 2 * ws2 - 1, s0 = (2 * ws1 - 1) * s1;
+
+  for (int i = threadIdx.x; i < npad * 2; i += blockDim.x) {
+    const int t = i >> 1, hf = i & 1;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (t < n) {
+      kv = *reinterpret_cast<const uint4*>(base + ((long long)(C8 + 2 * h + hf) * T + row0 + t) * 8);
+      vv = *reinterpret_cast<const uint4*>(base + ((long long)(2 * C8 + 2 * h + hf) * T + row0 + t) * 8);
+    }
+    *reinterpret_cast<uint4*>(sK + t * kAttKStride + hf * 8) = kv;
+    const __half* vh = reinterpret_cast<const __half*>(&vv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sK[t * 16 + half_ * 8 + j] = f[j];
-    ld8(base + ((long long)(2 * C8 + 2 * h + half_) * T + row0 + t) * 8, f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sV[t * 16 + half_ * 8 + j] = f[j];
+    for (int j = 0; j < 8; ++j) sVt[(hf * 8 + j) * vstride + t] = vh[j];
   }
-  if (region)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sR[i] = region[(long long)w * n + i];
+  for (int i = threadIdx.x; i < tab_len; i += blockDim.x) sTab[i] = table[(long long)i * heads + h];
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    const int td = i / (ws1 * ws2), th = (i / ws2) % ws1, tw = i % ws2;
+    sLin[i] = (short)(td * s0 + th * s1 + tw);
+    sReg[i] = (region && i < n) ? (unsigned char)region[(long long)w * n + i] : 0;
+  }
   __syncthreads();
-  const float* bh = biasT + (long long)h * n * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float q[16], o[16];
-    {
-      float f[8];
-      ld8(base + ((long long)(2 * h) * T + row0 + i) * 8, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] = f[j] * scale;
-      ld8(base + ((long long)(2 * h + 1) * T + row0 + i) * 8, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) q[8 + j] = f[j] * scale;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const int nwarps = blockDim.x >> 5;
+  const int lin_c = (ws0 - 1) * s0 + (ws1 - 1) * s1 + (ws2 - 1);
+  __half* ob = out + (long long)b * C8 * T * 8;
+  for (int rt = warp; rt * 16 < n; rt += nwarps) {
+    const int r0 = rt * 16 + g, r1 = r0 + 8;
+    // Q fragments (row-major A operand): a0 (r0, d 2t..), a1 (r1, d 2t..), a2 (r0, d 2t+8..), a3 (r1, d 2t+8..)
+    uint32_t qa[4] = {0, 0, 0, 0};
+    if (r0 < n) {
+      qa[0] = *reinterpret_cast<const uint32_t*>(base + ((long long)(2 * h) * T + row0 + r0) * 8 + 2 * t4);
+      qa[2] = *reinterpret_cast<const uint32_t*>(base + ((long long)(2 * h + 1) * T + row0 + r0) * 8 + 2 * t4);
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    const int ri = region ? sR[i] : 0;
-    for (int j = 0; j < n; ++j) {
-      const float4* kp = reinterpret_cast<const float4*>(sK + j * 16);
-      float s = 0.f;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float4 kv = kp[t];
-        s = fmaf(q[4 * t], kv.x, s); s = fmaf(q[4 * t + 1], kv.y, s); s = fmaf(q[4 * t + 2], kv.z, s); s = fmaf(q[4 * t + 3], kv.w, s);
-      }
-      s += bh[(long long)j * n + i];
-      if (region && sR[j] != ri) s += -100.0f;
-      const float mn = fmaxf(m, s);
-      const float corr = __expf(m - mn), pj = __expf(s - mn);
-      l = l * corr + pj;
-      const float4* vp = reinterpret_cast<const float4*>(sV + j * 16);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float4 vv = vp[t];
-        o[4 * t] = fmaf(o[4 * t], corr, pj * vv.x); o[4 * t + 1] = fmaf(o[4 * t + 1], corr, pj * vv.y);
-        o[4 * t + 2] = fmaf(o[4 * t + 2], corr, pj * vv.z); o[4 * t + 3] = fmaf(o[4 * t + 3], corr, pj * vv.w);
-      }
-      m = mn;
+    if (r1 < n) {
+      qa[1] = *reinterpret_cast<const uint32_t*>(base + ((long long)(2 * h) * T + row0 + r1) * 8 + 2 * t4);
+      qa[3] = *reinterpret_cast<const uint32_t*>(base + ((long long)(2 * h + 1) * T + row0 + r1) * 8 + 2 * t4);
     }
-    const float inv = 1.f / l;
-    float f0[8], f1[8];
+    const int lin0 = sLin[min(r0, npad - 1)] + lin_c, lin1 = sLin[min(r1, npad - 1)] + lin_c;
+    const int reg0 = sReg[min(r0, npad - 1)], reg1 = sReg[min(r1, npad - 1)];
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // O tile: d 0-7 and d 8-15
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int j0 = 0; j0 < npad; j0 += 16) {
+      float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // keys j0..j0+7 and j0+8..j0+15
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { f0[j] = o[j] * inv; f1[j] = o[8 + j] * inv; }
-    __half* ob = out + (long long)b * C8 * T * 8;
-    st8(ob + ((long long)(2 * h) * T + row0 + i) * 8, f0);
-    st8(ob + ((long long)(2 * h + 1) * T + row0 + i) * 8, f1);
+      for (int nt = 0; nt < 2; ++nt) {
+        const __half* kp = sK + (j0 + nt * 8 + g) * kAttKStride + 2 * t4;
+        mma_16816(sc[nt], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = j0 + nt * 8 + 2 * t4 + e;
+          float v0 = -INFINITY, v1 = -INFINITY;
+          if (j < n) {
+            const int lj = sLin[j];
+            v0 = fmaf(sc[nt][e], scale, sTab[lin0 - lj]);
+            v1 = fmaf(sc[nt][2 + e], scale, sTab[lin1 - lj]);
+            if (region) {
+              const int rj = sReg[j];
+              if (rj != reg0) v0 += -100.0f;
+              if (rj != reg1) v1 += -100.0f;
+            }
+          }
+          sc[nt][e] = v0; sc[nt][2 + e] = v1;
+          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float c0 = __expf(m0 - mn0), c1 = __expf(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pa[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float p00 = __expf(sc[nt][0] - mn0), p01 = __expf(sc[nt][1] - mn0);
+        const float p10 = __expf(sc[nt][2] - mn1), p11 = __expf(sc[nt][3] - mn1);
+        ps0 += p00 + p01; ps1 += p10 + p11;
+        pa[nt * 2] = pack_h2(p00, p01);       // a0 / a2: row r0
+        pa[nt * 2 + 1] = pack_h2(p10, p11);   // a1 / a3: row r1
+      }
+      l0 = l0 * c0 + ps0; l1 = l1 * c1 + ps1;
+#pragma unroll
+      for (int dt = 0; dt < 2; ++dt) {
+        o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1;
+        const __half* vp = sVt + (dt * 8 + g) * vstride + j0 + 2 * t4;
+        mma_16816(o[dt], pa, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+    for (int dt = 0; dt < 2; ++dt) {
+      if (r0 < n) *reinterpret_cast<uint32_t*>(ob + ((long long)(2 * h + dt) * T + row0 + r0) * 8 + 2 * t4) = pack_h2(o[dt][0] * i0, o[dt][1] * i0);
+      if (r1 < n) *reinterpret_cast<uint32_t*>(ob + ((long long)(2 * h + dt) * T + row0 + r1) * 8 + 2 * t4) = pack_h2(o[dt][2] * i1, o[dt][3] * i1);
+    }
   }
 }
 
 // -------------------------------------------------------------------------------------- single-input-channel convs
-template <typename T>
+// Each thread computes kVox consecutive output voxels along W for all Cout channels, 8 channels at a time: the k*k*
+// (k + (kVox-1)*stride) input values live in registers, every weight vector is read from shared memory once (LDS.128)
+// and reused for the kVox voxels, so the inner loop is FMA-bound (32 FMA per 2 LDS.128).
+constexpr int kVox = 4;
+
+template <typename T, int KS, int STRIDE>
 __global__ void __launch_bounds__(128) conv_cin1_nc8_kernel(const T* __restrict__ x, __half* __restrict__ y, const float* __restrict__ wgt,
                                                             const float* __restrict__ bias, int D, int H, int W, int Do, int Ho, int Wo,
-                                                            int Cout, int k, int stride, int pad, int out_ctot, int out_coff,
-                                                            float* __restrict__ stats) {
-  extern __shared__ float s_w[];  // [taps][Cout], then stats [2*Cout]
-  const int taps = k * k * k;
+                                                            int Cout, int pad, int out_ctot, int out_coff, float* __restrict__ stats) {
+  extern __shared__ __align__(16) float s_w[];  // [taps][Cout], then stats [2*Cout]
+  constexpr int taps = KS * KS * KS;
+  constexpr int XW = KS + (kVox - 1) * STRIDE;
   float* s_st = s_w + taps * Cout;
   for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
     const int co = i % Cout, t = i / Cout;
@@ -214,37 +287,67 @@ __global__ void __launch_bounds__(128) conv_cin1_nc8_kernel(const T* __restrict_
   for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) s_st[i] = 0.f;
   __syncthreads();
   const int n = blockIdx.y;
+  const int Wq = (Wo + kVox - 1) / kVox;
   const long long So = (long long)Do * Ho * Wo;
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool ok = r < So;
-  float xv[27];
+  const bool ok = r < (long long)Do * Ho * Wq;
+  const int ox0 = ok ? (int)(r % Wq) * kVox : 0, oy = ok ? (int)((r / Wq) % Ho) : 0, oz = ok ? (int)(r / ((long long)Wq * Ho)) : 0;
+  float xv[KS][KS][XW];
   if (ok) {
-    const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), oz = (int)(r / ((long long)Wo * Ho));
     const T* xn = x + (long long)n * D * H * W;
-    for (int t = 0; t < taps; ++t) {
-      const int kz = t / (k * k), ky = (t / k) % k, kx = t % k;
-      const int iz = oz * stride - pad + kz, iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-      xv[t] = (iz >= 0 && iz < D && iy >= 0 && iy < H && ix >= 0 && ix < W) ? io<T>::ld(xn + ((long long)iz * H + iy) * W + ix) : 0.f;
-    }
+#pragma unroll
+    for (int kz = 0; kz < KS; ++kz)
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        const int iz = oz * STRIDE - pad + kz, iy = oy * STRIDE - pad + ky;
+        const bool rok = iz >= 0 && iz < D && iy >= 0 && iy < H;
+#pragma unroll
+        for (int q = 0; q < XW; ++q) {
+          const int ix = ox0 * STRIDE - pad + q;
+          xv[kz][ky][q] = (rok && ix >= 0 && ix < W) ? io<T>::ld(xn + ((long long)iz * H + iy) * W + ix) : 0.f;
+        }
+      }
   }
   const int lane = threadIdx.x & 31;
-  __half* yo = y + (((long long)n * (out_ctot / 8) + out_coff / 8) * So + r) * 8;
+  const long long vbase = ((long long)oz * Ho + oy) * Wo + ox0;
+  __half* yo = y + (((long long)n * (out_ctot / 8) + out_coff / 8) * So + vbase) * 8;
   for (int c0 = 0; c0 < Cout; c0 += 8) {
-    float acc[8];
+    float acc[kVox][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
-    if (ok)
-      for (int t = 0; t < taps; ++t) {
-        const float xt = xv[t];
+    for (int v = 0; v < kVox; ++v)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xt, s_w[t * Cout + c0 + j], acc[j]);
-      }
-    if (ok) st8(yo + (long long)(c0 / 8) * So * 8, acc);
+      for (int j = 0; j < 8; ++j) acc[v][j] = bias ? bias[c0 + j] : 0.f;
+    if (ok) {
+#pragma unroll
+      for (int kz = 0; kz < KS; ++kz)
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const int t = (kz * KS + ky) * KS + kx;
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * Cout + c0);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_w + t * Cout + c0 + 4);
+#pragma unroll
+            for (int v = 0; v < kVox; ++v) {
+              const float xt = xv[kz][ky][v * STRIDE + kx];
+              acc[v][0] = fmaf(xt, w0.x, acc[v][0]); acc[v][1] = fmaf(xt, w0.y, acc[v][1]);
+              acc[v][2] = fmaf(xt, w0.z, acc[v][2]); acc[v][3] = fmaf(xt, w0.w, acc[v][3]);
+              acc[v][4] = fmaf(xt, w1.x, acc[v][4]); acc[v][5] = fmaf(xt, w1.y, acc[v][5]);
+              acc[v][6] = fmaf(xt, w1.z, acc[v][6]); acc[v][7] = fmaf(xt, w1.w, acc[v][7]);
+            }
+          }
+#pragma unroll
+      for (int v = 0; v < kVox; ++v)
+        if (ox0 + v < Wo) st8(yo + ((long long)(c0 / 8) * So + v) * 8, acc[v]);
+    }
     if (stats) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float a = ok ? acc[j] : 0.f;
-        const float s1 = warp_sum(a), s2 = warp_sum(a * a);
+        float a = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < kVox; ++v)
+          if (ok && ox0 + v < Wo) { a += acc[v][j]; q2 = fmaf(acc[v][j], acc[v][j], q2); }
+        const float s1 = warp_sum(a), s2 = warp_sum(q2);
         if (lane == 0) { atomicAdd(&s_st[2 * (c0 + j)], s1); atomicAdd(&s_st[2 * (c0 + j) + 1], s2); }
       }
     }
@@ -308,21 +411,45 @@ extern "C" int b200_patch_merge_ln_nc8(const void* x, int N, int C, int D, int H
 }
 
 extern "C" int b200_window_attention_nc8(const void* qkv, int N, int C, int heads, int nW, int n, float scale,
-                                         const float* bias, const int32_t* region, void* out, void* stream) {
-  B200_REQUIRE(qkv && out && bias, "window_attention_nc8: null pointer");
+                                         const float* table, int ws0, int ws1, int ws2, const int32_t* region, void* out,
+                                         void* stream) {
+  B200_REQUIRE(qkv && out && table, "window_attention_nc8: null pointer");
   B200_REQUIRE(N > 0 && heads > 0 && nW > 0 && n > 0, "window_attention_nc8: empty problem");
   B200_REQUIRE(C == heads * 16, "window_attention_nc8: head_dim must be 16 (C = %d, heads = %d)", C, heads);
-  B200_REQUIRE(nW <= 2147483647 / n && heads <= 65535 && N <= 65535, "window_attention_nc8: grid too large");
-  const size_t smem = (size_t)n * 32 * sizeof(float) + (size_t)n * sizeof(int);
-  B200_REQUIRE(smem <= 160 * 1024, "window_attention_nc8: window of %d tokens does not fit in shared memory", n);
+  B200_REQUIRE(ws0 > 0 && ws1 > 0 && ws2 > 0 && n <= ws0 * ws1 * ws2, "window_attention_nc8: window of %d tokens exceeds the module window", n);
+  B200_REQUIRE(heads <= 65535 && N <= 65535, "window_attention_nc8: grid too large");
+  const int npad = (n + 15) / 16 * 16;
+  const int tab_len = (2 * ws0 - 1) * (2 * ws1 - 1) * (2 * ws2 - 1);
+  B200_REQUIRE(tab_len < 32768, "window_attention_nc8: relative position table too large");
+  const size_t smem = (size_t)npad * kAttKStride * 2 + (size_t)16 * (npad + 8) * 2 + (size_t)tab_len * 4 + (size_t)npad * 2 + npad + 16;
+  B200_REQUIRE(smem <= 200 * 1024, "window_attention_nc8: window of %d tokens does not fit in shared memory", n);
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(window_attention_nc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(window_attention_nc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   dim3 grid(nW, heads, N);
-  window_attention_nc8_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)out, C, nW, n, scale, bias, region);
+  const int threads = n >= 128 ? 256 : (n >= 64 ? 128 : 64);
+  window_attention_nc8_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)out, C, heads, nW, n, scale, table,
+                                                                          tab_len, ws0, ws1, ws2, region);
   B200_LAUNCH_CHECK("window_attention_nc8_kernel");
+  return B200_OK;
+}
+
+template <typename T>
+static int launch_cin1(const T* x, __half* y, const float* weight, const float* bias, int N, int D, int H, int W, int Do, int Ho, int Wo,
+                       int Cout, int k, int stride, int pad, int out_ctot, int out_coff, float* stats, cudaStream_t st) {
+  const long long units = (long long)Do * Ho * ((Wo + kVox - 1) / kVox);
+  dim3 grid(ceil_div(units, 128), N);
+  const size_t smem = ((size_t)k * k * k * Cout + 2 * Cout) * sizeof(float);
+#define LCI(KS, SS) conv_cin1_nc8_kernel<T, KS, SS><<<grid, 128, smem, st>>>(x, y, weight, bias, D, H, W, Do, Ho, Wo, Cout, pad, out_ctot, out_coff, stats)
+  if (k == 3 && stride == 1) LCI(3, 1);
+  else if (k == 2 && stride == 2) LCI(2, 2);
+  else if (k == 1 && stride == 1) LCI(1, 1);
+  else if (k == 3 && stride == 2) LCI(3, 2);
+  else return set_err(B200_ERR_UNSUPPORTED, "conv_cin1_nc8: (kernel, stride) must be (3,1), (2,2), (1,1) or (3,2), got (%d,%d)", k, stride);
+#undef LCI
+  B200_LAUNCH_CHECK("conv_cin1_nc8_kernel");
   return B200_OK;
 }
 
@@ -335,17 +462,13 @@ extern "C" int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H,
                "conv_cin1_nc8: channel counts must be multiples of 8");
   const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   B200_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, "conv_cin1_nc8: empty output");
-  const long long So = (long long)Do * Ho * Wo;
-  dim3 grid(ceil_div(So, 128), N);
-  const size_t smem = ((size_t)k * k * k * Cout + 2 * Cout) * sizeof(float);
+  B200_REQUIRE(((size_t)k * k * k * Cout + 2 * Cout) * sizeof(float) <= 48 * 1024, "conv_cin1_nc8: Cout too large");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200_DT_F16)
-    conv_cin1_nc8_kernel<__half><<<grid, 128, smem, st>>>((const __half*)x, (__half*)y, weight, bias, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, stats);
-  else if (dtype == B200_DT_F32)
-    conv_cin1_nc8_kernel<float><<<grid, 128, smem, st>>>((const float*)x, (__half*)y, weight, bias, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, stats);
-  else return set_err(B200_ERR_INVALID, "conv_cin1_nc8: bad dtype");
-  B200_LAUNCH_CHECK("conv_cin1_nc8_kernel");
-  return B200_OK;
+    return launch_cin1<__half>((const __half*)x, (__half*)y, weight, bias, N, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, stats, st);
+  if (dtype == B200_DT_F32)
+    return launch_cin1<float>((const float*)x, (__half*)y, weight, bias, N, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, stats, st);
+  return set_err(B200_ERR_INVALID, "conv_cin1_nc8: bad dtype");
 }
 
 extern "C" int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,

@@ -342,16 +342,6 @@ class SwinUNETR(nn.Module):
 
         return self._cache.get(("up", key, conv.weight.device), [conv.weight], build)
 
-    def _attn_tables(self, blk: SwinTransformerBlock, key: str, n: int, dev):
-        attn = blk.attn
-
-        def build():
-            idx = attn.relative_position_index[:n, :n].reshape(-1).to(attn.relative_position_bias_table.device)
-            bias = attn.relative_position_bias_table.detach().float()[idx].reshape(n, n, -1)  # [i, j, h]
-            return bias.permute(2, 1, 0).contiguous().to(dev)  # [h, j, i]: coalesced over queries i
-
-        return self._cache.get(("bias", key, n, dev), [attn.relative_position_bias_table], build)
-
     def _plan(self, dims, ws, ss, dev):
         def build():
             src, region, nW, n = window_plan(dims, ws, ss)
@@ -391,7 +381,8 @@ class SwinUNETR(nn.Module):
             bkey = f"{key}.b{bi}"
             xw = K.layernorm_nc8(cur, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, src=src, out_sp=(1, nW, n))
             qkv, _ = K.gemm_tc(xw, self._wlin(blk.attn.qkv.weight, bkey + ".qkv"), C, 3 * C, bias=blk.attn.qkv.bias)
-            att = K.window_attention_nc8(qkv, C, blk.num_heads, nW, n, blk.attn.scale, self._attn_tables(blk, bkey, n, dev), region if any(s > 0 for s in ss) else None)
+            att = K.window_attention_nc8(qkv, C, blk.num_heads, nW, n, blk.attn.scale, blk.attn.relative_position_bias_table, blk.attn.window_size,
+                                         region if any(s > 0 for s in ss) else None)
             # x = shortcut + window_reverse(proj(att)): scattered back through the same table, residual fused
             x1, _ = K.gemm_tc(att, self._wlin(blk.attn.proj.weight, bkey + ".proj"), C, C, bias=blk.attn.proj.bias, res=cur, row_map=src, out_sp=dims, mode=1)
             y = K.layernorm_nc8(x1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)

@@ -26,7 +26,7 @@ def main():
     net = SwinUNETR(in_channels=1, out_channels=2, feature_size=48)
     net.load_state_dict(fill_state_dict(net.state_dict(), 4))
     net = net.eval().to(dev)
-    sd = {k: v.float().cpu() for k, v in net.state_dict().items()}
+    sd = {k: (v.float() if v.is_floating_point() else v).cpu() for k, v in net.state_dict().items()}
     x = torch.randn(1, 1, 64, 64, 64, generator=torch.Generator().manual_seed(15)).half().float()
     with torch.no_grad():
         hs = onet.swin_transformer_forward(sd, x)

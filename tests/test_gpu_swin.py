@@ -98,21 +98,27 @@ def test_layernorm_gather_and_patch_merging():
         assert _rel(got.numpy(), want.numpy()) < 2e-3, v2
 
 
-def test_window_attention_matches_reference_math():
+@pytest.mark.parametrize("ws,n,nW,heads", [((7, 7, 7), 343, 5, 3), ((7, 7, 7), 216, 3, 6), ((7, 7, 7), 8, 4, 24)])
+def test_window_attention_matches_reference_math(ws, n, nW, heads):
+    from monai_b200.networks.nets.swin_unetr import WindowAttention
+
     g = torch.Generator().manual_seed(3)
-    heads, C, nW, n, B = 3, 48, 5, 343, 2
+    C, B = heads * 16, 2
+    mod = WindowAttention(C, heads, ws, qkv_bias=True)
+    table = torch.randn(mod.relative_position_bias_table.shape, generator=g)
     qkv = torch.randn((B, nW, n, 3 * C), generator=g).half()
-    bias = torch.randn((heads, n, n), generator=g)
+    # reference bias gather: table[relative_position_index[:n, :n]] (swin_unetr.py:514-518)
+    bias = table[mod.relative_position_index[:n, :n].reshape(-1)].reshape(n, n, heads).permute(2, 0, 1)
     region = torch.randint(0, 3, (nW, n), generator=g, dtype=torch.int32)
     q, k, v = qkv.float().reshape(B, nW, n, 3, heads, 16).permute(3, 0, 1, 4, 2, 5)
     attn = (q * 0.25) @ k.transpose(-2, -1) + bias[None, None]
     mask = torch.where(region[:, None, :] != region[:, :, None], -100.0, 0.0)  # [nW, i, j]
-    attn = (attn + mask[None, :, None]).softmax(-1)
-    ref = (attn @ v).permute(0, 1, 3, 2, 4).reshape(B, nW, n, C)
-    x = K.pack_nc8(qkv.permute(0, 3, 1, 2).reshape(B, 3 * C, 1, nW, n).contiguous().to(DEV))
-    out = K.window_attention_nc8(x, C, heads, nW, n, 0.25, bias.permute(0, 2, 1).contiguous().to(DEV), region.to(DEV))
-    got = K.unpack_nc8(out, dtype=torch.float32).cpu().reshape(B, C, nW, n).permute(0, 2, 3, 1)
-    assert _rel(got.numpy(), ref.numpy()) < 3e-3
+    for reg, a in ((region, attn + mask[None, :, None]), (None, attn)):
+        ref = (a.softmax(-1) @ v).permute(0, 1, 3, 2, 4).reshape(B, nW, n, C)
+        x = K.pack_nc8(qkv.permute(0, 3, 1, 2).reshape(B, 3 * C, 1, nW, n).contiguous().to(DEV))
+        out = K.window_attention_nc8(x, C, heads, nW, n, 0.25, table.to(DEV), ws, None if reg is None else reg.to(DEV))
+        got = K.unpack_nc8(out, dtype=torch.float32).cpu().reshape(B, C, nW, n).permute(0, 2, 3, 1)
+        assert _rel(got.numpy(), ref.numpy()) < 4e-3, (n, reg is None)
 
 
 def test_cin1_stem_and_head():
@@ -155,7 +161,7 @@ def test_swin_unetr_matches_reference_fixture(golden_dir, tag):
 def test_swin_unetr_batch_and_fp32_input_vs_oracle():
     net = _build()
     x = torch.randn(2, 1, 64, 64, 64, generator=torch.Generator().manual_seed(8))
-    sd = {k: v.float().cpu() for k, v in net.state_dict().items()}
+    sd = {k: (v.float() if v.is_floating_point() else v).cpu() for k, v in net.state_dict().items()}
     with torch.no_grad():
         ref = onet.swin_unetr_forward(sd, x).numpy()
     y = net(x.to(DEV))  # fp32 in -> fp32 logits (internals fp16)
