@@ -286,7 +286,7 @@ def main():
     ms_e2e = timed(step_e2e, args.steps, 1)
 
     # per-kernel device time (CUDA events around every C-ABI launch, one extra untimed-for-value pass)
-    K.profile_start()
+    K.profile_start()   # CUDA-graph replay is bypassed while profiling so every launch is individually timed
     step_resident()
     prof = K.profile_stop()
 

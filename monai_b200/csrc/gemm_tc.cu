@@ -31,7 +31,7 @@ __host__ __device__ inline int gemm_tc_nt(int N) {
 
 struct GemmTcParams {
   b200_gemm_tc_desc d;
-  const __half* w; const float* bias; __half* y; const __half* res; float* stats; const int32_t* row_map;
+  const __half* x; const __half* w; const float* bias; __half* y; const __half* res; float* stats; const int32_t* row_map;
   int NT, tmem_cols;
 };
 
@@ -54,7 +54,7 @@ __global__ void gemm_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 
 // Persistent, warp-specialised: each CTA loops over (batch, row tile, N tile) work items.  Two TMEM accumulator
 // buffers let the epilogue of tile i overlap the MMAs of tile i+1; the shared-memory ring runs across tile boundaries.
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap, GemmTcParams p) {
+__global__ void __launch_bounds__(320, 1) gemm_tc_kernel(GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int NT = p.NT;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 256); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      tc::tma_prefetch_desc(&tmap);
       int s = 0; uint32_t ph = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % n_tiles);
@@ -100,8 +99,13 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         for (int st = 0; st < num_stages; ++st) {
           const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
           tc::mbar_wait(&empty[s], ph ^ 1);
-          tc::mbar_arrive_expect_tx(&full[s], kGemmAStage + steps * NT * 32);
-          tc::tma_load_4d(smem_a + s * kGemmAStage, &tmap, &full[s], 0, rt * 128, (d.in_coff / 8) + st * kGemmK16PerStage * 2, n);
+          // A: one contiguous 1-D bulk copy per 8-channel chunk (128 rows x 16 B = 2 KB in NC8); the last row tile is
+          // clamped to the valid rows so nothing is read past the chunk (stale smem rows are masked by the epilogue)
+          const int rows = min(128, d.S - rt * 128);
+          tc::mbar_arrive_expect_tx(&full[s], steps * 2 * rows * 16 + steps * NT * 32);
+          const __half* abase = p.x + (((long long)n * (d.in_ctot / 8) + d.in_coff / 8 + st * kGemmK16PerStage * 2) * d.S + rt * 128) * 8;
+          for (int c = 0; c < steps * 2; ++c)
+            tc::bulk_load(smem_a + s * kGemmAStage + c * 2048, abase + (long long)c * d.S * 8, rows * 16, &full[s]);
           tc::bulk_load(smem_b + s * b_stage, wbase + (long long)st * kGemmK16PerStage * (NT * 16), steps * NT * 32, &full[s]);
           if (++s == kGemmStages) { s = 0; ph ^= 1; }
         }
@@ -137,7 +141,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;      // two warps share a quarter and split the column chunks
     const int cout = d.mode == 2 ? d.N / 8 : d.N;  // channels of the destination tensor written by this GEMM
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -159,11 +164,16 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       tc::mbar_wait(&acc_full[buf], aph);
       tc::fence_after_sync();
       const uint32_t tacc = tmem_base + buf * NT + ((uint32_t)(q * 32) << 16);
+      const int ncc = NT / 8, cc_lo = chalf * ((ncc + 1) / 2), cc_hi = chalf ? ncc : (ncc + 1) / 2;
+      uint32_t vn[8];
+      if (cc_lo < cc_hi) tc::tmem_ld8(tacc + cc_lo * 8, vn);
 #pragma unroll 1
-      for (int cc = 0; cc < NT / 8; ++cc) {
+      for (int cc = cc_lo; cc < cc_hi; ++cc) {
         uint32_t v[8];
-        tc::tmem_ld8(tacc + cc * 8, v);
         tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = vn[j];
+        if (cc + 1 < cc_hi) tc::tmem_ld8(tacc + (cc + 1) * 8, vn);   // prefetch the next chunk while this one is processed
         const int nc = co0 + cc * 8;  // first GEMM column of this chunk
         float f[8];
 #pragma unroll
@@ -208,10 +218,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[buf]);
       if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int t = threadIdx.x - 64;
-        for (int i = t; i < 2 * NT; i += 128) { atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = t; i < 2 * NT; i += 256) { atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
   }
@@ -258,19 +268,8 @@ extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const 
   B200_REQUIRE(!res || (d.res_ctot % 8 == 0 && d.res_coff % 8 == 0 && d.res_coff + cout <= d.res_ctot), "gemm_tc: bad residual channel slice");
   B200_REQUIRE(d.act == 0 || d.act == 4, "gemm_tc: activation must be 0 (none) or 4 (gelu)");
   const int NT = gemm_tc_nt(d.N);
-  EncodeTiledFn enc = get_encode_tiled();
-  B200_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled entry point unavailable");
-  CUtensorMap tmap;
-  cuuint64_t gdim[4] = {8, (cuuint64_t)d.S, (cuuint64_t)(d.in_ctot / 8), (cuuint64_t)d.Nb};
-  cuuint64_t gstr[3] = {16, (cuuint64_t)d.S * 16, (cuuint64_t)d.S * 16 * (cuuint64_t)(d.in_ctot / 8)};
-  cuuint32_t box[4] = {8, 128, (cuuint32_t)(kGemmK16PerStage * 2), 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  B200_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   GemmTcParams p;
-  p.d = d; p.w = (const __half*)packed_w; p.bias = bias; p.y = (__half*)y; p.res = (const __half*)res; p.stats = stats;
+  p.d = d; p.x = (const __half*)x; p.w = (const __half*)packed_w; p.bias = bias; p.y = (__half*)y; p.res = (const __half*)res; p.stats = stats;
   p.row_map = row_map; p.NT = NT;
   p.tmem_cols = 2 * NT <= 32 ? 32 : 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;  // two accumulator buffers
   const int smem = kGemmStages * (kGemmAStage + kGemmK16PerStage * NT * 32) + 128 + 2 * NT * 4 + 128;
@@ -281,7 +280,7 @@ extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const 
   }
   const long long total_tiles = (long long)ceil_div(d.S, 128) * (d.N / NT) * d.Nb;
   dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
-  gemm_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmap, p);
+  gemm_tc_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   return B200_OK;
 }

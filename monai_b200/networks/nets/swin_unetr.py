@@ -20,6 +20,7 @@ feature_size 48), norm_name="instance" (non-affine), downsample "merging"/"mergi
 from __future__ import annotations
 
 import itertools
+import os
 from collections.abc import Sequence
 
 import numpy as np
@@ -316,6 +317,10 @@ class SwinUNETR(nn.Module):
         self.decoder1 = UnetrUpBlock(fs, fs)
         self.out = UnetOutBlock(fs, out_channels)
         self._cache = _Cache()
+        # the ~250 launches of one forward are captured into a CUDA graph per input shape and replayed (the per-launch
+        # host cost of ctypes + tensor-map encoding would otherwise bound throughput); MONAI_B200_GRAPH=0 disables it
+        self._graph_enabled = os.environ.get("MONAI_B200_GRAPH", "1") != "0"
+        self._graphs: dict = {}
 
     def _check_input_size(self, spatial_shape):
         img_size = np.array(spatial_shape)
@@ -414,6 +419,30 @@ class SwinUNETR(nn.Module):
             raise ValueError(f"expected {self.in_channels} input channel(s), got {x_in.shape[1]}")
         if x_in.dtype not in (torch.float16, torch.float32):
             raise TypeError(f"SwinUNETR takes float16/float32 inputs, got {x_in.dtype}")
+        if self._graph_enabled and not K._Prof.on and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(x_in)
+        return self._forward_impl(x_in)
+
+    def _forward_graphed(self, x_in: torch.Tensor) -> torch.Tensor:
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (tuple(x_in.shape), x_in.dtype, x_in.device)
+        ent = self._graphs.get(key)
+        if ent is None or ent["sig"] != sig:
+            static_in = x_in.detach().clone().contiguous()
+            self._forward_impl(static_in)  # eager warm-up: packs weights, sets kernel attributes, fills the plan caches
+            torch.cuda.synchronize(x_in.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_impl(static_in)
+            if len(self._graphs) >= 4:  # bound the private pools kept alive
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = {"sig": sig, "graph": graph, "inp": static_in, "out": static_out}
+            self._graphs[key] = ent
+        ent["inp"].copy_(x_in)
+        ent["graph"].replay()
+        return ent["out"].clone()
+
+    def _forward_impl(self, x_in: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
             x_in = x_in.contiguous()
             n = x_in.shape[0]

@@ -25,36 +25,41 @@ __all__ = ["ShardPlan", "make_shard_plan", "exchange_partials", "ShardedSlidingW
 @dataclass
 class ShardPlan:
     world: int
-    layers: list[tuple[int, int]]      # per rank: [first, last) start-layer indices along depth
+    win_range: list[tuple[int, int]]   # per rank: [first, last) flat window index within one batch item (depth-major order)
     slab: list[tuple[int, int]]        # per rank: depth rows covered by its windows [lo, hi)
     owned: list[tuple[int, int]]       # per rank: depth rows it finalises [lo, hi); a partition of [0, D)
 
 
-def make_shard_plan(starts_d: Sequence[int], roi_d: int, D: int, world: int) -> ShardPlan:
-    """Contiguous, balanced partition of the depth start-layers; ownership cuts sit mid-way through each overlap."""
+def make_shard_plan(starts_d: Sequence[int], roi_d: int, D: int, world: int, per_layer: int = 1) -> ShardPlan:
+    """Balanced partition of the depth-major window list: rank k runs flat windows [k*n/world, (k+1)*n/world) where
+    n = len(starts_d) * per_layer (per_layer = windows per depth start-layer).  A layer may be split between two
+    ranks, so the load imbalance is at most one window (8 GPUs on 2100 windows -> 262/263).
+    Ownership cuts are monotone depth positions near the window-range boundaries; correctness does not depend on
+    where they sit because `exchange_partials` routes every slab/owner intersection."""
     nl = len(starts_d)
     if world < 1:
         raise ValueError("world must be >= 1")
-    base, extra = divmod(nl, world)
-    layers, lo = [], 0
-    for r in range(world):
-        n = base + (1 if r < extra else 0)
-        layers.append((lo, lo + n))
-        lo += n
+    n = nl * per_layer
+    bounds = [(k * n) // world for k in range(world + 1)]
+    win_range = [(bounds[k], bounds[k + 1]) for k in range(world)]
     slab = []
-    for a, b in layers:
-        slab.append((int(starts_d[a]), int(starts_d[b - 1]) + roi_d) if b > a else (0, 0))
-    active = [r for r in range(world) if layers[r][1] > layers[r][0]]
-    owned = [(0, 0)] * world
+    for a, b in win_range:
+        slab.append((int(starts_d[a // per_layer]), int(starts_d[(b - 1) // per_layer]) + roi_d) if b > a else (0, 0))
     cuts = [0]
-    for i in range(1, len(active)):
-        prev, cur = active[i - 1], active[i]
-        ov_lo, ov_hi = slab[cur][0], slab[prev][1]          # overlap of neighbouring slabs (may be empty)
-        cuts.append((ov_lo + ov_hi) // 2 if ov_hi > ov_lo else ov_lo)
+    for k in range(1, world):
+        b = bounds[k]
+        if b <= 0:
+            cuts.append(0)
+        elif b >= n:
+            cuts.append(D)
+        else:
+            layer, frac = b // per_layer, (b % per_layer) / per_layer
+            nxt = starts_d[layer + 1] if layer + 1 < nl else starts_d[layer] + roi_d
+            pos = starts_d[layer] + frac * (nxt - starts_d[layer]) + (roi_d // 2 if frac == 0 else roi_d / 2)
+            cuts.append(int(min(max(round(pos), cuts[-1]), D)))
     cuts.append(D)
-    for i, r in enumerate(active):
-        owned[r] = (cuts[i], cuts[i + 1])
-    return ShardPlan(world, layers, slab, owned)
+    owned = [(cuts[k], cuts[k + 1]) for k in range(world)]
+    return ShardPlan(world, win_range, slab, owned)
 
 
 def _intersect(a, b):
@@ -114,9 +119,9 @@ class ShardedSlidingWindowInferer:
         overlap = _ensure_tuple_rep(self.overlap, 3)
         interval = _get_scan_interval((D, H, W), roi, 3, overlap)
         starts = dense_patch_starts((D, H, W), roi, interval)
-        plan = make_shard_plan(starts[0], roi[0], D, world)
-        la, lb = plan.layers[rank]
         nh, nw = len(starts[1]), len(starts[2])
+        plan = make_shard_plan(starts[0], roi[0], D, world, per_layer=nh * nw)
+        wa, wb = plan.win_range[rank]
         num_win = len(starts[0]) * nh * nw
         dev = inputs.device
         mode_s = str(getattr(self.mode, "value", self.mode)).lower()
@@ -129,7 +134,7 @@ class ShardedSlidingWindowInferer:
         acc = None
         out_c = None
         for b in range(B):
-            ids = [b * num_win + i for i in range(la * nh * nw, lb * nh * nw)]
+            ids = [b * num_win + i for i in range(wa, wb)]
             tab = torch.tensor([(b, starts[0][(i % num_win) // (nh * nw)], starts[1][((i % num_win) // nw) % nh], starts[2][(i % num_win) % nw]) for i in ids],
                                dtype=torch.int32, device=dev).reshape(-1, 4)
             for g in range(0, len(ids), self.sw_batch_size):

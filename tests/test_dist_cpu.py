@@ -35,15 +35,15 @@ def _worker(rank, world, port, shape, roi, overlap, ret):
         x = np.random.default_rng(0).standard_normal((1, 1, *shape)).astype(np.float32)
         interval = osw.get_scan_interval(shape, roi, (overlap,) * 3)
         starts = osw.dense_patch_starts(shape, roi, interval)
-        plan = make_shard_plan(starts[0], roi[0], shape[0], world)
+        nh, nw = len(starts[1]), len(starts[2])
+        plan = make_shard_plan(starts[0], roi[0], shape[0], world, per_layer=nh * nw)
         imp = osw.compute_importance_map(roi, "gaussian", 0.125)
-        la, lb = plan.layers[rank]
+        wa, wb = plan.win_range[rank]
         acc = np.zeros((1, 2, *shape), dtype=np.float32)
-        for sd in starts[0][la:lb]:
-            for sh in starts[1]:
-                for sw in starts[2]:
-                    sl = (slice(None), slice(None), slice(sd, sd + roi[0]), slice(sh, sh + roi[1]), slice(sw, sw + roi[2]))
-                    acc[sl] += _pred(x[sl]) * imp
+        for i in range(wa, wb):
+            sd, sh, sw = starts[0][i // (nh * nw)], starts[1][(i // nw) % nh], starts[2][i % nw]
+            sl = (slice(None), slice(None), slice(sd, sd + roi[0]), slice(sh, sh + roi[1]), slice(sw, sw + roi[2]))
+            acc[sl] += _pred(x[sl]) * imp
         # rows outside the slab must be untouched
         lo, hi = plan.slab[rank]
         assert not acc[:, :, :lo].any() and not acc[:, :, hi:].any()
@@ -79,13 +79,16 @@ def test_sharded_exchange_matches_single_process_oracle(world, shape, roi, overl
 
 
 def test_shard_plan_balance_and_coverage():
-    # config C5: 1024 depth rows, roi 96, interval 48 -> 21 layers; 8 ranks -> 3,3,3,3,3,2,2,2
+    # config C5: 1024 depth rows, roi 96, interval 48 -> 21 layers x 100 windows; 8 ranks -> 262/263 windows each
     starts = list(range(0, 913, 48)) + [928]
-    plan = make_shard_plan(starts, 96, 1024, 8)
-    assert [b - a for a, b in plan.layers] == [3, 3, 3, 3, 3, 2, 2, 2]
+    plan = make_shard_plan(starts, 96, 1024, 8, per_layer=100)
+    sizes = [b - a for a, b in plan.win_range]
+    assert sum(sizes) == 2100 and max(sizes) - min(sizes) <= 1
     assert plan.owned[0][0] == 0 and plan.owned[-1][1] == 1024
     for r in range(7):
-        assert plan.owned[r][1] == plan.owned[r + 1][0]
-        assert plan.slab[r][0] <= plan.owned[r][0] and plan.owned[r][1] <= plan.slab[r][1]
-    one = make_shard_plan(starts, 96, 1024, 1)
-    assert one.owned == [(0, 1024)] and one.layers == [(0, 21)]
+        assert plan.owned[r][1] == plan.owned[r + 1][0] and plan.owned[r][1] >= plan.owned[r][0]
+    one = make_shard_plan(starts, 96, 1024, 1, per_layer=100)
+    assert one.owned == [(0, 1024)] and one.win_range == [(0, 2100)]
+    # more ranks than windows: empty ranks own nothing and the plan stays consistent
+    tiny = make_shard_plan([0], 16, 16, 3, per_layer=2)
+    assert sum(b - a for a, b in tiny.win_range) == 2
