@@ -145,6 +145,25 @@ typedef struct b200_conv_tc_desc {
 int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
                       void* y, float* stats, void* stream);
 
+typedef struct b200_conv_gather_desc {
+  int N, Cin, Cout;         /* Cin % 16 == 0; Cout arbitrary for NCDHW output, % 8 == 0 for NC8 output */
+  int Di, Hi, Wi, Do, Ho, Wo;
+  int k, stride, pad;       /* cubic kernel k <= 3, stride 1 or 2, zero padding */
+  int transposed;           /* 0: Conv3d weight [Cout,Cin,k,k,k]; 1: ConvTranspose3d weight [Cin,Cout,k,k,k] */
+  int in_ctot, in_coff;     /* x = channels [in_coff, in_coff+Cin) of an NC8 buffer */
+  int out_ctot, out_coff;   /* NC8 destination slice (out_layout 0) */
+  int out_layout;           /* 0: NC8 fp16; 1: NCDHW (out_dtype) with exactly Cout channels */
+  int out_dtype;
+} b200_conv_gather_desc;
+
+/* General Conv3d / ConvTranspose3d (k <= 3, stride <= 2) as an implicit GEMM on tcgen05 with a cp.async im2col
+ * producer -- the stride-2 and transposed 3x3x3 layers of UNet (monai/networks/nets/unet.py:150-182).  Weights are
+ * packed per (N tile, parity class, live tap, 16-channel slice); stats as in b200_conv3x3x3_tc. */
+long long b200_conv_gather_tc_weight_bytes(const b200_conv_gather_desc* desc);
+int b200_conv_gather_tc_pack_weight(const b200_conv_gather_desc* desc, const float* w, void* packed, void* stream);
+int b200_conv_gather_tc(const b200_conv_gather_desc* desc, const void* x, const void* packed_w, const float* bias, void* y,
+                        float* stats, void* stream);
+
 typedef struct b200_gemm_tc_desc {
   int Nb;                   /* batch items (each with its own S rows) */
   int S;                    /* GEMM rows per batch item (tokens / voxels of x) */

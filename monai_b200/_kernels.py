@@ -453,3 +453,44 @@ def head_conv_nc8(x: NC8, weight: torch.Tensor, bias: torch.Tensor | None, out_d
     y = torch.empty((x.N, Cout, *x.sp), device=x.buf.device, dtype=out_dtype)
     _call("head_conv_nc8", L.ptr(x.buf), x.N, x.C, x.S, L.ptr(w32), L.ptr(b32), Cout, L.ptr(y), L.dt(y), L.stream_ptr(x.buf.device))
     return y
+
+
+def _cg_desc(x_sp, N, Cin, Cout, k, stride, pad, transposed, output_padding, in_ctot, in_coff, out_ctot, out_coff, out_layout, out_dtype):
+    sp_out = conv_out_shape(x_sp, (k,) * 3, (stride,) * 3, (pad,) * 3, transposed, (output_padding,) * 3)
+    return L.ConvGatherDesc(N, Cin, Cout, x_sp[0], x_sp[1], x_sp[2], sp_out[0], sp_out[1], sp_out[2], k, stride, pad, int(transposed),
+                            in_ctot, in_coff, out_ctot, out_coff, out_layout, out_dtype), sp_out
+
+
+def conv_gather_tc_pack_weight(weight: torch.Tensor, k: int, stride: int, pad: int, transposed: bool) -> torch.Tensor:
+    """Pack a Conv3d [Cout,Cin,k,k,k] / ConvTranspose3d [Cin,Cout,k,k,k] weight for conv_gather_tc."""
+    L.require_cuda(weight)
+    Cin, Cout = (weight.shape[0], weight.shape[1]) if transposed else (weight.shape[1], weight.shape[0])
+    d, _ = _cg_desc((8, 8, 8), 1, Cin, Cout, k, stride, pad, transposed, stride - 1 if transposed else 0, Cin, 0, (Cout + 7) // 8 * 8, 0, 1, L.DT_F16)
+    nbytes = L.load().b200_conv_gather_tc_weight_bytes(C.byref(d))
+    if nbytes < 0:
+        raise ValueError(f"conv_gather_tc needs Cin % 16 == 0, kernel <= 3, stride <= 2 (got Cin={Cin}, k={k}, stride={stride})")
+    w32 = weight.detach().float().contiguous()
+    packed = torch.empty(nbytes // 2, device=weight.device, dtype=torch.float16)
+    _call("conv_gather_tc_pack_weight", C.byref(d), L.ptr(w32), L.ptr(packed), L.stream_ptr(weight.device))
+    return packed
+
+
+def conv_gather_tc(
+    x: NC8, packed_w: torch.Tensor, Cin: int, Cout: int, k: int, stride: int, pad: int, transposed: bool = False, output_padding: int = 0,
+    in_coff: int = 0, bias: torch.Tensor | None = None, out: "NC8 | torch.Tensor | None" = None, out_coff: int = 0,
+    ncdhw_dtype: torch.dtype | None = None, want_stats: bool = False,
+):
+    """Conv3d / ConvTranspose3d on tensor cores.  Returns (NC8 | NCDHW tensor, stats)."""
+    layout = 0 if ncdhw_dtype is None else 1
+    d, sp_out = _cg_desc(x.sp, x.N, Cin, Cout, k, stride, pad, transposed, output_padding, x.C, in_coff,
+                         (out.C if isinstance(out, NC8) else (Cout + 7) // 8 * 8), out_coff, layout, L.dt(ncdhw_dtype) if layout else L.DT_F16)
+    if out is None:
+        out = NC8(x.N, Cout, sp_out, x.buf.device) if layout == 0 else torch.empty((x.N, Cout, *sp_out), device=x.buf.device, dtype=ncdhw_dtype)
+        d.out_ctot = out.C if layout == 0 else d.out_ctot
+    stats = torch.zeros((x.N * Cout, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
+    b32 = _f32c(bias)
+    taps = k**3 if not transposed else (k**3) / (stride**3)
+    _call("conv_gather_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf if layout == 0 else out), L.ptr(stats),
+          L.stream_ptr(x.buf.device), flops=2.0 * x.N * sp_out[0] * sp_out[1] * sp_out[2] * Cin * Cout * taps,
+          nbytes=float(x.N * (x.S * Cin + sp_out[0] * sp_out[1] * sp_out[2] * Cout) * 2) + _nb(packed_w))
+    return out, stats

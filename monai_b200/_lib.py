@@ -50,6 +50,12 @@ class ConvTcDesc(C.Structure):
     ]
 
 
+class ConvGatherDesc(C.Structure):
+    _fields_ = [(n, i32) for n in (
+        "N", "Cin", "Cout", "Di", "Hi", "Wi", "Do", "Ho", "Wo", "k", "stride", "pad", "transposed", "in_ctot", "in_coff",
+        "out_ctot", "out_coff", "out_layout", "out_dtype")]
+
+
 class GemmTcDesc(C.Structure):
     _fields_ = [
         ("Nb", i32), ("S", i32), ("K", i32), ("N", i32), ("in_ctot", i32), ("in_coff", i32), ("out_ctot", i32),
@@ -77,6 +83,9 @@ SIGNATURES = {
     "b200_conv3x3x3_tc_weight_bytes": (i64, [i32, i32]),
     "b200_conv3x3x3_tc_pack_weight": (i32, [vp, i32, i32, vp, vp]),
     "b200_conv3x3x3_tc": (i32, [C.POINTER(ConvTcDesc), vp, vp, vp, vp, vp, vp]),
+    "b200_conv_gather_tc_weight_bytes": (i64, [C.POINTER(ConvGatherDesc)]),
+    "b200_conv_gather_tc_pack_weight": (i32, [C.POINTER(ConvGatherDesc), vp, vp, vp]),
+    "b200_conv_gather_tc": (i32, [C.POINTER(ConvGatherDesc), vp, vp, vp, vp, vp, vp]),
     "b200_gemm_tc_weight_bytes": (i64, [i32, i32]),
     "b200_gemm_tc_pack_weight": (i32, [vp, i32, i32, i64, i64, vp, vp]),
     "b200_gemm_tc": (i32, [C.POINTER(GemmTcDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -148,9 +157,19 @@ def require_cuda(*tensors: torch.Tensor) -> None:
             raise RuntimeError("monai_b200 kernels need CUDA tensors (no CPU fallback exists in this package)")
 
 
+_replayed_launches = 0
+
+
+def add_replayed_launches(n: int) -> None:
+    """Kernels re-launched by a CUDA-graph replay (the C counter only sees them once, at capture time)."""
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def launch_count() -> int:
+    """monai_b200 kernels launched by this process: direct C-ABI launches + launches replayed from captured graphs."""
     lib = load(required=False)
-    return int(lib.b200_launch_count()) if lib is not None else 0
+    return (int(lib.b200_launch_count()) if lib is not None else 0) + _replayed_launches
 
 
 if os.environ.get("MONAI_B200_EAGER_LOAD"):

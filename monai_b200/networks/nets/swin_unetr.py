@@ -29,6 +29,7 @@ import torch.nn as nn
 
 from ... import _kernels as K
 from ... import _lib as L
+from .._graph import GraphedForward
 from ..blocks.convolutions import Convolution
 
 __all__ = ["SwinUNETR", "PatchMerging", "PatchMergingV2", "window_plan"]
@@ -248,7 +249,7 @@ class _Cache:
         return val
 
 
-class SwinUNETR(nn.Module):
+class SwinUNETR(GraphedForward, nn.Module):
     patch_size: int = 2
 
     def __init__(
@@ -317,10 +318,7 @@ class SwinUNETR(nn.Module):
         self.decoder1 = UnetrUpBlock(fs, fs)
         self.out = UnetOutBlock(fs, out_channels)
         self._cache = _Cache()
-        # the ~250 launches of one forward are captured into a CUDA graph per input shape and replayed (the per-launch
-        # host cost of ctypes + tensor-map encoding would otherwise bound throughput); MONAI_B200_GRAPH=0 disables it
-        self._graph_enabled = os.environ.get("MONAI_B200_GRAPH", "1") != "0"
-        self._graphs: dict = {}
+        self._graph_init()  # the ~250 launches of one forward are captured into a CUDA graph per input shape
 
     def _check_input_size(self, spatial_shape):
         img_size = np.array(spatial_shape)
@@ -419,28 +417,9 @@ class SwinUNETR(nn.Module):
             raise ValueError(f"expected {self.in_channels} input channel(s), got {x_in.shape[1]}")
         if x_in.dtype not in (torch.float16, torch.float32):
             raise TypeError(f"SwinUNETR takes float16/float32 inputs, got {x_in.dtype}")
-        if self._graph_enabled and not K._Prof.on and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(x_in)
+        if self._graph_ok():
+            return self._forward_graphed(x_in, self._forward_impl)
         return self._forward_impl(x_in)
-
-    def _forward_graphed(self, x_in: torch.Tensor) -> torch.Tensor:
-        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        key = (tuple(x_in.shape), x_in.dtype, x_in.device)
-        ent = self._graphs.get(key)
-        if ent is None or ent["sig"] != sig:
-            static_in = x_in.detach().clone().contiguous()
-            self._forward_impl(static_in)  # eager warm-up: packs weights, sets kernel attributes, fills the plan caches
-            torch.cuda.synchronize(x_in.device)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_out = self._forward_impl(static_in)
-            if len(self._graphs) >= 4:  # bound the private pools kept alive
-                self._graphs.pop(next(iter(self._graphs)))
-            ent = {"sig": sig, "graph": graph, "inp": static_in, "out": static_out}
-            self._graphs[key] = ent
-        ent["inp"].copy_(x_in)
-        ent["graph"].replay()
-        return ent["out"].clone()
 
     def _forward_impl(self, x_in: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():

@@ -7,19 +7,23 @@ accumulation is fp32.
 """
 from __future__ import annotations
 
+import os
 import warnings
 from collections.abc import Sequence
 
 import torch
 import torch.nn as nn
 
+from ... import _kernels as K
+from ... import _lib as L
+from .._graph import GraphedForward
 from ..blocks.convolutions import Convolution, ResidualUnit
 from ..layers.simplelayers import SkipConnection
 
 __all__ = ["UNet", "Unet"]
 
 
-class UNet(nn.Module):
+class UNet(GraphedForward, nn.Module):
     def __init__(
         self,
         spatial_dims: int,
@@ -62,6 +66,8 @@ class UNet(nn.Module):
         self.bias = bias
         self.adn_ordering = adn_ordering
         self.model = self._level(in_channels, out_channels, list(channels), list(strides), True)
+        self._graph_init()
+        self._tc_cache: dict = {}
 
     # -- builders (same construction order as the reference so that seeded initialisation matches) -------------
     def _level(self, inc: int, outc: int, channels: list[int], strides: list[int], is_top: bool) -> nn.Module:
@@ -103,11 +109,103 @@ class UNet(nn.Module):
             conv = nn.Sequential(conv, ru)
         return conv
 
+    # ------------------------------------------------------------------------------------------ tensor-core path
+    def _tc_eligible(self, x: torch.Tensor) -> bool:
+        """fp16 3-D single-channel input, plain conv levels (no residual units), InstanceNorm (non-affine) + PReLU(1) /
+        LeakyReLU / ReLU in "NDA" order, 3x3x3 kernels, strides 1 or 2, inner channel counts that are multiples of 16."""
+        if os.environ.get("MONAI_B200_UNET_TC", "1") == "0":
+            return False
+        if x.dtype != torch.float16 or self.dimensions != 3 or self.num_res_units != 0 or self.in_channels != 1:
+            return False
+        if self.kernel_size != 3 or self.up_kernel_size != 3 or self.adn_ordering.upper() != "NDA" or self.dropout not in (0, 0.0, None):
+            return False
+        if any(c % 16 for c in self.channels) or any(s not in (1, 2) for s in self.strides[: len(self.channels) - 1]):
+            return False
+        for m in self.modules():
+            if isinstance(m, (nn.InstanceNorm3d,)) and (m.affine or m.track_running_stats):
+                return False
+            if isinstance(m, (nn.BatchNorm3d, nn.GroupNorm, nn.LayerNorm)):
+                return False
+            if isinstance(m, nn.PReLU) and m.weight.numel() != 1:
+                return False
+        return all(isinstance(m, (nn.PReLU, nn.LeakyReLU, nn.ReLU)) for m in self.modules() if type(m).__module__.startswith("torch.nn.modules.activation"))
+
+    def _cached(self, key, params, build):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._tc_cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, build())
+            self._tc_cache[key] = hit
+        return hit[1]
+
+    def _act_of(self, conv: Convolution):
+        act = getattr(conv.adn, "A", None)
+        if isinstance(act, nn.PReLU):
+            return L.ACT_LEAKY, self._cached(("slope", id(act)), [act.weight], lambda: float(act.weight.detach().float().item()))
+        if isinstance(act, nn.LeakyReLU):
+            return L.ACT_LEAKY, float(act.negative_slope)
+        if isinstance(act, nn.ReLU):
+            return L.ACT_RELU, 0.0
+        return L.ACT_NONE, 0.0
+
+    def _tc_conv(self, conv: Convolution, x, cin: int, in_coff: int, out, out_coff: int, raw=None):
+        """Convolution block (conv + InstanceNorm + activation) on tensor cores; result goes to out[:, out_coff:...]."""
+        m = conv.conv
+        transposed = isinstance(m, nn.ConvTranspose3d)
+        cout = m.out_channels
+        k, s, p = m.kernel_size[0], m.stride[0], m.padding[0]
+        if raw is not None:
+            y, st = K.conv_cin1_nc8(raw, m.weight, m.bias, k, s, p, want_stats=True)
+        else:
+            pw = self._cached(("w", id(m)), [m.weight], lambda: K.conv_gather_tc_pack_weight(m.weight, k, s, p, transposed))
+            y, st = K.conv_gather_tc(x, pw, cin, cout, k, s, p, transposed=transposed, output_padding=m.output_padding[0] if transposed else 0,
+                                     in_coff=in_coff, bias=m.bias, want_stats=True)
+        act, slope = self._act_of(conv)
+        if out is None:
+            out, out_coff = y, 0
+        K.norm_act_nc8(y, cout, st, act=act, slope=slope, out=out, out_coff=out_coff)
+        return out
+
+    def _tc_level(self, block: nn.Sequential, x, cin: int, raw, top: bool, out, out_coff: int, out_dtype):
+        down, skip, up = block[0], block[1], block[2]
+        sub = skip.submodule
+        c = down.conv.out_channels
+        bottom = isinstance(sub, Convolution)
+        c_sub = sub.conv.out_channels if bottom else sub[2].conv.out_channels
+        # `down` output and the sub-network's output share one buffer: torch.cat([x, sub(x)], 1) without a copy
+        sp_in = raw.shape[2:] if raw is not None else x.sp
+        st = down.conv.stride[0]
+        sp = tuple((int(s) + 2 - 3) // st + 1 for s in sp_in)
+        n = raw.shape[0] if raw is not None else x.N
+        cat = K.NC8(n, c + c_sub, sp, (raw if raw is not None else x.buf).device)
+        self._tc_conv(down, x, cin, 0, cat, 0, raw=raw)
+        if bottom:
+            self._tc_conv(sub, cat, c, 0, cat, c)
+        else:
+            self._tc_level(sub, cat, c, None, False, cat, c, None)
+        upm = up.conv
+        if top:  # conv only: logits straight to NCDHW
+            pw = self._cached(("w", id(upm)), [upm.weight], lambda: K.conv_gather_tc_pack_weight(upm.weight, upm.kernel_size[0], upm.stride[0], upm.padding[0], True))
+            y, _ = K.conv_gather_tc(cat, pw, c + c_sub, upm.out_channels, upm.kernel_size[0], upm.stride[0], upm.padding[0], transposed=True,
+                                    output_padding=upm.output_padding[0], bias=upm.bias, ncdhw_dtype=out_dtype)
+            return y
+        return self._tc_conv(up, cat, c + c_sub, 0, out, out_coff)
+
+    def _forward_tc(self, x: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            return self._tc_level(self.model, None, 1, x.contiguous(), True, None, 0, x.dtype)
+
+    def _forward_direct(self, x: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            return self.model(x.contiguous())
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("monai_b200.UNet runs on CUDA tensors only (there is no CPU fallback)")
-        with torch.no_grad():
-            return self.model(x.contiguous())
+        impl = self._forward_tc if self._tc_eligible(x) else self._forward_direct
+        if self._graph_ok() and impl is self._forward_tc:
+            return self._forward_graphed(x, impl)
+        return impl(x)
 
 
 Unet = UNet

@@ -73,3 +73,20 @@ def test_basic_unet_matches_reference_fixture(golden_dir):
     ref = onet.basic_unet_forward({k: v.float().cpu() for k, v in net.state_dict().items()}, x).numpy()
     y = net(x.to(DEV)).cpu().numpy()
     assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-3
+
+
+def test_unet_tensor_core_path_matches_direct_path(monkeypatch):
+    """fp16 UNet (C2 topology): tcgen05 im2col path (NC8, CUDA-graph replay) vs the CUDA-core NCDHW path."""
+    net = _build(lambda: UNet(3, 1, 2, (16, 32, 64, 128, 256), (2, 2, 2, 2)), 1).half()
+    x = torch.randn(3, 1, 32, 48, 64, generator=torch.Generator().manual_seed(5)).to(DEV).half()
+    assert net._tc_eligible(x)
+    a = net(x).float()
+    a2 = net(x).float()  # second call replays the captured graph
+    torch.testing.assert_close(a, a2, rtol=0, atol=0)
+    monkeypatch.setenv("MONAI_B200_UNET_TC", "0")
+    assert not net._tc_eligible(x)
+    b = net(x).float()
+    err = float((a - b).abs().max() / b.abs().max())
+    assert err < 2e-2, err
+    ref = onet.unet_forward({k: v.float().cpu() for k, v in net.state_dict().items()}, x.float().cpu(), (2, 2, 2, 2))
+    assert float((a.cpu() - ref).abs().max() / ref.abs().max()) < 3e-2
