@@ -136,7 +136,10 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
     // ===================== im2col producers: thread r gathers GEMM row r =====================
     const int r = threadIdx.x;
     int s = 0; uint32_t ph = 0;
-    int pend_s = -1;  // stage whose cp.async group is in flight (completed one stage later to keep copies overlapped)
+    // up to kCgInflight cp.async groups (= stages) stay in flight per thread; a stage is handed to the MMA warp only
+    // after its group completed (wait_group) and a proxy fence made the generic-proxy writes visible to tcgen05
+    constexpr int kCgInflight = 3;
+    int pend_first = 0, pend_n = 0;   // pending stages are pend_first, pend_first+1, ... (mod kCgStages)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % n_tiles);
       long long t2 = tile / n_tiles;
@@ -168,19 +171,22 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
           tc::mbar_arrive_expect_tx(&full[s], nu * NT * 32);
           tc::bulk_load(smem_b + s * b_stage, wbase + (long long)u0 * (NT * 16), nu * NT * 32, &full[s]);
         }
-        if (pend_s >= 0) {
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (pend_n == 0) pend_first = s;
+        ++pend_n;
+        if (pend_n == kCgInflight) {
+          asm volatile("cp.async.wait_group 2;" ::: "memory");   // kCgInflight - 1 newest groups may still be pending
           tc::fence_proxy_async();
-          tc::mbar_arrive(&full[pend_s]);
+          tc::mbar_arrive(&full[pend_first]);
+          pend_first = (pend_first + 1) % kCgStages;
+          --pend_n;
         }
-        pend_s = s;
         if (++s == kCgStages) { s = 0; ph ^= 1; }
       }
     }
-    if (pend_s >= 0) {
+    if (pend_n > 0) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       tc::fence_proxy_async();
-      tc::mbar_arrive(&full[pend_s]);
+      for (; pend_n > 0; --pend_n) { tc::mbar_arrive(&full[pend_first]); pend_first = (pend_first + 1) % kCgStages; }
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================

@@ -230,6 +230,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
     const int co0 = nt * NT;
     const long long S = (long long)d.D * d.H * d.W;
     __half* ybase = p.y + (((long long)n * (d.out_ctot / 8) + (d.out_coff + co0) / 8) * S) * 8;
+    uint32_t vn[8];
+    tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16), vn);   // (cc = 0, sub = 0); every later load is prefetched one step ahead
 #pragma unroll 1
     for (int cc = 0; cc < NT / 8; ++cc) {
       float bsum[8], bsq[8], bias8[8];
@@ -238,19 +240,28 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
 #pragma unroll
       for (int sub = 0; sub < BD; ++sub) {
         uint32_t v[8];
-        tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + sub * NT + cc * 8, v);
         tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = vn[j];
+        {
+          const int nsub = sub + 1 < BD ? sub + 1 : 0, ncc = sub + 1 < BD ? cc : cc + 1;
+          if (ncc < NT / 8) tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + nsub * NT + ncc * 8, vn);
+        }
         const int dz = d0 + sub;
         const bool ok = hw_ok && dz < d.D;
-        __align__(16) __half hv[8];
+        float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float f = __uint_as_float(v[j]) + bias8[j];
-          hv[j] = __float2half_rn(f);
-          if (ok) { bsum[j] += f; bsq[j] = fmaf(f, f, bsq[j]); }
+          f[j] = __uint_as_float(v[j]) + bias8[j];
+          if (ok) { bsum[j] += f[j]; bsq[j] = fmaf(f[j], f[j], bsq[j]); }
         }
-        if (ok) *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * d.H + h) * d.W + w) * 8) =
-                    *reinterpret_cast<const uint4*>(hv);
+        if (ok) {
+          uint4 hv;
+          __half2* hp = reinterpret_cast<__half2*>(&hv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+          *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * d.H + h) * d.W + w) * 8) = hv;
+        }
       }
       if (p.stats) {
         // transpose-reduce 8 columns over the 32 lanes: 4+2+1 exchange steps, then 2 plain steps
