@@ -207,8 +207,11 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("B200_WORKLOAD", "unet_c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sw-batch", type=int, default=0, help="override the workload's sw_batch_size")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.sw_batch > 0:
+        wl["sw_batch"] = args.sw_batch
     if args.impl == "reference":
         return run_reference(args, wl)
 

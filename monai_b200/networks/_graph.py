@@ -33,7 +33,8 @@ class GraphedForward:
             torch.cuda.synchronize(x_in.device)
             graph = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
-            with torch.cuda.graph(graph):
+            # thread_local: other threads (e.g. the NCCL watchdog) may issue CUDA calls while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 static_out = impl(static_in)
             n_kernels = L.launch_count() - n0
             if len(self._graphs) >= 4:  # bound the private memory pools kept alive
