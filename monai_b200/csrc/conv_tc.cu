@@ -21,6 +21,7 @@
 #include "tc05.cuh"
 #include "../../include/monai_b200.h"
 #include <mutex>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -433,10 +434,24 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void*
   return B200_OK;
 }
 
+template <int NT, int BD>
+int launch_conv_tc2(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats, cudaStream_t st);
+
+// generation-2 kernel (A operand from TMEM, persistent, double-buffered accumulators) for the narrow-N layers;
+// B200_CONV_TC2=0 keeps the generation-1 kernel everywhere
+static bool use_tc2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200_CONV_TC2"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int NT>
 static int dispatch_bd(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats,
                        cudaStream_t st) {
   // deeper CTA tiles amortise the halo and the weight slab; TMEM (BD*NT <= 512) and the plane count bound BD
+  if constexpr (NT == 48 || NT == 32 || NT == 16) {
+    if (use_tc2() && (d.D % 4 == 0 || d.D >= 16)) return launch_conv_tc2<NT, 4>(d, x, w, bias, y, stats, st);
+  }
   if constexpr (NT * 4 <= 512) {
     if (d.D % 4 == 0 || d.D >= 16) return launch_conv_tc<NT, 4>(d, x, w, bias, y, stats, st);
   }

@@ -14,6 +14,8 @@ SHAPES = [  # name, rows per batch item, K, N, act, residual
     ("stage1.qkv 48->144", 343 * 343, 48, 144, 0, False),
     ("stage1.proj 48->48", 343 * 343, 48, 48, 0, True),
     ("stage1.fc1 48->192 gelu", 48**3, 48, 192, L.ACT_GELU, False),
+    ("stage1.fc1 48->192 (no gelu)", 48**3, 48, 192, 0, False),
+    ("stage1.fc2 192->48 (no res)", 48**3, 192, 48, 0, False),
     ("stage1.fc2 192->48 +res", 48**3, 192, 48, 0, True),
     ("stage1.merge 384->96", 24**3, 384, 96, 0, False),
     ("stage2.fc1 96->384 gelu", 24**3, 96, 384, L.ACT_GELU, False),
