@@ -434,8 +434,10 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void*
   return B200_OK;
 }
 
+namespace b200 {
 template <int NT, int BD>
 int launch_conv_tc2(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats, cudaStream_t st);
+}
 
 // generation-2 kernel (A operand from TMEM, persistent, double-buffered accumulators) for the narrow-N layers;
 // B200_CONV_TC2=0 keeps the generation-1 kernel everywhere
