@@ -230,6 +230,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
     if world > 1:
         import torch.distributed as dist
 

@@ -443,7 +443,7 @@ int launch_conv_tc2(const b200_conv_tc_desc& d, const void* x, const void* w, co
 // B200_CONV_TC2=0 keeps the generation-1 kernel everywhere
 static bool use_tc2() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("B200_CONV_TC2"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("B200_CONV_TC2"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
 

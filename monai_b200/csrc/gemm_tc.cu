@@ -62,7 +62,10 @@ __global__ void gemm_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 
 // Persistent, warp-specialised: each CTA loops over (batch, row tile, N tile) work items.  Two TMEM accumulator
 // buffers let the epilogue of tile i overlap the MMAs of tile i+1; the shared-memory ring runs across tile boundaries.
-__global__ void __launch_bounds__(320, 1) gemm_tc_kernel(GemmTcParams p) {
+constexpr int kGemmEpiWarps = 16;   // 4 per TMEM lane quarter: the epilogue is latency-bound (GELU, residual loads), not bandwidth-bound
+constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
+
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int NT = p.NT;
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(GemmTcParams p) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 32 * kGemmEpiWarps); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(GemmTcParams p) {
     __syncwarp();
   } else {
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;      // two warps share a quarter and split the column chunks
+    const int cpart = (warp - 2) >> 2;      // warps sharing a quarter split the 16-column steps between them
     const int cout = d.mode == 2 ? d.N / 8 : d.N;  // channels of the destination tensor written by this GEMM
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -173,7 +176,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(GemmTcParams p) {
       tc::fence_after_sync();
       const uint32_t tacc = tmem_base + buf * NT + ((uint32_t)(q * 32) << 16);
       // 16 columns per step: one tcgen05.ld.x16 (prefetched one step ahead), vector bias loads, packed fp16 converts
-      const int n16 = NT / 16, c_lo = chalf * ((n16 + 1) / 2), c_hi = chalf ? n16 : (n16 + 1) / 2;
+      constexpr int kParts = kGemmEpiWarps / 4;
+      const int n16 = NT / 16, c_lo = (cpart * n16) / kParts, c_hi = ((cpart + 1) * n16) / kParts;
       uint32_t vn[16];
       if (c_lo < c_hi) tc::tmem_ld16(tacc + c_lo * 16, vn);
 #pragma unroll 1
@@ -240,10 +244,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(GemmTcParams p) {
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[buf]);
       if (p.stats) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
         const int t = threadIdx.x - 64;
-        for (int i = t; i < 2 * NT; i += 256) { atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = t; i < 2 * NT; i += 32 * kGemmEpiWarps) { atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
       }
     }
   }
@@ -302,7 +306,7 @@ extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const 
   }
   const long long total_tiles = (long long)ceil_div(d.S, 128) * (d.N / NT) * d.Nb;
   dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
-  gemm_tc_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(p);
+  gemm_tc_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   return B200_OK;
 }

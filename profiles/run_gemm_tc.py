@@ -28,10 +28,13 @@ SHAPES = [  # name, rows per batch item, K, N, act, residual
 def main():
     dev = torch.device("cuda")
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    only = int(sys.argv[2]) if len(sys.argv) > 2 else -1
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, S, Kd, N, act, res in SHAPES:
+    for idx, (name, S, Kd, N, act, res) in enumerate(SHAPES):
+        if only >= 0 and idx != only:
+            continue
         x = K.NC8(batch, Kd, (1, 1, S), dev)
         x.buf.normal_()
         w = K.gemm_tc_pack_weight(torch.randn(N, Kd, device=dev) / Kd**0.5)
