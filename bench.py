@@ -37,7 +37,7 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "swin_c3": dict(
         desc="SwinUNETR(feature_size=48) sliding-window 512^3 fp16, roi 96^3, overlap 0.5, gaussian",
-        vol=(512, 512, 512), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=4, net="swin48", windows=1000,
+        vol=(512, 512, 512), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=8, net="swin48", windows=1000,
         flop_per_window=636e9,
     ),
 }
@@ -231,13 +231,19 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
+    _lib.load()
+    net = build_net(wl["net"], dev, half=True)
+    # capture the network's CUDA graphs (full batch + this rank's remainder batch) BEFORE NCCL starts its helper
+    # threads, so no capture ever runs concurrently with communicator activity
+    per_rank = [wl["windows"] * (k + 1) // world - wl["windows"] * k // world for k in range(world)]
+    for nb in sorted({wl["sw_batch"]} | {c % wl["sw_batch"] for c in per_rank if c % wl["sw_batch"]}):
+        net(torch.zeros((nb, 1, *wl["roi"]), device=dev, dtype=torch.float16))
+    torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
 
-    net = build_net(wl["net"], dev, half=True)
     vol = wl["vol"]
     host = torch.randn((1, 1, *vol), generator=torch.Generator().manual_seed(0)).half().pin_memory()
     x_dev = host.to(dev)

@@ -164,6 +164,11 @@ int b200_conv_gather_tc_pack_weight(const b200_conv_gather_desc* desc, const flo
 int b200_conv_gather_tc(const b200_conv_gather_desc* desc, const void* x, const void* packed_w, const float* bias, void* y,
                         float* stats, void* stream);
 
+/* Thin head: ConvTranspose3d(k3, s2, p1, output_padding 1) from NC8 features to <= 4 NCDHW logit channels
+ * (top layer of UNet, monai/networks/nets/unet.py); weight float32 [Cin][Cout][3][3][3]. */
+int b200_convt3s2_head_nc8(const void* x, int N, int Cin, int Di, int Hi, int Wi, int in_ctot, int in_coff,
+                           const float* weight, const float* bias, int Cout, void* y, int out_dtype, void* stream);
+
 typedef struct b200_gemm_tc_desc {
   int Nb;                   /* batch items (each with its own S rows) */
   int S;                    /* GEMM rows per batch item (tokens / voxels of x) */

@@ -494,3 +494,12 @@ def conv_gather_tc(
           L.stream_ptr(x.buf.device), flops=2.0 * x.N * sp_out[0] * sp_out[1] * sp_out[2] * Cin * Cout * taps,
           nbytes=float(x.N * (x.S * Cin + sp_out[0] * sp_out[1] * sp_out[2] * Cout) * 2) + _nb(packed_w))
     return out, stats
+
+
+def convt3s2_head_nc8(x: NC8, Cin: int, weight: torch.Tensor, bias: torch.Tensor | None, in_coff: int = 0, out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """ConvTranspose3d(k3, s2, p1, op1) head: NC8 features -> NCDHW logits with <= 4 channels (CUDA cores)."""
+    Cout = weight.shape[1]
+    y = torch.empty((x.N, Cout, *(2 * s for s in x.sp)), device=x.buf.device, dtype=out_dtype)
+    _call("convt3s2_head_nc8", L.ptr(x.buf), x.N, Cin, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, L.ptr(_f32c(weight)), L.ptr(_f32c(bias)), Cout,
+          L.ptr(y), L.dt(y), L.stream_ptr(x.buf.device), flops=2.0 * x.N * x.S * 27 * Cin * Cout, nbytes=float(x.N * x.S * Cin * 2) + _nb(y))
+    return y

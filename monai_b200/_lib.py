@@ -86,6 +86,7 @@ SIGNATURES = {
     "b200_conv_gather_tc_weight_bytes": (i64, [C.POINTER(ConvGatherDesc)]),
     "b200_conv_gather_tc_pack_weight": (i32, [C.POINTER(ConvGatherDesc), vp, vp, vp]),
     "b200_conv_gather_tc": (i32, [C.POINTER(ConvGatherDesc), vp, vp, vp, vp, vp, vp]),
+    "b200_convt3s2_head_nc8": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp]),
     "b200_gemm_tc_weight_bytes": (i64, [i32, i32]),
     "b200_gemm_tc_pack_weight": (i32, [vp, i32, i32, i64, i64, vp, vp]),
     "b200_gemm_tc": (i32, [C.POINTER(GemmTcDesc), vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -238,3 +238,98 @@ extern "C" int b200_copy_channels(const void* x, int dtype, int N, int C, int Di
   B200_LAUNCH_CHECK("copy_channels_kernel");
   return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Thin segmentation head: ConvTranspose3d(kernel 3, stride 2, padding 1, output_padding 1) from NC8 fp16 features to
+// <= 4 NCDHW logit channels (the top layer of UNet, monai/networks/nets/unet.py:_get_up_layer with is_top).  With two
+// output channels the GEMM is 16x padded on tensor cores and bound by the im2col gather, so this layer runs on CUDA
+// cores: one thread per output voxel of ONE parity class (block-uniform live taps), 16-byte channel vectors in,
+// weights broadcast from shared memory, fp32 accumulation.
+namespace b200 {
+
+struct HeadP {
+  const __half* x; void* y; const float* w; const float* bias;
+  int N, Cin, Cout, Di, Hi, Wi, in_ctot, in_coff, out_dtype;
+};
+
+template <typename TO>
+__global__ void __launch_bounds__(128) convt3s2_head_nc8_kernel(HeadP p) {
+  extern __shared__ float s_hw[];  // [27][Cin][4]
+  __shared__ int s_tp[8][4];
+  __shared__ int s_nt;
+  for (int i = threadIdx.x; i < 27 * p.Cin * 4; i += blockDim.x) {
+    const int co = i & 3, ci = (i >> 2) % p.Cin, tap = i / (4 * p.Cin);
+    s_hw[i] = co < p.Cout ? p.w[((long long)ci * p.Cout + co) * 27 + tap] : 0.f;   // ConvTranspose3d weight [Cin][Cout][3][3][3]
+  }
+  const int cls = blockIdx.y, n = blockIdx.z;
+  const int px = cls & 1, py = (cls >> 1) & 1, pz = cls >> 2;
+  if (threadIdx.x == 0) {
+    int nt = 0;
+    for (int kz = 0; kz < 3; ++kz)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int tz = pz + 1 - kz, ty = py + 1 - ky, tx = px + 1 - kx;   // (o + pad - k) must be even
+          if ((tz & 1) || (ty & 1) || (tx & 1)) continue;
+          s_tp[nt][0] = (kz * 3 + ky) * 3 + kx; s_tp[nt][1] = tz / 2; s_tp[nt][2] = ty / 2; s_tp[nt][3] = tx / 2;
+          ++nt;
+        }
+    s_nt = nt;
+  }
+  __syncthreads();
+  const long long Si = (long long)p.Di * p.Hi * p.Wi;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Si) return;
+  const int cx = (int)(t % p.Wi), cy = (int)((t / p.Wi) % p.Hi), cz = (int)(t / ((long long)p.Wi * p.Hi));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const __half* xn = p.x + ((long long)n * (p.in_ctot / 8) + p.in_coff / 8) * Si * 8;
+  const int nt = s_nt, C8 = p.Cin / 8;
+  for (int q = 0; q < nt; ++q) {
+    const int iz = cz + s_tp[q][1], iy = cy + s_tp[q][2], ix = cx + s_tp[q][3];
+    if (iz < 0 || iz >= p.Di || iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+    const __half* xp = xn + (((long long)iz * p.Hi + iy) * p.Wi + ix) * 8;
+    const float4* wp = reinterpret_cast<const float4*>(s_hw) + (long long)s_tp[q][0] * p.Cin;
+    for (int c = 0; c < C8; ++c) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xp + (long long)c * Si * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        const float4 w0 = wp[c * 8 + 2 * j], w1 = wp[c * 8 + 2 * j + 1];
+        acc[0] = fmaf(f.x, w0.x, acc[0]); acc[1] = fmaf(f.x, w0.y, acc[1]); acc[2] = fmaf(f.x, w0.z, acc[2]); acc[3] = fmaf(f.x, w0.w, acc[3]);
+        acc[0] = fmaf(f.y, w1.x, acc[0]); acc[1] = fmaf(f.y, w1.y, acc[1]); acc[2] = fmaf(f.y, w1.z, acc[2]); acc[3] = fmaf(f.y, w1.w, acc[3]);
+      }
+    }
+  }
+  const int Do = 2 * p.Di, Ho = 2 * p.Hi, Wo = 2 * p.Wi;
+  const long long So = (long long)Do * Ho * Wo;
+  const long long o = ((long long)(2 * cz + pz) * Ho + (2 * cy + py)) * Wo + (2 * cx + px);
+  for (int co = 0; co < p.Cout; ++co)
+    io<TO>::st((TO*)p.y + ((long long)n * p.Cout + co) * So + o, acc[co] + (p.bias ? p.bias[co] : 0.f));
+}
+
+}  // namespace b200
+
+extern "C" int b200_convt3s2_head_nc8(const void* x, int N, int Cin, int Di, int Hi, int Wi, int in_ctot, int in_coff,
+                                      const float* weight, const float* bias, int Cout, void* y, int out_dtype, void* stream) {
+  B200_REQUIRE(x && weight && y, "convt3s2_head_nc8: null pointer");
+  B200_REQUIRE(Cout >= 1 && Cout <= 4, "convt3s2_head_nc8: 1..4 output channels (got %d)", Cout);
+  B200_REQUIRE(Cin % 8 == 0 && in_ctot % 8 == 0 && in_coff % 8 == 0 && in_coff + Cin <= in_ctot, "convt3s2_head_nc8: bad channel slice");
+  B200_REQUIRE(N <= 65535, "convt3s2_head_nc8: batch too large");
+  HeadP p{(const __half*)x, y, weight, bias, N, Cin, Cout, Di, Hi, Wi, in_ctot, in_coff, out_dtype};
+  const long long Si = (long long)Di * Hi * Wi;
+  const size_t smem = (size_t)27 * Cin * 4 * sizeof(float);
+  B200_REQUIRE(smem <= 96 * 1024, "convt3s2_head_nc8: Cin too large (%d)", Cin);
+  dim3 grid(ceil_div(Si, 128), 8, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == B200_DT_F16) {
+    static bool a1 = false;
+    if (!a1) { B200_CUDA(cudaFuncSetAttribute(convt3s2_head_nc8_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); a1 = true; }
+    convt3s2_head_nc8_kernel<__half><<<grid, 128, smem, st>>>(p);
+  } else if (out_dtype == B200_DT_F32) {
+    static bool a2 = false;
+    if (!a2) { B200_CUDA(cudaFuncSetAttribute(convt3s2_head_nc8_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); a2 = true; }
+    convt3s2_head_nc8_kernel<float><<<grid, 128, smem, st>>>(p);
+  } else return set_err(B200_ERR_INVALID, "convt3s2_head_nc8: bad dtype");
+  B200_LAUNCH_CHECK("convt3s2_head_nc8_kernel");
+  return B200_OK;
+}

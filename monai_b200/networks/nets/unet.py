@@ -185,6 +185,8 @@ class UNet(GraphedForward, nn.Module):
             self._tc_level(sub, cat, c, None, False, cat, c, None)
         upm = up.conv
         if top:  # conv only: logits straight to NCDHW
+            if upm.out_channels <= 4 and upm.kernel_size[0] == 3 and upm.stride[0] == 2 and upm.padding[0] == 1 and upm.output_padding[0] == 1:
+                return K.convt3s2_head_nc8(cat, c + c_sub, upm.weight, upm.bias, out_dtype=out_dtype)
             pw = self._cached(("w", id(upm)), [upm.weight], lambda: K.conv_gather_tc_pack_weight(upm.weight, upm.kernel_size[0], upm.stride[0], upm.padding[0], True))
             y, _ = K.conv_gather_tc(cat, pw, c + c_sub, upm.out_channels, upm.kernel_size[0], upm.stride[0], upm.padding[0], transposed=True,
                                     output_padding=upm.output_padding[0], bias=upm.bias, ncdhw_dtype=out_dtype)

@@ -64,3 +64,15 @@ def test_transposed_head_to_ncdhw(dtype):
     y, _ = K.conv_gather_tc(K.pack_nc8(x.to(DEV)), pw, 32, 2, 3, 2, 1, transposed=True, output_padding=1, bias=b.to(DEV), ncdhw_dtype=dtype)
     assert y.shape == ref.shape and y.dtype == dtype
     _check(y.float().cpu(), ref, "head")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_thin_head_cuda_core_kernel(dtype):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((2, 32, 6, 7, 9), generator=g).half()
+    w = (torch.randn((32, 2, 3, 3, 3), generator=g) / 10).half()
+    b = torch.randn(2, generator=g)
+    ref = F.conv_transpose3d(x.float(), w.float(), b, stride=2, padding=1, output_padding=1)
+    y = K.convt3s2_head_nc8(K.pack_nc8(x.to(DEV)), 32, w.float().to(DEV), b.to(DEV), out_dtype=dtype)
+    assert y.shape == ref.shape and y.dtype == dtype
+    _check(y.float().cpu(), ref, "thin head")
