@@ -52,7 +52,7 @@ typedef struct b200_blend_desc {
   int out_dtype;
   const float* acc;         /* mode 2: fp32 accumulators */
   int box[4];               /* rows to visit: d in [box0,box1), h in [box2,box3); all-zero = whole volume */
-  int starts_w_all_even;    /* host hint: every entry of starts_w is even (enables the 2-voxels-per-thread path) */
+  int starts_w_align;       /* host hint: a common divisor of every starts_w entry (2 -> 2 voxels/thread, 8 -> 8 voxels/thread; 1 or 0 = unknown) */
 } b200_blend_desc;
 
 /* replaces monai/inferers/utils.py:264-275, 286-288, 297-298, 351-360.

@@ -240,7 +240,7 @@ def sw_blend(
     d.acc = L.ptr(acc)
     for i in range(4):
         d.box[i] = box[i]
-    d.starts_w_all_even = int(bool(getattr(starts[2], "_all_even", False)))
+    d.starts_w_align = int(getattr(starts[2], "_align", 1))
     nb = _nb(preds) + (_nb(out) if mode == 0 else 0.0) + (2.0 * _nb(out) if mode == 1 else 0.0) + (_nb(out, acc) if mode == 2 else 0.0)
     _call("sw_blend", C.byref(d), mode, L.stream_ptr(out.device), nbytes=nb)
 

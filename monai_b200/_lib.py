@@ -30,7 +30,7 @@ class BlendDesc(C.Structure):
         ("B", i32), ("C", i32), ("D", i32), ("H", i32), ("W", i32), ("rd", i32), ("rh", i32), ("rw", i32),
         ("starts_d", vp), ("nd", i32), ("starts_h", vp), ("nh", i32), ("starts_w", vp), ("nw", i32),
         ("gd", vp), ("gh", vp), ("gw", vp), ("clamp_min", f32), ("wmap", vp),
-        ("out", vp), ("out_dtype", i32), ("acc", vp), ("box", i32 * 4), ("starts_w_all_even", i32),
+        ("out", vp), ("out_dtype", i32), ("acc", vp), ("box", i32 * 4), ("starts_w_align", i32),
     ]
 
 

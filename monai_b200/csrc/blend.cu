@@ -163,6 +163,220 @@ __global__ void __launch_bounds__(128) sw_blend_kernel(BlendParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Eight voxels per thread (one 16-byte fp16 vector per prediction channel).  Usable when W, the roi and every window
+// start along W are multiples of 8, so a thread's octet is covered by whole windows only.  A warp owns one (d, h) row
+// segment: the covering ranges along D and H are warp-uniform, the loop over the covering W windows is per lane.
+// Same fp32 operation order as the scalar kernel (ascending window index), hence bit-identical results.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TP> struct Pred8;
+template <> struct Pred8<__half> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw ld(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void cvt(const Raw& r, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  }
+};
+template <> struct Pred8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw ld(const float* p) {
+    Raw r; r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1); return r;
+  }
+  static __device__ __forceinline__ void cvt(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
+};
+__device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename TO> __device__ __forceinline__ void st8o(TO* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void st8o<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void st8o<__half>(__half* p, const float (&v)[8]) {
+  uint4 r;
+  __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+constexpr int kBlend8Rows = 8;   // warps (= h rows) per block
+constexpr int kBlend8K = 3;      // W windows per (d, h) window pair handled by the pipelined path (overlap <= 2/3)
+
+template <typename TP, typename TO, int MODE>
+__global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_blend8_kernel(BlendParams p) {
+  using Raw = typename Pred8<TP>::Raw;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int w8 = (blockIdx.x * 32 + lane) * 8;
+  const int h = p.h0 + blockIdx.y * kBlend8Rows + wrp;
+  const int nd_box = p.d1 - p.d0;
+  const int d = blockIdx.z % nd_box + p.d0, b = blockIdx.z / nd_box;
+  if (h >= p.h1 || w8 >= p.W) return;
+  // the window starts are sorted, so the windows covering a coordinate form a contiguous index range per axis
+  int id_lo = 0, ndc = 0, ih_lo = 0, nhc = 0, iw_lo = 0, nwc = 0;
+  for (int i = 0; i < p.nd; ++i) { const int s = __ldg(p.starts_d + i); if (s <= d && d < s + p.rd) { if (!ndc) id_lo = i; ++ndc; } }
+  for (int i = 0; i < p.nh; ++i) { const int s = __ldg(p.starts_h + i); if (s <= h && h < s + p.rh) { if (!nhc) ih_lo = i; ++nhc; } }
+  for (int i = 0; i < p.nw; ++i) { const int s = __ldg(p.starts_w + i); if (s <= w8 && w8 < s + p.rw) { if (!nwc) iw_lo = i; ++nwc; } }
+  const int num_win = p.nd * p.nh * p.nw;
+  const long long vol = (long long)p.D * p.H * p.W;
+  const long long voff = ((long long)d * p.H + h) * p.W + w8;
+  const TP* __restrict__ preds = (const TP*)p.preds;
+  const bool dense = p.wmap != nullptr;
+  const bool piped = !dense && nwc <= kBlend8K;
+  // pipelined path: the W-factor vectors of this thread's (at most 3) W windows never change -> registers
+  int lwk[kBlend8K];
+  float gwk[kBlend8K][8];
+  if (piped) {
+#pragma unroll
+    for (int k = 0; k < kBlend8K; ++k) {
+      lwk[k] = k < nwc ? w8 - __ldg(p.starts_w + iw_lo + k) : 0;
+      ld8f(p.gw + lwk[k], gwk[k]);
+    }
+  }
+  float cnt[8];
+  for (int c0 = 0; c0 < (MODE == 2 ? 1 : p.C); c0 += 2) {
+    const bool two = (MODE != 2) && (c0 + 1 < p.C);
+    float a0[8], a1[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) { cnt[v] = 0.f; a0[v] = 0.f; a1[v] = 0.f; }
+    if (MODE == 1) {
+      ld8f((const float*)p.out + ((long long)b * p.C + c0) * vol + voff, a0);
+      if (two) ld8f((const float*)p.out + ((long long)b * p.C + c0 + 1) * vol + voff, a1);
+    }
+    if (piped) {
+      // The (d, h) window pairs are walked in ascending window order; the prediction vectors of pair q+1 are requested
+      // before pair q is accumulated, so up to 12 16-byte loads per thread are in flight (the kernel is latency-bound
+      // otherwise: every prediction is read exactly once and nothing is reused).
+      const int P = ndc * nhc;
+      auto issue = [&](int a, int e, Raw (&r0)[kBlend8K], Raw (&r1)[kBlend8K]) {
+        if (MODE == 2) return;
+        const int id = id_lo + a, ih = ih_lo + e;
+        const int ld = d - __ldg(p.starts_d + id), lh = h - __ldg(p.starts_h + ih);
+        const long long rowoff = (long long)ld * p.ps_d + (long long)lh * p.ps_h + (long long)c0 * p.ps_c;
+        const int wbase = b * num_win + (id * p.nh + ih) * p.nw + iw_lo;
+#pragma unroll
+        for (int k = 0; k < kBlend8K; ++k) {
+          const int widx = wbase + k;
+          if (k < nwc && widx >= p.win_begin && widx < p.win_end) {
+            const TP* pp = preds + (long long)(widx - p.win_begin) * p.ps_n + rowoff + lwk[k];
+            r0[k] = Pred8<TP>::ld(pp);
+            if (two) r1[k] = Pred8<TP>::ld(pp + p.ps_c);
+          }
+        }
+      };
+      auto consume = [&](int a, int e, const Raw (&r0)[kBlend8K], const Raw (&r1)[kBlend8K]) {
+        const int id = id_lo + a, ih = ih_lo + e;
+        const int ld = d - __ldg(p.starts_d + id), lh = h - __ldg(p.starts_h + ih);
+        const float gdh = __fmul_rn(__ldg(p.gd + ld), __ldg(p.gh + lh));
+        const int wbase = b * num_win + (id * p.nh + ih) * p.nw + iw_lo;
+#pragma unroll
+        for (int k = 0; k < kBlend8K; ++k) {
+          if (k < nwc) {
+            float t[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) { t[v] = fmaxf(__fmul_rn(gdh, gwk[k][v]), p.clamp_min); cnt[v] = __fadd_rn(cnt[v], t[v]); }
+            const int widx = wbase + k;
+            if (MODE != 2 && widx >= p.win_begin && widx < p.win_end) {
+              float xv[8];
+              Pred8<TP>::cvt(r0[k], xv);
+#pragma unroll
+              for (int v = 0; v < 8; ++v) a0[v] = __fadd_rn(a0[v], __fmul_rn(xv[v], t[v]));
+              if (two) {
+                Pred8<TP>::cvt(r1[k], xv);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) a1[v] = __fadd_rn(a1[v], __fmul_rn(xv[v], t[v]));
+              }
+            }
+          }
+        }
+      };
+      Raw A0[kBlend8K], A1[kBlend8K], B0[kBlend8K], B1[kBlend8K];
+      int ai = 0, ei = 0, ac = 0, ec = 0;   // (d, h) pair positions of the load stream and of the accumulate stream
+      auto adv = [&](int& a, int& e) { if (++e == nhc) { e = 0; ++a; } };
+      if (P > 0) { issue(ai, ei, A0, A1); adv(ai, ei); }
+      for (int q = 0; q < P; q += 2) {
+        if (q + 1 < P) { issue(ai, ei, B0, B1); adv(ai, ei); }
+        consume(ac, ec, A0, A1); adv(ac, ec);
+        if (q + 1 < P) {
+          if (q + 2 < P) { issue(ai, ei, A0, A1); adv(ai, ei); }
+          consume(ac, ec, B0, B1); adv(ac, ec);
+        }
+      }
+    } else {
+      for (int a = 0; a < ndc; ++a) {
+        const int id = id_lo + a;
+        const int ld = d - __ldg(p.starts_d + id);
+        for (int e = 0; e < nhc; ++e) {
+          const int ih = ih_lo + e;
+          const int lh = h - __ldg(p.starts_h + ih);
+          const float gdh = dense ? 0.f : __fmul_rn(__ldg(p.gd + ld), __ldg(p.gh + lh));
+          const long long rowoff = (long long)ld * p.ps_d + (long long)lh * p.ps_h + (long long)c0 * p.ps_c;
+          const int wbase = b * num_win + (id * p.nh + ih) * p.nw;
+          for (int k = 0; k < nwc; ++k) {
+            const int iw = iw_lo + k;
+            const int lw = w8 - __ldg(p.starts_w + iw);
+            const int widx = wbase + iw;
+            const bool res = (MODE != 2) && widx >= p.win_begin && widx < p.win_end;
+            Raw r0, r1;
+            if (res) {
+              const TP* pp = preds + (long long)(widx - p.win_begin) * p.ps_n + rowoff + lw;
+              r0 = Pred8<TP>::ld(pp);
+              if (two) r1 = Pred8<TP>::ld(pp + p.ps_c);
+            }
+            float t[8];
+            if (dense) {
+              ld8f(p.wmap + ((long long)ld * p.rh + lh) * p.rw + lw, t);
+            } else {
+              ld8f(p.gw + lw, t);
+#pragma unroll
+              for (int v = 0; v < 8; ++v) t[v] = fmaxf(__fmul_rn(gdh, t[v]), p.clamp_min);
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v) cnt[v] = __fadd_rn(cnt[v], t[v]);
+            if (res) {
+              float xv[8];
+              Pred8<TP>::cvt(r0, xv);
+#pragma unroll
+              for (int v = 0; v < 8; ++v) a0[v] = __fadd_rn(a0[v], __fmul_rn(xv[v], t[v]));
+              if (two) {
+                Pred8<TP>::cvt(r1, xv);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) a1[v] = __fadd_rn(a1[v], __fmul_rn(xv[v], t[v]));
+              }
+            }
+          }
+        }
+      }
+    }
+    if (MODE == 2) break;
+    const long long o0 = ((long long)b * p.C + c0) * vol + voff;
+    if (MODE == 0) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) { a0[v] = __fdiv_rn(a0[v], cnt[v]); a1[v] = __fdiv_rn(a1[v], cnt[v]); }
+      st8o<TO>((TO*)p.out + o0, a0);
+      if (two) st8o<TO>((TO*)p.out + o0 + vol, a1);
+    } else {
+      st8o<float>((float*)p.out + o0, a0);
+      if (two) st8o<float>((float*)p.out + o0 + vol, a1);
+    }
+  }
+  if (MODE == 2) {
+    for (int c = 0; c < p.C; ++c) {
+      const long long o = ((long long)b * p.C + c) * vol + voff;
+      float xv[8];
+      ld8f(p.acc + o, xv);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) xv[v] = __fdiv_rn(xv[v], cnt[v]);
+      st8o<TO>((TO*)p.out + o, xv);
+    }
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) sw_gather_kernel(const TI* __restrict__ vol, TO* __restrict__ out,
                                                         const int* __restrict__ tab, int C, int D, int H, int W,
@@ -205,7 +419,30 @@ static int launch_blend_v(const BlendParams& p, int pred_dtype, int out_dtype, c
 }
 
 template <int MODE>
-static int launch_blend(const BlendParams& p, int pred_dtype, int out_dtype, bool vec2, cudaStream_t st) {
+static int launch_blend8(const BlendParams& p, int pred_dtype, int out_dtype, cudaStream_t st) {
+  dim3 block(32 * kBlend8Rows);
+  dim3 grid(ceil_div(p.W / 8, 32), ceil_div(p.h1 - p.h0, kBlend8Rows), (p.d1 - p.d0) * p.B);
+  if (grid.y == 0 || grid.z == 0) return B200_OK;
+  B200_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "sw_blend: volume too large for the launch grid");
+#define LB(TP, TO) sw_blend8_kernel<TP, TO, MODE><<<grid, block, 0, st>>>(p)
+  if (MODE == 1) {
+    if (pred_dtype == B200_DT_F16) LB(__half, float); else LB(float, float);
+  } else if (MODE == 2) {
+    if (out_dtype == B200_DT_F16) LB(float, __half); else LB(float, float);
+  } else {
+    if (pred_dtype == B200_DT_F16 && out_dtype == B200_DT_F16) LB(__half, __half);
+    else if (pred_dtype == B200_DT_F16) LB(__half, float);
+    else if (out_dtype == B200_DT_F16) LB(float, __half);
+    else LB(float, float);
+  }
+#undef LB
+  B200_LAUNCH_CHECK("sw_blend8_kernel");
+  return B200_OK;
+}
+
+template <int MODE>
+static int launch_blend(const BlendParams& p, int pred_dtype, int out_dtype, bool vec2, bool vec8, cudaStream_t st) {
+  if (vec8) return launch_blend8<MODE>(p, pred_dtype, out_dtype, st);
   return vec2 ? launch_blend_v<MODE, 2>(p, pred_dtype, out_dtype, st) : launch_blend_v<MODE, 1>(p, pred_dtype, out_dtype, st);
 }
 
@@ -234,14 +471,20 @@ extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream)
   B200_REQUIRE(p.d0 >= 0 && p.d1 <= p.D && p.h0 >= 0 && p.h1 <= p.H, "sw_blend: box outside the volume");
   cudaStream_t st = (cudaStream_t)stream;
   // two voxels per thread when every window start, the roi and W are even and predictions are contiguous along W
-  bool vec2 = (p.W % 2 == 0) && (p.rw % 2 == 0) && (mode == 2 || p.ps_w == 1) && dsc->starts_w_all_even;
+  bool vec2 = (p.W % 2 == 0) && (p.rw % 2 == 0) && (mode == 2 || p.ps_w == 1) && dsc->starts_w_align >= 2 && dsc->starts_w_align % 2 == 0;
   if (vec2 && mode != 2) {
     const int esz = dsc->pred_dtype == B200_DT_F16 ? 2 : 4;
     vec2 = (reinterpret_cast<uintptr_t>(p.preds) % (2 * esz) == 0) && p.ps_n % 2 == 0 && p.ps_c % 2 == 0 && p.ps_d % 2 == 0 && p.ps_h % 2 == 0;
   }
-  if (mode == 0) return launch_blend<0>(p, dsc->pred_dtype, dsc->out_dtype, vec2, st);
-  if (mode == 1) return launch_blend<1>(p, dsc->pred_dtype, dsc->out_dtype, vec2, st);
-  return launch_blend<2>(p, dsc->pred_dtype, dsc->out_dtype, vec2, st);
+  // eight voxels per thread: everything along W is a multiple of 8 and every vector access is 16-byte aligned
+  bool vec8 = (p.W % 8 == 0) && (p.rw % 8 == 0) && (mode == 2 || p.ps_w == 1) && dsc->starts_w_align >= 8 && dsc->starts_w_align % 8 == 0 &&
+              reinterpret_cast<uintptr_t>(p.out) % 16 == 0 && (mode != 2 || reinterpret_cast<uintptr_t>(p.acc) % 16 == 0) &&
+              (p.wmap ? reinterpret_cast<uintptr_t>(p.wmap) % 16 == 0 : reinterpret_cast<uintptr_t>(p.gw) % 16 == 0);
+  if (vec8 && mode != 2)
+    vec8 = (reinterpret_cast<uintptr_t>(p.preds) % 16 == 0) && p.ps_n % 8 == 0 && p.ps_c % 8 == 0 && p.ps_d % 8 == 0 && p.ps_h % 8 == 0;
+  if (mode == 0) return launch_blend<0>(p, dsc->pred_dtype, dsc->out_dtype, vec2, vec8, st);
+  if (mode == 1) return launch_blend<1>(p, dsc->pred_dtype, dsc->out_dtype, vec2, vec8, st);
+  return launch_blend<2>(p, dsc->pred_dtype, dsc->out_dtype, vec2, vec8, st);
 }
 
 extern "C" int b200_sw_gather(const void* vol, int in_dtype, void* out, int out_dtype, const int32_t* win_tab,

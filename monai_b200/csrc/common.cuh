@@ -52,10 +52,12 @@ template <typename T> struct io;
 template <> struct io<float> {
   __device__ static __forceinline__ float ld(const float* p) { return __ldg(p); }
   __device__ static __forceinline__ void st(float* p, float v) { *p = v; }
+  __device__ static __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }  // 8-byte aligned
 };
 template <> struct io<__half> {
   __device__ static __forceinline__ float ld(const __half* p) { return __half2float(__ldg(p)); }
   __device__ static __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+  __device__ static __forceinline__ void st2(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }  // 4-byte aligned
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -252,59 +252,94 @@ struct HeadP {
   int N, Cin, Cout, Di, Hi, Wi, in_ctot, in_coff, out_dtype;
 };
 
-template <typename TO>
-__global__ void __launch_bounds__(128) convt3s2_head_nc8_kernel(HeadP p) {
-  extern __shared__ float s_hw[];  // [27][Cin][4]
-  __shared__ int s_tp[8][4];
-  __shared__ int s_nt;
-  for (int i = threadIdx.x; i < 27 * p.Cin * 4; i += blockDim.x) {
-    const int co = i & 3, ci = (i >> 2) % p.Cin, tap = i / (4 * p.Cin);
-    s_hw[i] = co < p.Cout ? p.w[((long long)ci * p.Cout + co) * 27 + tap] : 0.f;   // ConvTranspose3d weight [Cin][Cout][3][3][3]
+// Thin ConvTranspose3d(k3, s2, p1, output_padding 1) head (UNet's last up layer, convolutions.py:131-152 with
+// is_transposed=True): a handful of output channels, so CUDA cores.  One thread owns one INPUT cell (cz,cy,cx) and
+// produces the 2x2x2 output voxels (2c + p) of every output channel from the 2x2x2 input neighbourhood {c, c+1}^3:
+// along an axis, parity 0 takes (input c, tap 1) and parity 1 takes (input c, tap 2) + (input c+1, tap 0) -- 27
+// (neighbour, tap) pairs in total, all resolved at compile time.  Weights sit in shared memory as [tap][cin][CO].
+template <typename TO, int CO>
+__global__ void __launch_bounds__(256) convt3s2_head_nc8_kernel(HeadP p) {
+  extern __shared__ float s_hw[];  // [27][Cin][CO]
+  for (int i = threadIdx.x; i < 27 * p.Cin * p.Cout; i += blockDim.x) {
+    // ConvTranspose3d weight [Cin][Cout][3][3][3], read linearly
+    const int tap = i % 27, co = (i / 27) % p.Cout, ci = i / (27 * p.Cout);
+    s_hw[(tap * p.Cin + ci) * CO + co] = p.w[i];
   }
-  const int cls = blockIdx.y, n = blockIdx.z;
-  const int px = cls & 1, py = (cls >> 1) & 1, pz = cls >> 2;
-  if (threadIdx.x == 0) {
-    int nt = 0;
-    for (int kz = 0; kz < 3; ++kz)
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) {
-          const int tz = pz + 1 - kz, ty = py + 1 - ky, tx = px + 1 - kx;   // (o + pad - k) must be even
-          if ((tz & 1) || (ty & 1) || (tx & 1)) continue;
-          s_tp[nt][0] = (kz * 3 + ky) * 3 + kx; s_tp[nt][1] = tz / 2; s_tp[nt][2] = ty / 2; s_tp[nt][3] = tx / 2;
-          ++nt;
-        }
-    s_nt = nt;
-  }
+  if (p.Cout < CO)
+    for (int i = threadIdx.x; i < 27 * p.Cin; i += blockDim.x)
+      for (int co = p.Cout; co < CO; ++co) s_hw[i * CO + co] = 0.f;
   __syncthreads();
   const long long Si = (long long)p.Di * p.Hi * p.Wi;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Si) return;
-  const int cx = (int)(t % p.Wi), cy = (int)((t / p.Wi) % p.Hi), cz = (int)(t / ((long long)p.Wi * p.Hi));
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const __half* xn = p.x + ((long long)n * (p.in_ctot / 8) + p.in_coff / 8) * Si * 8;
-  const int nt = s_nt, C8 = p.Cin / 8;
-  for (int q = 0; q < nt; ++q) {
-    const int iz = cz + s_tp[q][1], iy = cy + s_tp[q][2], ix = cx + s_tp[q][3];
-    if (iz < 0 || iz >= p.Di || iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
-    const __half* xp = xn + (((long long)iz * p.Hi + iy) * p.Wi + ix) * 8;
-    const float4* wp = reinterpret_cast<const float4*>(s_hw) + (long long)s_tp[q][0] * p.Cin;
-    for (int c = 0; c < C8; ++c) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(xp + (long long)c * Si * 8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  const int Ho = 2 * p.Hi, Wo = 2 * p.Wi;
+  const long long So = 8 * Si;
+  const int C8 = p.Cin / 8;
+  float bias[CO];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h2[j]);
-        const float4 w0 = wp[c * 8 + 2 * j], w1 = wp[c * 8 + 2 * j + 1];
-        acc[0] = fmaf(f.x, w0.x, acc[0]); acc[1] = fmaf(f.x, w0.y, acc[1]); acc[2] = fmaf(f.x, w0.z, acc[2]); acc[3] = fmaf(f.x, w0.w, acc[3]);
-        acc[0] = fmaf(f.y, w1.x, acc[0]); acc[1] = fmaf(f.y, w1.y, acc[1]); acc[2] = fmaf(f.y, w1.z, acc[2]); acc[3] = fmaf(f.y, w1.w, acc[3]);
+  for (int co = 0; co < CO; ++co) bias[co] = (p.bias && co < p.Cout) ? p.bias[co] : 0.f;
+  for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < (long long)p.N * Si; cell += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(cell / Si);
+    const long long t = cell - (long long)n * Si;
+    const int cx = (int)(t % p.Wi), cy = (int)((t / p.Wi) % p.Hi), cz = (int)(t / ((long long)p.Wi * p.Hi));
+    const __half* xn = p.x + ((long long)n * (p.in_ctot / 8) + p.in_coff / 8) * Si * 8;
+    float acc[8][CO];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int co = 0; co < CO; ++co) acc[q][co] = bias[co];
+    for (int c = 0; c < C8; ++c) {
+      const float* wc = s_hw + c * 8 * CO;
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int iz = cz + dz, iy = cy + dy, ix = cx + dx;
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (iz < p.Di && iy < p.Hi && ix < p.Wi)
+              raw = __ldg(reinterpret_cast<const uint4*>(xn + ((long long)c * Si + ((long long)iz * p.Hi + iy) * p.Wi + ix) * 8));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f2 = __half22float2(h2[j]); v[2 * j] = f2.x; v[2 * j + 1] = f2.y; }
+#pragma unroll
+            for (int oz = 0; oz < (dz ? 1 : 2); ++oz)
+#pragma unroll
+              for (int oy = 0; oy < (dy ? 1 : 2); ++oy)
+#pragma unroll
+                for (int ox = 0; ox < (dx ? 1 : 2); ++ox) {
+                  const int pz = dz ? 1 : oz, py = dy ? 1 : oy, px = dx ? 1 : ox;
+                  const int kz = dz ? 0 : (oz ? 2 : 1), ky = dy ? 0 : (oy ? 2 : 1), kx = dx ? 0 : (ox ? 2 : 1);
+                  const int tap = (kz * 3 + ky) * 3 + kx, par = pz * 4 + py * 2 + px;
+                  const float* wt = wc + (long long)tap * p.Cin * CO;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    if (CO == 2) {
+                      const float2 w2 = *reinterpret_cast<const float2*>(wt + j * 2);
+                      acc[par][0] = fmaf(v[j], w2.x, acc[par][0]); acc[par][1] = fmaf(v[j], w2.y, acc[par][1]);
+                    } else {
+                      const float4 w4 = *reinterpret_cast<const float4*>(wt + j * 4);
+                      acc[par][0] = fmaf(v[j], w4.x, acc[par][0]); acc[par][1] = fmaf(v[j], w4.y, acc[par][1]);
+                      acc[par][2 % CO] = fmaf(v[j], w4.z, acc[par][2 % CO]); acc[par][3 % CO] = fmaf(v[j], w4.w, acc[par][3 % CO]);
+                    }
+                  }
+                }
+          }
+    }
+    TO* yn = (TO*)p.y + (long long)n * p.Cout * So;
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      if (co < p.Cout) {
+#pragma unroll
+        for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+          for (int py = 0; py < 2; ++py) {
+            TO* yp = yn + (long long)co * So + ((long long)(2 * cz + pz) * Ho + (2 * cy + py)) * Wo + 2 * cx;
+            io<TO>::st2(yp, acc[pz * 4 + py * 2][co], acc[pz * 4 + py * 2 + 1][co]);
+          }
       }
     }
   }
-  const int Do = 2 * p.Di, Ho = 2 * p.Hi, Wo = 2 * p.Wi;
-  const long long So = (long long)Do * Ho * Wo;
-  const long long o = ((long long)(2 * cz + pz) * Ho + (2 * cy + py)) * Wo + (2 * cx + px);
-  for (int co = 0; co < p.Cout; ++co)
-    io<TO>::st((TO*)p.y + ((long long)n * p.Cout + co) * So + o, acc[co] + (p.bias ? p.bias[co] : 0.f));
 }
 
 }  // namespace b200
@@ -317,19 +352,19 @@ extern "C" int b200_convt3s2_head_nc8(const void* x, int N, int Cin, int Di, int
   B200_REQUIRE(N <= 65535, "convt3s2_head_nc8: batch too large");
   HeadP p{(const __half*)x, y, weight, bias, N, Cin, Cout, Di, Hi, Wi, in_ctot, in_coff, out_dtype};
   const long long Si = (long long)Di * Hi * Wi;
-  const size_t smem = (size_t)27 * Cin * 4 * sizeof(float);
+  const int CO = Cout <= 2 ? 2 : 4;
+  const size_t smem = (size_t)27 * Cin * CO * sizeof(float);
   B200_REQUIRE(smem <= 96 * 1024, "convt3s2_head_nc8: Cin too large (%d)", Cin);
-  dim3 grid(ceil_div(Si, 128), 8, N);
+  const long long cells = (long long)N * Si;
+  dim3 grid((unsigned)std::min<long long>(ceil_div(cells, 256), (long long)num_sms() * 8));
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == B200_DT_F16) {
-    static bool a1 = false;
-    if (!a1) { B200_CUDA(cudaFuncSetAttribute(convt3s2_head_nc8_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); a1 = true; }
-    convt3s2_head_nc8_kernel<__half><<<grid, 128, smem, st>>>(p);
-  } else if (out_dtype == B200_DT_F32) {
-    static bool a2 = false;
-    if (!a2) { B200_CUDA(cudaFuncSetAttribute(convt3s2_head_nc8_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); a2 = true; }
-    convt3s2_head_nc8_kernel<float><<<grid, 128, smem, st>>>(p);
-  } else return set_err(B200_ERR_INVALID, "convt3s2_head_nc8: bad dtype");
+#define LH(TO, CO_) do { \
+    B200_CUDA(cudaFuncSetAttribute(convt3s2_head_nc8_kernel<TO, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+    convt3s2_head_nc8_kernel<TO, CO_><<<grid, 256, smem, st>>>(p); } while (0)
+  if (out_dtype == B200_DT_F16) { if (CO == 2) LH(__half, 2); else LH(__half, 4); }
+  else if (out_dtype == B200_DT_F32) { if (CO == 2) LH(float, 2); else LH(float, 4); }
+  else return set_err(B200_ERR_INVALID, "convt3s2_head_nc8: bad dtype");
+#undef LH
   B200_LAUNCH_CHECK("convt3s2_head_nc8_kernel");
   return B200_OK;
 }

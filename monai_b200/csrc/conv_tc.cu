@@ -16,6 +16,12 @@
 // image and arrive by 1-D bulk copies.  fp32 accumulators live in TMEM (BD planes x NT columns); the epilogue
 // reads them back with tcgen05.ld, adds bias, reduces InstanceNorm partial sums and stores fp16 NC8.
 //
+// Depth-fused N: with the operands in shared memory an MMA of N = 48 is bound by the 4 KB A read, not by the tensor
+// pipe (24 cycles of math against ~44 cycles of operand traffic).  The loop therefore walks the INPUT planes of the
+// halo tile: input plane ip feeds output planes ip-kd (kd = 0..2), whose accumulators are adjacent TMEM column
+// blocks, so one MMA with the weights of kd = 2,1,0 stacked along N (N up to 3*NT <= 256) replaces three -- the A
+// tile is read once per (plane, kh, kw) instead of once per tap.
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
 #include "common.cuh"
 #include "tc05.cuh"
@@ -70,7 +76,8 @@ __global__ void __launch_bounds__(256) unpack_nc8_kernel(const __half* __restric
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// weight packing: Conv3d weight [Cout][Cin][27] fp32 -> [nt][kc][kd][tap9][khalf][NT/8][8 cout][8 k] fp16
+// weight packing: Conv3d weight [Cout][Cin][27] fp32 -> [nt][kc][kh][kw][khalf][kd = 2,1,0][NT/8][8 cout][8 k] fp16
+// (one K-major B image of 3*NT rows per (kh, kw): rows of kd = 2 first, so a kd range is a contiguous row range)
 // ----------------------------------------------------------------------------------------------------------
 __host__ __device__ inline int conv_tc_nt(int Cout) {
   if (Cout <= 128) return Cout;
@@ -86,9 +93,9 @@ __global__ void conv_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
     const int kk = (int)(r % 8); r /= 8;
     const int row = (int)(r % 8); r /= 8;
     const int g = (int)(r % (NT / 8)); r /= (NT / 8);
+    const int kd = 2 - (int)(r % 3); r /= 3;
     const int khalf = (int)(r % 2); r /= 2;
-    const int t9 = (int)(r % 9); r /= 9;
-    const int kd = (int)(r % 3); r /= 3;
+    const int t9 = (int)(r % 9); r /= 9;    // kh*3 + kw
     const int kc = (int)(r % (Cin / 16)); r /= (Cin / 16);
     const int nt = (int)r;
     const int cout = nt * NT + g * 8 + row;
@@ -110,8 +117,9 @@ struct ConvTcCfg {
   static constexpr int kPlanes = BD + 2;
   static constexpr int kChunkBytes = kPlanes * kHH * kHW * 16;   // one 8-channel chunk of the halo tile
   static constexpr int kABytes = 2 * kChunkBytes;                // 16 input channels
-  static constexpr int kBTapBytes = NT * 32;                     // one tap: NT x 16 fp16
-  static constexpr int kBBytes = 9 * kBTapBytes;                 // one kd slab
+  static constexpr int kBTapBytes = 3 * NT * 32;                 // one (kh, kw): the three kd taps stacked along N, 3*NT x 16 fp16
+  static constexpr int kBBytes = 3 * kBTapBytes;                 // one kh slab (kw = 0..2)
+  static constexpr int kKdGroup = (3 * NT <= 256) ? 3 : ((2 * NT <= 256) ? 2 : 1);   // kd taps fused into one MMA (UMMA N <= 256)
   static constexpr int kTmemCols = (BD * NT <= 32) ? 32 : (BD * NT <= 64) ? 64 : (BD * NT <= 128) ? 128 : (BD * NT <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + 256 /*barriers*/ + 2 * NT * 4 /*stats*/ + 128 /*align slack*/;
   static_assert(BD * NT <= 512, "accumulators exceed TMEM");
@@ -178,10 +186,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
         tc::tma_load_5d(smem_a + sa * Cfg::kABytes, &tmap, &full_a[sa], (w0 - 1) * 8, h0 - 1, d0 - 1,
                         (d.in_coff + kc * 16) / 8, n);
         if (++sa == kSA) { sa = 0; pa ^= 1; }
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kh = 0; kh < 3; ++kh) {
           tc::mbar_wait(&empty_b[sb], pb ^ 1);
           tc::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBBytes);
-          tc::bulk_load(smem_b + sb * Cfg::kBBytes, wbase + ((long long)kc * 3 + kd) * (Cfg::kBBytes / 2), Cfg::kBBytes,
+          tc::bulk_load(smem_b + sb * Cfg::kBBytes, wbase + ((long long)kc * 3 + kh) * (Cfg::kBBytes / 2), Cfg::kBBytes,
                         &full_b[sb]);
           if (++sb == kSB) { sb = 0; pb ^= 1; }
         }
@@ -191,24 +199,42 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_f16(128, NT);
+      constexpr int G = Cfg::kKdGroup;
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int kc = 0; kc < num_kc; ++kc) {
         tc::mbar_wait(&full_a[sa], pa);
         const uint32_t a_base = tc::smem_u32(smem_a + sa * Cfg::kABytes);
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kh = 0; kh < 3; ++kh) {
           tc::mbar_wait(&full_b[sb], pb);
           tc::fence_after_sync();
           const uint32_t b_base = tc::smem_u32(smem_b + sb * Cfg::kBBytes);
 #pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const int kh = t9 / 3, kw = t9 % 3;
-            const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_base + t9 * Cfg::kBTapBytes, NT * 16, 128);
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint32_t b_tap = b_base + kw * Cfg::kBTapBytes;
+            const bool first = (kc | kh | kw) == 0;   // the pass that initialises the accumulators: one MMA per (plane, kd)
 #pragma unroll
-            for (int sub = 0; sub < BD; ++sub) {
-              const uint32_t a_addr = a_base + (((sub + kd) * kHH + kh) * kHW + kw) * 16;
+            for (int ip = 0; ip < BD + 2; ++ip) {     // input plane of the halo tile; feeds output planes ip - kd
+              constexpr int kdmax = 2;
+              const int kd_hi = ip < kdmax ? ip : kdmax, kd_lo = ip - (BD - 1) > 0 ? ip - (BD - 1) : 0;
+              const uint32_t a_addr = a_base + ((ip * kHH + kh) * kHW + kw) * 16;
               const uint64_t adesc = tc::make_desc_kmajor_noswz(a_addr, Cfg::kChunkBytes, kHW * 16);
-              tc::mma_f16_ss(tmem_base + sub * NT, adesc, bdesc, idesc, (kc | kd | t9) != 0 ? 1u : 0u);
+              if (first) {
+#pragma unroll
+                for (int kd = 2; kd >= 0; --kd) {
+                  if (kd > kd_hi || kd < kd_lo) continue;
+                  const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - kd) * NT * 16, 3 * NT * 16, 128);
+                  // plane ip - kd was initialised when it was the kd = 0 plane of an earlier ip
+                  tc::mma_f16_ss(tmem_base + (ip - kd) * NT, adesc, bdesc, tc::make_idesc_f16(128, NT), kd != 0 ? 1u : 0u);
+                }
+              } else {
+#pragma unroll
+                for (int top = 2; top >= 0; top -= G) {   // kd groups [top-G+1, top] clipped to [kd_lo, kd_hi]
+                  const int hi = top < kd_hi ? top : kd_hi, lo = (top - G + 1) > kd_lo ? (top - G + 1) : kd_lo;
+                  if (hi < lo) continue;
+                  const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - hi) * NT * 16, 3 * NT * 16, 128);
+                  tc::mma_f16_ss(tmem_base + (ip - hi) * NT, adesc, bdesc, tc::make_idesc_f16(128, (hi - lo + 1) * NT), 1u);
+                }
+              }
             }
           }
           tc::mma_commit(&empty_b[sb]);
@@ -434,26 +460,10 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void*
   return B200_OK;
 }
 
-namespace b200 {
-template <int NT, int BD>
-int launch_conv_tc2(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats, cudaStream_t st);
-}
-
-// generation-2 kernel (A operand from TMEM, persistent, double-buffered accumulators) for the narrow-N layers;
-// B200_CONV_TC2=0 keeps the generation-1 kernel everywhere
-static bool use_tc2() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("B200_CONV_TC2"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 template <int NT>
 static int dispatch_bd(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats,
                        cudaStream_t st) {
   // deeper CTA tiles amortise the halo and the weight slab; TMEM (BD*NT <= 512) and the plane count bound BD
-  if constexpr (NT == 48 || NT == 32 || NT == 16) {
-    if (use_tc2() && (d.D % 4 == 0 || d.D >= 16)) return launch_conv_tc2<NT, 4>(d, x, w, bias, y, stats, st);
-  }
   if constexpr (NT * 4 <= 512) {
     if (d.D % 4 == 0 || d.D >= 16) return launch_conv_tc<NT, 4>(d, x, w, bias, y, stats, st);
   }

@@ -62,9 +62,21 @@ __global__ void gemm_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 
 // Persistent, warp-specialised: each CTA loops over (batch, row tile, N tile) work items.  Two TMEM accumulator
 // buffers let the epilogue of tile i overlap the MMAs of tile i+1; the shared-memory ring runs across tile boundaries.
-constexpr int kGemmEpiWarps = 16;   // 4 per TMEM lane quarter: the epilogue is latency-bound (GELU, residual loads), not bandwidth-bound
+// The epilogue variant (row mapping, activation, residual, statistics) is a template parameter: the per-step
+// instruction stream is what bounds these HBM-shaped GEMMs, so nothing is decided at run time inside the column loop.
+constexpr int kGemmEpiWarps = 16;   // 4 per TMEM lane quarter; warps sharing a quarter split the 16-column steps
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 
+// tcgen05.wait::ld that names the destination registers, so the compiler cannot schedule their uses above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
+template <int MODE, int ACT, bool RES, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -92,7 +104,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 32 * kGemmEpiWarps); }
     tc::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+  if (STATS)
+    for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 1) tc::tmem_alloc(tmem_slot, p.tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
@@ -154,7 +167,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
   } else {
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int cpart = (warp - 2) >> 2;      // warps sharing a quarter split the 16-column steps between them
-    const int cout = d.mode == 2 ? d.N / 8 : d.N;  // channels of the destination tensor written by this GEMM
+    const int cout = MODE == 2 ? d.N / 8 : d.N;  // channels of the destination tensor written by this GEMM
+    constexpr int kParts = kGemmEpiWarps / 4;
+    const int n16 = NT / 16, c_lo = (cpart * n16) / kParts, c_hi = ((cpart + 1) * n16) / kParts;
+    const long long cs = (long long)d.S_out * 8;   // halves between consecutive 8-channel chunks of the destination
+    const float* __restrict__ bias = p.bias;
+    const bool has_bias = bias != nullptr;
+    const int W2 = 2 * d.W, HW4 = 4 * d.H * d.W;
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = (int)(tile % n_tiles);
@@ -165,69 +184,72 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
       const int row = rt * 128 + q * 32 + lane;
       const bool row_ok = row < d.S;
       long long drow = row;
-      if (row_ok && p.row_map) drow = p.row_map[row];  // the map is shared by all batch items
+      if (MODE == 1) drow = row_ok ? (long long)__ldg(p.row_map + row) : -1;  // the map is shared by all batch items
       const bool dst_ok = row_ok && drow >= 0;
-      int vz = 0, vy = 0, vx = 0;
-      if (d.mode == 2 && row_ok) { vx = row % d.W; vy = (row / d.W) % d.H; vz = row / (d.W * d.H); }
       const int co0 = nt * NT;
-      __half* ybase = p.y + ((long long)n * (d.out_ctot / 8)) * d.S_out * 8;
-      const __half* rbase = p.res ? p.res + ((long long)n * (d.res_ctot / 8)) * d.S_out * 8 : nullptr;
+      // running (tap, channel) position of this warp's first column for the upsample scatter
+      int tap = 0, cc = co0 + c_lo * 16;
+      if (MODE == 2) {
+        const int vx = row % d.W, vy = (row / d.W) % d.H, vz = row / (d.W * d.H);
+        drow = ((long long)(2 * vz) * (2 * d.H) + 2 * vy) * W2 + 2 * vx;
+        tap = cc / cout;  // GEMM columns are ordered [tap][cout]
+        cc -= tap * cout;
+      }
+      __half* ytile = p.y + ((long long)n * (d.out_ctot / 8) + (MODE == 2 ? 0 : (d.out_coff + co0) / 8)) * cs + drow * 8;
+      const __half* rtile = RES ? p.res + ((long long)n * (d.res_ctot / 8) + (d.res_coff + co0) / 8) * cs + drow * 8 : nullptr;
+      uint32_t va[16], vb[16];
+      uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
+      // the residual of the first step does not depend on the accumulator: fetch it before waiting for the MMAs
+      if (RES && dst_ok && c_lo < c_hi) {
+        ra0 = *reinterpret_cast<const uint4*>(rtile + (long long)(2 * c_lo) * cs);
+        ra1 = *reinterpret_cast<const uint4*>(rtile + (long long)(2 * c_lo + 1) * cs);
+      }
       tc::mbar_wait(&acc_full[buf], aph);
       tc::fence_after_sync();
       const uint32_t tacc = tmem_base + buf * NT + ((uint32_t)(q * 32) << 16);
-      // 16 columns per step: one tcgen05.ld.x16 (prefetched one step ahead), vector bias loads, packed fp16 converts
-      constexpr int kParts = kGemmEpiWarps / 4;
-      const int n16 = NT / 16, c_lo = (cpart * n16) / kParts, c_hi = ((cpart + 1) * n16) / kParts;
-      uint32_t vn[16];
-      if (c_lo < c_hi) tc::tmem_ld16(tacc + c_lo * 16, vn);
-#pragma unroll 1
-      for (int c16 = c_lo; c16 < c_hi; ++c16) {
+
+      auto process = [&](uint32_t (&v)[16], const uint4& r0, const uint4& r1, int c16) {
         float f[16];
-        tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(vn[j]);
-        if (c16 + 1 < c_hi) tc::tmem_ld16(tacc + (c16 + 1) * 16, vn);
-        const int nc0 = co0 + c16 * 16;  // first GEMM column of this step
-        if (p.bias) {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int nb = d.mode == 2 ? (nc0 + hh * 8) % cout : nc0 + hh * 8;
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nb)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 4));
-            f[hh * 8 + 0] += b0.x; f[hh * 8 + 1] += b0.y; f[hh * 8 + 2] += b0.z; f[hh * 8 + 3] += b0.w;
-            f[hh * 8 + 4] += b1.x; f[hh * 8 + 5] += b1.y; f[hh * 8 + 6] += b1.z; f[hh * 8 + 7] += b1.w;
-          }
-        }
-        if (d.act == 4) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.f + fast_erf(f[j] * 0.70710678118654752f));
-        }
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int nc = nc0 + hh * 8;
-          long long orow = drow; int ochunk;
-          if (d.mode == 2) {
-            const int tap = nc / cout;  // GEMM columns are ordered [tap][cout]
-            ochunk = (d.out_coff + (nc % cout)) / 8;
-            orow = ((long long)(2 * vz + (tap >> 2)) * (2 * d.H) + (2 * vy + ((tap >> 1) & 1))) * (2 * d.W) + (2 * vx + (tap & 1));
-          } else {
-            ochunk = (d.out_coff + nc) / 8;
-          }
           float* g = f + hh * 8;
-          if (dst_ok) {
-            if (rbase) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rbase + (((long long)(d.res_coff + nc) / 8) * d.S_out + orow) * 8);
-              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+          const int g8 = c16 * 2 + hh;           // 8-column group inside this N tile
+          __half* yp;
+          int bidx;
+          if (MODE == 2) {
+            const int tapoff = (tap >> 2) * HW4 + ((tap >> 1) & 1) * W2 + (tap & 1);
+            yp = ytile + (long long)((d.out_coff + cc) >> 3) * cs + (long long)tapoff * 8;
+            bidx = cc;
+            cc += 8;
+            if (cc >= cout) { cc = 0; ++tap; }
+          } else {
+            yp = ytile + (long long)g8 * cs;
+            bidx = co0 + g8 * 8;
+          }
+          if (has_bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + bidx)), b1 = __ldg(reinterpret_cast<const float4*>(bias + bidx + 4));
+            g[0] += b0.x; g[1] += b0.y; g[2] += b0.z; g[3] += b0.w;
+            g[4] += b1.x; g[5] += b1.y; g[6] += b1.z; g[7] += b1.w;
+          }
+          if (ACT == 4) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 r2 = __half22float2(rh[j]); g[2 * j] += r2.x; g[2 * j + 1] += r2.y; }
-            }
+            for (int j = 0; j < 8; ++j) g[j] = 0.5f * g[j] * (1.f + fast_erf(g[j] * 0.70710678118654752f));
+          }
+          if (RES) {
+            const __half2* rh = reinterpret_cast<const __half2*>(hh ? &r1 : &r0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 r2 = __half22float2(rh[j]); g[2 * j] += r2.x; g[2 * j + 1] += r2.y; }
+          }
+          if (dst_ok) {
             uint4 hv;
             __half2* hp = reinterpret_cast<__half2*>(&hv);
 #pragma unroll
             for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(g[2 * j], g[2 * j + 1]);
-            *reinterpret_cast<uint4*>(ybase + ((long long)ochunk * d.S_out + orow) * 8) = hv;
+            *reinterpret_cast<uint4*>(yp) = hv;
           }
-          if (p.stats) {
-            const int cc = c16 * 2 + hh;
+          if (STATS) {
             float a1[8], b1[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { a1[j] = dst_ok ? g[j] : 0.f; b1[j] = a1[j] * a1[j]; }
@@ -235,15 +257,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
             for (int j = 0; j < 8; ++j) { a1[j] = warp_sum(a1[j]); b1[j] = warp_sum(b1[j]); }
             if (lane == 0) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { atomicAdd(&s_stats[2 * (cc * 8 + j)], a1[j]); atomicAdd(&s_stats[2 * (cc * 8 + j) + 1], b1[j]); }
+              for (int j = 0; j < 8; ++j) { atomicAdd(&s_stats[2 * (g8 * 8 + j)], a1[j]); atomicAdd(&s_stats[2 * (g8 * 8 + j) + 1], b1[j]); }
             }
           }
+        }
+      };
+
+      // 16 columns per step: tcgen05.ld.x16 and the residual are fetched one step ahead into the other register set
+      if (c_lo < c_hi) tc::tmem_ld16(tacc + c_lo * 16, va);
+#pragma unroll 1
+      for (int c16 = c_lo; c16 < c_hi; c16 += 2) {
+        tmem_ld_wait16(va);
+        const bool more = c16 + 1 < c_hi;
+        if (more) {
+          tc::tmem_ld16(tacc + (c16 + 1) * 16, vb);
+          if (RES && dst_ok) {
+            rb0 = *reinterpret_cast<const uint4*>(rtile + (long long)(2 * c16 + 2) * cs);
+            rb1 = *reinterpret_cast<const uint4*>(rtile + (long long)(2 * c16 + 3) * cs);
+          }
+        }
+        process(va, ra0, ra1, c16);
+        if (more) {
+          tmem_ld_wait16(vb);
+          if (c16 + 2 < c_hi) {
+            tc::tmem_ld16(tacc + (c16 + 2) * 16, va);
+            if (RES && dst_ok) {
+              ra0 = *reinterpret_cast<const uint4*>(rtile + (long long)(2 * c16 + 4) * cs);
+              ra1 = *reinterpret_cast<const uint4*>(rtile + (long long)(2 * c16 + 5) * cs);
+            }
+          }
+          process(vb, rb0, rb1, c16 + 1);
         }
       }
       // this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[buf]);
-      if (p.stats) {
+      if (STATS) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
         const int t = threadIdx.x - 64;
         for (int i = t; i < 2 * NT; i += 32 * kGemmEpiWarps) { atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
@@ -256,6 +305,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, p.tmem_cols);
   }
+}
+
+using GemmKernelFn = void (*)(GemmTcParams);
+
+template <int MODE, int ACT>
+static GemmKernelFn gemm_pick2(bool res, bool stats) {
+  if (res) return stats ? gemm_tc_kernel<MODE, ACT, true, true> : gemm_tc_kernel<MODE, ACT, true, false>;
+  return stats ? gemm_tc_kernel<MODE, ACT, false, true> : gemm_tc_kernel<MODE, ACT, false, false>;
+}
+
+static GemmKernelFn gemm_pick(int mode, int act, bool res, bool stats) {
+  if (mode == 0) return act == 4 ? gemm_pick2<0, 4>(res, stats) : gemm_pick2<0, 0>(res, stats);
+  if (mode == 1) return act == 4 ? gemm_pick2<1, 4>(res, stats) : gemm_pick2<1, 0>(res, stats);
+  if (res) return nullptr;  // the upsample scatter has no residual form
+  if (act == 4) return stats ? gemm_tc_kernel<2, 4, false, true> : gemm_tc_kernel<2, 4, false, false>;
+  return stats ? gemm_tc_kernel<2, 0, false, true> : gemm_tc_kernel<2, 0, false, false>;
 }
 
 }  // namespace b200
@@ -299,14 +364,12 @@ extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const 
   p.row_map = row_map; p.NT = NT;
   p.tmem_cols = 2 * NT <= 32 ? 32 : 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;  // two accumulator buffers
   const int smem = kGemmStages * (kGemmAStage + kGemmK16PerStage * NT * 32) + 128 + 2 * NT * 4 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  GemmKernelFn fn = gemm_pick(d.mode, d.act, res != nullptr, stats != nullptr);
+  B200_REQUIRE(fn != nullptr, "gemm_tc: the 2x upsample scatter (mode 2) does not take a residual");
+  B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const long long total_tiles = (long long)ceil_div(d.S, 128) * (d.N / NT) * d.Nb;
   dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
-  gemm_tc_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
+  fn<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   return B200_OK;
 }

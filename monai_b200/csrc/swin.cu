@@ -145,17 +145,89 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// One 32-key step of the online softmax for 16 query rows per warp.  All scores are kept in log2 units (the bias table
+// is pre-multiplied by log2(e) when it is staged, scale2 = scale*log2(e)) so every exponential is a bare ex2.approx.
+// MASK: shifted windows (region ids differ -> -100 as in compute_mask, swin_unetr.py:457-487).  TAIL: keys >= n exist.
+struct AttRow {
+  int lin0, lin1, reg0, reg1;
+  float m0, m1, l0, l1;
+  float o[2][4];
+};
+
+template <bool MASK, bool TAIL>
+__device__ __forceinline__ void att_step32(const uint32_t (&qa)[4], AttRow& r, int j0, int n, float scale2, const __half* __restrict__ sK,
+                                           const __half* __restrict__ sVt, int vstride, const float* __restrict__ sTab,
+                                           const unsigned short* __restrict__ sLin, const unsigned char* __restrict__ sReg, int g, int t4) {
+  constexpr float kMaskAdd = -100.0f * 1.4426950408889634f;
+  float sc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+    const __half* kp = sK + (j0 + nt * 8 + g) * kAttKStride + 2 * t4;
+    mma_16816(sc[nt], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int j = j0 + nt * 8 + 2 * t4;                       // this thread's two keys j, j+1 of the tile
+    const uint32_t lj2 = *reinterpret_cast<const uint32_t*>(sLin + j);
+    const int lja = (int)(lj2 & 0xffffu), ljb = (int)(lj2 >> 16);
+    float v00 = fmaf(sc[nt][0], scale2, sTab[r.lin0 - lja]), v01 = fmaf(sc[nt][1], scale2, sTab[r.lin0 - ljb]);
+    float v10 = fmaf(sc[nt][2], scale2, sTab[r.lin1 - lja]), v11 = fmaf(sc[nt][3], scale2, sTab[r.lin1 - ljb]);
+    if (MASK) {
+      const unsigned short rj2 = *reinterpret_cast<const unsigned short*>(sReg + j);
+      const int rja = rj2 & 0xff, rjb = rj2 >> 8;
+      if (rja != r.reg0) v00 += kMaskAdd;
+      if (rjb != r.reg0) v01 += kMaskAdd;
+      if (rja != r.reg1) v10 += kMaskAdd;
+      if (rjb != r.reg1) v11 += kMaskAdd;
+    }
+    if (TAIL) {
+      if (j >= n) { v00 = -INFINITY; v10 = -INFINITY; }
+      if (j + 1 >= n) { v01 = -INFINITY; v11 = -INFINITY; }
+    }
+    sc[nt][0] = v00; sc[nt][1] = v01; sc[nt][2] = v10; sc[nt][3] = v11;
+    mx0 = fmaxf(mx0, fmaxf(v00, v01)); mx1 = fmaxf(mx1, fmaxf(v10, v11));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float mn0 = fmaxf(r.m0, mx0), mn1 = fmaxf(r.m1, mx1);
+  const float c0 = exp2f(r.m0 - mn0), c1 = exp2f(r.m1 - mn1);
+  r.m0 = mn0; r.m1 = mn1;
+  float ps0 = 0.f, ps1 = 0.f;
+  uint32_t pa[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float p00 = exp2f(sc[nt][0] - mn0), p01 = exp2f(sc[nt][1] - mn0);
+    const float p10 = exp2f(sc[nt][2] - mn1), p11 = exp2f(sc[nt][3] - mn1);
+    ps0 += p00 + p01; ps1 += p10 + p11;
+    pa[nt >> 1][(nt & 1) * 2] = pack_h2(p00, p01);       // a0 / a2: row r0
+    pa[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p10, p11);   // a1 / a3: row r1
+  }
+  r.l0 = fmaf(r.l0, c0, ps0); r.l1 = fmaf(r.l1, c1, ps1);
+#pragma unroll
+  for (int dt = 0; dt < 2; ++dt) {
+    r.o[dt][0] *= c0; r.o[dt][1] *= c0; r.o[dt][2] *= c1; r.o[dt][3] *= c1;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const __half* vp = sVt + (dt * 8 + g) * vstride + j0 + ks * 16 + 2 * t4;
+      mma_16816(r.o[dt], pa[ks], *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
+    }
+  }
+}
+
+template <bool MASK>
 __global__ void __launch_bounds__(256) window_attention_nc8_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int C,
                                                                    int heads, int nW, int n, float scale,
                                                                    const float* __restrict__ table, int tab_len, int ws0, int ws1,
                                                                    int ws2, const int* __restrict__ region) {
   extern __shared__ __align__(16) uint8_t s_att[];
-  const int npad = (n + 15) / 16 * 16;
+  const int npad = (n + 31) / 32 * 32;
   const int vstride = npad + 8;                       // halfs per V^T row (conflict-free b-fragment loads)
   __half* sK = reinterpret_cast<__half*>(s_att);      // [npad][kAttKStride]
   __half* sVt = sK + (size_t)npad * kAttKStride;      // [16][vstride]
-  float* sTab = reinterpret_cast<float*>(sVt + 16 * vstride);  // [tab_len]
-  short* sLin = reinterpret_cast<short*>(sTab + tab_len);      // [npad]
+  float* sTab = reinterpret_cast<float*>(sVt + 16 * vstride);  // [tab_len], times log2(e)
+  unsigned short* sLin = reinterpret_cast<unsigned short*>(sTab + tab_len);      // [npad]
   unsigned char* sReg = reinterpret_cast<unsigned char*>(sLin + npad);  // [npad]
   const int w = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int C8 = C / 8;
@@ -163,6 +235,7 @@ __global__ void __launch_bounds__(256) window_attention_nc8_kernel(const __half*
   const __half* base = qkv + (long long)b * (3 * C8) * T * 8;
   const long long row0 = (long long)w * n;
   const int s1 = 2 * ws2 - 1, s0 = (2 * ws1 - 1) * s1;
+  constexpr float kLog2e = 1.4426950408889634f;
 
   for (int i = threadIdx.x; i < npad * 2; i += blockDim.x) {
     const int t = i >> 1, hf = i & 1;
@@ -176,17 +249,20 @@ __global__ void __launch_bounds__(256) window_attention_nc8_kernel(const __half*
 #pragma unroll
     for (int j = 0; j < 8; ++j) sVt[(hf * 8 + j) * vstride + t] = vh[j];
   }
-  for (int i = threadIdx.x; i < tab_len; i += blockDim.x) sTab[i] = table[(long long)i * heads + h];
+  for (int i = threadIdx.x; i < tab_len; i += blockDim.x) sTab[i] = table[(long long)i * heads + h] * kLog2e;
   for (int i = threadIdx.x; i < npad; i += blockDim.x) {
     const int td = i / (ws1 * ws2), th = (i / ws2) % ws1, tw = i % ws2;
-    sLin[i] = (short)(td * s0 + th * s1 + tw);
-    sReg[i] = (region && i < n) ? (unsigned char)region[(long long)w * n + i] : 0;
+    // padded keys (i >= n) are masked by the TAIL step; their index only has to stay inside the table
+    sLin[i] = (unsigned short)(i < n ? td * s0 + th * s1 + tw : 0);
+    sReg[i] = (MASK && i < n) ? (unsigned char)region[(long long)w * n + i] : 0;
   }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const int nwarps = blockDim.x >> 5;
   const int lin_c = (ws0 - 1) * s0 + (ws1 - 1) * s1 + (ws2 - 1);
+  const float scale2 = scale * kLog2e;
+  const int n_full = n / 32 * 32;
   __half* ob = out + (long long)b * C8 * T * 8;
   for (int rt = warp; rt * 16 < n; rt += nwarps) {
     const int r0 = rt * 16 + g, r1 = r0 + 8;
@@ -200,68 +276,22 @@ __global__ void __launch_bounds__(256) window_attention_nc8_kernel(const __half*
       qa[1] = *reinterpret_cast<const uint32_t*>(base + ((long long)(2 * h) * T + row0 + r1) * 8 + 2 * t4);
       qa[3] = *reinterpret_cast<const uint32_t*>(base + ((long long)(2 * h + 1) * T + row0 + r1) * 8 + 2 * t4);
     }
-    const int lin0 = sLin[min(r0, npad - 1)] + lin_c, lin1 = sLin[min(r1, npad - 1)] + lin_c;
-    const int reg0 = sReg[min(r0, npad - 1)], reg1 = sReg[min(r1, npad - 1)];
-    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // O tile: d 0-7 and d 8-15
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int j0 = 0; j0 < npad; j0 += 16) {
-      float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // keys j0..j0+7 and j0+8..j0+15
+    AttRow r;
+    r.lin0 = sLin[min(r0, npad - 1)] + lin_c; r.lin1 = sLin[min(r1, npad - 1)] + lin_c;
+    r.reg0 = sReg[min(r0, npad - 1)]; r.reg1 = sReg[min(r1, npad - 1)];
+    r.m0 = r.m1 = -INFINITY; r.l0 = r.l1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const __half* kp = sK + (j0 + nt * 8 + g) * kAttKStride + 2 * t4;
-        mma_16816(sc[nt], qa, *reinterpret_cast<const uint32_t*>(kp), *reinterpret_cast<const uint32_t*>(kp + 8));
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = j0 + nt * 8 + 2 * t4 + e;
-          float v0 = -INFINITY, v1 = -INFINITY;
-          if (j < n) {
-            const int lj = sLin[j];
-            v0 = fmaf(sc[nt][e], scale, sTab[lin0 - lj]);
-            v1 = fmaf(sc[nt][2 + e], scale, sTab[lin1 - lj]);
-            if (region) {
-              const int rj = sReg[j];
-              if (rj != reg0) v0 += -100.0f;
-              if (rj != reg1) v1 += -100.0f;
-            }
-          }
-          sc[nt][e] = v0; sc[nt][2 + e] = v1;
-          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
-        }
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-      const float c0 = __expf(m0 - mn0), c1 = __expf(m1 - mn1);
-      m0 = mn0; m1 = mn1;
-      float ps0 = 0.f, ps1 = 0.f;
-      uint32_t pa[4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const float p00 = __expf(sc[nt][0] - mn0), p01 = __expf(sc[nt][1] - mn0);
-        const float p10 = __expf(sc[nt][2] - mn1), p11 = __expf(sc[nt][3] - mn1);
-        ps0 += p00 + p01; ps1 += p10 + p11;
-        pa[nt * 2] = pack_h2(p00, p01);       // a0 / a2: row r0
-        pa[nt * 2 + 1] = pack_h2(p10, p11);   // a1 / a3: row r1
-      }
-      l0 = l0 * c0 + ps0; l1 = l1 * c1 + ps1;
-#pragma unroll
-      for (int dt = 0; dt < 2; ++dt) {
-        o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1;
-        const __half* vp = sVt + (dt * 8 + g) * vstride + j0 + 2 * t4;
-        mma_16816(o[dt], pa, *reinterpret_cast<const uint32_t*>(vp), *reinterpret_cast<const uint32_t*>(vp + 8));
-      }
-    }
+    for (int dt = 0; dt < 2; ++dt) r.o[dt][0] = r.o[dt][1] = r.o[dt][2] = r.o[dt][3] = 0.f;
+    for (int j0 = 0; j0 < n_full; j0 += 32) att_step32<MASK, false>(qa, r, j0, n, scale2, sK, sVt, vstride, sTab, sLin, sReg, g, t4);
+    if (n_full < n) att_step32<MASK, true>(qa, r, n_full, n, scale2, sK, sVt, vstride, sTab, sLin, sReg, g, t4);
+    float l0 = r.l0, l1 = r.l1;
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
     for (int dt = 0; dt < 2; ++dt) {
-      if (r0 < n) *reinterpret_cast<uint32_t*>(ob + ((long long)(2 * h + dt) * T + row0 + r0) * 8 + 2 * t4) = pack_h2(o[dt][0] * i0, o[dt][1] * i0);
-      if (r1 < n) *reinterpret_cast<uint32_t*>(ob + ((long long)(2 * h + dt) * T + row0 + r1) * 8 + 2 * t4) = pack_h2(o[dt][2] * i1, o[dt][3] * i1);
+      if (r0 < n) *reinterpret_cast<uint32_t*>(ob + ((long long)(2 * h + dt) * T + row0 + r0) * 8 + 2 * t4) = pack_h2(r.o[dt][0] * i0, r.o[dt][1] * i0);
+      if (r1 < n) *reinterpret_cast<uint32_t*>(ob + ((long long)(2 * h + dt) * T + row0 + r1) * 8 + 2 * t4) = pack_h2(r.o[dt][2] * i1, r.o[dt][3] * i1);
     }
   }
 }
@@ -418,20 +448,16 @@ extern "C" int b200_window_attention_nc8(const void* qkv, int N, int C, int head
   B200_REQUIRE(C == heads * 16, "window_attention_nc8: head_dim must be 16 (C = %d, heads = %d)", C, heads);
   B200_REQUIRE(ws0 > 0 && ws1 > 0 && ws2 > 0 && n <= ws0 * ws1 * ws2, "window_attention_nc8: window of %d tokens exceeds the module window", n);
   B200_REQUIRE(heads <= 65535 && N <= 65535, "window_attention_nc8: grid too large");
-  const int npad = (n + 15) / 16 * 16;
+  const int npad = (n + 31) / 32 * 32;
   const int tab_len = (2 * ws0 - 1) * (2 * ws1 - 1) * (2 * ws2 - 1);
   B200_REQUIRE(tab_len < 32768, "window_attention_nc8: relative position table too large");
   const size_t smem = (size_t)npad * kAttKStride * 2 + (size_t)16 * (npad + 8) * 2 + (size_t)tab_len * 4 + (size_t)npad * 2 + npad + 16;
   B200_REQUIRE(smem <= 200 * 1024, "window_attention_nc8: window of %d tokens does not fit in shared memory", n);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(window_attention_nc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  auto kern = region ? window_attention_nc8_kernel<true> : window_attention_nc8_kernel<false>;
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   dim3 grid(nW, heads, N);
   const int threads = n >= 128 ? 256 : (n >= 64 ? 128 : 64);
-  window_attention_nc8_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)out, C, heads, nW, n, scale, table,
-                                                                          tab_len, ws0, ws1, ws2, region);
+  kern<<<grid, threads, smem, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)out, C, heads, nW, n, scale, table, tab_len, ws0, ws1, ws2, region);
   B200_LAUNCH_CHECK("window_attention_nc8_kernel");
   return B200_OK;
 }

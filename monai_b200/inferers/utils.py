@@ -12,6 +12,7 @@ There is no CPU or eager-PyTorch fallback: CUDA inputs are required and the C-AB
 from __future__ import annotations
 
 import itertools
+import math
 from collections.abc import Callable, Mapping, Sequence
 from typing import Any
 
@@ -116,7 +117,7 @@ class _OutputPlan:
         # window starts in output space: int(start * z) exactly as _compute_coords (utils.py:351-360)
         out_starts = [[int(s * zz) for s in ax] for ax, zz in zip(starts, z)]
         self.starts = [torch.tensor(ax, dtype=torch.int32, device=device) for ax in out_starts]
-        self.starts[2]._all_even = all(v % 2 == 0 for v in out_starts[2])  # enables the 2-voxels-per-thread blend path
+        self.starts[2]._align = math.gcd(8, *out_starts[2])  # 2 / 8 enable the vectorised blend paths
         self.batch_size = batch_size
         self.total = total
         per_win = self.chns * int(np.prod(seg_shape))

@@ -11,6 +11,8 @@ rows with the analytic count map (no count-map exchange) and the slabs are all-g
 """
 from __future__ import annotations
 
+import math
+
 from collections.abc import Callable, Sequence
 from dataclasses import dataclass
 from typing import Any
@@ -106,7 +108,7 @@ class ShardedSlidingWindowInferer:
     def __call__(self, inputs: torch.Tensor, network: Callable[..., torch.Tensor], *args: Any, **kwargs: Any) -> torch.Tensor:
         from .. import _kernels as K
         from ..data.utils import dense_patch_starts, importance_factors
-        from ..inferers.utils import _ensure_tuple_rep, _fall_back_tuple, _get_scan_interval
+        from ..inferers.utils import _RESIDENT_BYTES, _ensure_tuple_rep, _fall_back_tuple, _get_scan_interval
 
         if inputs.dim() != 5 or not inputs.is_cuda:
             raise RuntimeError("ShardedSlidingWindowInferer takes CUDA tensors [B, C, D, H, W]")
@@ -128,15 +130,26 @@ class ShardedSlidingWindowInferer:
         factors, clamp = importance_factors(roi, mode_s, self.sigma_scale)
         factors = [f.to(dev) for f in factors]
         starts_t = [torch.tensor(s, dtype=torch.int32, device=dev) for s in starts]
-        starts_t[2]._all_even = all(v % 2 == 0 for v in starts[2])
+        starts_t[2]._align = math.gcd(8, *[int(v) for v in starts[2]])
         x = inputs.detach()
         x = x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x
         acc = None
         out_c = None
+        store = None      # this rank's predictions stay resident (fp16/fp32 as produced) and are blended in one pass
+        per_layer = nh * nw
         for b in range(B):
-            ids = [b * num_win + i for i in range(wa, wb)]
-            tab = torch.tensor([(b, starts[0][(i % num_win) // (nh * nw)], starts[1][((i % num_win) // nw) % nh], starts[2][(i % num_win) % nw]) for i in ids],
+            ids = list(range(b * num_win + wa, b * num_win + wb))
+            tab = torch.tensor([(b, starts[0][(i % num_win) // per_layer], starts[1][((i % num_win) // nw) % nh], starts[2][(i % num_win) % nw]) for i in ids],
                                dtype=torch.int32, device=dev).reshape(-1, 4)
+            held, held_first = 0, ids[0] if ids else 0
+
+            def flush():
+                # numerators of the held windows are added to the fp32 accumulators over the depth rows they touch
+                # (row range from the host-side start table: no device synchronisation on the way)
+                lo_l, hi_l = (held_first - b * num_win) // per_layer, (held_first + held - 1 - b * num_win) // per_layer
+                K.sw_blend(1, store[:held], held_first, held_first + held, (B, out_c, D, H, W), roi, starts_t, factors, clamp, None, acc,
+                           box=(int(starts[0][lo_l]), int(starts[0][hi_l]) + roi[0], 0, 0))
+
             for g in range(0, len(ids), self.sw_batch_size):
                 win = K.sw_gather(x, tab[g : g + self.sw_batch_size], roi)
                 seg = network(win, *args, **kwargs)
@@ -146,11 +159,17 @@ class ShardedSlidingWindowInferer:
                 if acc is None:
                     out_c = seg.shape[1]
                     acc = torch.zeros((B, out_c, D, H, W), device=dev, dtype=torch.float32)
-                first = ids[g]
+                    per_win = out_c * int(np.prod(roi)) * seg.element_size()
+                    cap = max(self.sw_batch_size, min(len(ids), _RESIDENT_BYTES // max(1, per_win)))
+                    store = torch.empty((cap, out_c, *roi), device=dev, dtype=seg.dtype)
                 n = seg.shape[0]
-                d_lo = int(tab[g, 1])
-                d_hi = int(tab[min(g + n, len(ids)) - 1, 1]) + roi[0]
-                K.sw_blend(1, seg, first, first + n, (B, out_c, D, H, W), roi, starts_t, factors, clamp, None, acc, box=(d_lo, d_hi, 0, 0))
+                if held + n > store.shape[0]:
+                    flush()
+                    held_first, held = ids[g], 0
+                store[held : held + n].copy_(seg)
+                held += n
+            if held:
+                flush()
         if acc is None:  # a rank without windows still takes part in the exchange
             cshape = torch.zeros(1, dtype=torch.int64, device=dev)
             if world > 1:

@@ -21,7 +21,7 @@ def main():
         n = len(starts[0]) * len(starts[1]) * len(starts[2])
         preds = torch.randn((n, C, *roi), device=dev, dtype=torch.float16)
         st = [torch.tensor(s, dtype=torch.int32, device=dev) for s in starts]
-        st[2]._all_even = True
+        st[2]._align = 8
         f, clamp = importance_factors(roi, "gaussian", 0.125)
         f = [t.to(dev) for t in f]
         out = torch.empty((1, C, *vol), device=dev, dtype=torch.float16)

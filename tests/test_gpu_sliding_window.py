@@ -118,6 +118,34 @@ def test_streaming_path_equals_one_shot(monkeypatch):
     torch.testing.assert_close(a, b, rtol=0, atol=0)  # same fp32 op order -> identical
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_eight_voxel_blend_path_is_bit_identical_to_the_scalar_path(monkeypatch, dtype):
+    """W, roi and all W starts are multiples of 8 -> the 8-voxels-per-thread kernel runs; forcing the alignment hint
+    to 1 sends the same data through the scalar kernel.  Same op order, so one-shot and streaming results are identical."""
+    import monai_b200.inferers.utils as U
+
+    x = torch.randn(2, 1, 40, 48, 64, device=DEV).to(dtype)
+    roi = (16, 24, 32)
+    a = sliding_window_inference(x, roi, 4, _cheap_predictor, 0.5, "gaussian")
+    with monkeypatch.context() as m:
+        m.setattr(U, "_RESIDENT_BYTES", 7 * 2 * 16 * 24 * 32 * x.element_size())
+        a_stream = sliding_window_inference(x, roi, 4, _cheap_predictor, 0.5, "gaussian")
+    orig = U.K.sw_blend
+
+    def scalar(mode, preds, wb, we, vol_shape, roi_, starts, *rest, **kw):
+        assert starts[2]._align == 8
+        starts[2]._align = 1
+        return orig(mode, preds, wb, we, vol_shape, roi_, starts, *rest, **kw)
+
+    monkeypatch.setattr(U.K, "sw_blend", scalar)
+    b = sliding_window_inference(x, roi, 4, _cheap_predictor, 0.5, "gaussian")
+    torch.testing.assert_close(a, b, rtol=0, atol=0)
+    torch.testing.assert_close(a_stream, b, rtol=0, atol=0)
+    want = osw.sliding_window_inference(x.float().cpu().numpy(), roi, 4, lambda v: _cheap_predictor(torch.from_numpy(v)).numpy(), 0.5, "gaussian")
+    tol = 1e-5 if dtype == torch.float32 else 4e-3
+    np.testing.assert_allclose(a.float().cpu().numpy(), want, rtol=tol, atol=tol)
+
+
 def test_args_kwargs_process_fn_with_coord_and_device():
     x = torch.rand((1, 1, 12, 12, 12), device=DEV)
     t1, t2 = torch.ones(1, device=DEV), torch.ones(1, device=DEV)
