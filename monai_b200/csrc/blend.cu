@@ -27,6 +27,7 @@ struct BlendParams {
   void* out;                  // MODE 0: final [B,C,D,H,W] (out dtype); MODE 1: fp32 accumulators (+=)
   const float* acc;           // MODE 2: fp32 accumulators to normalise
   int d0, d1, h0, h1;         // box of output rows to visit (d in [d0,d1), h in [h0,h1))
+  int offsets_fit_i32;        // one (d) layer of windows spans < 2^31 prediction elements (8-voxel pipelined path)
 };
 
 constexpr int kMaxStarts = 512;
@@ -206,6 +207,7 @@ template <> __device__ __forceinline__ void st8o<__half>(__half* p, const float 
 }
 
 constexpr int kBlend8Rows = 8;   // warps (= h rows) per block
+constexpr int kBlend8MaxRoiW = 512;
 constexpr int kBlend8K = 3;      // W windows per (d, h) window pair handled by the pipelined path (overlap <= 2/3)
 
 template <typename TP, typename TO, int MODE>
@@ -216,6 +218,10 @@ __global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_
   const int h = p.h0 + blockIdx.y * kBlend8Rows + wrp;
   const int nd_box = p.d1 - p.d0;
   const int d = blockIdx.z % nd_box + p.d0, b = blockIdx.z / nd_box;
+  __shared__ __align__(16) float s_gw[kBlend8MaxRoiW];   // W-axis importance factors (pipelined path)
+  if (p.gw && p.rw <= kBlend8MaxRoiW)
+    for (int i = threadIdx.x; i < p.rw; i += blockDim.x) s_gw[i] = __ldg(p.gw + i);
+  __syncthreads();
   if (h >= p.h1 || w8 >= p.W) return;
   // the window starts are sorted, so the windows covering a coordinate form a contiguous index range per axis
   int id_lo = 0, ndc = 0, ih_lo = 0, nhc = 0, iw_lo = 0, nwc = 0;
@@ -227,15 +233,24 @@ __global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_
   const long long voff = ((long long)d * p.H + h) * p.W + w8;
   const TP* __restrict__ preds = (const TP*)p.preds;
   const bool dense = p.wmap != nullptr;
-  const bool piped = !dense && nwc <= kBlend8K;
-  // pipelined path: the W-factor vectors of this thread's (at most 3) W windows never change -> registers
+  // Pipelined path (the common geometry: at most 3 covering windows per axis, i.e. overlap <= 2/3): every per-axis
+  // quantity (local coordinate, 1-D weight, address offset) lives in registers, a prediction address is
+  // base + offA[a] + offE[e] + offK[k], and nothing but the predictions themselves is loaded inside the window loop.
+  const bool piped = !dense && ndc <= kBlend8K && nhc <= kBlend8K && nwc <= kBlend8K && p.offsets_fit_i32 && p.rw <= kBlend8MaxRoiW;
+  long long offA[kBlend8K];
+  int offE[kBlend8K], offK[kBlend8K];
+  float gda[kBlend8K], ghe[kBlend8K];
   int lwk[kBlend8K];
-  float gwk[kBlend8K][8];
   if (piped) {
 #pragma unroll
     for (int k = 0; k < kBlend8K; ++k) {
-      lwk[k] = k < nwc ? w8 - __ldg(p.starts_w + iw_lo + k) : 0;
-      ld8f(p.gw + lwk[k], gwk[k]);
+      const int ia = id_lo + (k < ndc ? k : 0), ie = ih_lo + (k < nhc ? k : 0), ik = iw_lo + (k < nwc ? k : 0);
+      const int ld = d - __ldg(p.starts_d + ia), lh = h - __ldg(p.starts_h + ie), lw = w8 - __ldg(p.starts_w + ik);
+      gda[k] = __ldg(p.gd + ld); ghe[k] = __ldg(p.gh + lh);
+      lwk[k] = lw;
+      offA[k] = (long long)ld * p.ps_d + (long long)ia * p.nh * p.nw * p.ps_n;
+      offE[k] = (int)(lh * p.ps_h + (long long)ie * p.nw * p.ps_n);
+      offK[k] = (int)(lw + (long long)ik * p.ps_n);
     }
   }
   float cnt[8];
@@ -250,38 +265,39 @@ __global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_
     }
     if (piped) {
       // The (d, h) window pairs are walked in ascending window order; the prediction vectors of pair q+1 are requested
-      // before pair q is accumulated, so up to 12 16-byte loads per thread are in flight (the kernel is latency-bound
-      // otherwise: every prediction is read exactly once and nothing is reused).
+      // before pair q is accumulated, so up to 12 16-byte loads per thread are in flight (every prediction is read
+      // exactly once and nothing is reused, so memory-level parallelism is what the kernel lives on).
       const int P = ndc * nhc;
-      auto issue = [&](int a, int e, Raw (&r0)[kBlend8K], Raw (&r1)[kBlend8K]) {
-        if (MODE == 2) return;
-        const int id = id_lo + a, ih = ih_lo + e;
-        const int ld = d - __ldg(p.starts_d + id), lh = h - __ldg(p.starts_h + ih);
-        const long long rowoff = (long long)ld * p.ps_d + (long long)lh * p.ps_h + (long long)c0 * p.ps_c;
-        const int wbase = b * num_win + (id * p.nh + ih) * p.nw + iw_lo;
+      const TP* pbase = preds + ((long long)b * num_win - p.win_begin) * p.ps_n + (long long)c0 * p.ps_c;
+      const unsigned nres = (unsigned)(p.win_end - p.win_begin);
+      const int wrel0 = b * num_win - p.win_begin + iw_lo;
+      struct Pair { float gdh; int wrel; };
+      auto issue = [&](int a, int e, Raw (&r0)[kBlend8K], Raw (&r1)[kBlend8K]) -> Pair {
+        Pair pr;
+        pr.gdh = __fmul_rn(a == 0 ? gda[0] : (a == 1 ? gda[1] : gda[2]), e == 0 ? ghe[0] : (e == 1 ? ghe[1] : ghe[2]));
+        pr.wrel = wrel0 + ((id_lo + a) * p.nh + ih_lo + e) * p.nw;
+        if (MODE != 2) {
+          const TP* pp = pbase + (a == 0 ? offA[0] : (a == 1 ? offA[1] : offA[2])) + (e == 0 ? offE[0] : (e == 1 ? offE[1] : offE[2]));
 #pragma unroll
-        for (int k = 0; k < kBlend8K; ++k) {
-          const int widx = wbase + k;
-          if (k < nwc && widx >= p.win_begin && widx < p.win_end) {
-            const TP* pp = preds + (long long)(widx - p.win_begin) * p.ps_n + rowoff + lwk[k];
-            r0[k] = Pred8<TP>::ld(pp);
-            if (two) r1[k] = Pred8<TP>::ld(pp + p.ps_c);
+          for (int k = 0; k < kBlend8K; ++k) {
+            if (k < nwc && (unsigned)(pr.wrel + k) < nres) {
+              r0[k] = Pred8<TP>::ld(pp + offK[k]);
+              if (two) r1[k] = Pred8<TP>::ld(pp + offK[k] + p.ps_c);
+            }
           }
         }
+        return pr;
       };
-      auto consume = [&](int a, int e, const Raw (&r0)[kBlend8K], const Raw (&r1)[kBlend8K]) {
-        const int id = id_lo + a, ih = ih_lo + e;
-        const int ld = d - __ldg(p.starts_d + id), lh = h - __ldg(p.starts_h + ih);
-        const float gdh = __fmul_rn(__ldg(p.gd + ld), __ldg(p.gh + lh));
-        const int wbase = b * num_win + (id * p.nh + ih) * p.nw + iw_lo;
+      auto consume = [&](const Pair& pr, const Raw (&r0)[kBlend8K], const Raw (&r1)[kBlend8K]) {
 #pragma unroll
         for (int k = 0; k < kBlend8K; ++k) {
           if (k < nwc) {
             float t[8];
+            const float4 g0 = *reinterpret_cast<const float4*>(s_gw + lwk[k]), g1 = *reinterpret_cast<const float4*>(s_gw + lwk[k] + 4);
+            t[0] = g0.x; t[1] = g0.y; t[2] = g0.z; t[3] = g0.w; t[4] = g1.x; t[5] = g1.y; t[6] = g1.z; t[7] = g1.w;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) { t[v] = fmaxf(__fmul_rn(gdh, gwk[k][v]), p.clamp_min); cnt[v] = __fadd_rn(cnt[v], t[v]); }
-            const int widx = wbase + k;
-            if (MODE != 2 && widx >= p.win_begin && widx < p.win_end) {
+            for (int v = 0; v < 8; ++v) { t[v] = fmaxf(__fmul_rn(pr.gdh, t[v]), p.clamp_min); cnt[v] = __fadd_rn(cnt[v], t[v]); }
+            if (MODE != 2 && (unsigned)(pr.wrel + k) < nres) {
               float xv[8];
               Pred8<TP>::cvt(r0[k], xv);
 #pragma unroll
@@ -296,15 +312,16 @@ __global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_
         }
       };
       Raw A0[kBlend8K], A1[kBlend8K], B0[kBlend8K], B1[kBlend8K];
-      int ai = 0, ei = 0, ac = 0, ec = 0;   // (d, h) pair positions of the load stream and of the accumulate stream
+      Pair pa, pb;
+      int ai = 0, ei = 0;   // (d, h) pair position of the load stream
       auto adv = [&](int& a, int& e) { if (++e == nhc) { e = 0; ++a; } };
-      if (P > 0) { issue(ai, ei, A0, A1); adv(ai, ei); }
+      if (P > 0) { pa = issue(ai, ei, A0, A1); adv(ai, ei); }
       for (int q = 0; q < P; q += 2) {
-        if (q + 1 < P) { issue(ai, ei, B0, B1); adv(ai, ei); }
-        consume(ac, ec, A0, A1); adv(ac, ec);
+        if (q + 1 < P) { pb = issue(ai, ei, B0, B1); adv(ai, ei); }
+        consume(pa, A0, A1);
         if (q + 1 < P) {
-          if (q + 2 < P) { issue(ai, ei, A0, A1); adv(ai, ei); }
-          consume(ac, ec, B0, B1); adv(ac, ec);
+          if (q + 2 < P) { pa = issue(ai, ei, A0, A1); adv(ai, ei); }
+          consume(pb, B0, B1);
         }
       }
     } else {
@@ -466,6 +483,7 @@ extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream)
   p.gd = dsc->gd; p.gh = dsc->gh; p.gw = dsc->gw; p.clamp_min = dsc->clamp_min; p.wmap = dsc->wmap;
   p.out = dsc->out; p.acc = dsc->acc;
   p.d0 = dsc->box[0]; p.d1 = dsc->box[1]; p.h0 = dsc->box[2]; p.h1 = dsc->box[3];
+  p.offsets_fit_i32 = mode == 2 || ((long long)(p.nh + 1) * p.nw * p.ps_n + (long long)p.rh * p.ps_h + p.rw < (1LL << 31));
   if (p.d1 <= 0) { p.d0 = 0; p.d1 = p.D; }
   if (p.h1 <= 0) { p.h0 = 0; p.h1 = p.H; }
   B200_REQUIRE(p.d0 >= 0 && p.d1 <= p.D && p.h0 >= 0 && p.h1 <= p.H, "sw_blend: box outside the volume");

@@ -27,6 +27,7 @@
 #include "tc05.cuh"
 #include "../../include/monai_b200.h"
 #include <mutex>
+#include <type_traits>
 #include <cstdlib>
 
 namespace b200 {
@@ -110,7 +111,7 @@ __global__ void conv_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 // ----------------------------------------------------------------------------------------------------------
 constexpr int kTH = 16, kTW = 8;                 // output patch per D-plane: 16 (H) x 8 (W) = 128 GEMM rows
 constexpr int kHH = kTH + 2, kHW = kTW + 2;      // halo patch
-constexpr int kSA = 2, kSB = 3;                  // pipeline depths (A halo tiles, B weight slabs)
+constexpr int kSA = 2;                           // halo tiles in flight (the weight ring depth depends on NT: ConvTcCfg::kSB)
 
 template <int NT, int BD>
 struct ConvTcCfg {
@@ -118,10 +119,12 @@ struct ConvTcCfg {
   static constexpr int kChunkBytes = kPlanes * kHH * kHW * 16;   // one 8-channel chunk of the halo tile
   static constexpr int kABytes = 2 * kChunkBytes;                // 16 input channels
   static constexpr int kBTapBytes = 3 * NT * 32;                 // one (kh, kw): the three kd taps stacked along N, 3*NT x 16 fp16
-  static constexpr int kBBytes = 3 * kBTapBytes;                 // one kh slab (kw = 0..2)
+  // weight ring: one (kh, kw) tap image per stage, ~44 KB in flight so a bulk copy has > 1 us to land before its
+  // MMAs are due (the ring, not the tensor pipe, was the limiter with three 9-tap slabs)
+  static constexpr int kSB = (45056 / kBTapBytes) > 9 ? 9 : ((45056 / kBTapBytes) < 3 ? 3 : (45056 / kBTapBytes));
   static constexpr int kKdGroup = (3 * NT <= 256) ? 3 : ((2 * NT <= 256) ? 2 : 1);   // kd taps fused into one MMA (UMMA N <= 256)
   static constexpr int kTmemCols = (BD * NT <= 32) ? 32 : (BD * NT <= 64) ? 64 : (BD * NT <= 128) ? 128 : (BD * NT <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + 256 /*barriers*/ + 2 * NT * 4 /*stats*/ + 128 /*align slack*/;
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + 256 /*barriers*/ + 2 * NT * 4 /*stats*/ + 128 /*align slack*/;
   static_assert(BD * NT <= 512, "accumulators exceed TMEM");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "invalid UMMA N");
 };
@@ -142,7 +145,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSA * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSB * Cfg::kBBytes);
+  constexpr int kSB = Cfg::kSB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSB * Cfg::kBTapBytes);
   uint64_t* full_a = bars;            // [kSA]
   uint64_t* empty_a = bars + kSA;     // [kSA]
   uint64_t* full_b = bars + 2 * kSA;  // [kSB]
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmap);
-      const __half* wbase = p.w + (long long)nt * num_kc * 3 * (Cfg::kBBytes / 2);
+      const __half* wbase = p.w + (long long)nt * num_kc * 9 * (Cfg::kBTapBytes / 2);
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int kc = 0; kc < num_kc; ++kc) {
         tc::mbar_wait(&empty_a[sa], pa ^ 1);
@@ -186,10 +190,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
         tc::tma_load_5d(smem_a + sa * Cfg::kABytes, &tmap, &full_a[sa], (w0 - 1) * 8, h0 - 1, d0 - 1,
                         (d.in_coff + kc * 16) / 8, n);
         if (++sa == kSA) { sa = 0; pa ^= 1; }
-        for (int kh = 0; kh < 3; ++kh) {
+        for (int t9 = 0; t9 < 9; ++t9) {
           tc::mbar_wait(&empty_b[sb], pb ^ 1);
-          tc::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBBytes);
-          tc::bulk_load(smem_b + sb * Cfg::kBBytes, wbase + ((long long)kc * 3 + kh) * (Cfg::kBBytes / 2), Cfg::kBBytes,
+          tc::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBTapBytes);
+          tc::bulk_load(smem_b + sb * Cfg::kBTapBytes, wbase + ((long long)kc * 9 + t9) * (Cfg::kBTapBytes / 2), Cfg::kBTapBytes,
                         &full_b[sb]);
           if (++sb == kSB) { sb = 0; pb ^= 1; }
         }
@@ -201,45 +205,50 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
     if (lane == 0) {
       constexpr int G = Cfg::kKdGroup;
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      for (int kc = 0; kc < num_kc; ++kc) {
-        tc::mbar_wait(&full_a[sa], pa);
-        const uint32_t a_base = tc::smem_u32(smem_a + sa * Cfg::kABytes);
-        for (int kh = 0; kh < 3; ++kh) {
-          tc::mbar_wait(&full_b[sb], pb);
-          tc::fence_after_sync();
-          const uint32_t b_base = tc::smem_u32(smem_b + sb * Cfg::kBBytes);
+      uint32_t a_base = 0;
+      // One (kh, kw) tap of one K-slice: every input plane ip of the halo tile feeds output planes ip - kd.  FIRST is the
+      // very first tap of the tile: it initialises the accumulators, so it issues one MMA per (plane, kd) with a
+      // static accumulate flag; every other tap fuses the kd range of a plane into one MMA.  (Kept as two separately
+      // instantiated bodies: a run-time "first" flag made ptxas merge the two forms into predicated code.)
+      auto tap = [&](auto first_c, int kh, int kw) {
+        constexpr bool FIRST = decltype(first_c)::value;
+        tc::mbar_wait(&full_b[sb], pb);
+        tc::fence_after_sync();
+        const uint32_t b_tap = tc::smem_u32(smem_b + sb * Cfg::kBTapBytes);
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const uint32_t b_tap = b_base + kw * Cfg::kBTapBytes;
-            const bool first = (kc | kh | kw) == 0;   // the pass that initialises the accumulators: one MMA per (plane, kd)
+        for (int ip = 0; ip < BD + 2; ++ip) {
+          const int kd_hi = ip < 2 ? ip : 2, kd_lo = ip - (BD - 1) > 0 ? ip - (BD - 1) : 0;
+          const uint32_t a_addr = a_base + ((ip * kHH + kh) * kHW + kw) * 16;
+          const uint64_t adesc = tc::make_desc_kmajor_noswz(a_addr, Cfg::kChunkBytes, kHW * 16);
+          if constexpr (FIRST) {
 #pragma unroll
-            for (int ip = 0; ip < BD + 2; ++ip) {     // input plane of the halo tile; feeds output planes ip - kd
-              constexpr int kdmax = 2;
-              const int kd_hi = ip < kdmax ? ip : kdmax, kd_lo = ip - (BD - 1) > 0 ? ip - (BD - 1) : 0;
-              const uint32_t a_addr = a_base + ((ip * kHH + kh) * kHW + kw) * 16;
-              const uint64_t adesc = tc::make_desc_kmajor_noswz(a_addr, Cfg::kChunkBytes, kHW * 16);
-              if (first) {
+            for (int kd = 2; kd >= 0; --kd) {
+              if (kd > kd_hi || kd < kd_lo) continue;
+              const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - kd) * NT * 16, 3 * NT * 16, 128);
+              // plane ip - kd was initialised when it was the kd = 0 plane of an earlier ip
+              tc::mma_f16_ss(tmem_base + (ip - kd) * NT, adesc, bdesc, tc::make_idesc_f16(128, NT), kd != 0 ? 1u : 0u);
+            }
+          } else {
 #pragma unroll
-                for (int kd = 2; kd >= 0; --kd) {
-                  if (kd > kd_hi || kd < kd_lo) continue;
-                  const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - kd) * NT * 16, 3 * NT * 16, 128);
-                  // plane ip - kd was initialised when it was the kd = 0 plane of an earlier ip
-                  tc::mma_f16_ss(tmem_base + (ip - kd) * NT, adesc, bdesc, tc::make_idesc_f16(128, NT), kd != 0 ? 1u : 0u);
-                }
-              } else {
-#pragma unroll
-                for (int top = 2; top >= 0; top -= G) {   // kd groups [top-G+1, top] clipped to [kd_lo, kd_hi]
-                  const int hi = top < kd_hi ? top : kd_hi, lo = (top - G + 1) > kd_lo ? (top - G + 1) : kd_lo;
-                  if (hi < lo) continue;
-                  const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - hi) * NT * 16, 3 * NT * 16, 128);
-                  tc::mma_f16_ss(tmem_base + (ip - hi) * NT, adesc, bdesc, tc::make_idesc_f16(128, (hi - lo + 1) * NT), 1u);
-                }
-              }
+            for (int top = 2; top >= 0; top -= G) {   // kd groups [top-G+1, top] clipped to [kd_lo, kd_hi]
+              const int hi = top < kd_hi ? top : kd_hi, lo = (top - G + 1) > kd_lo ? (top - G + 1) : kd_lo;
+              if (hi < lo) continue;
+              const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - hi) * NT * 16, 3 * NT * 16, 128);
+              tc::mma_f16_ss(tmem_base + (ip - hi) * NT, adesc, bdesc, tc::make_idesc_f16(128, (hi - lo + 1) * NT), 1u);
             }
           }
-          tc::mma_commit(&empty_b[sb]);
-          if (++sb == kSB) { sb = 0; pb ^= 1; }
         }
+        tc::mma_commit(&empty_b[sb]);
+        if (++sb == kSB) { sb = 0; pb ^= 1; }
+      };
+      for (int kc = 0; kc < num_kc; ++kc) {
+        tc::mbar_wait(&full_a[sa], pa);
+        tc::fence_after_sync();
+        a_base = tc::smem_u32(smem_a + sa * Cfg::kABytes);
+        if (kc == 0) tap(std::true_type{}, 0, 0);
+        else tap(std::false_type{}, 0, 0);
+#pragma unroll
+        for (int t9 = 1; t9 < 9; ++t9) tap(std::false_type{}, t9 / 3, t9 % 3);
         tc::mma_commit(&empty_a[sa]);
         if (++sa == kSA) { sa = 0; pa ^= 1; }
       }
