@@ -8,6 +8,7 @@
 // IEEE divide) and the count map is never materialised.  imp() is evaluated on the fly from the three 1-D
 // vectors of compute_importance_map (monai/data/utils.py:1084-1134): ((g_d*g_h)*g_w) clamped from below.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/monai_b200.h"
 
 namespace b200 {
@@ -210,24 +211,38 @@ constexpr int kBlend8Rows = 8;   // warps (= h rows) per block
 constexpr int kBlend8MaxRoiW = 512;
 constexpr int kBlend8K = 3;      // W windows per (d, h) window pair handled by the pipelined path (overlap <= 2/3)
 
-template <typename TP, typename TO, int MODE>
-__global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_blend8_kernel(BlendParams p) {
+// VAR 0: loads of the next (d, h) window pair are in flight while the current one is accumulated (fewer, fatter
+// threads); VAR 1: one pair at a time with fewer registers, so three blocks share an SM.
+template <typename TP, typename TO, int MODE, int VAR>
+__global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? (VAR == 0 ? 2 : 3) : 1) sw_blend8_kernel(BlendParams p) {
   using Raw = typename Pred8<TP>::Raw;
+  // A block covers 8 rows x 256 voxels of one depth plane; a WARP covers a compact 8 (h) x 32 (w) patch (lane = row*4 +
+  // octet), because the number of covering windows changes only every few voxels along an axis: a compact patch rarely
+  // straddles such a boundary, so the lanes of a warp agree on the loop trip counts (a 256-voxel row segment never does).
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int w8 = (blockIdx.x * 32 + lane) * 8;
-  const int h = p.h0 + blockIdx.y * kBlend8Rows + wrp;
+  const int w8 = (blockIdx.x * 32 + wrp * 4 + (lane & 3)) * 8;
+  const int h = p.h0 + blockIdx.y * kBlend8Rows + (lane >> 2);
   const int nd_box = p.d1 - p.d0;
   const int d = blockIdx.z % nd_box + p.d0, b = blockIdx.z / nd_box;
   __shared__ __align__(16) float s_gw[kBlend8MaxRoiW];   // W-axis importance factors (pipelined path)
+  __shared__ int s_cov[32 + kBlend8Rows + 1];            // covering window ranges (lo | count << 16): 32 octets, 8 rows, the plane
   if (p.gw && p.rw <= kBlend8MaxRoiW)
     for (int i = threadIdx.x; i < p.rw; i += blockDim.x) s_gw[i] = __ldg(p.gw + i);
+  if (threadIdx.x < 32 + kBlend8Rows + 1) {
+    // the window starts are sorted, so the windows covering a coordinate form a contiguous index range per axis
+    const int t = threadIdx.x;
+    const int* st = t < 32 ? p.starts_w : (t < 32 + kBlend8Rows ? p.starts_h : p.starts_d);
+    const int ns = t < 32 ? p.nw : (t < 32 + kBlend8Rows ? p.nh : p.nd);
+    const int r = t < 32 ? p.rw : (t < 32 + kBlend8Rows ? p.rh : p.rd);
+    const int xq = t < 32 ? (blockIdx.x * 32 + t) * 8 : (t < 32 + kBlend8Rows ? p.h0 + blockIdx.y * kBlend8Rows + (t - 32) : d);
+    int lo = 0, cn = 0;
+    for (int i = 0; i < ns; ++i) { const int s = __ldg(st + i); if (s <= xq && xq < s + r) { if (!cn) lo = i; ++cn; } }
+    s_cov[t] = lo | (cn << 16);
+  }
   __syncthreads();
   if (h >= p.h1 || w8 >= p.W) return;
-  // the window starts are sorted, so the windows covering a coordinate form a contiguous index range per axis
-  int id_lo = 0, ndc = 0, ih_lo = 0, nhc = 0, iw_lo = 0, nwc = 0;
-  for (int i = 0; i < p.nd; ++i) { const int s = __ldg(p.starts_d + i); if (s <= d && d < s + p.rd) { if (!ndc) id_lo = i; ++ndc; } }
-  for (int i = 0; i < p.nh; ++i) { const int s = __ldg(p.starts_h + i); if (s <= h && h < s + p.rh) { if (!nhc) ih_lo = i; ++nhc; } }
-  for (int i = 0; i < p.nw; ++i) { const int s = __ldg(p.starts_w + i); if (s <= w8 && w8 < s + p.rw) { if (!nwc) iw_lo = i; ++nwc; } }
+  const int cw = s_cov[wrp * 4 + (lane & 3)], ch = s_cov[32 + (lane >> 2)], cd = s_cov[32 + kBlend8Rows];
+  const int id_lo = cd & 0xffff, ndc = cd >> 16, ih_lo = ch & 0xffff, nhc = ch >> 16, iw_lo = cw & 0xffff, nwc = cw >> 16;
   const int num_win = p.nd * p.nh * p.nw;
   const long long vol = (long long)p.D * p.H * p.W;
   const long long voff = ((long long)d * p.H + h) * p.W + w8;
@@ -311,17 +326,25 @@ __global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_
           }
         }
       };
-      Raw A0[kBlend8K], A1[kBlend8K], B0[kBlend8K], B1[kBlend8K];
-      Pair pa, pb;
       int ai = 0, ei = 0;   // (d, h) pair position of the load stream
       auto adv = [&](int& a, int& e) { if (++e == nhc) { e = 0; ++a; } };
-      if (P > 0) { pa = issue(ai, ei, A0, A1); adv(ai, ei); }
-      for (int q = 0; q < P; q += 2) {
-        if (q + 1 < P) { pb = issue(ai, ei, B0, B1); adv(ai, ei); }
-        consume(pa, A0, A1);
-        if (q + 1 < P) {
-          if (q + 2 < P) { pa = issue(ai, ei, A0, A1); adv(ai, ei); }
-          consume(pb, B0, B1);
+      if (VAR == 0) {
+        Raw A0[kBlend8K], A1[kBlend8K], B0[kBlend8K], B1[kBlend8K];
+        Pair pa, pb;
+        if (P > 0) { pa = issue(ai, ei, A0, A1); adv(ai, ei); }
+        for (int q = 0; q < P; q += 2) {
+          if (q + 1 < P) { pb = issue(ai, ei, B0, B1); adv(ai, ei); }
+          consume(pa, A0, A1);
+          if (q + 1 < P) {
+            if (q + 2 < P) { pa = issue(ai, ei, A0, A1); adv(ai, ei); }
+            consume(pb, B0, B1);
+          }
+        }
+      } else {
+        Raw A0[kBlend8K], A1[kBlend8K];
+        for (int q = 0; q < P; ++q) {
+          const Pair pa = issue(ai, ei, A0, A1); adv(ai, ei);
+          consume(pa, A0, A1);
         }
       }
     } else {
@@ -441,7 +464,9 @@ static int launch_blend8(const BlendParams& p, int pred_dtype, int out_dtype, cu
   dim3 grid(ceil_div(p.W / 8, 32), ceil_div(p.h1 - p.h0, kBlend8Rows), (p.d1 - p.d0) * p.B);
   if (grid.y == 0 || grid.z == 0) return B200_OK;
   B200_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "sw_blend: volume too large for the launch grid");
-#define LB(TP, TO) sw_blend8_kernel<TP, TO, MODE><<<grid, block, 0, st>>>(p)
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("B200_BLEND_VARIANT"); variant = (e && e[0] == '1') ? 1 : 0; }
+#define LB(TP, TO) do { if (variant == 1) sw_blend8_kernel<TP, TO, MODE, 1><<<grid, block, 0, st>>>(p); else sw_blend8_kernel<TP, TO, MODE, 0><<<grid, block, 0, st>>>(p); } while (0)
   if (MODE == 1) {
     if (pred_dtype == B200_DT_F16) LB(__half, float); else LB(float, float);
   } else if (MODE == 2) {

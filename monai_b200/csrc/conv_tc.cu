@@ -111,7 +111,6 @@ __global__ void conv_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 // ----------------------------------------------------------------------------------------------------------
 constexpr int kTH = 16, kTW = 8;                 // output patch per D-plane: 16 (H) x 8 (W) = 128 GEMM rows
 constexpr int kHH = kTH + 2, kHW = kTW + 2;      // halo patch
-constexpr int kSA = 2;                           // halo tiles in flight (the weight ring depth depends on NT: ConvTcCfg::kSB)
 
 template <int NT, int BD>
 struct ConvTcCfg {
@@ -122,11 +121,15 @@ struct ConvTcCfg {
   // weight ring: one (kh, kw) tap image per stage, ~44 KB in flight so a bulk copy has > 1 us to land before its
   // MMAs are due (the ring, not the tensor pipe, was the limiter with three 9-tap slabs)
   static constexpr int kSB = (45056 / kBTapBytes) > 9 ? 9 : ((45056 / kBTapBytes) < 3 ? 3 : (45056 / kBTapBytes));
+  static constexpr int kSA = 4;                                  // halo tiles in flight (one CTA per SM owns the whole shared memory)
   static constexpr int kKdGroup = (3 * NT <= 256) ? 3 : ((2 * NT <= 256) ? 2 : 1);   // kd taps fused into one MMA (UMMA N <= 256)
-  static constexpr int kTmemCols = (BD * NT <= 32) ? 32 : (BD * NT <= 64) ? 64 : (BD * NT <= 128) ? 128 : (BD * NT <= 256) ? 256 : 512;
+  static constexpr int kAccBufs = (2 * BD * NT <= 512) ? 2 : 1;  // accumulator sets: 2 lets the epilogue of tile i overlap the MMAs of tile i+1
+  static constexpr int kAccCols = kAccBufs * BD * NT;
+  static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + 256 /*barriers*/ + 2 * NT * 4 /*stats*/ + 128 /*align slack*/;
   static_assert(BD * NT <= 512, "accumulators exceed TMEM");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "invalid UMMA N");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 struct ConvTcParams {
@@ -135,40 +138,54 @@ struct ConvTcParams {
   const float* bias;
   __half* y;
   float* stats;
-  int tiles_w, tiles_h, tiles_d;
+  int tiles_w, tiles_h, tiles_d, n_tiles;
+  long long total_tiles;   // tiles_w * tiles_h * tiles_d * n_tiles * N
 };
 
+struct ConvTile { int w0, h0, d0, nt, n; };
+
+template <int BD>
+__device__ __forceinline__ ConvTile conv_tile(const ConvTcParams& p, long long t) {
+  // spatial tiles fastest, then the N tile, then the batch item: CTAs that run concurrently stream the same weights
+  ConvTile c;
+  c.w0 = (int)(t % p.tiles_w) * kTW; t /= p.tiles_w;
+  c.h0 = (int)(t % p.tiles_h) * kTH; t /= p.tiles_h;
+  c.d0 = (int)(t % p.tiles_d) * BD; t /= p.tiles_d;
+  c.nt = (int)(t % p.n_tiles);
+  c.n = (int)(t / p.n_tiles);
+  return c;
+}
+
+// Persistent, warp-specialised (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-5 = epilogue.  Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the shared-memory rings run
+// across tile boundaries and (when 2*BD*NT <= 512 columns) two TMEM accumulator sets alternate.
 template <int NT, int BD>
 __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
   using Cfg = ConvTcCfg<NT, BD>;
+  constexpr int kSA = Cfg::kSA, kSB = Cfg::kSB, kNB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSA * Cfg::kABytes;
-  constexpr int kSB = Cfg::kSB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSB * Cfg::kBTapBytes);
-  uint64_t* full_a = bars;            // [kSA]
-  uint64_t* empty_a = bars + kSA;     // [kSA]
-  uint64_t* full_b = bars + 2 * kSA;  // [kSB]
-  uint64_t* empty_b = full_b + kSB;   // [kSB]
-  uint64_t* acc_full = empty_b + kSB; // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* full_a = bars;              // [kSA]
+  uint64_t* empty_a = bars + kSA;       // [kSA]
+  uint64_t* full_b = bars + 2 * kSA;    // [kSB]
+  uint64_t* empty_b = full_b + kSB;     // [kSB]
+  uint64_t* acc_full = empty_b + kSB;   // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  static_assert(2 * kSA + 2 * kSB + 4 + 1 <= 32, "barrier block");
   float* s_stats = reinterpret_cast<float*>(bars + 32);  // [2*NT]
 
   const b200_conv_tc_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th = tile % p.tiles_h; tile /= p.tiles_h;
-  const int td = tile;
-  const int w0 = tw * kTW, h0 = th * kTH, d0 = td * BD;
-  const int nt = blockIdx.y, n = blockIdx.z;
   const int num_kc = d.Cin / 16;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < kSB; ++i) { tc::mbar_init(&full_b[i], 1); tc::mbar_init(&empty_b[i], 1); }
-    tc::mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
@@ -182,30 +199,37 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmap);
-      const __half* wbase = p.w + (long long)nt * num_kc * 9 * (Cfg::kBTapBytes / 2);
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      for (int kc = 0; kc < num_kc; ++kc) {
-        tc::mbar_wait(&empty_a[sa], pa ^ 1);
-        tc::mbar_arrive_expect_tx(&full_a[sa], Cfg::kABytes);
-        tc::tma_load_5d(smem_a + sa * Cfg::kABytes, &tmap, &full_a[sa], (w0 - 1) * 8, h0 - 1, d0 - 1,
-                        (d.in_coff + kc * 16) / 8, n);
-        if (++sa == kSA) { sa = 0; pa ^= 1; }
-        for (int t9 = 0; t9 < 9; ++t9) {
-          tc::mbar_wait(&empty_b[sb], pb ^ 1);
-          tc::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBTapBytes);
-          tc::bulk_load(smem_b + sb * Cfg::kBTapBytes, wbase + ((long long)kc * 9 + t9) * (Cfg::kBTapBytes / 2), Cfg::kBTapBytes,
-                        &full_b[sb]);
-          if (++sb == kSB) { sb = 0; pb ^= 1; }
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const ConvTile c = conv_tile<BD>(p, t);
+        const __half* wbase = p.w + (long long)c.nt * num_kc * 9 * (Cfg::kBTapBytes / 2);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          tc::mbar_wait(&empty_a[sa], pa ^ 1);
+          tc::mbar_arrive_expect_tx(&full_a[sa], Cfg::kABytes);
+          tc::tma_load_5d(smem_a + sa * Cfg::kABytes, &tmap, &full_a[sa], (c.w0 - 1) * 8, c.h0 - 1, c.d0 - 1,
+                          (d.in_coff + kc * 16) / 8, c.n);
+          if (++sa == kSA) { sa = 0; pa ^= 1; }
+          for (int t9 = 0; t9 < 9; ++t9) {
+            tc::mbar_wait(&empty_b[sb], pb ^ 1);
+            tc::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBTapBytes);
+            tc::bulk_load(smem_b + sb * Cfg::kBTapBytes, wbase + ((long long)kc * 9 + t9) * (Cfg::kBTapBytes / 2), Cfg::kBTapBytes,
+                          &full_b[sb]);
+            if (++sb == kSB) { sb = 0; pb ^= 1; }
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop control (converged, so addresses and descriptors stay on the uniform datapath); one
+    // elected lane issues the tcgen05 instructions.
+    {
       constexpr int G = Cfg::kKdGroup;
+      const bool leader = tc::elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      uint32_t a_base = 0;
+      uint32_t a_base = 0, tacc = 0;
       // One (kh, kw) tap of one K-slice: every input plane ip of the halo tile feeds output planes ip - kd.  FIRST is the
       // very first tap of the tile: it initialises the accumulators, so it issues one MMA per (plane, kd) with a
       // static accumulate flag; every other tap fuses the kd range of a plane into one MMA.  (Kept as two separately
@@ -226,7 +250,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
               if (kd > kd_hi || kd < kd_lo) continue;
               const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - kd) * NT * 16, 3 * NT * 16, 128);
               // plane ip - kd was initialised when it was the kd = 0 plane of an earlier ip
-              tc::mma_f16_ss(tmem_base + (ip - kd) * NT, adesc, bdesc, tc::make_idesc_f16(128, NT), kd != 0 ? 1u : 0u);
+              if (leader) tc::mma_f16_ss(tacc + (ip - kd) * NT, adesc, bdesc, tc::make_idesc_f16(128, NT), kd != 0 ? 1u : 0u);
             }
           } else {
 #pragma unroll
@@ -234,108 +258,129 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
               const int hi = top < kd_hi ? top : kd_hi, lo = (top - G + 1) > kd_lo ? (top - G + 1) : kd_lo;
               if (hi < lo) continue;
               const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_tap + (2 - hi) * NT * 16, 3 * NT * 16, 128);
-              tc::mma_f16_ss(tmem_base + (ip - hi) * NT, adesc, bdesc, tc::make_idesc_f16(128, (hi - lo + 1) * NT), 1u);
+              if (leader) tc::mma_f16_ss(tacc + (ip - hi) * NT, adesc, bdesc, tc::make_idesc_f16(128, (hi - lo + 1) * NT), 1u);
             }
           }
         }
-        tc::mma_commit(&empty_b[sb]);
+        if (leader) tc::mma_commit(&empty_b[sb]);
+        __syncwarp();
         if (++sb == kSB) { sb = 0; pb ^= 1; }
       };
-      for (int kc = 0; kc < num_kc; ++kc) {
-        tc::mbar_wait(&full_a[sa], pa);
+      int it = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int buf = it % kNB;
+        const uint32_t aph = (uint32_t)((it / kNB) & 1);
+        tc::mbar_wait(&acc_empty[buf], aph ^ 1);   // the epilogue has drained this accumulator set
         tc::fence_after_sync();
-        a_base = tc::smem_u32(smem_a + sa * Cfg::kABytes);
-        if (kc == 0) tap(std::true_type{}, 0, 0);
-        else tap(std::false_type{}, 0, 0);
+        tacc = tmem_u + buf * (BD * NT);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          tc::mbar_wait(&full_a[sa], pa);
+          tc::fence_after_sync();
+          a_base = tc::smem_u32(smem_a + sa * Cfg::kABytes);
+          if (kc == 0) tap(std::true_type{}, 0, 0);
+          else tap(std::false_type{}, 0, 0);
 #pragma unroll
-        for (int t9 = 1; t9 < 9; ++t9) tap(std::false_type{}, t9 / 3, t9 % 3);
-        tc::mma_commit(&empty_a[sa]);
-        if (++sa == kSA) { sa = 0; pa ^= 1; }
+          for (int t9 = 1; t9 < 9; ++t9) tap(std::false_type{}, t9 / 3, t9 % 3);
+          if (leader) tc::mma_commit(&empty_a[sa]);
+          __syncwarp();
+          if (++sa == kSA) { sa = 0; pa ^= 1; }
+        }
+        if (leader) tc::mma_commit(&acc_full[buf]);
+        __syncwarp();
       }
-      tc::mma_commit(acc_full);
     }
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int h = h0 + (row >> 3), w = w0 + (row & 7);
-    const bool hw_ok = h < d.H && w < d.W;
-    tc::mbar_wait(acc_full, 0);
-    tc::fence_after_sync();
-    const int co0 = nt * NT;
     const long long S = (long long)d.D * d.H * d.W;
-    __half* ybase = p.y + (((long long)n * (d.out_ctot / 8) + (d.out_coff + co0) / 8) * S) * 8;
-    uint32_t vn[8];
-    tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16), vn);   // (cc = 0, sub = 0); every later load is prefetched one step ahead
+    int it = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const ConvTile c = conv_tile<BD>(p, t);
+      const int buf = it % kNB;
+      const uint32_t aph = (uint32_t)((it / kNB) & 1);
+      const int h = c.h0 + (row >> 3), w = c.w0 + (row & 7);
+      const bool hw_ok = h < d.H && w < d.W;
+      const int co0 = c.nt * NT;
+      __half* ybase = p.y + (((long long)c.n * (d.out_ctot / 8) + (d.out_coff + co0) / 8) * S) * 8;
+      tc::mbar_wait(&acc_full[buf], aph);
+      tc::fence_after_sync();
+      const uint32_t tq = tmem_base + buf * (BD * NT) + ((uint32_t)(q * 32) << 16);
+      uint32_t vn[8];
+      tc::tmem_ld8(tq, vn);   // (cc = 0, sub = 0); every later load is prefetched one step ahead
 #pragma unroll 1
-    for (int cc = 0; cc < NT / 8; ++cc) {
-      float bsum[8], bsq[8], bias8[8];
+      for (int cc = 0; cc < NT / 8; ++cc) {
+        float bsum[8], bsq[8], bias8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = p.bias ? p.bias[co0 + cc * 8 + j] : 0.f; }
+        for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = p.bias ? p.bias[co0 + cc * 8 + j] : 0.f; }
 #pragma unroll
-      for (int sub = 0; sub < BD; ++sub) {
-        uint32_t v[8];
-        tc::tmem_ld_wait();
+        for (int sub = 0; sub < BD; ++sub) {
+          uint32_t v[8];
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = vn[j];
-        {
-          const int nsub = sub + 1 < BD ? sub + 1 : 0, ncc = sub + 1 < BD ? cc : cc + 1;
-          if (ncc < NT / 8) tc::tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + nsub * NT + ncc * 8, vn);
+          for (int j = 0; j < 8; ++j) v[j] = vn[j];
+          {
+            const int nsub = sub + 1 < BD ? sub + 1 : 0, ncc = sub + 1 < BD ? cc : cc + 1;
+            if (ncc < NT / 8) tc::tmem_ld8(tq + nsub * NT + ncc * 8, vn);
+          }
+          const int dz = c.d0 + sub;
+          const bool ok = hw_ok && dz < d.D;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[j] = __uint_as_float(v[j]) + bias8[j];
+            if (ok) { bsum[j] += f[j]; bsq[j] = fmaf(f[j], f[j], bsq[j]); }
+          }
+          if (ok) {
+            uint4 hv;
+            __half2* hp = reinterpret_cast<__half2*>(&hv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * d.H + h) * d.W + w) * 8) = hv;
+          }
         }
-        const int dz = d0 + sub;
-        const bool ok = hw_ok && dz < d.D;
-        float f[8];
+        if (p.stats) {
+          // transpose-reduce 8 columns over the 32 lanes: 4+2+1 exchange steps, then 2 plain steps
+          float a4[4], b4[4];
+          const bool hi16 = lane & 16;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          f[j] = __uint_as_float(v[j]) + bias8[j];
-          if (ok) { bsum[j] += f[j]; bsq[j] = fmaf(f[j], f[j], bsq[j]); }
-        }
-        if (ok) {
-          uint4 hv;
-          __half2* hp = reinterpret_cast<__half2*>(&hv);
+          for (int j = 0; j < 4; ++j) {
+            const float send = hi16 ? bsum[j] : bsum[j + 4], keep = hi16 ? bsum[j + 4] : bsum[j];
+            a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            const float send2 = hi16 ? bsq[j] : bsq[j + 4], keep2 = hi16 ? bsq[j + 4] : bsq[j];
+            b4[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
+          }
+          float a2[2], b2[2];
+          const bool hi8 = lane & 8;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-          *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * d.H + h) * d.W + w) * 8) = hv;
+          for (int j = 0; j < 2; ++j) {
+            const float send = hi8 ? a4[j] : a4[j + 2], keep = hi8 ? a4[j + 2] : a4[j];
+            a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            const float send2 = hi8 ? b4[j] : b4[j + 2], keep2 = hi8 ? b4[j + 2] : b4[j];
+            b2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
+          }
+          const bool hi4 = lane & 4;
+          float a1 = (hi4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? a2[0] : a2[1], 4);
+          float b1 = (hi4 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? b2[0] : b2[1], 4);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 2); b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 1); b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+          if ((lane & 3) == 0) {
+            const int col = cc * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            atomicAdd(&s_stats[2 * col], a1);
+            atomicAdd(&s_stats[2 * col + 1], b1);
+          }
         }
       }
+      // this thread's TMEM reads of the set are complete: hand it back to the MMA warp
+      tc::fence_before_sync();
+      tc::mbar_arrive(&acc_empty[buf]);
       if (p.stats) {
-        // transpose-reduce 8 columns over the 32 lanes: 4+2+1 exchange steps, then 2 plain steps
-        float a4[4], b4[4];
-        const bool hi16 = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float send = hi16 ? bsum[j] : bsum[j + 4], keep = hi16 ? bsum[j + 4] : bsum[j];
-          a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-          const float send2 = hi16 ? bsq[j] : bsq[j + 4], keep2 = hi16 ? bsq[j + 4] : bsq[j];
-          b4[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
-        }
-        float a2[2], b2[2];
-        const bool hi8 = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float send = hi8 ? a4[j] : a4[j + 2], keep = hi8 ? a4[j + 2] : a4[j];
-          a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-          const float send2 = hi8 ? b4[j] : b4[j + 2], keep2 = hi8 ? b4[j + 2] : b4[j];
-          b2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
-        }
-        const bool hi4 = lane & 4;
-        float a1 = (hi4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? a2[0] : a2[1], 4);
-        float b1 = (hi4 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? b2[0] : b2[1], 4);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 2); b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
-        if ((lane & 3) == 0) {
-          const int col = cc * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-          atomicAdd(&s_stats[2 * col], a1);
-          atomicAdd(&s_stats[2 * col + 1], b1);
-        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int tt = threadIdx.x - 64;
+        for (int i = tt; i < 2 * NT; i += 128) { atomicAdd(&p.stats[((long long)c.n * d.Cout + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-    }
-    tc::fence_before_sync();
-    if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;
-      for (int i = t; i < 2 * NT; i += 128) atomicAdd(&p.stats[((long long)n * d.Cout + co0) * 2 + i], s_stats[i]);
     }
   }
   __syncthreads();
@@ -455,9 +500,9 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void*
   B200_REQUIRE(r == CUDA_SUCCESS, "conv3x3x3_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   ConvTcParams p;
   p.d = d; p.w = (const __half*)w; p.bias = bias; p.y = (__half*)y; p.stats = stats;
-  p.tiles_w = ceil_div(d.W, kTW); p.tiles_h = ceil_div(d.H, kTH); p.tiles_d = ceil_div(d.D, BD);
-  dim3 grid((unsigned)((long long)p.tiles_w * p.tiles_h * p.tiles_d), d.Cout / NT, d.N);
-  B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3x3x3_tc: grid too large");
+  p.tiles_w = ceil_div(d.W, kTW); p.tiles_h = ceil_div(d.H, kTH); p.tiles_d = ceil_div(d.D, BD); p.n_tiles = d.Cout / NT;
+  p.total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.n_tiles * d.N;
+  dim3 grid((unsigned)std::min<long long>(p.total_tiles, num_sms()));
   auto kern = conv3x3x3_tc_kernel<NT, BD>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -472,8 +517,9 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void*
 template <int NT>
 static int dispatch_bd(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats,
                        cudaStream_t st) {
-  // deeper CTA tiles amortise the halo and the weight slab; TMEM (BD*NT <= 512) and the plane count bound BD
-  if constexpr (NT * 4 <= 512) {
+  // deeper CTA tiles amortise the halo and fuse more kd taps per MMA; two accumulator sets (2*BD*NT <= 512 TMEM columns)
+  // let the epilogue overlap the next tile, which is worth more than depth for the wide-N layers
+  if constexpr (2 * NT * 4 <= 512) {
     if (d.D % 4 == 0 || d.D >= 16) return launch_conv_tc<NT, 4>(d, x, w, bias, y, stats, st);
   }
   if constexpr (NT * 2 <= 512) {

@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    // the whole warp runs the loop control (converged: descriptors stay on the uniform datapath), one elected lane issues
+    {
+      const bool leader = tc::elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = tc::make_idesc_f16(128, NT);
       int s = 0; uint32_t ph = 0;
       int it = 0;
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
         const uint32_t aph = (uint32_t)((it >> 1) & 1);
         tc::mbar_wait(&acc_empty[buf], aph ^ 1);     // epilogue has drained this accumulator buffer
         tc::fence_after_sync();
-        const uint32_t tacc = tmem_base + buf * NT;
+        const uint32_t tacc = tmem_u + buf * NT;
         for (int st = 0; st < num_stages; ++st) {
           const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
           tc::mbar_wait(&full[s], ph);
@@ -155,12 +158,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
           for (int k = 0; k < steps; ++k) {
             const uint64_t adesc = tc::make_desc_kmajor_noswz(a_base + k * 2 * 2048, 2048, 128);
             const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_base + k * NT * 32, NT * 16, 128);
-            tc::mma_f16_ss(tacc, adesc, bdesc, idesc, (st | k) != 0 ? 1u : 0u);
+            if (leader) tc::mma_f16_ss(tacc, adesc, bdesc, idesc, (st | k) != 0 ? 1u : 0u);
           }
-          tc::mma_commit(&empty[s]);
+          if (leader) tc::mma_commit(&empty[s]);
+          __syncwarp();
           if (++s == kGemmStages) { s = 0; ph ^= 1; }
         }
-        tc::mma_commit(&acc_full[buf]);
+        if (leader) tc::mma_commit(&acc_full[buf]);
+        __syncwarp();
       }
     }
     __syncwarp();
