@@ -341,32 +341,10 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
           }
         }
         if (p.stats) {
-          // transpose-reduce 8 columns over the 32 lanes: 4+2+1 exchange steps, then 2 plain steps
-          float a4[4], b4[4];
-          const bool hi16 = lane & 16;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float send = hi16 ? bsum[j] : bsum[j + 4], keep = hi16 ? bsum[j + 4] : bsum[j];
-            a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            const float send2 = hi16 ? bsq[j] : bsq[j + 4], keep2 = hi16 ? bsq[j + 4] : bsq[j];
-            b4[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
-          }
-          float a2[2], b2[2];
-          const bool hi8 = lane & 8;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float send = hi8 ? a4[j] : a4[j + 2], keep = hi8 ? a4[j + 2] : a4[j];
-            a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            const float send2 = hi8 ? b4[j] : b4[j + 2], keep2 = hi8 ? b4[j + 2] : b4[j];
-            b2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
-          }
-          const bool hi4 = lane & 4;
-          float a1 = (hi4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? a2[0] : a2[1], 4);
-          float b1 = (hi4 ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? b2[0] : b2[1], 4);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, 2); b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, 1); b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+          float a1, b1;
+          transpose_reduce8(bsum, bsq, lane, a1, b1);
           if ((lane & 3) == 0) {
-            const int col = cc * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            const int col = cc * 8 + transpose_reduce8_col(lane);
             atomicAdd(&s_stats[2 * col], a1);
             atomicAdd(&s_stats[2 * col + 1], b1);
           }
