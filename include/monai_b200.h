@@ -224,11 +224,28 @@ int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H, int W, con
 int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,
                        void* y, int out_dtype, void* stream);
 
+/* Output head fused with the tail of the last residual block: y = W * lrelu(instnorm(x) + instnorm?(res)) + b
+ * (UnetResBlock.forward norm2 + residual + lrelu, dynunet_block.py:97-111, then UnetOutBlock :247-267).  x is a whole NC8
+ * tensor of C channels with its (sum, sum of squares) statistics [N*C*2]; res is a channel slice of an NC8 buffer, normalised
+ * with res_stats when given (the block's conv3 branch) or added as is. */
+int b200_head_conv_norm_nc8(const void* x, int N, int C, long long S, const float* stats, float eps, const void* res,
+                            int res_ctot, int res_coff, const float* res_stats, float slope, const float* weight,
+                            const float* bias, int Cout, void* y, int out_dtype, void* stream);
+
 /* NC8 variant of b200_norm_act: y = act(instnorm(x) [+ instnorm?(res)]); act: 0 none, 1 leaky-relu(slope), 3 relu.
  * x / res / y are channel slices [coff, coff+C) of NC8 buffers with ctot channels. */
 int b200_norm_act_nc8(const void* x, int x_ctot, int x_coff, int N, int C, long long S, const float* stats, float eps,
                       const void* res, int res_ctot, int res_coff, const float* res_stats, int act, float slope,
                       void* y, int y_ctot, int y_coff, void* stream);
+
+/* Same, for a residual block whose input has ONE channel (SwinUNETR encoder1): the residual branch
+ * instnorm(conv1x1x1(u)) of UnetResBlock (dynunet_block.py:75-111) is evaluated analytically from the statistics of the
+ * raw input u [N][S] (fp16): conv3 gives w_c * u, so its instance norm is (w_c u - w_c mu) / sqrt(w_c^2 sigma^2 + eps).
+ * raw_stats = {sum, sum of squares} of u per batch item [N*2]; raw_weight = the C conv3 weights (the conv has no bias).
+ * The 1x1x1 convolution and its output tensor are never materialised. */
+int b200_norm_act_cin1res_nc8(const void* x, int x_ctot, int x_coff, int N, int C, long long S, const float* stats, float eps,
+                              const void* raw, const float* raw_stats, const float* raw_weight, int act, float slope, void* y,
+                              int y_ctot, int y_coff, void* stream);
 
 #ifdef __cplusplus
 }

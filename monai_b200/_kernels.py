@@ -332,6 +332,21 @@ def conv3x3x3_tc(
     return out, stats
 
 
+def norm_act_cin1res_nc8(x: NC8, C_: int, stats: torch.Tensor, raw: torch.Tensor, raw_stats: torch.Tensor, raw_weight: torch.Tensor,
+                         act: int = L.ACT_NONE, slope: float = 0.0, out: NC8 | None = None, out_coff: int = 0, eps: float = 1e-5) -> NC8:
+    """act(instnorm(x) + instnorm(conv1x1x1(raw))) for a ONE-channel `raw` [N,1,*sp] fp16: the residual branch is an affine
+    function of raw per channel, so neither the 1x1x1 convolution nor its output exist (see the header)."""
+    if raw.dtype != torch.float16 or raw.shape[1] != 1:
+        raise ValueError("norm_act_cin1res_nc8 expects a contiguous fp16 [N,1,D,H,W] input")
+    raw = raw.contiguous()
+    if out is None:
+        out = NC8(x.N, C_, x.sp, x.buf.device)
+    w32 = _f32c(raw_weight.reshape(-1))
+    _call("norm_act_cin1res_nc8", L.ptr(x.buf), x.C, 0, x.N, C_, x.S, L.ptr(stats), eps, L.ptr(raw), L.ptr(raw_stats), L.ptr(w32), act,
+          float(slope), L.ptr(out.buf), out.C, out_coff, L.stream_ptr(x.buf.device), nbytes=float(x.N * x.S * C_ * 4))
+    return out
+
+
 def norm_act_nc8(
     x: NC8, C_: int, stats: torch.Tensor | None, x_coff: int = 0, res: NC8 | None = None, res_coff: int = 0,
     res_stats: torch.Tensor | None = None, act: int = L.ACT_NONE, slope: float = 0.0, out: NC8 | None = None,
@@ -452,6 +467,19 @@ def head_conv_nc8(x: NC8, weight: torch.Tensor, bias: torch.Tensor | None, out_d
     b32 = _f32c(bias)
     y = torch.empty((x.N, Cout, *x.sp), device=x.buf.device, dtype=out_dtype)
     _call("head_conv_nc8", L.ptr(x.buf), x.N, x.C, x.S, L.ptr(w32), L.ptr(b32), Cout, L.ptr(y), L.dt(y), L.stream_ptr(x.buf.device))
+    return y
+
+
+def head_conv_norm_nc8(x: NC8, stats: torch.Tensor, res: NC8 | None, res_coff: int, res_stats: torch.Tensor | None, slope: float, eps: float,
+                       weight: torch.Tensor, bias: torch.Tensor | None, out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """logits = W * lrelu(instnorm(x) + instnorm?(res)) + b: the last residual block's tail fused into the 1x1x1 head."""
+    Cout = weight.shape[0]
+    w32 = _f32c(weight)
+    b32 = _f32c(bias)
+    y = torch.empty((x.N, Cout, *x.sp), device=x.buf.device, dtype=out_dtype)
+    _call("head_conv_norm_nc8", L.ptr(x.buf), x.N, x.C, x.S, L.ptr(stats), float(eps), L.ptr(res.buf) if res is not None else None,
+          res.C if res is not None else 0, res_coff, L.ptr(res_stats), float(slope), L.ptr(w32), L.ptr(b32), Cout, L.ptr(y), L.dt(y),
+          L.stream_ptr(x.buf.device), nbytes=float(x.N * x.S * (x.C * (4 if res is not None else 2) + Cout * y.element_size())))
     return y
 
 

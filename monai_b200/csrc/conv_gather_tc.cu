@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // converged warp + one elected lane (see conv_tc.cu): descriptors stay on the uniform datapath
+    {
+      const bool leader = tc::elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = tc::make_idesc_f16(128, NT);
       int s = 0; uint32_t ph = 0;
       int it = 0;
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
         const uint32_t aph = (uint32_t)((it >> 1) & 1);
         tc::mbar_wait(&acc_empty[buf], aph ^ 1);
         tc::fence_after_sync();
-        const uint32_t tacc = tmem_base + buf * NT;
+        const uint32_t tacc = tmem_u + buf * NT;
         for (int u0 = 0; u0 < units; u0 += kCgUnits) {
           const int nu = min(kCgUnits, units - u0);
           tc::mbar_wait(&full[s], ph);
@@ -210,12 +213,14 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
           for (int q = 0; q < nu; ++q) {
             const uint64_t adesc = tc::make_desc_kmajor_noswz(a_base + q * 2 * 2048, 2048, 128);
             const uint64_t bdesc = tc::make_desc_kmajor_noswz(b_base + q * NT * 32, NT * 16, 128);
-            tc::mma_f16_ss(tacc, adesc, bdesc, idesc, (u0 | q) != 0 ? 1u : 0u);
+            if (leader) tc::mma_f16_ss(tacc, adesc, bdesc, idesc, (u0 | q) != 0 ? 1u : 0u);
           }
-          tc::mma_commit(&empty[s]);
+          if (leader) tc::mma_commit(&empty[s]);
+          __syncwarp();
           if (++s == kCgStages) { s = 0; ph ^= 1; }
         }
-        tc::mma_commit(&acc_full[buf]);
+        if (leader) tc::mma_commit(&acc_full[buf]);
+        __syncwarp();
       }
     }
     __syncwarp();

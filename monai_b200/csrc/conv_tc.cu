@@ -375,6 +375,8 @@ struct NormActNc8P {
   long long S;
   const float* stats; const float* res_stats; float eps;
   int act; float slope;
+  // single-channel residual branch evaluated analytically (see b200_norm_act_cin1res_nc8)
+  const __half* raw; const float* raw_stats; const float* raw_w;
 };
 
 __global__ void __launch_bounds__(256) norm_act_nc8_kernel(NormActNc8P p) {
@@ -395,7 +397,14 @@ __global__ void __launch_bounds__(256) norm_act_nc8_kernel(NormActNc8P p) {
       const float mean = s * invS, var = fmaxf(q * invS - mean * mean, 0.f), rstd = 1.f / sqrtf(var + p.eps);
       rsc[j] = rstd; rsh[j] = -mean * rstd;
     }
+    if (p.raw) {
+      // residual = instnorm(w * u) of a 1-channel input u: mean = w mu, var = w^2 sigma^2  =>  alpha u + beta
+      const float s = p.raw_stats[2 * n], q = p.raw_stats[2 * n + 1];
+      const float mu = s * invS, var = fmaxf(q * invS - mu * mu, 0.f), w = p.raw_w[c];
+      rsc[j] = w / sqrtf(w * w * var + p.eps); rsh[j] = -rsc[j] * mu;
+    }
   }
+  const __half* u = p.raw ? p.raw + (long long)n * p.S : nullptr;
   const __half* x = p.x + (((long long)n * (p.x_ctot / 8) + p.x_coff / 8 + chunk) * p.S) * 8;
   __half* y = p.y + (((long long)n * (p.y_ctot / 8) + p.y_coff / 8 + chunk) * p.S) * 8;
   const __half* r = p.res ? p.res + (((long long)n * (p.r_ctot / 8) + p.r_coff / 8 + chunk) * p.S) * 8 : nullptr;
@@ -403,10 +412,12 @@ __global__ void __launch_bounds__(256) norm_act_nc8_kernel(NormActNc8P p) {
     __align__(16) __half v[8], rv[8];
     *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(x + s * 8);
     if (r) *reinterpret_cast<uint4*>(rv) = *reinterpret_cast<const uint4*>(r + s * 8);
+    const float uv = u ? __half2float(__ldg(u + s)) : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float f = fmaf(__half2float(v[j]), sc[j], sh[j]);
       if (r) f += fmaf(__half2float(rv[j]), rsc[j], rsh[j]);
+      if (u) f += fmaf(uv, rsc[j], rsh[j]);
       if (p.act == 1) f = f >= 0.f ? f : f * p.slope;
       else if (p.act == 3) f = fmaxf(f, 0.f);
       v[j] = __float2half_rn(f);
@@ -542,6 +553,26 @@ extern "C" int b200_norm_act_nc8(const void* x, int x_ctot, int x_coff, int N, i
   p.x = (const __half*)x; p.y = (__half*)y; p.res = (const __half*)res; p.C = C;
   p.x_ctot = x_ctot; p.x_coff = x_coff; p.y_ctot = y_ctot; p.y_coff = y_coff; p.r_ctot = res_ctot; p.r_coff = res_coff;
   p.S = S; p.stats = stats; p.res_stats = res_stats; p.eps = eps; p.act = act; p.slope = slope;
+  p.raw = nullptr; p.raw_stats = nullptr; p.raw_w = nullptr;
+  long long want = (long long)num_sms() * 16 / ((long long)N * (C / 8)) + 1;
+  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(want, (S + 255) / 256)), C / 8, N);
+  norm_act_nc8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  B200_LAUNCH_CHECK("norm_act_nc8_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_norm_act_cin1res_nc8(const void* x, int x_ctot, int x_coff, int N, int C, long long S, const float* stats,
+                                         float eps, const void* raw, const float* raw_stats, const float* raw_weight, int act,
+                                         float slope, void* y, int y_ctot, int y_coff, void* stream) {
+  B200_REQUIRE(x && y && stats && raw && raw_stats && raw_weight, "norm_act_cin1res_nc8: null pointer");
+  B200_REQUIRE(C % 8 == 0 && x_ctot % 8 == 0 && x_coff % 8 == 0 && y_ctot % 8 == 0 && y_coff % 8 == 0, "norm_act_cin1res_nc8: channels must be multiples of 8");
+  B200_REQUIRE(act == 0 || act == 1 || act == 3, "norm_act_cin1res_nc8: activation must be none, leaky-relu or relu");
+  if ((long long)N * C * S == 0) return B200_OK;
+  NormActNc8P p;
+  p.x = (const __half*)x; p.y = (__half*)y; p.res = nullptr; p.C = C;
+  p.x_ctot = x_ctot; p.x_coff = x_coff; p.y_ctot = y_ctot; p.y_coff = y_coff; p.r_ctot = 0; p.r_coff = 0;
+  p.S = S; p.stats = stats; p.res_stats = nullptr; p.eps = eps; p.act = act; p.slope = slope;
+  p.raw = (const __half*)raw; p.raw_stats = raw_stats; p.raw_w = raw_weight;
   long long want = (long long)num_sms() * 16 / ((long long)N * (C / 8)) + 1;
   dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(want, (S + 255) / 256)), C / 8, N);
   norm_act_nc8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);

@@ -22,14 +22,48 @@ __device__ __forceinline__ void st8(__half* p, const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------- LayerNorm
+__device__ __forceinline__ void cvt8(const uint4& r, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = __half22float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 r;
+  __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+  return r;
+}
+// y = (x - mean) * rstd * gamma + beta for one 8-channel vector; gamma / beta fetched as two float4 each
+__device__ __forceinline__ uint4 ln_apply8(const uint4& raw, float mean, float rstd, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, int ch) {
+  float f[8];
+  cvt8(raw, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd;
+  if (gamma) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch + 4));
+    f[0] *= g0.x; f[1] *= g0.y; f[2] *= g0.z; f[3] *= g0.w; f[4] *= g1.x; f[5] *= g1.y; f[6] *= g1.z; f[7] *= g1.w;
+  }
+  if (beta) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch + 4));
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+  }
+  return pack8(f);
+}
+
+// One thread per token.  KC8 > 0: the token's C = 8*KC8 channels stay in registers as raw 16-byte vectors (one global
+// read, one write; mean then centred variance, exactly the two-pass formula).  KC8 == 0: generic C, the centred second
+// pass and the output pass re-read the token (L1 hits).
+template <int KC8>
 __global__ void __launch_bounds__(256) layernorm_nc8_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C,
                                                             long long S_in, const int* __restrict__ src, long long S_out,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float eps) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= S_out) return;
-  const int n = blockIdx.y, C8 = C / 8;
-  const long long s = src ? (long long)src[r] : r;
+  const int n = blockIdx.y, C8 = KC8 > 0 ? KC8 : C / 8;
+  const long long s = src ? (long long)__ldg(src + r) : r;
   __half* yo = y + ((long long)n * C8 * S_out + r) * 8;
   if (s < 0) {  // padded token: exact zeros (F.pad after norm1, swin_unetr.py:603-606)
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -37,28 +71,47 @@ __global__ void __launch_bounds__(256) layernorm_nc8_kernel(const __half* __rest
     return;
   }
   const __half* xi = x + ((long long)n * C8 * S_in + s) * 8;
-  float sum = 0.f;
-  for (int c = 0; c < C8; ++c) {
-    float f[8]; ld8(xi + (long long)c * S_in * 8, f);
+  const float invC = 1.f / (float)(8 * C8);
+  if (KC8 > 0) {
+    uint4 raw[KC8 > 0 ? KC8 : 1];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sum += f[j];
-  }
-  const float mean = sum / (float)C;
-  float var = 0.f;
-  for (int c = 0; c < C8; ++c) {
-    float f[8]; ld8(xi + (long long)c * S_in * 8, f);
+    for (int c = 0; c < KC8; ++c) raw[c] = __ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S_in * 8));
+    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; var = fmaf(d, d, var); }
-  }
-  const float rstd = 1.f / sqrtf(var / (float)C + eps);
-  for (int c = 0; c < C8; ++c) {
-    float f[8]; ld8(xi + (long long)c * S_in * 8, f);
+    for (int c = 0; c < KC8; ++c) {
+      float f[8]; cvt8(raw[c], f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[j] = (f[j] - mean) * rstd;
-      if (gamma) f[j] = fmaf(f[j], gamma[c * 8 + j], beta ? beta[c * 8 + j] : 0.f);
+      for (int j = 0; j < 8; ++j) sum += f[j];
     }
-    st8(yo + (long long)c * S_out * 8, f);
+    const float mean = sum * invC;
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < KC8; ++c) {
+      float f[8]; cvt8(raw[c], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; var = fmaf(d, d, var); }
+    }
+    const float rstd = 1.f / sqrtf(var * invC + eps);
+#pragma unroll
+    for (int c = 0; c < KC8; ++c) *reinterpret_cast<uint4*>(yo + (long long)c * S_out * 8) = ln_apply8(raw[c], mean, rstd, gamma, beta, c * 8);
+  } else {
+    float sum = 0.f;
+    for (int c = 0; c < C8; ++c) {
+      float f[8]; cvt8(__ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S_in * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+    const float mean = sum * invC;
+    float var = 0.f;
+    for (int c = 0; c < C8; ++c) {
+      float f[8]; cvt8(__ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S_in * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; var = fmaf(d, d, var); }
+    }
+    const float rstd = 1.f / sqrtf(var * invC + eps);
+    for (int c = 0; c < C8; ++c)
+      *reinterpret_cast<uint4*>(yo + (long long)c * S_out * 8) =
+          ln_apply8(__ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S_in * 8)), mean, rstd, gamma, beta, c * 8);
   }
 }
 
@@ -66,6 +119,9 @@ __global__ void __launch_bounds__(256) layernorm_nc8_kernel(const __half* __rest
 __constant__ int kMergeV1[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
 __constant__ int kMergeV2[8][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {1, 0, 0}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1}};
 
+// One thread per merged token: the 2x2x2 neighbourhood (8 C channels) is read once for the mean, and the centred
+// variance and output passes re-read it from L1 (KC8 > 0 unrolls the channel loop so the 16-byte loads are batched).
+template <int KC8>
 __global__ void __launch_bounds__(128) patch_merge_ln_nc8_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C, int D,
                                                                  int H, int W, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps, int v2) {
@@ -73,7 +129,7 @@ __global__ void __launch_bounds__(128) patch_merge_ln_nc8_kernel(const __half* _
   const long long S2 = (long long)D2 * H2 * W2, S = (long long)D * H * W;
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= S2) return;
-  const int n = blockIdx.y, C8 = C / 8;
+  const int n = blockIdx.y, C8 = KC8 > 0 ? KC8 : C / 8;
   const int w2 = (int)(r % W2), h2 = (int)((r / W2) % H2), d2 = (int)(r / ((long long)W2 * H2));
   const __half* xn = x + (long long)n * C8 * S * 8;
   long long off[8]; bool ok[8];
@@ -82,45 +138,92 @@ __global__ void __launch_bounds__(128) patch_merge_ln_nc8_kernel(const __half* _
     const int* o = v2 ? kMergeV2[q] : kMergeV1[q];
     const int d = 2 * d2 + o[0], h = 2 * h2 + o[1], w = 2 * w2 + o[2];
     ok[q] = d < D && h < H && w < W;
-    off[q] = (((long long)d * H + h) * W + w) * 8;
+    off[q] = ok[q] ? (((long long)d * H + h) * W + w) * 8 : 0;
   }
-  const float Ct = 8.f * (float)C;
+  const float invC = 1.f / (8.f * (float)(8 * C8));
+  const uint4 zero = make_uint4(0, 0, 0, 0);
   float sum = 0.f;
-  for (int q = 0; q < 8; ++q)
-    if (ok[q])
-      for (int c = 0; c < C8; ++c) {
-        float f[8]; ld8(xn + (long long)c * S * 8 + off[q], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += f[j];
-      }
-  const float mean = sum / Ct;
-  float var = 0.f;
-  for (int q = 0; q < 8; ++q)
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll 6
     for (int c = 0; c < C8; ++c) {
       float f[8];
-      if (ok[q]) ld8(xn + (long long)c * S * 8 + off[q], f);
-      else {
+      cvt8(ok[q] ? __ldg(reinterpret_cast<const uint4*>(xn + (long long)c * S * 8 + off[q])) : zero, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.f;
-      }
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+  }
+  const float mean = sum * invC;
+  float var = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll 6
+    for (int c = 0; c < C8; ++c) {
+      float f[8];
+      cvt8(ok[q] ? __ldg(reinterpret_cast<const uint4*>(xn + (long long)c * S * 8 + off[q])) : zero, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { const float dd = f[j] - mean; var = fmaf(dd, dd, var); }
     }
-  const float rstd = 1.f / sqrtf(var / Ct + eps);
+  }
+  const float rstd = 1.f / sqrtf(var * invC + eps);
   __half* yo = y + ((long long)n * (8 * C8) * S2 + r) * 8;
-  for (int q = 0; q < 8; ++q)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll 6
     for (int c = 0; c < C8; ++c) {
-      float f[8];
-      if (ok[q]) ld8(xn + (long long)c * S * 8 + off[q], f);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.f;
-      }
-      const int ch = (q * C8 + c) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaf((f[j] - mean) * rstd, gamma ? gamma[ch + j] : 1.f, beta ? beta[ch + j] : 0.f);
-      st8(yo + (long long)(q * C8 + c) * S2 * 8, f);
+      const uint4 raw = ok[q] ? __ldg(reinterpret_cast<const uint4*>(xn + (long long)c * S * 8 + off[q])) : zero;
+      *reinterpret_cast<uint4*>(yo + (long long)(q * C8 + c) * S2 * 8) = ln_apply8(raw, mean, rstd, gamma, beta, (q * C8 + c) * 8);
     }
+  }
+}
+
+// Eight lanes per merged token (lane & 7 = neighbour q): every lane keeps its neighbour's C = 8*KC8 channels in registers
+// as raw 16-byte vectors, the statistics are reduced over the 8 lanes with three shuffles, and each lane writes its own
+// channel block (q*C .. q*C+C) of the output token.  One global read, one write; a warp's loads cover 4 (d,h) rows x 8
+// consecutive voxels = four full 128-byte lines per instruction.
+template <int KC8>
+__global__ void __launch_bounds__(256, 2) patch_merge_ln8_nc8_kernel(const __half* __restrict__ x, __half* __restrict__ y, int D, int H,
+                                                                  int W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float eps, int v2) {
+  const int D2 = (D + 1) / 2, H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const long long S2 = (long long)D2 * H2 * W2, S = (long long)D * H * W;
+  const int q = threadIdx.x & 7;
+  const long long r_raw = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool tok_ok = r_raw < S2;
+  const long long r = tok_ok ? r_raw : S2 - 1;   // lanes of an out-of-range token still take part in the shuffles
+  const int n = blockIdx.y;
+  const int w2 = (int)(r % W2), h2 = (int)((r / W2) % H2), d2 = (int)(r / ((long long)W2 * H2));
+  const int* o = v2 ? kMergeV2[q] : kMergeV1[q];
+  const int d = 2 * d2 + o[0], h = 2 * h2 + o[1], w = 2 * w2 + o[2];
+  const bool ok = d < D && h < H && w < W;      // odd sizes: the reference pads with zeros, which enter the statistics
+  const __half* xi = x + ((long long)n * KC8 * S + (((long long)d * H + h) * W + w)) * 8;
+  uint4 raw[KC8];
+#pragma unroll
+  for (int c = 0; c < KC8; ++c) raw[c] = ok ? __ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S * 8)) : make_uint4(0, 0, 0, 0);
+  const float invC = 1.f / (float)(8 * 8 * KC8);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < KC8; ++c) {
+    float f[8]; cvt8(raw[c], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += f[j];
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+  const float mean = sum * invC;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < KC8; ++c) {
+    float f[8]; cvt8(raw[c], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float dd = f[j] - mean; var = fmaf(dd, dd, var); }
+  }
+  var += __shfl_xor_sync(0xffffffffu, var, 1); var += __shfl_xor_sync(0xffffffffu, var, 2); var += __shfl_xor_sync(0xffffffffu, var, 4);
+  const float rstd = 1.f / sqrtf(var * invC + eps);
+  if (!tok_ok) return;
+  __half* yo = y + ((long long)n * (8 * KC8) * S2 + r) * 8;
+#pragma unroll
+  for (int c = 0; c < KC8; ++c)
+    *reinterpret_cast<uint4*>(yo + (long long)(q * KC8 + c) * S2 * 8) = ln_apply8(raw[c], mean, rstd, gamma, beta, (q * KC8 + c) * 8);
 }
 
 // ---------------------------------------------------------------------------------------------- window attention
@@ -148,6 +251,13 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 // One 32-key step of the online softmax for 16 query rows per warp.  All scores are kept in log2 units (the bias table
 // is pre-multiplied by log2(e) when it is staged, scale2 = scale*log2(e)) so every exponential is a bare ex2.approx.
 // MASK: shifted windows (region ids differ -> -100 as in compute_mask, swin_unetr.py:457-487).  TAIL: keys >= n exist.
+// bare MUFU.EX2 (exp2f() adds a denormal-range test and two scalings per call; the arguments here are <= 0 or -inf)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttRow {
   int lin0, lin1, reg0, reg1;
   float m0, m1, l0, l1;
@@ -171,9 +281,13 @@ __device__ __forceinline__ void att_step32(const uint32_t (&qa)[4], AttRow& r, i
   for (int nt = 0; nt < 4; ++nt) {
     const int j = j0 + nt * 8 + 2 * t4;                       // this thread's two keys j, j+1 of the tile
     const uint32_t lj2 = *reinterpret_cast<const uint32_t*>(sLin + j);
+    // sLin holds BYTE offsets (4 * lin) and r.lin0/1 the byte offset of the row's table origin: one subtract per lookup
     const int lja = (int)(lj2 & 0xffffu), ljb = (int)(lj2 >> 16);
-    float v00 = fmaf(sc[nt][0], scale2, sTab[r.lin0 - lja]), v01 = fmaf(sc[nt][1], scale2, sTab[r.lin0 - ljb]);
-    float v10 = fmaf(sc[nt][2], scale2, sTab[r.lin1 - lja]), v11 = fmaf(sc[nt][3], scale2, sTab[r.lin1 - ljb]);
+    const char* tb = reinterpret_cast<const char*>(sTab);
+    float v00 = fmaf(sc[nt][0], scale2, *reinterpret_cast<const float*>(tb + (r.lin0 - lja)));
+    float v01 = fmaf(sc[nt][1], scale2, *reinterpret_cast<const float*>(tb + (r.lin0 - ljb)));
+    float v10 = fmaf(sc[nt][2], scale2, *reinterpret_cast<const float*>(tb + (r.lin1 - lja)));
+    float v11 = fmaf(sc[nt][3], scale2, *reinterpret_cast<const float*>(tb + (r.lin1 - ljb)));
     if (MASK) {
       const unsigned short rj2 = *reinterpret_cast<const unsigned short*>(sReg + j);
       const int rja = rj2 & 0xff, rjb = rj2 >> 8;
@@ -192,14 +306,14 @@ __device__ __forceinline__ void att_step32(const uint32_t (&qa)[4], AttRow& r, i
   mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
   const float mn0 = fmaxf(r.m0, mx0), mn1 = fmaxf(r.m1, mx1);
-  const float c0 = exp2f(r.m0 - mn0), c1 = exp2f(r.m1 - mn1);
+  const float c0 = ex2_approx(r.m0 - mn0), c1 = ex2_approx(r.m1 - mn1);
   r.m0 = mn0; r.m1 = mn1;
   float ps0 = 0.f, ps1 = 0.f;
   uint32_t pa[2][4];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    const float p00 = exp2f(sc[nt][0] - mn0), p01 = exp2f(sc[nt][1] - mn0);
-    const float p10 = exp2f(sc[nt][2] - mn1), p11 = exp2f(sc[nt][3] - mn1);
+    const float p00 = ex2_approx(sc[nt][0] - mn0), p01 = ex2_approx(sc[nt][1] - mn0);
+    const float p10 = ex2_approx(sc[nt][2] - mn1), p11 = ex2_approx(sc[nt][3] - mn1);
     ps0 += p00 + p01; ps1 += p10 + p11;
     pa[nt >> 1][(nt & 1) * 2] = pack_h2(p00, p01);       // a0 / a2: row r0
     pa[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p10, p11);   // a1 / a3: row r1
@@ -253,7 +367,7 @@ __global__ void __launch_bounds__(256) window_attention_nc8_kernel(const __half*
   for (int i = threadIdx.x; i < npad; i += blockDim.x) {
     const int td = i / (ws1 * ws2), th = (i / ws2) % ws1, tw = i % ws2;
     // padded keys (i >= n) are masked by the TAIL step; their index only has to stay inside the table
-    sLin[i] = (unsigned short)(i < n ? td * s0 + th * s1 + tw : 0);
+    sLin[i] = (unsigned short)(i < n ? 4 * (td * s0 + th * s1 + tw) : 0);   // byte offset into the fp32 table
     sReg[i] = (MASK && i < n) ? (unsigned char)region[(long long)w * n + i] : 0;
   }
   __syncthreads();
@@ -277,7 +391,7 @@ __global__ void __launch_bounds__(256) window_attention_nc8_kernel(const __half*
       qa[3] = *reinterpret_cast<const uint32_t*>(base + ((long long)(2 * h + 1) * T + row0 + r1) * 8 + 2 * t4);
     }
     AttRow r;
-    r.lin0 = sLin[min(r0, npad - 1)] + lin_c; r.lin1 = sLin[min(r1, npad - 1)] + lin_c;
+    r.lin0 = sLin[min(r0, npad - 1)] + 4 * lin_c; r.lin1 = sLin[min(r1, npad - 1)] + 4 * lin_c;
     r.reg0 = sReg[min(r0, npad - 1)]; r.reg1 = sReg[min(r1, npad - 1)];
     r.m0 = r.m1 = -INFINITY; r.l0 = r.l1 = 0.f;
 #pragma unroll
@@ -415,16 +529,116 @@ __global__ void __launch_bounds__(256) head_conv_nc8_kernel(const __half* __rest
     if (o < Cout) io<TO>::st(y + ((long long)n * Cout + o) * S + r, acc[o]);
 }
 
+// Output head fused with the tail of the last residual block (UnetResBlock.forward, dynunet_block.py:97-111, followed by
+// UnetOutBlock): y = W * lrelu(instnorm(x) + instnorm?(res)) + b.  The normalised activation never goes to HBM.
+struct HeadNormP {
+  const __half* x; const __half* res; const float* stats; const float* res_stats; const float* wgt; const float* bias; void* y;
+  int C, Cout, res_ctot, res_coff;
+  long long S;
+  float eps, slope;
+};
+
+// CO = compile-time bound on the output channels (registers and FMAs are spent on CO, not on the ABI maximum of 16)
+template <typename TO, int CO>
+__global__ void __launch_bounds__(256) head_conv_norm_nc8_kernel(HeadNormP p) {
+  extern __shared__ float s_hn[];  // [Cout][C] weights, then scale, shift, res scale, res shift [C] each
+  float* s_sc = s_hn + p.Cout * p.C;
+  float* s_sh = s_sc + p.C;
+  float* s_rsc = s_sh + p.C;
+  float* s_rsh = s_rsc + p.C;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < p.Cout * p.C; i += blockDim.x) s_hn[i] = p.wgt[i];
+  const float invS = 1.f / (float)p.S;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    // same statistics arithmetic as norm_act_nc8_kernel
+    const float s = p.stats[2 * (n * p.C + c)], q = p.stats[2 * (n * p.C + c) + 1];
+    const float mean = s * invS, var = fmaxf(q * invS - mean * mean, 0.f), rstd = 1.f / sqrtf(var + p.eps);
+    s_sc[c] = rstd; s_sh[c] = -mean * rstd;
+    float rsc = 1.f, rsh = 0.f;
+    if (p.res_stats) {
+      const float rs = p.res_stats[2 * (n * p.C + c)], rq = p.res_stats[2 * (n * p.C + c) + 1];
+      const float rmean = rs * invS, rvar = fmaxf(rq * invS - rmean * rmean, 0.f), rrstd = 1.f / sqrtf(rvar + p.eps);
+      rsc = rrstd; rsh = -rmean * rrstd;
+    }
+    s_rsc[c] = rsc; s_rsh[c] = rsh;
+  }
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.S) return;
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = (o < p.Cout && p.bias) ? p.bias[o] : 0.f;
+  const __half* xi = p.x + ((long long)n * (p.C / 8) * p.S + r) * 8;
+  const __half* ri = p.res ? p.res + (((long long)n * (p.res_ctot / 8) + p.res_coff / 8) * p.S + r) * 8 : nullptr;
+  auto lds8 = [](const float* s, float (&v)[8]) {   // two 16-byte broadcast reads
+    const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  };
+  for (int c = 0; c < p.C / 8; ++c) {
+    float f[8], k0[8], k1[8];
+    cvt8(__ldg(reinterpret_cast<const uint4*>(xi + (long long)c * p.S * 8)), f);
+    lds8(s_sc + c * 8, k0); lds8(s_sh + c * 8, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], k0[j], k1[j]);
+    if (ri) {
+      float g[8];
+      cvt8(__ldg(reinterpret_cast<const uint4*>(ri + (long long)c * p.S * 8)), g);
+      lds8(s_rsc + c * 8, k0); lds8(s_rsh + c * 8, k1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += fmaf(g[j], k0[j], k1[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * p.slope;
+#pragma unroll
+    for (int o = 0; o < CO; ++o)
+      if (o < p.Cout) {
+        lds8(s_hn + o * p.C + c * 8, k0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] = fmaf(f[j], k0[j], acc[o]);
+      }
+  }
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+    if (o < p.Cout) io<TO>::st((TO*)p.y + ((long long)n * p.Cout + o) * p.S + r, acc[o]);
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_head_conv_norm_nc8(const void* x, int N, int C, long long S, const float* stats, float eps, const void* res,
+                                       int res_ctot, int res_coff, const float* res_stats, float slope, const float* weight,
+                                       const float* bias, int Cout, void* y, int out_dtype, void* stream) {
+  B200_REQUIRE(x && y && weight && stats, "head_conv_norm_nc8: null pointer");
+  B200_REQUIRE(C % 8 == 0 && Cout >= 1 && Cout <= 16, "head_conv_norm_nc8: C must be a multiple of 8 and Cout <= 16 (got %d, %d)", C, Cout);
+  B200_REQUIRE(!res || (res_ctot % 8 == 0 && res_coff % 8 == 0 && res_coff + C <= res_ctot), "head_conv_norm_nc8: bad residual channel slice");
+  B200_REQUIRE(res || !res_stats, "head_conv_norm_nc8: residual statistics without a residual");
+  HeadNormP p{(const __half*)x, (const __half*)res, stats, res_stats, weight, bias, y, C, Cout, res_ctot, res_coff, S, eps, slope};
+  dim3 grid(ceil_div(S, 256), N);
+  const size_t smem = ((size_t)Cout * C + 4 * (size_t)C) * sizeof(float);
+  B200_REQUIRE(smem <= 48 * 1024, "head_conv_norm_nc8: C too large (%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LHN(TO) do { if (Cout <= 2) head_conv_norm_nc8_kernel<TO, 2><<<grid, 256, smem, st>>>(p); \
+                     else if (Cout <= 4) head_conv_norm_nc8_kernel<TO, 4><<<grid, 256, smem, st>>>(p); \
+                     else head_conv_norm_nc8_kernel<TO, 16><<<grid, 256, smem, st>>>(p); } while (0)
+  if (out_dtype == B200_DT_F16) LHN(__half);
+  else if (out_dtype == B200_DT_F32) LHN(float);
+  else return set_err(B200_ERR_INVALID, "head_conv_norm_nc8: bad dtype");
+#undef LHN
+  B200_LAUNCH_CHECK("head_conv_norm_nc8_kernel");
+  return B200_OK;
+}
 
 extern "C" int b200_layernorm_nc8(const void* x, int N, int C, long long S_in, const int32_t* src, long long S_out,
                                   const float* gamma, const float* beta, float eps, void* y, void* stream) {
   B200_REQUIRE(x && y, "layernorm_nc8: null pointer");
   B200_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && S_in > 0 && S_out > 0, "layernorm_nc8: bad sizes");
   dim3 grid(ceil_div(S_out, 256), N);
-  layernorm_nc8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, C, S_in, src, S_out, gamma, beta, eps);
+  B200_REQUIRE((!gamma || reinterpret_cast<uintptr_t>(gamma) % 16 == 0) && (!beta || reinterpret_cast<uintptr_t>(beta) % 16 == 0),
+               "layernorm_nc8: gamma / beta must be 16-byte aligned");
+#define LLN(K) layernorm_nc8_kernel<K><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, C, S_in, src, S_out, gamma, beta, eps)
+  if (C == 48) LLN(6); else LLN(0);
+#undef LLN
   B200_LAUNCH_CHECK("layernorm_nc8_kernel");
   return B200_OK;
 }
@@ -435,7 +649,15 @@ extern "C" int b200_patch_merge_ln_nc8(const void* x, int N, int C, int D, int H
   B200_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && D > 0 && H > 0 && W > 0, "patch_merge_ln_nc8: bad sizes");
   const long long S2 = (long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
   dim3 grid(ceil_div(S2, 128), N);
-  patch_merge_ln_nc8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, C, D, H, W, gamma, beta, eps, v2);
+  B200_REQUIRE((!gamma || reinterpret_cast<uintptr_t>(gamma) % 16 == 0) && (!beta || reinterpret_cast<uintptr_t>(beta) % 16 == 0),
+               "patch_merge_ln_nc8: gamma / beta must be 16-byte aligned");
+  if (C == 48 || C == 96) {
+    dim3 g8(ceil_div(S2, 32), N);
+    if (C == 48) patch_merge_ln8_nc8_kernel<6><<<g8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, D, H, W, gamma, beta, eps, v2);
+    else patch_merge_ln8_nc8_kernel<12><<<g8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, D, H, W, gamma, beta, eps, v2);
+  } else {
+    patch_merge_ln_nc8_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, C, D, H, W, gamma, beta, eps, v2);
+  }
   B200_LAUNCH_CHECK("patch_merge_ln_nc8_kernel");
   return B200_OK;
 }
@@ -450,7 +672,7 @@ extern "C" int b200_window_attention_nc8(const void* qkv, int N, int C, int head
   B200_REQUIRE(heads <= 65535 && N <= 65535, "window_attention_nc8: grid too large");
   const int npad = (n + 31) / 32 * 32;
   const int tab_len = (2 * ws0 - 1) * (2 * ws1 - 1) * (2 * ws2 - 1);
-  B200_REQUIRE(tab_len < 32768, "window_attention_nc8: relative position table too large");
+  B200_REQUIRE(tab_len < 16384, "window_attention_nc8: relative position table too large");   // byte offsets are kept in 16 bits
   const size_t smem = (size_t)npad * kAttKStride * 2 + (size_t)16 * (npad + 8) * 2 + (size_t)tab_len * 4 + (size_t)npad * 2 + npad + 16;
   B200_REQUIRE(smem <= 200 * 1024, "window_attention_nc8: window of %d tokens does not fit in shared memory", n);
   auto kern = region ? window_attention_nc8_kernel<true> : window_attention_nc8_kernel<false>;

@@ -354,8 +354,10 @@ class SwinUNETR(GraphedForward, nn.Module):
 
     # ------------------------------------------------------------------------------------------------- sub-graphs
     def _res_block(self, x: K.NC8, cin: int, in_coff: int, blk: UnetResBlock, key: str, out: K.NC8 | None = None, out_coff: int = 0,
-                   x_in_raw: torch.Tensor | None = None) -> K.NC8:
-        """UnetResBlock.forward (dynunet_block.py:97-111) on NC8 buffers; `out` may be a slice of a concat buffer."""
+                   x_in_raw: torch.Tensor | None = None, defer_tail: bool = False):
+        """UnetResBlock.forward (dynunet_block.py:97-111) on NC8 buffers; `out` may be a slice of a concat buffer.
+        With `defer_tail` the final norm2 + residual + lrelu is NOT applied: the pieces (y2, stats2, res, res_coff,
+        res_stats) are returned so that the consumer (the output head) applies them on its operand load."""
         cout = blk.conv1.conv.out_channels
         if x_in_raw is not None:  # single input channel: direct stem kernels read the raw NCDHW window
             y1, st1 = K.conv_cin1_nc8(x_in_raw, blk.conv1.conv.weight, None, 3, 1, 1, want_stats=True)
@@ -363,13 +365,25 @@ class SwinUNETR(GraphedForward, nn.Module):
             y1, st1 = K.conv3x3x3_tc(x, self._w3(blk.conv1.conv, key + ".c1"), cin, cout, in_coff=in_coff, want_stats=True)
         K.norm_act_nc8(y1, cout, st1, act=L.ACT_LEAKY, slope=0.01, out=y1)
         y2, st2 = K.conv3x3x3_tc(y1, self._w3(blk.conv2.conv, key + ".c2"), cout, cout, want_stats=True)
-        if out is None:
-            out = K.NC8(y2.N, cout, y2.sp, y2.buf.device)
         if hasattr(blk, "conv3"):
+            if x_in_raw is not None and x_in_raw.dtype == torch.float16 and blk.conv3.conv.bias is None and not defer_tail:
+                # one input channel: norm3(conv3(u)) is an affine function of u per channel -- no conv3 launch, no y3 tensor
+                if out is None:
+                    out = K.NC8(y2.N, cout, y2.sp, y2.buf.device)
+                K.norm_act_cin1res_nc8(y2, cout, st2, x_in_raw, K.instnorm_stats(x_in_raw), blk.conv3.conv.weight, act=L.ACT_LEAKY, slope=0.01,
+                                       out=out, out_coff=out_coff)
+                return out
             if x_in_raw is not None:
                 y3, st3 = K.conv_cin1_nc8(x_in_raw, blk.conv3.conv.weight, None, 1, 1, 0, want_stats=True)
             else:
                 y3, st3 = K.gemm_tc(x, self._wlin(blk.conv3.conv.weight, key + ".c3"), cin, cout, in_coff=in_coff, want_stats=True)
+            if defer_tail:
+                return y2, st2, y3, 0, st3
+        elif defer_tail:
+            return y2, st2, x, in_coff, None
+        if out is None:
+            out = K.NC8(y2.N, cout, y2.sp, y2.buf.device)
+        if hasattr(blk, "conv3"):
             K.norm_act_nc8(y2, cout, st2, res=y3, res_stats=st3, act=L.ACT_LEAKY, slope=0.01, out=out, out_coff=out_coff)
         else:
             K.norm_act_nc8(y2, cout, st2, res=x, res_coff=in_coff, act=L.ACT_LEAKY, slope=0.01, out=out, out_coff=out_coff)
@@ -461,15 +475,16 @@ class SwinUNETR(GraphedForward, nn.Module):
             dec4 = self._res_block(h4, 16 * fs, 0, self.encoder10.layer, "enc10")
 
             # ---- decoders: ConvTranspose k2 s2 scatter into the concat buffer, then the residual block
-            def up(dec_in: K.NC8, cin: int, block: UnetrUpBlock, cat: K.NC8, key: str) -> K.NC8:
+            def up(dec_in: K.NC8, cin: int, block: UnetrUpBlock, cat: K.NC8, key: str, defer_tail: bool = False):
                 cout = block.transp_conv.conv.out_channels
                 K.gemm_tc(dec_in, self._wup(block.transp_conv.conv, key), cin, 8 * cout, out=cat, out_coff=0, mode=2)
-                return self._res_block(cat, 2 * cout, 0, block.conv_block, key + ".rb")
+                return self._res_block(cat, 2 * cout, 0, block.conv_block, key + ".rb", defer_tail=defer_tail)
 
             dec3 = up(dec4, 16 * fs, self.decoder5, cat5, "dec5")
             dec2 = up(dec3, 8 * fs, self.decoder4, cat4, "dec4")
             dec1 = up(dec2, 4 * fs, self.decoder3, cat3, "dec3")
             dec0 = up(dec1, 2 * fs, self.decoder2, cat2, "dec2")
-            outb = up(dec0, fs, self.decoder1, cat1, "dec1")
+            # decoder1's norm2 + residual + lrelu is applied by the output head on its operand load (one pass less over 96^3 x 48)
+            y2, st2, res, res_coff, res_st = up(dec0, fs, self.decoder1, cat1, "dec1", defer_tail=True)
             oc = self.out.conv.conv
-            return K.head_conv_nc8(outb, oc.weight, oc.bias, out_dtype=x_in.dtype)
+            return K.head_conv_norm_nc8(y2, st2, res, res_coff, res_st, 0.01, 1e-5, oc.weight, oc.bias, out_dtype=x_in.dtype)

@@ -137,6 +137,33 @@ def test_cin1_stem_and_head():
     assert _rel(got.cpu().numpy(), ref.numpy()) < 1e-3
 
 
+def test_fused_residual_tail_kernels():
+    """head_conv_norm_nc8 (norm2 + residual + lrelu + 1x1x1 head in one pass) and norm_act_cin1res_nc8 (the one-channel
+    residual branch evaluated analytically) against the unfused formulation in torch fp32."""
+    g = torch.Generator().manual_seed(11)
+    N, C, sp = 2, 48, (6, 10, 12)
+    y2 = (torch.randn((N, C, *sp), generator=g) * 1.7 + 0.3).half()
+    y3 = (torch.randn((N, C, *sp), generator=g) * 0.6 - 0.2).half()
+    w = torch.randn((2, C, 1, 1, 1), generator=g) / C**0.5
+    b = torch.randn(2, generator=g)
+    y2n, y3n = _to_nc8(y2), _to_nc8(y3)
+    st2, st3 = K.instnorm_stats(y2.to(DEV)), K.instnorm_stats(y3.to(DEV))
+    t = F.leaky_relu(F.instance_norm(y2.float()) + F.instance_norm(y3.float()), 0.01)
+    ref = F.conv3d(t, w, b)
+    got = K.head_conv_norm_nc8(y2n, st2, y3n, 0, st3, 0.01, 1e-5, w.to(DEV), b.to(DEV), out_dtype=torch.float32)
+    assert _rel(got.cpu().numpy(), ref.numpy()) < 3e-3
+    # identity residual (no conv3 branch): res added as is
+    ref_id = F.conv3d(F.leaky_relu(F.instance_norm(y2.float()) + y3.float(), 0.01), w, b)
+    got_id = K.head_conv_norm_nc8(y2n, st2, y3n, 0, None, 0.01, 1e-5, w.to(DEV), b.to(DEV), out_dtype=torch.float16)
+    assert _rel(got_id.float().cpu().numpy(), ref_id.numpy()) < 5e-3
+    # one-channel residual branch: instnorm(conv1x1x1(u)) == alpha_c * u + beta_c
+    u = (torch.randn((N, 1, *sp), generator=g) * 2.0 + 0.5).half()
+    w3 = torch.randn((C, 1, 1, 1, 1), generator=g)
+    ref_c = F.leaky_relu(F.instance_norm(y2.float()) + F.instance_norm(F.conv3d(u.float(), w3)), 0.01)
+    got_c = K.norm_act_cin1res_nc8(y2n, C, st2, u.to(DEV), K.instnorm_stats(u.to(DEV)), w3.to(DEV), act=L.ACT_LEAKY, slope=0.01)
+    assert _rel(K.unpack_nc8(got_c).float().cpu().numpy(), ref_c.numpy()) < 3e-3
+
+
 def _build():
     with contextlib.redirect_stdout(io.StringIO()):
         net = SwinUNETR(in_channels=1, out_channels=2, feature_size=48)
