@@ -82,6 +82,9 @@ __global__ void __launch_bounds__(256) unpack_nc8_kernel(const __half* __restric
 // ----------------------------------------------------------------------------------------------------------
 __host__ __device__ inline int conv_tc_nt(int Cout) {
   if (Cout <= 128) return Cout;
+  // very wide layers sit at the bottom of the networks (a few voxels per item): narrow N tiles there, so that enough CTAs
+  // stream the weights in parallel (the layer is bound by weight bandwidth per SM, not by the tensor pipe)
+  if (Cout >= 384 && Cout % 64 == 0) return 64;
   for (int nt = 128; nt >= 16; nt -= 16)
     if (Cout % nt == 0) return nt;
   return 16;

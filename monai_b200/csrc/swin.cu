@@ -119,74 +119,17 @@ __global__ void __launch_bounds__(256) layernorm_nc8_kernel(const __half* __rest
 __constant__ int kMergeV1[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
 __constant__ int kMergeV2[8][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {1, 0, 0}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1}};
 
-// One thread per merged token: the 2x2x2 neighbourhood (8 C channels) is read once for the mean, and the centred
-// variance and output passes re-read it from L1 (KC8 > 0 unrolls the channel loop so the 16-byte loads are batched).
-template <int KC8>
-__global__ void __launch_bounds__(128) patch_merge_ln_nc8_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C, int D,
-                                                                 int H, int W, const float* __restrict__ gamma,
-                                                                 const float* __restrict__ beta, float eps, int v2) {
-  const int D2 = (D + 1) / 2, H2 = (H + 1) / 2, W2 = (W + 1) / 2;
-  const long long S2 = (long long)D2 * H2 * W2, S = (long long)D * H * W;
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= S2) return;
-  const int n = blockIdx.y, C8 = KC8 > 0 ? KC8 : C / 8;
-  const int w2 = (int)(r % W2), h2 = (int)((r / W2) % H2), d2 = (int)(r / ((long long)W2 * H2));
-  const __half* xn = x + (long long)n * C8 * S * 8;
-  long long off[8]; bool ok[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int* o = v2 ? kMergeV2[q] : kMergeV1[q];
-    const int d = 2 * d2 + o[0], h = 2 * h2 + o[1], w = 2 * w2 + o[2];
-    ok[q] = d < D && h < H && w < W;
-    off[q] = ok[q] ? (((long long)d * H + h) * W + w) * 8 : 0;
-  }
-  const float invC = 1.f / (8.f * (float)(8 * C8));
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  float sum = 0.f;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-#pragma unroll 6
-    for (int c = 0; c < C8; ++c) {
-      float f[8];
-      cvt8(ok[q] ? __ldg(reinterpret_cast<const uint4*>(xn + (long long)c * S * 8 + off[q])) : zero, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += f[j];
-    }
-  }
-  const float mean = sum * invC;
-  float var = 0.f;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-#pragma unroll 6
-    for (int c = 0; c < C8; ++c) {
-      float f[8];
-      cvt8(ok[q] ? __ldg(reinterpret_cast<const uint4*>(xn + (long long)c * S * 8 + off[q])) : zero, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float dd = f[j] - mean; var = fmaf(dd, dd, var); }
-    }
-  }
-  const float rstd = 1.f / sqrtf(var * invC + eps);
-  __half* yo = y + ((long long)n * (8 * C8) * S2 + r) * 8;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-#pragma unroll 6
-    for (int c = 0; c < C8; ++c) {
-      const uint4 raw = ok[q] ? __ldg(reinterpret_cast<const uint4*>(xn + (long long)c * S * 8 + off[q])) : zero;
-      *reinterpret_cast<uint4*>(yo + (long long)(q * C8 + c) * S2 * 8) = ln_apply8(raw, mean, rstd, gamma, beta, (q * C8 + c) * 8);
-    }
-  }
-}
-
 // Eight lanes per merged token (lane & 7 = neighbour q): every lane keeps its neighbour's C = 8*KC8 channels in registers
 // as raw 16-byte vectors, the statistics are reduced over the 8 lanes with three shuffles, and each lane writes its own
 // channel block (q*C .. q*C+C) of the output token.  One global read, one write; a warp's loads cover 4 (d,h) rows x 8
 // consecutive voxels = four full 128-byte lines per instruction.
 template <int KC8>
-__global__ void __launch_bounds__(256, 2) patch_merge_ln8_nc8_kernel(const __half* __restrict__ x, __half* __restrict__ y, int D, int H,
-                                                                  int W, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  float eps, int v2) {
+__global__ void __launch_bounds__(256, 2) patch_merge_ln8_nc8_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C, int D,
+                                                                     int H, int W, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float eps, int v2) {
   const int D2 = (D + 1) / 2, H2 = (H + 1) / 2, W2 = (W + 1) / 2;
   const long long S2 = (long long)D2 * H2 * W2, S = (long long)D * H * W;
+  const int C8 = KC8 > 0 ? KC8 : C / 8;
   const int q = threadIdx.x & 7;
   const long long r_raw = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
   const bool tok_ok = r_raw < S2;
@@ -196,15 +139,90 @@ __global__ void __launch_bounds__(256, 2) patch_merge_ln8_nc8_kernel(const __hal
   const int* o = v2 ? kMergeV2[q] : kMergeV1[q];
   const int d = 2 * d2 + o[0], h = 2 * h2 + o[1], w = 2 * w2 + o[2];
   const bool ok = d < D && h < H && w < W;      // odd sizes: the reference pads with zeros, which enter the statistics
-  const __half* xi = x + ((long long)n * KC8 * S + (((long long)d * H + h) * W + w)) * 8;
-  uint4 raw[KC8];
+  const __half* xi = x + ((long long)n * C8 * S + (ok ? (((long long)d * H + h) * W + w) : 0)) * 8;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const float invC = 1.f / (float)(8 * 8 * C8);
+  __half* yo = y + ((long long)n * (8 * C8) * S2 + r) * 8;
+  if (KC8 > 0) {
+    uint4 raw[KC8 > 0 ? KC8 : 1];
 #pragma unroll
-  for (int c = 0; c < KC8; ++c) raw[c] = ok ? __ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S * 8)) : make_uint4(0, 0, 0, 0);
-  const float invC = 1.f / (float)(8 * 8 * KC8);
+    for (int c = 0; c < KC8; ++c) raw[c] = ok ? __ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S * 8)) : zero;
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < KC8; ++c) {
+      float f[8]; cvt8(raw[c], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float mean = sum * invC;
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < KC8; ++c) {
+      float f[8]; cvt8(raw[c], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float dd = f[j] - mean; var = fmaf(dd, dd, var); }
+    }
+    var += __shfl_xor_sync(0xffffffffu, var, 1); var += __shfl_xor_sync(0xffffffffu, var, 2); var += __shfl_xor_sync(0xffffffffu, var, 4);
+    const float rstd = 1.f / sqrtf(var * invC + eps);
+    if (!tok_ok) return;
+#pragma unroll
+    for (int c = 0; c < KC8; ++c)
+      *reinterpret_cast<uint4*>(yo + (long long)(q * KC8 + c) * S2 * 8) = ln_apply8(raw[c], mean, rstd, gamma, beta, (q * KC8 + c) * 8);
+  } else {
+    // wide channels (deep stages, few tokens): the lane re-reads its neighbour (L1 / L2 hits), loads unrolled by four
+    float sum = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C8; ++c) {
+      float f[8]; cvt8(ok ? __ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S * 8)) : zero, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float mean = sum * invC;
+    float var = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C8; ++c) {
+      float f[8]; cvt8(ok ? __ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S * 8)) : zero, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float dd = f[j] - mean; var = fmaf(dd, dd, var); }
+    }
+    var += __shfl_xor_sync(0xffffffffu, var, 1); var += __shfl_xor_sync(0xffffffffu, var, 2); var += __shfl_xor_sync(0xffffffffu, var, 4);
+    const float rstd = 1.f / sqrtf(var * invC + eps);
+    if (!tok_ok) return;
+#pragma unroll 4
+    for (int c = 0; c < C8; ++c) {
+      const uint4 raw = ok ? __ldg(reinterpret_cast<const uint4*>(xi + (long long)c * S * 8)) : zero;
+      *reinterpret_cast<uint4*>(yo + (long long)(q * C8 + c) * S2 * 8) = ln_apply8(raw, mean, rstd, gamma, beta, (q * C8 + c) * 8);
+    }
+  }
+}
+
+// LayerNorm with eight lanes per token for wide channels (C8 % 8 == 0, C8 / 8 <= 12: C = 64 .. 768): lane j keeps chunks
+// j, j+8, ... in registers.  The deep stages have few tokens, so one thread per token would leave most of the chip idle
+// behind a serial chain of 3 * C/8 loads.
+template <int PER>
+__global__ void __launch_bounds__(256) layernorm8_nc8_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long S_in,
+                                                             const int* __restrict__ src, long long S_out,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  constexpr int C8 = PER * 8;
+  const int j8 = threadIdx.x & 7;
+  const long long r_raw = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const bool tok_ok = r_raw < S_out;
+  const long long r = tok_ok ? r_raw : S_out - 1;
+  const int n = blockIdx.y;
+  const long long s = src ? (long long)__ldg(src + r) : r;
+  __half* yo = y + ((long long)n * C8 * S_out + r) * 8;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 raw[PER];
+  const __half* xi = x + ((long long)n * C8 * S_in + (s < 0 ? 0 : s)) * 8;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) raw[i] = s < 0 ? zero : __ldg(reinterpret_cast<const uint4*>(xi + (long long)(i * 8 + j8) * S_in * 8));
+  const float invC = 1.f / (float)(8 * C8);
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < KC8; ++c) {
-    float f[8]; cvt8(raw[c], f);
+  for (int i = 0; i < PER; ++i) {
+    float f[8]; cvt8(raw[i], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum += f[j];
   }
@@ -212,18 +230,20 @@ __global__ void __launch_bounds__(256, 2) patch_merge_ln8_nc8_kernel(const __hal
   const float mean = sum * invC;
   float var = 0.f;
 #pragma unroll
-  for (int c = 0; c < KC8; ++c) {
-    float f[8]; cvt8(raw[c], f);
+  for (int i = 0; i < PER; ++i) {
+    float f[8]; cvt8(raw[i], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { const float dd = f[j] - mean; var = fmaf(dd, dd, var); }
   }
   var += __shfl_xor_sync(0xffffffffu, var, 1); var += __shfl_xor_sync(0xffffffffu, var, 2); var += __shfl_xor_sync(0xffffffffu, var, 4);
   const float rstd = 1.f / sqrtf(var * invC + eps);
   if (!tok_ok) return;
-  __half* yo = y + ((long long)n * (8 * KC8) * S2 + r) * 8;
 #pragma unroll
-  for (int c = 0; c < KC8; ++c)
-    *reinterpret_cast<uint4*>(yo + (long long)(q * KC8 + c) * S2 * 8) = ln_apply8(raw[c], mean, rstd, gamma, beta, (q * KC8 + c) * 8);
+  for (int i = 0; i < PER; ++i) {
+    const int c = i * 8 + j8;
+    // padded token (s < 0): exact zeros, as F.pad after norm1 (swin_unetr.py:603-606)
+    *reinterpret_cast<uint4*>(yo + (long long)c * S_out * 8) = s < 0 ? zero : ln_apply8(raw[i], mean, rstd, gamma, beta, c * 8);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- window attention
@@ -637,8 +657,14 @@ extern "C" int b200_layernorm_nc8(const void* x, int N, int C, long long S_in, c
   B200_REQUIRE((!gamma || reinterpret_cast<uintptr_t>(gamma) % 16 == 0) && (!beta || reinterpret_cast<uintptr_t>(beta) % 16 == 0),
                "layernorm_nc8: gamma / beta must be 16-byte aligned");
 #define LLN(K) layernorm_nc8_kernel<K><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, C, S_in, src, S_out, gamma, beta, eps)
-  if (C == 48) LLN(6); else LLN(0);
+#define LL8(P) layernorm8_nc8_kernel<P><<<dim3(ceil_div(S_out, 32), N), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, S_in, src, S_out, gamma, beta, eps)
+  if (C == 48) LLN(6);
+  else if (C == 192) LL8(3);
+  else if (C == 384) LL8(6);
+  else if (C == 768) LL8(12);
+  else LLN(0);
 #undef LLN
+#undef LL8
   B200_LAUNCH_CHECK("layernorm_nc8_kernel");
   return B200_OK;
 }
@@ -648,16 +674,12 @@ extern "C" int b200_patch_merge_ln_nc8(const void* x, int N, int C, int D, int H
   B200_REQUIRE(x && y, "patch_merge_ln_nc8: null pointer");
   B200_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && D > 0 && H > 0 && W > 0, "patch_merge_ln_nc8: bad sizes");
   const long long S2 = (long long)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2);
-  dim3 grid(ceil_div(S2, 128), N);
   B200_REQUIRE((!gamma || reinterpret_cast<uintptr_t>(gamma) % 16 == 0) && (!beta || reinterpret_cast<uintptr_t>(beta) % 16 == 0),
                "patch_merge_ln_nc8: gamma / beta must be 16-byte aligned");
-  if (C == 48 || C == 96) {
-    dim3 g8(ceil_div(S2, 32), N);
-    if (C == 48) patch_merge_ln8_nc8_kernel<6><<<g8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, D, H, W, gamma, beta, eps, v2);
-    else patch_merge_ln8_nc8_kernel<12><<<g8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, D, H, W, gamma, beta, eps, v2);
-  } else {
-    patch_merge_ln_nc8_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, C, D, H, W, gamma, beta, eps, v2);
-  }
+  dim3 g8(ceil_div(S2, 32), N);
+#define LPM(K) patch_merge_ln8_nc8_kernel<K><<<g8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, C, D, H, W, gamma, beta, eps, v2)
+  if (C == 48) LPM(6); else if (C == 96) LPM(12); else LPM(0);
+#undef LPM
   B200_LAUNCH_CHECK("patch_merge_ln_nc8_kernel");
   return B200_OK;
 }
