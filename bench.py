@@ -40,6 +40,11 @@ WORKLOADS = {
         vol=(512, 512, 512), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=8, net="swin48", windows=1000,
         flop_per_window=636e9,
     ),
+    # BASELINE.json configs[3]
+    "transforms_c4": dict(
+        desc="Spacingd(1.25mm->1mm, bilinear) + RandAffined(prob 1, rotate .2, scale .1, translate 5, border) + GaussianSmoothd(sigma 1) on 32 x (1,256^3) fp32 MetaTensors",
+        vol=(256, 256, 256), volumes=32, net=None,
+    ),
 }
 
 
@@ -199,6 +204,144 @@ def cpu_baseline_leg(wl, budget_s: float = 20.0) -> dict:
                       f"seconds/window extrapolated to {wl['windows']} windows"}
 
 
+def _transform_pipeline():
+    from monai_b200.transforms import Compose, GaussianSmoothd, RandAffined, Spacingd
+
+    pipe = Compose([
+        Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear"),
+        RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border"),
+        GaussianSmoothd(keys=["image"], sigma=1.0),
+    ])
+    pipe.transforms[1].set_random_state(seed=0)
+    return pipe
+
+
+def run_transforms(args, wl):
+    """Config C4: the spatial pre-processing pipeline on a batch of volumes; replicas-only across GPUs
+    (DESIGN.md section 5), so N ranks each process the full batch and `value` is the aggregate."""
+    from monai_b200 import _kernels as K
+    from monai_b200 import _lib
+    from monai_b200.data import MetaTensor
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")
+    _lib.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    nvol, shape = wl["volumes"], wl["vol"]
+    aff = torch.diag(torch.tensor([1.25, 1.25, 1.25, 1.0], dtype=torch.float64))
+    g = torch.Generator().manual_seed(0)
+    host = [torch.rand((1, *shape), generator=g).pin_memory() for _ in range(nvol)]
+    dev_vols = [h.to(dev) for h in host]
+    pipe = _transform_pipeline()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out_host = None
+
+    def step_resident():
+        for v in dev_vols:
+            y = pipe({"image": MetaTensor(v, affine=aff)})["image"]
+        return y
+
+    def step_e2e():
+        nonlocal out_host
+        for h in host:
+            y = pipe({"image": MetaTensor(h.to(dev, non_blocking=True), affine=aff)})["image"]
+            if out_host is None:
+                out_host = torch.empty(tuple(y.shape), dtype=y.dtype).pin_memory()
+            out_host.copy_(y, non_blocking=True)
+        return y
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    launches = (_lib.launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if sampler else {}
+    ms_e2e = timed(step_e2e, args.steps, 1)
+    K.profile_start()
+    y = step_resident()
+    prof = K.profile_stop()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    nvox = float(np.prod(shape)) * nvol * world
+    ms_step = ms_total / args.steps
+    name, st = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    avg_ms = st["ms"] / max(1, st["n"])
+    ach = st.get("bytes", 0.0) / max(1, st["n"]) / (avg_ms * 1e-3) / 1e9
+    line = {
+        "metric": "voxels/sec spatial transform pipeline (input voxels)", "value": nvox / (ms_step * 1e-3), "unit": "voxels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "volumes_per_step": nvol, "output_shape": list(y.shape), "l2": "256 MiB flush write between timed steps",
+                   "parallelism": f"replicas x{world}" if world > 1 else "single GPU"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": nvox / (ms_e2e / args.steps * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": sum(h.numel() * 4 for h in host),
+                "d2h_bytes_per_step": int(out_host.numel() * 4 * nvol)},
+        "roofline": {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+                     "peak_source": pk["src"], "launches": st["n"], "avg_launch_ms": avg_ms,
+                     "share_of_kernel_time": st["ms"] / (sum(v["ms"] for v in prof.values()) or 1.0)},
+        "kernels": {k: {"ms": round(v["ms"], 4), "n": v["n"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = transforms_cpu_leg(wl)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def transforms_cpu_leg(wl, volumes: int = 1) -> dict:
+    """The oracle's torch-CPU restatement of the same three transforms on `volumes` full-size volumes."""
+    from oracle import transforms as otr
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(min(cores, int(os.environ.get("B200_REF_THREADS", "32"))))
+    aff = np.diag([1.25, 1.25, 1.25, 1.0])
+    g = torch.Generator().manual_seed(0)
+    t0 = time.perf_counter()
+    for i in range(volumes):
+        img = torch.rand((1, *wl["vol"]), generator=g)
+        a, _ = otr.spacing(img, aff, (1.0, 1.0, 1.0))
+        b, _ = otr.rand_affine(a, i, (0.2,) * 3, (), (5,) * 3, (0.1,) * 3, None, "bilinear", "border")
+        otr.gaussian_smooth(b, 1.0)
+    dt = time.perf_counter() - t0
+    return {"value": float(np.prod(wl["vol"])) * volumes / dt, "unit": "voxels/s", "cores": torch.get_num_threads(), "host_cores": cores,
+            "kind": "port", "sample": f"{volumes} of {wl['volumes']} volumes (1x256^3 fp32 -> 320^3), torch-CPU oracle of the three transforms"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,6 +359,16 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.sw_batch > 0:
         wl["sw_batch"] = args.sw_batch
+    if args.workload == "transforms_c4":
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                leg = transforms_cpu_leg(wl, volumes=max(1, min(args.steps, 3)))
+                print(json.dumps({"impl": "reference", "metric": "voxels/sec spatial transform pipeline (input voxels)", "value": leg["value"],
+                                  "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                                  "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
+                                  "cpu_baseline": leg, "e2e": {"value": leg["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return
+        return run_transforms(args, wl)
     if args.impl == "reference":
         return run_reference(args, wl)
 
@@ -258,9 +411,24 @@ def main():
         return inferer(x_dev, net)
 
     out_host = None
+    if world > 1:
+        # end to end, the sharded job moves every byte once: a rank uploads only the depth rows its windows read and
+        # downloads only the rows of the result it owns (no broadcast of the slabs between GPUs)
+        inferer_e2e = ShardedSlidingWindowInferer(wl["roi"], wl["sw_batch"], wl["overlap"], wl["mode"], gather=False)
+        plan = inferer_e2e.plan(vol, world)
+        (s_lo, s_hi), (o_lo, o_hi) = plan.slab[rank], plan.owned[rank]
+        x_e2e = torch.zeros_like(x_dev)
+        e2e_bytes = [host[:, :, s_lo:s_hi].numel() * host.element_size(), 0]
 
     def step_e2e():
         nonlocal out_host
+        if world > 1:
+            x_e2e[:, :, s_lo:s_hi].copy_(host[:, :, s_lo:s_hi], non_blocking=True)
+            y = inferer_e2e(x_e2e, net)
+            if out_host is None:
+                out_host = torch.empty((*y.shape[:2], o_hi - o_lo, *y.shape[3:]), dtype=y.dtype).pin_memory()
+            out_host.copy_(y[:, :, o_lo:o_hi], non_blocking=True)
+            return y
         xd = host.to(dev, non_blocking=True)
         y = inferer(xd, net)
         if out_host is None:
@@ -304,6 +472,13 @@ def main():
     step_resident()
     prof = K.profile_stop()
 
+    # bytes moved per step, summed over the ranks (each rank uploads its slab rows and downloads its owned rows)
+    h2d_total = e2e_bytes[0] if world > 1 else host.numel() * host.element_size()
+    d2h_total = out_host.numel() * out_host.element_size() if out_host is not None else 0
+    if dist is not None:
+        tb = torch.tensor([float(h2d_total), float(d2h_total)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tb)
+        h2d_total, d2h_total = float(tb[0].item()), float(tb[1].item())
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -332,8 +507,7 @@ def main():
         "config": {"workload": wl["desc"], "sw_batch_size": wl["sw_batch"], "windows": wl["windows"], "l2": "256 MiB flush write between timed steps",
                    "accumulate": "fp32", "parallelism": f"depth-shard x{world}" if world > 1 else "single GPU"},
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": nvox / (ms_e2e / args.steps * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
-                "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()) if out_host is not None else 0},
+        "e2e": {"value": nvox / (ms_e2e / args.steps * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total)},
         "model_tflops": wl["flop_per_window"] * wl["windows"] / (ms_step * 1e-3) / 1e12,
         "roofline": roofline,
         "kernels": {k: {"ms": round(v["ms"], 4), "n": v["n"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]},

@@ -256,7 +256,8 @@ def resample_affine(
     Cc, Di, Hi, Wi = src.shape
     dst = torch.empty((Cc, *out_shape), device=src.device, dtype=out_dtype)
     m = (C.c_double * 12)(*[float(v) for v in mat])
-    _call("resample_affine", L.ptr(src), L.dt(src), Cc, Di, Hi, Wi, L.ptr(dst), L.dt(dst), out_shape[0], out_shape[1], out_shape[2], m, interp, pad, int(bool(align_corners)), L.stream_ptr(src.device))
+    _call("resample_affine", L.ptr(src), L.dt(src), Cc, Di, Hi, Wi, L.ptr(dst), L.dt(dst), out_shape[0], out_shape[1], out_shape[2], m, interp, pad, int(bool(align_corners)), L.stream_ptr(src.device),
+          nbytes=_nb(src, dst))
     return dst
 
 
@@ -268,7 +269,8 @@ def separable_filter3d(src: torch.Tensor, taps: Sequence[torch.Tensor]) -> torch
     dst = torch.empty_like(src)
     tmp = torch.empty((2, Cc, D, H, W), device=src.device, dtype=torch.float32)
     t = [x.detach().to(device=src.device, dtype=torch.float32).contiguous() for x in taps]
-    _call("separable_filter3d", L.ptr(src), L.dt(src), Cc, D, H, W, L.ptr(t[0]), t[0].numel(), L.ptr(t[1]), t[1].numel(), L.ptr(t[2]), t[2].numel(), L.ptr(tmp), L.ptr(dst), L.stream_ptr(src.device))
+    _call("separable_filter3d", L.ptr(src), L.dt(src), Cc, D, H, W, L.ptr(t[0]), t[0].numel(), L.ptr(t[1]), t[1].numel(), L.ptr(t[2]), t[2].numel(), L.ptr(tmp), L.ptr(dst), L.stream_ptr(src.device),
+          nbytes=_nb(src, dst) + 4.0 * src.numel() * 4)   # three passes: read + write each, two of them through the fp32 scratch
     return dst
 
 

@@ -105,6 +105,21 @@ class ShardedSlidingWindowInferer:
     def __init__(self, roi_size, sw_batch_size: int = 1, overlap=0.25, mode="constant", sigma_scale=0.125, gather: bool = True):
         self.roi_size, self.sw_batch_size, self.overlap, self.mode, self.sigma_scale, self.gather = roi_size, sw_batch_size, overlap, mode, sigma_scale, gather
 
+    def plan(self, spatial_shape: Sequence[int], world: int | None = None) -> ShardPlan:
+        """The shard plan `__call__` uses for a volume of this spatial shape: `plan.slab[rank]` are the depth rows of the
+        INPUT a rank reads (callers may upload only those), `plan.owned[rank]` the rows of the result it finalises (with
+        `gather=False` only those rows of the returned tensor are valid)."""
+        from ..data.utils import dense_patch_starts
+        from ..inferers.utils import _ensure_tuple_rep, _fall_back_tuple, _get_scan_interval
+
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        D, H, W = (int(s) for s in spatial_shape)
+        roi = _fall_back_tuple(self.roi_size, (D, H, W))
+        interval = _get_scan_interval((D, H, W), roi, 3, _ensure_tuple_rep(self.overlap, 3))
+        starts = dense_patch_starts((D, H, W), roi, interval)
+        return make_shard_plan(starts[0], roi[0], D, world, per_layer=len(starts[1]) * len(starts[2]))
+
     def __call__(self, inputs: torch.Tensor, network: Callable[..., torch.Tensor], *args: Any, **kwargs: Any) -> torch.Tensor:
         from .. import _kernels as K
         from ..data.utils import dense_patch_starts, importance_factors

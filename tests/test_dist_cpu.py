@@ -92,3 +92,20 @@ def test_shard_plan_balance_and_coverage():
     # more ranks than windows: empty ranks own nothing and the plan stays consistent
     tiny = make_shard_plan([0], 16, 16, 3, per_layer=2)
     assert sum(b - a for a, b in tiny.win_range) == 2
+
+
+def test_sharded_inferer_plan_helper_matches_make_shard_plan():
+    """`plan()` tells a caller which input rows a rank reads and which result rows it owns (used by bench.py's e2e arm)."""
+    from monai_b200.data.utils import dense_patch_starts
+    from monai_b200.parallel import ShardedSlidingWindowInferer, make_shard_plan
+
+    inf = ShardedSlidingWindowInferer((96, 96, 96), 8, 0.5, "gaussian")
+    for world in (1, 2, 4, 8):
+        p = inf.plan((512, 512, 512), world)
+        starts = dense_patch_starts((512, 512, 512), (96, 96, 96), (48, 48, 48))
+        q = make_shard_plan(starts[0], 96, 512, world, per_layer=len(starts[1]) * len(starts[2]))
+        assert p.win_range == q.win_range and p.slab == q.slab and p.owned == q.owned
+        assert p.owned[0][0] == 0 and p.owned[-1][1] == 512 and all(a[1] == b[0] for a, b in zip(p.owned, p.owned[1:]))
+        assert sum(b - a for a, b in p.win_range) == 1000
+        for (s0, s1), (o0, o1) in zip(p.slab, p.owned):
+            assert s0 <= o0 < o1 <= s1 or o1 <= o0   # a rank's owned rows lie inside the rows its windows cover
