@@ -41,7 +41,10 @@ constexpr int kRsVox = 4;   // consecutive output voxels along W per thread (ind
 
 // A block is 32 (w quads) x 8 (h rows) threads = a 128 x 8 output patch of one depth plane: one voxel per thread and one
 // block per W row left the chip waiting on block turnover (204,800 tiny blocks for a 320^3 output, 3 % of HBM bandwidth).
-template <typename TI, typename TO>
+// MODE 0: trilinear with zeros padding, 3: trilinear with border padding (both: fp64 base coordinate + fp32 increments),
+// 1: trilinear with reflection padding (fp64 per voxel), 2: nearest.  Separate instantiations: the common paths carry no
+// fp64 reflection code, and the border path needs no corner validity tests (a clamped coordinate has valid corners).
+template <typename TI, typename TO, int MODE>
 __global__ void __launch_bounds__(256) resample_affine_kernel(ResampleP p) {
   const int k0 = (blockIdx.x * 32 + threadIdx.x) * kRsVox;  // fastest output axis
   const int j = blockIdx.y * 8 + threadIdx.y, i = blockIdx.z;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(256) resample_affine_kernel(ResampleP p) {
   TO* dst = (TO*)p.dst;
   // the (i, j) part of the affine map is shared by the thread's voxels; each voxel still evaluates the full fma chain
   // in the reference's order so the coordinates are bit-identical to the one-voxel formulation
-  if (p.interp == 0) {
+  if (MODE == 2) {
 #pragma unroll
     for (int v = 0; v < kRsVox; ++v) {
       const int k = k0 + v;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) resample_affine_kernel(ResampleP p) {
   // Trilinear, zeros / border padding: the coordinate of the thread's first voxel is evaluated in fp64 (the reference's
   // coordinate dtype) and split into integer + fraction; the next three voxels add v * m[.,k] to the fraction in fp32
   // (|error| < 1e-6 voxel).  Only 1/4 of the fp64 work per voxel remains -- the fp64 pipe, not HBM, bounded this kernel.
-  const bool split = p.pad != 2;
+  constexpr bool split = MODE == 0 || MODE == 3;
   int IA = 0, IB = 0, IC = 0;
   float FA = 0.f, FB = 0.f, FC = 0.f;
   if (split) {
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(256) resample_affine_kernel(ResampleP p) {
       const float fa = floorf(av), fb = floorf(bv), fc = floorf(cv);
       a0 = IA + (int)fa; b0 = IB + (int)fb; c0 = IC + (int)fc;
       ta = av - fa; tb = bv - fb; tc = cv - fc;
-      if (p.pad == 1) {  // border: clamp the coordinate to [0, size-1]
+      if (MODE == 3) {  // border: clamp the coordinate to [0, size-1]
         if (a0 < 0) { a0 = 0; ta = 0.f; } else if (a0 >= p.Di - 1) { a0 = p.Di - 1; ta = 0.f; }
         if (b0 < 0) { b0 = 0; tb = 0.f; } else if (b0 >= p.Hi - 1) { b0 = p.Hi - 1; tb = 0.f; }
         if (c0 < 0) { c0 = 0; tc = 0.f; } else if (c0 >= p.Wi - 1) { c0 = p.Wi - 1; tc = 0.f; }
@@ -114,12 +117,22 @@ __global__ void __launch_bounds__(256) resample_affine_kernel(ResampleP p) {
     }
     // per-axis weights with out-of-volume corners zeroed, and corner indices clamped into the volume so that every gather is
     // a valid address: eight offsets are then one base plus {0, dW} + {0, dH} + {0, dD}
-    const float wa[2] = {(a0 >= 0 && a0 < p.Di) ? 1.f - ta : 0.f, (a0 + 1 >= 0 && a0 + 1 < p.Di) ? ta : 0.f};
-    const float wb[2] = {(b0 >= 0 && b0 < p.Hi) ? 1.f - tb : 0.f, (b0 + 1 >= 0 && b0 + 1 < p.Hi) ? tb : 0.f};
-    const float wc[2] = {(c0 >= 0 && c0 < p.Wi) ? 1.f - tc : 0.f, (c0 + 1 >= 0 && c0 + 1 < p.Wi) ? tc : 0.f};
-    const int a0c = min(max(a0, 0), p.Di - 1), a1c = min(max(a0 + 1, 0), p.Di - 1);
-    const int b0c = min(max(b0, 0), p.Hi - 1), b1c = min(max(b0 + 1, 0), p.Hi - 1);
-    const int c0c = min(max(c0, 0), p.Wi - 1), c1c = min(max(c0 + 1, 0), p.Wi - 1);
+    float wa[2] = {1.f - ta, ta}, wb[2] = {1.f - tb, tb}, wc[2] = {1.f - tc, tc};
+    int a0c = a0, b0c = b0, c0c = c0, a1c, b1c, c1c;
+    if (MODE == 3) {
+      // the clamped coordinate lies in [0, size-1]: corner 0 is valid, corner 1 is at most `size` and then carries weight 0
+      a1c = min(a0 + 1, p.Di - 1); b1c = min(b0 + 1, p.Hi - 1); c1c = min(c0 + 1, p.Wi - 1);
+    } else {
+      if (a0 < 0 || a0 >= p.Di) wa[0] = 0.f;
+      if (a0 + 1 < 0 || a0 + 1 >= p.Di) wa[1] = 0.f;
+      if (b0 < 0 || b0 >= p.Hi) wb[0] = 0.f;
+      if (b0 + 1 < 0 || b0 + 1 >= p.Hi) wb[1] = 0.f;
+      if (c0 < 0 || c0 >= p.Wi) wc[0] = 0.f;
+      if (c0 + 1 < 0 || c0 + 1 >= p.Wi) wc[1] = 0.f;
+      a0c = min(max(a0, 0), p.Di - 1); a1c = min(max(a0 + 1, 0), p.Di - 1);
+      b0c = min(max(b0, 0), p.Hi - 1); b1c = min(max(b0 + 1, 0), p.Hi - 1);
+      c0c = min(max(c0, 0), p.Wi - 1); c1c = min(max(c0 + 1, 0), p.Wi - 1);
+    }
     const int base = (a0c * p.Hi + b0c) * p.Wi + c0c;
     const int dD = (a1c - a0c) * p.Hi * p.Wi, dH = (b1c - b0c) * p.Wi, dW = c1c - c0c;
 #pragma unroll
@@ -282,7 +295,10 @@ extern "C" int b200_resample_affine(const void* src, int src_dtype, int C, int D
   p.interp = interp; p.pad = pad; p.align = align_corners;
   dim3 block(32, 8), grid(ceil_div(Wo, 32 * kRsVox), ceil_div(Ho, 8), Do);
   cudaStream_t st = (cudaStream_t)stream;
-#define LR(TI, TO) resample_affine_kernel<TI, TO><<<grid, block, 0, st>>>(p)
+#define LR(TI, TO) do { if (interp == 0) resample_affine_kernel<TI, TO, 2><<<grid, block, 0, st>>>(p); \
+                       else if (pad == 2) resample_affine_kernel<TI, TO, 1><<<grid, block, 0, st>>>(p); \
+                       else if (pad == 1) resample_affine_kernel<TI, TO, 3><<<grid, block, 0, st>>>(p); \
+                       else resample_affine_kernel<TI, TO, 0><<<grid, block, 0, st>>>(p); } while (0)
   if (src_dtype == B200_DT_F32 && dst_dtype == B200_DT_F32) LR(float, float);
   else if (src_dtype == B200_DT_F16 && dst_dtype == B200_DT_F32) LR(__half, float);
   else if (src_dtype == B200_DT_F32 && dst_dtype == B200_DT_F16) LR(float, __half);

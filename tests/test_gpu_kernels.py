@@ -126,6 +126,32 @@ def test_separable_filter_matches_conv3d():
     torch.testing.assert_close(got.cpu(), ref[0], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,sp", [(9, (20, 37, 48)), (9, (5, 3, 8)), (5, (33, 17, 64)), (3, (16, 16, 16)), (1, (4, 4, 4))])
+def test_separable_filter_sliding_window_path(n, sp):
+    """Equal odd tap counts <= 9, fp32 and W % 4 == 0 take the register sliding-window kernels (runs of 16 along D / H,
+    ragged run tails, volumes shorter than the filter radius): compare with conv3d AND bit-compare with the generic path
+    (same data embedded in a volume whose W is not a multiple of 4 cannot share a launch, so the generic path is forced
+    through fp16->fp32 dispatch rules instead: different tap counts per axis)."""
+    g = torch.Generator().manual_seed(n + sp[0])
+    x = torch.randn((2, *sp), generator=g)
+    taps = [torch.rand(n, generator=g) for _ in range(3)]
+    ref = x[None]
+    for d, t in enumerate(taps):
+        shape = [1, 1, 1, 1, 1]
+        shape[d + 2] = -1
+        padv = [0, 0, 0]
+        padv[d] = (n - 1) // 2
+        ref = F.conv3d(ref, t.reshape(shape).repeat(2, 1, 1, 1, 1), padding=padv, groups=2)
+    got = K.separable_filter3d(x.to(DEV), [t.to(DEV) for t in taps])
+    torch.testing.assert_close(got.cpu(), ref[0], rtol=1e-5, atol=1e-5)
+    if n >= 3:
+        # generic kernels: pad the last axis' taps with two zeros on each side (n + 4 taps, unequal counts -> generic path);
+        # zero taps add exact zeros, so the two paths must agree bit for bit
+        wide = torch.cat([torch.zeros(2), taps[2], torch.zeros(2)])
+        gen = K.separable_filter3d(x.to(DEV), [taps[0].to(DEV), taps[1].to(DEV), wide.to(DEV)])
+        torch.testing.assert_close(got, gen, rtol=0, atol=0)
+
+
 def test_nc8_roundtrip():
     x = torch.randn((2, 24, 5, 6, 7), device=DEV).half()
     p = K.pack_nc8(x)
