@@ -708,7 +708,7 @@ extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream)
     vec8 = (reinterpret_cast<uintptr_t>(p.preds) % 16 == 0) && p.ps_n % 8 == 0 && p.ps_c % 8 == 0 && p.ps_d % 8 == 0 && p.ps_h % 8 == 0;
   // TMA-staged kernel: fp16 predictions, contiguous window rows, 16-byte aligned strides, separable importance factors
   static int use_tma = -1;
-  if (use_tma < 0) { const char* e = getenv("B200_BLEND_TMA"); use_tma = (e && e[0] == '1') ? 1 : 0;   // opt-in until validated on the GPU }
+  if (use_tma < 0) { const char* e = getenv("B200_BLEND_TMA"); use_tma = (e && e[0] == '1') ? 1 : 0; }   // opt-in until validated on the GPU
   const bool tma_ok = use_tma && mode != 2 && dsc->pred_dtype == B200_DT_F16 && !p.wmap && p.ps_w == 1 && p.C <= kTmaMaxC && p.W % 4 == 0 &&
                       p.rw % 8 == 0 && p.rh <= kTmaMaxRoi && p.rw <= kTmaMaxRoi && p.rh >= kTmaTH && p.rw >= kTmaTW && p.ps_h % 8 == 0 && p.ps_d % 8 == 0 && p.ps_c % 8 == 0 &&
                       p.ps_n % 8 == 0 && reinterpret_cast<uintptr_t>(p.preds) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
