@@ -146,6 +146,37 @@ def test_eight_voxel_blend_path_is_bit_identical_to_the_scalar_path(monkeypatch,
     np.testing.assert_allclose(a.float().cpu().numpy(), want, rtol=tol, atol=tol)
 
 
+def test_tma_staged_blend_is_bit_identical(tmp_path):
+    """The TMA-staged blend (opt-in: B200_BLEND_TMA=1, read once per process) must reproduce the default kernels bit for bit on
+    fp16 predictions, one-shot and streaming.  It runs in a child process because the switch is latched at first use."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, torch, numpy as np\n"
+        "sys.path.insert(0, sys.argv[1])\n"
+        "import monai_b200.inferers.utils as U\n"
+        "from monai_b200.inferers import sliding_window_inference\n"
+        "def pred(x):\n"
+        "    r = torch.arange(x.shape[-1], dtype=x.dtype, device=x.device) * 0.01\n"
+        "    return torch.cat([x.mean(dim=1, keepdim=True) * 1.5 + r, torch.tanh(x[:, :1]) - 0.25], dim=1)\n"
+        "x = torch.randn(2, 1, 40, 72, 128, generator=torch.Generator().manual_seed(7)).half().cuda()\n"
+        "a = sliding_window_inference(x, (16, 24, 64), 4, pred, 0.5, 'gaussian')\n"
+        "U._RESIDENT_BYTES = 9 * 2 * 16 * 24 * 64 * 2\n"
+        "b = sliding_window_inference(x, (16, 24, 64), 4, pred, 0.5, 'gaussian')\n"
+        "np.save(sys.argv[2], np.stack([a.float().cpu().numpy(), b.float().cpu().numpy()]))\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        out = str(tmp_path / f"blend_{flag}.npy")
+        env = dict(os.environ, B200_BLEND_TMA=flag)
+        subprocess.run([sys.executable, "-c", code, root, out], check=True, env=env, timeout=300)
+        outs.append(np.load(out))
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0][0], outs[0][1])
+
+
 def test_args_kwargs_process_fn_with_coord_and_device():
     x = torch.rand((1, 1, 12, 12, 12), device=DEV)
     t1, t2 = torch.ones(1, device=DEV), torch.ones(1, device=DEV)
