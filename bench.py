@@ -37,7 +37,7 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "swin_c3": dict(
         desc="SwinUNETR(feature_size=48) sliding-window 512^3 fp16, roi 96^3, overlap 0.5, gaussian",
-        vol=(512, 512, 512), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=8, net="swin48", windows=1000,
+        vol=(512, 512, 512), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=25, net="swin48", windows=1000,   # 25 divides the window share of 1, 2, 4 and 8 ranks
         flop_per_window=636e9,
     ),
     # BASELINE.json configs[3]
