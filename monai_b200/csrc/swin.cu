@@ -444,75 +444,88 @@ __global__ void __launch_bounds__(128) conv_cin1_nc8_kernel(const T* __restrict_
   constexpr int taps = KS * KS * KS;
   constexpr int XW = KS + (kVox - 1) * STRIDE;
   float* s_st = s_w + taps * Cout;
+  // the weights are staged once per block and the block then walks voxel groups with a grid stride (a block that handled
+  // a single group spent longer fetching its 27 x Cout weights from L2 than computing)
   for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
-    const int co = i % Cout, t = i / Cout;
-    s_w[i] = wgt[(long long)co * taps + t];
+    const int t = i % taps, co = i / taps;      // read the [Cout][taps] tensor linearly
+    s_w[t * Cout + co] = wgt[i];
   }
   for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) s_st[i] = 0.f;
   __syncthreads();
   const int n = blockIdx.y;
   const int Wq = (Wo + kVox - 1) / kVox;
   const long long So = (long long)Do * Ho * Wo;
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool ok = r < (long long)Do * Ho * Wq;
-  const int ox0 = ok ? (int)(r % Wq) * kVox : 0, oy = ok ? (int)((r / Wq) % Ho) : 0, oz = ok ? (int)(r / ((long long)Wq * Ho)) : 0;
-  float xv[KS][KS][XW];
-  if (ok) {
-    const T* xn = x + (long long)n * D * H * W;
-#pragma unroll
-    for (int kz = 0; kz < KS; ++kz)
-#pragma unroll
-      for (int ky = 0; ky < KS; ++ky) {
-        const int iz = oz * STRIDE - pad + kz, iy = oy * STRIDE - pad + ky;
-        const bool rok = iz >= 0 && iz < D && iy >= 0 && iy < H;
-#pragma unroll
-        for (int q = 0; q < XW; ++q) {
-          const int ix = ox0 * STRIDE - pad + q;
-          xv[kz][ky][q] = (rok && ix >= 0 && ix < W) ? io<T>::ld(xn + ((long long)iz * H + iy) * W + ix) : 0.f;
-        }
-      }
-  }
+  const long long total = (long long)Do * Ho * Wq;
+  const long long span = (long long)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  const long long vbase = ((long long)oz * Ho + oy) * Wo + ox0;
-  __half* yo = y + (((long long)n * (out_ctot / 8) + out_coff / 8) * So + vbase) * 8;
-  for (int c0 = 0; c0 < Cout; c0 += 8) {
-    float acc[kVox][8];
-#pragma unroll
-    for (int v = 0; v < kVox; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[v][j] = bias ? bias[c0 + j] : 0.f;
+  const T* xn = x + (long long)n * D * H * W;
+  for (long long r0 = (long long)blockIdx.x * blockDim.x; r0 < total; r0 += span) {   // block-uniform trip count (warp reductions inside)
+    const long long r = r0 + threadIdx.x;
+    const bool ok = r < total;
+    const int ox0 = ok ? (int)(r % Wq) * kVox : 0, oy = ok ? (int)((r / Wq) % Ho) : 0, oz = ok ? (int)(r / ((long long)Wq * Ho)) : 0;
+    float xv[KS][KS][XW];
     if (ok) {
 #pragma unroll
       for (int kz = 0; kz < KS; ++kz)
 #pragma unroll
-        for (int ky = 0; ky < KS; ++ky)
+        for (int ky = 0; ky < KS; ++ky) {
+          const int iz = oz * STRIDE - pad + kz, iy = oy * STRIDE - pad + ky;
+          const bool rok = iz >= 0 && iz < D && iy >= 0 && iy < H;
 #pragma unroll
-          for (int kx = 0; kx < KS; ++kx) {
-            const int t = (kz * KS + ky) * KS + kx;
-            const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * Cout + c0);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_w + t * Cout + c0 + 4);
-#pragma unroll
-            for (int v = 0; v < kVox; ++v) {
-              const float xt = xv[kz][ky][v * STRIDE + kx];
-              acc[v][0] = fmaf(xt, w0.x, acc[v][0]); acc[v][1] = fmaf(xt, w0.y, acc[v][1]);
-              acc[v][2] = fmaf(xt, w0.z, acc[v][2]); acc[v][3] = fmaf(xt, w0.w, acc[v][3]);
-              acc[v][4] = fmaf(xt, w1.x, acc[v][4]); acc[v][5] = fmaf(xt, w1.y, acc[v][5]);
-              acc[v][6] = fmaf(xt, w1.z, acc[v][6]); acc[v][7] = fmaf(xt, w1.w, acc[v][7]);
-            }
+          for (int q = 0; q < XW; ++q) {
+            const int ix = ox0 * STRIDE - pad + q;
+            xv[kz][ky][q] = (rok && ix >= 0 && ix < W) ? io<T>::ld(xn + ((long long)iz * H + iy) * W + ix) : 0.f;
           }
+        }
+    }
+    const long long vbase = ((long long)oz * Ho + oy) * Wo + ox0;
+    __half* yo = y + (((long long)n * (out_ctot / 8) + out_coff / 8) * So + vbase) * 8;
+    for (int c0 = 0; c0 < Cout; c0 += 8) {
+      float acc[kVox][8];
 #pragma unroll
       for (int v = 0; v < kVox; ++v)
-        if (ox0 + v < Wo) st8(yo + ((long long)(c0 / 8) * So + v) * 8, acc[v]);
-    }
-    if (stats) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a = 0.f, q2 = 0.f;
+        for (int j = 0; j < 8; ++j) acc[v][j] = bias ? bias[c0 + j] : 0.f;
+      if (ok) {
+#pragma unroll
+        for (int kz = 0; kz < KS; ++kz)
+#pragma unroll
+          for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+              const int t = (kz * KS + ky) * KS + kx;
+              const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * Cout + c0);
+              const float4 w1 = *reinterpret_cast<const float4*>(s_w + t * Cout + c0 + 4);
+#pragma unroll
+              for (int v = 0; v < kVox; ++v) {
+                const float xt = xv[kz][ky][v * STRIDE + kx];
+                acc[v][0] = fmaf(xt, w0.x, acc[v][0]); acc[v][1] = fmaf(xt, w0.y, acc[v][1]);
+                acc[v][2] = fmaf(xt, w0.z, acc[v][2]); acc[v][3] = fmaf(xt, w0.w, acc[v][3]);
+                acc[v][4] = fmaf(xt, w1.x, acc[v][4]); acc[v][5] = fmaf(xt, w1.y, acc[v][5]);
+                acc[v][6] = fmaf(xt, w1.z, acc[v][6]); acc[v][7] = fmaf(xt, w1.w, acc[v][7]);
+              }
+            }
 #pragma unroll
         for (int v = 0; v < kVox; ++v)
-          if (ok && ox0 + v < Wo) { a += acc[v][j]; q2 = fmaf(acc[v][j], acc[v][j], q2); }
-        const float s1 = warp_sum(a), s2 = warp_sum(q2);
-        if (lane == 0) { atomicAdd(&s_st[2 * (c0 + j)], s1); atomicAdd(&s_st[2 * (c0 + j) + 1], s2); }
+          if (ox0 + v < Wo) st8(yo + ((long long)(c0 / 8) * So + v) * 8, acc[v]);
+      }
+      if (stats) {
+        float a8[8], q8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = 0.f, q2 = 0.f;
+#pragma unroll
+          for (int v = 0; v < kVox; ++v)
+            if (ok && ox0 + v < Wo) { a += acc[v][j]; q2 = fmaf(acc[v][j], acc[v][j], q2); }
+          a8[j] = a; q8[j] = q2;
+        }
+        float cs, cq;
+        transpose_reduce8(a8, q8, lane, cs, cq);
+        if ((lane & 3) == 0) {
+          const int col = c0 + transpose_reduce8_col(lane);
+          atomicAdd(&s_st[2 * col], cs);
+          atomicAdd(&s_st[2 * col + 1], cq);
+        }
       }
     }
   }
@@ -710,7 +723,9 @@ template <typename T>
 static int launch_cin1(const T* x, __half* y, const float* weight, const float* bias, int N, int D, int H, int W, int Do, int Ho, int Wo,
                        int Cout, int k, int stride, int pad, int out_ctot, int out_coff, float* stats, cudaStream_t st) {
   const long long units = (long long)Do * Ho * ((Wo + kVox - 1) / kVox);
-  dim3 grid(ceil_div(units, 128), N);
+  // a few resident waves of blocks per batch item; each block strides over the voxel groups
+  const long long per_item = std::max<long long>(1, (long long)num_sms() * 8 / std::max(1, N));
+  dim3 grid((unsigned)std::min<long long>(ceil_div(units, 128), per_item), N);
   const size_t smem = ((size_t)k * k * k * Cout + 2 * Cout) * sizeof(float);
 #define LCI(KS, SS) conv_cin1_nc8_kernel<T, KS, SS><<<grid, 128, smem, st>>>(x, y, weight, bias, D, H, W, Do, Ho, Wo, Cout, pad, out_ctot, out_coff, stats)
   if (k == 3 && stride == 1) LCI(3, 1);
