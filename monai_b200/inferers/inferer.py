@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import warnings
 from abc import ABC, abstractmethod
-from collections.abc import Callable, Sequence
+from collections.abc import Callable, Mapping, Sequence
 from typing import Any
 
 import torch
@@ -17,7 +17,7 @@ import torch
 from ..data.utils import compute_importance_map
 from .utils import sliding_window_inference
 
-__all__ = ["Inferer", "SimpleInferer", "SlidingWindowInferer", "SlidingWindowInfererAdapt"]
+__all__ = ["Inferer", "SimpleInferer", "SlidingWindowInferer", "SlidingWindowInfererAdapt", "SliceInferer"]
 
 
 class Inferer(ABC):
@@ -130,3 +130,38 @@ class SlidingWindowInfererAdapt(SlidingWindowInferer):
             self.cpu_thresh = inputs.shape[2:].numel() - 1 if self.cpu_thresh is None else min(self.cpu_thresh, inputs.shape[2:].numel() - 1)
             warnings.warn("CUDA OOM during sliding-window inference; retrying with the stitched output on the host.")
             return super().__call__(inputs, network, *args, device="cpu", **kwargs)
+
+
+class SliceInferer(SlidingWindowInferer):
+    """Slice-by-slice (2-D network) inference over a 3-D volume with the same contract as the reference class
+    (monai/inferers/inferer.py:691-771): `roi_size` is 2-D, a singleton is inserted at `spatial_dim`, the window batch is
+    squeezed before the 2-D network runs and its outputs (tensor, sequence or mapping) are unsqueezed again.  Gather and
+    blend run in the CUDA kernels of `sliding_window_inference`; the 2-D predictor is any callable."""
+
+    def __init__(self, spatial_dim: int = 0, *args: Any, **kwargs: Any) -> None:
+        self.spatial_dim = spatial_dim
+        super().__init__(*args, **kwargs)
+        roi = self.roi_size
+        self.orig_roi_size = tuple(roi) if isinstance(roi, (list, tuple)) else (roi,)
+
+    def __call__(self, inputs: torch.Tensor, network: Callable, *args: Any, **kwargs: Any):
+        if self.spatial_dim > 2:
+            raise ValueError("`spatial_dim` can only be `0, 1, 2` with `[H, W, D]` respectively.")
+        if len(self.orig_roi_size) == 2 and len(inputs.shape[2:]) == 3:
+            roi = list(self.orig_roi_size)
+            roi.insert(self.spatial_dim, 1)
+            self.roi_size = roi
+        else:
+            raise RuntimeError(
+                f"Currently, only 2D `roi_size` ({self.orig_roi_size}) with 3D `inputs` tensor (shape={inputs.shape}) is supported."
+            )
+        return super().__call__(inputs, lambda x: self.network_wrapper(network, x, *args, **kwargs))
+
+    def network_wrapper(self, network: Callable, x: torch.Tensor, *args: Any, **kwargs: Any):
+        dim = self.spatial_dim + 2
+        out = network(x.squeeze(dim=dim), *args, **kwargs)
+        if isinstance(out, torch.Tensor):
+            return out.unsqueeze(dim=dim)
+        if isinstance(out, Mapping):
+            return {k: v.unsqueeze(dim=dim) for k, v in out.items()}
+        return tuple(o.unsqueeze(dim=dim) for o in out)

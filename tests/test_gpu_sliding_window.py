@@ -146,6 +146,33 @@ def test_eight_voxel_blend_path_is_bit_identical_to_the_scalar_path(monkeypatch,
     np.testing.assert_allclose(a.float().cpu().numpy(), want, rtol=tol, atol=tol)
 
 
+@pytest.mark.parametrize("spatial_dim", [0, 1, 2])
+def test_slice_inferer_equals_per_slice_prediction(spatial_dim):
+    """A 2-D predictor slid over a 3-D volume (reference tests/inferers/test_slice_inferer.py): with the roi covering whole
+    slices every voxel is predicted exactly once, so the stitched volume equals the per-slice predictions; tensor, tuple
+    and dict outputs; the inferer can be called repeatedly."""
+    from monai_b200.inferers import SliceInferer
+
+    def pred2d(t):   # [N, C, A, B] -> 2 channels
+        assert t.dim() == 4
+        ramp = torch.arange(t.shape[-1], dtype=t.dtype, device=t.device) * 0.01
+        return torch.cat([t * 2.0 + ramp, torch.tanh(t) - 0.5], dim=1)
+
+    x = torch.randn(2, 1, 6, 16, 24, device=DEV)
+    roi = list(x.shape[2:])
+    roi.pop(spatial_dim)
+    want = torch.stack([pred2d(s) for s in x.unbind(dim=spatial_dim + 2)], dim=spatial_dim + 2)
+    inf = SliceInferer(roi_size=roi, spatial_dim=spatial_dim, sw_batch_size=3, cval=-1)
+    for _ in range(2):
+        got = inf(x, pred2d)
+        assert got.shape == (2, 2, 6, 16, 24)
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+    got_t = inf(x, lambda t: (pred2d(t), pred2d(t)[:, :1] + 1))
+    torch.testing.assert_close(got_t[1], want[:, :1] + 1, rtol=1e-6, atol=1e-6)
+    got_d = inf(x, lambda t: {"a": pred2d(t)})
+    torch.testing.assert_close(got_d["a"], want, rtol=1e-6, atol=1e-6)
+
+
 def test_tma_staged_blend_is_bit_identical(tmp_path):
     """The TMA-staged blend (opt-in: B200_BLEND_TMA=1, read once per process) must reproduce the default kernels bit for bit on
     fp16 predictions, one-shot and streaming.  It runs in a child process because the switch is latched at first use."""

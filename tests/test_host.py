@@ -90,3 +90,22 @@ def test_kernels_refuse_cpu_tensors():
         K.instnorm_stats(torch.zeros(1, 2, 4, 4, 4))
     with pytest.raises(RuntimeError, match="CUDA"):
         K.conv3d_direct(torch.zeros(1, 1, 4, 4, 4), torch.zeros(2, 1, 3, 3, 3))
+
+
+def test_slice_inferer_argument_errors_match_reference():
+    """SliceInferer (monai/inferers/inferer.py:691-771): bad `spatial_dim` -> ValueError, non-2D roi or non-3D input -> RuntimeError,
+    both raised before any device work."""
+    import pytest
+    import torch
+
+    from monai_b200.inferers import SliceInferer
+
+    x = torch.zeros(1, 1, 4, 8, 8)
+    with pytest.raises(ValueError, match="spatial_dim"):
+        SliceInferer(roi_size=(8, 8), spatial_dim=3, sw_batch_size=1)(x, lambda t: t)
+    with pytest.raises(RuntimeError, match="only 2D `roi_size`"):
+        SliceInferer(roi_size=(4, 8, 8), spatial_dim=0, sw_batch_size=1)(x, lambda t: t)
+    with pytest.raises(RuntimeError, match="only 2D `roi_size`"):
+        SliceInferer(roi_size=(8, 8), spatial_dim=0, sw_batch_size=1)(torch.zeros(1, 1, 8, 8), lambda t: t)
+    inf = SliceInferer(roi_size=(8, 8), spatial_dim=1, sw_batch_size=2, cval=-1)
+    assert inf.orig_roi_size == (8, 8) and inf.cval == -1 and inf.sw_batch_size == 2
