@@ -220,6 +220,13 @@ int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H, int W, con
                        int Cout, int k, int stride, int pad, void* y, int out_ctot, int out_coff, float* stats,
                        void* stream);
 
+/* Channel-wise post-processing of channel-first logits x[C][S] (the transforms that follow the inferer in a segmentation bundle):
+ * op 0 softmax over C, 1 sigmoid  (Activations, monai/transforms/post/array.py:63-128);
+ * op 2 argmax over C -> y[1][S] (index as float) or, with onehot > 0, y[onehot][S]; op 3 `x >= param`; op 4 round-half-even;
+ * op 5 one-hot of a single-channel index map -> y[onehot][S]  (AsDiscrete, post/array.py:131-251).  dtypes: 0 f32, 1 f16. */
+int b200_channel_post(const void* x, int in_dtype, int C, long long S, int op, float param, int onehot, void* y, int out_dtype,
+                      void* stream);
+
 /* 1x1x1 output head (UnetOutBlock, dynunet_block.py:247-267): NC8 fp16 [N][C/8][S][8] -> NCDHW [N][Cout][S]. */
 int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,
                        void* y, int out_dtype, void* stream);

@@ -274,6 +274,21 @@ def separable_filter3d(src: torch.Tensor, taps: Sequence[torch.Tensor]) -> torch
     return dst
 
 
+POST_SOFTMAX, POST_SIGMOID, POST_ARGMAX, POST_THRESHOLD, POST_ROUND, POST_ONEHOT = range(6)
+
+
+def channel_post(x: torch.Tensor, op: int, param: float = 0.0, onehot: int = 0, out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """Channel-first post-processing x[C, *spatial] -> y (see b200_channel_post): softmax / sigmoid / argmax / threshold / round / one-hot."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    Cc = x.shape[0]
+    S = x[0].numel()
+    Co = (onehot if onehot > 0 else 1) if op in (POST_ARGMAX, POST_ONEHOT) else Cc
+    y = torch.empty((Co, *x.shape[1:]), device=x.device, dtype=out_dtype or x.dtype)
+    _call("channel_post", L.ptr(x), L.dt(x), Cc, S, op, float(param), int(onehot), L.ptr(y), L.dt(y), L.stream_ptr(x.device), nbytes=_nb(x, y))
+    return y
+
+
 # ---------------------------------------------------------------------------------------------- tensor-core path
 class NC8:
     """fp16 activation buffer in the channel-blocked layout [N][C/8][D][H][W][8] used by the tcgen05 kernels."""

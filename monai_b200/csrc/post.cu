@@ -1,0 +1,105 @@
+// Channel-wise post-processing of the stitched logits: the step on the other side of the inferer
+// in every segmentation bundle.  Replaces, for channel-first tensors [C][S] (S = flattened spatial size):
+//   Activations  (monai/transforms/post/array.py:63-128):  torch.sigmoid / torch.softmax(dim=0)
+//   AsDiscrete   (monai/transforms/post/array.py:131-251): torch.argmax(dim=0, keepdim=True), one_hot, `>= threshold`, torch.round
+// One thread owns one voxel: the C values are read once (stride S between channels, coalesced across the warp), the
+// result is written once -- HBM-bound passes.  Softmax is max-subtracted like ATen's; argmax keeps the FIRST maximum
+// (torch.argmax semantics for ties); round is half-to-even.
+#include "common.cuh"
+#include "../../include/monai_b200.h"
+
+namespace b200 {
+
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) channel_softmax_kernel(const TI* __restrict__ x, TO* __restrict__ y, int C, long long S) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, io<TI>::ld(x + (long long)c * S + s));
+  float sum = 0.f;
+  for (int c = 0; c < C; ++c) sum += expf(io<TI>::ld(x + (long long)c * S + s) - m);
+  const float inv = 1.f / sum;
+  for (int c = 0; c < C; ++c) io<TO>::st(y + (long long)c * S + s, expf(io<TI>::ld(x + (long long)c * S + s) - m) * inv);
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) channel_sigmoid_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = io<TI>::ld(x + i);
+    io<TO>::st(y + i, 1.f / (1.f + expf(-v)));
+  }
+}
+
+// argmax over channels; onehot == 0: y[0][s] = index as float, else y[k][s] = (k == index) for k < onehot
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) channel_argmax_kernel(const TI* __restrict__ x, TO* __restrict__ y, int C, long long S, int onehot) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float best = io<TI>::ld(x + s);
+  int arg = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = io<TI>::ld(x + (long long)c * S + s);
+    if (v > best || (v != v && best == best)) { best = v; arg = c; }   // first maximum wins; NaN is a maximum, as in torch
+  }
+  if (onehot <= 0) {
+    io<TO>::st(y + s, (float)arg);
+  } else {
+    for (int k = 0; k < onehot; ++k) io<TO>::st(y + (long long)k * S + s, k == arg ? 1.f : 0.f);
+  }
+}
+
+// mode 0: y = (x >= param), mode 1: y = round-half-even(x), mode 2: one-hot of an index map x[1][S] -> y[param][S]
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) elementwise_post_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long total, int mode,
+                                                               float param, long long S) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) io<TO>::st(y + i, io<TI>::ld(x + i) >= param ? 1.f : 0.f);
+    else if (mode == 1) io<TO>::st(y + i, rintf(io<TI>::ld(x + i)));
+    else {
+      const long long s = i % S;
+      const int k = (int)(i / S);
+      io<TO>::st(y + i, (int)io<TI>::ld(x + s) == k ? 1.f : 0.f);
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define B200_POST_DISPATCH(KERNEL_CALL)                                                            \
+  if (in_dtype == B200_DT_F32 && out_dtype == B200_DT_F32) { using TI = float; using TO = float; KERNEL_CALL; }   \
+  else if (in_dtype == B200_DT_F16 && out_dtype == B200_DT_F32) { using TI = __half; using TO = float; KERNEL_CALL; } \
+  else if (in_dtype == B200_DT_F32 && out_dtype == B200_DT_F16) { using TI = float; using TO = __half; KERNEL_CALL; } \
+  else if (in_dtype == B200_DT_F16 && out_dtype == B200_DT_F16) { using TI = __half; using TO = __half; KERNEL_CALL; } \
+  else return set_err(B200_ERR_INVALID, "channel_post: bad dtype");
+
+extern "C" int b200_channel_post(const void* x, int in_dtype, int C, long long S, int op, float param, int onehot, void* y,
+                                 int out_dtype, void* stream) {
+  B200_REQUIRE(x && y, "channel_post: null pointer");
+  B200_REQUIRE(C > 0 && S >= 0, "channel_post: bad sizes");
+  B200_REQUIRE(op >= 0 && op <= 5, "channel_post: op must be 0 (softmax), 1 (sigmoid), 2 (argmax), 3 (threshold), 4 (round) or 5 (one-hot)");
+  if (S == 0) return B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned vox_blocks = (unsigned)ceil_div(S, 256);
+  const long long total = (long long)C * S;
+  const unsigned flat_blocks = (unsigned)std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 32);
+  if (op == 0) {
+    B200_POST_DISPATCH((channel_softmax_kernel<TI, TO><<<vox_blocks, 256, 0, st>>>((const TI*)x, (TO*)y, C, S)));
+  } else if (op == 1) {
+    B200_POST_DISPATCH((channel_sigmoid_kernel<TI, TO><<<flat_blocks, 256, 0, st>>>((const TI*)x, (TO*)y, total)));
+  } else if (op == 2) {
+    B200_REQUIRE(onehot >= 0, "channel_post: negative class count");
+    B200_POST_DISPATCH((channel_argmax_kernel<TI, TO><<<vox_blocks, 256, 0, st>>>((const TI*)x, (TO*)y, C, S, onehot)));
+  } else if (op == 3 || op == 4) {
+    B200_POST_DISPATCH((elementwise_post_kernel<TI, TO><<<flat_blocks, 256, 0, st>>>((const TI*)x, (TO*)y, total, op == 3 ? 0 : 1, param, S)));
+  } else {
+    B200_REQUIRE(C == 1 && onehot > 0, "channel_post: one-hot takes a single-channel index map and a positive class count");
+    const long long tot = (long long)onehot * S;
+    const unsigned blocks = (unsigned)std::min<long long>(ceil_div(tot, 256), (long long)num_sms() * 32);
+    B200_POST_DISPATCH((elementwise_post_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI*)x, (TO*)y, tot, 2, 0.f, S)));
+  }
+  B200_LAUNCH_CHECK("channel_post_kernel");
+  return B200_OK;
+}

@@ -227,3 +227,34 @@ def gaussian_smooth(img: torch.Tensor, sigma):
         pad[d] = (k.numel() - 1) // 2
         x = conv(x, w, padding=pad, groups=c)
     return x[0]
+
+
+def activations(img: torch.Tensor, sigmoid: bool = False, softmax: bool = False) -> torch.Tensor:
+    """Activations.__call__ (monai/transforms/post/array.py:91-128): float32, sigmoid then softmax over dim 0."""
+    if sigmoid and softmax:
+        raise ValueError("Incompatible values: sigmoid=True and softmax=True.")
+    t = img.float()
+    if sigmoid:
+        t = torch.sigmoid(t)
+    if softmax:
+        t = torch.softmax(t, dim=0)
+    return t
+
+
+def as_discrete(img: torch.Tensor, argmax: bool = False, to_onehot: int | None = None, threshold: float | None = None,
+                rounding: str | None = None) -> torch.Tensor:
+    """AsDiscrete.__call__ (monai/transforms/post/array.py:190-251): argmax(dim 0, keepdim), one-hot (`one_hot`,
+    monai/networks/utils.py:170-230: scatter of ones along dim 0), `>= threshold`, torch.round; float32 result."""
+    t = img
+    if argmax:
+        t = torch.argmax(t, dim=0, keepdim=True)
+    if to_onehot is not None:
+        if t.shape[0] != 1:
+            raise AssertionError("labels should have a channel with length equal to one.")
+        oh = torch.zeros((to_onehot, *t.shape[1:]), dtype=torch.float)
+        t = oh.scatter_(0, t.long(), 1.0)
+    if threshold is not None:
+        t = t >= threshold
+    if rounding is not None:
+        t = torch.round(t)
+    return t.float()

@@ -185,8 +185,31 @@ def transforms():
     save("transforms.npz", **out)
 
 
+def post():
+    """Activations / AsDiscrete of the real reference on small logits (incl. ties and the goldens of its own unit tests)."""
+    from monai.transforms import Activations, AsDiscrete
+
+    out = {}
+    g = torch.Generator().manual_seed(33)
+    logits = torch.randn((3, 6, 7, 5), generator=g) * 2.0
+    logits[:, 0, 0, 0] = 0.5            # three-way tie: argmax must pick channel 0
+    logits[1:, 1, 1, 1] = 4.0           # two-way tie between channels 1 and 2
+    out["logits"] = logits.numpy()
+    out["softmax"] = Activations(softmax=True)(logits).numpy()
+    out["sigmoid"] = Activations(sigmoid=True)(logits).numpy()
+    out["argmax"] = AsDiscrete(argmax=True)(logits).numpy()
+    out["argmax_onehot"] = AsDiscrete(argmax=True, to_onehot=3)(logits).numpy()
+    out["threshold"] = AsDiscrete(threshold=0.25)(logits).numpy()
+    out["round"] = AsDiscrete(rounding="torchrounding")(torch.tensor([[0.5, 1.5, 2.5, -0.5, -1.5, 0.49, 2.51]])).numpy()
+    labels = torch.tensor([[[0.0, 2.0, 1.0], [1.0, 0.0, 2.0]]])
+    out["labels"] = labels.numpy()
+    out["onehot"] = AsDiscrete(to_onehot=3)(labels).numpy()
+    out["sigmoid_threshold"] = AsDiscrete(threshold=0.5)(Activations(sigmoid=True)(logits)).numpy()
+    save("post.npz", **out)
+
+
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms", "post"]
     for w in which:
         globals()[w]()

@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from monai_b200.data import MetaTensor
-from monai_b200.transforms import Compose, GaussianSmooth, GaussianSmoothd, RandAffine, RandAffined, Spacing, Spacingd
+from monai_b200.transforms import (Activations, Activationsd, AsDiscrete, AsDiscreted, Compose, GaussianSmooth, GaussianSmoothd, RandAffine,
+                                   RandAffined, Spacing, Spacingd)
 from oracle import transforms as otr
 
 pytestmark = pytest.mark.gpu
@@ -89,3 +90,35 @@ def test_rand_affine_without_transform_and_plain_tensor():
     torch.testing.assert_close(y, x)
     with pytest.raises(RuntimeError, match="CUDA"):
         Spacing(pixdim=(2.0, 2.0, 2.0))(torch.rand(1, 4, 4, 4))
+
+
+def test_post_transforms_match_reference_fixture(golden_dir):
+    """Activations / AsDiscrete on the channel-wise CUDA kernels vs outputs of the real reference; argmax ties pick the first
+    maximum, rounding is half-to-even, results are float32, MetaTensor metadata survives, dict versions and fp16 inputs work."""
+    g = np.load(os.path.join(golden_dir, "post.npz"))
+    logits = torch.from_numpy(g["logits"]).to(DEV)
+    np.testing.assert_allclose(Activations(softmax=True)(logits).cpu().numpy(), g["softmax"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(Activations(sigmoid=True)(logits).cpu().numpy(), g["sigmoid"], rtol=2e-6, atol=1e-7)
+    a = AsDiscrete(argmax=True)(logits)
+    assert a.dtype == torch.float32 and tuple(a.shape) == (1, 6, 7, 5)
+    np.testing.assert_array_equal(a.cpu().numpy(), g["argmax"])
+    np.testing.assert_array_equal(AsDiscrete(argmax=True, to_onehot=3)(logits).cpu().numpy(), g["argmax_onehot"])
+    np.testing.assert_array_equal(AsDiscrete(threshold=0.25)(logits).cpu().numpy(), g["threshold"])
+    r = torch.tensor([[0.5, 1.5, 2.5, -0.5, -1.5, 0.49, 2.51]], device=DEV)
+    np.testing.assert_array_equal(AsDiscrete(rounding="torchrounding")(r).cpu().numpy(), g["round"])
+    np.testing.assert_array_equal(AsDiscrete(to_onehot=3)(torch.from_numpy(g["labels"]).to(DEV)).cpu().numpy(), g["onehot"])
+    d = Compose([Activationsd(keys=["pred"], sigmoid=True), AsDiscreted(keys=["pred"], threshold=0.5)])({"pred": MetaTensor(logits, affine=torch.eye(4) * 2)})
+    assert isinstance(d["pred"], MetaTensor) and float(d["pred"].affine[0, 0]) == 2.0
+    np.testing.assert_array_equal(d["pred"].cpu().numpy(), g["sigmoid_threshold"])
+    # fp16 logits (what the fp16 inferer returns): softmax computed in fp32, returned as fp16; argmax unaffected by the dtype
+    h = logits.half()
+    np.testing.assert_allclose(Activations(softmax=True)(h).float().cpu().numpy(), otr.activations(h.float().cpu(), softmax=True).numpy(), atol=1e-3)
+    np.testing.assert_array_equal(AsDiscrete(argmax=True)(h).cpu().numpy(), otr.as_discrete(h.float().cpu(), argmax=True).numpy())
+    # error behaviour of the reference
+    with pytest.raises(ValueError, match="Incompatible values"):
+        Activations()(logits, sigmoid=True, softmax=True)
+    with pytest.raises(TypeError, match="other must be None or callable"):
+        Activations(other=3)
+    with pytest.raises(ValueError, match="deprecated"):
+        AsDiscrete(to_onehot=True)
+    np.testing.assert_allclose(Activations(other=torch.tanh)(logits).cpu().numpy(), np.tanh(g["logits"]), rtol=1e-6, atol=1e-6)

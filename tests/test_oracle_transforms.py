@@ -66,3 +66,19 @@ def test_gaussian_smooth_matches_reference_fixture(golden_dir):
         s = g[f"{tag}.sigma"].tolist()
         y = otr.gaussian_smooth(img, s[0] if len(s) == 1 else s)
         np.testing.assert_allclose(y.numpy(), g[f"{tag}.y"], rtol=1e-5, atol=1e-6)
+
+
+def test_post_transforms_oracle_matches_reference_fixture(golden_dir):
+    """Activations / AsDiscrete restatement vs outputs of the real reference (tests/golden/make_golden.py post), incl. argmax ties."""
+    g = np.load(os.path.join(golden_dir, "post.npz"))
+    logits = torch.from_numpy(g["logits"])
+    np.testing.assert_allclose(otr.activations(logits, softmax=True).numpy(), g["softmax"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(otr.activations(logits, sigmoid=True).numpy(), g["sigmoid"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(otr.as_discrete(logits, argmax=True).numpy(), g["argmax"])
+    np.testing.assert_array_equal(otr.as_discrete(logits, argmax=True, to_onehot=3).numpy(), g["argmax_onehot"])
+    np.testing.assert_array_equal(otr.as_discrete(logits, threshold=0.25).numpy(), g["threshold"])
+    r = torch.tensor([[0.5, 1.5, 2.5, -0.5, -1.5, 0.49, 2.51]])
+    np.testing.assert_array_equal(otr.as_discrete(r, rounding="torchrounding").numpy(), g["round"])
+    np.testing.assert_array_equal(otr.as_discrete(torch.from_numpy(g["labels"]), to_onehot=3).numpy(), g["onehot"])
+    np.testing.assert_array_equal(otr.as_discrete(otr.activations(logits, sigmoid=True), threshold=0.5).numpy(), g["sigmoid_threshold"])
+    assert g["argmax"][0, 0, 0, 0] == 0 and g["argmax"][0, 1, 1, 1] in (1.0, 2.0)
