@@ -227,6 +227,12 @@ int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H, int W, con
 int b200_channel_post(const void* x, int in_dtype, int C, long long S, int op, float param, int onehot, void* y, int out_dtype,
                       void* stream);
 
+/* AvgMerger of PatchInferer (monai/inferers/merger.py:103-205).  accumulate: values[NC][md][mh][mw] (fp32) += patch[NC][pd][ph][pw]
+ * at spatial location (ld, lh, lw) and counts += 1 there (counts: uint8 (count_bytes 1) or int32 (4)); finalize: values /= counts. */
+int b200_patch_accumulate(const void* patch, int dtype, long long NC, int pd, int ph, int pw, float* values, void* counts, int count_bytes,
+                          int md, int mh, int mw, int ld, int lh, int lw, void* stream);
+int b200_patch_finalize(float* values, const void* counts, int count_bytes, long long total, void* stream);
+
 /* 1x1x1 output head (UnetOutBlock, dynunet_block.py:247-267): NC8 fp16 [N][C/8][S][8] -> NCDHW [N][Cout][S]. */
 int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,
                        void* y, int out_dtype, void* stream);

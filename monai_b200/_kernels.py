@@ -274,6 +274,26 @@ def separable_filter3d(src: torch.Tensor, taps: Sequence[torch.Tensor]) -> torch
     return dst
 
 
+def patch_accumulate(patch: torch.Tensor, values: torch.Tensor, counts: torch.Tensor, location: Sequence[int]) -> None:
+    """values[:, :, loc : loc + patch_size] += patch, counts[...] += 1 (1-3 spatial dims, lifted to 3)."""
+    L.require_cuda(patch)
+    patch = patch.contiguous()
+    nd = patch.dim() - 2
+    if nd < 1 or nd > 3 or values.dim() != patch.dim() or counts.shape != values.shape or tuple(values.shape[:2]) != tuple(patch.shape[:2]):
+        raise ValueError(f"patch {tuple(patch.shape)} / merged {tuple(values.shape)} shapes are incompatible")
+    if values.dtype != torch.float32 or not values.is_contiguous() or not counts.is_contiguous() or counts.dtype not in (torch.uint8, torch.int32):
+        raise ValueError("AvgMerger buffers must be contiguous float32 values and uint8 / int32 counts")
+    ps = (1,) * (3 - nd) + tuple(patch.shape[2:])
+    ms = (1,) * (3 - nd) + tuple(values.shape[2:])
+    loc = (0,) * (3 - nd) + tuple(int(v) for v in location)
+    _call("patch_accumulate", L.ptr(patch), L.dt(patch), patch.shape[0] * patch.shape[1], *ps, L.ptr(values), L.ptr(counts), counts.element_size(), *ms, *loc,
+          L.stream_ptr(patch.device), nbytes=_nb(patch) + 2.0 * patch.numel() * (4 + counts.element_size()))
+
+
+def patch_finalize(values: torch.Tensor, counts: torch.Tensor) -> None:
+    _call("patch_finalize", L.ptr(values), L.ptr(counts), counts.element_size(), values.numel(), L.stream_ptr(values.device), nbytes=_nb(values, counts) + _nb(values))
+
+
 POST_SOFTMAX, POST_SIGMOID, POST_ARGMAX, POST_THRESHOLD, POST_ROUND, POST_ONEHOT = range(6)
 
 

@@ -64,9 +64,63 @@ __global__ void __launch_bounds__(256) elementwise_post_kernel(const TI* __restr
   }
 }
 
+// AvgMerger (monai/inferers/merger.py:103-205): values[.., loc : loc + patch] += patch, counts[..] += 1; finalize: values /= counts.
+// One thread per patch element; a patch covers each merged element at most once per call, so no atomics are needed.
+template <typename TI, typename TC>
+__global__ void __launch_bounds__(256) patch_accumulate_kernel(const TI* __restrict__ patch, float* __restrict__ values, TC* __restrict__ counts,
+                                                               long long NC, int pd, int ph, int pw, int md, int mh, int mw, int ld, int lh,
+                                                               int lw) {
+  const long long pvol = (long long)pd * ph * pw, mvol = (long long)md * mh * mw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < NC * pvol; i += (long long)gridDim.x * blockDim.x) {
+    const long long nc = i / pvol, r = i - nc * pvol;
+    const int w = (int)(r % pw), h = (int)((r / pw) % ph), d = (int)(r / ((long long)pw * ph));
+    const long long o = nc * mvol + ((long long)(ld + d) * mh + (lh + h)) * mw + (lw + w);
+    values[o] += io<TI>::ld(patch + i);
+    counts[o] = (TC)(counts[o] + 1);
+  }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(256) patch_finalize_kernel(float* __restrict__ values, const TC* __restrict__ counts, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    values[i] = __fdiv_rn(values[i], (float)counts[i]);   // 0 / 0 -> NaN for never-covered elements, as values.div_(counts) gives
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_patch_accumulate(const void* patch, int dtype, long long NC, int pd, int ph, int pw, float* values, void* counts,
+                                     int count_bytes, int md, int mh, int mw, int ld, int lh, int lw, void* stream) {
+  B200_REQUIRE(patch && values && counts, "patch_accumulate: null pointer");
+  B200_REQUIRE(count_bytes == 1 || count_bytes == 4, "patch_accumulate: counts must be uint8 or int32");
+  B200_REQUIRE(NC >= 0 && pd > 0 && ph > 0 && pw > 0, "patch_accumulate: bad patch shape");
+  B200_REQUIRE(ld >= 0 && lh >= 0 && lw >= 0 && ld + pd <= md && lh + ph <= mh && lw + pw <= mw,
+               "patch_accumulate: patch at (%d,%d,%d) of size (%d,%d,%d) leaves the merged volume (%d,%d,%d)", ld, lh, lw, pd, ph, pw, md, mh, mw);
+  const long long total = NC * pd * ph * pw;
+  if (total == 0) return B200_OK;
+  const unsigned blocks = (unsigned)std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LPA(TI, TC) patch_accumulate_kernel<TI, TC><<<blocks, 256, 0, st>>>((const TI*)patch, values, (TC*)counts, NC, pd, ph, pw, md, mh, mw, ld, lh, lw)
+  if (dtype == B200_DT_F32) { if (count_bytes == 1) LPA(float, unsigned char); else LPA(float, int); }
+  else if (dtype == B200_DT_F16) { if (count_bytes == 1) LPA(__half, unsigned char); else LPA(__half, int); }
+  else return set_err(B200_ERR_INVALID, "patch_accumulate: bad dtype");
+#undef LPA
+  B200_LAUNCH_CHECK("patch_accumulate_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_patch_finalize(float* values, const void* counts, int count_bytes, long long total, void* stream) {
+  B200_REQUIRE(values && counts, "patch_finalize: null pointer");
+  B200_REQUIRE(count_bytes == 1 || count_bytes == 4, "patch_finalize: counts must be uint8 or int32");
+  if (total <= 0) return B200_OK;
+  const unsigned blocks = (unsigned)std::min<long long>(ceil_div(total, 256), (long long)num_sms() * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (count_bytes == 1) patch_finalize_kernel<unsigned char><<<blocks, 256, 0, st>>>(values, (const unsigned char*)counts, total);
+  else patch_finalize_kernel<int><<<blocks, 256, 0, st>>>(values, (const int*)counts, total);
+  B200_LAUNCH_CHECK("patch_finalize_kernel");
+  return B200_OK;
+}
 
 #define B200_POST_DISPATCH(KERNEL_CALL)                                                            \
   if (in_dtype == B200_DT_F32 && out_dtype == B200_DT_F32) { using TI = float; using TO = float; KERNEL_CALL; }   \

@@ -1,4 +1,7 @@
-from .inferer import Inferer, SimpleInferer, SlidingWindowInferer, SlidingWindowInfererAdapt, SliceInferer
+from .inferer import Inferer, PatchInferer, SimpleInferer, SliceInferer, SlidingWindowInferer, SlidingWindowInfererAdapt
+from .merger import AvgMerger, Merger
+from .splitter import SlidingWindowSplitter, Splitter
 from .utils import sliding_window_inference
 
-__all__ = ["Inferer", "SimpleInferer", "SlidingWindowInferer", "SlidingWindowInfererAdapt", "SliceInferer", "sliding_window_inference"]
+__all__ = ["Inferer", "SimpleInferer", "PatchInferer", "SlidingWindowInferer", "SlidingWindowInfererAdapt", "SliceInferer", "Splitter",
+           "SlidingWindowSplitter", "Merger", "AvgMerger", "sliding_window_inference"]

@@ -15,9 +15,11 @@ from typing import Any
 import torch
 
 from ..data.utils import compute_importance_map
+from .merger import AvgMerger, Merger
+from .splitter import Splitter
 from .utils import sliding_window_inference
 
-__all__ = ["Inferer", "SimpleInferer", "SlidingWindowInferer", "SlidingWindowInfererAdapt", "SliceInferer"]
+__all__ = ["Inferer", "SimpleInferer", "PatchInferer", "SlidingWindowInferer", "SlidingWindowInfererAdapt", "SliceInferer"]
 
 
 class Inferer(ABC):
@@ -165,3 +167,126 @@ class SliceInferer(SlidingWindowInferer):
         if isinstance(out, Mapping):
             return {k: v.unsqueeze(dim=dim) for k, v in out.items()}
         return tuple(o.unsqueeze(dim=dim) for o in out)
+
+
+class PatchInferer(Inferer):
+    """Inference on patches from a `Splitter`, merged by a `Merger` (reference: monai/inferers/inferer.py:100-370).  Same
+    constructor / call contract: `batch_size` patches are concatenated per network call, `preprocessing` / `postprocessing`
+    wrap the network, tuple / dict outputs get one merger each (`output_keys` selects and orders dict entries), output
+    patches may be resized with respect to the input patches (the location is scaled by the size ratio), and
+    `match_spatial_shape` crops the padded merge back to the (scaled) input shape.  `buffer_size` (a background sampling
+    thread in the reference) is accepted and ignored: splitting here is a view of a device tensor."""
+
+    def __init__(self, splitter: Splitter | None = None, merger_cls: type[Merger] | str = AvgMerger, batch_size: int = 1,
+                 preprocessing: Callable | None = None, postprocessing: Callable | None = None, output_keys: Sequence | None = None,
+                 match_spatial_shape: bool = True, buffer_size: int = 0, **merger_kwargs: Any) -> None:
+        Inferer.__init__(self)
+        if not isinstance(splitter, (Splitter, type(None))):
+            raise TypeError(
+                f"'splitter' should be a `Splitter` object that returns: "
+                "an iterable of pairs of (patch, location) or a MetaTensor that has `PatchKeys.LOCATION` metadata)."
+                f"{type(splitter)} is given."
+            )
+        self.splitter = splitter
+        if isinstance(merger_cls, str):
+            from . import merger as _merger_mod
+
+            found = getattr(_merger_mod, merger_cls, None)
+            if found is None:
+                from pydoc import locate
+
+                found = locate(merger_cls)
+            if found is None:
+                raise ValueError(f"The requested `merger_cls` ['{merger_cls}'] does not exist.")
+            merger_cls = found
+        if not (isinstance(merger_cls, type) and issubclass(merger_cls, Merger)):
+            raise TypeError(f"'merger' should be a subclass of `Merger`, {merger_cls} is given.")
+        self.merger_cls = merger_cls
+        self.merger_kwargs = merger_kwargs
+        if preprocessing is not None and not callable(preprocessing):
+            raise TypeError(f"'preprocessing' should be a callable object, {type(preprocessing)} is given.")
+        self.preprocessing = preprocessing
+        if postprocessing is not None and not callable(postprocessing):
+            raise TypeError(f"'postprocessing' should be a callable object, {type(postprocessing)} is given.")
+        self.postprocessing = postprocessing
+        if batch_size < 1:
+            raise ValueError(f"`batch_size` must be a positive number, {batch_size} is given.")
+        self.batch_size = batch_size
+        self.output_keys = output_keys
+        self.match_spatial_shape = match_spatial_shape
+        self.buffer_size = buffer_size
+
+    def _batches(self, patches):
+        batch, locs = [], []
+        for patch, loc in patches:
+            batch.append(patch)
+            locs.append(loc)
+            if len(batch) == self.batch_size:
+                yield torch.cat(batch), locs, len(batch)
+                batch, locs = [], []
+        if batch:
+            yield torch.cat(batch), locs, len(batch)
+
+    def _as_tuple(self, outputs: Any) -> tuple:
+        if isinstance(outputs, dict):
+            if self.output_keys is None:
+                self.output_keys = list(outputs.keys())
+            return tuple(outputs[k] for k in self.output_keys)
+        return tuple(outputs) if isinstance(outputs, (list, tuple)) else (outputs,)
+
+    def _merged_shapes(self, inputs, out_patch, ratio):
+        if self.splitter is None:
+            return None, None
+        original = self.splitter.get_input_shape(inputs)
+        padded = self.splitter.get_padded_shape(inputs)
+        cropped_shape = tuple(out_patch.shape[:2]) + tuple(round(s * r) for s, r in zip(original, ratio))
+        merged_shape = tuple(out_patch.shape[:2]) + tuple(round(s * r) for s, r in zip(padded, ratio))
+        if not self.match_spatial_shape:
+            cropped_shape = merged_shape
+        return cropped_shape, merged_shape
+
+    def __call__(self, inputs: torch.Tensor, network: Callable, *args: Any, **kwargs: Any) -> Any:
+        if self.splitter is None:
+            if isinstance(inputs, torch.Tensor):
+                raise ValueError(
+                    "`splitter` should be set if the input is not already split into patches. "
+                    "For inputs that are split, the location of patches needs to be provided as "
+                    "(image, location) pairs, or as `PatchKey.LOCATION` metadata in a MetaTensor. "
+                    f"The provided inputs type is {type(inputs)}."
+                )
+            patches_locations = inputs
+        else:
+            patches_locations = self.splitter(inputs)
+        mergers: list[Merger] = []
+        ratios: list[tuple] = []
+        for patches, locations, nb in self._batches(patches_locations):
+            if self.preprocessing:
+                patches = self.preprocessing(patches)
+            outputs = network(patches, *args, **kwargs)
+            if self.postprocessing:
+                outputs = self.postprocessing(outputs)
+            outputs = self._as_tuple(outputs)
+            if not mergers:
+                in_patch = torch.chunk(patches, nb)[0]
+                for out_batch in outputs:
+                    out_patch = torch.chunk(out_batch, nb)[0]
+                    ratio = tuple(op / ip for ip, op in zip(in_patch.shape[2:], out_patch.shape[2:]))
+                    mk = dict(self.merger_kwargs)
+                    cropped_shape, merged_shape = self._merged_shapes(inputs, out_patch, ratio)
+                    if "merged_shape" not in mk:
+                        mk["merged_shape"] = merged_shape
+                        if mk["merged_shape"] is None:
+                            raise ValueError("`merged_shape` cannot be `None`.")
+                    if "cropped_shape" not in mk:
+                        mk["cropped_shape"] = cropped_shape
+                    if "device" not in mk and issubclass(self.merger_cls, AvgMerger):
+                        mk["device"] = out_patch.device
+                    mergers.append(self.merger_cls(**mk))
+                    ratios.append(ratio)
+            for out_batch, merger, ratio in zip(outputs, mergers, ratios):
+                for in_loc, out_patch in zip(locations, torch.chunk(out_batch, nb)):
+                    merger.aggregate(out_patch, [round(l * r) for l, r in zip(in_loc, ratio)])
+        merged = [m.finalize() for m in mergers]
+        if self.output_keys:
+            return dict(zip(self.output_keys, merged))
+        return merged[0] if len(merged) == 1 else merged

@@ -208,8 +208,48 @@ def post():
     save("post.npz", **out)
 
 
+from make_golden_cases import PATCH_CASES  # noqa: E402
+
+
+def _patch_net(p):          # tuple output: same size and a half-resolution head
+    return p * 2.0 + 1.0, torch.nn.functional.avg_pool3d(p, 2) - 0.5
+
+
+def patch():
+    """SlidingWindowSplitter grids / patches and PatchInferer(AvgMerger) outputs of the real reference."""
+    from monai.inferers import AvgMerger, PatchInferer, SlidingWindowSplitter
+
+    out = {}
+    g = torch.Generator().manual_seed(44)
+    for name, (shape, kw) in PATCH_CASES.items():
+        x = torch.rand(shape, generator=g)
+        s = SlidingWindowSplitter(**kw)
+        pl = list(s(x))
+        out[f"{name}.x"] = x.numpy()
+        out[f"{name}.loc"] = np.array([l for _, l in pl], dtype=np.int64)
+        out[f"{name}.patches"] = torch.stack([p for p, _ in pl]).numpy()
+        out[f"{name}.padded_shape"] = np.array(s.get_padded_shape(x), dtype=np.int64)
+    # filter_fn
+    x = torch.from_numpy(out["p2d.x"])
+    s = SlidingWindowSplitter(filter_fn=lambda patch, loc: loc[0] >= 1 and float(patch.mean()) > 0.4, **PATCH_CASES["p2d"][1])
+    out["p2d.filtered_loc"] = np.array([l for _, l in s(x)], dtype=np.int64)
+    # PatchInferer: tuple output with a resized head, batches of 3, cropped back to the input extent
+    x3 = torch.rand((1, 1, 10, 12, 10), generator=g)
+    out["pi.x"] = x3.numpy()
+    inf = PatchInferer(splitter=SlidingWindowSplitter(patch_size=4, overlap=0.5, pad_mode="constant"), merger_cls=AvgMerger, batch_size=3)
+    a, b = inf(x3, _patch_net)
+    out["pi.same"], out["pi.half"] = a.numpy(), b.numpy()
+    # dict output with selected keys, no cropping of the padded merge, pre / post processing
+    inf = PatchInferer(splitter=SlidingWindowSplitter(patch_size=(4, 5, 4), overlap=(2, 0, 1), pad_mode="constant", pad_value=0.25),
+                       batch_size=2, preprocessing=lambda p: p + 1.0, postprocessing=lambda o: {"a": o[0], "b": o[1], "c": o[0] * 0},
+                       output_keys=["b", "a"], match_spatial_shape=False)
+    d = inf(x3, _patch_net)
+    out["pi.dict_b"], out["pi.dict_a"] = d["b"].numpy(), d["a"].numpy()
+    save("patch.npz", **out)
+
+
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms", "post"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms", "post", "patch"]
     for w in which:
         globals()[w]()

@@ -173,6 +173,44 @@ def test_slice_inferer_equals_per_slice_prediction(spatial_dim):
     torch.testing.assert_close(got_d["a"], want, rtol=1e-6, atol=1e-6)
 
 
+def test_patch_inferer_matches_reference_fixture(golden_dir):
+    """PatchInferer(SlidingWindowSplitter, AvgMerger) vs the real reference (tests/golden/make_golden.py patch): tuple output
+    with a half-resolution head (location scaled by the size ratio), batches of 3, cropping of the padded merge; dict output
+    with selected keys, pre / post processing and `match_spatial_shape=False`; merger bookkeeping of AvgMerger."""
+    from monai_b200.inferers import AvgMerger, PatchInferer, SlidingWindowSplitter
+
+    def net(p):
+        return p * 2.0 + 1.0, torch.nn.functional.avg_pool3d(p, 2) - 0.5
+
+    g = np.load(os.path.join(golden_dir, "patch.npz"))
+    x = torch.from_numpy(g["pi.x"]).to(DEV)
+    inf = PatchInferer(splitter=SlidingWindowSplitter(patch_size=4, overlap=0.5, pad_mode="constant"), merger_cls=AvgMerger, batch_size=3)
+    a, b = inf(x, net)
+    assert a.dtype == torch.float32 and tuple(a.shape) == g["pi.same"].shape and tuple(b.shape) == g["pi.half"].shape
+    np.testing.assert_allclose(a.cpu().numpy(), g["pi.same"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(b.cpu().numpy(), g["pi.half"], rtol=1e-6, atol=1e-6)
+    inf = PatchInferer(splitter=SlidingWindowSplitter(patch_size=(4, 5, 4), overlap=(2, 0, 1), pad_mode="constant", pad_value=0.25),
+                       batch_size=2, preprocessing=lambda p: p + 1.0, postprocessing=lambda o: {"a": o[0], "b": o[1], "c": o[0] * 0},
+                       output_keys=["b", "a"], match_spatial_shape=False)
+    d = inf(x, net)
+    assert list(d.keys()) == ["b", "a"]
+    np.testing.assert_allclose(d["b"].cpu().numpy(), g["pi.dict_b"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(d["a"].cpu().numpy(), g["pi.dict_a"], rtol=1e-6, atol=1e-6)
+    # AvgMerger on its own: counts, fp16 patches, finalisation guard, never-covered elements are NaN as in the reference
+    m = AvgMerger(merged_shape=(1, 2, 6, 6), device=DEV)
+    p = torch.ones((1, 2, 4, 4), device=DEV).half()
+    m.aggregate(p, (0, 0))
+    m.aggregate(p * 3, (2, 2))
+    assert m.get_counts().dtype == torch.uint8 and int(m.get_counts()[0, 0, 2, 2]) == 2 and int(m.get_counts()[0, 1, 5, 0]) == 0
+    out = m.finalize()
+    assert float(out[0, 0, 0, 0]) == 1.0 and float(out[0, 1, 3, 3]) == 2.0 and float(out[0, 0, 5, 5]) == 3.0 and bool(torch.isnan(out[0, 0, 5, 0]))
+    assert m.finalize() is out
+    with pytest.raises(ValueError, match="already finalized"):
+        m.aggregate(p, (0, 0))
+    with pytest.raises(RuntimeError, match="leaves the merged volume"):
+        AvgMerger(merged_shape=(1, 2, 6, 6), device=DEV).aggregate(p, (3, 3))
+
+
 def test_tma_staged_blend_is_bit_identical(tmp_path):
     """The TMA-staged blend (opt-in: B200_BLEND_TMA=1, read once per process) must reproduce the default kernels bit for bit on
     fp16 predictions, one-shot and streaming.  It runs in a child process because the switch is latched at first use."""

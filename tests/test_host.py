@@ -3,6 +3,7 @@ loads and exports every symbol include/monai_b200.h declares, and argument valid
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -109,3 +110,68 @@ def test_slice_inferer_argument_errors_match_reference():
         SliceInferer(roi_size=(8, 8), spatial_dim=0, sw_batch_size=1)(torch.zeros(1, 1, 8, 8), lambda t: t)
     inf = SliceInferer(roi_size=(8, 8), spatial_dim=1, sw_batch_size=2, cval=-1)
     assert inf.orig_roi_size == (8, 8) and inf.cval == -1 and inf.sw_batch_size == 2
+
+
+def test_sliding_window_splitter_matches_reference_fixture(golden_dir):
+    """Patch grid, padding (constant / replicate / none), negative offsets, int and float overlaps and filter_fn of
+    SlidingWindowSplitter vs the real reference (tests/golden/make_golden.py patch); splitting is indexing, so CPU tensors work."""
+    import os
+
+    import numpy as np
+    import pytest
+    import torch
+
+    sys.path.insert(0, golden_dir)
+    from make_golden_cases import PATCH_CASES  # noqa: F401  (kept in a tiny module so the tests do not import the reference)
+
+    from monai_b200.inferers import SlidingWindowSplitter
+
+    g = np.load(os.path.join(golden_dir, "patch.npz"))
+    for name, (shape, kw) in PATCH_CASES.items():
+        x = torch.from_numpy(g[f"{name}.x"])
+        assert tuple(x.shape) == shape
+        s = SlidingWindowSplitter(**kw)
+        pl = list(s(x))
+        np.testing.assert_array_equal(np.array([l for _, l in pl], dtype=np.int64), g[f"{name}.loc"], err_msg=name)
+        np.testing.assert_array_equal(torch.stack([p for p, _ in pl]).numpy(), g[f"{name}.patches"], err_msg=name)
+        assert tuple(s.get_padded_shape(x)) == tuple(g[f"{name}.padded_shape"]), name
+    x = torch.from_numpy(g["p2d.x"])
+    s = SlidingWindowSplitter(filter_fn=lambda patch, loc: loc[0] >= 1 and float(patch.mean()) > 0.4, **PATCH_CASES["p2d"][1])
+    np.testing.assert_array_equal(np.array([l for _, l in s(x)], dtype=np.int64), g["p2d.filtered_loc"])
+    # argument validation of the reference
+    with pytest.raises(ValueError, match="Relative overlap must be between"):
+        SlidingWindowSplitter(4, overlap=1.0)
+    with pytest.raises(ValueError, match="cannot be negative"):
+        SlidingWindowSplitter(4, overlap=-1)
+    with pytest.raises(ValueError, match="requires a valid padding mode"):
+        SlidingWindowSplitter(4, offset=-1, pad_mode=None)
+    with pytest.raises(ValueError, match="at least two parameters"):
+        SlidingWindowSplitter(4, filter_fn=lambda p: True)
+    with pytest.raises(ValueError, match="cannot be larger than patch size"):
+        list(SlidingWindowSplitter(4, overlap=5)(torch.zeros(1, 1, 8, 8)))
+    with pytest.raises(ValueError, match="cannot be larger than inputs size"):
+        list(SlidingWindowSplitter(4, offset=9)(torch.zeros(1, 1, 8, 8)))
+
+
+def test_patch_inferer_argument_errors():
+    import pytest
+    import torch
+
+    from monai_b200.inferers import AvgMerger, PatchInferer, SlidingWindowSplitter
+
+    with pytest.raises(TypeError, match="'splitter' should be a `Splitter`"):
+        PatchInferer(splitter=lambda x: x)
+    with pytest.raises(ValueError, match="does not exist"):
+        PatchInferer(merger_cls="NoSuchMerger")
+    with pytest.raises(TypeError, match="subclass of `Merger`"):
+        PatchInferer(merger_cls=dict)
+    with pytest.raises(ValueError, match="positive number"):
+        PatchInferer(batch_size=0)
+    with pytest.raises(TypeError, match="'preprocessing' should be a callable"):
+        PatchInferer(preprocessing=3)
+    with pytest.raises(ValueError, match="`splitter` should be set"):
+        PatchInferer()(torch.zeros(1, 1, 4, 4), lambda p: p)
+    assert PatchInferer(merger_cls="AvgMerger").merger_cls is AvgMerger
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        AvgMerger(merged_shape=(1, 1, 4, 4), device="cpu")
+    assert isinstance(PatchInferer(splitter=SlidingWindowSplitter(4)).splitter, SlidingWindowSplitter)
