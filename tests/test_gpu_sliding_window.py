@@ -207,7 +207,7 @@ def test_patch_inferer_matches_reference_fixture(golden_dir):
     assert m.finalize() is out
     with pytest.raises(ValueError, match="already finalized"):
         m.aggregate(p, (0, 0))
-    with pytest.raises(RuntimeError, match="leaves the merged volume"):
+    with pytest.raises(ValueError, match="leaves the merged volume"):
         AvgMerger(merged_shape=(1, 2, 6, 6), device=DEV).aggregate(p, (3, 3))
 
 
