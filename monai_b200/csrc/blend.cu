@@ -4,8 +4,9 @@
 // (weighted scatter-add) and :297-298 (normalise) of the reference.  The blend is written in *gather form*:
 // one thread owns one output voxel and walks the (Cartesian) window table in ascending window index, so
 //   out[b,c,v] = ( sum_w imp(v - s_w) * pred_w[c, v - s_w] ) / ( sum_w imp(v - s_w) )
-// is produced with the same fp32 operation order as the reference loop (mul, then sequential adds, then one
-// IEEE divide) and the count map is never materialised.  imp() is evaluated on the fly from the three 1-D
+// is produced, for fp32 predictions, with the same fp32 operation order as the reference loop (mul, then sequential
+// adds, then one IEEE divide); fp16 predictions use one fused multiply-add per term (blend_acc).  The count map is
+// never materialised.  imp() is evaluated on the fly from the three 1-D
 // vectors of compute_importance_map (monai/data/utils.py:1084-1134): ((g_d*g_h)*g_w) clamped from below.
 #include "common.cuh"
 #include "tc05.cuh"

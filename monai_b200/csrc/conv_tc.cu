@@ -10,11 +10,12 @@
 //
 // GEMM view: M = 128 output voxels (one 16(H) x 8(W) patch of one D-plane), N = NT output channels, K = 27*Cin.
 // Per K-slice of 16 input channels the CTA stages ONE halo tile (BD+2) x 18 x 10 voxels with a single 5-D TMA
-// box load (out-of-bounds => zero fill == the convolution's zero padding) and issues the 27 taps as 27 UMMA
-// instructions whose A descriptors merely start at a shifted voxel of that tile (start += ((kd*18+kh)*10+kw)*16 B,
+// box load (out-of-bounds => zero fill == the convolution's zero padding) and issues the taps as UMMA instructions
+// whose A descriptors merely start at a shifted voxel of that tile (start += ((plane*18+kh)*10+kw)*16 B,
 // SBO = 10*16 B between the 16 row groups, LBO = chunk stride).  Weights are pre-packed into the exact B-operand
-// image and arrive by 1-D bulk copies.  fp32 accumulators live in TMEM (BD planes x NT columns); the epilogue
-// reads them back with tcgen05.ld, adds bias, reduces InstanceNorm partial sums and stores fp16 NC8.
+// image and arrive by 1-D bulk copies (one (kh, kw) tap image per ring stage).  fp32 accumulators live in TMEM (one or
+// two sets of BD planes x NT columns); the epilogue reads them back with tcgen05.ld, adds bias, reduces InstanceNorm
+// partial sums and stores fp16 NC8.  The kernel is persistent: one CTA per SM walks the tile list (see the kernel).
 //
 // Depth-fused N: with the operands in shared memory an MMA of N = 48 is bound by the 4 KB A read, not by the tensor
 // pipe (24 cycles of math against ~44 cycles of operand traffic).  The loop therefore walks the INPUT planes of the

@@ -11,8 +11,8 @@
 // contiguous in HBM and lands in shared memory as the UMMA K-major / no-swizzle core-matrix column
 // (LBO = 128*16 B between K chunks, SBO = 128 B between 8-row groups).  W is pre-packed into the B image
 // [nt][k16][khalf][NT/8][8][8] and streamed with 1-D bulk copies.  fp32 accumulators live in TMEM.
-// Epilogue (4 warps, one TMEM lane quarter each): + bias, GELU(erf), + residual, InstanceNorm partial sums, and a
-// row map (identity / index table / 2x upsample scatter) before the fp16 NC8 store.
+// Epilogue (16 warps, four per TMEM lane quarter, variant chosen at compile time): + bias, GELU(erf), + residual,
+// InstanceNorm partial sums, and a row map (identity / index table / 2x upsample scatter) before the fp16 NC8 store.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "../../include/monai_b200.h"
