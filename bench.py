@@ -186,7 +186,9 @@ def cpu_baseline_leg(wl, budget_s: float = 20.0) -> dict:
     t_all = time.perf_counter()
     with torch.no_grad():
         # oneDNN/ATen on many-core hosts can lose to a smaller pool on these small windows: take the best thread count
-        for threads in sorted({cores, min(cores, 32)} if wl["net"] != "unet_c2" else {cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+        # 32 threads first (the best pool on the many-core hosts measured so far), wider pools only while the budget lasts
+        order = [min(cores, 32), cores] if wl["net"] != "unet_c2" else [min(cores, 32), min(cores, 16), min(cores, 64), cores]
+        for threads in list(dict.fromkeys(order)):
             torch.set_num_threads(threads)
             for rep in range(2):
                 t0 = time.perf_counter()
