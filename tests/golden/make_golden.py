@@ -248,8 +248,78 @@ def patch():
     save("patch.npz", **out)
 
 
+def unit_goldens():
+    """Golden vectors of the reference's OWN unit tests, read mechanically from the TESTS lists of the
+    test modules under /root/reference/tests (a stub stands in for the `parameterized` decorator package, which this image
+    lacks): Spacing, GaussianSmooth, Activations, AsDiscrete and the 3-D RandAffined cases (seed 123).  Inputs, arguments and
+    expected outputs are stored side by side; nothing is recomputed here."""
+    import json
+    import types
+
+    stub = types.ModuleType("parameterized")
+
+    class _P:
+        @staticmethod
+        def expand(*a, **k):
+            return lambda fn: fn
+
+    stub.parameterized = _P()
+    sys.modules["parameterized"] = stub
+    import tests.transforms.test_activations as t_act
+    import tests.transforms.test_as_discrete as t_dis
+    import tests.transforms.test_gaussian_smooth as t_gau
+    import tests.transforms.test_rand_affined as t_rad
+    import tests.transforms.test_spacing as t_spa
+
+    def arr(v):
+        return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+
+    def plain(d):
+        out = {}
+        for k, v in d.items():
+            if k in ("device", "dtype"):
+                continue
+            if isinstance(v, torch.Tensor):
+                v = v.tolist()
+            elif isinstance(v, np.ndarray):
+                v = v.tolist()
+            elif callable(v):
+                v = f"<callable {getattr(v, '__name__', 'fn')}>"
+            out[k] = list(v) if isinstance(v, tuple) else v
+        return out
+
+    out, index = {}, []
+
+    def add(kind, i, init, call, data, expected, extra=None):
+        tag = f"{kind}{i}"
+        out[f"{tag}.x"], out[f"{tag}.y"] = arr(data).astype(np.float64), arr(expected).astype(np.float64)
+        rec = {"tag": tag, "kind": kind, "init": plain(init), "call": plain(call)}
+        if extra:
+            for k, v in extra.items():
+                if isinstance(v, (torch.Tensor, np.ndarray)):
+                    out[f"{tag}.{k}"] = arr(v).astype(np.float64)
+                else:
+                    rec[k] = v
+        index.append(rec)
+
+    for i, c in enumerate(t_spa.TESTS):
+        if arr(c[1]).size <= 100000:      # the 368x336x368 shape-only case carries no golden values worth 45 M elements
+            add("spacing", i, c[0], c[3], c[1], c[4], {"affine": c[2]})
+    for i, c in enumerate(t_gau.TESTS):
+        add("gauss", i, c[0], {}, c[1], c[2])
+    for i, c in enumerate(t_act.TEST_CASES):
+        add("act", i, c[0], {}, c[1], c[2])
+    for i, c in enumerate(t_dis.TEST_CASES):
+        add("disc", i, c[0], {}, c[1], c[2])
+    for i, c in enumerate(t_rad.TESTS):
+        if isinstance(c[1], dict) and "img" in c[1]:
+            add("randaffd", i, c[0], {}, c[1]["img"], c[2] if not isinstance(c[2], dict) else c[2]["img"], {"seed": 123})
+    out["index"] = np.array(json.dumps(index))
+    save("ref_unit_goldens.npz", **out)
+
+
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms", "post", "patch"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

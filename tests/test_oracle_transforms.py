@@ -82,3 +82,85 @@ def test_post_transforms_oracle_matches_reference_fixture(golden_dir):
     np.testing.assert_array_equal(otr.as_discrete(torch.from_numpy(g["labels"]), to_onehot=3).numpy(), g["onehot"])
     np.testing.assert_array_equal(otr.as_discrete(otr.activations(logits, sigmoid=True), threshold=0.5).numpy(), g["sigmoid_threshold"])
     assert g["argmax"][0, 0, 0, 0] == 0 and g["argmax"][0, 1, 1, 1] in (1.0, 2.0)
+
+
+def test_oracle_against_the_reference_unit_test_goldens(golden_dir):
+    """Every golden vector the reference's own unit tests hold for Spacing, GaussianSmooth, Activations, AsDiscrete and
+    RandAffined, extracted mechanically from the TESTS lists of /root/reference/tests/transforms
+    (tests/golden/make_golden.py unit_goldens -> ref_unit_goldens.npz).  Cases outside the oracle's scope are skipped by rule
+    and counted: `other=` callables / dim != 0 (user code, non-default axes), negative pixdims and 4-D spatial inputs, 2-D
+    RandAffined images (the oracle restates the 3-D path of config C4).  `spacing4` (align_corners=True over a unit-size
+    axis) is the one golden that depends on the torch version: the real reference run in this container returns ones, as
+    the oracle does, so it is held to the reference test's own tolerance (test_spacing.py: atol = rtol = 1e-1)."""
+    import json
+
+    g = np.load(os.path.join(golden_dir, "ref_unit_goldens.npz"))
+    index = json.loads(str(g["index"]))
+    ran, skipped = {}, {}
+    for rec in index:
+        tag, kind = rec["tag"], rec["kind"]
+        x = torch.from_numpy(g[tag + ".x"]).float()
+        want = g[tag + ".y"]
+        kw = {**rec["init"], **rec["call"]}
+        out = None
+        if kind == "spacing":
+            pix = np.atleast_1d(np.asarray(kw["pixdim"], dtype=np.float64))
+            if kw.get("scale_extent") or x.dim() - 1 > 3 or (pix <= 0).any():
+                skipped[kind] = skipped.get(kind, 0) + 1
+                continue
+            args = {k: kw[k] for k in ("diagonal", "mode", "padding_mode", "align_corners") if k in kw}
+            out, _ = otr.spacing(x, g[tag + ".affine"], pix, **args)
+        elif kind == "gauss":
+            out = otr.gaussian_smooth(x, kw["sigma"])
+        elif kind == "act":
+            if kw.get("other") or kw.get("dim", 0) != 0:
+                skipped[kind] = skipped.get(kind, 0) + 1
+                continue
+            out = otr.activations(x, sigmoid=kw.get("sigmoid", False), softmax=kw.get("softmax", False))
+        elif kind == "disc":
+            if kw.get("dim", 0) != 0 or x.dim() < 2:
+                skipped[kind] = skipped.get(kind, 0) + 1
+                continue
+            out = otr.as_discrete(x, argmax=kw.get("argmax", False), to_onehot=kw.get("to_onehot"), threshold=kw.get("threshold"),
+                                  rounding=kw.get("rounding"))
+        elif kind == "randaffd":
+            if x.dim() != 4:
+                skipped[kind] = skipped.get(kind, 0) + 1
+                continue
+            args = {k: kw[k] for k in ("rotate_range", "shear_range", "translate_range", "scale_range", "spatial_size", "mode", "padding_mode")
+                    if kw.get(k) is not None}
+            out, _ = otr.rand_affine(x, rec["seed"], **args)
+        got = out.numpy() if isinstance(out, torch.Tensor) else np.asarray(out)
+        tol = 1e-1 if tag == "spacing4" else 1e-4
+        assert got.shape == want.shape, (tag, kw, got.shape, want.shape)
+        np.testing.assert_allclose(got, want, rtol=tol, atol=tol, err_msg=f"{tag} {kw}")
+        ran[kind] = ran.get(kind, 0) + 1
+    assert ran == {"spacing": 15, "gauss": 9, "act": 6, "disc": 15, "randaffd": 6} and sum(ran.values()) == 51, (ran, skipped)
+
+
+# tests/networks/layers/test_gaussian.py:228-248 (inline goldens) and :281-307 (TEST_CASES_NORM_F: variance -> taps for the
+# "erf" and "sampled" approximations at extent 6, atol 1e-4)
+GAUSS1D_NORM_F = [
+    (0.5, [0.0, 0.0, 3.5762787e-07, 0.00020313263, 0.016743928, 0.22280261, 0.52049994, 0.22280261, 0.016743928, 0.00020313263, 3.5762787e-07, 0.0, 0.0],
+     [1.3086457e-16, 7.8354033e-12, 6.3491058e-08, 6.9626461e-05, 0.010333488, 0.20755373, 0.56418961, 0.20755373, 0.010333488, 6.9626461e-05,
+      6.3491058e-08, 7.8354033e-12, 1.3086457e-16]),
+]
+
+
+def test_gaussian_1d_reference_unit_test_goldens():
+    from monai_b200.networks.layers.convutils import gaussian_1d
+
+    for fn in (lambda s, t: otr.gaussian_1d_erf(s, t), lambda s, t: gaussian_1d(s, t)):
+        np.testing.assert_allclose(fn(0.5, 8).numpy(), [0.0, 2.9802e-07, 1.3496e-03, 1.5731e-01, 6.8269e-01, 1.5731e-01, 1.3496e-03, 2.9802e-07, 0.0],
+                                   rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(fn(1, 1).numpy(), [0.24173, 0.382925, 0.24173], rtol=1e-4)
+    np.testing.assert_allclose(gaussian_1d(1, 1, normalize=True).numpy(), [0.2790, 0.4420, 0.2790], rtol=1e-3)
+    for variance, erf_taps, sampled_taps in GAUSS1D_NORM_F:
+        sigma = float(np.sqrt(variance))
+        np.testing.assert_allclose(otr.gaussian_1d_erf(sigma, 6 / sigma).numpy(), erf_taps, atol=1e-4)
+        np.testing.assert_allclose(gaussian_1d(sigma, truncated=6 / sigma, approx="erf", normalize=False).numpy(), erf_taps, atol=1e-4)
+        np.testing.assert_allclose(gaussian_1d(sigma, truncated=6 / sigma, approx="sampled").numpy(), sampled_taps, atol=1e-4)
+    with pytest.raises(ValueError):
+        gaussian_1d(1, -10)
+    with pytest.raises(NotImplementedError):
+        gaussian_1d(1, 10, "wrong_arg")
