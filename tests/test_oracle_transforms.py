@@ -164,3 +164,25 @@ def test_gaussian_1d_reference_unit_test_goldens():
         gaussian_1d(1, -10)
     with pytest.raises(NotImplementedError):
         gaussian_1d(1, 10, "wrong_arg")
+
+
+def test_normalize_transform_and_to_norm_affine_reference_goldens():
+    """tests/networks/layers/test_affine_transform.py:27-86 (TEST_NORM_CASES / TEST_TO_NORM_AFFINE_CASES, zero_centered=False rows):
+    the index -> [-1, 1] normalisation that `spatial_resample` composes around the affine."""
+    norm_cases = [
+        ((4, 5), True, [[0.666667, 0, -1], [0, 0.5, -1], [0, 0, 1]]),
+        ((2, 4, 5), True, [[2.0, 0.0, 0.0, -1.0], [0.0, 0.6666667, 0.0, -1.0], [0.0, 0.0, 0.5, -1.0], [0.0, 0.0, 0.0, 1.0]]),
+        ((4, 5), False, [[0.5, 0.0, -0.75], [0.0, 0.4, -0.8], [0.0, 0.0, 1.0]]),
+        ((2, 4, 5), False, [[1.0, 0.0, 0.0, -0.5], [0.0, 0.5, 0.0, -0.75], [0.0, 0.0, 0.4, -0.8], [0.0, 0.0, 0.0, 1.0]]),
+    ]
+    for shape, align, expected in norm_cases:
+        np.testing.assert_allclose(otr._normalize_transform(shape, align).numpy(), np.array(expected), atol=1e-6)
+    to_norm_cases = [
+        (np.eye(3), (4, 6), (5, 3), True, [[1.3333334, 0.0, 0.33333337], [0.0, 0.4, -0.6], [0.0, 0.0, 1.0]]),
+        (np.eye(3), (4, 6), (5, 3), False, [[1.25, 0.0, 0.25], [0.0, 0.5, -0.5], [0.0, 0.0, 1.0]]),
+        (np.eye(4), (2, 4, 6), (3, 5, 3), True, [[2.0, 0.0, 0.0, 1.0], [0.0, 1.3333334, 0.0, 0.33333337], [0.0, 0.0, 0.4, -0.6], [0.0, 0.0, 0.0, 1.0]]),
+        (np.eye(4), (2, 4, 6), (3, 5, 3), False, [[1.5, 0.0, 0.0, 0.5], [0.0, 1.25, 0.0, 0.25], [0.0, 0.0, 0.5, -0.5], [0.0, 0.0, 0.0, 1.0]]),
+    ]
+    for affine, src, dst, align, expected in to_norm_cases:   # to_norm_affine = src_norm @ affine @ inv(dst_norm) (networks/utils.py:298-326)
+        got = otr._normalize_transform(src, align) @ torch.as_tensor(affine) @ torch.linalg.inv(otr._normalize_transform(dst, align))
+        np.testing.assert_allclose(got.numpy(), np.array(expected), atol=1e-6)
