@@ -64,3 +64,38 @@ def test_rand_affine_draw_order():
     g = t.rand_affine.rand_affine_grid
     rot, shear, trans, scale = otr.rand_affine_params(0, (0.2,) * 3, (), (5,) * 3, (0.1,) * 3)
     assert g.rotate_params == rot and g.translate_params == trans and g.scale_params == scale
+
+
+def test_spacing_host_algebra_reproduces_the_reference_unit_test_shapes(golden_dir):
+    """Spacing's host side (affine_to_spacing / zoom_affine / compute_shape_offset, float64 numpy) against the output shapes of
+    every golden case of the reference's tests/transforms/test_spacing.py (ref_unit_goldens.npz), negative pixdims and a
+    4-D spatial input included.  The resampler is stubbed: shapes are decided before any device work."""
+    import json
+    import os
+
+    import numpy as np
+    import torch
+
+    from monai_b200.data import MetaTensor
+    from monai_b200.transforms import Spacing
+
+    g = np.load(os.path.join(golden_dir, "ref_unit_goldens.npz"))
+    n = 0
+    for rec in json.loads(str(g["index"])):
+        if rec["kind"] != "spacing":
+            continue
+        tag = rec["tag"]
+        sp = Spacing(**rec["init"])
+        seen = {}
+
+        def stub(img, dst_affine=None, spatial_size=None, **kwargs):
+            seen["size"] = tuple(int(v) for v in spatial_size)
+            return img
+
+        sp.sp_resample = stub
+        x = torch.from_numpy(g[tag + ".x"]).float()
+        sp(MetaTensor(x, affine=torch.as_tensor(g[tag + ".affine"])), **rec["call"])
+        want = g[tag + ".y"].shape
+        assert seen["size"] == tuple(want[1 : 1 + len(seen["size"])]), (tag, rec["init"], seen["size"], want)
+        n += 1
+    assert n == 17
