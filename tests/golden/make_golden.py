@@ -314,6 +314,12 @@ def unit_goldens():
     for i, c in enumerate(t_rad.TESTS):
         if isinstance(c[1], dict) and "img" in c[1]:
             add("randaffd", i, c[0], {}, c[1]["img"], c[2] if not isinstance(c[2], dict) else c[2]["img"], {"seed": 123})
+    import tests.transforms.test_rand_affine as t_ra
+
+    for i, c in enumerate(t_ra.TESTS):
+        if isinstance(c[1], dict) and "img" in c[1]:
+            call = {k: v for k, v in c[1].items() if k != "img"}
+            add("randaff", i, c[0], call, c[1]["img"], c[2], {"seed": 123})
     out["index"] = np.array(json.dumps(index))
     save("ref_unit_goldens.npz", **out)
 

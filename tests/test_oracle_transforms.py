@@ -85,8 +85,8 @@ def test_post_transforms_oracle_matches_reference_fixture(golden_dir):
 
 
 def test_oracle_against_the_reference_unit_test_goldens(golden_dir):
-    """Every golden vector the reference's own unit tests hold for Spacing, GaussianSmooth, Activations, AsDiscrete and
-    RandAffined, extracted mechanically from the TESTS lists of /root/reference/tests/transforms
+    """Every golden vector the reference's own unit tests hold for Spacing, GaussianSmooth, Activations, AsDiscrete,
+    RandAffined and RandAffine, extracted mechanically from the TESTS lists of /root/reference/tests/transforms
     (tests/golden/make_golden.py unit_goldens -> ref_unit_goldens.npz).  Cases outside the oracle's scope are skipped by rule
     and counted: `other=` callables / dim != 0 (user code, non-default axes), negative pixdims and 4-D spatial inputs, 2-D
     RandAffined images (the oracle restates the 3-D path of config C4).  `spacing4` (align_corners=True over a unit-size
@@ -123,7 +123,7 @@ def test_oracle_against_the_reference_unit_test_goldens(golden_dir):
                 continue
             out = otr.as_discrete(x, argmax=kw.get("argmax", False), to_onehot=kw.get("to_onehot"), threshold=kw.get("threshold"),
                                   rounding=kw.get("rounding"))
-        elif kind == "randaffd":
+        elif kind in ("randaffd", "randaff"):
             if x.dim() != 4:
                 skipped[kind] = skipped.get(kind, 0) + 1
                 continue
@@ -135,7 +135,7 @@ def test_oracle_against_the_reference_unit_test_goldens(golden_dir):
         assert got.shape == want.shape, (tag, kw, got.shape, want.shape)
         np.testing.assert_allclose(got, want, rtol=tol, atol=tol, err_msg=f"{tag} {kw}")
         ran[kind] = ran.get(kind, 0) + 1
-    assert ran == {"spacing": 15, "gauss": 9, "act": 6, "disc": 15, "randaffd": 6} and sum(ran.values()) == 51, (ran, skipped)
+    assert ran == {"spacing": 15, "gauss": 9, "act": 6, "disc": 15, "randaffd": 6, "randaff": 24} and sum(ran.values()) == 75, (ran, skipped)
 
 
 # tests/networks/layers/test_gaussian.py:228-248 (inline goldens) and :281-307 (TEST_CASES_NORM_F: variance -> taps for the
