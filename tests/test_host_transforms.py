@@ -99,3 +99,35 @@ def test_spacing_host_algebra_reproduces_the_reference_unit_test_shapes(golden_d
         assert seen["size"] == tuple(want[1 : 1 + len(seen["size"])]), (tag, rec["init"], seen["size"], want)
         n += 1
     assert n == 17
+
+
+def test_spacingd_shapes_and_affines_of_the_reference_unit_tests(monkeypatch):
+    """tests/transforms/test_spacingd.py:28-99 (six dictionary cases: 3-D, 2-D with a 3x3 affine, no metadata, per-key modes,
+    keys with different affines): output shape and the MetaTensor affine after the transform.  Only the resampling kernel is
+    replaced (by a zero tensor of the requested shape); SpatialResample / Spacing / Spacingd bookkeeping runs as shipped."""
+    import numpy as np
+    import torch
+
+    import monai_b200.transforms.spatial as S
+    from monai_b200.data import MetaTensor
+    from monai_b200.transforms import Spacingd
+
+    monkeypatch.setattr(S, "_resample", lambda img, mat, r, out_shape, mode, padding_mode, align: torch.zeros((img.shape[0], *out_shape)))
+    ones = lambda *s: torch.ones(s)  # noqa: E731
+    cases = [
+        ({"image": MetaTensor(ones(2, 10, 15, 20), affine=torch.eye(4))}, dict(keys="image", pixdim=(1, 2, 1.4)), (2, 10, 8, 15), np.diag([1, 2, 1.4, 1.0])),
+        ({"image": MetaTensor(ones(2, 10, 20), affine=torch.eye(3))}, dict(keys="image", pixdim=(1, 2)), (2, 10, 10), np.diag((1, 2, 1))),
+        ({"image": MetaTensor(ones(2, 10, 20))}, dict(keys="image", pixdim=(1, 2)), (2, 10, 10), np.diag((1, 2, 1, 1))),
+        ({"image": MetaTensor(torch.arange(20.0).reshape(2, 1, 10), affine=torch.eye(4)), "seg": MetaTensor(ones(2, 1, 10), affine=torch.eye(4))},
+         dict(keys=("image", "seg"), mode="nearest", pixdim=(1, 0.2)), (2, 1, 46), np.diag((1, 0.2, 1, 1))),
+        ({"image": MetaTensor(ones(2, 1, 10), affine=torch.eye(4)), "seg": MetaTensor(ones(2, 1, 10), affine=torch.eye(4))},
+         dict(keys=("image", "seg"), mode=("bilinear", "nearest"), pixdim=(1, 0.2)), (2, 1, 46), np.diag((1, 0.2, 1, 1))),
+        ({"image": MetaTensor(ones(2, 1, 10), affine=torch.eye(4)), "seg1": MetaTensor(ones(2, 1, 10), affine=torch.diag(torch.tensor([2.0, 2, 2, 1]))),
+          "seg2": MetaTensor(ones(2, 1, 10), affine=torch.eye(4))},
+         dict(keys=("image", "seg1", "seg2"), mode=("bilinear", "nearest", "nearest"), pixdim=(1, 1, 1)), (2, 1, 10), np.diag((1, 1, 1, 1))),
+    ]
+    for data, kw, shape, affine in cases:
+        res = Spacingd(**kw)(data)
+        for key in data:
+            assert tuple(res[key].shape) == shape, (kw, key, tuple(res[key].shape))
+        np.testing.assert_allclose(res["image"].affine.numpy(), affine, atol=1e-9, err_msg=str(kw))
