@@ -173,32 +173,52 @@ def rand_affine_params(seed, rotate_range=(), shear_range=(), translate_range=()
 
 def rand_affine(img: torch.Tensor, seed, rotate_range=(), shear_range=(), translate_range=(), scale_range=(), spatial_size=None,
                 mode="bilinear", padding_mode="reflection"):
-    """RandAffined(prob=1) on one key: identity grid (create_grid, float32) -> affine @ grid -> Resample (float64)."""
+    """RandAffined(prob=1) on one key: identity grid (create_grid, float32) -> affine @ grid -> Resample (float64).
+    3-D images [C, D, H, W] (config C4) and 2-D images [C, H, W] (the 2-D goldens of the reference's unit tests):
+    create_rotate / _create_shear / create_translate / create_scale of monai/transforms/utils.py:859-1075 for both ranks."""
     rot, shear, trans, scale = rand_affine_params(seed, rotate_range, shear_range, translate_range, scale_range)
-    sp = list(img.shape[1:]) if spatial_size is None else list(spatial_size)
+    nd = img.dim() - 1
+    if nd not in (2, 3):
+        raise NotImplementedError("oracle rand_affine restates the 2-D and 3-D paths")
+    if spatial_size is None or isinstance(spatial_size, int):   # None / -1: the image's own size (fall_back_tuple)
+        sp = list(img.shape[1:])
+    else:
+        sp = [int(s) if int(s) > 0 else int(d) for s, d in zip(spatial_size, img.shape[1:])]
     axes = [torch.linspace(-(d - 1.0) / 2.0, (d - 1.0) / 2.0, int(d), dtype=torch.float32) for d in sp]
     coords = torch.meshgrid(*axes, indexing="ij")
     grid = torch.stack([*coords, torch.ones_like(coords[0])])
-    affine = torch.eye(4)
+    n = nd + 1
+    affine = torch.eye(n)
+    t32 = lambda v: torch.as_tensor(v, dtype=torch.float32)  # noqa: E731
     if rot:
-        affine = affine @ _create_rotate3(rot)
+        if nd == 3:
+            affine = affine @ _create_rotate3(rot)
+        else:
+            s, c = torch.sin(t32(rot[0])), torch.cos(t32(rot[0]))
+            m = torch.eye(3)
+            m[0, 0], m[0, 1], m[1, 0], m[1, 1] = c, -s, s, c
+            affine = affine @ m
     if shear:
-        m = torch.eye(4)
-        c = (list(shear) + [0.0] * 6)[:6]
-        m[0, 1], m[0, 2], m[1, 0], m[1, 2], m[2, 0], m[2, 1] = [torch.tensor(v, dtype=torch.float32) for v in c]
+        m = torch.eye(n)
+        if nd == 3:
+            c = (list(shear) + [0.0] * 6)[:6]
+            m[0, 1], m[0, 2], m[1, 0], m[1, 2], m[2, 0], m[2, 1] = [t32(v) for v in c]
+        else:
+            c = (list(shear) + [0.0] * 2)[:2]
+            m[0, 1], m[1, 0] = t32(c[0]), t32(c[1])
         affine = affine @ m
     if trans:
-        m = torch.eye(4)
-        for i, a in enumerate(trans[:3]):
-            m[i, 3] = a
+        m = torch.eye(n)
+        for i, a in enumerate(trans[:nd]):
+            m[i, nd] = a
         affine = affine @ m
     if scale:
-        f = (list(scale) + [1.0] * 3)[:3]
+        f = (list(scale) + [1.0] * nd)[:nd]
         affine = affine @ torch.diag(torch.as_tensor(f + [1.0], dtype=torch.float32))
-    grid = (affine @ grid.reshape(4, -1)).reshape(4, *sp)
+    grid = (affine @ grid.reshape(n, -1)).reshape(n, *sp)
     x = img[None].double()
-    g = grid[[2, 1, 0]].movedim(0, -1)[None].double().clone()
-    for i, dim in enumerate(x.shape[4:1:-1]):
+    g = grid[list(range(nd - 1, -1, -1))].movedim(0, -1)[None].double().clone()   # xyz order for grid_sample
+    for i, dim in enumerate(x.shape[:1:-1]):
         g[0, ..., i] *= 2.0 / max(2, dim)
     out = F.grid_sample(x, g, mode=mode, padding_mode=padding_mode, align_corners=False)[0]
     return out.float(), affine

@@ -88,8 +88,7 @@ def test_oracle_against_the_reference_unit_test_goldens(golden_dir):
     """Every golden vector the reference's own unit tests hold for Spacing, GaussianSmooth, Activations, AsDiscrete,
     RandAffined and RandAffine, extracted mechanically from the TESTS lists of /root/reference/tests/transforms
     (tests/golden/make_golden.py unit_goldens -> ref_unit_goldens.npz).  Cases outside the oracle's scope are skipped by rule
-    and counted: `other=` callables / dim != 0 (user code, non-default axes), negative pixdims and 4-D spatial inputs, 2-D
-    RandAffined images (the oracle restates the 3-D path of config C4).  `spacing4` (align_corners=True over a unit-size
+    and counted: `other=` callables / dim != 0 (user code, non-default axes), negative pixdims and 4-D spatial inputs.  `spacing4` (align_corners=True over a unit-size
     axis) is the one golden that depends on the torch version: the real reference run in this container returns ones, as
     the oracle does, so it is held to the reference test's own tolerance (test_spacing.py: atol = rtol = 1e-1)."""
     import json
@@ -124,18 +123,18 @@ def test_oracle_against_the_reference_unit_test_goldens(golden_dir):
             out = otr.as_discrete(x, argmax=kw.get("argmax", False), to_onehot=kw.get("to_onehot"), threshold=kw.get("threshold"),
                                   rounding=kw.get("rounding"))
         elif kind in ("randaffd", "randaff"):
-            if x.dim() != 4:
-                skipped[kind] = skipped.get(kind, 0) + 1
-                continue
             args = {k: kw[k] for k in ("rotate_range", "shear_range", "translate_range", "scale_range", "spatial_size", "mode", "padding_mode")
                     if kw.get(k) is not None}
+            for k in ("mode", "padding_mode"):          # dictionary version: per-key sequences, the golden is the first key ("img")
+                if isinstance(args.get(k), (list, tuple)):
+                    args[k] = args[k][0]
             out, _ = otr.rand_affine(x, rec["seed"], **args)
         got = out.numpy() if isinstance(out, torch.Tensor) else np.asarray(out)
         tol = 1e-1 if tag == "spacing4" else 1e-4
         assert got.shape == want.shape, (tag, kw, got.shape, want.shape)
         np.testing.assert_allclose(got, want, rtol=tol, atol=tol, err_msg=f"{tag} {kw}")
         ran[kind] = ran.get(kind, 0) + 1
-    assert ran == {"spacing": 15, "gauss": 9, "act": 6, "disc": 15, "randaffd": 6, "randaff": 24} and sum(ran.values()) == 75, (ran, skipped)
+    assert ran == {"spacing": 15, "gauss": 9, "act": 6, "disc": 15, "randaffd": 20, "randaff": 54} and sum(ran.values()) == 119, (ran, skipped)
 
 
 # tests/networks/layers/test_gaussian.py:228-248 (inline goldens) and :281-307 (TEST_CASES_NORM_F: variance -> taps for the
