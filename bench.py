@@ -40,6 +40,12 @@ WORKLOADS = {
         vol=(512, 512, 512), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=25, net="swin48", windows=1000,   # 25 divides the window share of 1, 2, 4 and 8 ranks
         flop_per_window=636e9,
     ),
+    # BASELINE.json configs[4] (the multi-GPU config; also runnable on one GPU)
+    "swin_c5": dict(
+        desc="SwinUNETR(feature_size=48) sliding-window 512x512x1024 fp16, roi 96^3, overlap 0.5, gaussian",
+        vol=(512, 512, 1024), roi=(96, 96, 96), overlap=0.5, mode="gaussian", sw_batch=25, net="swin48", windows=2100,
+        flop_per_window=636e9,
+    ),
     # BASELINE.json configs[3]
     "transforms_c4": dict(
         desc="Spacingd(1.25mm->1mm, bilinear) + RandAffined(prob 1, rotate .2, scale .1, translate 5, border) + GaussianSmoothd(sigma 1) on 32 x (1,256^3) fp32 MetaTensors",

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------------------- */
 int b200_abi_version(void);
@@ -79,7 +79,8 @@ typedef struct b200_conv_desc {
 int b200_conv3d_direct(const b200_conv_desc* desc, const void* x, const float* weight, const float* bias, void* y,
                        void* stream);
 
-/* per-(n,c) sum and sum of squares over S = D*H*W elements of x[N,C,S] -> stats[N*C][2] (float32, overwritten).
+/* per-(n,c) sum and sum of squares over S = D*H*W elements of x[N,C,S] -> stats[N*C][2] (float32, overwritten;
+ * deterministic: one block per plane, fixed summation order).
  * x_stride_n = element stride between samples. */
 int b200_instnorm_stats(const void* x, int dtype, int N, int C, long long S, long long x_stride_n, float* stats,
                         void* stream);
@@ -139,11 +140,14 @@ typedef struct b200_conv_tc_desc {
 
 /* 3x3x3, stride 1, zero padding 1 implicit-GEMM convolution on tcgen05 tensor cores: halo tile staged once
  * into shared memory by TMA, 27 taps issued as shifted UMMA shared-memory descriptors, fp32 accumulators in
- * TMEM.  stats (optional) receives per-(n,cout) {sum, sumsq} of the fp32 results (atomically accumulated:
- * zero it first) so InstanceNorm needs no extra pass.  replaces the Conv3d inside UnetResBlock
- * (monai/networks/blocks/dynunet_block.py:25-111) for SwinUNETR / DynUNet-style blocks. */
+ * TMEM.  stats (optional, overwritten) receives per-(n,cout) {sum, sumsq} of the fp32 results so InstanceNorm needs no
+ * extra pass.  The sums are DETERMINISTIC (bit-identical run to run): the epilogue warps write partial rows into
+ * `workspace` (device scratch of b200_conv3x3x3_tc_workspace_bytes(desc) bytes, required when stats != NULL; no
+ * initialisation needed) and a finishing pass adds them in a fixed order -- no floating-point atomics anywhere.
+ * replaces the Conv3d inside UnetResBlock (monai/networks/blocks/dynunet_block.py:25-111) for SwinUNETR / DynUNet blocks. */
+long long b200_conv3x3x3_tc_workspace_bytes(const b200_conv_tc_desc* desc);
 int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
-                      void* y, float* stats, void* stream);
+                      void* y, float* stats, void* workspace, void* stream);
 
 typedef struct b200_conv_gather_desc {
   int N, Cin, Cout;         /* Cin % 16 == 0; Cout arbitrary for NCDHW output, % 8 == 0 for NC8 output */
@@ -161,8 +165,9 @@ typedef struct b200_conv_gather_desc {
  * packed per (N tile, parity class, live tap, 16-channel slice); stats as in b200_conv3x3x3_tc. */
 long long b200_conv_gather_tc_weight_bytes(const b200_conv_gather_desc* desc);
 int b200_conv_gather_tc_pack_weight(const b200_conv_gather_desc* desc, const float* w, void* packed, void* stream);
+long long b200_conv_gather_tc_workspace_bytes(const b200_conv_gather_desc* desc);   /* statistics scratch, as for b200_conv3x3x3_tc */
 int b200_conv_gather_tc(const b200_conv_gather_desc* desc, const void* x, const void* packed_w, const float* bias, void* y,
-                        float* stats, void* stream);
+                        float* stats, void* workspace, void* stream);
 
 /* Thin head: ConvTranspose3d(k3, s2, p1, output_padding 1) from NC8 features to <= 4 NCDHW logit channels
  * (top layer of UNet, monai/networks/nets/unet.py); weight float32 [Cin][Cout][3][3][3]. */
@@ -188,10 +193,12 @@ int b200_gemm_tc_pack_weight(const float* w, int N, int K, long long stride_n, l
                              void* stream);
 /* y = [res +] act(x * W^T + bias) on tcgen05: nn.Linear (swin_unetr.py:509-532, blocks/mlp.py:75-80, PatchMerging
  * 749-773), 1x1x1 Conv3d (dynunet_block.py:75-87) and ConvTranspose3d k2 s2 (unetr_block.py:56-64, mode 2 with
- * GEMM columns ordered [tap = kd*4+kh*2+kw][cout]).  stats (optional, zero-initialised by the caller) accumulates
- * per-(batch, column) {sum, sumsq} of the stored values for InstanceNorm. */
+ * GEMM columns ordered [tap = kd*4+kh*2+kw][cout]).  stats (optional, overwritten) receives per-(batch, column)
+ * {sum, sumsq} of the stored values for InstanceNorm, deterministically, through `workspace`
+ * (b200_gemm_tc_workspace_bytes(desc) bytes; see b200_conv3x3x3_tc). */
+long long b200_gemm_tc_workspace_bytes(const b200_gemm_tc_desc* desc);
 int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const void* packed_w, const float* bias, const void* res,
-                 const int32_t* row_map, void* y, float* stats, void* stream);
+                 const int32_t* row_map, void* y, float* stats, void* workspace, void* stream);
 
 /* LayerNorm over channels of NC8 tokens with an optional row gather (window partition + cyclic shift + zero pad of
  * swin_unetr.py:596-625): y[n, :, r] = LN(x[n, :, src[r]]) (src[r] < 0 -> zeros; src == NULL -> identity).
@@ -214,11 +221,36 @@ int b200_patch_merge_ln_nc8(const void* x, int N, int C, int D, int H, int W, co
 int b200_window_attention_nc8(const void* qkv, int N, int C, int heads, int nW, int n, float scale, const float* table,
                               int ws0, int ws1, int ws2, const int32_t* region, void* out, void* stream);
 
+/* The same attention on tcgen05 tensor cores (n <= 352 tokens per window, head_dim 16): S = q k^T and the
+ * relative-position bias + shift mask are BOTH accumulated by tcgen05.mma (the bias as an fp16 B operand resident in
+ * shared memory, multiplied by an identity held in TMEM), softmax reads the scores from TMEM, P V runs on tcgen05 with V
+ * read in place (MN-major operand) and a ones column for the row sums.  Differences to b200_window_attention_nc8:
+ *   - q must be PRE-SCALED by scale * log2(e) (fold it into the q rows of the qkv projection): scores are in log2 units;
+ *   - the bias table and the shift mask are pre-packed per (mask type, head, 128-row tile) with
+ *     b200_window_attention_tc_pack_bias: region_types int32 [ntypes][n] holds ONE representative row of `region` per
+ *     distinct mask pattern (NULL with ntypes = 1: no mask); ntypes <= 8;
+ *   - sched int32 device array: count[8] (windows of each type), start[8] (offset of the type's window list),
+ *     win[nW] (window ids grouped by type). */
+long long b200_window_attention_tc_bias_bytes(int heads, int n, int ntypes);
+int b200_window_attention_tc_pack_bias(const float* table, int heads, int n, int ws0, int ws1, int ws2,
+                                       const int32_t* region_types, int ntypes, void* packed, void* stream);
+int b200_window_attention_tc(const void* qkv, int N, int C, int heads, int nW, int n, const void* packed_bias,
+                             const int32_t* sched, int ntypes, void* out, void* stream);
+
 /* Convolution with ONE input channel straight from an NCDHW volume to NC8 (patch embedding k2 s2, the 3x3x3 stem of
  * UnetrBasicBlock and its 1x1x1 residual conv): weight float32 [Cout][1][k][k][k]; stats optional {sum,sumsq}. */
+long long b200_conv_cin1_nc8_workspace_bytes(int N, int D, int H, int W, int Cout, int k, int stride, int pad);
 int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H, int W, const float* weight, const float* bias,
                        int Cout, int k, int stride, int pad, void* y, int out_ctot, int out_coff, float* stats,
-                       void* stream);
+                       void* workspace, void* stream);
+
+/* The same on tcgen05 tensor cores for (k, stride, pad) = (3, 1, 1) and (2, 2, 0), Cout in {16, 32, 48, 64, 96, 128}: an
+ * implicit GEMM with K = taps padded to 32 / 16 whose im2col operand is built in shared memory from a staged halo patch
+ * of the raw volume; bound by the fp16 store of its output instead of by CUDA-core FMAs.  Same arguments. */
+long long b200_conv_cin1_tc_workspace_bytes(int N, int D, int H, int W, int Cout, int k, int stride, int pad);
+int b200_conv_cin1_tc(const void* x, int dtype, int N, int D, int H, int W, const float* weight, const float* bias,
+                      int Cout, int k, int stride, int pad, void* y, int out_ctot, int out_coff, float* stats,
+                      void* workspace, void* stream);
 
 /* Channel-wise post-processing of channel-first logits x[C][S] (the transforms that follow the inferer in a segmentation bundle):
  * op 0 softmax over C, 1 sigmoid  (Activations, monai/transforms/post/array.py:63-128);

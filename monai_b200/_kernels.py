@@ -6,6 +6,8 @@ sm_100a kernel reached through ctypes.  All functions require CUDA tensors.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import weakref
 from typing import Sequence
 
 import torch
@@ -38,8 +40,17 @@ def profile_stop() -> dict:
 
 
 def _call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
-    """Launch one C-ABI entry point (b200_<name>) and raise on a non-zero status."""
+    """Launch one C-ABI entry point (b200_<name>) and raise on a non-zero status.  The launch runs with the device of the
+    stream handle among `args` current (see _lib.stream_ptr), so tensors on a non-current GPU work."""
     fn = getattr(L.load(), "b200_" + name)
+    dev = L.take_stream_device()   # the device whose stream handle is among `args`
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):   # kernels, tensor maps and events belong to the tensors' device, not to the current one
+            return _call_on(fn, name, args, flops, nbytes)
+    return _call_on(fn, name, args, flops, nbytes)
+
+
+def _call_on(fn, name, args, flops, nbytes) -> None:
     if _Prof.on:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -55,21 +66,35 @@ _F32_CACHE: dict = {}
 
 
 def _f32c(t: torch.Tensor | None) -> torch.Tensor | None:
-    """float32 contiguous view of a (parameter) tensor, cached per (storage, version) so fp16 models do not re-convert
-    their weights on every forward."""
+    """float32 contiguous view of a (parameter) tensor, cached so fp16 models do not re-convert their weights on every
+    forward.  An entry is tied to the IDENTITY of its source tensor (weak reference + version counter): when a model is
+    freed and another one lands on the same addresses, the stale entry is neither hit (the weak reference is dead or
+    points elsewhere) nor kept (its finaliser evicts it)."""
     if t is None:
         return None
+    src = t
     t = t.detach()
     if t.dtype == torch.float32 and t.is_contiguous():
         return t
-    key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype, t.device)
+    key = (id(src), tuple(t.shape), t.dtype, t.device)
     hit = _F32_CACHE.get(key)
-    if hit is None:
-        if len(_F32_CACHE) > 4096:
-            _F32_CACHE.clear()
-        hit = t.to(torch.float32).contiguous()
-        _F32_CACHE[key] = hit
-    return hit
+    if hit is not None and hit[0]() is src and hit[1] == src._version and hit[2] == src.data_ptr():
+        return hit[3]
+    val = t.to(torch.float32).contiguous()
+    try:
+        ref = weakref.ref(src, lambda _r, k=key: _F32_CACHE.pop(k, None))
+    except TypeError:   # pragma: no cover - objects without weak references are not cached
+        return val
+    _F32_CACHE[key] = (ref, src._version, src.data_ptr(), val)
+    return val
+
+
+def _ws(nbytes: int, device) -> torch.Tensor | None:
+    """Scratch for the deterministic statistics of the tensor-core epilogues (include/monai_b200.h): a fresh allocation per
+    call, so CUDA-graph capture keeps it alive inside the graph's pool."""
+    if nbytes < 0:
+        raise ValueError("monai_b200: workspace query failed for this shape")
+    return torch.empty(max(int(nbytes), 16), device=device, dtype=torch.uint8)
 
 
 def _nb(*tensors) -> float:
@@ -361,10 +386,12 @@ def conv3x3x3_tc(
 ) -> tuple[NC8, torch.Tensor | None]:
     if out is None:
         out = NC8(x.N, Cout, x.sp, x.buf.device)
-    stats = torch.zeros((x.N * Cout, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
+    dev = x.buf.device
+    stats = torch.empty((x.N * Cout, 2), device=dev, dtype=torch.float32) if want_stats else None
     b32 = _f32c(bias)
     d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff)
-    _call("conv3x3x3_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.stream_ptr(x.buf.device),
+    ws = _ws(L.load().b200_conv3x3x3_tc_workspace_bytes(C.byref(d)), dev) if want_stats else None
+    _call("conv3x3x3_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.ptr(ws), L.stream_ptr(dev),
           flops=2.0 * x.N * x.S * Cin * Cout * 27, nbytes=float(x.N * x.S * (Cin + Cout) * 2) + _nb(packed_w))
     return out, stats
 
@@ -438,14 +465,16 @@ def gemm_tc(
     if out is None:
         sp = tuple(out_sp) if out_sp is not None else (tuple(2 * s for s in x.sp) if mode == 2 else x.sp)
         out = NC8(x.N, cout, sp, x.buf.device)
-    stats = torch.zeros((x.N * N, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
+    dev = x.buf.device
+    stats = torch.empty((x.N * N, 2), device=dev, dtype=torch.float32) if want_stats else None
     b32 = _f32c(bias)
     d = L.GemmTcDesc(
         x.N, x.S, Kd, N, x.C, in_coff, out.C, out_coff, res.C if res is not None else 0, res_coff, out.S, mode, act,
         x.sp[0], x.sp[1], x.sp[2],
     )
+    ws = _ws(L.load().b200_gemm_tc_workspace_bytes(C.byref(d)), dev) if want_stats else None
     _call("gemm_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(res.buf) if res is not None else None,
-          L.ptr(row_map), L.ptr(out.buf), L.ptr(stats), L.stream_ptr(x.buf.device),
+          L.ptr(row_map), L.ptr(out.buf), L.ptr(stats), L.ptr(ws), L.stream_ptr(dev),
           flops=2.0 * x.N * x.S * Kd * N, nbytes=float(x.N * x.S * (Kd + N) * 2) + _nb(packed_w))
     return out, stats
 
@@ -480,6 +509,68 @@ def window_attention_nc8(qkv: NC8, Cc: int, heads: int, nW: int, n: int, scale: 
     return out
 
 
+_FORCE_CUDA_CORE_STEM = bool(os.environ.get("B200_STEM_CUDA_CORE"))
+
+
+def window_attention_tc_plan(region, nW: int, n: int):
+    """Host-side schedule of b200_window_attention_tc: windows grouped by shift-mask pattern.
+
+    region: int array [nW, n] of compute_mask labels (or None without a shift).  Returns (sched int32 numpy [16 + nW] =
+    count[8] | start[8] | window ids grouped by type, region_types int32 numpy [ntypes, n] or None, ntypes); ntypes > 8
+    means "not representable" (the caller keeps the mma.sync kernel)."""
+    import numpy as np
+
+    if region is None:
+        types = np.zeros(nW, dtype=np.int64)
+        reps = None
+        ntypes = 1
+    else:
+        region = np.asarray(region).reshape(nW, n)
+        canon = np.empty_like(region)
+        for w in range(nW):   # relabel by first appearance: equal masks <=> equal canonical rows
+            _, first, inv = np.unique(region[w], return_index=True, return_inverse=True)
+            order = np.argsort(np.argsort(first))
+            canon[w] = order[inv]
+        uniq, types = np.unique(canon, axis=0, return_inverse=True)
+        types = types.reshape(-1)
+        ntypes = int(uniq.shape[0])
+        reps = uniq.astype(np.int32)
+    sched = np.zeros(16 + nW, dtype=np.int32)
+    if ntypes <= 8:
+        pos = 0
+        for t in range(ntypes):
+            ids = np.nonzero(types == t)[0]
+            sched[t], sched[8 + t] = len(ids), pos
+            sched[16 + pos: 16 + pos + len(ids)] = ids
+            pos += len(ids)
+    return sched, reps, ntypes
+
+
+def window_attention_tc_pack_bias(table: torch.Tensor, heads: int, n: int, window: Sequence[int], region_types: torch.Tensor | None, ntypes: int) -> torch.Tensor:
+    """fp16 B-operand images of log2(e) * (relative-position bias + shift mask) per (mask type, head, 128-row tile)."""
+    tab = _f32c(table)
+    nbytes = L.load().b200_window_attention_tc_bias_bytes(heads, n, ntypes)
+    if nbytes < 0:
+        raise ValueError(f"window_attention_tc: unsupported shape (n={n}, mask types={ntypes})")
+    packed = torch.empty(nbytes // 2, device=tab.device, dtype=torch.float16)
+    _call("window_attention_tc_pack_bias", L.ptr(tab), heads, n, int(window[0]), int(window[1]), int(window[2]), L.ptr(region_types), ntypes,
+          L.ptr(packed), L.stream_ptr(tab.device))
+    return packed
+
+
+def window_attention_tc(qkv: NC8, Cc: int, heads: int, nW: int, n: int, packed_bias: torch.Tensor, sched: torch.Tensor, ntypes: int) -> NC8:
+    """Window attention on tcgen05 (b200_window_attention_tc); q must be pre-scaled by scale * log2(e)."""
+    out = NC8(qkv.N, Cc, qkv.sp, qkv.buf.device)
+    n_pad = (n + 31) // 32 * 32
+    _call("window_attention_tc", L.ptr(qkv.buf), qkv.N, Cc, heads, nW, n, L.ptr(packed_bias), L.ptr(sched), ntypes, L.ptr(out.buf),
+          L.stream_ptr(qkv.buf.device), flops=4.0 * qkv.N * nW * heads * n * n * 16, nbytes=float(qkv.N * 4 * Cc * nW * n * 2))
+    return out
+
+
+ATTN_TC = not bool(os.environ.get("B200_ATTN_HMMA"))   # tcgen05 attention unless the mma.sync kernel is forced (debugging)
+LOG2E = 1.4426950408889634
+
+
 def conv_cin1_nc8(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, k: int, stride: int, pad: int,
                   out: NC8 | None = None, out_coff: int = 0, want_stats: bool = False) -> tuple[NC8, torch.Tensor | None]:
     """x [N,1,D,H,W] (f16/f32) -> NC8 with Cout channels."""
@@ -492,9 +583,15 @@ def conv_cin1_nc8(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | No
         out = NC8(N, Cout, sp, x.device)
     w32 = _f32c(weight)
     b32 = _f32c(bias)
-    stats = torch.zeros((N * Cout, 2), device=x.device, dtype=torch.float32) if want_stats else None
-    _call("conv_cin1_nc8", L.ptr(x), L.dt(x), N, D, H, W, L.ptr(w32), L.ptr(b32), Cout, k, stride, pad, L.ptr(out.buf), out.C, out_coff, L.ptr(stats), L.stream_ptr(x.device),
-          flops=2.0 * N * sp[0] * sp[1] * sp[2] * Cout * k**3)
+    stats = torch.empty((N * Cout, 2), device=x.device, dtype=torch.float32) if want_stats else None
+    # tensor-core stem for the shapes it covers (the 3x3x3 stem and the patch embedding); CUDA-core kernel otherwise
+    tc = (k, stride, pad) in ((3, 1, 1), (2, 2, 0)) and Cout in (16, 32, 48, 64, 96, 128) and not _FORCE_CUDA_CORE_STEM
+    name = "conv_cin1_tc" if tc else "conv_cin1_nc8"
+    ws = None
+    if want_stats:
+        ws = _ws(getattr(L.load(), f"b200_{name}_workspace_bytes")(N, D, H, W, Cout, k, stride, pad), x.device)
+    _call(name, L.ptr(x), L.dt(x), N, D, H, W, L.ptr(w32), L.ptr(b32), Cout, k, stride, pad, L.ptr(out.buf), out.C, out_coff, L.ptr(stats), L.ptr(ws),
+          L.stream_ptr(x.device), flops=2.0 * N * sp[0] * sp[1] * sp[2] * Cout * k**3, nbytes=_nb(x) + float(N * sp[0] * sp[1] * sp[2] * Cout * 2))
     return out, stats
 
 
@@ -552,10 +649,11 @@ def conv_gather_tc(
     if out is None:
         out = NC8(x.N, Cout, sp_out, x.buf.device) if layout == 0 else torch.empty((x.N, Cout, *sp_out), device=x.buf.device, dtype=ncdhw_dtype)
         d.out_ctot = out.C if layout == 0 else d.out_ctot
-    stats = torch.zeros((x.N * Cout, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
+    stats = torch.empty((x.N * Cout, 2), device=x.buf.device, dtype=torch.float32) if want_stats else None
     b32 = _f32c(bias)
     taps = k**3 if not transposed else (k**3) / (stride**3)
-    _call("conv_gather_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf if layout == 0 else out), L.ptr(stats),
+    ws = _ws(L.load().b200_conv_gather_tc_workspace_bytes(C.byref(d)), x.buf.device) if want_stats else None
+    _call("conv_gather_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf if layout == 0 else out), L.ptr(stats), L.ptr(ws),
           L.stream_ptr(x.buf.device), flops=2.0 * x.N * sp_out[0] * sp_out[1] * sp_out[2] * Cin * Cout * taps,
           nbytes=float(x.N * (x.S * Cin + sp_out[0] * sp_out[1] * sp_out[2] * Cout) * 2) + _nb(packed_w))
     return out, stats

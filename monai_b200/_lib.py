@@ -14,6 +14,7 @@ import torch
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libmonai_b200.so"
 
+ABI_VERSION = 2
 DT_F32, DT_F16 = 0, 1
 _DT = {torch.float32: DT_F32, torch.float16: DT_F16}
 
@@ -82,18 +83,27 @@ SIGNATURES = {
     "b200_unpack_nc8": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, vp]),
     "b200_conv3x3x3_tc_weight_bytes": (i64, [i32, i32]),
     "b200_conv3x3x3_tc_pack_weight": (i32, [vp, i32, i32, vp, vp]),
-    "b200_conv3x3x3_tc": (i32, [C.POINTER(ConvTcDesc), vp, vp, vp, vp, vp, vp]),
+    "b200_conv3x3x3_tc_workspace_bytes": (i64, [C.POINTER(ConvTcDesc)]),
+    "b200_conv3x3x3_tc": (i32, [C.POINTER(ConvTcDesc), vp, vp, vp, vp, vp, vp, vp]),
     "b200_conv_gather_tc_weight_bytes": (i64, [C.POINTER(ConvGatherDesc)]),
     "b200_conv_gather_tc_pack_weight": (i32, [C.POINTER(ConvGatherDesc), vp, vp, vp]),
-    "b200_conv_gather_tc": (i32, [C.POINTER(ConvGatherDesc), vp, vp, vp, vp, vp, vp]),
+    "b200_conv_gather_tc_workspace_bytes": (i64, [C.POINTER(ConvGatherDesc)]),
+    "b200_conv_gather_tc": (i32, [C.POINTER(ConvGatherDesc), vp, vp, vp, vp, vp, vp, vp]),
     "b200_convt3s2_head_nc8": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp]),
     "b200_gemm_tc_weight_bytes": (i64, [i32, i32]),
     "b200_gemm_tc_pack_weight": (i32, [vp, i32, i32, i64, i64, vp, vp]),
-    "b200_gemm_tc": (i32, [C.POINTER(GemmTcDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b200_gemm_tc_workspace_bytes": (i64, [C.POINTER(GemmTcDesc)]),
+    "b200_gemm_tc": (i32, [C.POINTER(GemmTcDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200_layernorm_nc8": (i32, [vp, i32, i32, i64, vp, i64, vp, vp, f32, vp, vp]),
     "b200_patch_merge_ln_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp]),
     "b200_window_attention_nc8": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, i32, i32, i32, vp, vp, vp]),
-    "b200_conv_cin1_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "b200_conv_cin1_nc8_workspace_bytes": (i64, [i32] * 8),
+    "b200_conv_cin1_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]),
+    "b200_conv_cin1_tc_workspace_bytes": (i64, [i32] * 8),
+    "b200_conv_cin1_tc": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]),
+    "b200_window_attention_tc_bias_bytes": (i64, [i32, i32, i32]),
+    "b200_window_attention_tc_pack_bias": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp]),
+    "b200_window_attention_tc": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "b200_patch_accumulate": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "b200_patch_finalize": (i32, [vp, vp, i32, i64, vp]),
     "b200_channel_post": (i32, [vp, i32, i32, i64, i32, f32, i32, vp, i32, vp]),
@@ -116,7 +126,7 @@ def load(required: bool = True):
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)
                 fn.restype, fn.argtypes = res, args
-            if lib.b200_abi_version() != 1:
+            if lib.b200_abi_version() != ABI_VERSION:
                 raise OSError(f"ABI version mismatch: {lib.b200_abi_version()}")
             _lib = lib
         except (OSError, AttributeError) as e:  # pragma: no cover - exercised only on broken installs
@@ -153,8 +163,21 @@ def ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
 
+_last_stream_device: torch.device | None = None
+
+
 def stream_ptr(device: torch.device | None = None) -> int:
+    """Handle of torch's current stream on `device`; the device is remembered so that the launch that consumes the handle
+    (monai_b200._kernels._call evaluates it as its last argument) runs with that device current."""
+    global _last_stream_device
+    _last_stream_device = device if device is None or isinstance(device, torch.device) else torch.device(device)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def take_stream_device() -> torch.device | None:
+    global _last_stream_device
+    d, _last_stream_device = _last_stream_device, None
+    return d
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:

@@ -1,0 +1,391 @@
+// Windowed multi-head self-attention on tcgen05 tensor cores.
+//
+// Reference: WindowAttention.forward (monai/networks/nets/swin_unetr.py:509-532): per window of n <= 343 tokens and head
+// (head_dim 16):  softmax(q k^T * scale + relative_position_bias[:n,:n] + shift_mask) v.
+//
+// One persistent CTA per SM works on tiles = (window, head, 128-query row tile).  Per tile
+//   S[128 x n_pad] = Q K^T                      1 tcgen05.mma per key half   (SS form, K = 16 = the whole head)
+//                  + I[128 x 128] * B'          8 tcgen05.mma per key half   (TS form: A = identity held in TMEM)
+// where B'[i][j] = log2(e) * (bias[i][j] + mask[i][j]) is an fp16 B operand that stays RESIDENT in shared memory: it depends
+// on (head, row tile, mask type) only, so tiles are scheduled (mask type, head, row tile)-major and a CTA reloads it a
+// handful of times per launch.  Adding the bias with the tensor core (1.0 * fp16 value into the fp32 accumulator: exact)
+// removes the per-element table lookup and mask test that bounded the mma.sync kernel (swin.cu) -- with head_dim 16 the
+// tensor pipe is otherwise idle.  Padded keys carry B' = -30000 (P = 0).  Scores are in log2 units: the caller folds
+// scale * log2(e) into the q rows of the qkv projection.
+//   softmax: 8 warps, two threads per query row (one per key half): exact row maximum from TMEM (pass 1), then
+//            P = ex2(S - max) in fp32, packed to fp16 and written straight into the K-major core-matrix image
+//            of an A operand in shared memory (pass 2);
+//   O[128 x 32] = P [V | 1 | 0]                 n_pad/16 tcgen05.mma, V read in place as an MN-major B operand (NC8 rows
+//            are 16-byte vectors of 8 dims), the ones column accumulates the row sums in fp32;
+//   epilogue: O / rowsum -> fp16 NC8.
+// Q, K, V tiles are 1-D bulk copies of NC8 rows (contiguous per 8-channel chunk).
+//
+// Warp roles (320 threads): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = softmax / epilogue.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "../../include/monai_b200.h"
+
+namespace b200 {
+
+constexpr int kAtNPadMax = 352;                       // keys per window, padded (n <= 343 -> 352)
+constexpr int kAtKChunk = kAtNPadMax * 16;            // bytes of one 8-dim chunk of K / V in shared memory
+constexpr int kAtBiasBytes = 16 * kAtNPadMax * 16;    // 16 chunks of 8 query rows
+constexpr int kAtPBytes = (kAtNPadMax / 8) * 2048;    // P: [key block of 8][128 rows][16 B]
+constexpr int kAtColS1 = 176, kAtColO = 352, kAtColI = 384;   // TMEM columns: S half 0 at 0, half 1, O, identity (64)
+constexpr int kAtSmem = kAtBiasBytes + kAtPBytes + 2 * 2048 + 2 * kAtKChunk + 4 * kAtKChunk + 2 * 128 * 4 + 256 + 128;
+constexpr float kAtPadBias = -30000.f;
+
+struct AttnTcParams {
+  const __half* qkv; __half* out; const __half* bias; const int32_t* sched;
+  int N, C8, heads, nW, n, n_pad, nrt, ntypes;
+};
+
+struct AttnTile { int ty, h, rt, b, w; };
+
+// flattened tile index -> (mask type, head, row tile, batch item, window); order: type, (head, row tile), batch, window
+__device__ __forceinline__ AttnTile attn_decode(const AttnTcParams& p, long long f) {
+  const int32_t* cnt = p.sched;
+  const int32_t* start = p.sched + 8;
+  const int32_t* win = p.sched + 16;
+  AttnTile t;
+  t.ty = 0;
+  const long long hr_n = (long long)p.heads * p.nrt;
+  for (;;) {
+    const long long blk = (long long)cnt[t.ty] * p.N * hr_n;
+    if (f < blk || t.ty + 1 >= p.ntypes) break;
+    f -= blk; ++t.ty;
+  }
+  const int c = cnt[t.ty];
+  const long long per = (long long)c * p.N;
+  const int hr = (int)(f / per);
+  const int l2 = (int)(f % per);
+  t.h = hr / p.nrt; t.rt = hr % p.nrt;
+  t.b = l2 / c;
+  t.w = win[start[t.ty] + l2 % c];
+  return t;
+}
+
+// 2^(a - m), 2^(b - m) as packed fp16.  (ex2.approx.f16x2 is split by ptxas into one MUFU per half plus a PRMT, so the fp32
+// MUFU form costs the same MUFU slots, one instruction less, and keeps the exponent argument in fp32.)
+__device__ __forceinline__ uint32_t exp2_pack(float a, float b, float m) {
+  float ea, eb;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(a - m));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(b - m));
+  const __half2 h = __floats2half2_rn(ea, eb);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* s_bias = smem;
+  uint8_t* s_p = s_bias + kAtBiasBytes;
+  uint8_t* s_q = s_p + kAtPBytes;
+  uint8_t* s_k = s_q + 2 * 2048;
+  uint8_t* s_v = s_k + 2 * kAtKChunk;                 // 4 chunk slots: V dims 0-7, 8-15, ones column, zeros
+  float* s_max = reinterpret_cast<float*>(s_v + 4 * kAtKChunk);   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_max + 256);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* qk_empty = bars + 1;
+  uint64_t* s_full = bars + 2;      // [2]
+  uint64_t* s_empty = bars + 4;     // [2]
+  uint64_t* p_full = bars + 6;      // [2]
+  uint64_t* v_full = bars + 8;
+  uint64_t* pv_done = bars + 9;
+  uint64_t* o_empty = bars + 10;
+  uint64_t* init_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.n, n_pad = p.n_pad, NH = n_pad / 2;
+  const long long T = (long long)p.nW * n;
+  const long long total = (long long)p.N * p.nW * p.heads * p.nrt;
+  const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(qk_full, 1); tc::mbar_init(qk_empty, 1); tc::mbar_init(v_full, 1); tc::mbar_init(pv_done, 1);
+    tc::mbar_init(o_empty, 128); tc::mbar_init(init_done, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128); tc::mbar_init(&p_full[i], 128); }
+    tc::fence_barrier_init();
+  }
+  // zero Q / K / V (rows the bulk copies never write must be finite), the ones column, and the identity (staged in the P region)
+  {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* zq = reinterpret_cast<uint4*>(s_q);
+    const int nz = (2 * 2048 + 2 * kAtKChunk + 4 * kAtKChunk) / 16;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) zq[i] = z;
+    uint4* zi = reinterpret_cast<uint4*>(s_p);
+    for (int i = threadIdx.x; i < 16 * 2048 / 16; i += blockDim.x) zi[i] = z;
+  }
+  __syncthreads();
+  {
+    __half* ones = reinterpret_cast<__half*>(s_v + 2 * kAtKChunk);
+    for (int j = threadIdx.x; j < kAtNPadMax; j += blockDim.x) ones[j * 8] = __float2half_rn(1.f);
+    __half* id = reinterpret_cast<__half*>(s_p);   // [k chunk of 8][row][8]: element (row r, k = r) = 1
+    for (int r = threadIdx.x; r < 128; r += blockDim.x) id[((r >> 3) * 128 + r) * 8 + (r & 7)] = __float2half_rn(1.f);
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== copy producer =====================
+    if (lane == 0) {
+      int last_combo = -1;
+      int it = 0;
+      for (long long f = lo; f < hi; ++f, ++it) {
+        const AttnTile t = attn_decode(p, f);
+        const int combo = (t.ty * p.heads + t.h) * p.nrt + t.rt;
+        const int rows = min(128, n - t.rt * 128);
+        tc::mbar_wait(qk_empty, (uint32_t)((it & 1) ^ 1));      // the S MMAs of the previous tile (readers of Q, K, bias) are done
+        const uint32_t bias_bytes = combo != last_combo ? (uint32_t)(16 * n_pad * 16) : 0u;
+        tc::mbar_arrive_expect_tx(qk_full, bias_bytes + 2u * rows * 16u + 2u * n * 16u);
+        if (bias_bytes) tc::bulk_load(s_bias, p.bias + (long long)combo * (16 * n_pad * 8), bias_bytes, qk_full);
+        last_combo = combo;
+        const __half* base = p.qkv + (long long)t.b * (3 * p.C8) * T * 8;
+        const long long row0 = (long long)t.w * n;
+        for (int c = 0; c < 2; ++c) {
+          tc::bulk_load(s_q + c * 2048, base + ((long long)(2 * t.h + c) * T + row0 + t.rt * 128) * 8, rows * 16, qk_full);
+          tc::bulk_load(s_k + c * kAtKChunk, base + ((long long)(p.C8 + 2 * t.h + c) * T + row0) * 8, n * 16, qk_full);
+        }
+        if (it > 0) tc::mbar_wait(pv_done, (uint32_t)((it - 1) & 1));   // the PV MMAs of the previous tile (readers of V) are done
+        tc::mbar_arrive_expect_tx(v_full, 2u * n * 16u);
+        for (int c = 0; c < 2; ++c)
+          tc::bulk_load(s_v + c * kAtKChunk, base + ((long long)(2 * p.C8 + 2 * t.h + c) * T + row0) * 8, n * 16, v_full);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = tc::elect_one();
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc_s = tc::make_idesc_f16(128, NH);
+    const uint32_t idesc_pv = tc::make_idesc_f16(128, 32) | (1u << 16);   // B (= V) is MN-major
+    const uint32_t q_a = tc::smem_u32(s_q), k_a = tc::smem_u32(s_k), v_a = tc::smem_u32(s_v), b_a = tc::smem_u32(s_bias), p_a = tc::smem_u32(s_p);
+    // identity -> TMEM (8 K-steps of 16: 8 columns each), staged in the P region by all threads above
+    if (leader) {
+      for (int s = 0; s < 8; ++s) tc::tmem_cp_128x256b(tm + kAtColI + 8 * s, tc::make_desc_kmajor_noswz(p_a + s * 4096, 2048, 128));
+      tc::mma_commit(init_done);
+    }
+    __syncwarp();
+    int it = 0;
+    for (long long f = lo; f < hi; ++f, ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      tc::mbar_wait(qk_full, ph);
+      tc::fence_after_sync();
+      for (int hf = 0; hf < 2; ++hf) {
+        tc::mbar_wait(&s_empty[hf], ph ^ 1);        // the softmax threads have read this half of the previous tile
+        tc::fence_after_sync();
+        const uint32_t ts = tm + hf * kAtColS1;
+        const uint64_t qd = tc::make_desc_kmajor_noswz(q_a, 2048, 128);
+        const uint64_t kd = tc::make_desc_kmajor_noswz(k_a + hf * NH * 16, kAtKChunk, 128);
+        if (leader) tc::mma_f16_ss(ts, qd, kd, idesc_s, 0u);
+        for (int s = 0; s < 8; ++s) {
+          const uint64_t bd = tc::make_desc_kmajor_noswz(b_a + (2 * s) * n_pad * 16 + hf * NH * 16, n_pad * 16, 128);
+          if (leader) tc::mma_f16_ts(ts, tm + kAtColI + 8 * s, bd, idesc_s, 1u);
+        }
+        if (leader) tc::mma_commit(&s_full[hf]);
+        __syncwarp();
+      }
+      if (leader) tc::mma_commit(qk_empty);
+      __syncwarp();
+      tc::mbar_wait(v_full, ph);
+      for (int hf = 0; hf < 2; ++hf) {
+        tc::mbar_wait(&p_full[hf], ph);
+        if (hf == 0) tc::mbar_wait(o_empty, ph ^ 1);  // the epilogue has read O of the previous tile
+        tc::fence_after_sync();
+        for (int s = 0; s < NH / 16; ++s) {
+          const int ks = hf * (NH / 16) + s;
+          const uint64_t pd = tc::make_desc_kmajor_noswz(p_a + ks * 4096, 2048, 128);
+          // MN-major B: 8 keys x 16 B (8 dims) per core matrix, next 8 keys +128 B (LBO), next 8 dims +chunk (SBO)
+          const uint64_t vd = tc::make_desc_kmajor_noswz(v_a + ks * 256, 128, kAtKChunk);
+          if (leader) tc::mma_f16_ss(tm + kAtColO, pd, vd, idesc_pv, (hf | s) != 0 ? 1u : 0u);
+        }
+      }
+      if (leader) tc::mma_commit(pv_done);
+      __syncwarp();
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue (warps 2..9) =====================
+    const int hf = (warp - 2) >> 2;           // key half of this thread
+    const int q = warp & 3;                   // TMEM lane quarter
+    const int row = q * 32 + lane;
+    const uint32_t ts = tmem_base + ((uint32_t)(q * 32) << 16) + hf * kAtColS1;
+    const uint32_t to = tmem_base + ((uint32_t)(q * 32) << 16) + kAtColO;
+    uint8_t* prow = s_p + (hf * NH / 8) * 2048 + row * 16;
+    int it = 0;
+    for (long long f = lo; f < hi; ++f, ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      tc::mbar_wait(&s_full[hf], ph);
+      tc::fence_after_sync();
+      // ---- pass 1: exact row maximum over this thread's key half
+      float m = -INFINITY;
+      {
+        uint32_t va[16], vb[16];
+        tc::tmem_ld16(ts, va);
+        for (int c = 0; c < NH; c += 32) {
+          tc::tmem_ld_wait16(va);
+          if (c + 16 < NH) tc::tmem_ld16(ts + c + 16, vb);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(va[j]));
+          if (c + 16 < NH) {
+            tc::tmem_ld_wait16(vb);
+            if (c + 32 < NH) tc::tmem_ld16(ts + c + 32, va);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(vb[j]));
+          }
+        }
+      }
+      s_max[hf * 128 + row] = m;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m = fmaxf(m, s_max[(hf ^ 1) * 128 + row]);
+      // P buffer free?  (first tile: the identity staged there has been copied to TMEM)
+      if (it == 0) tc::mbar_wait(init_done, 0u);
+      else tc::mbar_wait(pv_done, (uint32_t)((it - 1) & 1));
+      // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs
+      {
+        uint32_t va[16], vb[16];
+        auto emit = [&](const uint32_t (&v)[16], int c) {
+          uint4 u0, u1;
+          u0.x = exp2_pack(__uint_as_float(v[0]), __uint_as_float(v[1]), m);
+          u0.y = exp2_pack(__uint_as_float(v[2]), __uint_as_float(v[3]), m);
+          u0.z = exp2_pack(__uint_as_float(v[4]), __uint_as_float(v[5]), m);
+          u0.w = exp2_pack(__uint_as_float(v[6]), __uint_as_float(v[7]), m);
+          u1.x = exp2_pack(__uint_as_float(v[8]), __uint_as_float(v[9]), m);
+          u1.y = exp2_pack(__uint_as_float(v[10]), __uint_as_float(v[11]), m);
+          u1.z = exp2_pack(__uint_as_float(v[12]), __uint_as_float(v[13]), m);
+          u1.w = exp2_pack(__uint_as_float(v[14]), __uint_as_float(v[15]), m);
+          *reinterpret_cast<uint4*>(prow + (c / 8) * 2048) = u0;
+          *reinterpret_cast<uint4*>(prow + (c / 8 + 1) * 2048) = u1;
+        };
+        tc::tmem_ld16(ts, va);
+        for (int c = 0; c < NH; c += 32) {
+          tc::tmem_ld_wait16(va);
+          if (c + 16 < NH) tc::tmem_ld16(ts + c + 16, vb);
+          emit(va, c);
+          if (c + 16 < NH) {
+            tc::tmem_ld_wait16(vb);
+            if (c + 32 < NH) tc::tmem_ld16(ts + c + 32, va);
+            emit(vb, c + 16);
+          }
+        }
+      }
+      tc::fence_proxy_async();       // P (generic-proxy stores) -> visible to the tensor core
+      tc::fence_before_sync();       // this thread's TMEM reads of S are complete
+      tc::mbar_arrive(&p_full[hf]);
+      tc::mbar_arrive(&s_empty[hf]);
+      if (hf == 0) {
+        // ---- epilogue: O / rowsum -> fp16 NC8
+        const AttnTile t = attn_decode(p, f);
+        tc::mbar_wait(pv_done, ph);
+        tc::fence_after_sync();
+        uint32_t o[16], o2[16];
+        tc::tmem_ld16(to, o);
+        tc::tmem_ld16(to + 16, o2);
+        tc::tmem_ld_wait16(o);
+        tc::tmem_ld_wait16(o2);
+        tc::fence_before_sync();
+        tc::mbar_arrive(o_empty);
+        const int r = t.rt * 128 + row;
+        if (r < n) {
+          const float inv = 1.f / __uint_as_float(o2[0]);
+          __half* ob = p.out + (long long)t.b * p.C8 * T * 8 + ((long long)t.w * n + r) * 8;
+#pragma unroll
+          for (int dt = 0; dt < 2; ++dt) {
+            uint4 hv;
+            __half2* hp = reinterpret_cast<__half2*>(&hv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              hp[j] = __floats2half2_rn(__uint_as_float(o[dt * 8 + 2 * j]) * inv, __uint_as_float(o[dt * 8 + 2 * j + 1]) * inv);
+            *reinterpret_cast<uint4*>(ob + (long long)(2 * t.h + dt) * T * 8) = hv;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// B' operand images: [type][head][row tile][16 chunks of 8 query rows][n_pad keys][8] fp16 (see the header comment)
+__global__ void attn_bias_pack_kernel(const float* __restrict__ table, const int32_t* __restrict__ region, __half* __restrict__ out,
+                                      int heads, int n, int n_pad, int nrt, int ntypes, int ws0, int ws1, int ws2) {
+  const long long total = (long long)ntypes * heads * nrt * 16 * n_pad * 8;
+  const int s1 = 2 * ws2 - 1, s0 = (2 * ws1 - 1) * s1;
+  const int lin_c = (ws0 - 1) * s0 + (ws1 - 1) * s1 + (ws2 - 1);
+  constexpr float kLog2e = 1.4426950408889634f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int e = (int)(r % 8); r /= 8;
+    const int j = (int)(r % n_pad); r /= n_pad;
+    const int c = (int)(r % 16); r /= 16;
+    const int rt = (int)(r % nrt); r /= nrt;
+    const int h = (int)(r % heads); r /= heads;
+    const int ty = (int)r;
+    const int ig = rt * 128 + c * 8 + e;
+    float v;
+    if (j >= n) v = kAtPadBias;
+    else if (ig >= n) v = 0.f;
+    else {
+      // tokens keep their coordinates in the MODULE window (relative_position_index[:n, :n], swin_unetr.py:514-516)
+      const int li = (ig / (ws1 * ws2)) * s0 + ((ig / ws2) % ws1) * s1 + ig % ws2;
+      const int lj = (j / (ws1 * ws2)) * s0 + ((j / ws2) % ws1) * s1 + j % ws2;
+      v = table[(long long)(li - lj + lin_c) * heads + h] * kLog2e;
+      if (region && region[(long long)ty * n + ig] != region[(long long)ty * n + j]) v += -100.f * kLog2e;   // compute_mask, swin_unetr.py:779-816
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static bool attn_tc_shape_ok(int heads, int n, int ntypes) {
+  return heads > 0 && n > 0 && n <= kAtNPadMax && ntypes >= 1 && ntypes <= 8;
+}
+
+extern "C" long long b200_window_attention_tc_bias_bytes(int heads, int n, int ntypes) {
+  if (!attn_tc_shape_ok(heads, n, ntypes) || n > kAtNPadMax) return -1;
+  const int n_pad = (n + 31) / 32 * 32, nrt = (n + 127) / 128;
+  return (long long)ntypes * heads * nrt * 16 * n_pad * 16;
+}
+
+extern "C" int b200_window_attention_tc_pack_bias(const float* table, int heads, int n, int ws0, int ws1, int ws2,
+                                                  const int32_t* region_types, int ntypes, void* packed, void* stream) {
+  B200_REQUIRE(table && packed, "window_attention_tc_pack_bias: null pointer");
+  B200_REQUIRE(attn_tc_shape_ok(heads, n, ntypes) && n <= kAtNPadMax, "window_attention_tc: unsupported shape (n = %d, types = %d)", n, ntypes);
+  B200_REQUIRE(ws0 > 0 && ws1 > 0 && ws2 > 0 && n <= ws0 * ws1 * ws2, "window_attention_tc: window of %d tokens exceeds the module window", n);
+  B200_REQUIRE(ntypes == 1 || region_types, "window_attention_tc_pack_bias: several mask types need their region rows");
+  const int n_pad = (n + 31) / 32 * 32, nrt = (n + 127) / 128;
+  const long long total = (long long)ntypes * heads * nrt * 16 * n_pad * 8;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 8192);
+  attn_bias_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, region_types, (__half*)packed, heads, n, n_pad, nrt, ntypes, ws0, ws1, ws2);
+  B200_LAUNCH_CHECK("attn_bias_pack_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_window_attention_tc(const void* qkv, int N, int C, int heads, int nW, int n, const void* packed_bias,
+                                        const int32_t* sched, int ntypes, void* out, void* stream) {
+  B200_REQUIRE(qkv && out && packed_bias && sched, "window_attention_tc: null pointer");
+  B200_REQUIRE(N > 0 && nW > 0, "window_attention_tc: empty problem");
+  B200_REQUIRE(C == heads * 16, "window_attention_tc: head_dim must be 16 (C = %d, heads = %d)", C, heads);
+  B200_REQUIRE(attn_tc_shape_ok(heads, n, ntypes) && n <= kAtNPadMax, "window_attention_tc: unsupported shape (n = %d, types = %d)", n, ntypes);
+  AttnTcParams p;
+  p.qkv = (const __half*)qkv; p.out = (__half*)out; p.bias = (const __half*)packed_bias; p.sched = sched;
+  p.N = N; p.C8 = C / 8; p.heads = heads; p.nW = nW; p.n = n; p.n_pad = (n + 31) / 32 * 32; p.nrt = (n + 127) / 128; p.ntypes = ntypes;
+  // per-device attribute: set on every call (cheap), so a second GPU in the same process works
+  B200_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+  const long long total = (long long)N * nW * heads * p.nrt;
+  dim3 grid((unsigned)std::min<long long>(total, num_sms()));
+  window_attention_tc_kernel<<<grid, 320, kAtSmem, (cudaStream_t)stream>>>(p);
+  B200_LAUNCH_CHECK("window_attention_tc_kernel");
+  return B200_OK;
+}

@@ -1,0 +1,121 @@
+// Shared output stage of the tcgen05 convolution kernels (conv_tc.cu: 3x3x3 stride 1; conv_cin1_tc.cu: the
+// single-input-channel stems): tile geometry and the TMEM -> registers -> fp16 NC8 epilogue with bias and the
+// deterministic InstanceNorm partial sums of stats.cuh.
+//
+// GEMM rows of a tile = one 16 (H) x 8 (W) patch of an output D-plane; a tile holds BD consecutive planes whose fp32
+// accumulators are adjacent TMEM column blocks of NT columns; NB accumulator sets alternate between tiles.
+#pragma once
+#include "common.cuh"
+#include "stats.cuh"
+#include "tc05.cuh"
+
+namespace b200 {
+
+constexpr int kTH = 16, kTW = 8;                 // output patch per D-plane: 16 (H) x 8 (W) = 128 GEMM rows
+
+struct ConvEpiP {
+  __half* y;                 // NC8 destination
+  const float* bias;         // [Cout] or null
+  StatsPartials sp;          // deterministic statistics (buf == null: none)
+  int D, H, W;               // OUTPUT spatial size
+  int Cout, out_ctot, out_coff;
+  int tiles_w, tiles_h, tiles_d, n_tiles;
+  long long total_tiles;     // tiles_w * tiles_h * tiles_d * n_tiles * N
+};
+
+struct ConvTile { int w0, h0, d0, nt, n; };
+
+template <int BD>
+__device__ __forceinline__ ConvTile conv_tile(const ConvEpiP& p, long long t) {
+  // spatial tiles fastest, then the N tile, then the batch item: CTAs that run concurrently stream the same weights
+  ConvTile c;
+  c.w0 = (int)(t % p.tiles_w) * kTW; t /= p.tiles_w;
+  c.h0 = (int)(t % p.tiles_h) * kTH; t /= p.tiles_h;
+  c.d0 = (int)(t % p.tiles_d) * BD; t /= p.tiles_d;
+  c.nt = (int)(t % p.n_tiles);
+  c.n = (int)(t / p.n_tiles);
+  return c;
+}
+
+// Run by the four epilogue warps (any four warps whose ids cover the residues mod 4: warp w reads TMEM lanes
+// 32*(w & 3) ..).  acc_full[b] is completed by tcgen05.commit of the MMA warp, acc_empty[b] expects 128 arrivals.
+// s_stats: shared memory, 4 warp-private rows of 2*NT floats, zero-initialised by the caller.
+template <int NT, int BD, int NB>
+__device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                              float* s_stats, int warp, int lane) {
+  const int q = warp & 3;                 // TMEM lane quarter this warp may access
+  const int row = q * 32 + lane;
+  const long long S = (long long)p.D * p.H * p.W;
+  const long long sp_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d;
+  float* ws = s_stats + q * (2 * NT);
+  long long group = -1;
+  int it = 0;
+  for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    const ConvTile c = conv_tile<BD>(p, t);
+    if (p.sp.buf) {
+      const long long g = t / sp_tiles;
+      if (g != group) {
+        if (group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, 0, NT);
+        group = g;
+      }
+    }
+    const int buf = it % NB;
+    const uint32_t aph = (uint32_t)((it / NB) & 1);
+    const int h = c.h0 + (row >> 3), w = c.w0 + (row & 7);
+    const bool hw_ok = h < p.H && w < p.W;
+    const int co0 = c.nt * NT;
+    __half* ybase = p.y + (((long long)c.n * (p.out_ctot / 8) + (p.out_coff + co0) / 8) * S) * 8;
+    tc::mbar_wait(&acc_full[buf], aph);
+    tc::fence_after_sync();
+    const uint32_t tq = tmem_base + buf * (BD * NT) + ((uint32_t)(q * 32) << 16);
+    uint32_t vn[8];
+    tc::tmem_ld8(tq, vn);   // (cc = 0, sub = 0); every later load is prefetched one step ahead
+#pragma unroll 1
+    for (int cc = 0; cc < NT / 8; ++cc) {
+      float bsum[8], bsq[8], bias8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = p.bias ? p.bias[co0 + cc * 8 + j] : 0.f; }
+#pragma unroll
+      for (int sub = 0; sub < BD; ++sub) {
+        uint32_t v[8];
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = vn[j];
+        {
+          const int nsub = sub + 1 < BD ? sub + 1 : 0, ncc = sub + 1 < BD ? cc : cc + 1;
+          if (ncc < NT / 8) tc::tmem_ld8(tq + nsub * NT + ncc * 8, vn);
+        }
+        const int dz = c.d0 + sub;
+        const bool ok = hw_ok && dz < p.D;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = __uint_as_float(v[j]) + bias8[j];
+          if (ok) { bsum[j] += f[j]; bsq[j] = fmaf(f[j], f[j], bsq[j]); }
+        }
+        if (ok) {
+          uint4 hv;
+          __half2* hp = reinterpret_cast<__half2*>(&hv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+          *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * p.H + h) * p.W + w) * 8) = hv;
+        }
+      }
+      if (p.sp.buf) {
+        float a1, b1;
+        transpose_reduce8(bsum, bsq, lane, a1, b1);
+        if ((lane & 3) == 0) {   // eight lanes, eight different columns of the warp-private row: no atomics
+          const int col = cc * 8 + transpose_reduce8_col(lane);
+          ws[2 * col] += a1;
+          ws[2 * col + 1] += b1;
+        }
+      }
+    }
+    // this thread's TMEM reads of the set are complete: hand it back to the MMA warp
+    tc::fence_before_sync();
+    tc::mbar_arrive(&acc_empty[buf]);
+  }
+  if (p.sp.buf && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, 0, NT);
+}
+
+}  // namespace b200

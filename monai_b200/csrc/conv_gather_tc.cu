@@ -13,6 +13,7 @@
 // either NC8 fp16 (optionally into a channel slice of a concat buffer) or NCDHW (the Cout = 2 segmentation head).
 #include "common.cuh"
 #include "tc05.cuh"
+#include "stats.cuh"
 #include "../../include/monai_b200.h"
 
 namespace b200 {
@@ -25,7 +26,8 @@ struct CgTap { unsigned char id; signed char dz, dy, dx; };
 
 struct CgParams {
   b200_conv_gather_desc d;
-  const __half* x; const __half* w; const float* bias; void* y; float* stats;
+  const __half* x; const __half* w; const float* bias; void* y;
+  StatsPartials sp;           // deterministic InstanceNorm partial sums (stats.cuh)
   int NT, tmem_cols, cout_pad;
   int ncls, mul;              // classes; input coordinate = coarse * mul + tap offset
   int Dc, Hc, Wc;             // coarse extent of one class
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 4) tc::tmem_alloc(tmem_slot, p.tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
@@ -141,11 +143,13 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
     constexpr int kCgInflight = 3;
     int pend_first = 0, pend_n = 0;   // pending stages are pend_first, pend_first+1, ... (mod kCgStages)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = (int)(tile % n_tiles);
-      long long t2 = tile / n_tiles;
-      const int rt = (int)(t2 % row_tiles); t2 /= row_tiles;
-      const int cls = (int)(t2 % p.ncls);
-      const int n = (int)(t2 / p.ncls);
+      // tile order: row tile fastest, then parity class, then N tile, then batch item (consecutive tiles share their
+      // weights; the tiles of one (batch item, N tile) group are contiguous for the deterministic statistics)
+      const int rt = (int)(tile % row_tiles);
+      long long t2 = tile / row_tiles;
+      const int cls = (int)(t2 % p.ncls); t2 /= p.ncls;
+      const int nt = (int)(t2 % n_tiles);
+      const int n = (int)(t2 / n_tiles);
       const long long cv = (long long)rt * 128 + r;
       const bool row_ok = cv < coarse;
       const int cx = row_ok ? (int)(cv % p.Wc) : 0, cy = row_ok ? (int)((cv / p.Wc) % p.Hc) : 0, cz = row_ok ? (int)(cv / ((long long)p.Wc * p.Hc)) : 0;
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
       int s = 0; uint32_t ph = 0;
       int it = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int cls = (int)((tile / n_tiles / row_tiles) % p.ncls);
+        const int cls = (int)((tile / row_tiles) % p.ncls);
         const int units = p.cls_ntaps[cls] * kcs;
         const int buf = it & 1;
         const uint32_t aph = (uint32_t)((it >> 1) & 1);
@@ -227,13 +231,24 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
   } else {
     // ===================== epilogue (warps 5..8) =====================
     const int q = warp & 3;
+    float* ws = s_stats + q * (2 * NT);
+    long long group = -1;
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int nt = (int)(tile % n_tiles);
-      long long t2 = tile / n_tiles;
-      const int rt = (int)(t2 % row_tiles); t2 /= row_tiles;
-      const int cls = (int)(t2 % p.ncls);
-      const int n = (int)(t2 / p.ncls);
+      if (p.sp.buf) {
+        const long long g = tile / ((long long)p.ncls * row_tiles);
+        if (g != group) {
+          if (group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, 0, NT);
+          group = g;
+        }
+      }
+      // tile order: row tile fastest, then parity class, then N tile, then batch item (consecutive tiles share their
+      // weights; the tiles of one (batch item, N tile) group are contiguous for the deterministic statistics)
+      const int rt = (int)(tile % row_tiles);
+      long long t2 = tile / row_tiles;
+      const int cls = (int)(t2 % p.ncls); t2 /= p.ncls;
+      const int nt = (int)(t2 % n_tiles);
+      const int n = (int)(t2 / n_tiles);
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)((it >> 1) & 1);
       const long long cv = (long long)rt * 128 + q * 32 + lane;
@@ -284,31 +299,23 @@ __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
               }
           }
         }
-        if (p.stats) {
-          float a1[8], b1[8];
+        if (p.sp.buf) {
+          float a8[8], b8[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { a1[j] = ok ? f[j] : 0.f; b1[j] = a1[j] * a1[j]; }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { a1[j] = warp_sum(a1[j]); b1[j] = warp_sum(b1[j]); }
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { atomicAdd(&s_stats[2 * (cc * 8 + j)], a1[j]); atomicAdd(&s_stats[2 * (cc * 8 + j) + 1], b1[j]); }
+          for (int j = 0; j < 8; ++j) { a8[j] = ok ? f[j] : 0.f; b8[j] = a8[j] * a8[j]; }
+          float cs, cq;
+          transpose_reduce8(a8, b8, lane, cs, cq);
+          if ((lane & 3) == 0) {
+            const int col = cc * 8 + transpose_reduce8_col(lane);
+            ws[2 * col] += cs;
+            ws[2 * col + 1] += cq;
           }
         }
       }
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[buf]);
-      if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int t = threadIdx.x - 160;
-        for (int i = t; i < 2 * NT; i += 128) {
-          const int col = co0 + i / 2;
-          if (col < d.Cout) atomicAdd(&p.stats[((long long)n * d.Cout + col) * 2 + (i & 1)], s_stats[i]);
-          s_stats[i] = 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
     }
+    if (p.sp.buf && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, 0, NT);
   }
   __syncthreads();
   if (warp == 4) {
@@ -365,9 +372,19 @@ extern "C" int b200_conv_gather_tc_pack_weight(const b200_conv_gather_desc* desc
   return B200_OK;
 }
 
+extern "C" long long b200_conv_gather_tc_workspace_bytes(const b200_conv_gather_desc* desc) {
+  if (!desc) return -1;
+  CgParams p;
+  if (cg_setup(*desc, p)) return -1;
+  const long long coarse = (long long)p.Dc * p.Hc * p.Wc;
+  const long long tpg = (long long)p.ncls * ((coarse + 127) / 128), groups = (long long)desc->N * (p.cout_pad / p.NT);
+  return stats_partial_bytes(groups, stats_rows(tpg, tpg * groups), p.NT);
+}
+
 extern "C" int b200_conv_gather_tc(const b200_conv_gather_desc* desc, const void* x, const void* packed_w, const float* bias,
-                                   void* y, float* stats, void* stream) {
+                                   void* y, float* stats, void* workspace, void* stream) {
   B200_REQUIRE(desc && x && packed_w && y, "conv_gather_tc: null pointer");
+  B200_REQUIRE(!stats || workspace, "conv_gather_tc: statistics need the workspace of b200_conv_gather_tc_workspace_bytes()");
   CgParams p;
   int rc = cg_setup(*desc, p);
   if (rc) return rc;
@@ -381,17 +398,19 @@ extern "C" int b200_conv_gather_tc(const b200_conv_gather_desc* desc, const void
     B200_REQUIRE(d.Do >= lo_d && d.Do < lo_d + d.stride && d.Ho >= lo_h && d.Ho < lo_h + d.stride && d.Wo >= lo_w && d.Wo < lo_w + d.stride,
                  "conv_gather_tc: output shape does not match transposed-conv arithmetic");
   }
-  p.x = (const __half*)x; p.w = (const __half*)packed_w; p.bias = bias; p.y = y; p.stats = stats;
-  const int smem = kCgStages * (kCgAStage + kCgUnits * p.NT * 32) + 128 + 2 * p.NT * 4 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  p.x = (const __half*)x; p.w = (const __half*)packed_w; p.bias = bias; p.y = y;
+  const int smem = kCgStages * (kCgAStage + kCgUnits * p.NT * 32) + 128 + 4 * 2 * p.NT * 4 + 128;
+  // per-device attribute: set on every call (cheap), so a second GPU in the same process works
+  B200_CUDA(cudaFuncSetAttribute(conv_gather_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   const long long coarse = (long long)p.Dc * p.Hc * p.Wc;
-  const long long total_tiles = (long long)d.N * p.ncls * ((coarse + 127) / 128) * (p.cout_pad / p.NT);
+  const long long tpg = (long long)p.ncls * ((coarse + 127) / 128), groups = (long long)d.N * (p.cout_pad / p.NT);
+  const long long total_tiles = tpg * groups;
+  p.sp.buf = stats ? (float*)workspace : nullptr;
+  p.sp.R = stats_rows(tpg, total_tiles);
+  p.sp.tiles_per_group = tpg;
   dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
   conv_gather_tc_kernel<<<grid, 288, smem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("conv_gather_tc_kernel");
+  if (stats) return launch_stats_finish((const float*)workspace, groups, p.sp.R, p.NT, p.cout_pad / p.NT, d.Cout, stats, (cudaStream_t)stream);
   return B200_OK;
 }

@@ -26,6 +26,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
 #include "common.cuh"
 #include "tc05.cuh"
+#include "conv_epi.cuh"
 #include "../../include/monai_b200.h"
 #include <mutex>
 #include <type_traits>
@@ -113,8 +114,7 @@ __global__ void conv_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 // ----------------------------------------------------------------------------------------------------------
 // the convolution kernel
 // ----------------------------------------------------------------------------------------------------------
-constexpr int kTH = 16, kTW = 8;                 // output patch per D-plane: 16 (H) x 8 (W) = 128 GEMM rows
-constexpr int kHH = kTH + 2, kHW = kTW + 2;      // halo patch
+constexpr int kHH = kTH + 2, kHW = kTW + 2;      // halo patch (kTH x kTW output patch: conv_epi.cuh)
 
 template <int NT, int BD>
 struct ConvTcCfg {
@@ -130,7 +130,7 @@ struct ConvTcCfg {
   static constexpr int kAccBufs = (2 * BD * NT <= 512) ? 2 : 1;  // accumulator sets: 2 lets the epilogue of tile i overlap the MMAs of tile i+1
   static constexpr int kAccCols = kAccBufs * BD * NT;
   static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + 256 /*barriers*/ + 2 * NT * 4 /*stats*/ + 128 /*align slack*/;
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + 256 /*barriers*/ + 4 * 2 * NT * 4 /*warp-private stats rows*/ + 128 /*align slack*/;
   static_assert(BD * NT <= 512, "accumulators exceed TMEM");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "invalid UMMA N");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -139,26 +139,8 @@ struct ConvTcCfg {
 struct ConvTcParams {
   b200_conv_tc_desc d;
   const __half* w;      // packed
-  const float* bias;
-  __half* y;
-  float* stats;
-  int tiles_w, tiles_h, tiles_d, n_tiles;
-  long long total_tiles;   // tiles_w * tiles_h * tiles_d * n_tiles * N
+  ConvEpiP e;           // output stage (conv_epi.cuh)
 };
-
-struct ConvTile { int w0, h0, d0, nt, n; };
-
-template <int BD>
-__device__ __forceinline__ ConvTile conv_tile(const ConvTcParams& p, long long t) {
-  // spatial tiles fastest, then the N tile, then the batch item: CTAs that run concurrently stream the same weights
-  ConvTile c;
-  c.w0 = (int)(t % p.tiles_w) * kTW; t /= p.tiles_w;
-  c.h0 = (int)(t % p.tiles_h) * kTH; t /= p.tiles_h;
-  c.d0 = (int)(t % p.tiles_d) * BD; t /= p.tiles_d;
-  c.nt = (int)(t % p.n_tiles);
-  c.n = (int)(t / p.n_tiles);
-  return c;
-}
 
 // Persistent, warp-specialised (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2-5 = epilogue.  Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the shared-memory rings run
@@ -180,7 +162,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
   uint64_t* acc_empty = acc_full + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   static_assert(2 * kSA + 2 * kSB + 4 + 1 <= 32, "barrier block");
-  float* s_stats = reinterpret_cast<float*>(bars + 32);  // [2*NT]
+  float* s_stats = reinterpret_cast<float*>(bars + 32);  // [4][2*NT]
 
   const b200_conv_tc_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,7 +174,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc::fence_before_sync();
   __syncthreads();
@@ -204,8 +186,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmap);
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const ConvTile c = conv_tile<BD>(p, t);
+      for (long long t = blockIdx.x; t < p.e.total_tiles; t += gridDim.x) {
+        const ConvTile c = conv_tile<BD>(p.e, t);
         const __half* wbase = p.w + (long long)c.nt * num_kc * 9 * (Cfg::kBTapBytes / 2);
         for (int kc = 0; kc < num_kc; ++kc) {
           tc::mbar_wait(&empty_a[sa], pa ^ 1);
@@ -271,7 +253,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
         if (++sb == kSB) { sb = 0; pb ^= 1; }
       };
       int it = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      for (long long t = blockIdx.x; t < p.e.total_tiles; t += gridDim.x, ++it) {
         const int buf = it % kNB;
         const uint32_t aph = (uint32_t)((it / kNB) & 1);
         tc::mbar_wait(&acc_empty[buf], aph ^ 1);   // the epilogue has drained this accumulator set
@@ -296,74 +278,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const long long S = (long long)d.D * d.H * d.W;
-    int it = 0;
-    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const ConvTile c = conv_tile<BD>(p, t);
-      const int buf = it % kNB;
-      const uint32_t aph = (uint32_t)((it / kNB) & 1);
-      const int h = c.h0 + (row >> 3), w = c.w0 + (row & 7);
-      const bool hw_ok = h < d.H && w < d.W;
-      const int co0 = c.nt * NT;
-      __half* ybase = p.y + (((long long)c.n * (d.out_ctot / 8) + (d.out_coff + co0) / 8) * S) * 8;
-      tc::mbar_wait(&acc_full[buf], aph);
-      tc::fence_after_sync();
-      const uint32_t tq = tmem_base + buf * (BD * NT) + ((uint32_t)(q * 32) << 16);
-      uint32_t vn[8];
-      tc::tmem_ld8(tq, vn);   // (cc = 0, sub = 0); every later load is prefetched one step ahead
-#pragma unroll 1
-      for (int cc = 0; cc < NT / 8; ++cc) {
-        float bsum[8], bsq[8], bias8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = p.bias ? p.bias[co0 + cc * 8 + j] : 0.f; }
-#pragma unroll
-        for (int sub = 0; sub < BD; ++sub) {
-          uint32_t v[8];
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = vn[j];
-          {
-            const int nsub = sub + 1 < BD ? sub + 1 : 0, ncc = sub + 1 < BD ? cc : cc + 1;
-            if (ncc < NT / 8) tc::tmem_ld8(tq + nsub * NT + ncc * 8, vn);
-          }
-          const int dz = c.d0 + sub;
-          const bool ok = hw_ok && dz < d.D;
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            f[j] = __uint_as_float(v[j]) + bias8[j];
-            if (ok) { bsum[j] += f[j]; bsq[j] = fmaf(f[j], f[j], bsq[j]); }
-          }
-          if (ok) {
-            uint4 hv;
-            __half2* hp = reinterpret_cast<__half2*>(&hv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-            *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * d.H + h) * d.W + w) * 8) = hv;
-          }
-        }
-        if (p.stats) {
-          float a1, b1;
-          transpose_reduce8(bsum, bsq, lane, a1, b1);
-          if ((lane & 3) == 0) {
-            const int col = cc * 8 + transpose_reduce8_col(lane);
-            atomicAdd(&s_stats[2 * col], a1);
-            atomicAdd(&s_stats[2 * col + 1], b1);
-          }
-        }
-      }
-      // this thread's TMEM reads of the set are complete: hand it back to the MMA warp
-      tc::fence_before_sync();
-      tc::mbar_arrive(&acc_empty[buf]);
-      if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int tt = threadIdx.x - 64;
-        for (int i = tt; i < 2 * NT; i += 128) { atomicAdd(&p.stats[((long long)c.n * d.Cout + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-    }
+    conv_epilogue<NT, BD, kNB>(p.e, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
   }
   __syncthreads();
   if (warp == 1) {
@@ -476,9 +391,27 @@ extern "C" int b200_conv3x3x3_tc_pack_weight(const float* w, int Cin, int Cout, 
 }
 
 template <int NT, int BD>
-static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats,
-                          cudaStream_t st) {
+struct ConvTcGeom {
+  static void fill(const b200_conv_tc_desc& d, ConvEpiP& e) {
+    e.D = d.D; e.H = d.H; e.W = d.W; e.Cout = d.Cout; e.out_ctot = d.out_ctot; e.out_coff = d.out_coff;
+    e.tiles_w = ceil_div(d.W, kTW); e.tiles_h = ceil_div(d.H, kTH); e.tiles_d = ceil_div(d.D, BD); e.n_tiles = d.Cout / NT;
+    e.total_tiles = (long long)e.tiles_w * e.tiles_h * e.tiles_d * e.n_tiles * d.N;
+  }
+};
+
+// what a launch needs beyond the operands: mode 0 = run, mode 1 = only report the statistics workspace size
+struct ConvTcCall { const void* x; const void* w; const float* bias; void* y; float* stats; void* ws; cudaStream_t st; long long ws_bytes; int query; };
+
+template <int NT, int BD>
+static int launch_conv_tc(const b200_conv_tc_desc& d, ConvTcCall& c) {
   using Cfg = ConvTcCfg<NT, BD>;
+  ConvTcParams p;
+  p.d = d; p.w = (const __half*)c.w;
+  ConvTcGeom<NT, BD>::fill(d, p.e);
+  const long long sp_tiles = (long long)p.e.tiles_w * p.e.tiles_h * p.e.tiles_d, groups = (long long)d.N * p.e.n_tiles;
+  const int R = stats_rows(sp_tiles, p.e.total_tiles);
+  c.ws_bytes = stats_partial_bytes(groups, R, NT);
+  if (c.query) return B200_OK;
   EncodeTiledFn enc = get_encode_tiled();
   B200_REQUIRE(enc != nullptr, "conv3x3x3_tc: cuTensorMapEncodeTiled entry point unavailable");
   CUtensorMap tmap;
@@ -487,63 +420,69 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, const void* x, const void*
   cuuint64_t gstr[4] = {(cuuint64_t)d.W * 16, (cuuint64_t)d.H * d.W * 16, S * 16, S * 16 * (cuuint64_t)(d.in_ctot / 8)};
   cuuint32_t box[5] = {(cuuint32_t)kHW * 8, (cuuint32_t)kHH, (cuuint32_t)(BD + 2), 2, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(c.x), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "conv3x3x3_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  ConvTcParams p;
-  p.d = d; p.w = (const __half*)w; p.bias = bias; p.y = (__half*)y; p.stats = stats;
-  p.tiles_w = ceil_div(d.W, kTW); p.tiles_h = ceil_div(d.H, kTH); p.tiles_d = ceil_div(d.D, BD); p.n_tiles = d.Cout / NT;
-  p.total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.n_tiles * d.N;
-  dim3 grid((unsigned)std::min<long long>(p.total_tiles, num_sms()));
+  p.e.y = (__half*)c.y; p.e.bias = c.bias;
+  p.e.sp.buf = c.stats ? (float*)c.ws : nullptr; p.e.sp.R = R; p.e.sp.tiles_per_group = sp_tiles;
+  dim3 grid((unsigned)std::min<long long>(p.e.total_tiles, num_sms()));
   auto kern = conv3x3x3_tc_kernel<NT, BD>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tmap, p);
+  // per-device attribute: set on every call (cheap), so a second GPU in the same process works
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  kern<<<grid, 192, Cfg::kSmemBytes, c.st>>>(tmap, p);
   B200_LAUNCH_CHECK("conv3x3x3_tc_kernel");
+  if (c.stats) return launch_stats_finish((const float*)c.ws, groups, R, NT, p.e.n_tiles, d.Cout, c.stats, c.st);
   return B200_OK;
 }
 
 template <int NT>
-static int dispatch_bd(const b200_conv_tc_desc& d, const void* x, const void* w, const float* bias, void* y, float* stats,
-                       cudaStream_t st) {
+static int dispatch_bd(const b200_conv_tc_desc& d, ConvTcCall& c) {
   // deeper CTA tiles amortise the halo and fuse more kd taps per MMA; two accumulator sets (2*BD*NT <= 512 TMEM columns)
   // let the epilogue overlap the next tile, which is worth more than depth for the wide-N layers
   if constexpr (2 * NT * 4 <= 512) {
-    if (d.D % 4 == 0 || d.D >= 16) return launch_conv_tc<NT, 4>(d, x, w, bias, y, stats, st);
+    if (d.D % 4 == 0 || d.D >= 16) return launch_conv_tc<NT, 4>(d, c);
   }
   if constexpr (NT * 2 <= 512) {
-    if (d.D >= 2) return launch_conv_tc<NT, 2>(d, x, w, bias, y, stats, st);
+    if (d.D >= 2) return launch_conv_tc<NT, 2>(d, c);
   }
-  return launch_conv_tc<NT, 1>(d, x, w, bias, y, stats, st);
+  return launch_conv_tc<NT, 1>(d, c);
 }
 
-extern "C" int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
-                                 void* y, float* stats, void* stream) {
-  B200_REQUIRE(desc && x && packed_w && y, "conv3x3x3_tc: null pointer");
-  const b200_conv_tc_desc& d = *desc;
+static int conv_tc_dispatch(const b200_conv_tc_desc& d, ConvTcCall& c) {
   B200_REQUIRE(d.N > 0 && d.D > 0 && d.H > 0 && d.W > 0, "conv3x3x3_tc: empty problem");
   B200_REQUIRE(d.Cin > 0 && d.Cin % 16 == 0 && d.Cout > 0 && d.Cout % 16 == 0,
                "conv3x3x3_tc: Cin and Cout must be multiples of 16 (got %d, %d)", d.Cin, d.Cout);
   B200_REQUIRE(d.in_ctot % 8 == 0 && d.in_coff % 8 == 0 && d.in_coff + d.Cin <= d.in_ctot, "conv3x3x3_tc: bad input channel slice");
   B200_REQUIRE(d.out_ctot % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + d.Cout <= d.out_ctot, "conv3x3x3_tc: bad output channel slice");
-  B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(packed_w) & 15) == 0, "conv3x3x3_tc: pointers must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
   switch (conv_tc_nt(d.Cout)) {
-    case 16: return dispatch_bd<16>(d, x, packed_w, bias, y, stats, st);
-    case 32: return dispatch_bd<32>(d, x, packed_w, bias, y, stats, st);
-    case 48: return dispatch_bd<48>(d, x, packed_w, bias, y, stats, st);
-    case 64: return dispatch_bd<64>(d, x, packed_w, bias, y, stats, st);
-    case 80: return dispatch_bd<80>(d, x, packed_w, bias, y, stats, st);
-    case 96: return dispatch_bd<96>(d, x, packed_w, bias, y, stats, st);
-    case 112: return dispatch_bd<112>(d, x, packed_w, bias, y, stats, st);
-    case 128: return dispatch_bd<128>(d, x, packed_w, bias, y, stats, st);
+    case 16: return dispatch_bd<16>(d, c);
+    case 32: return dispatch_bd<32>(d, c);
+    case 48: return dispatch_bd<48>(d, c);
+    case 64: return dispatch_bd<64>(d, c);
+    case 80: return dispatch_bd<80>(d, c);
+    case 96: return dispatch_bd<96>(d, c);
+    case 112: return dispatch_bd<112>(d, c);
+    case 128: return dispatch_bd<128>(d, c);
     default: return set_err(B200_ERR_UNSUPPORTED, "conv3x3x3_tc: unsupported Cout %d", d.Cout);
   }
+}
+
+extern "C" long long b200_conv3x3x3_tc_workspace_bytes(const b200_conv_tc_desc* desc) {
+  if (!desc) return -1;
+  ConvTcCall c{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1};
+  if (conv_tc_dispatch(*desc, c)) return -1;
+  return c.ws_bytes;
+}
+
+extern "C" int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
+                                 void* y, float* stats, void* workspace, void* stream) {
+  B200_REQUIRE(desc && x && packed_w && y, "conv3x3x3_tc: null pointer");
+  B200_REQUIRE(!stats || workspace, "conv3x3x3_tc: statistics need the workspace of b200_conv3x3x3_tc_workspace_bytes()");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(packed_w) & 15) == 0, "conv3x3x3_tc: pointers must be 16-byte aligned");
+  ConvTcCall c{x, packed_w, bias, y, stats, workspace, (cudaStream_t)stream, 0, 0};
+  return conv_tc_dispatch(*desc, c);
 }
 
 extern "C" int b200_norm_act_nc8(const void* x, int x_ctot, int x_coff, int N, int C, long long S, const float* stats,

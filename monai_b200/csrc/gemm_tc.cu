@@ -15,6 +15,7 @@
 // InstanceNorm partial sums, and a row map (identity / index table / 2x upsample scatter) before the fp16 NC8 store.
 #include "common.cuh"
 #include "tc05.cuh"
+#include "stats.cuh"
 #include "../../include/monai_b200.h"
 
 namespace b200 {
@@ -51,7 +52,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 struct GemmTcParams {
   b200_gemm_tc_desc d;
-  const __half* x; const __half* w; const float* bias; __half* y; const __half* res; float* stats; const int32_t* row_map;
+  const __half* x; const __half* w; const float* bias; __half* y; const __half* res; const int32_t* row_map;
+  StatsPartials sp;   // deterministic InstanceNorm partial sums (stats.cuh)
   int NT, tmem_cols;
 };
 
@@ -79,13 +81,21 @@ __global__ void gemm_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 constexpr int kGemmEpiWarps = 16;   // 4 per TMEM lane quarter; warps sharing a quarter split the 16-column steps
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 
-// tcgen05.wait::ld that names the destination registers, so the compiler cannot schedule their uses above it
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-               :
-               : "memory");
+using tc::tmem_ld_wait16;
+
+// tile -> (N tile, row tile, batch item).  Without statistics the N tiles of a row tile run back to back (the A tile is
+// re-read from L2); with statistics the row tiles of one (batch item, N tile) group are contiguous, which is what the
+// deterministic partial sums of stats.cuh need.
+template <bool STATS>
+__device__ __forceinline__ void gemm_tile(long long tile, int n_tiles, int row_tiles, int& nt, int& rt, int& n) {
+  if (STATS) {
+    rt = (int)(tile % row_tiles);
+    nt = (int)((tile / row_tiles) % n_tiles);
+  } else {
+    nt = (int)(tile % n_tiles);
+    rt = (int)((tile / n_tiles) % row_tiles);
+  }
+  n = (int)(tile / ((long long)n_tiles * row_tiles));
 }
 
 template <int MODE, int ACT, bool RES, bool STATS>
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
   uint64_t* acc_full = bars + 2 * kGemmStages;       // [2]
   uint64_t* acc_empty = acc_full + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_stats = reinterpret_cast<float*>(bars + 16);  // [2*NT]
+  float* s_stats = reinterpret_cast<float*>(bars + 16);  // [4][2*NT] (one row per TMEM lane quarter)
 
   const b200_gemm_tc_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
     tc::fence_barrier_init();
   }
   if (STATS)
-    for (int i = threadIdx.x; i < 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 1) tc::tmem_alloc(tmem_slot, p.tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
@@ -128,9 +138,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = (int)(tile % n_tiles);
-        const int rt = (int)((tile / n_tiles) % row_tiles);
-        const int n = (int)(tile / ((long long)n_tiles * row_tiles));
+        int nt, rt, n;
+        gemm_tile<STATS>(tile, n_tiles, row_tiles, nt, rt, n);
         const __half* wbase = p.w + (long long)nt * num_k16 * (NT * 16);
         for (int st = 0; st < num_stages; ++st) {
           const int steps = min(kGemmK16PerStage, num_k16 - st * kGemmK16PerStage);
@@ -191,11 +200,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
     const float* __restrict__ bias = p.bias;
     const bool has_bias = bias != nullptr;
     const int W2 = 2 * d.W, HW4 = 4 * d.H * d.W;
+    float* ws = s_stats + q * (2 * NT);   // running column sums of this lane quarter; the warps of a quarter own disjoint columns
+    long long group = -1;
     int it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int nt = (int)(tile % n_tiles);
-      const int rt = (int)((tile / n_tiles) % row_tiles);
-      const int n = (int)(tile / ((long long)n_tiles * row_tiles));
+      int nt, rt, n;
+      gemm_tile<STATS>(tile, n_tiles, row_tiles, nt, rt, n);
+      if (STATS) {
+        const long long g = tile / row_tiles;   // (batch item, N tile): tiles of a group are contiguous (row tile fastest)
+        if (g != group) {
+          if (group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, c_lo * 16, c_hi * 16);
+          group = g;
+        }
+      }
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)((it >> 1) & 1);
       const int row = rt * 128 + q * 32 + lane;
@@ -274,8 +291,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
             transpose_reduce8(a8, b8, lane, cs, cq);
             if ((lane & 3) == 0) {
               const int col = g8 * 8 + transpose_reduce8_col(lane);
-              atomicAdd(&s_stats[2 * col], cs);
-              atomicAdd(&s_stats[2 * col + 1], cq);
+              ws[2 * col] += cs;
+              ws[2 * col + 1] += cq;
             }
           }
         }
@@ -310,13 +327,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
       // this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[buf]);
-      if (STATS) {
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
-        const int t = threadIdx.x - 64;
-        for (int i = t; i < 2 * NT; i += 32 * kGemmEpiWarps) { atomicAdd(&p.stats[((long long)n * d.N + co0) * 2 + i], s_stats[i]); s_stats[i] = 0.f; }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
-      }
     }
+    if (STATS && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, c_lo * 16, c_hi * 16);
   }
   __syncthreads();
   if (warp == 1) {
@@ -361,10 +373,7 @@ extern "C" int b200_gemm_tc_pack_weight(const float* w, int N, int K, long long 
   return B200_OK;
 }
 
-extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
-                            const void* res, const int32_t* row_map, void* y, float* stats, void* stream) {
-  B200_REQUIRE(desc && x && packed_w && y, "gemm_tc: null pointer");
-  const b200_gemm_tc_desc& d = *desc;
+static int gemm_tc_check(const b200_gemm_tc_desc& d, const void* res, const int32_t* row_map) {
   B200_REQUIRE(d.Nb > 0 && d.S > 0 && d.S_out > 0, "gemm_tc: empty problem");
   B200_REQUIRE(d.K > 0 && d.K % 16 == 0 && d.N > 0 && d.N % 16 == 0, "gemm_tc: N and K must be multiples of 16 (got %d, %d)", d.N, d.K);
   B200_REQUIRE(d.in_ctot % 8 == 0 && d.in_coff % 8 == 0 && d.in_coff + d.K <= d.in_ctot, "gemm_tc: bad input channel slice");
@@ -376,18 +385,40 @@ extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const 
   B200_REQUIRE(d.out_ctot % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + cout <= d.out_ctot, "gemm_tc: bad output channel slice");
   B200_REQUIRE(!res || (d.res_ctot % 8 == 0 && d.res_coff % 8 == 0 && d.res_coff + cout <= d.res_ctot), "gemm_tc: bad residual channel slice");
   B200_REQUIRE(d.act == 0 || d.act == 4, "gemm_tc: activation must be 0 (none) or 4 (gelu)");
+  return B200_OK;
+}
+
+extern "C" long long b200_gemm_tc_workspace_bytes(const b200_gemm_tc_desc* desc) {
+  if (!desc || desc->N <= 0 || desc->N % 16 || desc->S <= 0 || desc->Nb <= 0) return -1;
+  const int NT = gemm_tc_nt(desc->N);
+  const long long row_tiles = ceil_div(desc->S, 128), groups = (long long)desc->Nb * (desc->N / NT);
+  return stats_partial_bytes(groups, stats_rows(row_tiles, row_tiles * groups), NT);
+}
+
+extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
+                            const void* res, const int32_t* row_map, void* y, float* stats, void* workspace, void* stream) {
+  B200_REQUIRE(desc && x && packed_w && y, "gemm_tc: null pointer");
+  B200_REQUIRE(!stats || workspace, "gemm_tc: statistics need the workspace of b200_gemm_tc_workspace_bytes()");
+  const b200_gemm_tc_desc& d = *desc;
+  int rc = gemm_tc_check(d, res, row_map);
+  if (rc) return rc;
   const int NT = gemm_tc_nt(d.N);
   GemmTcParams p;
-  p.d = d; p.x = (const __half*)x; p.w = (const __half*)packed_w; p.bias = bias; p.y = (__half*)y; p.res = (const __half*)res; p.stats = stats;
+  p.d = d; p.x = (const __half*)x; p.w = (const __half*)packed_w; p.bias = bias; p.y = (__half*)y; p.res = (const __half*)res;
   p.row_map = row_map; p.NT = NT;
   p.tmem_cols = 2 * NT <= 32 ? 32 : 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;  // two accumulator buffers
-  const int smem = kGemmStages * (kGemmAStage + kGemmK16PerStage * NT * 32) + 128 + 2 * NT * 4 + 128;
+  const int smem = kGemmStages * (kGemmAStage + kGemmK16PerStage * NT * 32) + 128 + 4 * 2 * NT * 4 + 128;
   GemmKernelFn fn = gemm_pick(d.mode, d.act, res != nullptr, stats != nullptr);
   B200_REQUIRE(fn != nullptr, "gemm_tc: the 2x upsample scatter (mode 2) does not take a residual");
-  B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  const long long total_tiles = (long long)ceil_div(d.S, 128) * (d.N / NT) * d.Nb;
+  B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  const long long row_tiles = ceil_div(d.S, 128), groups = (long long)d.Nb * (d.N / NT);
+  const long long total_tiles = row_tiles * groups;
+  p.sp.buf = stats ? (float*)workspace : nullptr;
+  p.sp.R = stats_rows(row_tiles, total_tiles);
+  p.sp.tiles_per_group = row_tiles;
   dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
   fn<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
+  if (stats) return launch_stats_finish((const float*)workspace, groups, p.sp.R, NT, d.N / NT, d.N, stats, (cudaStream_t)stream);
   return B200_OK;
 }

@@ -4,33 +4,33 @@
 // PReLU / LeakyReLU as ordered by ADN("NDA") (monai/networks/blocks/acti_norm.py:19-101), and the residual
 // tail of UnetResBlock (monai/networks/blocks/dynunet_block.py:97-111: out = lrelu(norm2(conv2) + norm3(conv3(x)))).
 #include "common.cuh"
+#include "stats.cuh"
 #include "../../include/monai_b200.h"
 
 namespace b200 {
 
-// One block handles `chunk` consecutive elements of one (n,c) plane; partial sums go through fp32 atomics.
+// One block per (n,c) plane: every thread adds a fixed strided subset, the warp totals are combined in warp order --
+// the same bits on every run (no floating-point atomics).
 template <typename T>
-__global__ void __launch_bounds__(256) instnorm_stats_kernel(const T* __restrict__ x, int C, long long S,
-                                                             long long stride_n, long long chunk, float* __restrict__ stats) {
-  const int nc = blockIdx.y;
+__global__ void __launch_bounds__(1024) instnorm_stats_kernel(const T* __restrict__ x, int C, long long S,
+                                                              long long stride_n, float* __restrict__ stats) {
+  const int nc = blockIdx.x;
   const int n = nc / C, c = nc % C;
   const T* p = x + (long long)n * stride_n + (long long)c * S;
-  const long long lo = (long long)blockIdx.x * chunk, hi = min(S, lo + chunk);
   float s = 0.f, q = 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+  for (long long i = threadIdx.x; i < S; i += blockDim.x) {
     const float v = io<T>::ld(p + i);
     s += v; q = fmaf(v, v, q);
   }
   s = warp_sum(s); q = warp_sum(q);
-  __shared__ float ss[8], sq[8];
+  __shared__ float ss[32], sq[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) { ss[wid] = s; sq[wid] = q; }
   __syncthreads();
-  if (wid == 0) {
-    s = lane < (blockDim.x >> 5) ? ss[lane] : 0.f;
-    q = lane < (blockDim.x >> 5) ? sq[lane] : 0.f;
-    s = warp_sum(s); q = warp_sum(q);
-    if (lane == 0) { atomicAdd(stats + 2 * nc, s); atomicAdd(stats + 2 * nc + 1, q); }
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += (double)ss[w]; tq += (double)sq[w]; }
+    stats[2 * nc] = (float)ts; stats[2 * nc + 1] = (float)tq;
   }
 }
 
@@ -92,16 +92,11 @@ extern "C" int b200_instnorm_stats(const void* x, int dtype, int N, int C, long 
                                    float* stats, void* stream) {
   B200_REQUIRE(x && stats, "instnorm_stats: null pointer");
   B200_REQUIRE(N > 0 && C > 0 && S > 0, "instnorm_stats: empty problem");
-  B200_REQUIRE((long long)N * C <= 65535, "instnorm_stats: N*C too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
-  B200_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * C, st));
-  // aim for ~4 waves of blocks over the machine, at least 2048 elements per block
-  long long want = (long long)num_sms() * 8 / ((long long)N * C) + 1;
-  long long chunk = std::max<long long>(2048, (S + want - 1) / want);
-  chunk = (chunk + 255) / 256 * 256;
-  dim3 grid(ceil_div(S, chunk), N * C);
-  if (dtype == B200_DT_F16) instnorm_stats_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, C, S, x_stride_n, chunk, stats);
-  else if (dtype == B200_DT_F32) instnorm_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, C, S, x_stride_n, chunk, stats);
+  const int threads = S >= 32768 ? 1024 : (S >= 4096 ? 256 : 64);
+  dim3 grid(N * C);
+  if (dtype == B200_DT_F16) instnorm_stats_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, C, S, x_stride_n, stats);
+  else if (dtype == B200_DT_F32) instnorm_stats_kernel<float><<<grid, threads, 0, st>>>((const float*)x, C, S, x_stride_n, stats);
   else return set_err(B200_ERR_INVALID, "instnorm_stats: bad dtype");
   B200_LAUNCH_CHECK("instnorm_stats_kernel");
   return B200_OK;
@@ -130,3 +125,42 @@ extern "C" int b200_norm_act(const void* x, int dtype, int N, int C, long long S
   B200_LAUNCH_CHECK("norm_act_kernel");
   return B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// finishing pass of the deterministic statistics (stats.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+// one block per (batch item, N tile) group; blockDim = (2*NT, L): thread (i, l) adds the rows r = l, l+L, ... of column i
+// in increasing r, then the L lane totals are added in increasing l -- a fixed order, in double precision.
+__global__ void stats_finish_kernel(const float* __restrict__ partials, int rows, int nt2, int n_tiles, int NT, int Cout,
+                                    float* __restrict__ stats) {
+  extern __shared__ double s_fin[];   // [L][nt2]
+  const long long g = blockIdx.x;
+  const int i = threadIdx.x, l = threadIdx.y, L = blockDim.y;
+  const float* src = partials + g * (long long)rows * nt2;
+  double acc = 0.0;
+  for (int r = l; r < rows; r += L) acc += (double)src[(long long)r * nt2 + i];
+  s_fin[l * nt2 + i] = acc;
+  __syncthreads();
+  if (l == 0) {
+    double t = 0.0;
+    for (int k = 0; k < L; ++k) t += s_fin[k * nt2 + i];
+    const int n = (int)(g / n_tiles), nt = (int)(g % n_tiles);
+    const int col = nt * NT + i / 2;
+    if (col < Cout) stats[((long long)n * Cout + col) * 2 + (i & 1)] = (float)t;
+  }
+}
+
+int launch_stats_finish(const float* partials, long long groups, int R, int NT, int n_tiles, int Cout, float* stats, cudaStream_t st) {
+  const int nt2 = 2 * NT;
+  B200_REQUIRE(nt2 <= 1024 && groups > 0 && groups < (1LL << 31), "stats_finish: bad sizes");
+  int L = 1024 / nt2;
+  L = L > 8 ? 8 : (L < 1 ? 1 : L);
+  dim3 block(nt2, L);
+  stats_finish_kernel<<<(unsigned)groups, block, (size_t)L * nt2 * sizeof(double), st>>>(partials, R * 4, nt2, n_tiles, NT, Cout, stats);
+  B200_LAUNCH_CHECK("stats_finish_kernel");
+  return B200_OK;
+}
+
+}  // namespace b200

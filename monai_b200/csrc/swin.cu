@@ -4,6 +4,7 @@
 // PatchMerging 701-773, compute_mask 779-816, proj_out 1040-1053), monai/networks/blocks/patchembedding.py:141-219,
 // monai/networks/blocks/dynunet_block.py:247-267.
 #include "common.cuh"
+#include "stats.cuh"
 #include "../../include/monai_b200.h"
 
 namespace b200 {
@@ -440,7 +441,7 @@ template <typename T, int KS, int STRIDE>
 __global__ void __launch_bounds__(128) conv_cin1_nc8_kernel(const T* __restrict__ x, __half* __restrict__ y, const float* __restrict__ wgt,
                                                             const float* __restrict__ bias, int D, int H, int W, int Do, int Ho, int Wo,
                                                             int Cout, int pad, int out_ctot, int out_coff, float* __restrict__ stats) {
-  extern __shared__ __align__(16) float s_w[];  // [taps][Cout], then stats [2*Cout]
+  extern __shared__ __align__(16) float s_w[];  // [taps][Cout], then one warp-private statistics row [2*Cout] per warp
   constexpr int taps = KS * KS * KS;
   constexpr int XW = KS + (kVox - 1) * STRIDE;
   float* s_st = s_w + taps * Cout;
@@ -450,9 +451,10 @@ __global__ void __launch_bounds__(128) conv_cin1_nc8_kernel(const T* __restrict_
     const int t = i % taps, co = i / taps;      // read the [Cout][taps] tensor linearly
     s_w[t * Cout + co] = wgt[i];
   }
-  for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) s_st[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 2 * Cout; i += blockDim.x) s_st[i] = 0.f;
   __syncthreads();
   const int n = blockIdx.y;
+  float* ws = s_st + (threadIdx.x >> 5) * (2 * Cout);
   const int Wq = (Wo + kVox - 1) / kVox;
   const long long So = (long long)Do * Ho * Wo;
   const long long total = (long long)Do * Ho * Wq;
@@ -521,17 +523,18 @@ __global__ void __launch_bounds__(128) conv_cin1_nc8_kernel(const T* __restrict_
         }
         float cs, cq;
         transpose_reduce8(a8, q8, lane, cs, cq);
-        if ((lane & 3) == 0) {
+        if ((lane & 3) == 0) {   // warp-private row, eight distinct columns: no atomics (deterministic, stats.cuh)
           const int col = c0 + transpose_reduce8_col(lane);
-          atomicAdd(&s_st[2 * col], cs);
-          atomicAdd(&s_st[2 * col + 1], cq);
+          ws[2 * col] += cs;
+          ws[2 * col + 1] += cq;
         }
       }
     }
   }
-  if (stats) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) atomicAdd(&stats[(long long)n * Cout * 2 + i], s_st[i]);
+  if (stats) {   // partial rows [n][block][warp][2*Cout]; every block writes its four rows (zeros if it had no work)
+    __syncwarp();
+    float* dst = stats + (((long long)n * gridDim.x + blockIdx.x) * 4 + (threadIdx.x >> 5)) * (2 * Cout);
+    for (int i = lane; i < 2 * Cout; i += 32) dst[i] = ws[i];
   }
 }
 
@@ -719,15 +722,19 @@ extern "C" int b200_window_attention_nc8(const void* qkv, int N, int C, int head
   return B200_OK;
 }
 
-template <typename T>
-static int launch_cin1(const T* x, __half* y, const float* weight, const float* bias, int N, int D, int H, int W, int Do, int Ho, int Wo,
-                       int Cout, int k, int stride, int pad, int out_ctot, int out_coff, float* stats, cudaStream_t st) {
+static dim3 cin1_grid(int N, int Do, int Ho, int Wo) {
   const long long units = (long long)Do * Ho * ((Wo + kVox - 1) / kVox);
   // a few resident waves of blocks per batch item; each block strides over the voxel groups
   const long long per_item = std::max<long long>(1, (long long)num_sms() * 8 / std::max(1, N));
-  dim3 grid((unsigned)std::min<long long>(ceil_div(units, 128), per_item), N);
-  const size_t smem = ((size_t)k * k * k * Cout + 2 * Cout) * sizeof(float);
-#define LCI(KS, SS) conv_cin1_nc8_kernel<T, KS, SS><<<grid, 128, smem, st>>>(x, y, weight, bias, D, H, W, Do, Ho, Wo, Cout, pad, out_ctot, out_coff, stats)
+  return dim3((unsigned)std::min<long long>(ceil_div(units, 128), per_item), N);
+}
+
+template <typename T>
+static int launch_cin1(const T* x, __half* y, const float* weight, const float* bias, int N, int D, int H, int W, int Do, int Ho, int Wo,
+                       int Cout, int k, int stride, int pad, int out_ctot, int out_coff, float* partials, cudaStream_t st) {
+  const dim3 grid = cin1_grid(N, Do, Ho, Wo);
+  const size_t smem = ((size_t)k * k * k * Cout + 4 * 2 * Cout) * sizeof(float);
+#define LCI(KS, SS) conv_cin1_nc8_kernel<T, KS, SS><<<grid, 128, smem, st>>>(x, y, weight, bias, D, H, W, Do, Ho, Wo, Cout, pad, out_ctot, out_coff, partials)
   if (k == 3 && stride == 1) LCI(3, 1);
   else if (k == 2 && stride == 2) LCI(2, 2);
   else if (k == 1 && stride == 1) LCI(1, 1);
@@ -738,22 +745,35 @@ static int launch_cin1(const T* x, __half* y, const float* weight, const float* 
   return B200_OK;
 }
 
+extern "C" long long b200_conv_cin1_nc8_workspace_bytes(int N, int D, int H, int W, int Cout, int k, int stride, int pad) {
+  if (N <= 0 || Cout <= 0 || k < 1 || stride < 1) return -1;
+  const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  if (Do <= 0 || Ho <= 0 || Wo <= 0) return -1;
+  return (long long)N * cin1_grid(N, Do, Ho, Wo).x * 4 * 2 * Cout * (long long)sizeof(float);
+}
+
 extern "C" int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H, int W, const float* weight, const float* bias,
                                   int Cout, int k, int stride, int pad, void* y, int out_ctot, int out_coff, float* stats,
-                                  void* stream) {
+                                  void* workspace, void* stream) {
   B200_REQUIRE(x && y && weight, "conv_cin1_nc8: null pointer");
+  B200_REQUIRE(!stats || workspace, "conv_cin1_nc8: statistics need the workspace of b200_conv_cin1_nc8_workspace_bytes()");
   B200_REQUIRE(k >= 1 && k <= 3 && stride >= 1 && pad >= 0, "conv_cin1_nc8: kernel size must be 1..3");
   B200_REQUIRE(Cout > 0 && Cout % 8 == 0 && out_ctot % 8 == 0 && out_coff % 8 == 0 && out_coff + Cout <= out_ctot,
                "conv_cin1_nc8: channel counts must be multiples of 8");
   const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   B200_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, "conv_cin1_nc8: empty output");
-  B200_REQUIRE(((size_t)k * k * k * Cout + 2 * Cout) * sizeof(float) <= 48 * 1024, "conv_cin1_nc8: Cout too large");
+  B200_REQUIRE(((size_t)k * k * k * Cout + 4 * 2 * Cout) * sizeof(float) <= 48 * 1024, "conv_cin1_nc8: Cout too large");
+  B200_REQUIRE(!stats || 2 * Cout <= 1024, "conv_cin1_nc8: Cout too large for the statistics pass");
   cudaStream_t st = (cudaStream_t)stream;
+  float* part = stats ? (float*)workspace : nullptr;
+  int rc;
   if (dtype == B200_DT_F16)
-    return launch_cin1<__half>((const __half*)x, (__half*)y, weight, bias, N, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, stats, st);
-  if (dtype == B200_DT_F32)
-    return launch_cin1<float>((const float*)x, (__half*)y, weight, bias, N, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, stats, st);
-  return set_err(B200_ERR_INVALID, "conv_cin1_nc8: bad dtype");
+    rc = launch_cin1<__half>((const __half*)x, (__half*)y, weight, bias, N, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, part, st);
+  else if (dtype == B200_DT_F32)
+    rc = launch_cin1<float>((const float*)x, (__half*)y, weight, bias, N, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, part, st);
+  else return set_err(B200_ERR_INVALID, "conv_cin1_nc8: bad dtype");
+  if (rc || !stats) return rc;
+  return launch_stats_finish(part, N, (int)cin1_grid(N, Do, Ho, Wo).x, Cout, 1, Cout, stats, st);
 }
 
 extern "C" int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,

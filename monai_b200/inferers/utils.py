@@ -116,6 +116,12 @@ class _OutputPlan:
         self.vol = tuple(int(i * s) for i, s in zip(image_size, z)) if self.z_scale else tuple(image_size)
         # window starts in output space: int(start * z) exactly as _compute_coords (utils.py:351-360)
         out_starts = [[int(s * zz) for s in ax] for ax, zz in zip(starts, z)]
+        # the blend kernels keep at most 32 covering windows per axis in registers / shared tables (blend.cu): an overlap so
+        # high that more windows cover one voxel along an axis would be truncated silently -- refuse it here instead
+        for ax, r in zip(out_starts, self.roi):
+            cover = max((sum(1 for s in ax if s <= v < s + int(r)) for v in sorted(set(ax))), default=1)
+            if cover > 32:
+                raise ValueError(f"sliding_window_inference: {cover} windows overlap one voxel along an axis; monai_b200 blends at most 32 (lower the overlap)")
         self.starts = [torch.tensor(ax, dtype=torch.int32, device=device) for ax in out_starts]
         self.starts[2]._align = math.gcd(8, *out_starts[2])  # 2 / 8 enable the vectorised blend paths
         self.batch_size = batch_size

@@ -348,9 +348,35 @@ class SwinUNETR(GraphedForward, nn.Module):
     def _plan(self, dims, ws, ss, dev):
         def build():
             src, region, nW, n = window_plan(dims, ws, ss)
-            return (torch.from_numpy(src).to(dev), None if region is None else torch.from_numpy(region).to(dev), nW, n)
+            # schedule of the tcgen05 attention: windows grouped by shift-mask pattern (at most 8 patterns)
+            sched, reps, ntypes = K.window_attention_tc_plan(region, nW, n)
+            tc = None
+            if ntypes <= 8 and n <= 352:
+                tc = (torch.from_numpy(sched).to(dev), None if reps is None else torch.from_numpy(reps).contiguous().to(dev), ntypes)
+            return (torch.from_numpy(src).to(dev), None if region is None else torch.from_numpy(region).to(dev), nW, n, tc)
 
         return self._cache.get(("plan", tuple(dims), tuple(ws), tuple(ss), dev), [], build)
+
+    def _wqkv_scaled(self, attn: WindowAttention, key: str):
+        """qkv projection with scale * log2(e) folded into its q rows (the tcgen05 attention works in log2 units)."""
+        def build():
+            C = attn.dim
+            f = attn.scale * K.LOG2E
+            w = attn.qkv.weight.detach().float().clone()
+            w[:C] *= f
+            b = None
+            if attn.qkv.bias is not None:
+                b = attn.qkv.bias.detach().float().clone()
+                b[:C] *= f
+            return K.gemm_tc_pack_weight(w), b
+
+        params = [attn.qkv.weight] + ([attn.qkv.bias] if attn.qkv.bias is not None else [])
+        return self._cache.get(("qkvs", key, attn.qkv.weight.device), params, build)
+
+    def _attn_bias(self, attn: WindowAttention, key, n: int, tc):
+        _, reps, ntypes = tc
+        return self._cache.get(("attnb", key, n, ntypes, attn.relative_position_bias_table.device), [attn.relative_position_bias_table],
+                               lambda: K.window_attention_tc_pack_bias(attn.relative_position_bias_table, attn.num_heads, n, attn.window_size, reps, ntypes))
 
     # ------------------------------------------------------------------------------------------------- sub-graphs
     def _res_block(self, x: K.NC8, cin: int, in_coff: int, blk: UnetResBlock, key: str, out: K.NC8 | None = None, out_coff: int = 0,
@@ -394,12 +420,18 @@ class SwinUNETR(GraphedForward, nn.Module):
         dev = cur.buf.device
         for bi, blk in enumerate(layer.blocks):
             ws, ss = _get_window_size(dims, blk.window_size, blk.shift_size)
-            src, region, nW, n = self._plan(dims, ws, ss, dev)
+            src, region, nW, n, tc = self._plan(dims, ws, ss, dev)
             bkey = f"{key}.b{bi}"
             xw = K.layernorm_nc8(cur, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, src=src, out_sp=(1, nW, n))
-            qkv, _ = K.gemm_tc(xw, self._wlin(blk.attn.qkv.weight, bkey + ".qkv"), C, 3 * C, bias=blk.attn.qkv.bias)
-            att = K.window_attention_nc8(qkv, C, blk.num_heads, nW, n, blk.attn.scale, blk.attn.relative_position_bias_table, blk.attn.window_size,
-                                         region if any(s > 0 for s in ss) else None)
+            if K.ATTN_TC and tc is not None:
+                # tcgen05 attention: bias + shift mask accumulated by the tensor core, scores in log2 units
+                wq, bq = self._wqkv_scaled(blk.attn, bkey)
+                qkv, _ = K.gemm_tc(xw, wq, C, 3 * C, bias=bq)
+                att = K.window_attention_tc(qkv, C, blk.num_heads, nW, n, self._attn_bias(blk.attn, (bkey, tuple(dims), tuple(ws), tuple(ss)), n, tc), tc[0], tc[2])
+            else:
+                qkv, _ = K.gemm_tc(xw, self._wlin(blk.attn.qkv.weight, bkey + ".qkv"), C, 3 * C, bias=blk.attn.qkv.bias)
+                att = K.window_attention_nc8(qkv, C, blk.num_heads, nW, n, blk.attn.scale, blk.attn.relative_position_bias_table, blk.attn.window_size,
+                                             region if any(s > 0 for s in ss) else None)
             # x = shortcut + window_reverse(proj(att)): scattered back through the same table, residual fused
             x1, _ = K.gemm_tc(att, self._wlin(blk.attn.proj.weight, bkey + ".proj"), C, C, bias=blk.attn.proj.bias, res=cur, row_map=src, out_sp=dims, mode=1)
             y = K.layernorm_nc8(x1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)

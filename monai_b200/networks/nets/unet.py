@@ -128,6 +128,12 @@ class UNet(GraphedForward, nn.Module):
                 return False
             if isinstance(m, nn.PReLU) and m.weight.numel() != 1:
                 return False
+            # every conv block on this path applies InstanceNorm (with the module's eps) and then the activation: a block
+            # without a norm (norm=None), with another ordering or with dropout takes the direct path instead
+            if isinstance(m, Convolution) and m is not self.model[2]:   # model[2]: the top transposed conv (conv only)
+                adn = getattr(m, "adn", None)
+                if adn is None or not isinstance(getattr(adn, "N", None), nn.InstanceNorm3d) or hasattr(adn, "D"):
+                    return False
         return all(isinstance(m, (nn.PReLU, nn.LeakyReLU, nn.ReLU)) for m in self.modules() if type(m).__module__.startswith("torch.nn.modules.activation"))
 
     def _cached(self, key, params, build):
@@ -163,7 +169,7 @@ class UNet(GraphedForward, nn.Module):
         act, slope = self._act_of(conv)
         if out is None:
             out, out_coff = y, 0
-        K.norm_act_nc8(y, cout, st, act=act, slope=slope, out=out, out_coff=out_coff)
+        K.norm_act_nc8(y, cout, st, act=act, slope=slope, out=out, out_coff=out_coff, eps=float(conv.adn.N.eps))
         return out
 
     def _tc_level(self, block: nn.Sequential, x, cin: int, raw, top: bool, out, out_coff: int, out_dtype):

@@ -200,10 +200,13 @@ class Spacingd(MapTransform):
         for i, key in enumerate(self.key_iterator(d)):
             idx = self.keys.index(key)
             if self.ensure_same_shape and is_meta(d[key]):
+                # the reference reuses the first key's output shape only for keys with the same input shape AND the same
+                # affine-derived spacing (monai/transforms/spatial/dictionary.py:500-512)
+                pix_k = U.affine_to_spacing(np.asarray(get_affine(d[key]), dtype=np.float64), len(d[key].shape) - 1)
                 if _init_shape is None:
-                    _init_shape, _pixdim = tuple(d[key].shape[1:]), d[key].meta.get("pixdim") if hasattr(d[key], "meta") else None
+                    _init_shape, _pixdim = tuple(d[key].shape[1:]), pix_k
                 else:
-                    should_match = tuple(d[key].shape[1:]) == _init_shape
+                    should_match = tuple(d[key].shape[1:]) == _init_shape and bool(np.allclose(_pixdim, pix_k, atol=1e-3))
             d[key] = self.spacing_transform(
                 d[key], mode=self.mode[idx], padding_mode=self.padding_mode[idx], align_corners=self.align_corners[idx], dtype=self.dtype[idx],
                 scale_extent=self.scale_extent[idx], output_spatial_shape=output_shape_k if should_match else None,

@@ -190,7 +190,7 @@ def swin_transformer_forward(sd, x, heads=(3, 6, 12, 24), window=(7, 7, 7), dept
         ws = [window[i] if (d, h, w)[i] > window[i] else (d, h, w)[i] for i in range(3)]
         ss = [shift[i] if (d, h, w)[i] > window[i] else 0 for i in range(3)]
         dims = [-(-d // ws[0]) * ws[0], -(-h // ws[1]) * ws[1], -(-w // ws[2]) * ws[2]]
-        mask = _compute_mask(dims, ws, ss) if any(s > 0 for s in ss) else None
+        mask = _compute_mask(dims, ws, ss).to(device=t.device, dtype=t.dtype) if any(s > 0 for s in ss) else None
         for bi in range(depths[li]):
             t = _swin_block(t, sd, f"{lp}.blocks.{bi}", heads[li], window, (0, 0, 0) if bi % 2 == 0 else shift, mask)
         t = _patch_merging(t, sd, lp + ".downsample")

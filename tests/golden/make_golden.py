@@ -148,6 +148,25 @@ def nets():
              h4=hs[4].numpy()[:, ::8], y_mean=np.array(float(y.double().mean())), y_absmean=np.array(float(y.double().abs().mean())))
 
 
+def nets_r2():
+    """Round-2 additions: the 96^3 window every C3 / C5 window has, and the SwinUNETR variants of the reference's
+    constructor surface (default feature_size=24, multi-channel input, use_v2)."""
+    def dump(tag, net, x):
+        with torch.no_grad():
+            hs = net.swinViT(x, True)
+            y = net(x)
+        save(f"swin_unetr_{tag}.npz", x=x.numpy().astype(np.float16), y_sub=y.numpy()[..., ::4, ::4, ::4],
+             h0_sub=hs[0].numpy()[..., ::4, ::4, ::4], h4=hs[4].numpy()[:, ::8],
+             y_mean=np.array(float(y.double().mean())), y_absmean=np.array(float(y.double().abs().mean())))
+
+    net = _load_named(SwinUNETR(in_channels=1, out_channels=2, feature_size=48), 4)
+    dump("fs48_96", net, torch.randn(1, 1, 96, 96, 96, generator=torch.Generator().manual_seed(17)).half().float())
+    net = _load_named(SwinUNETR(in_channels=1, out_channels=2, feature_size=24), 5)
+    dump("fs24_64", net, torch.randn(1, 1, 64, 64, 64, generator=torch.Generator().manual_seed(18)).half().float())
+    net = _load_named(SwinUNETR(in_channels=4, out_channels=3, feature_size=48, use_v2=True), 6)
+    dump("fs48_in4_v2_64", net, torch.randn(1, 4, 64, 64, 64, generator=torch.Generator().manual_seed(19)).half().float())
+
+
 def transforms():
     from monai.data import MetaTensor
     from monai.transforms import GaussianSmooth, RandAffined, Spacing, Spacingd
@@ -326,6 +345,6 @@ def unit_goldens():
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "transforms", "post", "patch", "unit_goldens"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

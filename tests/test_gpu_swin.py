@@ -121,15 +121,94 @@ def test_window_attention_matches_reference_math(ws, n, nW, heads):
         assert _rel(got.numpy(), ref.numpy()) < 4e-3, (n, reg is None)
 
 
-def test_cin1_stem_and_head():
+@pytest.mark.parametrize("ws,n,nW,heads", [((7, 7, 7), 343, 5, 3), ((7, 7, 7), 216, 3, 6), ((7, 7, 7), 8, 4, 24), ((7, 7, 7), 196, 9, 12)])
+def test_window_attention_tcgen05_matches_reference_math(ws, n, nW, heads):
+    """b200_window_attention_tc: bias + shift mask added by the tensor core, softmax from TMEM, P V on tcgen05."""
+    from monai_b200.networks.nets.swin_unetr import WindowAttention
+
+    g = torch.Generator().manual_seed(5)
+    C, B = heads * 16, 3
+    mod = WindowAttention(C, heads, ws, qkv_bias=True)
+    table = torch.randn(mod.relative_position_bias_table.shape, generator=g)
+    qkv = torch.randn((B, nW, n, 3 * C), generator=g).half()
+    bias = table[mod.relative_position_index[:n, :n].reshape(-1)].reshape(n, n, heads).permute(2, 0, 1)
+    # at most 8 distinct mask patterns (as the shift mask has): windows draw their region row from 3 prototypes
+    protos = torch.randint(0, 3, (3, n), generator=g, dtype=torch.int32)
+    region = protos[torch.arange(nW) % 3]
+    q, k, v = qkv.float().reshape(B, nW, n, 3, heads, 16).permute(3, 0, 1, 4, 2, 5)
+    attn = (q * 0.25) @ k.transpose(-2, -1) + bias[None, None]
+    mask = torch.where(region[:, None, :] != region[:, :, None], -100.0, 0.0)
+    # the kernel works in log2 units: q rows pre-scaled by scale * log2(e) (done in the qkv projection in the network)
+    qs = qkv.clone().float()
+    qs[..., :C] *= 0.25 * K.LOG2E
+    x = K.pack_nc8(qs.half().permute(0, 3, 1, 2).reshape(B, 3 * C, 1, nW, n).contiguous().to(DEV))
+    for reg, a in ((region, attn + mask[None, :, None]), (None, attn)):
+        ref = (a.softmax(-1) @ v).permute(0, 1, 3, 2, 4).reshape(B, nW, n, C)
+        sched, reps, ntypes = K.window_attention_tc_plan(None if reg is None else reg.numpy(), nW, n)
+        assert ntypes <= 8
+        pb = K.window_attention_tc_pack_bias(table.to(DEV), heads, n, ws, None if reps is None else torch.from_numpy(reps).to(DEV), ntypes)
+        out = K.window_attention_tc(x, C, heads, nW, n, pb, torch.from_numpy(sched).to(DEV), ntypes)
+        torch.cuda.synchronize()
+        got = K.unpack_nc8(out, dtype=torch.float32).cpu().reshape(B, C, nW, n).permute(0, 2, 3, 1)
+        err = _rel(got.numpy(), ref.numpy())
+        assert err < 4e-3, (n, reg is None, err)
+
+
+def test_instance_norm_statistics_are_deterministic():
+    """The epilogue statistics never go through floating-point atomics: two runs give the same bits, and the values agree
+    with a float64 reference (conv3x3x3_tc, gemm_tc with a 1x1x1 conv, the single-channel stems)."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((3, 32, 10, 20, 24), generator=g).half()
+    w = (torch.randn((48, 32, 3, 3, 3), generator=g) / 30).half()
+    xn, wp = _to_nc8(x), K.conv3x3x3_tc_pack_weight(w.float().to(DEV))
+    runs = [K.conv3x3x3_tc(xn, wp, 32, 48, want_stats=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    ref = F.conv3d(x.double(), w.double(), padding=1)
+    for y, st in runs[1:]:
+        assert torch.equal(st, runs[0][1]) and torch.equal(y.buf, runs[0][0].buf)
+    st = runs[0][1].cpu().double().reshape(3, 48, 2)
+    torch.testing.assert_close(st[..., 0], ref.sum(dim=(2, 3, 4)), rtol=2e-3, atol=5e-2)
+    torch.testing.assert_close(st[..., 1], (ref * ref).sum(dim=(2, 3, 4)), rtol=2e-3, atol=5e-2)
+    w1 = (torch.randn((48, 32, 1, 1, 1), generator=g) / 6).half()
+    wl = K.gemm_tc_pack_weight(w1.reshape(48, 32).to(DEV))
+    r1 = [K.gemm_tc(xn, wl, 32, 48, want_stats=True)[1] for _ in range(3)]
+    assert torch.equal(r1[0], r1[1]) and torch.equal(r1[0], r1[2])
+    ref1 = F.conv3d(x.double(), w1.double())
+    torch.testing.assert_close(r1[0].cpu().double().reshape(3, 48, 2)[..., 1], (ref1 * ref1).sum(dim=(2, 3, 4)), rtol=2e-3, atol=5e-2)
+    u = torch.randn((3, 1, 12, 20, 24), generator=g).half().to(DEV)
+    wc = torch.randn((48, 1, 3, 3, 3), generator=g).to(DEV) / 5
+    for force in (False, True):
+        K._FORCE_CUDA_CORE_STEM = force
+        try:
+            rs = [K.conv_cin1_nc8(u, wc, None, 3, 1, 1, want_stats=True)[1] for _ in range(3)]
+        finally:
+            K._FORCE_CUDA_CORE_STEM = False
+        assert torch.equal(rs[0], rs[1]) and torch.equal(rs[0], rs[2])
+        refc = F.conv3d(u.double().cpu(), wc.double().cpu(), padding=1)
+        torch.testing.assert_close(rs[0].cpu().double().reshape(3, 48, 2)[..., 1], (refc * refc).sum(dim=(2, 3, 4)), rtol=3e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize("force_cuda_core", [False, True])
+def test_cin1_stem_and_head(force_cuda_core):
     g = torch.Generator().manual_seed(4)
     x = torch.randn((2, 1, 8, 10, 12), generator=g)
-    for k, s, p in [(3, 1, 1), (2, 2, 0), (1, 1, 0)]:
-        w, b = torch.randn((48, 1, k, k, k), generator=g) / k**1.5, torch.randn(48, generator=g)
-        ref = F.conv3d(x, w, b, stride=s, padding=p)
-        y, st = K.conv_cin1_nc8(x.to(DEV), w.to(DEV), b.to(DEV), k, s, p, want_stats=True)
-        assert _rel(K.unpack_nc8(y, dtype=torch.float32).cpu().numpy(), ref.numpy()) < 2e-3
-        torch.testing.assert_close(st[:, 0].cpu(), ref.sum(dim=(2, 3, 4)).reshape(-1), rtol=1e-3, atol=1e-2)
+    K._FORCE_CUDA_CORE_STEM = force_cuda_core   # False: tcgen05 stems for (3,1,1) and (2,2,0); True: CUDA-core kernel for all
+    try:
+        for k, s, p in [(3, 1, 1), (2, 2, 0), (1, 1, 0)]:
+            w, b = torch.randn((48, 1, k, k, k), generator=g) / k**1.5, torch.randn(48, generator=g)
+            ref = F.conv3d(x, w, b, stride=s, padding=p)
+            for xin in (x, x.half()):
+                y, st = K.conv_cin1_nc8(xin.to(DEV), w.to(DEV), b.to(DEV), k, s, p, want_stats=True)
+                assert _rel(K.unpack_nc8(y, dtype=torch.float32).cpu().numpy(), ref.numpy()) < 3e-3, (k, s, p, xin.dtype)
+                torch.testing.assert_close(st[:, 0].cpu(), ref.sum(dim=(2, 3, 4)).reshape(-1), rtol=2e-3, atol=3e-2)
+        # a volume that needs several tiles per axis and a partial last tile on every axis
+        xb = torch.randn((2, 1, 21, 37, 19), generator=g).half()
+        wb = torch.randn((32, 1, 3, 3, 3), generator=g) / 5
+        refb = F.conv3d(xb.float(), wb, padding=1)
+        yb, _ = K.conv_cin1_nc8(xb.to(DEV), wb.to(DEV), None, 3, 1, 1)
+        assert _rel(K.unpack_nc8(yb, dtype=torch.float32).cpu().numpy(), refb.numpy()) < 3e-3
+    finally:
+        K._FORCE_CUDA_CORE_STEM = False
     h = torch.randn((2, 48, 4, 5, 6), generator=g).half()
     w, b = torch.randn((2, 48, 1, 1, 1), generator=g) / 7, torch.randn(2, generator=g)
     ref = F.conv3d(h.float(), w, b)

@@ -60,7 +60,7 @@ def test_abi_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"symbols declared in include/monai_b200.h but not exported: {missing}"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
-    assert _lib.load().b200_abi_version() == 1
+    assert _lib.load().b200_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header_sizes():
