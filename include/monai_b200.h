@@ -53,6 +53,19 @@ typedef struct b200_blend_desc {
   const float* acc;         /* mode 2: fp32 accumulators */
   int box[4];               /* rows to visit: d in [box0,box1), h in [box2,box3); all-zero = whole volume */
   int starts_w_align;       /* host hint: a common divisor of every starts_w entry (2 -> 2 voxels/thread, 8 -> 8 voxels/thread; 1 or 0 = unknown) */
+  int max_cover;            /* host hint: most windows covering one voxel along any single axis (0 = unknown; <= 3 enables the lean kernel) */
+  const int32_t* slot_map;  /* mode 1, optional device array [B * n_windows]: flat window id -> slot of its prediction in `preds`
+                               (-1 = not resident).  For callers that visit windows in another order than their ids (the buffered
+                               mode of monai/inferers/utils.py:182-191, 239-253); win_begin / win_end are then ignored. */
+  int n_slots;              /* resident predictions when slot_map is given */
+  const double* resample;   /* optional HOST pointer to a 3x4 row-major matrix M: OUTPUT voxel index (d,h,w,1) -> coordinate in the
+                               blended volume.  Non-null selects the FUSED blend + affine resample (modes 0 and 2): out is then
+                               [B,C,out_D,out_H,out_W] = trilinear / nearest sample of the blended volume, which is never stored
+                               (inferers/utils.py:286-298 composed with transforms/spatial/functional.py:68-184, e.g. the inverse of
+                               Spacingd applied to the logits).  An identity M gives the bits of the plain blend. */
+  int out_D, out_H, out_W;  /* output grid of the fused resample */
+  int resample_interp;      /* 0 nearest (round half to even), 1 trilinear */
+  int resample_pad;         /* 0 zeros, 1 border */
 } b200_blend_desc;
 
 /* replaces monai/inferers/utils.py:264-275, 286-288, 297-298, 351-360.

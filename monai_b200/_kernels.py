@@ -242,7 +242,11 @@ def sw_blend(
     out: torch.Tensor,
     acc: torch.Tensor | None = None,
     box: Sequence[int] = (0, 0, 0, 0),
+    slot_map: torch.Tensor | None = None,
+    n_slots: int = 0,
+    resample: "tuple | None" = None,
 ) -> None:
+    """`resample` = (mat12, (oD, oH, oW), interp, pad) selects the fused blend + affine resample (see include/monai_b200.h)."""
     d = L.BlendDesc()
     B, Cc, D, H, W = vol_shape
     if preds is not None:
@@ -266,6 +270,15 @@ def sw_blend(
     for i in range(4):
         d.box[i] = box[i]
     d.starts_w_align = int(getattr(starts[2], "_align", 1))
+    d.max_cover = int(getattr(starts[2], "_max_cover", 0))
+    d.slot_map, d.n_slots = L.ptr(slot_map), int(n_slots)
+    keep = None
+    if resample is not None:
+        mat, oshape, interp, pad = resample
+        keep = (C.c_double * 12)(*[float(v) for v in mat])
+        d.resample = C.cast(keep, C.POINTER(C.c_double))
+        d.out_D, d.out_H, d.out_W = (int(v) for v in oshape)
+        d.resample_interp, d.resample_pad = int(interp), int(pad)
     nb = _nb(preds) + (_nb(out) if mode == 0 else 0.0) + (2.0 * _nb(out) if mode == 1 else 0.0) + (_nb(out, acc) if mode == 2 else 0.0)
     _call("sw_blend", C.byref(d), mode, L.stream_ptr(out.device), nbytes=nb)
 

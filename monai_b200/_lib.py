@@ -32,6 +32,8 @@ class BlendDesc(C.Structure):
         ("starts_d", vp), ("nd", i32), ("starts_h", vp), ("nh", i32), ("starts_w", vp), ("nw", i32),
         ("gd", vp), ("gh", vp), ("gw", vp), ("clamp_min", f32), ("wmap", vp),
         ("out", vp), ("out_dtype", i32), ("acc", vp), ("box", i32 * 4), ("starts_w_align", i32),
+        ("max_cover", i32), ("slot_map", vp), ("n_slots", i32), ("resample", C.POINTER(C.c_double)),
+        ("out_D", i32), ("out_H", i32), ("out_W", i32), ("resample_interp", i32), ("resample_pad", i32),
     ]
 
 

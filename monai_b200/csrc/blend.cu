@@ -10,37 +10,11 @@
 // vectors of compute_importance_map (monai/data/utils.py:1084-1134): ((g_d*g_h)*g_w) clamped from below.
 #include "common.cuh"
 #include "tc05.cuh"
+#include "blend.cuh"
 #include <cstdlib>
 #include "../../include/monai_b200.h"
 
 namespace b200 {
-
-struct BlendParams {
-  const void* preds;          // windows [win_begin, win_end) resident, element strides below
-  long long ps_n, ps_c, ps_d, ps_h, ps_w;
-  int win_begin, win_end;     // flat window indices (batch-major, then d,h,w "ij" order)
-  int B, C, D, H, W;          // blended volume (already padded to >= roi)
-  int rd, rh, rw;             // roi
-  const int* starts_d; int nd;
-  const int* starts_h; int nh;
-  const int* starts_w; int nw;
-  const float* gd; const float* gh; const float* gw;   // 1-D importance factors
-  float clamp_min;
-  const float* wmap;          // optional dense roi weight map [rd,rh,rw] (overrides gd/gh/gw)
-  void* out;                  // MODE 0: final [B,C,D,H,W] (out dtype); MODE 1: fp32 accumulators (+=)
-  const float* acc;           // MODE 2: fp32 accumulators to normalise
-  int d0, d1, h0, h1;         // box of output rows to visit (d in [d0,d1), h in [h0,h1))
-  int offsets_fit_i32;        // one (d) layer of windows spans < 2^31 prediction elements (8-voxel pipelined path)
-};
-
-constexpr int kMaxStarts = 512;
-
-// numerator update.  fp32 predictions: separate multiply and add, the reference's operation order, so results are
-// bit-identical to it.  fp16 predictions (where the reference itself accumulates in fp16 and parity is a tolerance): one
-// fused multiply-add in fp32 -- fewer instructions and one rounding less.
-template <typename TP> __device__ __forceinline__ float blend_acc(float acc, float x, float w);
-template <> __device__ __forceinline__ float blend_acc<float>(float acc, float x, float w) { return __fadd_rn(acc, __fmul_rn(x, w)); }
-template <> __device__ __forceinline__ float blend_acc<__half>(float acc, float x, float w) { return fmaf(x, w, acc); }
 
 // MODE 0: all windows resident -> write normalised result.  MODE 1: accumulate numerators (+=) for the
 // resident window range.  MODE 2: divide accumulators by the analytic count (all windows).
@@ -119,13 +93,22 @@ __global__ void __launch_bounds__(128) sw_blend_kernel(BlendParams p) {
         for (int k0 = 0; k0 < nwc; k0 += 4) {
           float wt[4][VEC], v0[4][VEC], v1[4][VEC];
           bool res[4];
+          int slotq[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int iw = iw_lo + k0 + q;
             const bool in = k0 + q < nwc;
             const int lw = in ? w - s_w[iw] : 0;
             const int widx = wbase + iw;
-            res[q] = in && (MODE != 2) && widx >= p.win_begin && widx < p.win_end;
+            // resident slot of this window: contiguous range [win_begin, win_end) or, with a slot map (buffered mode: the
+            // windows are visited in another order than their ids), wherever the map says
+            int slot = -1;
+            if (in && MODE != 2) {
+              if (p.slot_map) slot = __ldg(p.slot_map + widx);
+              else if (widx >= p.win_begin && widx < p.win_end) slot = widx - p.win_begin;
+            }
+            slotq[q] = slot;
+            res[q] = slot >= 0;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
               float t = 0.f;
@@ -133,7 +116,7 @@ __global__ void __launch_bounds__(128) sw_blend_kernel(BlendParams p) {
               wt[q][v] = t; v0[q][v] = 0.f; v1[q][v] = 0.f;
             }
             if (res[q]) {
-              const TP* pp = preds + (long long)(widx - p.win_begin) * p.ps_n + rowoff + (long long)lw * p.ps_w;
+              const TP* pp = preds + (long long)slotq[q] * p.ps_n + rowoff + (long long)lw * p.ps_w;
               PredVec<TP, VEC>::ld(pp, v0[q]);
               if (two) PredVec<TP, VEC>::ld(pp + p.ps_c, v1[q]);
             }
@@ -157,8 +140,9 @@ __global__ void __launch_bounds__(128) sw_blend_kernel(BlendParams p) {
     for (int v = 0; v < VEC; ++v) {
       const long long o0 = ((long long)b * p.C + c0) * vol + voff + v;
       if (MODE == 0) {
-        io<TO>::st((TO*)p.out + o0, __fdiv_rn(acc0[v], cnt[v]));
-        if (two) io<TO>::st((TO*)p.out + o0 + vol, __fdiv_rn(acc1[v], cnt[v]));
+        const float cf = BlendFin<TO>::prep(cnt[v]);
+        io<TO>::st((TO*)p.out + o0, BlendFin<TO>::apply(acc0[v], cf));
+        if (two) io<TO>::st((TO*)p.out + o0 + vol, BlendFin<TO>::apply(acc1[v], cf));
       } else {
         *((float*)p.out + o0) = acc0[v];
         if (two) *((float*)p.out + o0 + vol) = acc1[v];
@@ -169,7 +153,7 @@ __global__ void __launch_bounds__(128) sw_blend_kernel(BlendParams p) {
     for (int c = 0; c < p.C; ++c) {
       const long long o = ((long long)b * p.C + c) * vol + voff;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) io<TO>::st((TO*)p.out + o + v, __fdiv_rn(p.acc[o + v], cnt[v]));
+      for (int v = 0; v < VEC; ++v) io<TO>::st((TO*)p.out + o + v, BlendFin<TO>::apply(p.acc[o + v], BlendFin<TO>::prep(cnt[v])));
     }
   }
 }
@@ -397,7 +381,7 @@ __global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_
     const long long o0 = ((long long)b * p.C + c0) * vol + voff;
     if (MODE == 0) {
 #pragma unroll
-      for (int v = 0; v < 8; ++v) { a0[v] = __fdiv_rn(a0[v], cnt[v]); a1[v] = __fdiv_rn(a1[v], cnt[v]); }
+      for (int v = 0; v < 8; ++v) { const float cf = BlendFin<TO>::prep(cnt[v]); a0[v] = BlendFin<TO>::apply(a0[v], cf); a1[v] = BlendFin<TO>::apply(a1[v], cf); }
       st8o<TO>((TO*)p.out + o0, a0);
       if (two) st8o<TO>((TO*)p.out + o0 + vol, a1);
     } else {
@@ -411,7 +395,7 @@ __global__ void __launch_bounds__(32 * kBlend8Rows, sizeof(TP) == 2 ? 2 : 1) sw_
       float xv[8];
       ld8f(p.acc + o, xv);
 #pragma unroll
-      for (int v = 0; v < 8; ++v) xv[v] = __fdiv_rn(xv[v], cnt[v]);
+      for (int v = 0; v < 8; ++v) xv[v] = BlendFin<TO>::apply(xv[v], BlendFin<TO>::prep(cnt[v]));
       st8o<TO>((TO*)p.out + o, xv);
     }
   }
@@ -556,7 +540,7 @@ __global__ void __launch_bounds__(160) sw_blend_tma_kernel(const __grid_constant
       if (MODE == 0) {
         float r[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) r[v] = __fdiv_rn(acc[c][v], cnt[v]);
+        for (int v = 0; v < 4; ++v) r[v] = BlendFin<TO>::apply(acc[c][v], BlendFin<TO>::prep(cnt[v]));
         if (sizeof(TO) == 2) {
           uint2 o2;
           *reinterpret_cast<__half2*>(&o2.x) = __floats2half2_rn(r[0], r[1]);
@@ -585,6 +569,11 @@ __global__ void __launch_bounds__(256) sw_gather_kernel(const TI* __restrict__ v
   for (int lw = blockIdx.x * blockDim.x + threadIdx.x; lw < rw; lw += gridDim.x * blockDim.x)
     io<TO>::st(dst + lw, io<TI>::ld(src + lw));
 }
+
+// blend_fused.cu
+int launch_blend8_lean(const BlendParams& p, int out_dtype, cudaStream_t st);
+int launch_blend_resample(const BlendParams& p, const double* m, int oD, int oH, int oW, int interp, int pad, int mode, int pred_dtype,
+                          int out_dtype, cudaStream_t st);
 
 }  // namespace b200
 
@@ -690,11 +679,16 @@ extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream)
   p.gd = dsc->gd; p.gh = dsc->gh; p.gw = dsc->gw; p.clamp_min = dsc->clamp_min; p.wmap = dsc->wmap;
   p.out = dsc->out; p.acc = dsc->acc;
   p.d0 = dsc->box[0]; p.d1 = dsc->box[1]; p.h0 = dsc->box[2]; p.h1 = dsc->box[3];
+  p.slot_map = dsc->slot_map; p.n_slots = dsc->n_slots;
+  B200_REQUIRE(!p.slot_map || mode == 1, "sw_blend: a slot map goes with mode 1 (accumulate)");
   p.offsets_fit_i32 = mode == 2 || ((long long)(p.nh + 1) * p.nw * p.ps_n + (long long)p.rh * p.ps_h + p.rw < (1LL << 31));
   if (p.d1 <= 0) { p.d0 = 0; p.d1 = p.D; }
   if (p.h1 <= 0) { p.h0 = 0; p.h1 = p.H; }
   B200_REQUIRE(p.d0 >= 0 && p.d1 <= p.D && p.h0 >= 0 && p.h1 <= p.H, "sw_blend: box outside the volume");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dsc->resample)   // fused blend + affine resample: the blended volume is never materialised
+    return launch_blend_resample(p, dsc->resample, dsc->out_D, dsc->out_H, dsc->out_W, dsc->resample_interp, dsc->resample_pad, mode,
+                                 dsc->pred_dtype, dsc->out_dtype, st);
   // two voxels per thread when every window start, the roi and W are even and predictions are contiguous along W
   bool vec2 = (p.W % 2 == 0) && (p.rw % 2 == 0) && (mode == 2 || p.ps_w == 1) && dsc->starts_w_align >= 2 && dsc->starts_w_align % 2 == 0;
   if (vec2 && mode != 2) {
@@ -707,10 +701,17 @@ extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream)
               (p.wmap ? reinterpret_cast<uintptr_t>(p.wmap) % 16 == 0 : reinterpret_cast<uintptr_t>(p.gw) % 16 == 0);
   if (vec8 && mode != 2)
     vec8 = (reinterpret_cast<uintptr_t>(p.preds) % 16 == 0) && p.ps_n % 8 == 0 && p.ps_c % 8 == 0 && p.ps_d % 8 == 0 && p.ps_h % 8 == 0;
+  if (p.slot_map) vec8 = false;   // only the general kernel looks windows up through a slot map
+  // lean 8-voxel kernel: everything resident, fp16 predictions, separable weights, at most three covering windows per axis
+  static int no_lean = -1;
+  if (no_lean < 0) { const char* e = getenv("B200_BLEND_NO_LEAN"); no_lean = (e && e[0] == '1') ? 1 : 0; }
+  if (!no_lean && mode == 0 && vec8 && dsc->pred_dtype == B200_DT_F16 && !p.wmap && dsc->max_cover >= 1 && dsc->max_cover <= 3 && p.rw <= 512 &&
+      p.win_begin == 0 && p.win_end == p.B * p.nd * p.nh * p.nw)
+    return launch_blend8_lean(p, dsc->out_dtype, st);
   // TMA-staged kernel: fp16 predictions, contiguous window rows, 16-byte aligned strides, separable importance factors
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("B200_BLEND_TMA"); use_tma = (e && e[0] == '1') ? 1 : 0; }   // opt-in until validated on the GPU
-  const bool tma_ok = use_tma && mode != 2 && dsc->pred_dtype == B200_DT_F16 && !p.wmap && p.ps_w == 1 && p.C <= kTmaMaxC && p.W % 4 == 0 &&
+  const bool tma_ok = use_tma && !p.slot_map && mode != 2 && dsc->pred_dtype == B200_DT_F16 && !p.wmap && p.ps_w == 1 && p.C <= kTmaMaxC && p.W % 4 == 0 &&
                       p.rw % 8 == 0 && p.rh <= kTmaMaxRoi && p.rw <= kTmaMaxRoi && p.rh >= kTmaTH && p.rw >= kTmaTW && p.ps_h % 8 == 0 && p.ps_d % 8 == 0 && p.ps_c % 8 == 0 &&
                       p.ps_n % 8 == 0 && reinterpret_cast<uintptr_t>(p.preds) % 16 == 0 && reinterpret_cast<uintptr_t>(p.out) % 16 == 0 &&
                       p.win_end > p.win_begin && (long long)p.ps_h * 2 < (1LL << 40);

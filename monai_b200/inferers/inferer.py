@@ -120,18 +120,52 @@ class SlidingWindowInferer(Inferer):
 
 
 class SlidingWindowInfererAdapt(SlidingWindowInferer):
-    """Same call contract as the reference class; retries with the result on the host after a CUDA OOM."""
+    """The reference's adaptive policy (monai/inferers/inferer.py:555-641) with the same call contract: stitch on the GPU; after a
+    CUDA out-of-memory error switch to buffered stitching (halving `buffer_steps` on further failures) and finally to a result
+    held in host memory; `cpu_thresh` remembers the size from which GPU stitching is not attempted again.  With an explicit
+    stitching `device` no adaptation takes place.  The buffer axis is the longest one when it is at least twice the last axis."""
 
     def __call__(self, inputs: torch.Tensor, network: Callable, *args: Any, **kwargs: Any):
-        if self.device is not None or "device" in kwargs:
+        if self.device is not None:
             return super().__call__(inputs, network, *args, **kwargs)
-        try:
-            return super().__call__(inputs, network, *args, **kwargs)
-        except torch.cuda.OutOfMemoryError:
-            torch.cuda.empty_cache()
-            self.cpu_thresh = inputs.shape[2:].numel() - 1 if self.cpu_thresh is None else min(self.cpu_thresh, inputs.shape[2:].numel() - 1)
-            warnings.warn("CUDA OOM during sliding-window inference; retrying with the stitched output on the host.")
-            return super().__call__(inputs, network, *args, device="cpu", **kwargs)
+        skip_buffer = self.buffer_steps is not None and self.buffer_steps <= 0
+        cpu_cond = self.cpu_thresh is not None and inputs.shape[2:].numel() > self.cpu_thresh
+        gpu_stitching = inputs.is_cuda and not cpu_cond
+        buffered_stitching = inputs.is_cuda and cpu_cond and not skip_buffer
+        buffer_steps = max(1, self.buffer_steps) if self.buffer_steps is not None else 1
+        buffer_dim = -1
+        sh = list(inputs.shape[2:])
+        max_dim = sh.index(max(sh))
+        if inputs.shape[max_dim + 2] / inputs.shape[-1] >= 2:
+            buffer_dim = max_dim
+        for _ in range(10):  # at most 10 trials
+            try:
+                return super().__call__(
+                    inputs, network, *args, device=inputs.device if gpu_stitching else torch.device("cpu"),
+                    buffer_steps=buffer_steps if buffered_stitching else None, buffer_dim=buffer_dim, **kwargs,
+                )
+            except RuntimeError as e:
+                if (not gpu_stitching and not buffered_stitching) or "OutOfMemoryError" not in type(e).__name__:
+                    raise
+                torch.cuda.empty_cache()
+                if gpu_stitching:  # GPU stitching failed: remember the size, go buffered (or straight to the host)
+                    gpu_stitching = False
+                    self.cpu_thresh = inputs.shape[2:].numel() - 1
+                    if skip_buffer:
+                        buffered_stitching = False
+                        warnings.warn(f"GPU stitching failed, attempting on CPU, image dim {tuple(inputs.shape)}.")
+                    else:
+                        buffered_stitching = True
+                        self.buffer_steps = buffer_steps
+                        warnings.warn(f"GPU stitching failed, buffer {buffer_steps} dim {buffer_dim}, image dim {tuple(inputs.shape)}.")
+                elif buffer_steps > 1:
+                    buffer_steps = max(1, buffer_steps // 2)
+                    self.buffer_steps = buffer_steps
+                    warnings.warn(f"GPU buffered stitching failed, image dim {tuple(inputs.shape)} reducing buffer to {buffer_steps}.")
+                else:
+                    buffered_stitching = False
+                    warnings.warn(f"GPU buffered stitching failed, attempting on CPU, image dim {tuple(inputs.shape)}.")
+        raise RuntimeError(f"SlidingWindowInfererAdapt {skip_buffer} {cpu_cond} {gpu_stitching} {buffered_stitching} {buffer_steps}")
 
 
 class SliceInferer(SlidingWindowInferer):

@@ -24,11 +24,21 @@ from .. import _kernels as K
 from .. import _lib as L
 from ..data.utils import compute_importance_map, dense_patch_starts, get_valid_patch_size, importance_factors
 
-__all__ = ["sliding_window_inference"]
+__all__ = ["sliding_window_inference", "sliding_window_inference_resampled", "resample_matrix"]
 
 # keep at most this many bytes of window predictions resident before they are folded into the accumulators;
 # when everything fits, the whole blend is ONE launch (mode 0) and the fp32 accumulators are never allocated.
 _RESIDENT_BYTES = 24 << 30
+
+
+def _resident_budget(device) -> int:
+    """Bytes of window predictions kept resident: at most _RESIDENT_BYTES and at most 40 % of the memory currently free on `device`
+    (the fp32 accumulators and the network's activations need the rest)."""
+    try:
+        free, _ = torch.cuda.mem_get_info(device)
+        return int(max(1, min(_RESIDENT_BYTES, 0.4 * free)))
+    except Exception:  # pragma: no cover - no CUDA context yet
+        return _RESIDENT_BYTES
 
 _PAD_MODES = {"constant", "reflect", "replicate", "circular"}
 
@@ -118,21 +128,25 @@ class _OutputPlan:
         out_starts = [[int(s * zz) for s in ax] for ax, zz in zip(starts, z)]
         # the blend kernels keep at most 32 covering windows per axis in registers / shared tables (blend.cu): an overlap so
         # high that more windows cover one voxel along an axis would be truncated silently -- refuse it here instead
+        max_cover = 1
         for ax, r in zip(out_starts, self.roi):
             cover = max((sum(1 for s in ax if s <= v < s + int(r)) for v in sorted(set(ax))), default=1)
             if cover > 32:
                 raise ValueError(f"sliding_window_inference: {cover} windows overlap one voxel along an axis; monai_b200 blends at most 32 (lower the overlap)")
+            max_cover = max(max_cover, cover)
         self.starts = [torch.tensor(ax, dtype=torch.int32, device=device) for ax in out_starts]
         self.starts[2]._align = math.gcd(8, *out_starts[2])  # 2 / 8 enable the vectorised blend paths
+        self.starts[2]._max_cover = max_cover                # <= 3 enables the lean kernel
         self.batch_size = batch_size
         self.total = total
         per_win = self.chns * int(np.prod(seg_shape))
-        self.cap = max(1, min(total, _RESIDENT_BYTES // max(1, per_win * seg.element_size())))
+        self.cap = max(1, min(total, _resident_budget(device) // max(1, per_win * seg.element_size())))
         self.store = torch.empty((self.cap, self.chns, *seg_shape), device=device, dtype=seg.dtype)
         self.first = 0      # flat index of store[0]
         self.count = 0      # windows currently resident
         self.acc: torch.Tensor | None = None
         self.dtype = seg.dtype
+        self.slot_ids: list[int] = []   # buffered mode: flat window ids of the resident predictions, in slot order
         self.result: torch.Tensor | None = None
         self.factors = None
 
@@ -161,15 +175,97 @@ def sliding_window_inference(
     """Sliding-window inference on `inputs` with `predictor`; see the reference docstring for argument semantics.
 
     Differences that are improvements rather than incompatibilities: the weighted sum is accumulated in fp32 even
-    for fp16 inputs (the reference accumulates in the input dtype, utils.py:148,269-270), and `buffer_steps` only
-    affects memory in the reference, so here it is validated and otherwise ignored (the resident-prediction budget
-    bounds memory instead).
+    for fp16 inputs (the reference accumulates in the input dtype, utils.py:148,269-270).  With `buffer_steps` the windows
+    are visited in the reference's buffered order (sorted by their start along `buffer_dim`, batches never cross a buffer
+    or a batch item, utils.py:182-191, 324-348) and each buffer is folded into the fp32 accumulators when it completes.
     """
+    return _swi_core(inputs, roi_size, sw_batch_size, predictor, overlap, mode, sigma_scale, padding_mode, cval, sw_device, device, progress,
+                     roi_weight_map, process_fn, buffer_steps, buffer_dim, with_coord, None, args, kwargs)
+
+
+def sliding_window_inference_resampled(
+    inputs: torch.Tensor,
+    roi_size: Sequence[int] | int,
+    sw_batch_size: int,
+    predictor: Callable[..., torch.Tensor],
+    matrix: Any,
+    output_shape: Sequence[int],
+    overlap: Sequence[float] | float = 0.25,
+    mode: str = "constant",
+    sigma_scale: Sequence[float] | float = 0.125,
+    interp_mode: str = "bilinear",
+    resample_padding_mode: str = "border",
+    padding_mode: str = "constant",
+    cval: float = 0.0,
+    sw_device: torch.device | str | None = None,
+    device: torch.device | str | None = None,
+    *args: Any,
+    **kwargs: Any,
+) -> torch.Tensor:
+    """Sliding-window inference whose overlap blend and the affine resampling that follows it run as ONE kernel.
+
+    out[b, c, o] = sample(blend(windows)[b, c], M @ (o, 1)) for a 3x4 (or 4x4) `matrix` M that maps an OUTPUT voxel index to a
+    coordinate in the inference grid -- what `sliding_window_inference` followed by `Spacing.inverse` / `SpatialResample`
+    computes in the reference (monai/inferers/utils.py:286-298,351-360 then monai/transforms/spatial/functional.py:68-184),
+    without ever writing the blended volume.  `interp_mode` "bilinear" | "nearest", `resample_padding_mode` "border" | "zeros".
+    3-D volumes, single-tensor predictors.
+    """
+    m = np.asarray(matrix.detach().cpu().numpy() if isinstance(matrix, torch.Tensor) else matrix, dtype=np.float64)
+    if m.shape not in ((3, 4), (4, 4)):
+        raise ValueError(f"matrix must be 3x4 or 4x4 (output voxel index -> inference-grid coordinate), got {m.shape}")
+    if len(inputs.shape) != 5 or len(tuple(output_shape)) != 3:
+        raise NotImplementedError("sliding_window_inference_resampled handles 3-D volumes")
+    interp = {"bilinear": 1, "trilinear": 1, "linear": 1, "nearest": 0}.get(str(getattr(interp_mode, "value", interp_mode)).lower())
+    pad = {"border": 1, "zeros": 0}.get(str(getattr(resample_padding_mode, "value", resample_padding_mode)).lower())
+    if interp is None or pad is None:
+        raise ValueError(f"unsupported interp_mode / resample_padding_mode: {interp_mode}, {resample_padding_mode}")
+    rs = ([float(v) for v in m[:3].reshape(-1)], tuple(int(v) for v in output_shape), interp, pad)
+    return _swi_core(inputs, roi_size, sw_batch_size, predictor, overlap, mode, sigma_scale, padding_mode, cval, sw_device, device, False,
+                     None, None, None, -1, False, rs, args, kwargs)
+
+
+def resample_matrix(src_affine, dst_affine, in_shape: Sequence[int], out_shape: Sequence[int], align_corners: bool = False) -> np.ndarray:
+    """3x4 matrix for `sliding_window_inference_resampled`: voxel index on the DESTINATION grid (affine `dst_affine`, shape
+    `out_shape`) -> coordinate on the inference grid (affine `src_affine`, shape `in_shape`), with the conventions of
+    SpatialResample (monai/transforms/spatial/functional.py:68-184) -- e.g. src = the Spacingd output the network ran on,
+    dst = the original image grid: the inverse of Spacingd applied to the logits."""
+    from ..transforms import utils as TU
+
+    src = TU.to_affine_nd(3, np.asarray(src_affine, dtype=np.float64))
+    dst = TU.to_affine_nd(3, np.asarray(dst_affine, dtype=np.float64))
+    xform = TU.to_affine_nd(3, np.linalg.solve(src, dst))
+    return TU.sample_matrix_from_xform(xform, tuple(int(v) for v in in_shape), np.asarray([int(v) for v in out_shape]), align_corners)
+
+
+def _create_buffered_order(starts_nd, roi_size, batch_size: int, sw_batch_size: int, buffer_dim: int, buffer_steps: int):
+    """Window order and buffer boundaries of the reference's buffered mode (monai/inferers/utils.py:324-348).
+
+    Returns (order, groups): `order` = permutation of the canonical ("ij") window ids, stably sorted by the start along
+    `buffer_dim`; `groups` = list of (first, last) positions IN THE SORTED LIST per buffer and batch item, expressed as flat
+    indices b * num_win + position, in visiting order."""
+    flat = list(itertools.product(*starts_nd))
+    num_win = len(flat)
+    key = np.asarray([f[buffer_dim] for f in flat])
+    order = np.argsort(key, kind="mergesort")
+    sorted_key = key[order]
+    _, counts = np.unique(sorted_key, return_counts=True)
+    b_ends = np.cumsum(counts).tolist()                      # possible buffer flush boundaries
+    x = [0, *b_ends][:: min(len(b_ends), int(buffer_steps))]
+    if x[-1] < b_ends[-1]:
+        x.append(b_ends[-1])
+    groups = [(b * num_win + x[i], b * num_win + x[i + 1]) for b in range(batch_size) for i in range(len(x) - 1)]
+    return order, groups
+
+
+def _swi_core(inputs, roi_size, sw_batch_size, predictor, overlap, mode, sigma_scale, padding_mode, cval, sw_device, device, progress,
+              roi_weight_map, process_fn, buffer_steps, buffer_dim, with_coord, resample, args, kwargs):
     buffered = buffer_steps is not None and buffer_steps > 0
     num_spatial_dims = len(inputs.shape) - 2
     if buffered:
         if buffer_dim < -num_spatial_dims or buffer_dim > num_spatial_dims:
             raise ValueError(f"buffer_dim must be in [{-num_spatial_dims}, {num_spatial_dims}], got {buffer_dim}.")
+        if buffer_dim < 0:
+            buffer_dim += num_spatial_dims
     overlap = _ensure_tuple_rep(overlap, num_spatial_dims)
     for o in overlap:
         if o < 0 or o >= 1:
@@ -194,6 +290,8 @@ def sliding_window_inference(
     temp_meta = inputs if _is_meta(inputs) else None
     x = inputs.as_subclass(torch.Tensor) if type(inputs) is not torch.Tensor else inputs
     x = x.detach()
+    if x.dtype == torch.float64:   # float64 volumes are blended in fp32 and returned as float64 (the kernels take f16 / f32)
+        x = x.float()
     roi_size = _fall_back_tuple(roi_size, image_size_)
 
     # pad when the image is smaller than the roi (utils.py:163-170): symmetric, half / diff-half
@@ -207,6 +305,14 @@ def sliding_window_inference(
         x = F.pad(x, pad=pad_size, mode=pad_s, value=cval)
     x = x.to(sw_dev)
 
+    # fused resample: the kernel samples the PADDED blended volume, so the matrix takes the leading pad of each axis
+    rs_plan = None
+    if resample is not None:
+        mat, oshape, interp, rpad = resample
+        mat = list(mat)
+        for ax in range(3):
+            mat[4 * ax + 3] += float(pad_size[2 * (2 - ax)]) if any(pad_size) else 0.0   # pad_size lists the LAST axis first
+        rs_plan = (mat, oshape, interp, rpad)
     scan_interval = _get_scan_interval(image_size, roi_size, num_spatial_dims, overlap)
     starts_nd = dense_patch_starts(image_size, roi_size, scan_interval)
     valid_patch_size = get_valid_patch_size(image_size, roi_size)
@@ -257,15 +363,26 @@ def sliding_window_inference(
     def _dense3(w: torch.Tensor, shape3) -> torch.Tensor:
         return w.to(device=sw_dev, dtype=torch.float32).reshape(shape3).contiguous()
 
+    def _out_shape(pl: _OutputPlan):
+        return (batch_size, pl.chns, *(rs_plan[1] if rs_plan is not None else pl.vol))
+
     def _flush(pl: _OutputPlan, wmap_now: torch.Tensor | None, final: bool) -> None:
         """Fold the resident predictions into the result (mode 0 when they are ALL resident, else mode 1)."""
         if pl.count == 0:
             return
         vol_shape = (batch_size, pl.chns, *pl.vol)
         preds = pl.store[: pl.count]
-        if final and pl.acc is None and pl.count == pl.total:
-            pl.result = torch.empty(vol_shape, device=sw_dev, dtype=pl.dtype)
-            K.sw_blend(0, preds, 0, pl.total, vol_shape, pl.roi, pl.starts, pl.factors, clamp, wmap_now, pl.result)
+        if buffered:
+            # the resident predictions are the windows `pl.slot_ids` (visiting order != id order): look them up through a slot map
+            if pl.acc is None:
+                pl.acc = torch.zeros(vol_shape, device=sw_dev, dtype=torch.float32)
+            slot_map = torch.full((total_slices,), -1, dtype=torch.int32, device=sw_dev)
+            slot_map[torch.tensor(pl.slot_ids, dtype=torch.int64, device=sw_dev)] = torch.arange(pl.count, dtype=torch.int32, device=sw_dev)
+            K.sw_blend(1, preds, 0, 0, vol_shape, pl.roi, pl.starts, pl.factors, clamp, wmap_now, pl.acc, slot_map=slot_map, n_slots=pl.count)
+            pl.slot_ids = []
+        elif final and pl.acc is None and pl.count == pl.total:
+            pl.result = torch.empty(_out_shape(pl), device=sw_dev, dtype=pl.dtype)
+            K.sw_blend(0, preds, 0, pl.total, vol_shape, pl.roi, pl.starts, pl.factors, clamp, wmap_now, pl.result, resample=rs_plan)
         else:
             if pl.acc is None:
                 pl.acc = torch.zeros(vol_shape, device=sw_dev, dtype=torch.float32)
@@ -273,18 +390,33 @@ def sliding_window_inference(
         pl.first += pl.count
         pl.count = 0
 
-    rng = range(0, total_slices, sw_batch_size)
+    # batches of flat window ids (b * num_win + canonical "ij" id) in visiting order; `ends` = batches after which a buffer is complete
+    if not buffered:
+        batches: list = [range(g, min(g + sw_batch_size, total_slices)) for g in range(0, total_slices, sw_batch_size)]
+        ends: set = set()
+    else:
+        order, groups = _create_buffered_order(starts_nd, roi_size, batch_size, sw_batch_size, buffer_dim, int(buffer_steps))
+        batches, ends = [], set()
+        for first, last in groups:
+            b_off = (first // num_win) * num_win
+            for g in range(first, last, sw_batch_size):
+                batches.append([b_off + int(order[pos - b_off]) for pos in range(g, min(g + sw_batch_size, last))])
+            ends.add(len(batches) - 1)
+    it = batches
     if progress:
         try:
             from tqdm import tqdm
 
-            rng = tqdm(rng)
+            it = tqdm(batches)
         except ImportError:  # pragma: no cover
             pass
     nd_slices = [tuple(slice(s, s + r) for s, r in zip(st[lift:], roi_size)) for st in flat_starts]
-    for slice_g in rng:
-        slice_range = range(slice_g, min(slice_g + sw_batch_size, total_slices))
-        win_data3 = K.sw_gather(x3, win_tab_all[slice_range.start : slice_range.stop], roi3)
+    for bi, slice_range in enumerate(it):
+        if isinstance(slice_range, range):
+            tab = win_tab_all[slice_range.start : slice_range.stop]
+        else:
+            tab = win_tab_all[torch.tensor(slice_range, dtype=torch.int64, device=sw_dev)]
+        win_data3 = K.sw_gather(x3, tab, roi3)
         win_data = win_data3.reshape(win_data3.shape[0], win_data3.shape[1], *roi_size)
         if with_coord:
             unravel_slice = [
@@ -294,6 +426,8 @@ def sliding_window_inference(
         else:
             seg_prob_out = predictor(win_data, *args, **kwargs)
         dict_keys, seg_tuple = _flatten_struct(seg_prob_out)
+        if buffered:
+            seg_tuple = tuple(seg_tuple[:1])   # the reference's buffered mode blends the first output only (utils.py:241)
         w_t = None
         if process_fn is not None:
             seg_tuple, w_t = process_fn(seg_tuple, win_data, importance_map_for_fn)
@@ -335,24 +469,34 @@ def sliding_window_inference(
                 _flush(pl, wm_now, final=False)
             pl.store[pl.count : pl.count + n].copy_(seg3)
             pl.count += n
+            if buffered:
+                pl.slot_ids.extend(int(i) for i in slice_range)
             if process_fn is not None:  # the weight map may change from batch to batch: fold immediately
                 _flush(pl, wm_now, final=(pl.first + pl.count == pl.total and pl.acc is None))
+            elif buffered and bi in ends:   # this buffer is complete: fold it into the accumulators
+                _flush(pl, wm_now, final=False)
 
     outputs = []
     for ss, pl in enumerate(plans):
         _flush(pl, first_wmaps[ss], final=True)
         if pl.result is None:
             vol_shape = (batch_size, pl.chns, *pl.vol)
-            pl.result = torch.empty(vol_shape, device=sw_dev, dtype=pl.dtype)
+            pl.result = torch.empty(_out_shape(pl), device=sw_dev, dtype=pl.dtype)
             # count map is analytic: sum of the (first) weight map over all windows (utils.py:272-275)
-            K.sw_blend(2, None, 0, pl.total, vol_shape, pl.roi, pl.starts, pl.factors, clamp, first_wmaps[ss], pl.result, acc=pl.acc)
+            K.sw_blend(2, None, 0, pl.total, vol_shape, pl.roi, pl.starts, pl.factors, clamp, first_wmaps[ss], pl.result, acc=pl.acc, resample=rs_plan)
             pl.acc = None
+        if rs_plan is not None:
+            if pl.z_scale is not None:
+                raise NotImplementedError("sliding_window_inference_resampled needs predictor outputs at the window resolution")
+            outputs.append(pl.result)
+            pl.store = None
+            continue
         out = pl.result.reshape(batch_size, pl.chns, *pl.vol[lift:])
         pl.store = None
         outputs.append(out)
 
     # remove padding if the image was smaller than the roi (utils.py:301-313)
-    if any(pad_size):
+    if any(pad_size) and rs_plan is None:
         for ss, out in enumerate(outputs):
             zoom_scale = [s / r for s, r in zip(out.shape[2:], roi_size)]
             final_slicing: list[slice] = []
@@ -367,6 +511,6 @@ def sliding_window_inference(
                 )
             outputs[ss] = out[(slice(None), slice(None), *final_slicing)]
 
-    outputs = [o.to(device=out_device, dtype=compute_dtype if compute_dtype in (torch.float16, torch.float32) else o.dtype) for o in outputs]
+    outputs = [o.to(device=out_device, dtype=compute_dtype if compute_dtype in (torch.float16, torch.float32, torch.float64) else o.dtype) for o in outputs]
     outputs = [_rewrap(o, temp_meta) for o in outputs]
     return _pack_struct(outputs, dict_keys)

@@ -22,6 +22,7 @@ def main():
         preds = torch.randn((n, C, *roi), device=dev, dtype=torch.float16)
         st = [torch.tensor(s, dtype=torch.int32, device=dev) for s in starts]
         st[2]._align = 8
+        st[2]._max_cover = 3   # roi 96 / interval 48 with a snapped last window: at most three windows cover a voxel per axis
         f, clamp = importance_factors(roi, "gaussian", 0.125)
         f = [t.to(dev) for t in f]
         out = torch.empty((1, C, *vol), device=dev, dtype=torch.float16)

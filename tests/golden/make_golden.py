@@ -167,6 +167,28 @@ def nets_r2():
     dump("fs48_in4_v2_64", net, torch.randn(1, 4, 64, 64, 64, generator=torch.Generator().manual_seed(19)).half().float())
 
 
+def buffered():
+    """Window order / batching the predictor observes in the reference's buffered mode (with_coord=True), plus the result."""
+    out = {}
+    cases = [((2, 3, 10, 11, 12), (7, 8, 10), 0.2, 2, 3, 1), ((1, 2, 20, 9, 14), (6, 9, 5), 0.5, 3, 2, -1), ((2, 1, 30, 17), (8, 6), 0.4, 4, 4, 0)]
+    for ci, (img_size, roi, ov, swb, steps, dim) in enumerate(cases):
+        x = torch.rand(img_size, generator=torch.Generator().manual_seed(70 + ci))
+        seen = []
+
+        def pred(patch, coords):
+            seen.append(np.asarray([[c[0].start] + [s.start for s in c[2:]] for c in coords], dtype=np.int64))
+            return 2.0 * patch + 1.0
+
+        y = sliding_window_inference(x, roi, swb, pred, ov, mode="gaussian", buffer_steps=steps, buffer_dim=dim, with_coord=True)
+        out[f"c{ci}.x"], out[f"c{ci}.y"] = x.numpy(), y.numpy()
+        out[f"c{ci}.cfg"] = np.asarray(list(roi) + [swb, steps, dim], dtype=np.int64)
+        out[f"c{ci}.ov"] = np.asarray(ov, dtype=np.float64)
+        out[f"c{ci}.batch_sizes"] = np.asarray([len(a) for a in seen], dtype=np.int64)
+        out[f"c{ci}.coords"] = np.concatenate(seen, 0)
+    out["n"] = np.array(len(cases))
+    save("buffered.npz", **out)
+
+
 def transforms():
     from monai.data import MetaTensor
     from monai.transforms import GaussianSmooth, RandAffined, Spacing, Spacingd
@@ -345,6 +367,6 @@ def unit_goldens():
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "transforms", "post", "patch", "unit_goldens"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "buffered", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

@@ -175,3 +175,35 @@ def test_patch_inferer_argument_errors():
     with pytest.raises(RuntimeError, match="CUDA device"):
         AvgMerger(merged_shape=(1, 1, 4, 4), device="cpu")
     assert isinstance(PatchInferer(splitter=SlidingWindowSplitter(4)).splitter, SlidingWindowSplitter)
+
+
+def test_buffered_window_order_matches_the_reference(golden_dir):
+    """buffer_steps / buffer_dim: the order and batching in which the predictor sees the windows is the reference's
+    (monai/inferers/utils.py:324-348), checked against coordinates recorded from the real reference (with_coord=True)."""
+    import itertools
+
+    import numpy as np
+
+    from monai_b200.data.utils import dense_patch_starts
+    from monai_b200.inferers.utils import _create_buffered_order, _get_scan_interval
+
+    g = np.load(os.path.join(golden_dir, "buffered.npz"))
+    for ci in range(int(g["n"])):
+        x, cfg = g[f"c{ci}.x"], g[f"c{ci}.cfg"]
+        nd = x.ndim - 2
+        roi, swb, steps, dim = tuple(int(v) for v in cfg[:nd]), int(cfg[nd]), int(cfg[nd + 1]), int(cfg[nd + 2])
+        dim = dim + nd if dim < 0 else dim
+        image = tuple(max(i, r) for i, r in zip(x.shape[2:], roi))
+        interval = _get_scan_interval(image, roi, nd, (float(g[f"c{ci}.ov"]),) * nd)
+        starts = dense_patch_starts(image, roi, interval)
+        flat = list(itertools.product(*starts))
+        order, groups = _create_buffered_order(starts, roi, x.shape[0], swb, dim, steps)
+        coords, sizes = [], []
+        for first, last in groups:
+            b = first // len(flat)
+            for g0 in range(first, last, swb):
+                ids = [int(order[pos - b * len(flat)]) for pos in range(g0, min(g0 + swb, last))]
+                sizes.append(len(ids))
+                coords.extend([b, *flat[i]] for i in ids)
+        np.testing.assert_array_equal(np.asarray(sizes), g[f"c{ci}.batch_sizes"], err_msg=f"case {ci}")
+        np.testing.assert_array_equal(np.asarray(coords), g[f"c{ci}.coords"], err_msg=f"case {ci}")
