@@ -126,6 +126,20 @@ int b200_resample_affine(const void* src, int src_dtype, int C, int Di, int Hi, 
                          int Do, int Ho, int Wo, const double* mat3x4, int interp, int pad, int align_corners,
                          void* stream);
 
+/* Dense-grid spline resampling: replaces monai._C.grid_pull (monai/csrc/ext.cpp:66-74, csrc/resample/pushpull.h:58-110,
+ * python wrapper monai/networks/layers/spatial_transforms.py:35-132) and the dense-grid form of Resample.__call__
+ * (monai/transforms/spatial/array.py:2015-2117).  src [B,C,X,Y,Z] (f16/f32); grid holds three coordinate components per output
+ * voxel, addressed as grid[b*stride_b + comp*stride_c + voxel*stride_v] (channel-last [B,Xo,Yo,Zo,3]: stride_c 1, stride_v 3;
+ * channel-first [3|4,Xo,Yo,Zo]: stride_c Xo*Yo*Zo, stride_v 1), dtype 0 float32 or 2 float64; the VOXEL coordinate of axis a is
+ * scale3[a] * value + shift3[a] (NULL = identity).  bound3 / order3 per axis: bound 0 replicate, 1 dct1, 2 dct2, 3 dst1, 4 dst2,
+ * 5 dft, 7 zero (monai/csrc/resample/bounds_common.h); order 0..7 = centred cardinal B-spline weights without prefilter
+ * (csrc/resample/interpolation_common.h).  extrapolate = 0 zeroes voxels whose coordinate leaves [-0.05, size-1+0.05).
+ * nearest_half_even selects ATen's rounding for order 0 (grid_sample) instead of monai._C's std::round.  out [B,C,Xo,Yo,Zo]. */
+int b200_grid_pull(const void* src, int src_dtype, int B, int C, int X, int Y, int Z, const void* grid, int grid_dtype,
+                   long long grid_stride_b, long long grid_stride_c, long long grid_stride_v, int Xo, int Yo, int Zo,
+                   const double* scale3, const double* shift3, const int* bound3, const int* order3, int extrapolate,
+                   int nearest_half_even, void* out, int out_dtype, void* stream);
+
 /* zero-padded separable 3-D filter (GaussianFilter, monai/networks/layers/simplelayers.py:170-249, 542-595):
  * taps_* are float32 device arrays of odd length n_*; src/dst [C,D,H,W]; tmp is a float32 scratch buffer of
  * 2*C*D*H*W elements (the two intermediate passes stay fp32). */

@@ -299,6 +299,43 @@ def resample_affine(
     return dst
 
 
+BOUNDS = {"replicate": 0, "nearest": 0, "border": 0, "dct1": 1, "mirror": 1, "dct2": 2, "reflect": 2, "dst1": 3, "antimirror": 3,
+          "dst2": 4, "antireflect": 4, "dft": 5, "wrap": 5, "zero": 7, "zeros": 7}
+ORDERS = {"nearest": 0, "linear": 1, "quadratic": 2, "cubic": 3, "fourth": 4, "fifth": 5, "sixth": 6, "seventh": 7}
+
+
+def grid_pull(src: torch.Tensor, grid: torch.Tensor, bound: Sequence[int], order: Sequence[int], extrapolate: bool = True,
+              channel_last: bool = True, scale: Sequence[float] | None = None, shift: Sequence[float] | None = None,
+              half_even: bool = False, out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """src [B,C,X,Y,Z]; grid [B,Xo,Yo,Zo,3] (channel_last) or [>=3,Xo,Yo,Zo] shared by the batch (channel first), float32 /
+    float64, voxel coordinates after the per-axis `scale` / `shift`.  See b200_grid_pull."""
+    L.require_cuda(src, grid)
+    src = src.contiguous()
+    grid = grid.contiguous()
+    if grid.dtype not in (torch.float32, torch.float64):
+        grid = grid.float()
+    Bn, Cc, X, Y, Z = src.shape
+    if channel_last:
+        _, Xo, Yo, Zo, ncomp = grid.shape
+        if ncomp != 3 or grid.shape[0] != Bn:
+            raise ValueError(f"grid must be [B, Xo, Yo, Zo, 3] with B = {Bn}, got {tuple(grid.shape)}")
+        sb, sc, sv = Xo * Yo * Zo * 3, 1, 3
+    else:
+        ncomp, Xo, Yo, Zo = grid.shape
+        if ncomp < 3:
+            raise ValueError(f"channel-first grid needs at least 3 coordinate rows, got {tuple(grid.shape)}")
+        sb, sc, sv = 0, Xo * Yo * Zo, 1
+    out = torch.empty((Bn, Cc, Xo, Yo, Zo), device=src.device, dtype=out_dtype or (src.dtype if src.dtype in (torch.float16, torch.float32) else torch.float32))
+    dbl3 = C.c_double * 3
+    int3 = C.c_int * 3
+    sc3 = dbl3(*[float(v) for v in scale]) if scale is not None else None
+    sh3 = dbl3(*[float(v) for v in shift]) if shift is not None else None
+    _call("grid_pull", L.ptr(src), L.dt(src), Bn, Cc, X, Y, Z, L.ptr(grid), 2 if grid.dtype == torch.float64 else 0, sb, sc, sv, Xo, Yo, Zo,
+          sc3, sh3, int3(*[int(b) for b in bound]), int3(*[int(o) for o in order]), int(bool(extrapolate)), int(bool(half_even)),
+          L.ptr(out), L.dt(out), L.stream_ptr(src.device), nbytes=_nb(src, out) + 3.0 * Xo * Yo * Zo * grid.element_size() * (Bn if channel_last else 1))
+    return out
+
+
 def separable_filter3d(src: torch.Tensor, taps: Sequence[torch.Tensor]) -> torch.Tensor:
     """src [C,D,H,W]; taps = three float32 device vectors of odd length; zero padding."""
     L.require_cuda(src)

@@ -305,20 +305,58 @@ class RandAffineGrid(Randomizable, Transform):
 
 
 class Resample(Transform):
-    """Resample with an explicit grid (spatial/array.py:1962-2117).  Affine grids produced by this package are resolved
-    to their matrix (no dense grid traffic); arbitrary dense grids are not implemented on this path."""
+    """Resample with an explicit grid (spatial/array.py:1962-2117).  Affine grids produced by this package (AffineSpec) are
+    resolved to their matrix (no dense grid traffic); a dense grid tensor [3|4, H, W[, D]] (a deformation field, the output of
+    the reference's AffineGrid, ...) is sampled by the dense-grid kernel (b200_grid_pull) with the torch path's conventions:
+    centred voxel coordinates scaled by 2 / max(2, size) when `norm_coords`, values in [-1, 1] otherwise, grid_sample's
+    un-normalisation for `align_corners`, zeros / border / reflection padding, bilinear or nearest interpolation."""
 
     def __init__(self, mode="bilinear", padding_mode="border", norm_coords: bool = True, device=None, align_corners: bool = False, dtype=np.float64):
         self.mode, self.padding_mode, self.norm_coords, self.device, self.align_corners, self.dtype = mode, padding_mode, norm_coords, device, align_corners, dtype
 
+    def _dense(self, img, grid, mode, padding_mode, align: bool):
+        if not img.is_cuda:
+            raise RuntimeError("monai_b200 spatial transforms run on CUDA tensors only (there is no CPU fallback)")
+        t = img.as_subclass(torch.Tensor) if type(img) is not torch.Tensor else img
+        if t.dtype not in (torch.float16, torch.float32):
+            t = t.float()
+        sr = min(t.dim() - 1, 3)
+        g = torch.as_tensor(grid)
+        g = (g.as_subclass(torch.Tensor) if type(g) is not torch.Tensor else g).to(t.device)
+        if g.shape[0] < sr or tuple(g.shape[1:]) == () or g.dim() != sr + 1:
+            raise ValueError(f"grid must be [{sr} or {sr + 1}, *spatial], got {tuple(g.shape)}")
+        if g.dtype not in (torch.float32, torch.float64):
+            g = g.to(torch.float64 if self.dtype in (np.float64, torch.float64, None) else torch.float32)
+        in_sp = tuple(int(s) for s in t.shape[1 : 1 + sr])
+        # voxel coordinate of axis i = a_i * grid[i] + b_i: (x 2/max(2,size)) then grid_sample's un-normalisation
+        scale, shift = [], []
+        for size in in_sp:
+            k = 2.0 / max(2, size) if self.norm_coords else 1.0
+            if align:
+                scale.append(k * (size - 1) / 2.0); shift.append((size - 1) / 2.0)
+            else:
+                scale.append(k * size / 2.0); shift.append((size - 1) / 2.0)
+        pad_code = _pad(padding_mode)
+        bound = {L.PAD_ZEROS: 7, L.PAD_BORDER: 0, L.PAD_REFLECTION: 1 if align else 2}[pad_code]   # reflection: about centres (dct1) / edges (dct2)
+        order = 1 if _mode(mode) == L.INTERP_LINEAR else 0
+        lift = 3 - sr
+        out_sp = tuple(int(s) for s in g.shape[1:])
+        t3 = t.reshape(1, t.shape[0], *([1] * lift), *in_sp)
+        g3 = g[:sr].reshape(sr, *([1] * lift), *out_sp)
+        if lift:
+            g3 = torch.cat([torch.zeros((lift, *g3.shape[1:]), dtype=g3.dtype, device=g3.device), g3], 0)
+        out = K.grid_pull(t3, g3.contiguous(), [0] * lift + [bound] * sr, [0] * lift + [order] * sr, extrapolate=True, channel_last=False,
+                          scale=[1.0] * lift + scale, shift=[0.0] * lift + shift, half_even=True, out_dtype=torch.float32)
+        return rewrap(out.reshape(t.shape[0], *out_sp), img)
+
     def __call__(self, img, grid=None, mode=None, padding_mode=None, dtype=None, align_corners=None):
         if grid is None:
             return img
-        if not isinstance(grid, AffineSpec):
-            raise NotImplementedError("monai_b200 Resample takes the affine grids of AffineGrid/RandAffineGrid (AffineSpec); dense deformation grids are not implemented")
-        if not self.norm_coords:
-            raise NotImplementedError("norm_coords=False is not implemented")
         align = self.align_corners if align_corners is None else align_corners
+        if not isinstance(grid, AffineSpec):
+            return self._dense(img, grid, self.mode if mode is None else mode, self.padding_mode if padding_mode is None else padding_mode, bool(align))
+        if not self.norm_coords:
+            raise NotImplementedError("norm_coords=False with an affine grid specification is not implemented (pass the dense grid)")
         r = len(grid.spatial_size)
         mat = U.sample_matrix_from_centered_affine(grid.affine if not (grid.grid_align_corners) else grid.affine, tuple(img.shape[1 : 1 + r]), grid.spatial_size, align)
         out = _resample(img, mat, r, grid.spatial_size, self.mode if mode is None else mode, self.padding_mode if padding_mode is None else padding_mode, align)

@@ -189,6 +189,83 @@ def buffered():
     save("buffered.npz", **out)
 
 
+def resampler():
+    """Dense-grid Resample of the real reference (torch path): its own unit-test cases (tests/transforms/test_resampler.py) run
+    through the class, plus random deformation grids for every (mode, padding_mode, align_corners, norm_coords)."""
+    from monai.transforms import Resample
+    from monai.transforms.utils import create_grid
+
+    out, n = {}, 0
+    for pad, gsz, isz, mode in [("zeros", (2, 2), (1, 2, 2), None), ("zeros", (4, 4), (1, 2, 2), None), ("border", (4, 4), (1, 2, 2), None),
+                                ("zeros", (4, 4, 4), (1, 2, 2, 2), "bilinear"), ("border", (4, 4, 4), (1, 2, 2, 2), "bilinear")]:
+        img = torch.arange(int(np.prod(isz)), dtype=torch.float32).reshape(isz)
+        grid = torch.as_tensor(create_grid(gsz))
+        kw = {} if mode is None else {"mode": mode}
+        y = Resample(padding_mode=pad)(img=img, grid=grid, **kw)
+        out[f"c{n}.img"], out[f"c{n}.grid"], out[f"c{n}.y"] = img.numpy(), grid.numpy(), np.asarray(y)
+        out[f"c{n}.cfg"] = np.asarray([str(mode or "bilinear"), pad, "0", "1"])
+        n += 1
+    g = torch.Generator().manual_seed(41)
+    for mode in ("bilinear", "nearest"):
+        for pad in ("zeros", "border", "reflection"):
+            for align in (False, True):
+                for norm in (True, False):
+                    img = torch.rand((2, 9, 7, 11), generator=g)
+                    osz = (8, 10, 6)
+                    base = torch.as_tensor(create_grid(osz, dtype=np.float64))[:3]          # centred voxel coordinates
+                    grid = base * (torch.tensor([9, 7, 11.0]) / torch.tensor(osz, dtype=torch.float64)).reshape(3, 1, 1, 1)
+                    grid = grid + (torch.rand(grid.shape, generator=g, dtype=torch.float64) - 0.5) * 5.0   # incl. samples outside the image
+                    if not norm:
+                        grid = grid / (torch.tensor([9, 7, 11.0], dtype=torch.float64).reshape(3, 1, 1, 1) / 2.0)
+                    if mode == "nearest":   # keep clear of the .5 ties whose rounding is round-off dependent
+                        pass
+                    y = Resample(mode=mode, padding_mode=pad, norm_coords=norm, align_corners=align)(img=img, grid=grid)
+                    out[f"c{n}.img"], out[f"c{n}.grid"], out[f"c{n}.y"] = img.numpy(), grid.numpy(), np.asarray(y)
+                    out[f"c{n}.cfg"] = np.asarray([mode, pad, str(int(align)), str(int(norm))])
+                    n += 1
+    out["n"] = np.array(n)
+    save("resampler.npz", **out)
+
+
+def grid_pull_ref():
+    """monai._C.grid_pull of the REAL reference (its own C++ sources compiled into oracle/_ref, CPU): every bound x every spline
+    order on a random 3-D volume with samples far outside the field of view, the per-axis mixed case, extrapolate=False, and the
+    56 rows of tests/testing_data/1D_BP_fwd.txt (transcribed mechanically and re-checked against the compiled reference)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import build_ref
+
+    C = build_ref.load()
+    assert C is not None, "run python oracle/build_ref.py first"
+    out = {}
+    rows, labels = [], []
+    for line in open("/root/reference/tests/testing_data/1D_BP_fwd.txt"):
+        if "#" not in line:
+            continue
+        vals, lab = line.split("#")
+        rows.append([float(v) for v in vals.split(",") if v.strip()])
+        labels.append(lab.strip())
+    out["bp1d.rows"], out["bp1d.labels"] = np.asarray(rows, dtype=np.float64), np.asarray(labels)
+    bnames = {"replicate": 0, "dct1": 1, "dct2": 2, "dst1": 3, "dst2": 4, "dft": 5, "zero": 7}
+    inames = ["nearest", "linear", "quadratic", "cubic", "fourth", "fifth", "sixth", "seventh"]
+    x1 = torch.arange(10, dtype=torch.float32).reshape(1, 1, 10)
+    g1 = (torch.arange(20, dtype=torch.float32) + 0.5).reshape(1, 20, 1)
+    for r, lab in zip(rows, labels):
+        it, bt = lab.split()
+        o, b = inames.index(it.split(".")[1]), bnames[bt.split(".")[1]]
+        got = C.grid_pull(x1, g1, [C.BoundType(b)], [C.InterpolationType(o)], True).reshape(-1).numpy()
+        np.testing.assert_allclose(got, np.asarray(r), rtol=1e-4, atol=1e-4, err_msg=lab)
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn((2, 2, 6, 7, 5), generator=g)
+    grid = torch.rand((2, 4, 5, 6, 3), generator=g) * torch.tensor([14.0, 15.0, 13.0]) - 4.0
+    out["x"], out["grid"] = x.numpy(), grid.numpy()
+    for bn, b in bnames.items():
+        for o in range(8):
+            out[f"y.{bn}.{o}"] = C.grid_pull(x, grid, [C.BoundType(b)] * 3, [C.InterpolationType(o)] * 3, True).numpy()
+    out["y.mixed"] = C.grid_pull(x, grid, [C.BoundType(2), C.BoundType(5), C.BoundType(3)], [C.InterpolationType(3), C.InterpolationType(1), C.InterpolationType(2)], True).numpy()
+    out["y.noextrap"] = C.grid_pull(x, grid, [C.BoundType(0)] * 3, [C.InterpolationType(1)] * 3, False).numpy()
+    save("grid_pull.npz", **out)
+
+
 def transforms():
     from monai.data import MetaTensor
     from monai.transforms import GaussianSmooth, RandAffined, Spacing, Spacingd
@@ -367,6 +444,6 @@ def unit_goldens():
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "buffered", "transforms", "post", "patch", "unit_goldens"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "buffered", "resampler", "grid_pull_ref", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

@@ -1,0 +1,50 @@
+"""CPU: the numpy restatement of monai._C.grid_pull (oracle/resample.py) against the reference's golden rows and against outputs
+of the reference's own C++ sources (compiled into oracle/_ref by oracle/build_ref.py; fixtures in tests/golden/grid_pull.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import resample as ors
+
+INTERP = ["nearest", "linear", "quadratic", "cubic", "fourth", "fifth", "sixth", "seventh"]
+
+
+def test_oracle_reproduces_1d_bp_fwd_rows(golden_dir):
+    """tests/testing_data/1D_BP_fwd.txt (56 rows = 7 bounds x 8 orders), the vectors of tests/networks/layers/test_grid_pull.py."""
+    g = np.load(os.path.join(golden_dir, "grid_pull.npz"))
+    x = np.arange(10, dtype=np.float32).reshape(1, 1, 10, 1, 1)
+    grid = np.zeros((1, 20, 1, 1, 3), dtype=np.float32)
+    grid[0, :, 0, 0, 0] = np.arange(20, dtype=np.float32) + 0.5
+    assert len(g["bp1d.labels"]) == 56
+    for row, lab in zip(g["bp1d.rows"], g["bp1d.labels"]):
+        it, bt = str(lab).split()
+        o, b = INTERP.index(it.split(".")[1]), ors.BOUNDS[bt.split(".")[1]]
+        got = ors.grid_pull(x, grid, [b, 0, 0], [o, 0, 0]).reshape(-1)
+        np.testing.assert_allclose(got, row, rtol=1e-4, atol=1e-4, err_msg=str(lab))
+
+
+def test_oracle_matches_compiled_reference_3d(golden_dir):
+    g = np.load(os.path.join(golden_dir, "grid_pull.npz"))
+    for bn, b in ors.BOUNDS.items():
+        for o in range(8):
+            got = ors.grid_pull(g["x"], g["grid"], [b] * 3, [o] * 3)
+            np.testing.assert_allclose(got, g[f"y.{bn}.{o}"], rtol=2e-4, atol=2e-5, err_msg=f"{bn} order {o}")
+    np.testing.assert_allclose(ors.grid_pull(g["x"], g["grid"], [2, 5, 3], [3, 1, 2]), g["y.mixed"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(ors.grid_pull(g["x"], g["grid"], [0, 0, 0], [1, 1, 1], extrapolate=False), g["y.noextrap"], rtol=2e-4, atol=2e-5)
+
+
+def test_compiled_reference_loads_when_present():
+    """oracle/_ref travels with the snapshot: when the .so is there it must import and agree with the restatement."""
+    from oracle import build_ref
+
+    C = build_ref.load()
+    if C is None:
+        pytest.skip("oracle/_ref has not been built on this box")
+    import torch
+
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1, 2, 5, 4, 6)).astype(np.float32)
+    grid = (rng.random((1, 3, 4, 5, 3)) * 9 - 2).astype(np.float32)
+    ref = C.grid_pull(torch.from_numpy(x), torch.from_numpy(grid), [C.BoundType(4)] * 3, [C.InterpolationType(3)] * 3, True).numpy()
+    np.testing.assert_allclose(ors.grid_pull(x, grid, [4] * 3, [3] * 3), ref, rtol=2e-4, atol=2e-5)
