@@ -23,6 +23,7 @@ class MetaTensor(torch.Tensor):
     def __init__(self, x, affine=None, meta: dict | None = None, applied_operations: list | None = None, *args, **kwargs) -> None:
         self.meta: dict[str, Any] = dict(meta) if meta is not None else dict(getattr(x, "meta", {}) or {})
         self.applied_operations: list = list(applied_operations) if applied_operations is not None else list(getattr(x, "applied_operations", []) or [])
+        self.pending_operations: list = list(getattr(x, "pending_operations", []) or [])   # lazy resampling (transforms/lazy.py)
         if affine is not None:
             self.affine = affine
         elif "affine" not in self.meta:
@@ -42,13 +43,47 @@ class MetaTensor(torch.Tensor):
     def copy_meta_from(self, other, copy_attr: bool = True):
         self.meta = copy.deepcopy(other.meta) if copy_attr else dict(other.meta)
         self.applied_operations = copy.deepcopy(other.applied_operations) if copy_attr else list(getattr(other, "applied_operations", []))
+        self.pending_operations = copy.deepcopy(getattr(other, "pending_operations", [])) if copy_attr else list(getattr(other, "pending_operations", []))
         return self
 
+    # ---- lazy resampling bookkeeping (monai/data/meta_tensor.py:480-507, meta_obj.py push/pop/clear) ----------------------
+    def push_pending_operation(self, info: dict) -> None:
+        self.pending_operations.append(info)
+
+    def pop_pending_operation(self) -> dict:
+        return self.pending_operations.pop()
+
+    def clear_pending_operations(self) -> None:
+        self.pending_operations = []
+
+    def push_applied_operation(self, info: dict) -> None:
+        self.applied_operations.append(info)
+
+    def pop_applied_operation(self) -> dict:
+        return self.applied_operations.pop()
+
     def peek_pending_shape(self):
-        return tuple(self.shape[1:])
+        """spatial shape as if all the pending operations were executed"""
+        res = self.pending_operations[-1].get("lazy_shape", None) if self.pending_operations else None
+        return tuple(int(s) for s in self.shape[1:]) if res is None else tuple(int(s) for s in res)
 
     def peek_pending_affine(self):
-        return self.affine
+        res = torch.as_tensor(self.affine, dtype=torch.float64)
+        r = len(res) - 1
+        for p in self.pending_operations:
+            m = p.get("lazy_affine")
+            if m is None:
+                continue
+            m = torch.as_tensor(m, dtype=torch.float64)
+            full = torch.eye(r + 1, dtype=torch.float64)
+            k = min(r, m.shape[0] - 1)
+            full[:k, :k], full[:k, -1] = m[:k, :k], m[:k, -1]
+            res = res @ full
+        return res
+
+    def peek_pending_rank(self) -> int:
+        a = self.pending_operations[-1].get("lazy_affine", None) if self.pending_operations else self.affine
+        return 1 if a is None else int(max(1, len(a) - 1))
 
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):

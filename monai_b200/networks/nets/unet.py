@@ -132,7 +132,10 @@ class UNet(GraphedForward, nn.Module):
             # without a norm (norm=None), with another ordering or with dropout takes the direct path instead
             if isinstance(m, Convolution) and m is not self.model[2]:   # model[2]: the top transposed conv (conv only)
                 adn = getattr(m, "adn", None)
-                if adn is None or not isinstance(getattr(adn, "N", None), nn.InstanceNorm3d) or hasattr(adn, "D"):
+                if adn is None or not isinstance(getattr(adn, "N", None), nn.InstanceNorm3d):
+                    return False
+                drop = getattr(adn, "D", None)   # Dropout(p=0) / eval-mode dropout is the identity; an active one is not on this path
+                if drop is not None and getattr(drop, "p", 0.0) > 0 and drop.training:
                     return False
         return all(isinstance(m, (nn.PReLU, nn.LeakyReLU, nn.ReLU)) for m in self.modules() if type(m).__module__.startswith("torch.nn.modules.activation"))
 

@@ -17,7 +17,7 @@ from .. import _kernels as K
 from ..data.meta_tensor import rewrap
 from .transform import MapTransform, Transform
 
-__all__ = ["Activations", "Activationsd", "AsDiscrete", "AsDiscreted"]
+__all__ = ["Activations", "Activationsd", "AsDiscrete", "AsDiscreted", "Invertd"]
 
 
 def _cuda_plain(img) -> torch.Tensor:
@@ -127,3 +127,79 @@ class AsDiscreted(MapTransform):
         for key in self.key_iterator(d):
             d[key] = self.converter(d[key])
         return d
+
+
+class Invertd(MapTransform):
+    """Apply the inverse of the pre-processing `transform` to model outputs (monai/transforms/post/dictionary.py, `Invertd`):
+    for every key, the prediction takes over the applied operations and the metadata (affine) of `orig_keys`' entry -- the
+    pre-processed image the network saw -- and `transform.inverse` maps it back to the original grid (e.g. the inverse of
+    Spacingd resamples the logits to the image's native spacing).  `nearest_interp=True` (the reference's default) switches
+    the recorded interpolation modes to "nearest" for the inversion; `post_func` runs on the inverted tensor."""
+
+    def __init__(self, keys, transform, orig_keys=None, meta_keys=None, orig_meta_keys=None, meta_key_postfix: str = "meta_dict",
+                 nearest_interp: bool | tuple = True, to_tensor: bool | tuple = True, device: Any = None, post_func: Callable | tuple | None = None,
+                 allow_missing_keys: bool = False) -> None:
+        super().__init__(keys, allow_missing_keys)
+        if not hasattr(transform, "inverse"):
+            raise ValueError("transform is not invertible, can't invert transform for the data.")
+        self.transform = transform
+        n = len(self.keys)
+        rep = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * n  # noqa: E731
+        self.orig_keys = rep(orig_keys) if orig_keys is not None else self.keys
+        self.nearest_interp, self.to_tensor, self.device, self.post_func = rep(nearest_interp), rep(to_tensor), rep(device), rep(post_func)
+
+    @staticmethod
+    def _to_nearest(ops: list) -> list:
+        """convert_applied_interp_mode(trans_info, mode="nearest", align_corners=None) of monai/transforms/utils.py."""
+        import copy
+
+        out = copy.deepcopy(ops)
+        for op in out:
+            tgt = op.get("extra_info", op)
+            if isinstance(tgt, dict) and "mode" in tgt and str(tgt["mode"]).lower() in ("bilinear", "trilinear", "linear", "bicubic", "nearest"):
+                tgt["mode"] = "nearest"
+                if "align_corners" in tgt:
+                    tgt["align_corners"] = "none"
+        return out
+
+    def __call__(self, data: Mapping[Hashable, Any]) -> dict:
+        import copy
+
+        from ..data.meta_tensor import MetaTensor, is_meta
+
+        d = dict(data)
+        for i, key in enumerate(self.key_iterator(d)):
+            orig_key = self.orig_keys[i]
+            if orig_key not in d or not is_meta(d[orig_key]) or not is_meta(d[key]):
+                # the reference skips (with this warning) entries whose transform information is not available: plain-tensor
+                # predictions without a trace entry, or a missing pre-processed MetaTensor (post/dictionary.py:677-686)
+                import warnings
+
+                warnings.warn(f"transform info of `{orig_key}` is not available or no InvertibleTransform applied.")
+                continue
+            ops = list(d[orig_key].applied_operations)
+            if self.nearest_interp[i]:
+                ops = self._to_nearest(ops)
+            src = d[key]
+            t = src.detach() if isinstance(src, torch.Tensor) else torch.as_tensor(src)
+            inputs = MetaTensor(t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t)
+            inputs.meta = copy.deepcopy(d[orig_key].meta)
+            inputs.applied_operations = copy.deepcopy(ops)
+            inverted = _inverse_allow_missing(self.transform, {orig_key: inputs})[orig_key]
+            if self.device[i] is not None:
+                inverted = inverted.to(self.device[i])
+            d[key] = self.post_func[i](inverted) if callable(self.post_func[i]) else inverted
+        return d
+
+
+def _inverse_allow_missing(transform, data: dict) -> dict:
+    """transform.inverse(data) with `allow_missing_keys` switched on for every dictionary member (allow_missing_keys_mode)."""
+    members = list(getattr(transform, "transforms", [transform]))
+    saved = [(m, m.allow_missing_keys) for m in members if hasattr(m, "allow_missing_keys")]
+    try:
+        for m, _ in saved:
+            m.allow_missing_keys = True
+        return transform.inverse(data)
+    finally:
+        for m, v in saved:
+            m.allow_missing_keys = v

@@ -50,6 +50,17 @@ def _fall_back(user, default) -> tuple[int, ...]:
     return tuple(int(u) if (u is not None and u > 0) else int(d) for u, d in zip(user, default))
 
 
+def _pop_applied(data, cls_name: str) -> dict:
+    """Pop the most recent applied operation of `data` and check that it was recorded by `cls_name` (inverse.py:300-360)."""
+    if not is_meta(data) or not getattr(data, "applied_operations", None):
+        raise RuntimeError(f"{cls_name}.inverse needs a MetaTensor that went through the forward transform (no applied operations found)")
+    op = data.applied_operations[-1]
+    if op.get("class") != cls_name:
+        raise RuntimeError(f"Error {cls_name} getting the most recently applied invertible transform {op.get('class')}.")
+    data.applied_operations.pop()
+    return op
+
+
 def _resample(img: torch.Tensor, mat: np.ndarray, r: int, out_shape: Sequence[int], mode, padding_mode, align_corners: bool) -> torch.Tensor:
     """img [C, *spatial(r)] (CUDA) -> float32 [C, *out_shape] through the 3-D kernel (leading singleton axes for r < 3)."""
     if not img.is_cuda:
@@ -73,16 +84,24 @@ class SpatialResample(Transform):
     """Resample to a destination affine / shape (spatial/array.py:122-253; functional.py:68-184)."""
 
     def __init__(self, mode="bilinear", padding_mode="border", align_corners: bool = False, dtype=np.float64, lazy: bool = False):
-        if lazy:
-            raise NotImplementedError("lazy resampling is not part of the monai_b200 hot path yet")
-        self.mode, self.padding_mode, self.align_corners, self.dtype = mode, padding_mode, align_corners, dtype
+        self.mode, self.padding_mode, self.align_corners, self.dtype, self.lazy = mode, padding_mode, align_corners, dtype, lazy
+        self._trace = True
+
+    def inverse(self, data):
+        """Resample back to the grid the forward call started from (spatial/array.py:238-253)."""
+        op = _pop_applied(data, "SpatialResample")
+        ex = op["extra_info"]
+        inv = SpatialResample(mode=ex["mode"], padding_mode=ex["padding_mode"], align_corners=bool(ex["align_corners"]) if ex["align_corners"] not in (None, "none") else False, dtype=self.dtype)
+        inv._trace = False
+        return inv(data, dst_affine=ex["src_affine"], spatial_size=op["orig_size"])
 
     def __call__(self, img, dst_affine=None, spatial_size=None, mode=None, padding_mode=None, align_corners=None, dtype=None, lazy=None):
         align = self.align_corners if align_corners is None else align_corners
+        lazy_ = self.lazy if lazy is None else lazy
         src_affine_full = get_affine(img)
         if src_affine_full is None:
             src_affine_full = torch.eye(4, dtype=torch.float64)
-        original_shape = tuple(img.shape[1:])
+        original_shape = tuple(img.peek_pending_shape()) + tuple(img.shape[1 + len(img.peek_pending_shape()):]) if is_meta(img) and getattr(img, "pending_operations", None) else tuple(img.shape[1:])
         rank = min(len(img.shape) - 1, src_affine_full.shape[0] - 1, 3)
         if (not isinstance(spatial_size, int) or spatial_size != -1) and spatial_size is not None:
             rank = min(len(tuple(spatial_size)), 3)
@@ -104,6 +123,12 @@ class SpatialResample(Transform):
         )
         info = {"class": type(self).__name__, "orig_size": original_shape, "extra_info": {"src_affine": src_affine, "align_corners": align,
                 "mode": getattr(mode or self.mode, "value", mode or self.mode), "padding_mode": getattr(padding_mode or self.padding_mode, "value", padding_mode or self.padding_mode)}}
+        if not self._trace:
+            info = None
+        if lazy_:   # record the operation, leave the voxels alone (spatial/functional.py:138-150)
+            from .lazy import push_pending
+
+            return push_pending(img, info or {"class": type(self).__name__}, xform, sp)
         new_affine = None
         if is_meta(img):
             # track_transform_meta: affine <- affine @ xform (the voxel->world map of the resampled grid)
@@ -137,8 +162,12 @@ class Spacing(Transform):
                 raise ValueError(f"min_pixdim {self.min_pixdim} must be positive, smaller than max {self.max_pixdim}.")
         self.sp_resample = SpatialResample(mode=mode, padding_mode=padding_mode, align_corners=align_corners, dtype=dtype, lazy=lazy)
 
+    def inverse(self, data):
+        """spatial/array.py:545-546: the inverse of the SpatialResample this transform ran."""
+        return self.sp_resample.inverse(data)
+
     def __call__(self, data_array, mode=None, padding_mode=None, align_corners=None, dtype=None, scale_extent=None, output_spatial_shape=None, lazy=None):
-        original_shape = tuple(data_array.shape[1:])
+        original_shape = tuple(data_array.peek_pending_shape()) if is_meta(data_array) and getattr(data_array, "pending_operations", None) else tuple(data_array.shape[1:])
         sr = len(original_shape)
         if sr <= 0:
             raise ValueError(f"data_array must have at least one spatial dimension, got {original_shape}.")
@@ -167,8 +196,11 @@ class Spacing(Transform):
         output_shape, offset = U.compute_shape_offset(original_shape, affine_, new_affine, scale_extent)
         new_affine[:sr, -1] = offset[:sr]
         actual_shape = list(output_shape) if output_spatial_shape is None else output_spatial_shape
+        lazy_ = self.sp_resample.lazy if lazy is None else lazy
         out = self.sp_resample(data_array, dst_affine=new_affine, spatial_size=actual_shape, mode=mode, padding_mode=padding_mode,
-                               align_corners=align_corners, dtype=dtype)
+                               align_corners=align_corners, dtype=dtype, lazy=lazy_)
+        if lazy_:
+            return out
         if self.recompute_affine and is_meta(out):
             # scale_affine(original, actual) (monai/transforms/utils.py): centre-preserving rescale of the index grid
             r = len(original_shape)
@@ -193,26 +225,42 @@ class Spacingd(MapTransform):
         self.mode, self.padding_mode, self.align_corners, self.dtype, self.scale_extent = rep(mode), rep(padding_mode), rep(align_corners), rep(dtype), rep(scale_extent)
         self.ensure_same_shape = ensure_same_shape
 
+    def inverse(self, data: Mapping[Hashable, Any]) -> dict:
+        d = dict(data)
+        for key in self.key_iterator(d):
+            d[key] = self.spacing_transform.inverse(d[key])
+        return d
+
+    @property
+    def lazy(self) -> bool:
+        return self.spacing_transform.sp_resample.lazy
+
+    @lazy.setter
+    def lazy(self, v: bool) -> None:
+        self.spacing_transform.sp_resample.lazy = bool(v)
+
     def __call__(self, data: Mapping[Hashable, Any], lazy=None) -> dict:
         d = dict(data)
         _init_shape, _pixdim, should_match = None, None, False
         output_shape_k = None
+        lazy_ = self.lazy if lazy is None else lazy
         for i, key in enumerate(self.key_iterator(d)):
             idx = self.keys.index(key)
             if self.ensure_same_shape and is_meta(d[key]):
                 # the reference reuses the first key's output shape only for keys with the same input shape AND the same
                 # affine-derived spacing (monai/transforms/spatial/dictionary.py:500-512)
                 pix_k = U.affine_to_spacing(np.asarray(get_affine(d[key]), dtype=np.float64), len(d[key].shape) - 1)
+                shp_k = tuple(d[key].peek_pending_shape()) if hasattr(d[key], "peek_pending_shape") else tuple(d[key].shape[1:])
                 if _init_shape is None:
-                    _init_shape, _pixdim = tuple(d[key].shape[1:]), pix_k
+                    _init_shape, _pixdim = shp_k, pix_k
                 else:
-                    should_match = tuple(d[key].shape[1:]) == _init_shape and bool(np.allclose(_pixdim, pix_k, atol=1e-3))
+                    should_match = shp_k == _init_shape and bool(np.allclose(_pixdim, pix_k, atol=1e-3))
             d[key] = self.spacing_transform(
                 d[key], mode=self.mode[idx], padding_mode=self.padding_mode[idx], align_corners=self.align_corners[idx], dtype=self.dtype[idx],
-                scale_extent=self.scale_extent[idx], output_spatial_shape=output_shape_k if should_match else None,
+                scale_extent=self.scale_extent[idx], output_spatial_shape=output_shape_k if should_match else None, lazy=lazy_,
             )
             if output_shape_k is None:
-                output_shape_k = tuple(d[key].shape[1:])
+                output_shape_k = tuple(d[key].peek_pending_shape()) if lazy_ else tuple(d[key].shape[1:])
         return d
 
 
@@ -422,7 +470,18 @@ class RandAffine(RandomizableTransform):
         RandomizableTransform.__init__(self, prob)
         self.rand_affine_grid = RandAffineGrid(rotate_range, shear_range, translate_range, scale_range, device=device)
         self.resampler = Resample(device=device)
-        self.spatial_size, self.mode, self.padding_mode, self.cache_grid = spatial_size, mode, padding_mode, cache_grid
+        self.spatial_size, self.mode, self.padding_mode, self.cache_grid, self.lazy = spatial_size, mode, padding_mode, cache_grid, lazy
+
+    def inverse(self, data):
+        """spatial/array.py:2545-2577: resample with the inverse of the recorded matrix back to the original size."""
+        op = _pop_applied(data, "RandAffine")
+        if not op.get("do_resampling", True):
+            return data
+        orig_size = tuple(int(v) for v in op["orig_size"])
+        inv = np.linalg.inv(np.asarray(op["affine"], dtype=np.float64))
+        r = len(orig_size)
+        out = self.resampler(data, grid=AffineSpec(inv, orig_size), mode=op["mode"], padding_mode=op["padding_mode"])
+        return rewrap(out.as_subclass(torch.Tensor) if type(out) is not torch.Tensor else out, data, _update_affine(data, inv, tuple(data.shape[1 : 1 + r]), orig_size))
 
     def set_random_state(self, seed=None, state=None):
         self.rand_affine_grid.set_random_state(seed, state)
@@ -441,7 +500,8 @@ class RandAffine(RandomizableTransform):
     def __call__(self, img, spatial_size=None, mode=None, padding_mode=None, randomize: bool = True, grid=None, lazy=None):
         if randomize:
             self.randomize()
-        ori = tuple(img.shape[1:])
+        lazy_ = self.lazy if lazy is None else lazy
+        ori = tuple(img.peek_pending_shape()) if is_meta(img) and getattr(img, "pending_operations", None) else tuple(img.shape[1:])
         r = min(len(ori), 3)
         sp = _fall_back(self.spatial_size if spatial_size is None else spatial_size, ori[:r])
         do_resampling = self._do_transform or (sp != tuple(ori[:r]))
@@ -452,13 +512,21 @@ class RandAffine(RandomizableTransform):
             if self._do_transform:
                 grid = AffineSpec(self.rand_affine_grid.matrix(r, randomize=randomize), sp)
         affine = self.rand_affine_grid.get_transformation_matrix()
+        a = np.asarray(grid.affine)
+        info = {"class": "RandAffine", "affine": a, "rand_affine_matrix": affine, "orig_size": ori[:r], "mode": getattr(_mode_, "value", _mode_),
+                "padding_mode": getattr(_pad_, "value", _pad_), "do_resampling": bool(do_resampling)}
+        if lazy_:   # affine_func(lazy=True): pending matrix = centre shifts around the centred affine (Affine.compute_w_affine)
+            from .lazy import push_pending
+
+            t_src, t_dst = np.eye(r + 1), np.eye(r + 1)
+            t_src[:r, -1] = (np.asarray(ori[:r], dtype=np.float64) - 1) / 2.0
+            t_dst[:r, -1] = -(np.asarray(sp, dtype=np.float64) - 1) / 2.0
+            return push_pending(img, info, t_src @ U.to_affine_nd(r, a) @ t_dst, sp)
         if not do_resampling:
             t = img.as_subclass(torch.Tensor) if type(img) is not torch.Tensor else img
-            return rewrap(t.to(torch.float32), img)
+            return rewrap(t.to(torch.float32), img, None, info)
         out = self.resampler(img, grid=grid, mode=_mode_, padding_mode=_pad_)
-        a = np.asarray(grid.affine)
-        return rewrap(out.as_subclass(torch.Tensor) if type(out) is not torch.Tensor else out, img, _update_affine(img, a, ori, sp),
-                      {"class": "RandAffine", "affine": a, "rand_affine_matrix": affine})
+        return rewrap(out.as_subclass(torch.Tensor) if type(out) is not torch.Tensor else out, img, _update_affine(img, a, ori, sp), info)
 
 
 class RandAffined(RandomizableTransform, MapTransform):
@@ -479,15 +547,30 @@ class RandAffined(RandomizableTransform, MapTransform):
         super().set_random_state(seed, state)
         return self
 
+    def inverse(self, data: Mapping[Hashable, Any]) -> dict:
+        d = dict(data)
+        for key in self.key_iterator(d):
+            d[key] = self.rand_affine.inverse(d[key])
+        return d
+
+    @property
+    def lazy(self) -> bool:
+        return self.rand_affine.lazy
+
+    @lazy.setter
+    def lazy(self, v: bool) -> None:
+        self.rand_affine.lazy = bool(v)
+
     def __call__(self, data: Mapping[Hashable, Any], lazy=None) -> dict:
         d = dict(data)
         keys = [k for k in self.key_iterator(d)]
         if not keys:
             return d
+        lazy_ = self.lazy if lazy is None else lazy
         self.randomize(None)
         self.rand_affine.randomize()  # all the keys share the same random affine factor
         item = d[keys[0]]
-        ori = tuple(item.shape[1:])
+        ori = tuple(item.peek_pending_shape()) if is_meta(item) and getattr(item, "pending_operations", None) else tuple(item.shape[1:])
         r = min(len(ori), 3)
         sp = _fall_back(self.rand_affine.spatial_size, ori[:r])
         do_resampling = self._do_transform or (sp != tuple(ori[:r]))
@@ -501,8 +584,8 @@ class RandAffined(RandomizableTransform, MapTransform):
             if do_resampling:
                 # the reference passes randomize=True here too (dictionary.py:1156): the per-key redraw only consumes
                 # RNG state, the shared grid is what is applied
-                d[key] = self.rand_affine(d[key], None, self.mode[idx], self.padding_mode[idx], True, grid)
-            else:
+                d[key] = self.rand_affine(d[key], None, self.mode[idx], self.padding_mode[idx], True, grid, lazy=lazy_)
+            elif not lazy_:
                 t = d[key].as_subclass(torch.Tensor) if type(d[key]) is not torch.Tensor else d[key]
                 d[key] = rewrap(t.to(torch.float32), d[key])
         return d

@@ -64,10 +64,17 @@ class MapTransform(Transform):
 
 class Compose(Randomizable, Transform):
     """Sequential composition (monai/transforms/compose.py); `set_random_state` seeds every randomizable member from
-    this object's stream, as the reference does."""
+    this object's stream, as the reference does.
 
-    def __init__(self, transforms=None) -> None:
+    `lazy=True` runs the lazy-capable members (those with a `lazy` attribute: Spacing(d), RandAffine(d), SpatialResample)
+    without resampling -- they record their matrix -- and executes the composed matrix in ONE resample right before the first
+    member that is not lazy-capable and at the end (monai/transforms/compose.py:226-270, lazy/functional.py); `lazy=None`
+    honours each member's own flag; `overrides` = {key: {"mode": ..., "padding_mode": ...}} (or a flat dict for tensors).
+    `inverse` applies the members' inverses in reverse order."""
+
+    def __init__(self, transforms=None, lazy: bool | None = False, overrides: dict | None = None) -> None:
         self.transforms = tuple(transforms) if isinstance(transforms, (list, tuple)) else ((transforms,) if transforms is not None else ())
+        self.lazy, self.overrides = lazy, overrides
         self.set_random_state(seed=int(np.random.randint(MAX_SEED, dtype="uint32")) if False else None)
 
     def set_random_state(self, seed: int | None = None, state: np.random.RandomState | None = None):
@@ -77,7 +84,27 @@ class Compose(Randomizable, Transform):
                 t.set_random_state(seed=int(self.R.randint(MAX_SEED, dtype="uint32")))
         return self
 
-    def __call__(self, data):
+    def __call__(self, data, lazy: bool | None = None):
+        from .lazy import apply_pending_transforms
+
+        lazy_ = self.lazy if lazy is None else lazy
+        if lazy_ is False:
+            for t in self.transforms:
+                data = t(data)
+            return data
         for t in self.transforms:
-            data = t(data)
+            capable = hasattr(t, "lazy")
+            run_lazy = capable and (lazy_ is True or bool(getattr(t, "lazy", False)))
+            if run_lazy:
+                data = t(data, lazy=True)
+            else:
+                # a member that needs real voxels: execute what is pending on the entries it reads first
+                data = apply_pending_transforms(data, getattr(t, "keys", None) if isinstance(t, MapTransform) else None, self.overrides)
+                data = t(data, lazy=False) if capable else t(data)
+        return apply_pending_transforms(data, None, self.overrides)
+
+    def inverse(self, data):
+        for t in reversed(self.transforms):
+            if hasattr(t, "inverse"):
+                data = t.inverse(data)
         return data

@@ -266,6 +266,40 @@ def grid_pull_ref():
     save("grid_pull.npz", **out)
 
 
+def lazy_inverse():
+    """Lazy resampling (Compose(lazy=True): Spacingd o RandAffined composed into one resample) and the inversion of Spacingd through
+    Invertd, both from the real reference."""
+    from monai.data import MetaTensor
+    from monai.transforms import Compose, Invertd, RandAffined, Spacingd
+
+    out = {}
+    g = torch.Generator().manual_seed(61)
+    img = torch.rand((1, 20, 24, 18), generator=g)
+    aff = np.diag([1.25, 1.25, 1.25, 1.0])
+
+    def pipe(lazy):
+        c = Compose([Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear"),
+                     RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border")],
+                    lazy=lazy)
+        c.transforms[1].set_random_state(seed=0)
+        return c
+
+    for tag, lazy in (("eager", False), ("lazy", True)):
+        y = pipe(lazy)({"image": MetaTensor(img.clone(), affine=torch.as_tensor(aff))})["image"]
+        out[f"{tag}.y"], out[f"{tag}.affine"] = y.numpy(), np.asarray(y.affine)
+        out[f"{tag}.n_applied"] = np.array(len(y.applied_operations))
+    out["x"], out["x_affine"] = img.numpy(), aff
+    # inversion: pre-process, "predict" on the 1 mm grid, bring the prediction back to the 1.25 mm grid
+    pre = Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear")
+    d = pre({"image": MetaTensor(img.clone(), affine=torch.as_tensor(aff))})
+    pred = MetaTensor(torch.cat([d["image"].as_tensor() * 2.0, 1.0 - d["image"].as_tensor()], 0))   # network outputs are MetaTensors
+    for tag, nearest in (("nearest", True), ("bilinear", False)):
+        inv = Invertd(keys=["pred"], transform=pre, orig_keys=["image"], nearest_interp=nearest)({"image": d["image"], "pred": pred.clone()})["pred"]
+        out[f"inv.{tag}"], out[f"inv.{tag}.affine"] = inv.numpy(), np.asarray(inv.affine)
+    out["pre.y"], out["pred"] = d["image"].numpy(), pred.numpy()
+    save("lazy_inverse.npz", **out)
+
+
 def transforms():
     from monai.data import MetaTensor
     from monai.transforms import GaussianSmooth, RandAffined, Spacing, Spacingd
@@ -444,6 +478,6 @@ def unit_goldens():
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "buffered", "resampler", "grid_pull_ref", "transforms", "post", "patch", "unit_goldens"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "buffered", "resampler", "grid_pull_ref", "lazy_inverse", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

@@ -150,7 +150,7 @@ def test_fused_blend_resample_equals_blend_then_spatial_resample():
         fused = sliding_window_inference_resampled(x.to(DEV), roi, 3, _pred, m, out_shape, ov, "gaussian", interp_mode=interp, resample_padding_mode=pad)
         assert tuple(fused.shape) == (1, 3, *out_shape)
         blended = sliding_window_inference(x.to(DEV), roi, 3, _pred, ov, "gaussian")
-        two_step = K.resample_affine(blended[0], out_shape, m.reshape(-1), 1 if interp == "bilinear" else 0, 1 if pad == "border" else 0, False)
+        two_step = K.resample_affine(blended[0], out_shape, np.asarray(m)[:3].reshape(-1), 1 if interp == "bilinear" else 0, 1 if pad == "border" else 0, False)
         if interp == "bilinear":
             np.testing.assert_allclose(fused[0].cpu().numpy(), two_step.cpu().numpy(), rtol=2e-5, atol=2e-5, err_msg=f"{interp} {pad}")
         want_b = osw.sliding_window_inference(x.numpy(), roi, 3, lambda a: _pred(torch.from_numpy(a)).numpy(), ov, "gaussian")

@@ -122,3 +122,38 @@ def test_post_transforms_match_reference_fixture(golden_dir):
     with pytest.raises(ValueError, match="deprecated"):
         AsDiscrete(to_onehot=True)
     np.testing.assert_allclose(Activations(other=torch.tanh)(logits).cpu().numpy(), np.tanh(g["logits"]), rtol=1e-6, atol=1e-6)
+
+
+def test_lazy_resampling_and_invertd_match_the_real_reference(golden_dir):
+    """f1: Compose(lazy=True) -- Spacingd o RandAffined as ONE resample -- and f2: Invertd(Spacingd) of a prediction, values
+    against fixtures of the real reference (tests/golden/lazy_inverse.npz)."""
+    from monai_b200.data import MetaTensor
+    from monai_b200.transforms import Compose, Invertd, RandAffined, Spacingd
+
+    g = np.load(os.path.join(golden_dir, "lazy_inverse.npz"))
+
+    def pipe(lazy):
+        c = Compose([Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear"),
+                     RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border")],
+                    lazy=lazy)
+        c.transforms[1].set_random_state(seed=0)
+        return c
+
+    for tag, lazy in (("eager", False), ("lazy", True)):
+        x = MetaTensor(torch.from_numpy(g["x"]).to(DEV), affine=torch.as_tensor(g["x_affine"]))
+        y = pipe(lazy)({"image": x})["image"]
+        np.testing.assert_allclose(y.cpu().numpy(), g[f"{tag}.y"], rtol=1e-4, atol=1e-4, err_msg=tag)
+        np.testing.assert_allclose(np.asarray(y.affine), g[f"{tag}.affine"], atol=1e-6)
+    pre = Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear")
+    d = pre({"image": MetaTensor(torch.from_numpy(g["x"]).to(DEV), affine=torch.as_tensor(g["x_affine"]))})
+    np.testing.assert_allclose(d["image"].cpu().numpy(), g["pre.y"], rtol=1e-4, atol=1e-4)
+    pred = MetaTensor(torch.from_numpy(g["pred"]).to(DEV))
+    for tag, nearest in (("nearest", True), ("bilinear", False)):
+        inv = Invertd(keys=["pred"], transform=pre, orig_keys=["image"], nearest_interp=nearest)({"image": d["image"], "pred": pred})["pred"]
+        assert tuple(inv.shape) == tuple(g[f"inv.{tag}"].shape)
+        diff = np.abs(inv.cpu().numpy() - g[f"inv.{tag}"])
+        if nearest:
+            assert (diff > 1e-4).mean() < 2e-3, tag
+        else:
+            assert diff.max() < 2e-4, (tag, diff.max())
+        np.testing.assert_allclose(np.asarray(inv.affine), g[f"inv.{tag}.affine"], atol=1e-6)

@@ -133,3 +133,44 @@ def test_spacingd_shapes_and_affines_of_the_reference_unit_tests(monkeypatch):
             want = (2, 1, 19) if key == "seg1" else shape
             assert tuple(res[key].shape) == want, (kw, key, tuple(res[key].shape))
         np.testing.assert_allclose(res["image"].affine.numpy(), affine, atol=1e-9, err_msg=str(kw))
+
+
+def test_lazy_compose_runs_one_resample_and_matches_the_reference_affine(monkeypatch, golden_dir):
+    """Compose(lazy=True): Spacingd o RandAffined record their matrices and ONE resample runs with the composed matrix; shape,
+    affine and the number of applied operations equal the real reference's (fixture: tests/golden/lazy_inverse.npz)."""
+    import os
+
+    import numpy as np
+    import torch
+
+    import monai_b200.transforms.spatial as S
+    from monai_b200.data import MetaTensor
+    from monai_b200.transforms import Compose, RandAffined, Spacingd
+
+    g = np.load(os.path.join(golden_dir, "lazy_inverse.npz"))
+    calls = []
+
+    def stub(img, mat, r, out_shape, mode, padding_mode, align):
+        calls.append((np.asarray(mat).copy(), tuple(out_shape), mode, padding_mode))
+        return torch.zeros((img.shape[0], *out_shape))
+
+    monkeypatch.setattr(S, "_resample", stub)
+
+    def pipe(lazy):
+        c = Compose([Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear"),
+                     RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border")],
+                    lazy=lazy)
+        c.transforms[1].set_random_state(seed=0)
+        return c
+
+    x = MetaTensor(torch.from_numpy(g["x"]), affine=torch.as_tensor(g["x_affine"]))
+    y = pipe(True)({"image": x})["image"]
+    assert len(calls) == 1, "lazy mode must resample once"
+    assert tuple(y.shape) == tuple(g["lazy.y"].shape) and calls[0][1] == tuple(g["lazy.y"].shape[1:])
+    assert calls[0][2] == "bilinear" and calls[0][3] == "border"
+    np.testing.assert_allclose(y.affine.numpy(), g["lazy.affine"], atol=1e-6)
+    assert len(y.applied_operations) == int(g["lazy.n_applied"]) and not y.pending_operations
+    calls.clear()
+    y2 = pipe(False)({"image": MetaTensor(torch.from_numpy(g["x"]), affine=torch.as_tensor(g["x_affine"]))})["image"]
+    assert len(calls) == 2
+    np.testing.assert_allclose(y2.affine.numpy(), g["eager.affine"], atol=1e-6)
