@@ -196,9 +196,10 @@ class Spacing(Transform):
         output_shape, offset = U.compute_shape_offset(original_shape, affine_, new_affine, scale_extent)
         new_affine[:sr, -1] = offset[:sr]
         actual_shape = list(output_shape) if output_spatial_shape is None else output_spatial_shape
-        lazy_ = self.sp_resample.lazy if lazy is None else lazy
+        lazy_ = bool(getattr(self.sp_resample, "lazy", False)) if lazy is None else bool(lazy)
+        kw = {"lazy": True} if lazy_ else {}
         out = self.sp_resample(data_array, dst_affine=new_affine, spatial_size=actual_shape, mode=mode, padding_mode=padding_mode,
-                               align_corners=align_corners, dtype=dtype, lazy=lazy_)
+                               align_corners=align_corners, dtype=dtype, **kw)
         if lazy_:
             return out
         if self.recompute_affine and is_meta(out):
