@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
   if (threadIdx.x == 0) {
     tc::mbar_init(qk_full, 1); tc::mbar_init(qk_empty, 1); tc::mbar_init(v_full, 1); tc::mbar_init(pv_done, 1);
     tc::mbar_init(o_empty, 128); tc::mbar_init(init_done, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128); tc::mbar_init(&p_full[i], 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 256); tc::mbar_init(&p_full[i], 256); }
     tc::fence_barrier_init();
   }
   // zero Q / K / V (rows the bulk copies never write must be finite), the ones column, and the identity (staged in the P region)
@@ -171,83 +171,112 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
       tc::mma_commit(init_done);
     }
     __syncwarp();
-    int it = 0;
-    for (long long f = lo; f < hi; ++f, ++it) {
-      const uint32_t ph = (uint32_t)(it & 1);
-      tc::mbar_wait(qk_full, ph);
-      tc::fence_after_sync();
-      for (int hf = 0; hf < 2; ++hf) {
-        tc::mbar_wait(&s_empty[hf], ph ^ 1);        // the softmax threads have read this half of the previous tile
-        tc::fence_after_sync();
-        const uint32_t ts = tm + hf * kAtColS1;
-        const uint64_t qd = tc::make_desc_kmajor_noswz(q_a, 2048, 128);
-        const uint64_t kd = tc::make_desc_kmajor_noswz(k_a + hf * NH * 16, kAtKChunk, 128);
-        if (leader) tc::mma_f16_ss(ts, qd, kd, idesc_s, 0u);
-        for (int s = 0; s < 8; ++s) {
-          const uint64_t bd = tc::make_desc_kmajor_noswz(b_a + (2 * s) * n_pad * 16 + hf * NH * 16, n_pad * 16, 128);
-          if (leader) tc::mma_f16_ts(ts, tm + kAtColI + 8 * s, bd, idesc_s, 1u);
-        }
-        if (leader) tc::mma_commit(&s_full[hf]);
-        __syncwarp();
+    // S = Q K^T + I B' for one key half of the tile whose Q / K / bias are in shared memory
+    auto issue_s = [&](int hf) {
+      const uint32_t ts = tm + hf * kAtColS1;
+      const uint64_t qd = tc::make_desc_kmajor_noswz(q_a, 2048, 128);
+      const uint64_t kd = tc::make_desc_kmajor_noswz(k_a + hf * NH * 16, kAtKChunk, 128);
+      if (leader) tc::mma_f16_ss(ts, qd, kd, idesc_s, 0u);
+      for (int s = 0; s < 8; ++s) {
+        const uint64_t bd = tc::make_desc_kmajor_noswz(b_a + (2 * s) * n_pad * 16 + hf * NH * 16, n_pad * 16, 128);
+        if (leader) tc::mma_f16_ts(ts, tm + kAtColI + 8 * s, bd, idesc_s, 1u);
       }
+      if (leader) tc::mma_commit(&s_full[hf]);
+      __syncwarp();
+    };
+    // O (+)= P V for one key half
+    auto issue_pv = [&](int hf) {
+      for (int s = 0; s < NH / 16; ++s) {
+        const int ks = hf * (NH / 16) + s;
+        const uint64_t pd = tc::make_desc_kmajor_noswz(p_a + ks * 4096, 2048, 128);
+        // MN-major B: 8 keys x 16 B (8 dims) per core matrix, next 8 keys +128 B (LBO), next 8 dims +chunk (SBO)
+        const uint64_t vd = tc::make_desc_kmajor_noswz(v_a + ks * 256, 128, kAtKChunk);
+        if (leader) tc::mma_f16_ss(tm + kAtColO, pd, vd, idesc_pv, (hf | s) != 0 ? 1u : 0u);
+      }
+    };
+    // Software pipeline across tiles: the S MMAs of tile i+1 are issued as soon as the softmax threads have drained the
+    // matching half of tile i, i.e. they run on the tensor pipe while the softmax of tile i is still exponentiating the
+    // other half -- the issue order is  PV0(i), S0(i+1), PV1(i), S1(i+1).
+    const long long ntile = hi - lo;
+    if (ntile > 0) {
+      tc::mbar_wait(qk_full, 0u);
+      tc::fence_after_sync();
+      issue_s(0);
+      issue_s(1);
       if (leader) tc::mma_commit(qk_empty);
       __syncwarp();
+    }
+    for (long long it = 0; it < ntile; ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const bool more = it + 1 < ntile;
       tc::mbar_wait(v_full, ph);
-      for (int hf = 0; hf < 2; ++hf) {
-        tc::mbar_wait(&p_full[hf], ph);
-        if (hf == 0) tc::mbar_wait(o_empty, ph ^ 1);  // the epilogue has read O of the previous tile
+      tc::mbar_wait(&p_full[0], ph);
+      tc::mbar_wait(o_empty, ph ^ 1);               // the epilogue has read O of the previous tile
+      tc::fence_after_sync();
+      issue_pv(0);
+      if (more) {
+        tc::mbar_wait(qk_full, ph ^ 1);             // Q, K (and bias) of tile it+1 have landed
+        tc::mbar_wait(&s_empty[0], ph);             // every softmax thread has read half 0 of tile it
         tc::fence_after_sync();
-        for (int s = 0; s < NH / 16; ++s) {
-          const int ks = hf * (NH / 16) + s;
-          const uint64_t pd = tc::make_desc_kmajor_noswz(p_a + ks * 4096, 2048, 128);
-          // MN-major B: 8 keys x 16 B (8 dims) per core matrix, next 8 keys +128 B (LBO), next 8 dims +chunk (SBO)
-          const uint64_t vd = tc::make_desc_kmajor_noswz(v_a + ks * 256, 128, kAtKChunk);
-          if (leader) tc::mma_f16_ss(tm + kAtColO, pd, vd, idesc_pv, (hf | s) != 0 ? 1u : 0u);
-        }
+        issue_s(0);
       }
+      tc::mbar_wait(&p_full[1], ph);
+      tc::fence_after_sync();
+      issue_pv(1);
       if (leader) tc::mma_commit(pv_done);
       __syncwarp();
+      if (more) {
+        tc::mbar_wait(&s_empty[1], ph);
+        tc::fence_after_sync();
+        issue_s(1);
+        if (leader) tc::mma_commit(qk_empty);
+        __syncwarp();
+      }
     }
     __syncwarp();
   } else {
     // ===================== softmax + epilogue (warps 2..9) =====================
-    const int hf = (warp - 2) >> 2;           // key half of this thread
+    const int jj = (warp - 2) >> 2;           // the two threads of a query row split the 16-column chunks of each key half
     const int q = warp & 3;                   // TMEM lane quarter
     const int row = q * 32 + lane;
-    const uint32_t ts = tmem_base + ((uint32_t)(q * 32) << 16) + hf * kAtColS1;
-    const uint32_t to = tmem_base + ((uint32_t)(q * 32) << 16) + kAtColO;
-    uint8_t* prow = s_p + (hf * NH / 8) * 2048 + row * 16;
+    const int nchunk = NH / 16;
+    const int c_lo = jj == 0 ? 0 : (nchunk + 1) / 2, c_hi = jj == 0 ? (nchunk + 1) / 2 : nchunk;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t to = tlane + kAtColO;
     int it = 0;
     for (long long f = lo; f < hi; ++f, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      tc::mbar_wait(&s_full[hf], ph);
-      tc::fence_after_sync();
-      // ---- pass 1: exact row maximum over this thread's key half
+      // ---- pass 1: exact row maximum (this thread's chunks of both halves)
       float m = -INFINITY;
-      {
+      for (int hf = 0; hf < 2; ++hf) {
+        tc::mbar_wait(&s_full[hf], ph);
+        tc::fence_after_sync();
+        const uint32_t ts = tlane + hf * kAtColS1;
         uint32_t va[16], vb[16];
-        tc::tmem_ld16(ts, va);
-        for (int c = 0; c < NH; c += 32) {
+        tc::tmem_ld16(ts + c_lo * 16, va);
+        for (int c = c_lo; c < c_hi; c += 2) {
           tc::tmem_ld_wait16(va);
-          if (c + 16 < NH) tc::tmem_ld16(ts + c + 16, vb);
+          if (c + 1 < c_hi) tc::tmem_ld16(ts + (c + 1) * 16, vb);
 #pragma unroll
           for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(va[j]));
-          if (c + 16 < NH) {
+          if (c + 1 < c_hi) {
             tc::tmem_ld_wait16(vb);
-            if (c + 32 < NH) tc::tmem_ld16(ts + c + 32, va);
+            if (c + 2 < c_hi) tc::tmem_ld16(ts + (c + 2) * 16, va);
 #pragma unroll
             for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(vb[j]));
           }
         }
       }
-      s_max[hf * 128 + row] = m;
+      s_max[jj * 128 + row] = m;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      m = fmaxf(m, s_max[(hf ^ 1) * 128 + row]);
+      m = fmaxf(m, s_max[(jj ^ 1) * 128 + row]);
       // P buffer free?  (first tile: the identity staged there has been copied to TMEM)
       if (it == 0) tc::mbar_wait(init_done, 0u);
       else tc::mbar_wait(pv_done, (uint32_t)((it - 1) & 1));
-      // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs
-      {
+      // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs, half by half
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint32_t ts = tlane + hf * kAtColS1;
+        uint8_t* prow = s_p + (hf * NH / 8) * 2048 + row * 16;
         uint32_t va[16], vb[16];
         auto emit = [&](const uint32_t (&v)[16], int c) {
           uint4 u0, u1;
@@ -259,26 +288,26 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
           u1.y = exp2_pack(__uint_as_float(v[10]), __uint_as_float(v[11]), m);
           u1.z = exp2_pack(__uint_as_float(v[12]), __uint_as_float(v[13]), m);
           u1.w = exp2_pack(__uint_as_float(v[14]), __uint_as_float(v[15]), m);
-          *reinterpret_cast<uint4*>(prow + (c / 8) * 2048) = u0;
-          *reinterpret_cast<uint4*>(prow + (c / 8 + 1) * 2048) = u1;
+          *reinterpret_cast<uint4*>(prow + (2 * c) * 2048) = u0;
+          *reinterpret_cast<uint4*>(prow + (2 * c + 1) * 2048) = u1;
         };
-        tc::tmem_ld16(ts, va);
-        for (int c = 0; c < NH; c += 32) {
+        tc::tmem_ld16(ts + c_lo * 16, va);
+        for (int c = c_lo; c < c_hi; c += 2) {
           tc::tmem_ld_wait16(va);
-          if (c + 16 < NH) tc::tmem_ld16(ts + c + 16, vb);
+          if (c + 1 < c_hi) tc::tmem_ld16(ts + (c + 1) * 16, vb);
           emit(va, c);
-          if (c + 16 < NH) {
+          if (c + 1 < c_hi) {
             tc::tmem_ld_wait16(vb);
-            if (c + 32 < NH) tc::tmem_ld16(ts + c + 32, va);
-            emit(vb, c + 16);
+            if (c + 2 < c_hi) tc::tmem_ld16(ts + (c + 2) * 16, va);
+            emit(vb, c + 1);
           }
         }
+        tc::fence_proxy_async();       // P (generic-proxy stores) -> visible to the tensor core
+        tc::fence_before_sync();       // this thread's TMEM reads of this S half are complete
+        tc::mbar_arrive(&p_full[hf]);
+        tc::mbar_arrive(&s_empty[hf]);
       }
-      tc::fence_proxy_async();       // P (generic-proxy stores) -> visible to the tensor core
-      tc::fence_before_sync();       // this thread's TMEM reads of S are complete
-      tc::mbar_arrive(&p_full[hf]);
-      tc::mbar_arrive(&s_empty[hf]);
-      if (hf == 0) {
+      if (jj == 0) {
         // ---- epilogue: O / rowsum -> fp16 NC8
         const AttnTile t = attn_decode(p, f);
         tc::mbar_wait(pv_done, ph);

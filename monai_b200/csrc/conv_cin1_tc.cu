@@ -104,25 +104,39 @@ __global__ void __launch_bounds__(288, 1) conv_cin1_tc_kernel(Cin1TcParams p) {
     const int r = threadIdx.x;                     // GEMM row: h = r >> 3, w = r & 7 inside the 16 x 8 patch
     const int rh = (r >> 3) * STRIDE, rw = (r & 7) * STRIDE;
     const T* xg = reinterpret_cast<const T*>(p.x);
+    // The raw halo patch of a tile is fetched into REGISTERS one tile ahead (all loads of a thread issued back to back, then
+    // left in flight while the im2col of the current tile runs): a load -> convert -> store loop per element had the
+    // producers waiting on one global-memory latency per element (9 in a row per tile) -- slower than the output store.
+    constexpr int kHV = (Cfg::kHaloElems + 127) / 128;
+    __half hv[kHV];
+    auto fetch = [&](long long t) {
+      const ConvTile c = conv_tile<BD>(p.e, t);
+      const int z0 = c.d0 * STRIDE - p.pad, y0 = c.h0 * STRIDE - p.pad, x0 = c.w0 * STRIDE - p.pad;
+      const T* xn = xg + (long long)c.n * p.D * p.H * p.W;
+#pragma unroll
+      for (int j = 0; j < kHV; ++j) {
+        const int i = r + j * 128;
+        const int hx = i % Cfg::kHWw, hy = (i / Cfg::kHWw) % Cfg::kHHh, hz = i / (Cfg::kHWw * Cfg::kHHh);
+        const int iz = z0 + hz, iy = y0 + hy, ix = x0 + hx;
+        float v = 0.f;
+        if (i < Cfg::kHaloElems && iz >= 0 && iz < p.D && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = io<T>::ld(xn + ((long long)iz * p.H + iy) * p.W + ix);
+        hv[j] = __float2half_rn(v);
+      }
+    };
+    if ((long long)blockIdx.x < p.e.total_tiles) fetch(blockIdx.x);
     int it = 0;
     for (long long t = blockIdx.x; t < p.e.total_tiles; t += gridDim.x, ++it) {
-      const ConvTile c = conv_tile<BD>(p.e, t);
       const int st = it & 1;
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       tc::mbar_wait(&a_empty[st], ph ^ 1);         // the MMAs that read this stage's A image have completed
       __half* halo = reinterpret_cast<__half*>(smem_h + st * Cfg::kHaloBytes);
-      const int z0 = c.d0 * STRIDE - p.pad, y0 = c.h0 * STRIDE - p.pad, x0 = c.w0 * STRIDE - p.pad;
-      const T* xn = xg + (long long)c.n * p.D * p.H * p.W;
-      for (int i = r; i < Cfg::kHaloElems; i += 128) {
-        const int hx = i % Cfg::kHWw, hy = (i / Cfg::kHWw) % Cfg::kHHh, hz = i / (Cfg::kHWw * Cfg::kHHh);
-        const int iz = z0 + hz, iy = y0 + hy, ix = x0 + hx;
-        float v = 0.f;
-        if (iz >= 0 && iz < p.D && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = io<T>::ld(xn + ((long long)iz * p.H + iy) * p.W + ix);
-        halo[i] = __float2half_rn(v);
-      }
+#pragma unroll
+      for (int j = 0; j < kHV; ++j)
+        if (r + j * 128 < Cfg::kHaloElems) halo[r + j * 128] = hv[j];
       // all 128 producers have written the patch (and, transitively, finished reading the OTHER patch: a thread reaches
       // this barrier of tile i+1 only after its im2col of tile i)
       asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (t + gridDim.x < p.e.total_tiles) fetch(t + gridDim.x);   // next tile's patch: in flight during the im2col below
       uint8_t* a_st = smem_a + st * Cfg::kAStage;
 #pragma unroll
       for (int pl = 0; pl < BD; ++pl) {
