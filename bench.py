@@ -54,6 +54,27 @@ WORKLOADS = {
 }
 
 
+def _quiet_nccl() -> None:
+    """Keep stdout to the single JSON line WITHOUT overriding the caller's NCCL_DEBUG: when the driver sets NCCL_DEBUG (to read the
+    communicator lines), NCCL's log goes to its own file unless a destination is already configured."""
+    if "NCCL_DEBUG" in os.environ:
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "nccl_%h_%p.log"))
+    else:
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json: kernel ->
+    {"dram_bytes_per_launch", "algorithmic_bytes_per_launch", "source"}); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -237,7 +258,7 @@ def run_transforms(args, wl):
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")
+    _quiet_nccl()
     _lib.load()
     dist = None
     if world > 1:
@@ -359,6 +380,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sw-batch", type=int, default=0, help="override the workload's sw_batch_size")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C4 lines appended to the default single-GPU run")
     args = ap.parse_args()
     if os.environ.get("B200_BENCH_WATCHDOG"):
         import faulthandler
@@ -391,7 +413,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
-    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
+    _quiet_nccl()
     _lib.load()
     net = build_net(wl["net"], dev, half=True)
     # capture the network's CUDA graphs (full batch + this rank's remainder batch) BEFORE NCCL starts its helper
@@ -480,6 +502,21 @@ def main():
     step_resident()
     prof = K.profile_stop()
 
+    # correctness of the sharded job, carried in the line: the gathered multi-GPU result against the single-GPU result of the
+    # same volume (rank 0 runs the whole volume alone once, outside every timed region)
+    parity = None
+    if world > 1:
+        y_sh = inferer(x_dev, net).float()
+        if rank == 0:
+            y_one = SlidingWindowInferer(wl["roi"], wl["sw_batch"], wl["overlap"], wl["mode"])(x_dev, net).float()
+            diff = (y_sh - y_one).abs()
+            parity = {"max_abs_diff": float(diff.max()), "max_abs": float(y_one.abs().max()), "mismatch_frac_1e-3": float((diff > 1e-3 * y_one.abs().max()).float().mean()),
+                      "checksum_sharded": float(y_sh.double().sum()), "checksum_single": float(y_one.double().sum())}
+            del y_one, diff
+        del y_sh
+        torch.cuda.synchronize()
+        dist.barrier()
+
     # bytes moved per step, summed over the ranks (each rank uploads its slab rows and downloads its owned rows)
     h2d_total = e2e_bytes[0] if world > 1 else host.numel() * host.element_size()
     d2h_total = out_host.numel() * out_host.element_size() if out_host is not None else 0
@@ -520,11 +557,32 @@ def main():
         "roofline": roofline,
         "kernels": {k: {"ms": round(v["ms"], 4), "n": v["n"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]},
     }
+    if roofline is not None:
+        roofline["traffic"] = ncu_traffic(roofline["kernel"])
+    if parity is not None:
+        line["parity_vs_single_gpu"] = parity
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_leg(wl)
+    if world == 1 and args.workload == "swin_c3" and not args.no_secondary:
+        line["secondary"] = secondary_lines()
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def secondary_lines() -> dict:
+    """BASELINE.json configs[1] (UNet, 256^3) and configs[3] (transform pipeline) measured by this same script in sub-processes, so
+    the driver-visible line carries them too (value, ms_per_step, e2e, roofline, cpu_baseline)."""
+    out = {}
+    for key, extra in (("unet_c2", ["--steps", "10", "--warmup", "3"]), ("transforms_c4", ["--steps", "3", "--warmup", "3"])):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", key, "--no-secondary", *extra], capture_output=True, text=True, timeout=600)
+            js = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            d = json.loads(js[-1])
+            out[key] = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "roofline", "cpu_baseline", "gpu_launches", "kernels")}
+        except Exception as e:  # pragma: no cover - the headline line must survive a failing side measurement
+            out[key] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 if __name__ == "__main__":

@@ -292,6 +292,10 @@ int b200_patch_accumulate(const void* patch, int dtype, long long NC, int pd, in
                           int md, int mh, int mw, int ld, int lh, int lw, void* stream);
 int b200_patch_finalize(float* values, const void* counts, int count_bytes, long long total, void* stream);
 
+/* dst[i] += src[i], float32 (16-byte aligned): folds the partial numerators a peer rank sends into the local accumulators of the
+ * depth-sharded sliding-window job (no reference counterpart: the reference does not shard a volume over GPUs). */
+int b200_add_f32(float* dst, const float* src, long long n, void* stream);
+
 /* 1x1x1 output head (UnetOutBlock, dynunet_block.py:247-267): NC8 fp16 [N][C/8][S][8] -> NCDHW [N][Cout][S]. */
 int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,
                        void* y, int out_dtype, void* stream);

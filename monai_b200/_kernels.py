@@ -365,6 +365,13 @@ def patch_accumulate(patch: torch.Tensor, values: torch.Tensor, counts: torch.Te
           L.stream_ptr(patch.device), nbytes=_nb(patch) + 2.0 * patch.numel() * (4 + counts.element_size()))
 
 
+def add_f32(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst += src for contiguous float32 CUDA tensors of equal size."""
+    if dst.dtype != torch.float32 or src.dtype != torch.float32 or not dst.is_contiguous() or not src.is_contiguous() or dst.numel() != src.numel():
+        raise ValueError("add_f32 needs two contiguous float32 tensors of equal size")
+    _call("add_f32", L.ptr(dst), L.ptr(src), dst.numel(), L.stream_ptr(dst.device), nbytes=3.0 * dst.numel() * 4)
+
+
 def patch_finalize(values: torch.Tensor, counts: torch.Tensor) -> None:
     _call("patch_finalize", L.ptr(values), L.ptr(counts), counts.element_size(), values.numel(), L.stream_ptr(values.device), nbytes=_nb(values, counts) + _nb(values))
 

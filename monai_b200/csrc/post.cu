@@ -157,3 +157,29 @@ extern "C" int b200_channel_post(const void* x, int in_dtype, int C, long long S
   B200_LAUNCH_CHECK("channel_post_kernel");
   return B200_OK;
 }
+
+
+// dst[i] += src[i] (fp32): the add of the partial numerators received from a peer rank in the depth-sharded sliding-window job
+// (monai_b200/parallel/sharded.py; the reference has no multi-GPU form of sliding_window_inference to cite).
+namespace b200 {
+__global__ void __launch_bounds__(256) add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+}  // namespace b200
+
+extern "C" int b200_add_f32(float* dst, const float* src, long long n, void* stream) {
+  B200_REQUIRE(dst && src, "add_f32: null pointer");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0, "add_f32: pointers must be 16-byte aligned");
+  if (n <= 0) return B200_OK;
+  const int blocks = (int)std::min<long long>((n / 4 + 255) / 256 + 1, (long long)b200::num_sms() * 8);
+  b200::add_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+  B200_LAUNCH_CHECK("add_f32_kernel");
+  return B200_OK;
+}

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["ShardPlan", "make_shard_plan", "exchange_partials", "ShardedSlidingWindowInferer"]
+__all__ = ["ShardPlan", "make_shard_plan", "exchange_partials", "allgather_owned", "ShardedSlidingWindowInferer"]
 
 
 @dataclass
@@ -69,9 +69,25 @@ def _intersect(a, b):
     return (lo, hi) if hi > lo else None
 
 
+def _planes(t: torch.Tensor, lo: int, hi: int):
+    """The (batch, channel) pieces of t[:, :, lo:hi]: each is a contiguous block of rows, so it can be sent / received in place."""
+    return [t[b, c, lo:hi] for b in range(t.shape[0]) for c in range(t.shape[1])]
+
+
+def _add_inplace(dst: torch.Tensor, src: torch.Tensor) -> None:
+    if dst.is_cuda:
+        from .. import _kernels as K
+
+        K.add_f32(dst, src)
+    else:   # gloo unit tests of the host logic run on CPU tensors
+        dst += src
+
+
 def exchange_partials(acc: torch.Tensor, plan: ShardPlan, rank: int, group=None) -> None:
     """acc [B, C, D, H, W] fp32 holds this rank's partial numerators on its slab rows (zeros elsewhere).  After the
-    call the rows this rank OWNS hold the complete sums.  Sends: my slab ∩ peer's owned rows; receives the converse."""
+    call the rows this rank OWNS hold the complete sums.  Sends: my slab ∩ peer's owned rows; receives the converse.
+    Every (batch, channel) plane of a row range is contiguous, so the sends go straight out of the accumulator (no staging
+    copy); ONE grouped P2P call carries all transfers; received planes are added by a CUDA kernel."""
     world = plan.world
     if world == 1:
         return
@@ -81,18 +97,43 @@ def exchange_partials(acc: torch.Tensor, plan: ShardPlan, rank: int, group=None)
             continue
         s = _intersect(plan.slab[rank], plan.owned[peer])
         if s is not None:
-            buf = acc[:, :, s[0] : s[1]].contiguous()
-            ops.append(dist.P2POp(dist.isend, buf, peer, group=group))
+            for piece in _planes(acc, s[0], s[1]):
+                ops.append(dist.P2POp(dist.isend, piece, peer, group=group))
         r = _intersect(plan.slab[peer], plan.owned[rank])
         if r is not None:
-            buf = torch.empty_like(acc[:, :, r[0] : r[1]])
-            recv_bufs.append((r, buf))
-            ops.append(dist.P2POp(dist.irecv, buf, peer, group=group))
+            for piece in _planes(acc, r[0], r[1]):
+                buf = torch.empty_like(piece)
+                recv_bufs.append((piece, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, peer, group=group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-    for r, buf in recv_bufs:
-        acc[:, :, r[0] : r[1]] += buf
+    for piece, buf in recv_bufs:
+        _add_inplace(piece, buf)
+
+
+def allgather_owned(out: torch.Tensor, plan: ShardPlan, rank: int, group=None) -> None:
+    """Every rank holds valid result rows plan.owned[rank] of out [B, C, D, H, W]; after the call every rank holds all rows.
+    One grouped P2P call (an all-gather with uneven, in-place pieces): each rank sends the contiguous (batch, channel) planes
+    of its owned rows to every peer and receives the peers' planes directly into `out`."""
+    world = plan.world
+    if world == 1:
+        return
+    ops = []
+    lo, hi = plan.owned[rank]
+    mine = _planes(out, lo, hi) if hi > lo else []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        for piece in mine:
+            ops.append(dist.P2POp(dist.isend, piece, peer, group=group))
+        plo, phi = plan.owned[peer]
+        if phi > plo:
+            for piece in _planes(out, plo, phi):
+                ops.append(dist.P2POp(dist.irecv, piece, peer, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
 
 
 class ShardedSlidingWindowInferer:
@@ -140,12 +181,15 @@ class ShardedSlidingWindowInferer:
         plan = make_shard_plan(starts[0], roi[0], D, world, per_layer=nh * nw)
         wa, wb = plan.win_range[rank]
         num_win = len(starts[0]) * nh * nw
+        if num_win < world:   # every rank computes the same numbers: all of them raise, none enters a collective
+            raise ValueError(f"sharded inference over {world} ranks needs at least {world} windows, the volume has {num_win}")
         dev = inputs.device
         mode_s = str(getattr(self.mode, "value", self.mode)).lower()
         factors, clamp = importance_factors(roi, mode_s, self.sigma_scale)
         factors = [f.to(dev) for f in factors]
         starts_t = [torch.tensor(s, dtype=torch.int32, device=dev) for s in starts]
         starts_t[2]._align = math.gcd(8, *[int(v) for v in starts[2]])
+        starts_t[2]._max_cover = max(max(sum(1 for s0 in ax if s0 <= v < s0 + r) for v in ax) for ax, r in zip(starts, roi))
         x = inputs.detach()
         x = x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x
         acc = None
@@ -185,27 +229,12 @@ class ShardedSlidingWindowInferer:
                 held += n
             if held:
                 flush()
-        if acc is None:  # a rank without windows still takes part in the exchange
-            cshape = torch.zeros(1, dtype=torch.int64, device=dev)
-            if world > 1:
-                dist.all_reduce(cshape, op=dist.ReduceOp.MAX)
-            raise RuntimeError("rank without windows: use fewer ranks than depth start-layers")
+        if acc is None:  # unreachable: the window count was validated against the world size before any collective
+            raise RuntimeError("rank without windows")
         exchange_partials(acc, plan, rank)
         o_lo, o_hi = plan.owned[rank]
         out = torch.empty((B, out_c, D, H, W), device=dev, dtype=inputs.dtype if inputs.dtype in (torch.float16, torch.float32) else torch.float32)
         K.sw_blend(2, None, 0, B * num_win, (B, out_c, D, H, W), roi, starts_t, factors, clamp, None, out, acc=acc, box=(o_lo, o_hi, 0, 0))
         if world > 1 and self.gather:
-            ops = []
-            for peer in range(world):
-                lo, hi = plan.owned[peer]
-                if hi <= lo:
-                    continue
-                slab = out[:, :, lo:hi]
-                if slab.is_contiguous():
-                    dist.broadcast(slab, src=peer)
-                else:
-                    buf = slab.contiguous()
-                    dist.broadcast(buf, src=peer)
-                    if peer != rank:
-                        slab.copy_(buf)
+            allgather_owned(out, plan, rank)
         return out
