@@ -56,7 +56,11 @@ def _worker(rank, world, port, shape, roi, overlap, ret):
                     cnt[:, :, sd : sd + roi[0], sh : sh + roi[1], sw : sw + roi[2]] += imp
         o_lo, o_hi = plan.owned[rank]
         mine = t.numpy()[:, :, o_lo:o_hi] / cnt[:, :, o_lo:o_hi]
-        ret[rank] = (o_lo, o_hi, mine)
+        # the owned rows are then shared with every rank in ONE grouped exchange (uneven, in-place all-gather)
+        res = torch.full((1, 2, *shape), float("nan"))
+        res[:, :, o_lo:o_hi] = torch.from_numpy(mine)
+        allgather_owned(res, plan, rank)
+        ret[rank] = (o_lo, o_hi, mine, res.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -71,9 +75,10 @@ def test_sharded_exchange_matches_single_process_oracle(world, shape, roi, overl
     got = np.zeros_like(want)
     covered = np.zeros(shape[0], dtype=int)
     for r in range(world):
-        lo, hi, part = ret[r]
+        lo, hi, part, gathered = ret[r]
         got[:, :, lo:hi] = part
         covered[lo:hi] += 1
+        np.testing.assert_allclose(gathered, want, rtol=1e-5, atol=1e-6, err_msg=f"all-gathered result on rank {r}")
     assert (covered == 1).all()  # owned rows partition the depth axis
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
 
