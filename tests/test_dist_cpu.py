@@ -13,6 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from monai_b200.parallel import exchange_partials, make_shard_plan
+from monai_b200.parallel.sharded import allgather_owned
 from oracle import sliding_window as osw
 
 
