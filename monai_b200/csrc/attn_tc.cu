@@ -12,7 +12,7 @@
 // removes the per-element table lookup and mask test that bounded the mma.sync kernel (swin.cu) -- with head_dim 16 the
 // tensor pipe is otherwise idle.  Padded keys carry B' = -30000 (P = 0).  Scores are in log2 units: the caller folds
 // scale * log2(e) into the q rows of the qkv projection.
-//   softmax: 8 warps, two threads per query row (one per key half): exact row maximum from TMEM (pass 1), then
+//   softmax: 16 warps, four threads per query row: exact row maximum from TMEM (pass 1), then
 //            P = ex2(S - max) in fp32, packed to fp16 and written straight into the K-major core-matrix image
 //            of an A operand in shared memory (pass 2);
 //   O[128 x 32] = P [V | 1 | 0]                 n_pad/16 tcgen05.mma, V read in place as an MN-major B operand (NC8 rows
@@ -20,7 +20,9 @@
 //   epilogue: O / rowsum -> fp16 NC8.
 // Q, K, V tiles are 1-D bulk copies of NC8 rows (contiguous per 8-channel chunk).
 //
-// Warp roles (320 threads): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = softmax / epilogue.
+// Warp roles (576 threads): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-17 = softmax / epilogue (four
+// threads per query row, each with a share of the 16-column chunks of both key halves: 4 warps per scheduler hide the TMEM /
+// MUFU latencies that 2 per scheduler left exposed -- ncu: 33 % issue-active, MUFU 38 %, tensor 25 % with 8 softmax warps).
 #include "common.cuh"
 #include "tc05.cuh"
 #include "../../include/monai_b200.h"
@@ -32,7 +34,7 @@ constexpr int kAtKChunk = kAtNPadMax * 16;            // bytes of one 8-dim chun
 constexpr int kAtBiasBytes = 16 * kAtNPadMax * 16;    // 16 chunks of 8 query rows
 constexpr int kAtPBytes = (kAtNPadMax / 8) * 2048;    // P: [key block of 8][128 rows][16 B]
 constexpr int kAtColS1 = 176, kAtColO = 352, kAtColI = 384;   // TMEM columns: S half 0 at 0, half 1, O, identity (64)
-constexpr int kAtSmem = kAtBiasBytes + kAtPBytes + 2 * 2048 + 2 * kAtKChunk + 4 * kAtKChunk + 2 * 128 * 4 + 256 + 128;
+constexpr int kAtSmem = kAtBiasBytes + kAtPBytes + 2 * 2048 + 2 * kAtKChunk + 4 * kAtKChunk + 4 * 128 * 4 + 256 + 128;
 constexpr float kAtPadBias = -30000.f;
 
 struct AttnTcParams {
@@ -75,7 +77,10 @@ __device__ __forceinline__ uint32_t exp2_pack(float a, float b, float m) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParams p) {
+constexpr int kAtSplit = 4;                 // softmax threads per query row (each takes a share of the 16-column chunks)
+constexpr int kAtThreads = 64 + 128 * kAtSplit;
+
+__global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* s_bias = smem;
@@ -83,8 +88,8 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
   uint8_t* s_q = s_p + kAtPBytes;
   uint8_t* s_k = s_q + 2 * 2048;
   uint8_t* s_v = s_k + 2 * kAtKChunk;                 // 4 chunk slots: V dims 0-7, 8-15, ones column, zeros
-  float* s_max = reinterpret_cast<float*>(s_v + 4 * kAtKChunk);   // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_max + 256);
+  float* s_max = reinterpret_cast<float*>(s_v + 4 * kAtKChunk);   // [kAtSplit][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_max + 128 * kAtSplit);
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* s_full = bars + 2;      // [2]
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
   if (threadIdx.x == 0) {
     tc::mbar_init(qk_full, 1); tc::mbar_init(qk_empty, 1); tc::mbar_init(v_full, 1); tc::mbar_init(pv_done, 1);
     tc::mbar_init(o_empty, 128); tc::mbar_init(init_done, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 256); tc::mbar_init(&p_full[i], 256); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128 * kAtSplit); tc::mbar_init(&p_full[i], 128 * kAtSplit); }
     tc::fence_barrier_init();
   }
   // zero Q / K / V (rows the bulk copies never write must be finite), the ones column, and the identity (staged in the P region)
@@ -236,11 +241,11 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
     __syncwarp();
   } else {
     // ===================== softmax + epilogue (warps 2..9) =====================
-    const int jj = (warp - 2) >> 2;           // the two threads of a query row split the 16-column chunks of each key half
+    const int jj = (warp - 2) >> 2;           // the kAtSplit threads of a query row split the 16-column chunks of each key half
     const int q = warp & 3;                   // TMEM lane quarter
     const int row = q * 32 + lane;
     const int nchunk = NH / 16;
-    const int c_lo = jj == 0 ? 0 : (nchunk + 1) / 2, c_hi = jj == 0 ? (nchunk + 1) / 2 : nchunk;
+    const int c_lo = (jj * nchunk) / kAtSplit, c_hi = ((jj + 1) * nchunk) / kAtSplit;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t to = tlane + kAtColO;
     int it = 0;
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
         tc::fence_after_sync();
         const uint32_t ts = tlane + hf * kAtColS1;
         uint32_t va[16], vb[16];
-        tc::tmem_ld16(ts + c_lo * 16, va);
+        if (c_lo < c_hi) tc::tmem_ld16(ts + c_lo * 16, va);
         for (int c = c_lo; c < c_hi; c += 2) {
           tc::tmem_ld_wait16(va);
           if (c + 1 < c_hi) tc::tmem_ld16(ts + (c + 1) * 16, vb);
@@ -268,8 +273,9 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
         }
       }
       s_max[jj * 128 + row] = m;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      m = fmaxf(m, s_max[(jj ^ 1) * 128 + row]);
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kAtSplit) : "memory");
+#pragma unroll
+      for (int k = 0; k < kAtSplit; ++k) m = fmaxf(m, s_max[k * 128 + row]);
       // P buffer free?  (first tile: the identity staged there has been copied to TMEM)
       if (it == 0) tc::mbar_wait(init_done, 0u);
       else tc::mbar_wait(pv_done, (uint32_t)((it - 1) & 1));
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(320, 1) window_attention_tc_kernel(AttnTcParam
           *reinterpret_cast<uint4*>(prow + (2 * c) * 2048) = u0;
           *reinterpret_cast<uint4*>(prow + (2 * c + 1) * 2048) = u1;
         };
-        tc::tmem_ld16(ts + c_lo * 16, va);
+        if (c_lo < c_hi) tc::tmem_ld16(ts + c_lo * 16, va);
         for (int c = c_lo; c < c_hi; c += 2) {
           tc::tmem_ld_wait16(va);
           if (c + 1 < c_hi) tc::tmem_ld16(ts + (c + 1) * 16, vb);
@@ -414,7 +420,7 @@ extern "C" int b200_window_attention_tc(const void* qkv, int N, int C, int heads
   B200_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
   const long long total = (long long)N * nW * heads * p.nrt;
   dim3 grid((unsigned)std::min<long long>(total, num_sms()));
-  window_attention_tc_kernel<<<grid, 320, kAtSmem, (cudaStream_t)stream>>>(p);
+  window_attention_tc_kernel<<<grid, kAtThreads, kAtSmem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("window_attention_tc_kernel");
   return B200_OK;
 }

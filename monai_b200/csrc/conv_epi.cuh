@@ -37,17 +37,22 @@ __device__ __forceinline__ ConvTile conv_tile(const ConvEpiP& p, long long t) {
   return c;
 }
 
-// Run by the four epilogue warps (any four warps whose ids cover the residues mod 4: warp w reads TMEM lanes
-// 32*(w & 3) ..).  acc_full[b] is completed by tcgen05.commit of the MMA warp, acc_empty[b] expects 128 arrivals.
-// s_stats: shared memory, 4 warp-private rows of 2*NT floats, zero-initialised by the caller.
-template <int NT, int BD, int NB>
+// Run by EG groups of four epilogue warps (each group: four warps whose ids cover the residues mod 4 -- warp w reads TMEM lanes
+// 32*(w & 3) ..); group `eg` handles the planes sub = eg, eg + EG, ... of every tile.  acc_full[b] is completed by tcgen05.commit
+// of the MMA warp, acc_empty[b] expects 128 * EG arrivals.  s_stats: shared memory, 4 * EG warp-private rows of 2*NT floats,
+// zero-initialised by the caller.  (One group suffices while the MMAs of a tile take longer than its epilogue -- conv_tc.cu; the
+// store-bound stems of conv_cin1_tc.cu run four groups.)
+template <int NT, int BD, int NB, int EG = 1>
 __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
-                                              float* s_stats, int warp, int lane) {
+                                              float* s_stats, int warp, int lane, int eg = 0) {
+  static_assert(BD % EG == 0 || EG == 1, "planes must divide evenly among the epilogue groups");
+  constexpr int kSubs = (BD + EG - 1) / EG;   // planes per group
   const int q = warp & 3;                 // TMEM lane quarter this warp may access
   const int row = q * 32 + lane;
+  const int slot = eg * 4 + q;
   const long long S = (long long)p.D * p.H * p.W;
   const long long sp_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d;
-  float* ws = s_stats + q * (2 * NT);
+  float* ws = s_stats + slot * (2 * NT);
   long long group = -1;
   int it = 0;
   for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -55,7 +60,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_b
     if (p.sp.buf) {
       const long long g = t / sp_tiles;
       if (g != group) {
-        if (group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, 0, NT);
+        if (group >= 0) stats_flush(p.sp, ws, 2 * NT, group, slot, lane, 0, NT);
         group = g;
       }
     }
@@ -69,20 +74,21 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_b
     tc::fence_after_sync();
     const uint32_t tq = tmem_base + buf * (BD * NT) + ((uint32_t)(q * 32) << 16);
     uint32_t vn[8];
-    tc::tmem_ld8(tq, vn);   // (cc = 0, sub = 0); every later load is prefetched one step ahead
+    tc::tmem_ld8(tq + eg * NT, vn);   // (cc = 0, first plane of this group); every later load is prefetched one step ahead
 #pragma unroll 1
     for (int cc = 0; cc < NT / 8; ++cc) {
       float bsum[8], bsq[8], bias8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = p.bias ? p.bias[co0 + cc * 8 + j] : 0.f; }
 #pragma unroll
-      for (int sub = 0; sub < BD; ++sub) {
+      for (int si = 0; si < kSubs; ++si) {
+        const int sub = eg + si * EG;
         uint32_t v[8];
         tc::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = vn[j];
         {
-          const int nsub = sub + 1 < BD ? sub + 1 : 0, ncc = sub + 1 < BD ? cc : cc + 1;
+          const int nsub = si + 1 < kSubs ? sub + EG : eg, ncc = si + 1 < kSubs ? cc : cc + 1;
           if (ncc < NT / 8) tc::tmem_ld8(tq + nsub * NT + ncc * 8, vn);
         }
         const int dz = c.d0 + sub;
@@ -115,7 +121,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_b
     tc::fence_before_sync();
     tc::mbar_arrive(&acc_empty[buf]);
   }
-  if (p.sp.buf && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, 0, NT);
+  if (p.sp.buf && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, slot, lane, 0, NT);
 }
 
 }  // namespace b200

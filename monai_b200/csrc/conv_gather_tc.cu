@@ -408,9 +408,10 @@ extern "C" int b200_conv_gather_tc(const b200_conv_gather_desc* desc, const void
   p.sp.buf = stats ? (float*)workspace : nullptr;
   p.sp.R = stats_rows(tpg, total_tiles);
   p.sp.tiles_per_group = tpg;
+  p.sp.rows_per_cta = 4;
   dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
   conv_gather_tc_kernel<<<grid, 288, smem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("conv_gather_tc_kernel");
-  if (stats) return launch_stats_finish((const float*)workspace, groups, p.sp.R, p.NT, p.cout_pad / p.NT, d.Cout, stats, (cudaStream_t)stream);
+  if (stats) return launch_stats_finish((const float*)workspace, groups, p.sp.R * 4, p.NT, p.cout_pad / p.NT, d.Cout, stats, (cudaStream_t)stream);
   return B200_OK;
 }

@@ -425,14 +425,14 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, ConvTcCall& c) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "conv3x3x3_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   p.e.y = (__half*)c.y; p.e.bias = c.bias;
-  p.e.sp.buf = c.stats ? (float*)c.ws : nullptr; p.e.sp.R = R; p.e.sp.tiles_per_group = sp_tiles;
+  p.e.sp.buf = c.stats ? (float*)c.ws : nullptr; p.e.sp.R = R; p.e.sp.tiles_per_group = sp_tiles; p.e.sp.rows_per_cta = 4;
   dim3 grid((unsigned)std::min<long long>(p.e.total_tiles, num_sms()));
   auto kern = conv3x3x3_tc_kernel<NT, BD>;
   // per-device attribute: set on every call (cheap), so a second GPU in the same process works
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   kern<<<grid, 192, Cfg::kSmemBytes, c.st>>>(tmap, p);
   B200_LAUNCH_CHECK("conv3x3x3_tc_kernel");
-  if (c.stats) return launch_stats_finish((const float*)c.ws, groups, R, NT, p.e.n_tiles, d.Cout, c.stats, c.st);
+  if (c.stats) return launch_stats_finish((const float*)c.ws, groups, R * 4, NT, p.e.n_tiles, d.Cout, c.stats, c.st);
   return B200_OK;
 }
 

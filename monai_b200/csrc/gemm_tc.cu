@@ -416,9 +416,10 @@ extern "C" int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const 
   p.sp.buf = stats ? (float*)workspace : nullptr;
   p.sp.R = stats_rows(row_tiles, total_tiles);
   p.sp.tiles_per_group = row_tiles;
+  p.sp.rows_per_cta = 4;
   dim3 grid((unsigned)std::min<long long>(total_tiles, num_sms()));
   fn<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("gemm_tc_kernel");
-  if (stats) return launch_stats_finish((const float*)workspace, groups, p.sp.R, NT, d.N / NT, d.N, stats, (cudaStream_t)stream);
+  if (stats) return launch_stats_finish((const float*)workspace, groups, p.sp.R * 4, NT, d.N / NT, d.N, stats, (cudaStream_t)stream);
   return B200_OK;
 }

@@ -152,13 +152,13 @@ __global__ void stats_finish_kernel(const float* __restrict__ partials, int rows
   }
 }
 
-int launch_stats_finish(const float* partials, long long groups, int R, int NT, int n_tiles, int Cout, float* stats, cudaStream_t st) {
+int launch_stats_finish(const float* partials, long long groups, int rows, int NT, int n_tiles, int Cout, float* stats, cudaStream_t st) {
   const int nt2 = 2 * NT;
   B200_REQUIRE(nt2 <= 1024 && groups > 0 && groups < (1LL << 31), "stats_finish: bad sizes");
   int L = 1024 / nt2;
   L = L > 8 ? 8 : (L < 1 ? 1 : L);
   dim3 block(nt2, L);
-  stats_finish_kernel<<<(unsigned)groups, block, (size_t)L * nt2 * sizeof(double), st>>>(partials, R * 4, nt2, n_tiles, NT, Cout, stats);
+  stats_finish_kernel<<<(unsigned)groups, block, (size_t)L * nt2 * sizeof(double), st>>>(partials, rows, nt2, n_tiles, NT, Cout, stats);
   B200_LAUNCH_CHECK("stats_finish_kernel");
   return B200_OK;
 }

@@ -19,18 +19,20 @@
 namespace b200 {
 
 struct StatsPartials {
-  float* buf;                 // [groups][R][4][2*NT]; null = no statistics
+  float* buf;                 // [groups][R][rows_per_cta][2*NT]; null = no statistics
   int R;                      // min(tiles_per_group, gridDim.x)
   long long tiles_per_group;
+  int rows_per_cta;           // partial rows one CTA writes per group: 4 (one per TMEM lane quarter) x epilogue warp groups
 };
 
-// flush the warp-private running sums of columns [col_lo, col_hi) (in {sum,sumsq} pairs) and clear them
-__device__ __forceinline__ void stats_flush(const StatsPartials& sp, float* ws, int nt2, long long group, int q, int lane,
+// flush the warp-private running sums of columns [col_lo, col_hi) (in {sum,sumsq} pairs) and clear them; `slot` = this
+// warp's row among the CTA's rows_per_cta rows
+__device__ __forceinline__ void stats_flush(const StatsPartials& sp, float* ws, int nt2, long long group, int slot, int lane,
                                             int pair_lo, int pair_hi) {
   __syncwarp();
   const long long G = gridDim.x;
   const int c = (int)((((long long)blockIdx.x - (group * sp.tiles_per_group) % G) + G) % G);
-  float* dst = sp.buf + (((group * sp.R + c) * 4 + q) * (long long)nt2);
+  float* dst = sp.buf + (((group * sp.R + c) * sp.rows_per_cta + slot) * (long long)nt2);
   for (int i = 2 * pair_lo + lane; i < 2 * pair_hi; i += 32) { dst[i] = ws[i]; ws[i] = 0.f; }
   __syncwarp();
 }
@@ -40,9 +42,9 @@ inline int stats_rows(long long tiles_per_group, long long total_tiles) {
   const long long grid = std::min<long long>(total_tiles, num_sms());
   return (int)std::min<long long>(tiles_per_group, grid);
 }
-inline long long stats_partial_bytes(long long groups, int R, int NT) { return groups * R * 4LL * 2 * NT * (long long)sizeof(float); }
+inline long long stats_partial_bytes(long long groups, int R, int NT, int rows_per_cta = 4) { return groups * R * (long long)rows_per_cta * 2 * NT * (long long)sizeof(float); }
 
-// stats[(n*Cout + nt*NT + col)*2 + {0,1}] = sum over the R*4 partial rows of group (n, nt), fixed order, fp64.
-int launch_stats_finish(const float* partials, long long groups, int R, int NT, int n_tiles, int Cout, float* stats, cudaStream_t st);
+// stats[(n*Cout + nt*NT + col)*2 + {0,1}] = sum over the `rows` (= R * rows_per_cta) partial rows of group (n, nt), fixed order, fp64.
+int launch_stats_finish(const float* partials, long long groups, int rows, int NT, int n_tiles, int Cout, float* stats, cudaStream_t st);
 
 }  // namespace b200

@@ -773,7 +773,7 @@ extern "C" int b200_conv_cin1_nc8(const void* x, int dtype, int N, int D, int H,
     rc = launch_cin1<float>((const float*)x, (__half*)y, weight, bias, N, D, H, W, Do, Ho, Wo, Cout, k, stride, pad, out_ctot, out_coff, part, st);
   else return set_err(B200_ERR_INVALID, "conv_cin1_nc8: bad dtype");
   if (rc || !stats) return rc;
-  return launch_stats_finish(part, N, (int)cin1_grid(N, Do, Ho, Wo).x, Cout, 1, Cout, stats, st);
+  return launch_stats_finish(part, N, (int)cin1_grid(N, Do, Ho, Wo).x * 4, Cout, 1, Cout, stats, st);
 }
 
 extern "C" int b200_head_conv_nc8(const void* x, int N, int C, long long S, const float* weight, const float* bias, int Cout,
