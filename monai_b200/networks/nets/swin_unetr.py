@@ -14,8 +14,9 @@ the whole network runs on fp16 channel-blocked ("NC8") buffers through the C ABI
 
 Skip concatenations are zero-copy: producers write straight into channel slices of the decoder's input buffer.
 
-Supported on this path: spatial_dims=3, feature_size % 48 == 0 with head_dim 16 (the default num_heads for
-feature_size 48), norm_name="instance" (non-affine), downsample "merging"/"mergingv2", use_v2=False, inference only.
+Supported on this path: spatial_dims=3, any number of input channels (several channels: zero-padded to 16-channel tiles),
+feature_size % 48 == 0 with head_dim 16 (the default num_heads for feature_size 48), norm_name="instance" (non-affine),
+downsample "merging"/"mergingv2", use_v2 (the residual conv block in front of every stage), inference only.
 """
 from __future__ import annotations
 
@@ -132,17 +133,22 @@ class BasicLayer(nn.Module):
 
 class SwinTransformer(nn.Module):
     def __init__(self, in_chans, embed_dim, window_size, patch_size, depths, num_heads, mlp_ratio=4.0, qkv_bias=True,
-                 norm_layer=nn.LayerNorm, patch_norm=False, downsample="merging"):
+                 norm_layer=nn.LayerNorm, patch_norm=False, downsample="merging", use_v2=False):
         super().__init__()
+        self.use_v2 = use_v2
         self.num_layers = len(depths)
         self.embed_dim, self.patch_norm, self.window_size, self.patch_size = embed_dim, patch_norm, tuple(window_size), tuple(patch_size)
         self.patch_embed = PatchEmbed(self.patch_size, in_chans, embed_dim, norm_layer if patch_norm else None)
         self.pos_drop = nn.Dropout(p=0.0)
         self.layers1, self.layers2, self.layers3, self.layers4 = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         down = MERGING_MODE[downsample] if isinstance(downsample, str) else downsample
+        if use_v2:   # SwinUNETR-V2: a residual convolution block in front of every stage (swin_unetr.py:990-1036)
+            self.layers1c, self.layers2c, self.layers3c, self.layers4c = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         for i in range(self.num_layers):
             layer = BasicLayer(int(embed_dim * 2**i), depths[i], num_heads[i], self.window_size, mlp_ratio, qkv_bias, norm_layer, down)
             (self.layers1, self.layers2, self.layers3, self.layers4)[i].append(layer)
+            if use_v2:
+                (self.layers1c, self.layers2c, self.layers3c, self.layers4c)[i].append(UnetrBasicBlock(int(embed_dim * 2**i), int(embed_dim * 2**i)))
         self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
 
 
@@ -284,8 +290,8 @@ class SwinUNETR(GraphedForward, nn.Module):
                 raise ValueError(f"{name} should be between 0 and 1.")
         if feature_size % 12 != 0:
             raise ValueError("feature_size should be divisible by 12.")
-        if spatial_dims != 3 or use_v2:
-            raise NotImplementedError("monai_b200 SwinUNETR implements spatial_dims=3, use_v2=False")
+        if spatial_dims != 3:
+            raise NotImplementedError("monai_b200 SwinUNETR implements spatial_dims=3")
         if feature_size % 48 != 0:
             raise NotImplementedError("monai_b200 SwinUNETR needs feature_size % 48 == 0 (tensor-core tiles need 16-channel multiples)")
         if any((feature_size * 2**i) // h != 16 for i, h in enumerate(num_heads)):
@@ -300,11 +306,12 @@ class SwinUNETR(GraphedForward, nn.Module):
         self.feature_size = feature_size
         self.out_channels = out_channels
         self.in_channels = in_channels
-        if in_channels != 1:
-            raise NotImplementedError("monai_b200 SwinUNETR implements in_channels=1 (the configured workloads)")
+        if in_channels < 1:
+            raise ValueError("in_channels must be positive")
+        self.use_v2 = use_v2
         ws = _rep(window_size, 3)
         self.swinViT = SwinTransformer(in_channels, feature_size, ws, _rep(patch_size, 3), depths, num_heads, mlp_ratio, qkv_bias,
-                                       norm_layer, patch_norm, downsample)
+                                       norm_layer, patch_norm, downsample, use_v2)
         fs = feature_size
         self.encoder1 = UnetrBasicBlock(in_channels, fs)
         self.encoder2 = UnetrBasicBlock(fs, fs)
@@ -331,11 +338,24 @@ class SwinUNETR(GraphedForward, nn.Module):
             )
 
     # ----------------------------------------------------------------------------------------------- weight prep
-    def _w3(self, conv: nn.Conv3d, key: str):
-        return self._cache.get(("w3", key, conv.weight.device), [conv.weight], lambda: K.conv3x3x3_tc_pack_weight(conv.weight))
+    @staticmethod
+    def _pad_cin(w: torch.Tensor, cin_pad: int | None) -> torch.Tensor:
+        """Zero-pad the input-channel axis (dim 1) of a conv / linear weight: the multi-channel stems run on 16-channel tiles."""
+        if cin_pad is None or w.shape[1] == cin_pad:
+            return w
+        out = torch.zeros((w.shape[0], cin_pad, *w.shape[2:]), device=w.device, dtype=torch.float32)
+        out[:, : w.shape[1]] = w.detach().float()
+        return out
 
-    def _wlin(self, w: torch.Tensor, key: str):
-        return self._cache.get(("lin", key, w.device), [w], lambda: K.gemm_tc_pack_weight(w.reshape(w.shape[0], -1)))
+    def _w3(self, conv: nn.Conv3d, key: str, cin_pad: int | None = None):
+        return self._cache.get(("w3", key, cin_pad, conv.weight.device), [conv.weight], lambda: K.conv3x3x3_tc_pack_weight(self._pad_cin(conv.weight, cin_pad)))
+
+    def _wlin(self, w: torch.Tensor, key: str, cin_pad: int | None = None):
+        def build():
+            wp = self._pad_cin(w, cin_pad)
+            return K.gemm_tc_pack_weight(wp.reshape(wp.shape[0], -1))
+
+        return self._cache.get(("lin", key, cin_pad, w.device), [w], build)
 
     def _wup(self, conv: nn.ConvTranspose3d, key: str):
         # ConvTranspose3d weight [Cin, Cout, 2,2,2] -> GEMM W[(tap, cout), cin]
@@ -380,7 +400,7 @@ class SwinUNETR(GraphedForward, nn.Module):
 
     # ------------------------------------------------------------------------------------------------- sub-graphs
     def _res_block(self, x: K.NC8, cin: int, in_coff: int, blk: UnetResBlock, key: str, out: K.NC8 | None = None, out_coff: int = 0,
-                   x_in_raw: torch.Tensor | None = None, defer_tail: bool = False):
+                   x_in_raw: torch.Tensor | None = None, defer_tail: bool = False, cin_pad: int | None = None):
         """UnetResBlock.forward (dynunet_block.py:97-111) on NC8 buffers; `out` may be a slice of a concat buffer.
         With `defer_tail` the final norm2 + residual + lrelu is NOT applied: the pieces (y2, stats2, res, res_coff,
         res_stats) are returned so that the consumer (the output head) applies them on its operand load."""
@@ -388,7 +408,7 @@ class SwinUNETR(GraphedForward, nn.Module):
         if x_in_raw is not None:  # single input channel: direct stem kernels read the raw NCDHW window
             y1, st1 = K.conv_cin1_nc8(x_in_raw, blk.conv1.conv.weight, None, 3, 1, 1, want_stats=True)
         else:
-            y1, st1 = K.conv3x3x3_tc(x, self._w3(blk.conv1.conv, key + ".c1"), cin, cout, in_coff=in_coff, want_stats=True)
+            y1, st1 = K.conv3x3x3_tc(x, self._w3(blk.conv1.conv, key + ".c1", cin_pad), cin, cout, in_coff=in_coff, want_stats=True)
         K.norm_act_nc8(y1, cout, st1, act=L.ACT_LEAKY, slope=0.01, out=y1)
         y2, st2 = K.conv3x3x3_tc(y1, self._w3(blk.conv2.conv, key + ".c2"), cout, cout, want_stats=True)
         if hasattr(blk, "conv3"):
@@ -402,7 +422,7 @@ class SwinUNETR(GraphedForward, nn.Module):
             if x_in_raw is not None:
                 y3, st3 = K.conv_cin1_nc8(x_in_raw, blk.conv3.conv.weight, None, 1, 1, 0, want_stats=True)
             else:
-                y3, st3 = K.gemm_tc(x, self._wlin(blk.conv3.conv.weight, key + ".c3"), cin, cout, in_coff=in_coff, want_stats=True)
+                y3, st3 = K.gemm_tc(x, self._wlin(blk.conv3.conv.weight, key + ".c3", cin_pad), cin, cout, in_coff=in_coff, want_stats=True)
             if defer_tail:
                 return y2, st2, y3, 0, st3
         elif defer_tail:
@@ -415,9 +435,11 @@ class SwinUNETR(GraphedForward, nn.Module):
             K.norm_act_nc8(y2, cout, st2, res=x, res_coff=in_coff, act=L.ACT_LEAKY, slope=0.01, out=out, out_coff=out_coff)
         return out
 
-    def _swin_stage(self, cur: K.NC8, layer: BasicLayer, key: str) -> K.NC8:
+    def _swin_stage(self, cur: K.NC8, layer: BasicLayer, key: str, pre: UnetrBasicBlock | None = None) -> K.NC8:
         dims, C = cur.sp, cur.C
         dev = cur.buf.device
+        if pre is not None:   # SwinUNETR-V2: residual conv block on the token grid (swin_unetr.py:1059-1072)
+            cur = self._res_block(cur, C, 0, pre.layer, key + ".c")
         for bi, blk in enumerate(layer.blocks):
             ws, ss = _get_window_size(dims, blk.window_size, blk.shift_size)
             src, region, nW, n, tc = self._plan(dims, ws, ss, dev)
@@ -463,6 +485,14 @@ class SwinUNETR(GraphedForward, nn.Module):
             raise ValueError(f"expected {self.in_channels} input channel(s), got {x_in.shape[1]}")
         if x_in.dtype not in (torch.float16, torch.float32):
             raise TypeError(f"SwinUNETR takes float16/float32 inputs, got {x_in.dtype}")
+        if x_in.dtype == torch.float32 and not getattr(self, "_warned_fp32", False):
+            import warnings
+
+            # no silent degradation: the tensor-core path stores activations in fp16 (fp32 accumulation everywhere); an fp32
+            # input gets fp32 logits of that fp16-storage computation (measured ~5e-3 of the output scale)
+            warnings.warn("monai_b200.SwinUNETR computes with fp16 activation storage (fp32 accumulation); float32 inputs are converted. "
+                          "Expect ~1e-2 relative agreement with an fp32 reference, not 1e-3.")
+            self._warned_fp32 = True
         if self._graph_ok():
             return self._forward_graphed(x_in, self._forward_impl)
         return self._forward_impl(x_in)
@@ -486,21 +516,37 @@ class SwinUNETR(GraphedForward, nn.Module):
 
             # ---- Swin transformer encoder (swin_unetr.py:1055-1075)
             pe = vit.patch_embed
-            t0, _ = K.conv_cin1_nc8(x_in, pe.proj.weight, pe.proj.bias, 2, 2, 0)
+            xp = None
+            if self.in_channels == 1:
+                t0, _ = K.conv_cin1_nc8(x_in, pe.proj.weight, pe.proj.bias, 2, 2, 0)
+            else:
+                # several input channels: the volume is repacked once into channel-blocked fp16 with the channels zero-padded to a
+                # multiple of 16, and the stems run on the general tensor-core kernels with zero-padded weights
+                cp = (self.in_channels + 15) // 16 * 16
+                xz = torch.zeros((n, cp, *sp0), device=dev, dtype=torch.float16)
+                K.copy_channels(x_in.to(torch.float16), xz, 0)
+                xp = K.pack_nc8(xz)
+                pw = self._cache.get(("pe", cp, pe.proj.weight.device), [pe.proj.weight],
+                                     lambda: K.conv_gather_tc_pack_weight(self._pad_cin(pe.proj.weight, cp), 2, 2, 0, False))
+                t0, _ = K.conv_gather_tc(xp, pw, cp, fs, 2, 2, 0, bias=pe.proj.bias)
             if pe.norm is not None:
                 t0 = K.layernorm_nc8(t0, pe.norm.weight, pe.norm.bias, pe.norm.eps)
+            v2 = (lambda i: getattr(vit, f"layers{i}c")[0]) if self.use_v2 else (lambda i: None)
             h0 = self._proj_out(t0)
-            t1 = self._swin_stage(t0, vit.layers1[0], "l1")
+            t1 = self._swin_stage(t0, vit.layers1[0], "l1", v2(1))
             h1 = self._proj_out(t1)
-            t2 = self._swin_stage(t1, vit.layers2[0], "l2")
+            t2 = self._swin_stage(t1, vit.layers2[0], "l2", v2(2))
             h2 = self._proj_out(t2)
-            t3 = self._swin_stage(t2, vit.layers3[0], "l3")
+            t3 = self._swin_stage(t2, vit.layers3[0], "l3", v2(3))
             self._proj_out(t3, out=cat5, out_coff=8 * fs)
-            t4 = self._swin_stage(t3, vit.layers4[0], "l4")
+            t4 = self._swin_stage(t3, vit.layers4[0], "l4", v2(4))
             h4 = self._proj_out(t4)
 
             # ---- CNN encoders on the hidden states (swin_unetr.py:319-324)
-            self._res_block(None, 1, 0, self.encoder1.layer, "enc1", out=cat1, out_coff=fs, x_in_raw=x_in)
+            if xp is None:
+                self._res_block(None, 1, 0, self.encoder1.layer, "enc1", out=cat1, out_coff=fs, x_in_raw=x_in)
+            else:
+                self._res_block(xp, xp.C, 0, self.encoder1.layer, "enc1", out=cat1, out_coff=fs, cin_pad=xp.C)
             self._res_block(h0, fs, 0, self.encoder2.layer, "enc2", out=cat2, out_coff=fs)
             self._res_block(h1, 2 * fs, 0, self.encoder3.layer, "enc3", out=cat3, out_coff=2 * fs)
             self._res_block(h2, 4 * fs, 0, self.encoder4.layer, "enc4", out=cat4, out_coff=4 * fs)

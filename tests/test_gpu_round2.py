@@ -205,6 +205,22 @@ def test_swin_unetr_96_cube_window_matches_the_real_reference(golden_dir):
     assert np.array_equal(y, y2)
 
 
+def test_swin_unetr_multi_channel_input_and_v2_match_the_real_reference(golden_dir):
+    """SwinUNETR(in_channels=4, out_channels=3, feature_size=48, use_v2=True): the multi-channel stems (zero-padded 16-channel
+    tiles on the general tensor-core kernels) and the V2 residual blocks in front of every stage, against a fixture of the real
+    reference; plus the state_dict contract (same keys as the fixture's generator loaded by name)."""
+    g = np.load(os.path.join(golden_dir, "swin_unetr_fs48_in4_v2_64.npz"))
+    net = _build(lambda: SwinUNETR(in_channels=4, out_channels=3, feature_size=48, use_v2=True), 6)
+    y = net(torch.from_numpy(g["x"]).to(DEV)).float().cpu().numpy()
+    assert y.shape == (1, 3, 64, 64, 64)
+    ref = g["y_sub"]
+    err = float(np.abs(y[..., ::4, ::4, ::4] - ref).max() / np.abs(ref).max())
+    agree = float((y[..., ::4, ::4, ::4].argmax(1) == ref.argmax(1)).mean())
+    assert err < 3e-2 and agree > 0.98, f"max rel err {err:.3e}, arg-max agreement {agree:.4f}"
+    with pytest.raises(ValueError, match="expected 4 input"):
+        net(torch.zeros(1, 1, 64, 64, 64, device=DEV))
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_kernels_follow_the_tensors_device_not_the_current_one():
     """tensors on cuda:1 while cuda:0 is current."""
