@@ -31,9 +31,10 @@ long long b200_launch_count(void);
 
 /* ---- sliding-window inference: gather + blend -------------------------------------------------------- */
 /* replaces monai/inferers/utils.py:217-224 -- copy n_win windows (win_tab[n_win][4] = {batch, d0, h0, w0},
- * device int32) out of vol[B,C,D,H,W] into out[n_win,C,rd,rh,rw]; dtype conversion allowed. */
+ * device int32) out of vol[B,C,D,H,W] into out[n_win,C,rd,rh,rw]; dtype conversion allowed.  starts_w_align: a common divisor of
+ * every w0 in the table (0 / 1 = unknown): with 16-byte alignment all along W the copy runs on 16-byte vectors. */
 int b200_sw_gather(const void* vol, int in_dtype, void* out, int out_dtype, const int32_t* win_tab, int n_win,
-                   int C, int D, int H, int W, int rd, int rh, int rw, void* stream);
+                   int C, int D, int H, int W, int rd, int rh, int rw, int starts_w_align, void* stream);
 
 typedef struct b200_blend_desc {
   const void* preds;        /* resident window predictions, windows [win_begin, win_end) */
@@ -93,10 +94,12 @@ int b200_conv3d_direct(const b200_conv_desc* desc, const void* x, const float* w
                        void* stream);
 
 /* per-(n,c) sum and sum of squares over S = D*H*W elements of x[N,C,S] -> stats[N*C][2] (float32, overwritten;
- * deterministic: one block per plane, fixed summation order).
+ * deterministic: fixed summation order; with few large planes the work is split into chunks whose {sum, sumsq} pairs go through
+ * `workspace` (b200_instnorm_stats_workspace_bytes, may be NULL: one block per plane then) and are added in chunk order).
  * x_stride_n = element stride between samples. */
+long long b200_instnorm_stats_workspace_bytes(int N, int C, long long S);   /* 0: no scratch needed for this shape */
 int b200_instnorm_stats(const void* x, int dtype, int N, int C, long long S, long long x_stride_n, float* stats,
-                        void* stream);
+                        void* workspace, void* stream);
 
 /* y = act( (x - mean) * rstd * gamma + beta  [+ res] ) with mean/rstd from stats (biased variance, eps);
  * stats == NULL skips the normalisation.  replaces InstanceNorm3d + PReLU/LeakyReLU (ADN,

@@ -167,7 +167,9 @@ def instnorm_stats(x: torch.Tensor) -> torch.Tensor:
     N, Cc = x.shape[:2]
     S = x[0, 0].numel()
     stats = torch.empty((N * Cc, 2), device=x.device, dtype=torch.float32)
-    _call("instnorm_stats", L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), L.stream_ptr(x.device), nbytes=_nb(x))
+    nws = L.load().b200_instnorm_stats_workspace_bytes(N, Cc, S)
+    ws = _ws(nws, x.device) if nws > 0 else None
+    _call("instnorm_stats", L.ptr(x), L.dt(x), N, Cc, S, x.stride(0) if N > 1 else Cc * S, L.ptr(stats), L.ptr(ws), L.stream_ptr(x.device), nbytes=_nb(x))
     return stats
 
 
@@ -217,14 +219,16 @@ def copy_channels(x: torch.Tensor, dst: torch.Tensor, c_off: int) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ sliding window
-def sw_gather(vol: torch.Tensor, win_tab: torch.Tensor, roi: Sequence[int], out_dtype: torch.dtype | None = None) -> torch.Tensor:
-    """vol [B,C,D,H,W] -> [n_win,C,*roi]; win_tab int32 device [n_win,4] = (batch, d0, h0, w0)."""
+def sw_gather(vol: torch.Tensor, win_tab: torch.Tensor, roi: Sequence[int], out_dtype: torch.dtype | None = None, w_align: int = 1) -> torch.Tensor:
+    """vol [B,C,D,H,W] -> [n_win,C,*roi]; win_tab int32 device [n_win,4] = (batch, d0, h0, w0); `w_align` = a common divisor of every
+    w0 (the caller knows the starts on the host), which lets the copy use 16-byte vectors."""
     L.require_cuda(vol, win_tab)
     vol = vol.contiguous()
     B, Cc, D, H, W = vol.shape
     n = win_tab.shape[0]
     out = torch.empty((n, Cc, *roi), device=vol.device, dtype=out_dtype or vol.dtype)
-    _call("sw_gather", L.ptr(vol), L.dt(vol), L.ptr(out), L.dt(out), L.ptr(win_tab), n, Cc, D, H, W, roi[0], roi[1], roi[2], L.stream_ptr(vol.device))
+    _call("sw_gather", L.ptr(vol), L.dt(vol), L.ptr(out), L.dt(out), L.ptr(win_tab), n, Cc, D, H, W, roi[0], roi[1], roi[2], int(w_align),
+          L.stream_ptr(vol.device), nbytes=2.0 * _nb(out))
     return out
 
 

@@ -72,10 +72,11 @@ SIGNATURES = {
     "b200_abi_version": (i32, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_launch_count": (i64, []),
-    "b200_sw_gather": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "b200_sw_gather": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "b200_sw_blend": (i32, [C.POINTER(BlendDesc), i32, vp]),
     "b200_conv3d_direct": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp]),
-    "b200_instnorm_stats": (i32, [vp, i32, i32, i32, i64, i64, vp, vp]),
+    "b200_instnorm_stats_workspace_bytes": (i64, [i32, i32, i64]),
+    "b200_instnorm_stats": (i32, [vp, i32, i32, i32, i64, i64, vp, vp, vp]),
     "b200_norm_act": (i32, [vp, i32, i32, i32, i64, i64, vp, f32, vp, vp, vp, i64, vp, i32, f32, vp, i32, vp, i64, vp]),
     "b200_maxpool3d_2": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "b200_copy_channels": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp]),

@@ -570,6 +570,30 @@ __global__ void __launch_bounds__(256) sw_gather_kernel(const TI* __restrict__ v
     io<TO>::st(dst + lw, io<TI>::ld(src + lw));
 }
 
+// Same copy with 16-byte vectors (both element types equal, rw / W / every start along W multiples of the vector width):
+// a thread moves one vector, a block walks (window, channel, d, h, vector) with a grid stride -- the one-row-per-block form
+// above spends its time on block turnover (0.05 of HBM bandwidth on the 96^3 windows of C3).
+template <typename T>
+__global__ void __launch_bounds__(256) sw_gather_vec_kernel(const T* __restrict__ vol, T* __restrict__ out, const int* __restrict__ tab,
+                                                            int n_win, int C, int D, int H, int W, int rd, int rh, int rw) {
+  constexpr int V = 16 / sizeof(T);
+  const int rwv = rw / V;
+  const long long per_win = (long long)C * rd * rh * rwv;
+  const long long total = per_win * n_win;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int win = (int)(i / per_win);
+    long long r = i % per_win;
+    const int wv = (int)(r % rwv); r /= rwv;
+    const int lh = (int)(r % rh); r /= rh;
+    const int ld = (int)(r % rd);
+    const int c = (int)(r / rd);
+    const int b = __ldg(tab + win * 4), sd = __ldg(tab + win * 4 + 1), sh = __ldg(tab + win * 4 + 2), sw = __ldg(tab + win * 4 + 3);
+    const T* src = vol + ((((long long)b * C + c) * D + sd + ld) * H + sh + lh) * W + sw + wv * V;
+    T* dst = out + ((((long long)win * C + c) * rd + ld) * rh + lh) * (long long)rw + wv * V;
+    *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+  }
+}
+
 // blend_fused.cu
 int launch_blend8_lean(const BlendParams& p, int out_dtype, cudaStream_t st);
 int launch_blend_resample(const BlendParams& p, const double* m, int oD, int oH, int oW, int interp, int pad, int mode, int pred_dtype,
@@ -723,13 +747,24 @@ extern "C" int b200_sw_blend(const b200_blend_desc* dsc, int mode, void* stream)
 }
 
 extern "C" int b200_sw_gather(const void* vol, int in_dtype, void* out, int out_dtype, const int32_t* win_tab,
-                              int n_win, int C, int D, int H, int W, int rd, int rh, int rw, void* stream) {
+                              int n_win, int C, int D, int H, int W, int rd, int rh, int rw, int starts_w_align, void* stream) {
   if (n_win == 0) return B200_OK;
   B200_REQUIRE(vol && out && win_tab, "sw_gather: null pointer");
   B200_REQUIRE(rd <= D && rh <= H && rw <= W, "sw_gather: roi larger than the volume");
+  cudaStream_t st = (cudaStream_t)stream;
+  // vector path: equal dtypes and everything along W aligned to 16 bytes; `starts_w_align` is the caller's promise about the
+  // window starts along W (a common divisor of all of them; 0 / 1 = unknown), which cannot be seen from here
+  const int esz = in_dtype == B200_DT_F16 ? 2 : 4, V = 16 / esz;
+  if (in_dtype == out_dtype && starts_w_align >= V && starts_w_align % V == 0 && rw % V == 0 && W % V == 0 && reinterpret_cast<uintptr_t>(vol) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    const long long total = (long long)n_win * C * rd * rh * (rw / V);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+    if (in_dtype == B200_DT_F16) sw_gather_vec_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)vol, (__half*)out, win_tab, n_win, C, D, H, W, rd, rh, rw);
+    else sw_gather_vec_kernel<float><<<blocks, 256, 0, st>>>((const float*)vol, (float*)out, win_tab, n_win, C, D, H, W, rd, rh, rw);
+    B200_LAUNCH_CHECK("sw_gather_vec_kernel");
+    return B200_OK;
+  }
   B200_REQUIRE((long long)n_win * C <= 65535 && (long long)rd * rh <= 65535, "sw_gather: batch too large for one launch");
   dim3 block(rw >= 128 ? 128 : 64), grid(ceil_div(rw, block.x), rd * rh, n_win * C);
-  cudaStream_t st = (cudaStream_t)stream;
 #define LG(TI, TO) sw_gather_kernel<TI, TO><<<grid, block, 0, st>>>((const TI*)vol, (TO*)out, win_tab, C, D, H, W, rd, rh, rw)
   if (in_dtype == B200_DT_F16 && out_dtype == B200_DT_F16) LG(__half, __half);
   else if (in_dtype == B200_DT_F16 && out_dtype == B200_DT_F32) LG(__half, float);

@@ -88,16 +88,65 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActP p) {
 
 using namespace b200;
 
+// chunked form: block (chunk, plane) adds its slice in a fixed order and writes one {sum, sumsq} pair; stats_finish_kernel then adds
+// the chunks of a plane in chunk order in double precision
+template <typename T>
+__global__ void __launch_bounds__(256) instnorm_partial_kernel(const T* __restrict__ x, int C, long long S, long long stride_n, long long chunk,
+                                                               float* __restrict__ part) {
+  const int nc = blockIdx.y;
+  const int n = nc / C, c = nc % C;
+  const T* p = x + (long long)n * stride_n + (long long)c * S;
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(S, lo + chunk);
+  float s = 0.f, q = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float v = io<T>::ld(p + i);
+    s += v; q = fmaf(v, v, q);
+  }
+  s = warp_sum(s); q = warp_sum(q);
+  __shared__ float ss[8], sq[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { ss[wid] = s; sq[wid] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int w = 0; w < 8; ++w) { ts += ss[w]; tq += sq[w]; }
+    part[((long long)nc * gridDim.x + blockIdx.x) * 2] = ts;
+    part[((long long)nc * gridDim.x + blockIdx.x) * 2 + 1] = tq;
+  }
+}
+
+static int instnorm_chunks(int N, int C, long long S) {
+  // enough blocks to fill the chip when there are few planes, at least 16 K elements per block
+  const long long want = (long long)num_sms() * 4 / std::max(1LL, (long long)N * C);
+  return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(want, 256), S / 16384));
+}
+
+extern "C" long long b200_instnorm_stats_workspace_bytes(int N, int C, long long S) {
+  if (N <= 0 || C <= 0 || S <= 0) return -1;
+  const int ch = instnorm_chunks(N, C, S);
+  return ch > 1 ? (long long)N * C * ch * 2 * (long long)sizeof(float) : 0;
+}
+
 extern "C" int b200_instnorm_stats(const void* x, int dtype, int N, int C, long long S, long long x_stride_n,
-                                   float* stats, void* stream) {
+                                   float* stats, void* workspace, void* stream) {
   B200_REQUIRE(x && stats, "instnorm_stats: null pointer");
   B200_REQUIRE(N > 0 && C > 0 && S > 0, "instnorm_stats: empty problem");
+  B200_REQUIRE(dtype == B200_DT_F16 || dtype == B200_DT_F32, "instnorm_stats: bad dtype");
   cudaStream_t st = (cudaStream_t)stream;
+  const int ch = workspace ? instnorm_chunks(N, C, S) : 1;
+  if (ch > 1) {
+    B200_REQUIRE((long long)N * C <= 65535, "instnorm_stats: N*C too large for one launch");
+    const long long chunk = ((S + ch - 1) / ch + 255) / 256 * 256;
+    dim3 grid(ch, N * C);
+    if (dtype == B200_DT_F16) instnorm_partial_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, C, S, x_stride_n, chunk, (float*)workspace);
+    else instnorm_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, C, S, x_stride_n, chunk, (float*)workspace);
+    B200_LAUNCH_CHECK("instnorm_partial_kernel");
+    return launch_stats_finish((const float*)workspace, (long long)N * C, ch, 1, 1, 1, stats, st);
+  }
   const int threads = S >= 32768 ? 1024 : (S >= 4096 ? 256 : 64);
   dim3 grid(N * C);
   if (dtype == B200_DT_F16) instnorm_stats_kernel<__half><<<grid, threads, 0, st>>>((const __half*)x, C, S, x_stride_n, stats);
-  else if (dtype == B200_DT_F32) instnorm_stats_kernel<float><<<grid, threads, 0, st>>>((const float*)x, C, S, x_stride_n, stats);
-  else return set_err(B200_ERR_INVALID, "instnorm_stats: bad dtype");
+  else instnorm_stats_kernel<float><<<grid, threads, 0, st>>>((const float*)x, C, S, x_stride_n, stats);
   B200_LAUNCH_CHECK("instnorm_stats_kernel");
   return B200_OK;
 }

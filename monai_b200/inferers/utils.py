@@ -352,6 +352,7 @@ def _swi_core(inputs, roi_size, sw_batch_size, predictor, overlap, mode, sigma_s
             else compute_importance_map(valid_patch_size, mode_s, sigma_scale, sw_dev, compute_dtype)
         )
 
+    w_align = math.gcd(16, *[int(v) for v in starts3[2]])   # the gather copies 16-byte vectors when the W starts allow it
     win_tab_all = torch.tensor(
         [(b, *s) for b in range(batch_size) for s in flat_starts], dtype=torch.int32, device=sw_dev
     ).reshape(-1, 4)
@@ -416,7 +417,7 @@ def _swi_core(inputs, roi_size, sw_batch_size, predictor, overlap, mode, sigma_s
             tab = win_tab_all[slice_range.start : slice_range.stop]
         else:
             tab = win_tab_all[torch.tensor(slice_range, dtype=torch.int64, device=sw_dev)]
-        win_data3 = K.sw_gather(x3, tab, roi3)
+        win_data3 = K.sw_gather(x3, tab, roi3, w_align=w_align)
         win_data = win_data3.reshape(win_data3.shape[0], win_data3.shape[1], *roi_size)
         if with_coord:
             unravel_slice = [

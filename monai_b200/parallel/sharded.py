@@ -210,7 +210,7 @@ class ShardedSlidingWindowInferer:
                            box=(int(starts[0][lo_l]), int(starts[0][hi_l]) + roi[0], 0, 0))
 
             for g in range(0, len(ids), self.sw_batch_size):
-                win = K.sw_gather(x, tab[g : g + self.sw_batch_size], roi)
+                win = K.sw_gather(x, tab[g : g + self.sw_batch_size], roi, w_align=math.gcd(16, *[int(v) for v in starts[2]]))
                 seg = network(win, *args, **kwargs)
                 if not isinstance(seg, torch.Tensor) or tuple(seg.shape[2:]) != tuple(roi):
                     raise NotImplementedError("sharded inference supports single-tensor predictors at the input resolution")
