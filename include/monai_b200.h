@@ -230,6 +230,15 @@ long long b200_gemm_tc_workspace_bytes(const b200_gemm_tc_desc* desc);
 int b200_gemm_tc(const b200_gemm_tc_desc* desc, const void* x, const void* packed_w, const float* bias, const void* res,
                  const int32_t* row_map, void* y, float* stats, void* workspace, void* stream);
 
+/* Fused transformer MLP of a Swin block, one launch (swin_unetr.py:675-698: x + mlp(norm2(x)); blocks/mlp.py:75-80):
+ *   y = x + W2 * gelu(W1 * LayerNorm(x) + b1) + b2,   x, y NC8 fp16 [Nb][C/8][S][8] (y may not alias x).
+ * packed_w1 / packed_w2 are b200_gemm_tc_pack_weight() images of linear1.weight [hidden, C] and linear2.weight [C, hidden].
+ * The hidden activations stay in shared memory.  Implemented for C = 48, hidden = 192 (anything else: B200_ERR_INVALID_ARGUMENT,
+ * callers use layernorm_nc8 + two gemm_tc). */
+int b200_mlp_fused_tc(const void* x, int x_ctot, int Nb, int S, int C, int hidden, const void* packed_w1, const float* b1,
+                      const void* packed_w2, const float* b2, const float* gamma, const float* beta, float eps, void* y,
+                      int y_ctot, void* stream);
+
 /* LayerNorm over channels of NC8 tokens with an optional row gather (window partition + cyclic shift + zero pad of
  * swin_unetr.py:596-625): y[n, :, r] = LN(x[n, :, src[r]]) (src[r] < 0 -> zeros; src == NULL -> identity).
  * gamma/beta NULL = no affine (SwinTransformer.proj_out, swin_unetr.py:1040-1053).  src is shared by all batch items. */

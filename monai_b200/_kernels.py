@@ -540,6 +540,23 @@ def gemm_tc(
     return out, stats
 
 
+MLP_FUSED = os.environ.get("B200_MLP_UNFUSED", "") == ""   # B200_MLP_UNFUSED=1: layernorm_nc8 + two gemm_tc (A/B measurements)
+
+
+def mlp_fused_supported(C_: int, hidden: int) -> bool:
+    return MLP_FUSED and C_ == 48 and hidden == 192
+
+
+def mlp_fused_tc(x: NC8, packed_w1: torch.Tensor, b1: torch.Tensor, packed_w2: torch.Tensor, b2: torch.Tensor, hidden: int,
+                 gamma: torch.Tensor | None, beta: torch.Tensor | None, eps: float = 1e-5) -> NC8:
+    """x + fc2(gelu(fc1(LayerNorm(x)))) in one launch (hidden activations never reach HBM)."""
+    out = NC8(x.N, x.C, x.sp, x.buf.device)
+    _call("mlp_fused_tc", L.ptr(x.buf), x.C, x.N, x.S, x.C, hidden, L.ptr(packed_w1), L.ptr(_f32c(b1)), L.ptr(packed_w2), L.ptr(_f32c(b2)),
+          L.ptr(_f32c(gamma)), L.ptr(_f32c(beta)), float(eps), L.ptr(out.buf), out.C, L.stream_ptr(x.buf.device),
+          flops=4.0 * x.N * x.S * x.C * hidden, nbytes=float(x.N * x.S * x.C * 2 * 3))
+    return out
+
+
 def layernorm_nc8(x: NC8, gamma: torch.Tensor | None, beta: torch.Tensor | None, eps: float = 1e-5, src: torch.Tensor | None = None,
                   out_sp: Sequence[int] | None = None, out: NC8 | None = None) -> NC8:
     """LayerNorm over channels; with `src` (int32 [S_out]) the output rows are gathered (−1 = zero row)."""

@@ -456,9 +456,15 @@ class SwinUNETR(GraphedForward, nn.Module):
                                              region if any(s > 0 for s in ss) else None)
             # x = shortcut + window_reverse(proj(att)): scattered back through the same table, residual fused
             x1, _ = K.gemm_tc(att, self._wlin(blk.attn.proj.weight, bkey + ".proj"), C, C, bias=blk.attn.proj.bias, res=cur, row_map=src, out_sp=dims, mode=1)
-            y = K.layernorm_nc8(x1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-            h, _ = K.gemm_tc(y, self._wlin(blk.mlp.linear1.weight, bkey + ".fc1"), C, blk.mlp.linear1.out_features, bias=blk.mlp.linear1.bias, act=L.ACT_GELU)
-            cur, _ = K.gemm_tc(h, self._wlin(blk.mlp.linear2.weight, bkey + ".fc2"), blk.mlp.linear1.out_features, C, bias=blk.mlp.linear2.bias, res=x1)
+            hid = blk.mlp.linear1.out_features
+            w1, w2 = self._wlin(blk.mlp.linear1.weight, bkey + ".fc1"), self._wlin(blk.mlp.linear2.weight, bkey + ".fc2")
+            if K.mlp_fused_supported(C, hid):
+                # x = x + mlp(norm2(x)) in one launch: the 4C-wide hidden tensor never reaches HBM
+                cur = K.mlp_fused_tc(x1, w1, blk.mlp.linear1.bias, w2, blk.mlp.linear2.bias, hid, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+            else:
+                y = K.layernorm_nc8(x1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+                h, _ = K.gemm_tc(y, w1, C, hid, bias=blk.mlp.linear1.bias, act=L.ACT_GELU)
+                cur, _ = K.gemm_tc(h, w2, hid, C, bias=blk.mlp.linear2.bias, res=x1)
         if layer.downsample is not None:
             ds = layer.downsample
             m = K.patch_merge_ln_nc8(cur, ds.norm.weight, ds.norm.bias, ds.norm.eps, v2=ds.v2)

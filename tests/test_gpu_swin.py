@@ -46,6 +46,37 @@ def test_gemm_tc_linear_bias_gelu_residual():
         assert _rel(got.numpy(), ref2.numpy()) < 3e-3, (S, Kd, N)
 
 
+def test_fused_mlp_matches_reference_math_and_the_unfused_kernels():
+    """x + fc2(gelu(fc1(LN(x)))) -- monai/networks/nets/swin_unetr.py:675-698 with blocks/mlp.py:75-80 -- in one launch."""
+    g = torch.Generator().manual_seed(3)
+    C, Hd = 48, 192
+    for (Nb, S) in [(1, 128), (2, 1000), (3, 128 * 151 + 77), (4, 110592)]:
+        x = (torch.randn((Nb, C, 1, 1, S), generator=g) * 1.5 + 0.3).half()
+        w1 = (torch.randn((Hd, C), generator=g) / C**0.5).half()
+        w2 = (torch.randn((C, Hd), generator=g) / Hd**0.5).half()
+        b1, b2 = torch.randn(Hd, generator=g) * 0.2, torch.randn(C, generator=g) * 0.2
+        gam, bet = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+        xd = _to_nc8(x)
+        p1, p2 = K.gemm_tc_pack_weight(w1.to(DEV)), K.gemm_tc_pack_weight(w2.to(DEV))
+        out = K.mlp_fused_tc(xd, p1, b1.to(DEV), p2, b2.to(DEV), Hd, gam.to(DEV), bet.to(DEV), 1e-5)
+        got = K.unpack_nc8(out, dtype=torch.float32).reshape(Nb, C, S)
+        # the unfused kernels (LayerNorm, two GEMMs): the fused path rounds the same intermediates to fp16
+        y = K.layernorm_nc8(xd, gam.to(DEV), bet.to(DEV), 1e-5)
+        h, _ = K.gemm_tc(y, p1, C, Hd, bias=b1.to(DEV), act=L.ACT_GELU)
+        o2, _ = K.gemm_tc(h, p2, Hd, C, bias=b2.to(DEV), res=xd)
+        unf = K.unpack_nc8(o2, dtype=torch.float32).reshape(Nb, C, S)
+        d_unf = float((got - unf).abs().max())
+        assert d_unf < 4e-3 * float(unf.abs().max()), (Nb, S, d_unf)
+        if S <= 20000:
+            xt = x.float().reshape(Nb, C, S).transpose(1, 2).to(DEV)
+            ref = xt + F.linear(F.gelu(F.linear(F.layer_norm(xt, (C,), gam.to(DEV), bet.to(DEV), 1e-5), w1.float().to(DEV), b1.to(DEV))), w2.float().to(DEV), b2.to(DEV))
+            r = _rel(got.transpose(1, 2).cpu().numpy(), ref.cpu().numpy())
+            assert r < 3e-3, (Nb, S, r)
+        # run to run bit-identical
+        out2 = K.mlp_fused_tc(xd, p1, b1.to(DEV), p2, b2.to(DEV), Hd, gam.to(DEV), bet.to(DEV), 1e-5)
+        assert torch.equal(out.buf, out2.buf)
+
+
 def test_gemm_tc_conv_transpose_k2s2_and_1x1_stats():
     g = torch.Generator().manual_seed(1)
     x = torch.randn((2, 96, 3, 5, 6), generator=g).half()
