@@ -25,11 +25,14 @@ def profile_start() -> None:
     _Prof.on, _Prof.events = True, []
 
 
-def profile_stop() -> dict:
+def profile_stop(by_shape: bool = False) -> dict:
+    """Totals per entry point; with `by_shape` launches are further split by their (flops, bytes) signature."""
     torch.cuda.synchronize()
     _Prof.on = False
     out: dict = {}
     for name, e0, e1, flops, nbytes in _Prof.events:
+        if by_shape:
+            name = f"{name} [{flops / 1e9:.2f} GF, {nbytes / 1e6:.1f} MB]"
         d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
         d["ms"] += e0.elapsed_time(e1)
         d["n"] += 1

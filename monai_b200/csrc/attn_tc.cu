@@ -12,17 +12,22 @@
 // removes the per-element table lookup and mask test that bounded the mma.sync kernel (swin.cu) -- with head_dim 16 the
 // tensor pipe is otherwise idle.  Padded keys carry B' = -30000 (P = 0).  Scores are in log2 units: the caller folds
 // scale * log2(e) into the q rows of the qkv projection.
-//   softmax: 16 warps, four threads per query row: exact row maximum from TMEM (pass 1), then
-//            P = ex2(S - max) in fp32, packed to fp16 and written straight into the K-major core-matrix image
-//            of an A operand in shared memory (pass 2);
-//   O[128 x 32] = P [V | 1 | 0]                 n_pad/16 tcgen05.mma, V read in place as an MN-major B operand (NC8 rows
-//            are 16-byte vectors of 8 dims), the ones column accumulates the row sums in fp32;
-//   epilogue: O / rowsum -> fp16 NC8.
+//   softmax: the two key halves of a tile are INDEPENDENT pipelines (flash-attention style): each half has its own exact row
+//            maximum m_h (pass 1 over TMEM), its own P_h = ex2(S_h - m_h) -- fp32 MUFU, packed to fp16 and written straight into
+//            the K-major core-matrix image of an A operand in shared memory (pass 2) -- and its own accumulator
+//   O_h[128 x 32] = P_h [V | 1 | 0]_h           n_pad/32 tcgen05.mma, V read in place as an MN-major B operand (NC8 rows
+//            are 16-byte vectors of 8 dims); the ones column accumulates the row sums l_h in fp32;
+//   epilogue: O = (a0 O0 + a1 O1) / (a0 l0 + a1 l1), a_h = 2^(m_h - max(m0, m1))  -> fp16 NC8.
+// Because no maximum is shared between the halves, the tensor pipe computes PV_h(i) and S_h(i+1) for one half while the softmax
+// warps of the OTHER half exponentiate: TMEM has room for one S tile only (2 x 176 + 2 x 32 + 64 identity columns), and the
+// earlier single-maximum version (both halves needed before any exponential) left every softmax warp idle for the ~1 000 cycles
+// the S MMAs of the next tile take -- 8 300 cycles per tile against a MUFU floor of 2 816 (ncu: 33 % issue-active, MUFU 38 %,
+// tensor 25 %).
 // Q, K, V tiles are 1-D bulk copies of NC8 rows (contiguous per 8-channel chunk).
 //
-// Warp roles (576 threads): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-17 = softmax / epilogue (four
-// threads per query row, each with a share of the 16-column chunks of both key halves: 4 warps per scheduler hide the TMEM /
-// MUFU latencies that 2 per scheduler left exposed -- ncu: 33 % issue-active, MUFU 38 %, tensor 25 % with 8 softmax warps).
+// Warp roles (576 threads): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = softmax of key half 0,
+// warps 10-17 = softmax of key half 1 (+ the epilogue); the two threads of a (query row, half) split its 16-column chunks and
+// exchange their maxima through shared memory and a 64-thread named barrier.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "../../include/monai_b200.h"
@@ -33,8 +38,8 @@ constexpr int kAtNPadMax = 352;                       // keys per window, padded
 constexpr int kAtKChunk = kAtNPadMax * 16;            // bytes of one 8-dim chunk of K / V in shared memory
 constexpr int kAtBiasBytes = 16 * kAtNPadMax * 16;    // 16 chunks of 8 query rows
 constexpr int kAtPBytes = (kAtNPadMax / 8) * 2048;    // P: [key block of 8][128 rows][16 B]
-constexpr int kAtColS1 = 176, kAtColO = 352, kAtColI = 384;   // TMEM columns: S half 0 at 0, half 1, O, identity (64)
-constexpr int kAtSmem = kAtBiasBytes + kAtPBytes + 2 * 2048 + 2 * kAtKChunk + 4 * kAtKChunk + 4 * 128 * 4 + 256 + 128;
+constexpr int kAtColS1 = 176, kAtColO0 = 352, kAtColI = 384, kAtColO1 = 448;   // TMEM columns: S half 0 at 0, S half 1, O of half 0 (32), identity (64), O of half 1 (32)
+constexpr int kAtSmem = kAtBiasBytes + kAtPBytes + 2 * 2048 + 2 * kAtKChunk + 4 * kAtKChunk + 8 * 128 * 4 + 256 + 128;
 constexpr float kAtPadBias = -30000.f;
 
 struct AttnTcParams {
@@ -77,29 +82,36 @@ __device__ __forceinline__ uint32_t exp2_pack(float a, float b, float m) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-constexpr int kAtSplit = 4;                 // softmax threads per query row (each takes a share of the 16-column chunks)
-constexpr int kAtThreads = 64 + 128 * kAtSplit;
+// running maximum of 16 fp32 TMEM values (FMNMX3: two values per instruction)
+__device__ __forceinline__ float max16(const uint32_t (&v)[16], float m) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) asm("max.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
+  return m;
+}
+
+constexpr int kAtThreads = 64 + 512;        // producer, MMA issuer, 16 softmax warps (2 key halves x 2 threads per query row)
 
 __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* s_bias = smem;
   uint8_t* s_p = s_bias + kAtBiasBytes;
   uint8_t* s_q = s_p + kAtPBytes;
   uint8_t* s_k = s_q + 2 * 2048;
   uint8_t* s_v = s_k + 2 * kAtKChunk;                 // 4 chunk slots: V dims 0-7, 8-15, ones column, zeros
-  float* s_max = reinterpret_cast<float*>(s_v + 4 * kAtKChunk);   // [kAtSplit][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_max + 128 * kAtSplit);
+  float* s_max = reinterpret_cast<float*>(s_v + 4 * kAtKChunk);   // [half][sub][128]: maxima exchanged by the two threads of a (row, half)
+  float* s_hmax = s_max + 4 * 128;                                // [tile parity][half][128]: half maxima for the epilogue
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hmax + 4 * 128);
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* s_full = bars + 2;      // [2]
   uint64_t* s_empty = bars + 4;     // [2]
   uint64_t* p_full = bars + 6;      // [2]
   uint64_t* v_full = bars + 8;
-  uint64_t* pv_done = bars + 9;
-  uint64_t* o_empty = bars + 10;
-  uint64_t* init_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* pv_done = bars + 9;     // [2]
+  uint64_t* o_empty = bars + 11;
+  uint64_t* init_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = p.n, n_pad = p.n_pad, NH = n_pad / 2;
@@ -108,9 +120,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
   const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
 
   if (threadIdx.x == 0) {
-    tc::mbar_init(qk_full, 1); tc::mbar_init(qk_empty, 1); tc::mbar_init(v_full, 1); tc::mbar_init(pv_done, 1);
+    tc::mbar_init(qk_full, 1); tc::mbar_init(qk_empty, 1); tc::mbar_init(v_full, 1);
     tc::mbar_init(o_empty, 128); tc::mbar_init(init_done, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128 * kAtSplit); tc::mbar_init(&p_full[i], 128 * kAtSplit); }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 256); tc::mbar_init(&p_full[i], 256); tc::mbar_init(&pv_done[i], 1);
+    }
     tc::fence_barrier_init();
   }
   // zero Q / K / V (rows the bulk copies never write must be finite), the ones column, and the identity (staged in the P region)
@@ -156,7 +170,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
           tc::bulk_load(s_q + c * 2048, base + ((long long)(2 * t.h + c) * T + row0 + t.rt * 128) * 8, rows * 16, qk_full);
           tc::bulk_load(s_k + c * kAtKChunk, base + ((long long)(p.C8 + 2 * t.h + c) * T + row0) * 8, n * 16, qk_full);
         }
-        if (it > 0) tc::mbar_wait(pv_done, (uint32_t)((it - 1) & 1));   // the PV MMAs of the previous tile (readers of V) are done
+        if (it > 0) tc::mbar_wait(&pv_done[1], (uint32_t)((it - 1) & 1));   // the PV MMAs of the previous tile (readers of V) are done
         tc::mbar_arrive_expect_tx(v_full, 2u * n * 16u);
         for (int c = 0; c < 2; ++c)
           tc::bulk_load(s_v + c * kAtKChunk, base + ((long long)(2 * p.C8 + 2 * t.h + c) * T + row0) * 8, n * 16, v_full);
@@ -189,19 +203,21 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
       if (leader) tc::mma_commit(&s_full[hf]);
       __syncwarp();
     };
-    // O (+)= P V for one key half
+    // O_hf = P_hf [V | 1 | 0]_hf: every key half has its own accumulator (its probabilities are scaled by its own row maximum)
     auto issue_pv = [&](int hf) {
+      const uint32_t to = tm + (hf ? kAtColO1 : kAtColO0);
       for (int s = 0; s < NH / 16; ++s) {
         const int ks = hf * (NH / 16) + s;
         const uint64_t pd = tc::make_desc_kmajor_noswz(p_a + ks * 4096, 2048, 128);
         // MN-major B: 8 keys x 16 B (8 dims) per core matrix, next 8 keys +128 B (LBO), next 8 dims +chunk (SBO)
         const uint64_t vd = tc::make_desc_kmajor_noswz(v_a + ks * 256, 128, kAtKChunk);
-        if (leader) tc::mma_f16_ss(tm + kAtColO, pd, vd, idesc_pv, (hf | s) != 0 ? 1u : 0u);
+        if (leader) tc::mma_f16_ss(to, pd, vd, idesc_pv, s != 0 ? 1u : 0u);
       }
+      if (leader) tc::mma_commit(&pv_done[hf]);
+      __syncwarp();
     };
-    // Software pipeline across tiles: the S MMAs of tile i+1 are issued as soon as the softmax threads have drained the
-    // matching half of tile i, i.e. they run on the tensor pipe while the softmax of tile i is still exponentiating the
-    // other half -- the issue order is  PV0(i), S0(i+1), PV1(i), S1(i+1).
+    // Ping-pong between the key halves, across tiles: the issue order is  PV0(i), S0(i+1), PV1(i), S1(i+1) -- while the softmax
+    // warps of one half exponentiate, the tensor pipe works for the other half.
     const long long ntile = hi - lo;
     if (ntile > 0) {
       tc::mbar_wait(qk_full, 0u);
@@ -216,20 +232,18 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
       const bool more = it + 1 < ntile;
       tc::mbar_wait(v_full, ph);
       tc::mbar_wait(&p_full[0], ph);
-      tc::mbar_wait(o_empty, ph ^ 1);               // the epilogue has read O of the previous tile
+      tc::mbar_wait(o_empty, ph ^ 1);               // the epilogue has read O0 / O1 of the previous tile
       tc::fence_after_sync();
       issue_pv(0);
       if (more) {
         tc::mbar_wait(qk_full, ph ^ 1);             // Q, K (and bias) of tile it+1 have landed
-        tc::mbar_wait(&s_empty[0], ph);             // every softmax thread has read half 0 of tile it
+        tc::mbar_wait(&s_empty[0], ph);             // the softmax threads of half 0 have read S0 of tile it
         tc::fence_after_sync();
         issue_s(0);
       }
       tc::mbar_wait(&p_full[1], ph);
       tc::fence_after_sync();
       issue_pv(1);
-      if (leader) tc::mma_commit(pv_done);
-      __syncwarp();
       if (more) {
         tc::mbar_wait(&s_empty[1], ph);
         tc::fence_after_sync();
@@ -240,49 +254,50 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
     }
     __syncwarp();
   } else {
-    // ===================== softmax + epilogue (warps 2..9) =====================
-    const int jj = (warp - 2) >> 2;           // the kAtSplit threads of a query row split the 16-column chunks of each key half
+    // ===================== softmax + epilogue (warps 2..17) =====================
+    // Warps 2-9 own key half 0, warps 10-17 key half 1; the two threads of a (query row, half) split its 16-column chunks.
+    const int jj = (warp - 2) >> 2;
+    const int hf = jj >> 1, sub = jj & 1;
     const int q = warp & 3;                   // TMEM lane quarter
     const int row = q * 32 + lane;
     const int nchunk = NH / 16;
-    const int c_lo = (jj * nchunk) / kAtSplit, c_hi = ((jj + 1) * nchunk) / kAtSplit;
+    // half 1 / sub 0 also runs the epilogue: it takes the smaller share
+    const int c_split = hf ? nchunk / 2 : (nchunk + 1) / 2;
+    const int c_lo = sub ? c_split : 0, c_hi = sub ? nchunk : c_split;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t to = tlane + kAtColO;
+    const uint32_t ts = tlane + hf * kAtColS1;
+    uint8_t* prow = s_p + (hf * NH / 8) * 2048 + row * 16;
+    const int bar_id = 1 + hf * 4 + q;
     int it = 0;
     for (long long f = lo; f < hi; ++f, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      // ---- pass 1: exact row maximum (this thread's chunks of both halves)
+      // ---- pass 1: exact maximum of this key half of the row
       float m = -INFINITY;
-      for (int hf = 0; hf < 2; ++hf) {
-        tc::mbar_wait(&s_full[hf], ph);
-        tc::fence_after_sync();
-        const uint32_t ts = tlane + hf * kAtColS1;
+      tc::mbar_wait(&s_full[hf], ph);
+      tc::fence_after_sync();
+      {
         uint32_t va[16], vb[16];
         if (c_lo < c_hi) tc::tmem_ld16(ts + c_lo * 16, va);
         for (int c = c_lo; c < c_hi; c += 2) {
           tc::tmem_ld_wait16(va);
           if (c + 1 < c_hi) tc::tmem_ld16(ts + (c + 1) * 16, vb);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(va[j]));
+          m = max16(va, m);
           if (c + 1 < c_hi) {
             tc::tmem_ld_wait16(vb);
             if (c + 2 < c_hi) tc::tmem_ld16(ts + (c + 2) * 16, va);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(vb[j]));
+            m = max16(vb, m);
           }
         }
       }
-      s_max[jj * 128 + row] = m;
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * kAtSplit) : "memory");
-#pragma unroll
-      for (int k = 0; k < kAtSplit; ++k) m = fmaxf(m, s_max[k * 128 + row]);
-      // P buffer free?  (first tile: the identity staged there has been copied to TMEM)
+      s_max[(hf * 2 + sub) * 128 + row] = m;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      m = fmaxf(m, s_max[(hf * 2 + (sub ^ 1)) * 128 + row]);
+      if (sub == 0) s_hmax[((it & 1) * 2 + hf) * 128 + row] = m;     // read by the epilogue of this tile
+      // P half free?  (first tile: the identity staged in the P region has been copied to TMEM)
       if (it == 0) tc::mbar_wait(init_done, 0u);
-      else tc::mbar_wait(pv_done, (uint32_t)((it - 1) & 1));
-      // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs, half by half
-      for (int hf = 0; hf < 2; ++hf) {
-        const uint32_t ts = tlane + hf * kAtColS1;
-        uint8_t* prow = s_p + (hf * NH / 8) * 2048 + row * 16;
+      else tc::mbar_wait(&pv_done[hf], (uint32_t)((it - 1) & 1));
+      // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs
+      {
         uint32_t va[16], vb[16];
         auto emit = [&](const uint32_t (&v)[16], int c) {
           uint4 u0, u1;
@@ -308,34 +323,46 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
             emit(vb, c + 1);
           }
         }
-        tc::fence_proxy_async();       // P (generic-proxy stores) -> visible to the tensor core
-        tc::fence_before_sync();       // this thread's TMEM reads of this S half are complete
-        tc::mbar_arrive(&p_full[hf]);
-        tc::mbar_arrive(&s_empty[hf]);
       }
-      if (jj == 0) {
-        // ---- epilogue: O / rowsum -> fp16 NC8
+      tc::fence_proxy_async();       // P (generic-proxy stores) -> visible to the tensor core
+      tc::fence_before_sync();       // this thread's TMEM reads of this S half are complete
+      tc::mbar_arrive(&p_full[hf]);
+      tc::mbar_arrive(&s_empty[hf]);
+      if (hf == 1 && sub == 0) {
+        // ---- epilogue: combine the two halves (flash-attention style) and normalise:  O = (a0 O0 + a1 O1) / (a0 l0 + a1 l1),
+        //      a_h = 2^(m_h - max(m0, m1)), l_h = the ones column of O_h
         const AttnTile t = attn_decode(p, f);
-        tc::mbar_wait(pv_done, ph);
+        tc::mbar_wait(&pv_done[0], ph);
+        tc::mbar_wait(&pv_done[1], ph);
         tc::fence_after_sync();
-        uint32_t o[16], o2[16];
-        tc::tmem_ld16(to, o);
-        tc::tmem_ld16(to + 16, o2);
-        tc::tmem_ld_wait16(o);
-        tc::tmem_ld_wait16(o2);
+        uint32_t o0[16], o1[16], l0[8], l1[8];
+        tc::tmem_ld16(tlane + kAtColO0, o0);
+        tc::tmem_ld8(tlane + kAtColO0 + 16, l0);
+        tc::tmem_ld16(tlane + kAtColO1, o1);
+        tc::tmem_ld8(tlane + kAtColO1 + 16, l1);
+        const float m0 = s_hmax[((it & 1) * 2 + 0) * 128 + row], m1 = m;
+        tc::tmem_ld_wait();
         tc::fence_before_sync();
         tc::mbar_arrive(o_empty);
         const int r = t.rt * 128 + row;
         if (r < n) {
-          const float inv = 1.f / __uint_as_float(o2[0]);
+          const float mm = fmaxf(m0, m1);
+          float a0, a1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(m0 - mm));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(m1 - mm));
+          const float inv = 1.f / (a0 * __uint_as_float(l0[0]) + a1 * __uint_as_float(l1[0]));
+          a0 *= inv; a1 *= inv;
           __half* ob = p.out + (long long)t.b * p.C8 * T * 8 + ((long long)t.w * n + r) * 8;
 #pragma unroll
           for (int dt = 0; dt < 2; ++dt) {
             uint4 hv;
             __half2* hp = reinterpret_cast<__half2*>(&hv);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              hp[j] = __floats2half2_rn(__uint_as_float(o[dt * 8 + 2 * j]) * inv, __uint_as_float(o[dt * 8 + 2 * j + 1]) * inv);
+            for (int j = 0; j < 4; ++j) {
+              const int k = dt * 8 + 2 * j;
+              hp[j] = __floats2half2_rn(a0 * __uint_as_float(o0[k]) + a1 * __uint_as_float(o1[k]),
+                                        a0 * __uint_as_float(o0[k + 1]) + a1 * __uint_as_float(o1[k + 1]));
+            }
             *reinterpret_cast<uint4*>(ob + (long long)(2 * t.h + dt) * T * 8) = hv;
           }
         }

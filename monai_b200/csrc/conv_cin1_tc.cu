@@ -60,7 +60,7 @@ template <typename T, int KS, int STRIDE, int NT, int BD>
 __global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcParams p) {
   using Cfg = Cin1Cfg<KS, STRIDE, NT, BD>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* smem_a = smem;                                        // [kStages][BD][kKP/8][128][16 B]
   uint8_t* smem_h = smem_a + Cfg::kStages * Cfg::kAStage;        // [kStages] halo patches (fp16)
   uint8_t* smem_b = smem_h + Cfg::kStages * Cfg::kHaloBytes;     // packed weights

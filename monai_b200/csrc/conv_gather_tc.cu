@@ -100,7 +100,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int sr
 
 __global__ void __launch_bounds__(288, 1) conv_gather_tc_kernel(CgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   const int NT = p.NT;
   const int b_stage = kCgUnits * NT * 32;
   uint8_t* smem_a = smem;

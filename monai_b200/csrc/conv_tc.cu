@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
   using Cfg = ConvTcCfg<NT, BD>;
   constexpr int kSA = Cfg::kSA, kSB = Cfg::kSB, kNB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSA * Cfg::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSB * Cfg::kBTapBytes);

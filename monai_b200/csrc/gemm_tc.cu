@@ -82,7 +82,7 @@ __device__ __forceinline__ void gemm_tile(long long tile, int n_tiles, int row_t
 template <int MODE, int ACT, bool RES, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   const int NT = p.NT;
   const int b_stage = kGemmK16PerStage * NT * 32;
   uint8_t* smem_a = smem;

@@ -43,7 +43,7 @@ struct MlpParams {
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_tc_kernel(MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* s_x = smem;                                  // [2] X tiles (raw, then normalised in place)
   uint8_t* s_h = s_x + 2 * kMlpXBytes;                  // [2] hidden tiles (A operand of GEMM2)
   uint8_t* s_w1 = s_h + 2 * kMlpHBytes;

@@ -11,6 +11,8 @@ namespace b200 {
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 128-byte aligned start of the dynamic shared memory, derived by pointer arithmetic so the compiler keeps the address space
+__device__ __forceinline__ uint8_t* align_smem128(uint8_t* raw) { return raw + ((128u - (smem_u32(raw) & 127u)) & 127u); }
 
 // ---- mbarrier -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -1,6 +1,7 @@
 """GPU parity of the transform operator surface (Spacing / Spacingd / RandAffined / GaussianSmooth) vs the reference
 fixtures and the torch-CPU oracle.  fp32 resample tolerance 1e-3 relative (north star); measured errors are ~1e-5."""
 import ast
+import itertools
 import os
 
 import numpy as np
@@ -153,7 +154,24 @@ def test_lazy_resampling_and_invertd_match_the_real_reference(golden_dir):
         assert tuple(inv.shape) == tuple(g[f"inv.{tag}"].shape)
         diff = np.abs(inv.cpu().numpy() - g[f"inv.{tag}"])
         if nearest:
-            assert (diff > 1e-4).mean() < 2e-3, tag
+            # The inverse samples the 1 mm grid at c = 1.25 * i: every fourth index per axis is an exact .5 tie, which the
+            # reference (nearbyint on float32 coordinates that went through a normalise / un-normalise round trip) resolves by
+            # round-off.  Away from ties the value must be the reference's; on a tie it must be one of the two neighbours.
+            got, pr = inv.cpu().numpy(), g["pred"]
+            lo, hi, tie_ax = [], [], []
+            for n_out, n_in in zip(got.shape[1:], pr.shape[1:]):
+                c = 1.25 * np.arange(n_out)
+                tie = np.abs(c - np.floor(c) - 0.5) < 1e-6
+                lo.append(np.clip(np.where(tie, np.floor(c), np.rint(c)).astype(int), 0, n_in - 1))
+                hi.append(np.clip(np.where(tie, np.ceil(c), np.rint(c)).astype(int), 0, n_in - 1))
+                tie_ax.append(tie)
+            any_tie = tie_ax[0][:, None, None] | tie_ax[1][None, :, None] | tie_ax[2][None, None, :]
+            assert (diff[:, ~any_tie] > 1e-4).mean() < 2e-3, tag
+            ok = np.zeros(got.shape, dtype=bool)
+            for sel in itertools.product((0, 1), repeat=3):
+                idx = [(lo, hi)[s_][a] for a, s_ in enumerate(sel)]
+                ok |= np.abs(pr[:, idx[0]][:, :, idx[1]][:, :, :, idx[2]] - got) < 1e-4
+            assert ok.mean() > 1 - 2e-3, (tag, ok.mean())
         else:
             assert diff.max() < 2e-4, (tag, diff.max())
         np.testing.assert_allclose(np.asarray(inv.affine), g[f"inv.{tag}.affine"], atol=1e-6)
