@@ -76,8 +76,9 @@ __device__ __forceinline__ AttnTile attn_decode(const AttnTcParams& p, long long
 // MUFU form costs the same MUFU slots, one instruction less, and keeps the exponent argument in fp32.)
 __device__ __forceinline__ uint32_t exp2_pack(float a, float b, float m) {
   float ea, eb;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(a - m));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(b - m));
+  // volatile: keeps the exponentials BEHIND the tcgen05.ld of the next chunk in program order (the prefetch must be issued first)
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(a - m));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(b - m));
   const __half2 h = __floats2half2_rn(ea, eb);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
@@ -91,6 +92,7 @@ __device__ __forceinline__ float max16(const uint32_t (&v)[16], float m) {
 
 constexpr int kAtThreads = 64 + 512;        // producer, MMA issuer, 16 softmax warps (2 key halves x 2 threads per query row)
 
+template <int NPAD>
 __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -114,7 +116,9 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = p.n, n_pad = p.n_pad, NH = n_pad / 2;
+  // NPAD (keys per window, padded to a multiple of 32) is a template parameter: the softmax passes are straight-line code
+  constexpr int n_pad = NPAD, NH = NPAD / 2;
+  const int n = p.n;
   const long long T = (long long)p.nW * n;
   const long long total = (long long)p.N * p.nW * p.heads * p.nrt;
   const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
@@ -260,35 +264,41 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
     const int hf = jj >> 1, sub = jj & 1;
     const int q = warp & 3;                   // TMEM lane quarter
     const int row = q * 32 + lane;
-    const int nchunk = NH / 16;
-    // half 1 / sub 0 also runs the epilogue: it takes the smaller share
-    const int c_split = hf ? nchunk / 2 : (nchunk + 1) / 2;
-    const int c_lo = sub ? c_split : 0, c_hi = sub ? nchunk : c_split;
+    constexpr int nchunk = NH / 16;
+    // contiguous chunk ranges; the thread that also runs the epilogue (half 1 / sub 0) takes the smaller share
+    constexpr int kCMax = (nchunk + 1) / 2;                       // chunks of the larger share
+    const bool big = (sub == 0) != (hf == 1);                     // sub 0 of half 0 and sub 1 of half 1 take the larger share
+    const int cnt = big ? kCMax : nchunk - kCMax;                 // warp-uniform
+    const int c_lo = sub ? nchunk - cnt : 0;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t ts = tlane + hf * kAtColS1;
-    uint8_t* prow = s_p + (hf * NH / 8) * 2048 + row * 16;
+    const uint32_t ts = tlane + hf * kAtColS1 + c_lo * 16;        // this thread's first S column
+    uint8_t* prow = s_p + ((hf * NH) / 8 + 2 * c_lo) * 2048 + row * 16;
     const int bar_id = 1 + hf * 4 + q;
     int it = 0;
     for (long long f = lo; f < hi; ++f, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      // ---- pass 1: exact maximum of this key half of the row
-      float m = -INFINITY;
+      // ---- pass 1: exact maximum of this key half of the row (two independent running maxima)
+      float m = -INFINITY, m2 = -INFINITY;
       tc::mbar_wait(&s_full[hf], ph);
       tc::fence_after_sync();
       {
         uint32_t va[16], vb[16];
-        if (c_lo < c_hi) tc::tmem_ld16(ts + c_lo * 16, va);
-        for (int c = c_lo; c < c_hi; c += 2) {
-          tc::tmem_ld_wait16(va);
-          if (c + 1 < c_hi) tc::tmem_ld16(ts + (c + 1) * 16, vb);
-          m = max16(va, m);
-          if (c + 1 < c_hi) {
+        if (cnt > 0) tc::tmem_ld16(ts, va);
+#pragma unroll
+        for (int k = 0; k < kCMax; k += 2) {
+          if (k < cnt) {
+            tc::tmem_ld_wait16(va);
+            if (k + 1 < cnt) tc::tmem_ld16(ts + (k + 1) * 16, vb);
+            m = max16(va, m);
+          }
+          if (k + 1 < kCMax && k + 1 < cnt) {
             tc::tmem_ld_wait16(vb);
-            if (c + 2 < c_hi) tc::tmem_ld16(ts + (c + 2) * 16, va);
-            m = max16(vb, m);
+            if (k + 2 < cnt) tc::tmem_ld16(ts + (k + 2) * 16, va);
+            m2 = max16(vb, m2);
           }
         }
       }
+      m = fmaxf(m, m2);
       s_max[(hf * 2 + sub) * 128 + row] = m;
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       m = fmaxf(m, s_max[(hf * 2 + (sub ^ 1)) * 128 + row]);
@@ -299,28 +309,31 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
       // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs
       {
         uint32_t va[16], vb[16];
-        auto emit = [&](const uint32_t (&v)[16], int c) {
+        auto emit = [&](const uint32_t (&v)[16], int k) {
           uint4 u0, u1;
           u0.x = exp2_pack(__uint_as_float(v[0]), __uint_as_float(v[1]), m);
           u0.y = exp2_pack(__uint_as_float(v[2]), __uint_as_float(v[3]), m);
           u0.z = exp2_pack(__uint_as_float(v[4]), __uint_as_float(v[5]), m);
           u0.w = exp2_pack(__uint_as_float(v[6]), __uint_as_float(v[7]), m);
+          *reinterpret_cast<uint4*>(prow + (2 * k) * 2048) = u0;
           u1.x = exp2_pack(__uint_as_float(v[8]), __uint_as_float(v[9]), m);
           u1.y = exp2_pack(__uint_as_float(v[10]), __uint_as_float(v[11]), m);
           u1.z = exp2_pack(__uint_as_float(v[12]), __uint_as_float(v[13]), m);
           u1.w = exp2_pack(__uint_as_float(v[14]), __uint_as_float(v[15]), m);
-          *reinterpret_cast<uint4*>(prow + (2 * c) * 2048) = u0;
-          *reinterpret_cast<uint4*>(prow + (2 * c + 1) * 2048) = u1;
+          *reinterpret_cast<uint4*>(prow + (2 * k + 1) * 2048) = u1;
         };
-        if (c_lo < c_hi) tc::tmem_ld16(ts + c_lo * 16, va);
-        for (int c = c_lo; c < c_hi; c += 2) {
-          tc::tmem_ld_wait16(va);
-          if (c + 1 < c_hi) tc::tmem_ld16(ts + (c + 1) * 16, vb);
-          emit(va, c);
-          if (c + 1 < c_hi) {
+        if (cnt > 0) tc::tmem_ld16(ts, va);
+#pragma unroll
+        for (int k = 0; k < kCMax; k += 2) {
+          if (k < cnt) {
+            tc::tmem_ld_wait16(va);
+            if (k + 1 < cnt) tc::tmem_ld16(ts + (k + 1) * 16, vb);
+            emit(va, k);
+          }
+          if (k + 1 < kCMax && k + 1 < cnt) {
             tc::tmem_ld_wait16(vb);
-            if (c + 2 < c_hi) tc::tmem_ld16(ts + (c + 2) * 16, va);
-            emit(vb, c + 1);
+            if (k + 2 < cnt) tc::tmem_ld16(ts + (k + 2) * 16, va);
+            emit(vb, k + 1);
           }
         }
       }
@@ -443,11 +456,19 @@ extern "C" int b200_window_attention_tc(const void* qkv, int N, int C, int heads
   AttnTcParams p;
   p.qkv = (const __half*)qkv; p.out = (__half*)out; p.bias = (const __half*)packed_bias; p.sched = sched;
   p.N = N; p.C8 = C / 8; p.heads = heads; p.nW = nW; p.n = n; p.n_pad = (n + 31) / 32 * 32; p.nrt = (n + 127) / 128; p.ntypes = ntypes;
-  // per-device attribute: set on every call (cheap), so a second GPU in the same process works
-  B200_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
   const long long total = (long long)N * nW * heads * p.nrt;
   dim3 grid((unsigned)std::min<long long>(total, num_sms()));
-  window_attention_tc_kernel<<<grid, kAtThreads, kAtSmem, (cudaStream_t)stream>>>(p);
+  void (*kern)(AttnTcParams) = nullptr;
+  switch (p.n_pad) {
+#define B200_ATTN_CASE(NP) case NP: kern = window_attention_tc_kernel<NP>; break;
+    B200_ATTN_CASE(32) B200_ATTN_CASE(64) B200_ATTN_CASE(96) B200_ATTN_CASE(128) B200_ATTN_CASE(160) B200_ATTN_CASE(192)
+    B200_ATTN_CASE(224) B200_ATTN_CASE(256) B200_ATTN_CASE(288) B200_ATTN_CASE(320) B200_ATTN_CASE(352)
+#undef B200_ATTN_CASE
+  }
+  B200_REQUIRE(kern != nullptr, "window_attention_tc: no kernel for %d padded keys", p.n_pad);
+  // per-device attribute: set on every call (cheap), so a second GPU in the same process works
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+  kern<<<grid, kAtThreads, kAtSmem, (cudaStream_t)stream>>>(p);
   B200_LAUNCH_CHECK("window_attention_tc_kernel");
   return B200_OK;
 }

@@ -56,6 +56,9 @@ struct Cin1TcParams {
   ConvEpiP e;
 };
 
+__device__ __forceinline__ __half to_half(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ __half to_half(__half v) { return v; }
+
 template <typename T, int KS, int STRIDE, int NT, int BD>
 __global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcParams p) {
   using Cfg = Cin1Cfg<KS, STRIDE, NT, BD>;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcP
     // left in flight while the im2col of the current tile runs): a load -> convert -> store loop per element had the
     // producers waiting on one global-memory latency per element (9 in a row per tile) -- slower than the output store.
     constexpr int kHV = (Cfg::kHaloElems + 127) / 128;
-    __half hv[kHV];
+    T hv[kHV];   // RAW values: converting here would make the warp wait for its loads inside fetch()
     auto fetch = [&](long long t) {
       const ConvTile c = conv_tile<BD>(p.e, t);
       const int z0 = c.d0 * STRIDE - p.pad, y0 = c.h0 * STRIDE - p.pad, x0 = c.w0 * STRIDE - p.pad;
@@ -122,9 +125,8 @@ __global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcP
         const int i = r + j * 128;
         const int hx = i % Cfg::kHWw, hy = (i / Cfg::kHWw) % Cfg::kHHh, hz = i / (Cfg::kHWw * Cfg::kHHh);
         const int iz = z0 + hz, iy = y0 + hy, ix = x0 + hx;
-        float v = 0.f;
-        if (i < Cfg::kHaloElems && iz >= 0 && iz < p.D && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = io<T>::ld(xn + ((long long)iz * p.H + iy) * p.W + ix);
-        hv[j] = __float2half_rn(v);
+        const bool in = i < Cfg::kHaloElems && iz >= 0 && iz < p.D && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        hv[j] = in ? __ldg(xn + ((long long)iz * p.H + iy) * p.W + ix) : T(0.f);
       }
     };
     if ((long long)blockIdx.x < p.e.total_tiles) fetch(blockIdx.x);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcP
       __half* halo = reinterpret_cast<__half*>(smem_h + st * Cfg::kHaloBytes);
 #pragma unroll
       for (int j = 0; j < kHV; ++j)
-        if (r + j * 128 < Cfg::kHaloElems) halo[r + j * 128] = hv[j];
+        if (r + j * 128 < Cfg::kHaloElems) halo[r + j * 128] = to_half(hv[j]);
       // all 128 producers have written the patch (and, transitively, finished reading the OTHER patch: a thread reaches
       // this barrier of tile i+1 only after its im2col of tile i)
       asm volatile("bar.sync 2, 128;" ::: "memory");
