@@ -166,6 +166,14 @@ typedef struct b200_conv_tc_desc {
   int N, Cin, Cout, D, H, W;
   int in_ctot, in_coff;     /* x is channels [in_coff, in_coff+Cin) of an NC8 buffer with in_ctot channels */
   int out_ctot, out_coff;   /* y likewise */
+  /* Fused InstanceNorm + activation of the INPUT (round 2; all zero = off): x is the raw output of the previous
+   * convolution and in_stats its per-(n, channel of the slice) {sum, sumsq} (float32 device, [N][Cin][2], as written by the
+   * `stats` output of these entry points).  The kernel feeds act((x - mean) * rstd) to the tensor core -- exactly the fp16
+   * values b200_norm_act_nc8 would have stored (dynunet_block.py:97-103: conv1 -> norm1 -> lrelu -> conv2). */
+  const float* in_stats;
+  float in_eps;
+  int in_act;               /* 0 none, 1 leaky-relu (in_slope), 3 relu */
+  float in_slope;
 } b200_conv_tc_desc;
 
 /* 3x3x3, stride 1, zero padding 1 implicit-GEMM convolution on tcgen05 tensor cores: halo tile staged once

@@ -447,13 +447,21 @@ def conv3x3x3_tc_pack_weight(weight: torch.Tensor) -> torch.Tensor:
 def conv3x3x3_tc(
     x: NC8, packed_w: torch.Tensor, Cin: int, Cout: int, in_coff: int = 0, bias: torch.Tensor | None = None,
     out: NC8 | None = None, out_coff: int = 0, want_stats: bool = False,
+    in_norm: tuple[torch.Tensor, float, int, float] | None = None,
 ) -> tuple[NC8, torch.Tensor | None]:
+    """3x3x3 / stride 1 / pad 1 convolution.  `in_norm` = (stats, eps, act, slope): x is the RAW output of the previous
+    convolution and InstanceNorm + activation are applied on the operand load (no norm_act pass in between)."""
     if out is None:
         out = NC8(x.N, Cout, x.sp, x.buf.device)
     dev = x.buf.device
     stats = torch.empty((x.N * Cout, 2), device=dev, dtype=torch.float32) if want_stats else None
     b32 = _f32c(bias)
-    d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff)
+    d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff, None, 0.0, 0, 0.0)
+    if in_norm is not None:
+        st, eps, act, slope = in_norm
+        if st.dtype != torch.float32 or st.numel() != x.N * Cin * 2 or not st.is_contiguous() or st.device != dev:
+            raise ValueError("conv3x3x3_tc: in_norm statistics must be a contiguous float32 [N*Cin, 2] tensor on the input's device")
+        d.in_stats, d.in_eps, d.in_act, d.in_slope = L.ptr(st), float(eps), int(act), float(slope)
     ws = _ws(L.load().b200_conv3x3x3_tc_workspace_bytes(C.byref(d)), dev) if want_stats else None
     _call("conv3x3x3_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.ptr(ws), L.stream_ptr(dev),
           flops=2.0 * x.N * x.S * Cin * Cout * 27, nbytes=float(x.N * x.S * (Cin + Cout) * 2) + _nb(packed_w))
@@ -543,6 +551,7 @@ def gemm_tc(
     return out, stats
 
 
+NORM_ON_LOAD = os.environ.get("B200_NORM_UNFUSED", "") == ""   # B200_NORM_UNFUSED=1: norm_act_nc8 pass between conv1 and conv2 (A/B measurements)
 MLP_FUSED = os.environ.get("B200_MLP_UNFUSED", "") == ""   # B200_MLP_UNFUSED=1: layernorm_nc8 + two gemm_tc (A/B measurements)
 
 

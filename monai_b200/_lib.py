@@ -50,6 +50,7 @@ class ConvTcDesc(C.Structure):
     _fields_ = [
         ("N", i32), ("Cin", i32), ("Cout", i32), ("D", i32), ("H", i32), ("W", i32),
         ("in_ctot", i32), ("in_coff", i32), ("out_ctot", i32), ("out_coff", i32),
+        ("in_stats", vp), ("in_eps", f32), ("in_act", i32), ("in_slope", f32),
     ]
 
 

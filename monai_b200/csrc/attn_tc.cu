@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
       if (leader) tc::mma_commit(&pv_done[hf]);
       __syncwarp();
     };
-    // Ping-pong between the key halves, across tiles: the issue order is  S0(i+1), PV0(i), S1(i+1), PV1(i) -- while the softmax
+    // (Issuing S0(i+1) BEFORE PV0(i) -- so that the idle softmax warps of half 0 restart sooner -- measured slower: 0.578 ms
+    // against 0.473 ms on the stage-1 shape; PV0 then delays the P buffer and the epilogue of the other half.)
+    // Ping-pong between the key halves, across tiles: the issue order is  PV0(i), S0(i+1), PV1(i), S1(i+1) -- while the softmax
     // warps of one half exponentiate, the tensor pipe works for the other half.
     const long long ntile = hi - lo;
     if (ntile > 0) {
@@ -234,20 +236,20 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
     for (long long it = 0; it < ntile; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const bool more = it + 1 < ntile;
-      // half 0: the S MMAs of the NEXT tile go first -- the softmax warps of this half are idle until they complete, whereas
-      // PV0 is only needed by the epilogue (and by the P buffer, which the next pass 2 reaches after its pass 1)
+      tc::mbar_wait(v_full, ph);
       tc::mbar_wait(&p_full[0], ph);
+      tc::mbar_wait(o_empty, ph ^ 1);               // the epilogue has read O0 / O1 of the previous tile
+      tc::fence_after_sync();
+      issue_pv(0);
       if (more) {
         tc::mbar_wait(qk_full, ph ^ 1);             // Q, K (and bias) of tile it+1 have landed
         tc::mbar_wait(&s_empty[0], ph);             // the softmax threads of half 0 have read S0 of tile it
         tc::fence_after_sync();
         issue_s(0);
       }
-      tc::mbar_wait(v_full, ph);
-      tc::mbar_wait(o_empty, ph ^ 1);               // the epilogue has read O0 / O1 of the previous tile
-      tc::fence_after_sync();
-      issue_pv(0);
       tc::mbar_wait(&p_full[1], ph);
+      tc::fence_after_sync();
+      issue_pv(1);
       if (more) {
         tc::mbar_wait(&s_empty[1], ph);
         tc::fence_after_sync();
@@ -255,8 +257,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
         if (leader) tc::mma_commit(qk_empty);
         __syncwarp();
       }
-      tc::fence_after_sync();
-      issue_pv(1);
     }
     __syncwarp();
   } else {

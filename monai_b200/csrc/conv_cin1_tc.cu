@@ -8,14 +8,14 @@
 //   M = 128 output voxels (a 16 x 8 patch of one D-plane, BD planes per tile), N = Cout, K = taps (zero padded),
 // so the kernel is bound by the fp16 NC8 store of its output (2 * Cout bytes per voxel) instead.
 //
-// Warp roles (160 + 128 * BD threads, one persistent CTA per SM):
+// Warp roles (160 + 128 * EG threads, EG = Cout / 16 epilogue groups, one persistent CTA per SM):
 //   warps 0-3  producers: stage the raw halo patch of a tile in shared memory (plain loads, zero outside the volume
 //              = the convolution's zero padding), then build the im2col A operand -- thread r owns GEMM row r and
 //              writes its K-vector as 16-byte pieces straight into the UMMA K-major / no-swizzle core-matrix image
 //              ([k-chunk of 8][row][8 taps], LBO = 2048 B, SBO = 128 B); fence.proxy.async + mbarrier hand-over;
 //   warp 4     TMEM owner + MMA issuer (converged warp, one elected lane): BD x K/16 tcgen05.mma per tile;
-//   warps 5..  epilogue shared with conv_tc.cu (conv_epi.cuh), one group of four warps per plane of the tile: bias,
-//              deterministic InstanceNorm partial sums, NC8 store.
+//   warps 5..  epilogue (conv_epi.cuh: conv_epilogue_cg), groups of four warps that each own fixed 8-channel chunks: bias,
+//              deterministic InstanceNorm sums kept in registers across tiles, NC8 store.
 // The weights [Cout][taps] fp32 are packed into the B image in shared memory once per CTA.
 #include "common.cuh"
 #include "tc05.cuh"
@@ -24,8 +24,9 @@
 
 namespace b200 {
 
-// epilogue warp groups = planes per tile (one group of four warps per plane): the stems are bound by their output store, one
-// group for all planes left the store stream waiting on a single warp per scheduler
+// epilogue warp groups: each owns a fixed set of 8-channel chunks (two per group up to Cout = 96) of every plane, see
+// conv_epilogue_cg -- per-channel sums stay in registers across tiles
+__host__ __device__ constexpr int cin1_eg(int NT) { return NT / 16 <= 6 ? (NT / 16 > 0 ? NT / 16 : 1) : 4; }
 
 template <int KS, int STRIDE, int NT, int BD>
 struct Cin1Cfg {
@@ -42,7 +43,9 @@ struct Cin1Cfg {
   static constexpr int kBBytes = NT * kKP * 2;
   static constexpr int kAccCols = 2 * BD * NT;
   static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * (kAStage + kHaloBytes) + kBBytes + 256 + BD * 4 * 2 * NT * 4 + 128;
+  static constexpr int kEG = cin1_eg(NT);
+  static constexpr int kThreads = 160 + 128 * kEG;
+  static constexpr int kSmemBytes = kStages * (kAStage + kHaloBytes) + kBBytes + 256 + kEG * 4 * 2 * NT * 4 + 128;
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "invalid UMMA N");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -60,7 +63,7 @@ __device__ __forceinline__ __half to_half(float v) { return __float2half_rn(v); 
 __device__ __forceinline__ __half to_half(__half v) { return v; }
 
 template <typename T, int KS, int STRIDE, int NT, int BD>
-__global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcParams p) {
+__global__ void __launch_bounds__(Cin1Cfg<KS, STRIDE, NT, BD>::kThreads, 1) conv_cin1_tc_kernel(Cin1TcParams p) {
   using Cfg = Cin1Cfg<KS, STRIDE, NT, BD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -79,11 +82,11 @@ __global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcP
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1);
-      tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128 * BD);
+      tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128 * Cfg::kEG);
     }
     tc::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < BD * 4 * 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < Cfg::kEG * 4 * 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
   // B image [k16][khalf][NT/8][8 cout][8 k] (same as gemm_tc): element (cout, k) with k = (kd*KS + kh)*KS + kw
   {
     __half* sb = reinterpret_cast<__half*>(smem_b);
@@ -192,8 +195,8 @@ __global__ void __launch_bounds__(160 + 128 * BD, 1) conv_cin1_tc_kernel(Cin1TcP
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 5 .. 4 + 4 * BD): group g takes plane g of every tile =====================
-    conv_epilogue<NT, BD, 2, BD>(p.e, tmem_base, acc_full, acc_empty, s_stats, warp, lane, (warp - 5) >> 2);
+    // ===================== epilogue (warps 5 .. 4 + 4 * kEG): group g takes its channel chunks of every plane =====================
+    conv_epilogue_cg<NT, BD, 2, Cfg::kEG>(p.e, tmem_base, acc_full, acc_empty, s_stats, warp, lane, (warp - 5) >> 2);
   }
   __syncthreads();
   if (warp == 4) {
@@ -216,22 +219,22 @@ static int launch_cin1_tc(int N, int D, int H, int W, int pad, int out_ctot, int
   e.total_tiles = (long long)e.tiles_w * e.tiles_h * e.tiles_d * N;
   const long long sp_tiles = (long long)e.tiles_w * e.tiles_h * e.tiles_d;
   const int R = stats_rows(sp_tiles, e.total_tiles);
-  c.ws_bytes = stats_partial_bytes(N, R, NT, 4 * BD);
+  c.ws_bytes = stats_partial_bytes(N, R, NT, 4 * Cfg::kEG);
   if (c.query) return B200_OK;
   e.y = (__half*)c.y; e.bias = c.bias;
-  e.sp.buf = c.stats ? (float*)c.ws : nullptr; e.sp.R = R; e.sp.tiles_per_group = sp_tiles; e.sp.rows_per_cta = 4 * BD;
+  e.sp.buf = c.stats ? (float*)c.ws : nullptr; e.sp.R = R; e.sp.tiles_per_group = sp_tiles; e.sp.rows_per_cta = 4 * Cfg::kEG;
   dim3 grid((unsigned)std::min<long long>(e.total_tiles, num_sms()));
   if (c.dtype == B200_DT_F16) {
     auto kern = conv_cin1_tc_kernel<__half, KS, STRIDE, NT, BD>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    kern<<<grid, 160 + 128 * BD, Cfg::kSmemBytes, c.st>>>(p);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, c.st>>>(p);
   } else {
     auto kern = conv_cin1_tc_kernel<float, KS, STRIDE, NT, BD>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    kern<<<grid, 160 + 128 * BD, Cfg::kSmemBytes, c.st>>>(p);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, c.st>>>(p);
   }
   B200_LAUNCH_CHECK("conv_cin1_tc_kernel");
-  if (c.stats) return launch_stats_finish((const float*)c.ws, N, R * 4 * BD, NT, 1, NT, c.stats, c.st);
+  if (c.stats) return launch_stats_finish((const float*)c.ws, N, R * 4 * Cfg::kEG, NT, 1, NT, c.stats, c.st);
   return B200_OK;
 }
 

@@ -124,4 +124,104 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_b
   if (p.sp.buf && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, slot, lane, 0, NT);
 }
 
+// Channel-grouped variant for the store-bound stems (conv_cin1_tc.cu).  EG groups of four epilogue warps; group `eg` owns the
+// 8-channel chunks cc = eg, eg + EG, ... of EVERY plane of every tile, so a thread meets the same channels tile after tile and
+// keeps their InstanceNorm sums in REGISTERS: the cross-lane transpose-reduce (64 of the ~100 instructions a (row, chunk) cost
+// in conv_epilogue -- ncu: FSEL + FADD + SHFL = 40 % of the stem's instruction stream, issue-bound at 74 %) runs once per batch
+// item instead of once per (tile, plane, chunk).  The order of the additions is fixed (tile order), so the sums stay
+// deterministic.  acc_empty expects 128 * EG arrivals; s_stats holds 4 * EG zero-initialised rows of 2 * NT floats.
+template <int NT, int BD, int NB, int EG>
+__device__ __forceinline__ void conv_epilogue_cg(const ConvEpiP& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                                 float* s_stats, int warp, int lane, int eg) {
+  constexpr int kChunks = NT / 8;
+  constexpr int kCC = (kChunks + EG - 1) / EG;   // chunks per group (the last groups may own one fewer)
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int slot = eg * 4 + q;
+  const long long S = (long long)p.D * p.H * p.W;
+  const long long sp_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d;
+  float* ws = s_stats + slot * (2 * NT);
+  float asum[kCC][8], asq[kCC][8];
+#pragma unroll
+  for (int ci = 0; ci < kCC; ++ci)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { asum[ci][j] = 0.f; asq[ci][j] = 0.f; }
+  auto flush = [&](long long group) {
+#pragma unroll
+    for (int ci = 0; ci < kCC; ++ci) {
+      const int cc = eg + ci * EG;
+      if (cc < kChunks) {
+        float a1, b1;
+        transpose_reduce8(asum[ci], asq[ci], lane, a1, b1);
+        if ((lane & 3) == 0) {
+          const int col = cc * 8 + transpose_reduce8_col(lane);
+          ws[2 * col] = a1;
+          ws[2 * col + 1] = b1;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { asum[ci][j] = 0.f; asq[ci][j] = 0.f; }
+      }
+    }
+    stats_flush(p.sp, ws, 2 * NT, group, slot, lane, 0, NT);   // columns of other groups are zero in this row
+  };
+  long long group = -1;
+  int it = 0;
+  for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    const ConvTile c = conv_tile<BD>(p, t);
+    if (p.sp.buf) {
+      const long long g = t / sp_tiles;
+      if (g != group) {
+        if (group >= 0) flush(group);
+        group = g;
+      }
+    }
+    const int buf = it % NB;
+    const uint32_t aph = (uint32_t)((it / NB) & 1);
+    const int h = c.h0 + (row >> 3), w = c.w0 + (row & 7);
+    const bool hw_ok = h < p.H && w < p.W;
+    __half* ybase = p.y + (((long long)c.n * (p.out_ctot / 8) + p.out_coff / 8) * S + ((long long)c.d0 * p.H + h) * p.W + w) * 8;
+    tc::mbar_wait(&acc_full[buf], aph);
+    tc::fence_after_sync();
+    const uint32_t tq = tmem_base + buf * (BD * NT) + ((uint32_t)(q * 32) << 16) + eg * 8;
+    uint32_t vn[8];
+    tc::tmem_ld8(tq, vn);   // (chunk 0, plane 0) of this group; every later load is prefetched one step ahead
+#pragma unroll
+    for (int ci = 0; ci < kCC; ++ci) {
+      const int cc = eg + ci * EG;
+      if (cc < kChunks) {
+        float bias8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bias8[j] = p.bias ? p.bias[cc * 8 + j] : 0.f;
+#pragma unroll
+        for (int sub = 0; sub < BD; ++sub) {
+          uint32_t v[8];
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = vn[j];
+          {
+            const int nsub = sub + 1 < BD ? sub + 1 : 0, nci = sub + 1 < BD ? ci : ci + 1;
+            if (nci < kCC && eg + nci * EG < kChunks) tc::tmem_ld8(tq + nsub * NT + nci * EG * 8, vn);
+          }
+          const bool ok = hw_ok && c.d0 + sub < p.D;
+          if (ok) {
+            uint4 hv;
+            __half2* hp = reinterpret_cast<__half2*>(&hv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float f0 = __uint_as_float(v[2 * j]) + bias8[2 * j], f1 = __uint_as_float(v[2 * j + 1]) + bias8[2 * j + 1];
+              asum[ci][2 * j] += f0; asq[ci][2 * j] = fmaf(f0, f0, asq[ci][2 * j]);
+              asum[ci][2 * j + 1] += f1; asq[ci][2 * j + 1] = fmaf(f1, f1, asq[ci][2 * j + 1]);
+              hp[j] = __floats2half2_rn(f0, f1);
+            }
+            *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + (long long)sub * p.H * p.W) * 8) = hv;
+          }
+        }
+      }
+    }
+    tc::fence_before_sync();
+    tc::mbar_arrive(&acc_empty[buf]);
+  }
+  if (p.sp.buf && group >= 0) flush(group);
+}
+
 }  // namespace b200

@@ -23,7 +23,8 @@
 // blocks, so one MMA with the weights of kd = 2,1,0 stacked along N (N up to 3*NT <= 256) replaces three -- the A
 // tile is read once per (plane, kh, kw) instead of once per tap.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue; with the
+// fused input normalisation (NORM, see the kernel) four more warps rewrite each staged halo tile in place.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "conv_epi.cuh"
@@ -130,7 +131,7 @@ struct ConvTcCfg {
   static constexpr int kAccBufs = (2 * BD * NT <= 512) ? 2 : 1;  // accumulator sets: 2 lets the epilogue of tile i overlap the MMAs of tile i+1
   static constexpr int kAccCols = kAccBufs * BD * NT;
   static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + 256 /*barriers*/ + 4 * 2 * NT * 4 /*warp-private stats rows*/ + 128 /*align slack*/;
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + 384 /*barriers*/ + 4 * 2 * NT * 4 /*warp-private stats rows*/ + 128 /*align slack*/;
   static_assert(BD * NT <= 512, "accumulators exceed TMEM");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "invalid UMMA N");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -140,13 +141,21 @@ struct ConvTcParams {
   b200_conv_tc_desc d;
   const __half* w;      // packed
   ConvEpiP e;           // output stage (conv_epi.cuh)
+  const float* in_stats;   // NORM: {sum, sumsq} per (n, input channel) of the raw input (see b200_conv_tc_desc.in_stats)
 };
 
 // Persistent, warp-specialised (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2-5 = epilogue.  Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the shared-memory rings run
 // across tile boundaries and (when 2*BD*NT <= 512 columns) two TMEM accumulator sets alternate.
-template <int NT, int BD>
-__global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
+//
+// NORM (320 threads): the input is the RAW output of the previous convolution and InstanceNorm + activation
+// (monai/networks/blocks/dynunet_block.py:97-103: conv1 -> norm1 -> lrelu -> conv2) is applied on the operand load: warps 6-9
+// rewrite every staged halo tile in place -- y = act(x * rstd - mean * rstd), the exact expression and rounding of
+// norm_act_nc8_kernel, so the MMAs consume bit-identical fp16 operands -- between the TMA completion (full_a) and the MMAs
+// (ready_a).  Voxels outside the volume keep the TMA's zero fill: the convolution pads the NORMALISED tensor with zeros.
+// This removes one read and one write of the activation tensor per residual block (norm_act_nc8: 102 ms per C3 step).
+template <int NT, int BD, bool NORM>
+__global__ void __launch_bounds__(NORM ? 320 : 192, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
   using Cfg = ConvTcCfg<NT, BD>;
   constexpr int kSA = Cfg::kSA, kSB = Cfg::kSB, kNB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
@@ -160,16 +169,17 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
   uint64_t* empty_b = full_b + kSB;     // [kSB]
   uint64_t* acc_full = empty_b + kSB;   // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  static_assert(2 * kSA + 2 * kSB + 4 + 1 <= 32, "barrier block");
-  float* s_stats = reinterpret_cast<float*>(bars + 32);  // [4][2*NT]
+  uint64_t* ready_a = acc_empty + 2;    // [kSA] NORM: 128 arrivals of the transform warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_a + kSA);
+  static_assert(3 * kSA + 2 * kSB + 4 + 1 <= 48, "barrier block");
+  float* s_stats = reinterpret_cast<float*>(bars + 48);  // [4][2*NT]
 
   const b200_conv_tc_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kc = d.Cin / 16;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&ready_a[i], 128); }
     for (int i = 0; i < kSB; ++i) { tc::mbar_init(&full_b[i], 1); tc::mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
         tc::fence_after_sync();
         tacc = tmem_u + buf * (BD * NT);
         for (int kc = 0; kc < num_kc; ++kc) {
-          tc::mbar_wait(&full_a[sa], pa);
+          tc::mbar_wait(NORM ? &ready_a[sa] : &full_a[sa], pa);
           tc::fence_after_sync();
           a_base = tc::smem_u32(smem_a + sa * Cfg::kABytes);
           if (kc == 0) tap(std::true_type{}, 0, 0);
@@ -276,9 +286,56 @@ __global__ void __launch_bounds__(192, 1) conv3x3x3_tc_kernel(const __grid_const
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
     conv_epilogue<NT, BD, kNB>(p.e, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
+  } else if constexpr (NORM) {
+    // ===================== operand transform (warps 6..9): InstanceNorm + activation in place =====================
+    const int tt = threadIdx.x - 192;                      // 0..127: threads 0-63 own the first 8-channel chunk, 64-127 the second
+    const int chunk = tt >> 6, t64 = tt & 63;
+    constexpr int kVox = Cfg::kPlanes * kHH * kHW;         // 16-byte voxel vectors per chunk image
+    const float invS = 1.f / ((float)d.D * (float)d.H * (float)d.W);
+    const int act = d.in_act;
+    const float slope = d.in_slope, eps = d.in_eps;
+    int sa = 0; uint32_t pa = 0;
+    for (long long t = blockIdx.x; t < p.e.total_tiles; t += gridDim.x) {
+      const ConvTile c = conv_tile<BD>(p.e, t);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        float sc[8], sh[8];
+        {
+          const float* st = p.in_stats + 2 * ((long long)c.n * d.Cin + kc * 16 + chunk * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float sm = __ldg(st + 2 * j), q = __ldg(st + 2 * j + 1);
+            const float mean = sm * invS, var = fmaxf(q * invS - mean * mean, 0.f), rstd = 1.f / sqrtf(var + eps);
+            sc[j] = rstd; sh[j] = -mean * rstd;
+          }
+        }
+        tc::mbar_wait(&full_a[sa], pa);
+        uint8_t* img = smem_a + sa * Cfg::kABytes + chunk * Cfg::kChunkBytes;
+#pragma unroll 2
+        for (int v = t64; v < kVox; v += 64) {
+          const int pz = v / (kHH * kHW), rem = v - pz * (kHH * kHW), py = rem / kHW, px = rem - py * kHW;
+          const int gz = c.d0 - 1 + pz, gy = c.h0 - 1 + py, gx = c.w0 - 1 + px;
+          if ((unsigned)gz < (unsigned)d.D && (unsigned)gy < (unsigned)d.H && (unsigned)gx < (unsigned)d.W) {
+            uint4 raw = *reinterpret_cast<const uint4*>(img + v * 16);
+            __half2* h2 = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(h2[j]);
+              float a = fmaf(f.x, sc[2 * j], sh[2 * j]), b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+              if (act == 1) { a = a >= 0.f ? a : a * slope; b = b >= 0.f ? b : b * slope; }
+              else if (act == 3) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              h2[j] = __floats2half2_rn(a, b);
+            }
+            *reinterpret_cast<uint4*>(img + v * 16) = raw;
+          }
+        }
+        tc::fence_proxy_async();       // generic-proxy stores -> visible to tcgen05.mma
+        tc::mbar_arrive(&ready_a[sa]);
+        if (++sa == kSA) { sa = 0; pa ^= 1; }
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -402,11 +459,11 @@ struct ConvTcGeom {
 // what a launch needs beyond the operands: mode 0 = run, mode 1 = only report the statistics workspace size
 struct ConvTcCall { const void* x; const void* w; const float* bias; void* y; float* stats; void* ws; cudaStream_t st; long long ws_bytes; int query; };
 
-template <int NT, int BD>
+template <int NT, int BD, bool NORM>
 static int launch_conv_tc(const b200_conv_tc_desc& d, ConvTcCall& c) {
   using Cfg = ConvTcCfg<NT, BD>;
   ConvTcParams p;
-  p.d = d; p.w = (const __half*)c.w;
+  p.d = d; p.w = (const __half*)c.w; p.in_stats = (const float*)d.in_stats;
   ConvTcGeom<NT, BD>::fill(d, p.e);
   const long long sp_tiles = (long long)p.e.tiles_w * p.e.tiles_h * p.e.tiles_d, groups = (long long)d.N * p.e.n_tiles;
   const int R = stats_rows(sp_tiles, p.e.total_tiles);
@@ -427,10 +484,10 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, ConvTcCall& c) {
   p.e.y = (__half*)c.y; p.e.bias = c.bias;
   p.e.sp.buf = c.stats ? (float*)c.ws : nullptr; p.e.sp.R = R; p.e.sp.tiles_per_group = sp_tiles; p.e.sp.rows_per_cta = 4;
   dim3 grid((unsigned)std::min<long long>(p.e.total_tiles, num_sms()));
-  auto kern = conv3x3x3_tc_kernel<NT, BD>;
+  auto kern = conv3x3x3_tc_kernel<NT, BD, NORM>;
   // per-device attribute: set on every call (cheap), so a second GPU in the same process works
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  kern<<<grid, 192, Cfg::kSmemBytes, c.st>>>(tmap, p);
+  kern<<<grid, NORM ? 320 : 192, Cfg::kSmemBytes, c.st>>>(tmap, p);
   B200_LAUNCH_CHECK("conv3x3x3_tc_kernel");
   if (c.stats) return launch_stats_finish((const float*)c.ws, groups, R * 4, NT, p.e.n_tiles, d.Cout, c.stats, c.st);
   return B200_OK;
@@ -441,12 +498,12 @@ static int dispatch_bd(const b200_conv_tc_desc& d, ConvTcCall& c) {
   // deeper CTA tiles amortise the halo and fuse more kd taps per MMA; two accumulator sets (2*BD*NT <= 512 TMEM columns)
   // let the epilogue overlap the next tile, which is worth more than depth for the wide-N layers
   if constexpr (2 * NT * 4 <= 512) {
-    if (d.D % 4 == 0 || d.D >= 16) return launch_conv_tc<NT, 4>(d, c);
+    if (d.D % 4 == 0 || d.D >= 16) return d.in_stats ? launch_conv_tc<NT, 4, true>(d, c) : launch_conv_tc<NT, 4, false>(d, c);
   }
   if constexpr (NT * 2 <= 512) {
-    if (d.D >= 2) return launch_conv_tc<NT, 2>(d, c);
+    if (d.D >= 2) return d.in_stats ? launch_conv_tc<NT, 2, true>(d, c) : launch_conv_tc<NT, 2, false>(d, c);
   }
-  return launch_conv_tc<NT, 1>(d, c);
+  return d.in_stats ? launch_conv_tc<NT, 1, true>(d, c) : launch_conv_tc<NT, 1, false>(d, c);
 }
 
 static int conv_tc_dispatch(const b200_conv_tc_desc& d, ConvTcCall& c) {
@@ -455,6 +512,7 @@ static int conv_tc_dispatch(const b200_conv_tc_desc& d, ConvTcCall& c) {
                "conv3x3x3_tc: Cin and Cout must be multiples of 16 (got %d, %d)", d.Cin, d.Cout);
   B200_REQUIRE(d.in_ctot % 8 == 0 && d.in_coff % 8 == 0 && d.in_coff + d.Cin <= d.in_ctot, "conv3x3x3_tc: bad input channel slice");
   B200_REQUIRE(d.out_ctot % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + d.Cout <= d.out_ctot, "conv3x3x3_tc: bad output channel slice");
+  B200_REQUIRE(!d.in_stats || d.in_act == 0 || d.in_act == 1 || d.in_act == 3, "conv3x3x3_tc: in_act must be none, leaky-relu or relu");
   switch (conv_tc_nt(d.Cout)) {
     case 16: return dispatch_bd<16>(d, c);
     case 32: return dispatch_bd<32>(d, c);

@@ -61,3 +61,39 @@ def test_conv3x3x3_tc_bias_and_channel_slices():
 
 def test_conv3x3x3_tc_full_window_shape():
     _run(1, 48, 48, (96, 96, 96), bias=False, seed=5)
+
+
+@pytest.mark.parametrize(
+    "N,Cin,Cout,sp",
+    [
+        (1, 16, 16, (5, 19, 11)),     # ragged edges: the zero padding must stay zero AFTER the normalisation
+        (2, 48, 48, (8, 32, 16)),     # UnetResBlock conv2 of SwinUNETR (BD = 4)
+        (3, 48, 48, (6, 12, 12)),     # BD = 2 path, batch > 1 (per-item statistics)
+        (1, 192, 96, (3, 6, 6)),      # many K slices on a tiny volume (BD = 1)
+    ],
+)
+def test_conv3x3x3_tc_instance_norm_on_the_operand_load(N, Cin, Cout, sp):
+    """conv2(lrelu(norm1(y1))) of UnetResBlock (monai/networks/blocks/dynunet_block.py:97-103) with the normalisation applied to
+    the staged halo tile: bit-identical to running norm_act_nc8 first (same expression, same fp16 rounding of the operand)."""
+    from monai_b200 import _lib as L
+
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn((N, Cin, *sp), generator=g) * torch.rand((1, Cin, 1, 1, 1), generator=g) * 3 + torch.randn((1, Cin, 1, 1, 1), generator=g)).half()
+    w = (torch.randn((Cout, Cin, 3, 3, 3), generator=g) / (27 * Cin) ** 0.5).half()
+    pw = K.conv3x3x3_tc_pack_weight(w.float().to(DEV))
+    xr = K.pack_nc8(x.to(DEV))
+    S = sp[0] * sp[1] * sp[2]
+    xf = x.float()
+    st = torch.stack([xf.sum(dim=(2, 3, 4)), (xf * xf).sum(dim=(2, 3, 4))], dim=-1).reshape(N * Cin, 2).contiguous().to(DEV)
+    fused, fst = K.conv3x3x3_tc(xr, pw, Cin, Cout, want_stats=True, in_norm=(st, 1e-5, L.ACT_LEAKY, 0.01))
+    xn = K.norm_act_nc8(xr, Cin, st, act=L.ACT_LEAKY, slope=0.01)
+    plain, pst = K.conv3x3x3_tc(xn, pw, Cin, Cout, want_stats=True)
+    assert torch.equal(fused.buf, plain.buf)
+    assert torch.equal(fst, pst)
+    # and against torch: instance_norm + leaky_relu + conv3d in fp32 on the fp16-rounded normalised operand
+    ref = F.conv3d(K.unpack_nc8(xn, dtype=torch.float32).cpu(), w.float(), None, padding=1)
+    got = K.unpack_nc8(fused, dtype=torch.float32).cpu()
+    assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+    nrm = F.leaky_relu(F.instance_norm(xf, eps=1e-5), 0.01)
+    assert (K.unpack_nc8(xn, dtype=torch.float32).cpu() - nrm).abs().max().item() < 2e-2
+    assert not (S == 0)
