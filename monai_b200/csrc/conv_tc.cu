@@ -24,7 +24,7 @@
 // tile is read once per (plane, kh, kw) instead of once per tap.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue; with the
-// fused input normalisation (NORM, see the kernel) four more warps rewrite each staged halo tile in place.
+// fused input normalisation (NORM, see the kernel) eight more warps rewrite each staged halo tile in place.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "conv_epi.cuh"
@@ -148,14 +148,14 @@ struct ConvTcParams {
 // warps 2-5 = epilogue.  Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the shared-memory rings run
 // across tile boundaries and (when 2*BD*NT <= 512 columns) two TMEM accumulator sets alternate.
 //
-// NORM (320 threads): the input is the RAW output of the previous convolution and InstanceNorm + activation
-// (monai/networks/blocks/dynunet_block.py:97-103: conv1 -> norm1 -> lrelu -> conv2) is applied on the operand load: warps 6-9
+// NORM (448 threads): the input is the RAW output of the previous convolution and InstanceNorm + activation
+// (monai/networks/blocks/dynunet_block.py:97-103: conv1 -> norm1 -> lrelu -> conv2) is applied on the operand load: warps 6-13
 // rewrite every staged halo tile in place -- y = act(x * rstd - mean * rstd), the exact expression and rounding of
 // norm_act_nc8_kernel, so the MMAs consume bit-identical fp16 operands -- between the TMA completion (full_a) and the MMAs
 // (ready_a).  Voxels outside the volume keep the TMA's zero fill: the convolution pads the NORMALISED tensor with zeros.
 // This removes one read and one write of the activation tensor per residual block (norm_act_nc8: 102 ms per C3 step).
 template <int NT, int BD, bool NORM>
-__global__ void __launch_bounds__(NORM ? 320 : 192, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
+__global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
   using Cfg = ConvTcCfg<NT, BD>;
   constexpr int kSA = Cfg::kSA, kSB = Cfg::kSB, kNB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(NORM ? 320 : 192, 1) conv3x3x3_tc_kernel(const
   uint64_t* empty_b = full_b + kSB;     // [kSB]
   uint64_t* acc_full = empty_b + kSB;   // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
-  uint64_t* ready_a = acc_empty + 2;    // [kSA] NORM: 128 arrivals of the transform warps
+  uint64_t* ready_a = acc_empty + 2;    // [kSA] NORM: 256 arrivals of the transform warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_a + kSA);
   static_assert(3 * kSA + 2 * kSB + 4 + 1 <= 48, "barrier block");
   float* s_stats = reinterpret_cast<float*>(bars + 48);  // [4][2*NT]
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(NORM ? 320 : 192, 1) conv3x3x3_tc_kernel(const
   const int num_kc = d.Cin / 16;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&ready_a[i], 128); }
+    for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&ready_a[i], 256); }
     for (int i = 0; i < kSB; ++i) { tc::mbar_init(&full_b[i], 1); tc::mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
@@ -290,16 +290,28 @@ __global__ void __launch_bounds__(NORM ? 320 : 192, 1) conv3x3x3_tc_kernel(const
     // ===================== epilogue (warps 2..5) =====================
     conv_epilogue<NT, BD, kNB>(p.e, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
   } else if constexpr (NORM) {
-    // ===================== operand transform (warps 6..9): InstanceNorm + activation in place =====================
-    const int tt = threadIdx.x - 192;                      // 0..127: threads 0-63 own the first 8-channel chunk, 64-127 the second
-    const int chunk = tt >> 6, t64 = tt & 63;
+    // ===================== operand transform (warps 6..13): InstanceNorm + activation in place =====================
+    // 256 threads: 128 per 8-channel chunk; four vectors are loaded before the first is converted (one warp per scheduler with
+    // a load -> convert -> store chain per vector left the tensor pipe waiting: 37 % active against 65 % without the fusion)
+    const int tt = threadIdx.x - 192;                      // 0..255
+    const int chunk = tt >> 7, t128 = tt & 127;
     constexpr int kVox = Cfg::kPlanes * kHH * kHW;         // 16-byte voxel vectors per chunk image
+    constexpr int kIter = (kVox + 127) / 128;
     const float invS = 1.f / ((float)d.D * (float)d.H * (float)d.W);
     const int act = d.in_act;
     const float slope = d.in_slope, eps = d.in_eps;
     int sa = 0; uint32_t pa = 0;
     for (long long t = blockIdx.x; t < p.e.total_tiles; t += gridDim.x) {
       const ConvTile c = conv_tile<BD>(p.e, t);
+      // which of this thread's vectors lie inside the volume (same for every K slice of the tile)
+      uint32_t inside = 0;
+#pragma unroll
+      for (int k = 0; k < kIter; ++k) {
+        const int v = t128 + 128 * k;
+        const int pz = v / (kHH * kHW), rem = v - pz * (kHH * kHW), py = rem / kHW, px = rem - py * kHW;
+        const int gz = c.d0 - 1 + pz, gy = c.h0 - 1 + py, gx = c.w0 - 1 + px;
+        if (v < kVox && (unsigned)gz < (unsigned)d.D && (unsigned)gy < (unsigned)d.H && (unsigned)gx < (unsigned)d.W) inside |= 1u << k;
+      }
       for (int kc = 0; kc < num_kc; ++kc) {
         float sc[8], sh[8];
         {
@@ -312,24 +324,30 @@ __global__ void __launch_bounds__(NORM ? 320 : 192, 1) conv3x3x3_tc_kernel(const
           }
         }
         tc::mbar_wait(&full_a[sa], pa);
-        uint8_t* img = smem_a + sa * Cfg::kABytes + chunk * Cfg::kChunkBytes;
-#pragma unroll 2
-        for (int v = t64; v < kVox; v += 64) {
-          const int pz = v / (kHH * kHW), rem = v - pz * (kHH * kHW), py = rem / kHW, px = rem - py * kHW;
-          const int gz = c.d0 - 1 + pz, gy = c.h0 - 1 + py, gx = c.w0 - 1 + px;
-          if ((unsigned)gz < (unsigned)d.D && (unsigned)gy < (unsigned)d.H && (unsigned)gx < (unsigned)d.W) {
-            uint4 raw = *reinterpret_cast<const uint4*>(img + v * 16);
-            __half2* h2 = reinterpret_cast<__half2*>(&raw);
+        uint8_t* img = smem_a + sa * Cfg::kABytes + chunk * Cfg::kChunkBytes + t128 * 16;
+        auto xform = [&](uint4& raw) {
+          __half2* h2 = reinterpret_cast<__half2*>(&raw);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(h2[j]);
-              float a = fmaf(f.x, sc[2 * j], sh[2 * j]), b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-              if (act == 1) { a = a >= 0.f ? a : a * slope; b = b >= 0.f ? b : b * slope; }
-              else if (act == 3) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              h2[j] = __floats2half2_rn(a, b);
-            }
-            *reinterpret_cast<uint4*>(img + v * 16) = raw;
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h2[j]);
+            float a = fmaf(f.x, sc[2 * j], sh[2 * j]), b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+            if (act == 1) { a = a >= 0.f ? a : a * slope; b = b >= 0.f ? b : b * slope; }
+            else if (act == 3) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            h2[j] = __floats2half2_rn(a, b);
           }
+        };
+#pragma unroll
+        for (int k0 = 0; k0 < kIter; k0 += 4) {
+          uint4 raw[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (k0 + u < kIter && (inside >> (k0 + u) & 1u)) raw[u] = *reinterpret_cast<const uint4*>(img + (k0 + u) * 2048);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (k0 + u < kIter && (inside >> (k0 + u) & 1u)) {
+              xform(raw[u]);
+              *reinterpret_cast<uint4*>(img + (k0 + u) * 2048) = raw[u];
+            }
         }
         tc::fence_proxy_async();       // generic-proxy stores -> visible to tcgen05.mma
         tc::mbar_arrive(&ready_a[sa]);
@@ -487,7 +505,7 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, ConvTcCall& c) {
   auto kern = conv3x3x3_tc_kernel<NT, BD, NORM>;
   // per-device attribute: set on every call (cheap), so a second GPU in the same process works
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  kern<<<grid, NORM ? 320 : 192, Cfg::kSmemBytes, c.st>>>(tmap, p);
+  kern<<<grid, NORM ? 448 : 192, Cfg::kSmemBytes, c.st>>>(tmap, p);
   B200_LAUNCH_CHECK("conv3x3x3_tc_kernel");
   if (c.stats) return launch_stats_finish((const float*)c.ws, groups, R * 4, NT, p.e.n_tiles, d.Cout, c.stats, c.st);
   return B200_OK;

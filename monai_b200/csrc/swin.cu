@@ -5,6 +5,7 @@
 // monai/networks/blocks/dynunet_block.py:247-267.
 #include "common.cuh"
 #include "stats.cuh"
+#include <cstdlib>
 #include "../../include/monai_b200.h"
 
 namespace b200 {
@@ -640,6 +641,12 @@ __global__ void __launch_bounds__(256) head_conv_norm_nc8_kernel(HeadNormP p) {
 
 }  // namespace b200
 
+namespace b200 {
+int launch_head_conv_norm_tc(const void* x, int N, int C, long long S, const float* stats, float eps, const void* res, int res_ctot,
+                             int res_coff, const float* res_stats, float slope, const float* weight, const float* bias, int Cout,
+                             void* y, int out_dtype, cudaStream_t st);
+}
+
 using namespace b200;
 
 extern "C" int b200_head_conv_norm_nc8(const void* x, int N, int C, long long S, const float* stats, float eps, const void* res,
@@ -649,6 +656,16 @@ extern "C" int b200_head_conv_norm_nc8(const void* x, int N, int C, long long S,
   B200_REQUIRE(C % 8 == 0 && Cout >= 1 && Cout <= 16, "head_conv_norm_nc8: C must be a multiple of 8 and Cout <= 16 (got %d, %d)", C, Cout);
   B200_REQUIRE(!res || (res_ctot % 8 == 0 && res_coff % 8 == 0 && res_coff + C <= res_ctot), "head_conv_norm_nc8: bad residual channel slice");
   B200_REQUIRE(res || !res_stats, "head_conv_norm_nc8: residual statistics without a residual");
+  B200_REQUIRE(out_dtype == B200_DT_F16 || out_dtype == B200_DT_F32, "head_conv_norm_nc8: bad dtype");
+  {
+    // tensor-core version (head_tc.cu) for the shapes it covers; B200_HEAD_CUDA_CORE=1 keeps the CUDA-core kernel (A/B runs)
+    static const bool cuda_core_only = std::getenv("B200_HEAD_CUDA_CORE") != nullptr;
+    if (!cuda_core_only) {
+      const int rc = launch_head_conv_norm_tc(x, N, C, S, stats, eps, res, res_ctot, res_coff, res_stats, slope, weight, bias, Cout, y,
+                                              out_dtype, (cudaStream_t)stream);
+      if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+  }
   HeadNormP p{(const __half*)x, (const __half*)res, stats, res_stats, weight, bias, y, C, Cout, res_ctot, res_coff, S, eps, slope};
   dim3 grid(ceil_div(S, 256), N);
   const size_t smem = ((size_t)Cout * C + 4 * (size_t)C) * sizeof(float);

@@ -5,7 +5,7 @@
         -o gpurun_out/r02_swin_kernels python profiles/run_ncu_forward.py
     python profiles/summarize_ncu.py gpurun_out/r02_swin_kernels.ncu-rep > profiles/r02_swin_kernels_ncu_summary.txt
 
-(the first pass -- 33 matching launches -- warms up and is skipped).
+(the first pass -- 33 matching launches -- warms up and is skipped).  An optional argument sets the batch (default 4; bench.py runs 25).
 """
 import os
 import sys
@@ -17,7 +17,8 @@ from monai_b200.networks.nets import SwinUNETR  # noqa: E402
 
 torch.manual_seed(0)
 net = SwinUNETR(in_channels=1, out_channels=14, feature_size=48).cuda().half().eval()
-x = torch.randn(4, 1, 96, 96, 96, device="cuda").half()
+BATCH = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+x = torch.randn(BATCH, 1, 96, 96, 96, device="cuda").half()
 with torch.no_grad():
     for _ in range(2):
         y = net(x)

@@ -274,6 +274,27 @@ def test_fused_residual_tail_kernels():
     assert _rel(K.unpack_nc8(got_c).float().cpu().numpy(), ref_c.numpy()) < 3e-3
 
 
+def test_head_on_tensor_cores_many_tiles_and_classes():
+    """head_conv_norm_nc8 at C = 48 runs as one UMMA per 128 voxels (head_tc.cu): 14 classes, several batch items, a ragged last
+    tile, fp16 and fp32 logits -- against torch fp32 (dynunet_block.py:104-111 + 247-267)."""
+    g = torch.Generator().manual_seed(5)
+    N, C, sp, CO = 3, 48, (9, 20, 23), 14
+    y2 = (torch.randn((N, C, *sp), generator=g) * 1.3 + 0.2).half()
+    y3 = (torch.randn((N, C, *sp), generator=g) * 0.8 - 0.1).half()
+    w = torch.randn((CO, C, 1, 1, 1), generator=g) / C**0.5
+    b = torch.randn(CO, generator=g)
+    y2n, y3n = _to_nc8(y2), _to_nc8(y3)
+    st2, st3 = K.instnorm_stats(y2.to(DEV)), K.instnorm_stats(y3.to(DEV))
+    ref = F.conv3d(F.leaky_relu(F.instance_norm(y2.float()) + F.instance_norm(y3.float()), 0.01), w, b)
+    for dt in (torch.float32, torch.float16):
+        got = K.head_conv_norm_nc8(y2n, st2, y3n, 0, st3, 0.01, 1e-5, w.to(DEV), b.to(DEV), out_dtype=dt)
+        assert got.dtype == dt and tuple(got.shape) == tuple(ref.shape)
+        r = _rel(got.float().cpu().numpy(), ref.numpy())
+        assert r < 3e-3, (dt, r)
+    again = K.head_conv_norm_nc8(y2n, st2, y3n, 0, st3, 0.01, 1e-5, w.to(DEV), b.to(DEV), out_dtype=torch.float16)
+    assert torch.equal(again, got)
+
+
 def _build():
     with contextlib.redirect_stdout(io.StringIO()):
         net = SwinUNETR(in_channels=1, out_channels=2, feature_size=48)
