@@ -298,8 +298,7 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
     constexpr int kVox = Cfg::kPlanes * kHH * kHW;         // 16-byte voxel vectors per chunk image
     constexpr int kIter = (kVox + 127) / 128;
     const float invS = 1.f / ((float)d.D * (float)d.H * (float)d.W);
-    const int act = d.in_act;
-    const float slope = d.in_slope, eps = d.in_eps;
+    const float slope = d.in_act == 1 ? d.in_slope : (d.in_act == 3 ? 0.f : 1.f), eps = d.in_eps;
     int sa = 0; uint32_t pa = 0;
     for (long long t = blockIdx.x; t < p.e.total_tiles; t += gridDim.x) {
       const ConvTile c = conv_tile<BD>(p.e, t);
@@ -330,10 +329,10 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 f = __half22float2(h2[j]);
-            float a = fmaf(f.x, sc[2 * j], sh[2 * j]), b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-            if (act == 1) { a = a >= 0.f ? a : a * slope; b = b >= 0.f ? b : b * slope; }
-            else if (act == 3) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            h2[j] = __floats2half2_rn(a, b);
+            const float a = fmaf(f.x, sc[2 * j], sh[2 * j]), b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+            // one branch-free form for none / leaky-relu / relu: max(a, a * s) with s = 1 / slope / 0 (0 <= slope <= 1) returns
+            // exactly what `a >= 0 ? a : a * slope` returns
+            h2[j] = __floats2half2_rn(fmaxf(a, a * slope), fmaxf(b, b * slope));
           }
         };
 #pragma unroll
@@ -531,6 +530,7 @@ static int conv_tc_dispatch(const b200_conv_tc_desc& d, ConvTcCall& c) {
   B200_REQUIRE(d.in_ctot % 8 == 0 && d.in_coff % 8 == 0 && d.in_coff + d.Cin <= d.in_ctot, "conv3x3x3_tc: bad input channel slice");
   B200_REQUIRE(d.out_ctot % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + d.Cout <= d.out_ctot, "conv3x3x3_tc: bad output channel slice");
   B200_REQUIRE(!d.in_stats || d.in_act == 0 || d.in_act == 1 || d.in_act == 3, "conv3x3x3_tc: in_act must be none, leaky-relu or relu");
+  B200_REQUIRE(!d.in_stats || d.in_act != 1 || (d.in_slope >= 0.f && d.in_slope <= 1.f), "conv3x3x3_tc: in_slope must lie in [0, 1] (got %g)", (double)d.in_slope);
   switch (conv_tc_nt(d.Cout)) {
     case 16: return dispatch_bd<16>(d, c);
     case 32: return dispatch_bd<32>(d, c);

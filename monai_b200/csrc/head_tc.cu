@@ -12,7 +12,8 @@
 // The per-(batch item, channel) scale / shift tables of ALL batch items are built once per CTA in shared memory.
 //
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 and
-// 6-9 = two "row" groups that alternate tiles (transform of tile i, then the output of tile i - 2 of the same group).
+// 6-9 = two "row" groups that alternate tiles (transform of tile i, then the output of tile i - 2 of the same group); four
+// operand stages keep ~96 KB of loads in flight per SM.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "../../include/monai_b200.h"
@@ -23,6 +24,7 @@ constexpr int kHdC = 48, kHdN = 16;
 constexpr int kHdTile = (kHdC / 8) * 2048;            // one operand tile: 6 chunks of 128 rows x 16 B
 constexpr int kHdWBytes = kHdN * kHdC * 2;
 constexpr int kHdMaxTab = 64 * 1024;                  // scale / shift tables: N * C * 16 bytes
+constexpr int kHdStages = 4;                          // operand tiles in flight per SM (4 x 24 KB: the HBM latency-bandwidth product)
 
 struct HeadTcParams {
   const __half* x; const __half* res; const float* stats; const float* res_stats; const float* wgt; const float* bias;
@@ -36,17 +38,17 @@ template <typename TO>
 __global__ void __launch_bounds__(320, 1) head_conv_norm_tc_kernel(HeadTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = tc::align_smem128(smem_raw);
-  uint8_t* s_x = smem;                                  // [2] y2 tiles (raw, then t in place)
-  uint8_t* s_r = s_x + 2 * kHdTile;                     // [2] residual tiles
-  uint8_t* s_w = s_r + 2 * kHdTile;                     // B image of W_out (16 x 48)
+  uint8_t* s_x = smem;                                  // [kHdStages] y2 tiles (raw, then t in place)
+  uint8_t* s_r = s_x + kHdStages * kHdTile;             // [kHdStages] residual tiles
+  uint8_t* s_w = s_r + kHdStages * kHdTile;             // B image of W_out (16 x 48)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kHdWBytes);
-  uint64_t* x_full = bars;          // [2] tx
-  uint64_t* x_free = bars + 2;      // [2] commit
-  uint64_t* a_ready = bars + 4;     // [2] 128 arrivals
-  uint64_t* d_full = bars + 6;      // [2] commit
-  uint64_t* d_free = bars + 8;      // [2] 128 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* s_bias = reinterpret_cast<float*>(bars + 12);  // [16]
+  uint64_t* x_full = bars;                      // [kHdStages] tx
+  uint64_t* x_free = bars + kHdStages;          // [kHdStages] commit
+  uint64_t* a_ready = bars + 2 * kHdStages;     // [kHdStages] 128 arrivals
+  uint64_t* d_full = bars + 3 * kHdStages;      // [2] commit
+  uint64_t* d_free = d_full + 2;                // [2] 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 2);
+  float* s_bias = reinterpret_cast<float*>(bars + 3 * kHdStages + 6);  // [16]
   float4* s_tab = reinterpret_cast<float4*>(s_bias + 16);   // [N][48] {sc, sh, rsc, rsh}
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -54,16 +56,14 @@ __global__ void __launch_bounds__(320, 1) head_conv_norm_tc_kernel(HeadTcParams 
   const long long total = (long long)p.N * row_tiles;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_free[i], 1); tc::mbar_init(&a_ready[i], 128);
-      tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_free[i], 128);
-    }
+    for (int i = 0; i < kHdStages; ++i) { tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_free[i], 1); tc::mbar_init(&a_ready[i], 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_free[i], 128); }
     tc::fence_barrier_init();
   }
   {  // rows a clamped bulk copy never writes must hold finite values
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4* zx = reinterpret_cast<uint4*>(s_x);
-    for (int i = threadIdx.x; i < 4 * kHdTile / 16; i += blockDim.x) zx[i] = z;
+    for (int i = threadIdx.x; i < 2 * kHdStages * kHdTile / 16; i += blockDim.x) zx[i] = z;
   }
   {  // B image [k16][khalf][2 groups][8 cout][8 k] (the gemm_tc packing with NT = 16); rows >= Cout are zero
     __half* sb = reinterpret_cast<__half*>(s_w);
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(320, 1) head_conv_norm_tc_kernel(HeadTcParams 
     if (lane == 0) {
       int it = 0;
       for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int b = it & 1;
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        const int b = it % kHdStages;
+        const uint32_t ph = (uint32_t)((it / kHdStages) & 1);
         const int n = (int)(t / row_tiles), rt = (int)(t % row_tiles);
         const int rows = (int)min((long long)128, p.S - (long long)rt * 128);
         tc::mbar_wait(&x_free[b], ph ^ 1);
@@ -127,18 +127,17 @@ __global__ void __launch_bounds__(320, 1) head_conv_norm_tc_kernel(HeadTcParams 
     const uint32_t x_a = tc::smem_u32(s_x), w_a = tc::smem_u32(s_w);
     int it = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int b = it & 1;
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
-      tc::mbar_wait(&a_ready[b], ph);
-      tc::mbar_wait(&d_free[b], ph ^ 1);
+      const int st = it % kHdStages, b = it & 1;
+      tc::mbar_wait(&a_ready[st], (uint32_t)((it / kHdStages) & 1));
+      tc::mbar_wait(&d_free[b], (uint32_t)(((it >> 1) & 1) ^ 1));
       tc::fence_after_sync();
 #pragma unroll
       for (int k = 0; k < kHdC / 16; ++k) {
-        const uint64_t ad = tc::make_desc_kmajor_noswz(x_a + b * kHdTile + k * 4096, 2048, 128);
+        const uint64_t ad = tc::make_desc_kmajor_noswz(x_a + st * kHdTile + k * 4096, 2048, 128);
         const uint64_t bd = tc::make_desc_kmajor_noswz(w_a + k * kHdN * 32, kHdN * 16, 128);
         if (leader) tc::mma_f16_ss(tm + b * kHdN, ad, bd, idesc, k != 0 ? 1u : 0u);
       }
-      if (leader) { tc::mma_commit(&d_full[b]); tc::mma_commit(&x_free[b]); }
+      if (leader) { tc::mma_commit(&d_full[b]); tc::mma_commit(&x_free[st]); }
       __syncwarp();
     }
     __syncwarp();
@@ -169,11 +168,11 @@ __global__ void __launch_bounds__(320, 1) head_conv_norm_tc_kernel(HeadTcParams 
     int it = g;
     long long prev_t = -1;
     for (long long t = (long long)blockIdx.x + (long long)g * gridDim.x; t < total; t += 2LL * gridDim.x, it += 2) {
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      const int st = it % kHdStages;
       const int n = (int)(t / row_tiles);
-      tc::mbar_wait(&x_full[g], ph);
-      uint8_t* xr = s_x + g * kHdTile + row * 16;
-      const uint8_t* rr = s_r + g * kHdTile + row * 16;
+      tc::mbar_wait(&x_full[st], (uint32_t)((it / kHdStages) & 1));
+      uint8_t* xr = s_x + st * kHdTile + row * 16;
+      const uint8_t* rr = s_r + st * kHdTile + row * 16;
       const float4* tab = s_tab + n * kHdC;
 #pragma unroll
       for (int c = 0; c < kHdC / 8; ++c) {
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(320, 1) head_conv_norm_tc_kernel(HeadTcParams 
         *reinterpret_cast<uint4*>(xr + c * 2048) = o;
       }
       tc::fence_proxy_async();
-      tc::mbar_arrive(&a_ready[g]);
+      tc::mbar_arrive(&a_ready[st]);
       if (prev_t >= 0) output(it - 2, prev_t);
       prev_t = t;
     }
@@ -214,7 +213,7 @@ int launch_head_conv_norm_tc(const void* x, int N, int C, long long S, const flo
                              void* y, int out_dtype, cudaStream_t st) {
   if (C != kHdC || !res || (long long)N * C * 16 > kHdMaxTab || Cout > 16) return B200_ERR_UNSUPPORTED;
   HeadTcParams p{(const __half*)x, (const __half*)res, stats, res_stats, weight, bias, y, N, Cout, res_ctot, res_coff, S, eps, slope};
-  const int smem = 4 * kHdTile + kHdWBytes + 96 + 64 + N * C * 16 + 128;
+  const int smem = 2 * kHdStages * kHdTile + kHdWBytes + (3 * kHdStages + 6) * 8 + 64 + N * C * 16 + 128;
   const long long total = (long long)N * ((S + 127) / 128);
   dim3 grid((unsigned)std::min<long long>(total, num_sms()));
   if (out_dtype == B200_DT_F16) {
