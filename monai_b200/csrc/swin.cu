@@ -658,9 +658,11 @@ extern "C" int b200_head_conv_norm_nc8(const void* x, int N, int C, long long S,
   B200_REQUIRE(res || !res_stats, "head_conv_norm_nc8: residual statistics without a residual");
   B200_REQUIRE(out_dtype == B200_DT_F16 || out_dtype == B200_DT_F32, "head_conv_norm_nc8: bad dtype");
   {
-    // tensor-core version (head_tc.cu) for the shapes it covers; B200_HEAD_CUDA_CORE=1 keeps the CUDA-core kernel (A/B runs)
-    static const bool cuda_core_only = std::getenv("B200_HEAD_CUDA_CORE") != nullptr;
-    if (!cuda_core_only) {
+    // B200_HEAD_TC=1: tensor-core version (head_tc.cu) for the shapes it covers.  Off by default: both forms run at the same
+    // 4.1-4.4 TB/s on the C3 head (44.1 ms against 42.0 ms per volume) -- twelve concurrent 2 KB streams per tile, not the FMAs, set
+    // the pace -- so the UMMA buys nothing here.
+    static const bool use_tc = std::getenv("B200_HEAD_TC") != nullptr;
+    if (use_tc) {
       const int rc = launch_head_conv_norm_tc(x, N, C, S, stats, eps, res, res_ctot, res_coff, res_stats, slope, weight, bias, Cout, y,
                                               out_dtype, (cudaStream_t)stream);
       if (rc != B200_ERR_UNSUPPORTED) return rc;

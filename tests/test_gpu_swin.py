@@ -275,8 +275,8 @@ def test_fused_residual_tail_kernels():
 
 
 def test_head_on_tensor_cores_many_tiles_and_classes():
-    """head_conv_norm_nc8 at C = 48 runs as one UMMA per 128 voxels (head_tc.cu): 14 classes, several batch items, a ragged last
-    tile, fp16 and fp32 logits -- against torch fp32 (dynunet_block.py:104-111 + 247-267)."""
+    """head_conv_norm_nc8 at C = 48 (with B200_HEAD_TC=1: one UMMA per 128 voxels, head_tc.cu): 14 classes, several batch items, a
+    ragged last tile, fp16 and fp32 logits -- against torch fp32 (dynunet_block.py:104-111 + 247-267)."""
     g = torch.Generator().manual_seed(5)
     N, C, sp, CO = 3, 48, (9, 20, 23), 14
     y2 = (torch.randn((N, C, *sp), generator=g) * 1.3 + 0.2).half()
@@ -293,6 +293,20 @@ def test_head_on_tensor_cores_many_tiles_and_classes():
         assert r < 3e-3, (dt, r)
     again = K.head_conv_norm_nc8(y2n, st2, y3n, 0, st3, 0.01, 1e-5, w.to(DEV), b.to(DEV), out_dtype=torch.float16)
     assert torch.equal(again, got)
+
+
+def test_head_tensor_core_variant_in_a_subprocess():
+    """The opt-in UMMA form of the head (B200_HEAD_TC=1, read once per process) against the same references."""
+    import subprocess
+    import sys
+
+    if os.environ.get("B200_HEAD_TC"):
+        pytest.skip("already running with B200_HEAD_TC")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "head_on_tensor_cores or fused_residual_tail"], env=dict(os.environ, B200_HEAD_TC="1"),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout, r.stdout[-500:]
 
 
 def _build():
