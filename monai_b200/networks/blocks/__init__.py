@@ -1,2 +1,3 @@
 from .acti_norm import ADN
 from .convolutions import Convolution, ResidualUnit
+from .dynunet_block import UnetBasicBlock, UnetOutBlock, UnetResBlock, UnetUpBlock, get_conv_layer, get_output_padding, get_padding

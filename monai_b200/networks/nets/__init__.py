@@ -1,3 +1,4 @@
 from .basic_unet import BasicUNet, BasicUnet, Basicunet, basicunet
 from .unet import UNet, Unet
 from .swin_unetr import SwinUNETR
+from .dynunet import DynUNet, DynUnet, Dynunet

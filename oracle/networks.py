@@ -213,3 +213,53 @@ def swin_unetr_forward(sd: dict, x: torch.Tensor, heads=(3, 6, 12, 24)) -> torch
     dec0 = _up_block(dec1, enc1, sd, "decoder2")
     out = _up_block(dec0, enc0, sd, "decoder1")
     return F.conv3d(out, sd["out.conv.conv.weight"], sd["out.conv.conv.bias"])
+
+
+# -------------------------------------------------------------------------------------------------------- DynUNet
+def _t3(v):
+    return (int(v),) * 3 if isinstance(v, int) else tuple(int(i) for i in v)
+
+
+def _dyn_pad(k, s):
+    """get_padding / get_output_padding (monai/networks/blocks/dynunet_block.py:304-327)."""
+    k, s = _t3(k), _t3(s)
+    p = tuple(int((ki - si + 1) / 2) for ki, si in zip(k, s))
+    return p, tuple(2 * pi + si - ki for pi, si, ki in zip(p, s, k))
+
+
+def _dyn_norm(x, sd, prefix):
+    return F.instance_norm(x, weight=sd.get(prefix + ".weight"), bias=sd.get(prefix + ".bias"), eps=1e-5)
+
+
+def _dyn_block(x, sd, prefix, k, s, res):
+    """UnetBasicBlock / UnetResBlock (dynunet_block.py:25-177)."""
+    out = F.conv3d(x, sd[prefix + ".conv1.conv.weight"], None, stride=_t3(s), padding=_dyn_pad(k, s)[0])
+    out = F.leaky_relu(_dyn_norm(out, sd, prefix + ".norm1"), 0.01)
+    out = _dyn_norm(F.conv3d(out, sd[prefix + ".conv2.conv.weight"], None, stride=1, padding=_dyn_pad(k, 1)[0]), sd, prefix + ".norm2")
+    if res:
+        r = x
+        if (prefix + ".conv3.conv.weight") in sd:
+            r = _dyn_norm(F.conv3d(x, sd[prefix + ".conv3.conv.weight"], None, stride=_t3(s), padding=_dyn_pad(1, s)[0]), sd, prefix + ".norm3")
+        out = out + r
+    return F.leaky_relu(out, 0.01)
+
+
+def dynunet_forward(sd: dict, x: torch.Tensor, kernel_size, strides, upsample_kernel_size, res_block: bool = False) -> torch.Tensor:
+    """DynUNet in eval mode (monai/networks/nets/dynunet.py:265-272 with the skip chain of :24-53, 170-236): input block, down
+    blocks, bottleneck, then transposed convolution + concat + basic block per level, 1x1 output block."""
+    n = len(strides)
+    skips = []
+    cur = _dyn_block(x, sd, "input_block", kernel_size[0], strides[0], res_block)
+    skips.append(cur)
+    for i in range(n - 2):
+        cur = _dyn_block(cur, sd, f"downsamples.{i}", kernel_size[1 + i], strides[1 + i], res_block)
+        skips.append(cur)
+    cur = _dyn_block(cur, sd, "bottleneck", kernel_size[-1], strides[-1], res_block)
+    for j in range(n - 1):   # upsamples[j] pairs with level n - 2 - j
+        lvl = n - 2 - j
+        uk = upsample_kernel_size[::-1][j]
+        pad, opad = _dyn_pad(uk, uk)
+        p = f"upsamples.{j}"
+        up = F.conv_transpose3d(cur, sd[p + ".transp_conv.conv.weight"], sd.get(p + ".transp_conv.conv.bias"), stride=_t3(uk), padding=pad, output_padding=opad)
+        cur = _dyn_block(torch.cat((up, skips[lvl]), dim=1), sd, p + ".conv_block", kernel_size[1:][::-1][j], 1, False)
+    return F.conv3d(cur, sd["output_block.conv.conv.weight"], sd["output_block.conv.conv.bias"])

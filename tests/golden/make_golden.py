@@ -167,6 +167,28 @@ def nets_r2():
     dump("fs48_in4_v2_64", net, torch.randn(1, 4, 64, 64, 64, generator=torch.Generator().manual_seed(19)).half().float())
 
 
+from dynunet_cases import DYNUNET_CASES  # noqa: E402  (shared with the tests)
+
+
+def dynunet():
+    """DynUNet (eval mode) of the real reference on name-keyed deterministic weights: outputs and state_dict key / shape lists."""
+    import json
+
+    from monai.networks.nets import DynUNet
+
+    out, keys = {}, {}
+    for i, (kw, shape, seed) in enumerate(DYNUNET_CASES):
+        net = _load_named(DynUNet(**kw), seed)
+        x = torch.randn(shape, generator=torch.Generator().manual_seed(40 + i))
+        with torch.no_grad():
+            y = net(x)
+        out[f"c{i}.x"], out[f"c{i}.y"] = x.numpy(), y.numpy()
+        keys[f"c{i}"] = {k: list(v.shape) for k, v in net.state_dict().items()}
+    save("dynunet.npz", **out)
+    with open(os.path.join(HERE, "dynunet_state_dict_keys.json"), "w") as f:
+        json.dump(keys, f)
+
+
 def buffered():
     """Window order / batching the predictor observes in the reference's buffered mode (with_coord=True), plus the result."""
     out = {}
@@ -478,6 +500,6 @@ def unit_goldens():
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "buffered", "resampler", "grid_pull_ref", "lazy_inverse", "transforms", "post", "patch", "unit_goldens"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "dynunet", "buffered", "resampler", "grid_pull_ref", "lazy_inverse", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

@@ -185,3 +185,36 @@ def test_state_dict_keys_and_shapes_match_the_reference(golden_dir):
     # legacy bundles pass img_size: accepted and ignored
     with contextlib.redirect_stdout(io.StringIO()):
         SwinUNETR(img_size=96, in_channels=1, out_channels=2, feature_size=48)
+
+
+def _dynunet_cases():
+    sys_path_golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_mk_golden_cases", os.path.join(sys_path_golden, "dynunet_cases.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.DYNUNET_CASES
+
+
+def test_dynunet_oracle_and_module_tree_match_the_reference(golden_dir):
+    """f4 (other predictors): oracle.networks.dynunet_forward against outputs of the real reference DynUNet (tests/golden/dynunet.npz:
+    isotropic default with affine instance norm, anisotropic residual variant, deep supervision in eval mode), and the product's
+    DynUNet has the reference's state_dict keys and shapes (tests/golden/dynunet_state_dict_keys.json)."""
+    import json
+
+    from monai_b200.networks.nets import DynUNet
+    from weights import fill_state_dict
+
+    g = np.load(os.path.join(golden_dir, "dynunet.npz"))
+    want = json.load(open(os.path.join(golden_dir, "dynunet_state_dict_keys.json")))
+    for i, (kw, shape, seed) in enumerate(_dynunet_cases()):
+        net = DynUNet(**kw)
+        sd = net.state_dict()
+        assert {k: list(v.shape) for k, v in sd.items()} == want[f"c{i}"], i
+        # blocks are registered twice (flat containers + skip chain): load through the module so that aliases resolve as in the reference
+        net.load_state_dict(fill_state_dict(sd, seed))
+        sd = net.state_dict()
+        y = onet.dynunet_forward(sd, torch.from_numpy(g[f"c{i}.x"]), kw["kernel_size"], kw["strides"], kw["upsample_kernel_size"], kw.get("res_block", False))
+        assert tuple(y.shape) == tuple(g[f"c{i}.y"].shape)
+        np.testing.assert_allclose(y.numpy(), g[f"c{i}.y"], rtol=1e-4, atol=1e-4)
