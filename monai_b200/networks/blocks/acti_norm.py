@@ -50,6 +50,17 @@ def norm_act_from_modules(
             if norm.track_running_stats:
                 raise NotImplementedError("InstanceNorm with running statistics is not supported")
             stats, eps, gamma, beta = K.instnorm_stats(x), norm.eps, norm.weight, norm.bias
+        elif isinstance(norm, nn.GroupNorm):
+            # the channels of a group are contiguous in NCDHW: group statistics = "instance" statistics of the [N, G, (C/G)*D, H, W] view;
+            # handing every channel its group's sums divided by C/G makes b200_norm_act's mean = sum / S the group mean (same for E[x^2])
+            G = norm.num_groups
+            N_, C_ = x.shape[:2]
+            cg = C_ // G
+            if x.dim() < 3 or not x[0].is_contiguous():
+                raise NotImplementedError("GroupNorm needs a [N, C, *spatial] input that is contiguous per sample")
+            gstats = K.instnorm_stats(x.reshape(N_, G, cg * x.shape[2], *x.shape[3:]))
+            stats = (gstats / float(cg)).repeat_interleave(cg, dim=0).contiguous()   # [N*C, 2]: a tiny table
+            eps, gamma, beta = norm.eps, norm.weight, norm.bias
         elif isinstance(norm, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
             if norm.training:
                 raise RuntimeError("monai_b200 is inference-only: call .eval() before running BatchNorm layers")

@@ -45,7 +45,9 @@ def get_norm_layer(name, spatial_dims: int = 1, channels: int | None = 1):
         return (nn.InstanceNorm1d, nn.InstanceNorm2d, nn.InstanceNorm3d)[spatial_dims - 1](channels, **kw)
     if key == "batch":
         return (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)[spatial_dims - 1](channels, **kw)
-    raise NotImplementedError(f"monai_b200 supports 'instance' and 'batch' normalisation, got {norm_name!r}.")
+    if key == "group":   # Norm.GROUP (monai/networks/layers/factories.py): nn.GroupNorm(num_groups, num_channels, ...)
+        return nn.GroupNorm(num_channels=channels, **kw)
+    raise NotImplementedError(f"monai_b200 supports 'instance', 'batch' and 'group' normalisation, got {norm_name!r}.")
 
 
 def get_dropout_layer(name, dropout_dim: int = 1):

@@ -263,3 +263,45 @@ def dynunet_forward(sd: dict, x: torch.Tensor, kernel_size, strides, upsample_ke
         up = F.conv_transpose3d(cur, sd[p + ".transp_conv.conv.weight"], sd.get(p + ".transp_conv.conv.bias"), stride=_t3(uk), padding=pad, output_padding=opad)
         cur = _dyn_block(torch.cat((up, skips[lvl]), dim=1), sd, p + ".conv_block", kernel_size[1:][::-1][j], 1, False)
     return F.conv3d(cur, sd["output_block.conv.conv.weight"], sd["output_block.conv.conv.bias"])
+
+
+# ------------------------------------------------------------------------------------------------------ SegResNet
+def _seg_norm_act(x, sd, prefix, groups, slope):
+    """get_norm_layer(("GROUP", {"num_groups": g})) | "instance", then ReLU / LeakyReLU (segresnet_block.py:60-66)."""
+    if groups:
+        x = F.group_norm(x, groups, sd[prefix + ".weight"], sd[prefix + ".bias"], eps=1e-5)
+    else:
+        x = F.instance_norm(x, eps=1e-5)
+    return F.relu(x) if slope is None else F.leaky_relu(x, slope)
+
+
+def _seg_resblock(x, sd, prefix, groups, slope):
+    """ResBlock.forward (monai/networks/blocks/segresnet_block.py:83-96)."""
+    y = F.conv3d(_seg_norm_act(x, sd, prefix + ".norm1", groups, slope), sd[prefix + ".conv1.conv.weight"], None, padding=1)
+    y = F.conv3d(_seg_norm_act(y, sd, prefix + ".norm2", groups, slope), sd[prefix + ".conv2.conv.weight"], None, padding=1)
+    return y + x
+
+
+def segresnet_forward(sd: dict, x: torch.Tensor, blocks_down=(1, 2, 2, 4), blocks_up=(1, 1, 1), groups: int = 8, slope=None,
+                      upsample_mode: str = "nontrainable") -> torch.Tensor:
+    """SegResNet.forward in eval mode (monai/networks/nets/segresnet.py:160-197): encode, reverse the skips, decode, conv_final."""
+    x = F.conv3d(x, sd["convInit.conv.weight"], None, padding=1)
+    down = []
+    for i, n in enumerate(blocks_down):
+        if i > 0:
+            x = F.conv3d(x, sd[f"down_layers.{i}.0.conv.weight"], None, stride=2, padding=1)
+        for j in range(n):
+            x = _seg_resblock(x, sd, f"down_layers.{i}.{j + 1}", groups, slope)
+        down.append(x)
+    down.reverse()
+    for i, n in enumerate(blocks_up):
+        x = F.conv3d(x, sd[f"up_samples.{i}.0.conv.weight"], None)
+        if upsample_mode == "deconv":
+            x = F.conv_transpose3d(x, sd[f"up_samples.{i}.1.deconv.weight"], sd[f"up_samples.{i}.1.deconv.bias"], stride=2)
+        else:
+            x = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+        x = x + down[i + 1]
+        for j in range(n):
+            x = _seg_resblock(x, sd, f"up_layers.{i}.{j}", groups, slope)
+    x = _seg_norm_act(x, sd, "conv_final.0", groups, slope)
+    return F.conv3d(x, sd["conv_final.2.conv.weight"], sd["conv_final.2.conv.bias"])

@@ -218,3 +218,25 @@ def test_dynunet_oracle_and_module_tree_match_the_reference(golden_dir):
         y = onet.dynunet_forward(sd, torch.from_numpy(g[f"c{i}.x"]), kw["kernel_size"], kw["strides"], kw["upsample_kernel_size"], kw.get("res_block", False))
         assert tuple(y.shape) == tuple(g[f"c{i}.y"].shape)
         np.testing.assert_allclose(y.numpy(), g[f"c{i}.y"], rtol=1e-4, atol=1e-4)
+
+
+def test_segresnet_oracle_and_module_tree_match_the_reference(golden_dir):
+    """f4: oracle.networks.segresnet_forward against outputs of the real reference SegResNet (tests/golden/segresnet.npz: defaults with
+    GroupNorm + trilinear upsampling, transposed-convolution variant, instance norm + LeakyReLU), and the product's SegResNet has
+    the reference's state_dict keys and shapes."""
+    import importlib.util
+    import json
+
+    from monai_b200.networks.nets import SegResNet
+
+    spec = importlib.util.spec_from_file_location("_segresnet_cases", os.path.join(golden_dir, "segresnet_cases.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(golden_dir, "segresnet.npz"))
+    want = json.load(open(os.path.join(golden_dir, "segresnet_state_dict_keys.json")))
+    for i, (kw, okw, shape, seed) in enumerate(mod.SEGRESNET_CASES):
+        net = SegResNet(**kw)
+        assert {k: list(v.shape) for k, v in net.state_dict().items()} == want[f"c{i}"], i
+        net.load_state_dict(fill_state_dict(net.state_dict(), seed))
+        y = onet.segresnet_forward(net.state_dict(), torch.from_numpy(g[f"c{i}.x"]), **okw)
+        np.testing.assert_allclose(y.numpy(), g[f"c{i}.y"], rtol=1e-4, atol=1e-4)
