@@ -233,14 +233,14 @@ def cpu_baseline_leg(wl, budget_s: float = 20.0) -> dict:
                       f"seconds/window extrapolated to {wl['windows']} windows"}
 
 
-def _transform_pipeline():
+def _transform_pipeline(lazy: bool = False):
     from monai_b200.transforms import Compose, GaussianSmoothd, RandAffined, Spacingd
 
     pipe = Compose([
         Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear"),
         RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border"),
         GaussianSmoothd(keys=["image"], sigma=1.0),
-    ])
+    ], lazy=lazy)   # lazy: Spacingd and RandAffined compose into ONE resample (monai/transforms/lazy/functional.py:84-296)
     pipe.transforms[1].set_random_state(seed=0)
     return pipe
 
@@ -321,6 +321,10 @@ def run_transforms(args, wl):
     K.profile_start()
     y = step_resident()
     prof = K.profile_stop()
+    # the same pipeline with Compose(lazy=True): reported next to the eager (reference default) number, not instead of it
+    eager_pipe, pipe = pipe, _transform_pipeline(lazy=True)
+    ms_lazy = timed(step_resident, args.steps, 1)
+    pipe = eager_pipe
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -344,6 +348,8 @@ def run_transforms(args, wl):
                      "peak_source": pk["src"], "launches": st["n"], "avg_launch_ms": avg_ms,
                      "share_of_kernel_time": st["ms"] / (sum(v["ms"] for v in prof.values()) or 1.0)},
         "kernels": {k: {"ms": round(v["ms"], 4), "n": v["n"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]},
+        "lazy": {"ms_per_step": ms_lazy / args.steps, "value": nvox / (ms_lazy / args.steps * 1e-3), "unit": "voxels/s",
+                 "note": "Compose(lazy=True): Spacingd + RandAffined fused into one resample launch per volume"},
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = transforms_cpu_leg(wl)

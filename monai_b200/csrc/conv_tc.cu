@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
   uint64_t* empty_b = full_b + kSB;     // [kSB]
   uint64_t* acc_full = empty_b + kSB;   // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
-  uint64_t* ready_a = acc_empty + 2;    // [kSA] NORM: 256 arrivals of the transform warps
+  uint64_t* ready_a = acc_empty + 2;    // [kSA] NORM: 8 arrivals (one per transform warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_a + kSA);
   static_assert(3 * kSA + 2 * kSB + 4 + 1 <= 48, "barrier block");
   float* s_stats = reinterpret_cast<float*>(bars + 48);  // [4][2*NT]
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
   const int num_kc = d.Cin / 16;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&ready_a[i], 256); }
+    for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&ready_a[i], 8); }
     for (int i = 0; i < kSB; ++i) { tc::mbar_init(&full_b[i], 1); tc::mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
             }
         }
         tc::fence_proxy_async();       // generic-proxy stores -> visible to tcgen05.mma
-        tc::mbar_arrive(&ready_a[sa]);
+        __syncwarp();                  // one arrival per warp
+        if (lane == 0) tc::mbar_arrive(&ready_a[sa]);
         if (++sa == kSA) { sa = 0; pa ^= 1; }
       }
     }

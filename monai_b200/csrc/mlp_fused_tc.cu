@@ -51,13 +51,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_tc_kernel(MlpParams 
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_w2 + kMlpW2Bytes);
   uint64_t* x_full = bars;          // [2] tx
   uint64_t* x_free = bars + 2;      // [2] commit (GEMM1 has read the tile)
-  uint64_t* ln_done = bars + 4;     // [2] 128 arrivals
+  uint64_t* ln_done = bars + 4;     // [2] 4 arrivals (one per row warp)
   uint64_t* d1_full = bars + 6;     // [2] commit
-  uint64_t* d1_free = bars + 8;     // [2] 512 arrivals
-  uint64_t* h_full = bars + 10;     // [2] 512 arrivals
+  uint64_t* d1_free = bars + 8;     // [2] 16 arrivals (one per GELU warp)
+  uint64_t* h_full = bars + 10;     // [2] 16 arrivals
   uint64_t* h_free = bars + 12;     // [2] commit (GEMM2 has read the tile)
   uint64_t* d2_full = bars + 14;    // [2] commit
-  uint64_t* d2_free = bars + 16;    // [2] 128 arrivals
+  uint64_t* d2_free = bars + 16;    // [2] 4 arrivals
   uint64_t* w_full = bars + 18;     // tx
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   float* s_gamma = reinterpret_cast<float*>(bars + 32);   // 256 bytes of barrier space precede the parameter table
@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_tc_kernel(MlpParams 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_free[i], 1); tc::mbar_init(&ln_done[i], 128);
-      tc::mbar_init(&d1_full[i], 1); tc::mbar_init(&d1_free[i], 512); tc::mbar_init(&h_full[i], 512); tc::mbar_init(&h_free[i], 1);
-      tc::mbar_init(&d2_full[i], 1); tc::mbar_init(&d2_free[i], 128);
+      tc::mbar_init(&x_full[i], 1); tc::mbar_init(&x_free[i], 1); tc::mbar_init(&ln_done[i], 4);
+      tc::mbar_init(&d1_full[i], 1); tc::mbar_init(&d1_free[i], 16); tc::mbar_init(&h_full[i], 16); tc::mbar_init(&h_free[i], 1);
+      tc::mbar_init(&d2_full[i], 1); tc::mbar_init(&d2_free[i], 4);
     }
     tc::mbar_init(w_full, 1);
     tc::fence_barrier_init();
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_tc_kernel(MlpParams 
         *reinterpret_cast<uint4*>(xr + c * 2048) = o;
       }
       tc::fence_proxy_async();
-      tc::mbar_arrive(&ln_done[b]);
+      __syncwarp();                     // one arrival per warp: per-thread arrivals serialise on one shared-memory word
+      if (lane == 0) tc::mbar_arrive(&ln_done[b]);
     };
     auto epilogue = [&](int it, long long t) {
       const int b = it & 1;
@@ -215,7 +216,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_tc_kernel(MlpParams 
       tc::tmem_ld16(td, v0); tc::tmem_ld16(td + 16, v1); tc::tmem_ld16(td + 32, v2);
       tc::tmem_ld_wait16(v0); tc::tmem_ld_wait16(v1); tc::tmem_ld_wait16(v2);
       tc::fence_before_sync();
-      tc::mbar_arrive(&d2_free[b]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&d2_free[b]);
       if (ok) {
         __half* yg = p.y + ((long long)n * (p.y_ctot / 8) * p.S + r) * 8;
         auto put = [&](const uint32_t (&v)[16], int c16) {
@@ -278,8 +280,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_tc_kernel(MlpParams 
       tc::tmem_ld_wait16(vc); emit(vc, 2);
       tc::fence_proxy_async();
       tc::fence_before_sync();
-      tc::mbar_arrive(&h_full[b]);
-      tc::mbar_arrive(&d1_free[b]);
+      __syncwarp();
+      if (lane == 0) { tc::mbar_arrive(&h_full[b]); tc::mbar_arrive(&d1_free[b]); }
     }
   }
   __syncthreads();
