@@ -19,15 +19,15 @@
 //            are 16-byte vectors of 8 dims); the ones column accumulates the row sums l_h in fp32;
 //   epilogue: O = (a0 O0 + a1 O1) / (a0 l0 + a1 l1), a_h = 2^(m_h - max(m0, m1))  -> fp16 NC8.
 // Because no maximum is shared between the halves, the tensor pipe computes PV_h(i) and S_h(i+1) for one half while the softmax
-// warps exponentiate the OTHER half: TMEM has room for one S tile only (2 x 176 + 2 x 32 + 64 identity columns), and the
+// warps of the OTHER half exponentiate: TMEM has room for one S tile only (2 x 176 + 2 x 32 + 64 identity columns), and the
 // earlier single-maximum version (both halves needed before any exponential) left every softmax warp idle for the ~1 000 cycles
 // the S MMAs of the next tile take -- 8 300 cycles per tile against a MUFU floor of 2 816 (ncu: 33 % issue-active, MUFU 38 %,
 // tensor 25 %).
 // Q, K, V tiles are 1-D bulk copies of NC8 rows (contiguous per 8-channel chunk).
 //
-// Warp roles (576 threads): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-17 = softmax (+ the epilogue): all
-// sixteen work on key half 0, then on key half 1; the four threads of a query row split the 16-column chunks of the half and
-// exchange their maxima through shared memory and a 128-thread named barrier.
+// Warp roles (576 threads): warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = softmax of key half 0,
+// warps 10-17 = softmax of key half 1 (+ the epilogue); the two threads of a (query row, half) split its 16-column chunks and
+// exchange their maxima through shared memory and a 64-thread named barrier.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "../../include/monai_b200.h"
@@ -90,7 +90,7 @@ __device__ __forceinline__ float max16(const uint32_t (&v)[16], float m) {
   return m;
 }
 
-constexpr int kAtThreads = 64 + 512;        // producer, MMA issuer, 16 softmax warps (four threads per query row)
+constexpr int kAtThreads = 64 + 512;        // producer, MMA issuer, 16 softmax warps (2 key halves x 2 threads per query row)
 
 template <int NPAD>
 __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(AttnTcParams p) {
@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
   uint8_t* s_q = s_p + kAtPBytes;
   uint8_t* s_k = s_q + 2 * 2048;
   uint8_t* s_v = s_k + 2 * kAtKChunk;                 // 4 chunk slots: V dims 0-7, 8-15, ones column, zeros
-  float* s_max = reinterpret_cast<float*>(s_v + 4 * kAtKChunk);   // [half][sub 0..3][128]: maxima exchanged by the four threads of a (row, half)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_max + 8 * 128);
+  float* s_max = reinterpret_cast<float*>(s_v + 4 * kAtKChunk);   // [half][sub][128]: maxima exchanged by the two threads of a (row, half)
+  float* s_hmax = s_max + 4 * 128;                                // [tile parity][half][128]: half maxima for the epilogue
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hmax + 4 * 128);
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* s_full = bars + 2;      // [2]
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
     tc::mbar_init(qk_full, 1); tc::mbar_init(qk_empty, 1); tc::mbar_init(v_full, 1);
     tc::mbar_init(o_empty, 4); tc::mbar_init(init_done, 1);
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 16); tc::mbar_init(&p_full[i], 16); tc::mbar_init(&pv_done[i], 1);
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 8); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&pv_done[i], 1);
     }
     tc::fence_barrier_init();
   }
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
       if (leader) tc::mma_commit(&pv_done[hf]);
       __syncwarp();
     };
-    // (Issuing S0(i+1) BEFORE PV0(i) -- so that the idle softmax warps of half 0 restart sooner -- measured slower: 0.578 ms
-    // against 0.473 ms on the stage-1 shape; PV0 then delays the P buffer and the epilogue of the other half.)
+    // Measured alternatives that were NOT faster (stage-1 shape, batch 8: this version 0.473 ms): issuing S0(i+1) before PV0(i)
+    // 0.578 ms; all sixteen softmax warps on one half at a time (full MUFU rate per half) 0.522 ms.
     // Ping-pong between the key halves, across tiles: the issue order is  PV0(i), S0(i+1), PV1(i), S1(i+1) -- while the softmax
     // warps of one half exponentiate, the tensor pipe works for the other half.
     const long long ntile = hi - lo;
@@ -260,99 +261,91 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
     __syncwarp();
   } else {
     // ===================== softmax + epilogue (warps 2..17) =====================
-    // ALL sixteen warps work on key half 0, then on key half 1 (four threads per query row split the 16-column chunks of the
-    // half): the exponentials of one half run at the full MUFU rate while the tensor pipe produces PV and the next S of the
-    // OTHER half.  (Dedicated warps per half -- the previous scheme -- had both halves exponentiating at the same time at half the
-    // MUFU rate each and then BOTH waiting for their S MMAs: 5 100 cycles per tile, 37 % of the softmax warps' time in that wait.)
-    const int sub = (warp - 2) >> 2;          // 0..3: which share of the chunks of a half
+    // Warps 2-9 own key half 0, warps 10-17 key half 1; the two threads of a (query row, half) split its 16-column chunks.
+    const int jj = (warp - 2) >> 2;
+    const int hf = jj >> 1, sub = jj & 1;
     const int q = warp & 3;                   // TMEM lane quarter
     const int row = q * 32 + lane;
     constexpr int nchunk = NH / 16;
-    constexpr int kCMax = (nchunk + 3) / 4;                       // chunks of the largest share
-    const int cnt = (nchunk + 3 - sub) / 4;                       // warp-uniform; shares differ by at most one chunk
-    int c_lo = 0;
-    for (int t = 0; t < sub; ++t) c_lo += (nchunk + 3 - t) / 4;
+    // contiguous chunk ranges; the thread that also runs the epilogue (half 1 / sub 0) takes the smaller share
+    constexpr int kCMax = (nchunk + 1) / 2;                       // chunks of the larger share
+    const bool big = (sub == 0) != (hf == 1);                     // sub 0 of half 0 and sub 1 of half 1 take the larger share
+    const int cnt = big ? kCMax : nchunk - kCMax;                 // warp-uniform
+    const int c_lo = sub ? nchunk - cnt : 0;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int bar_id = 1 + q;                 // the four warps of a lane quarter exchange their maxima
+    const uint32_t ts = tlane + hf * kAtColS1 + c_lo * 16;        // this thread's first S column
+    uint8_t* prow = s_p + ((hf * NH) / 8 + 2 * c_lo) * 2048 + row * 16;
+    const int bar_id = 1 + hf * 4 + q;
     int it = 0;
     for (long long f = lo; f < hi; ++f, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      float mh[2];
+      // ---- pass 1: exact maximum of this key half of the row (two independent running maxima)
+      float m = -INFINITY, m2 = -INFINITY;
+      tc::mbar_wait(&s_full[hf], ph);
+      tc::fence_after_sync();
+      {
+        uint32_t va[16], vb[16];
+        if (cnt > 0) tc::tmem_ld16(ts, va);
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const uint32_t ts = tlane + hf * kAtColS1 + c_lo * 16;        // this thread's first S column of the half
-        uint8_t* prow = s_p + ((hf * NH) / 8 + 2 * c_lo) * 2048 + row * 16;
-        // ---- pass 1: exact maximum of this key half of the row (two independent running maxima)
-        float m = -INFINITY, m2 = -INFINITY;
-        tc::mbar_wait(&s_full[hf], ph);
-        tc::fence_after_sync();
-        {
-          uint32_t va[16], vb[16];
-          if (cnt > 0) tc::tmem_ld16(ts, va);
-#pragma unroll
-          for (int k = 0; k < kCMax; k += 2) {
-            if (k < cnt) {
-              tc::tmem_ld_wait16(va);
-              if (k + 1 < cnt) tc::tmem_ld16(ts + (k + 1) * 16, vb);
-              m = max16(va, m);
-            }
-            if (k + 1 < kCMax && k + 1 < cnt) {
-              tc::tmem_ld_wait16(vb);
-              if (k + 2 < cnt) tc::tmem_ld16(ts + (k + 2) * 16, va);
-              m2 = max16(vb, m2);
-            }
+        for (int k = 0; k < kCMax; k += 2) {
+          if (k < cnt) {
+            tc::tmem_ld_wait16(va);
+            if (k + 1 < cnt) tc::tmem_ld16(ts + (k + 1) * 16, vb);
+            m = max16(va, m);
+          }
+          if (k + 1 < kCMax && k + 1 < cnt) {
+            tc::tmem_ld_wait16(vb);
+            if (k + 2 < cnt) tc::tmem_ld16(ts + (k + 2) * 16, va);
+            m2 = max16(vb, m2);
           }
         }
-        m = fmaxf(m, m2);
-        float* sm = s_max + hf * 512;                                 // [half][sub][128]
-        sm[sub * 128 + row] = m;
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        m = fmaxf(fmaxf(sm[row], sm[128 + row]), fmaxf(sm[256 + row], sm[384 + row]));
-        mh[hf] = m;
-        // P half free?  (first tile: the identity staged in the P region has been copied to TMEM)
-        if (it == 0) tc::mbar_wait(init_done, 0u);
-        else tc::mbar_wait(&pv_done[hf], (uint32_t)((it - 1) & 1));
-        // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs
-        {
-          uint32_t va[16], vb[16];
-          auto emit = [&](const uint32_t (&v)[16], int k) {
-            uint4 u0, u1;
-            u0.x = exp2_pack(__uint_as_float(v[0]), __uint_as_float(v[1]), m);
-            u0.y = exp2_pack(__uint_as_float(v[2]), __uint_as_float(v[3]), m);
-            u0.z = exp2_pack(__uint_as_float(v[4]), __uint_as_float(v[5]), m);
-            u0.w = exp2_pack(__uint_as_float(v[6]), __uint_as_float(v[7]), m);
-            *reinterpret_cast<uint4*>(prow + (2 * k) * 2048) = u0;
-            u1.x = exp2_pack(__uint_as_float(v[8]), __uint_as_float(v[9]), m);
-            u1.y = exp2_pack(__uint_as_float(v[10]), __uint_as_float(v[11]), m);
-            u1.z = exp2_pack(__uint_as_float(v[12]), __uint_as_float(v[13]), m);
-            u1.w = exp2_pack(__uint_as_float(v[14]), __uint_as_float(v[15]), m);
-            *reinterpret_cast<uint4*>(prow + (2 * k + 1) * 2048) = u1;
-          };
-          if (cnt > 0) tc::tmem_ld16(ts, va);
-#pragma unroll
-          for (int k = 0; k < kCMax; k += 2) {
-            if (k < cnt) {
-              tc::tmem_ld_wait16(va);
-              if (k + 1 < cnt) tc::tmem_ld16(ts + (k + 1) * 16, vb);
-              emit(va, k);
-            }
-            if (k + 1 < kCMax && k + 1 < cnt) {
-              tc::tmem_ld_wait16(vb);
-              if (k + 2 < cnt) tc::tmem_ld16(ts + (k + 2) * 16, va);
-              emit(vb, k + 1);
-            }
-          }
-        }
-        tc::fence_proxy_async();       // P (generic-proxy stores) -> visible to the tensor core
-        tc::fence_before_sync();       // this thread's TMEM reads of this S half are complete
-        // ONE arrival per warp (the barriers count 16): 512 per-thread arrivals are 512 serialised shared-memory atomics on one
-        // word, four times per tile -- comparable to the softmax itself
-        __syncwarp();
-        if (lane == 0) { tc::mbar_arrive(&p_full[hf]); tc::mbar_arrive(&s_empty[hf]); }
       }
-      if (sub == 3) {
-        // ---- epilogue (the warps with the smallest chunk share): combine the two halves (flash-attention style) and normalise:
-        //      O = (a0 O0 + a1 O1) / (a0 l0 + a1 l1),  a_h = 2^(m_h - max(m0, m1)), l_h = the ones column of O_h
+      m = fmaxf(m, m2);
+      s_max[(hf * 2 + sub) * 128 + row] = m;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      m = fmaxf(m, s_max[(hf * 2 + (sub ^ 1)) * 128 + row]);
+      if (sub == 0) s_hmax[((it & 1) * 2 + hf) * 128 + row] = m;     // read by the epilogue of this tile
+      // P half free?  (first tile: the identity staged in the P region has been copied to TMEM)
+      if (it == 0) tc::mbar_wait(init_done, 0u);
+      else tc::mbar_wait(&pv_done[hf], (uint32_t)((it - 1) & 1));
+      // ---- pass 2: P = 2^(S - m) as fp16, written as the K-major A operand of the PV MMAs
+      {
+        uint32_t va[16], vb[16];
+        auto emit = [&](const uint32_t (&v)[16], int k) {
+          uint4 u0, u1;
+          u0.x = exp2_pack(__uint_as_float(v[0]), __uint_as_float(v[1]), m);
+          u0.y = exp2_pack(__uint_as_float(v[2]), __uint_as_float(v[3]), m);
+          u0.z = exp2_pack(__uint_as_float(v[4]), __uint_as_float(v[5]), m);
+          u0.w = exp2_pack(__uint_as_float(v[6]), __uint_as_float(v[7]), m);
+          *reinterpret_cast<uint4*>(prow + (2 * k) * 2048) = u0;
+          u1.x = exp2_pack(__uint_as_float(v[8]), __uint_as_float(v[9]), m);
+          u1.y = exp2_pack(__uint_as_float(v[10]), __uint_as_float(v[11]), m);
+          u1.z = exp2_pack(__uint_as_float(v[12]), __uint_as_float(v[13]), m);
+          u1.w = exp2_pack(__uint_as_float(v[14]), __uint_as_float(v[15]), m);
+          *reinterpret_cast<uint4*>(prow + (2 * k + 1) * 2048) = u1;
+        };
+        if (cnt > 0) tc::tmem_ld16(ts, va);
+#pragma unroll
+        for (int k = 0; k < kCMax; k += 2) {
+          if (k < cnt) {
+            tc::tmem_ld_wait16(va);
+            if (k + 1 < cnt) tc::tmem_ld16(ts + (k + 1) * 16, vb);
+            emit(va, k);
+          }
+          if (k + 1 < kCMax && k + 1 < cnt) {
+            tc::tmem_ld_wait16(vb);
+            if (k + 2 < cnt) tc::tmem_ld16(ts + (k + 2) * 16, va);
+            emit(vb, k + 1);
+          }
+        }
+      }
+      tc::fence_proxy_async();       // P (generic-proxy stores) -> visible to the tensor core
+      tc::fence_before_sync();       // this thread's TMEM reads of this S half are complete
+      __syncwarp();                  // one arrival per warp (the barriers count 8): per-thread arrivals serialise on one word
+      if (lane == 0) { tc::mbar_arrive(&p_full[hf]); tc::mbar_arrive(&s_empty[hf]); }
+      if (hf == 1 && sub == 0) {
+        // ---- epilogue: combine the two halves (flash-attention style) and normalise:  O = (a0 O0 + a1 O1) / (a0 l0 + a1 l1),
+        //      a_h = 2^(m_h - max(m0, m1)), l_h = the ones column of O_h
         const AttnTile t = attn_decode(p, f);
         tc::mbar_wait(&pv_done[0], ph);
         tc::mbar_wait(&pv_done[1], ph);
@@ -362,16 +355,17 @@ __global__ void __launch_bounds__(kAtThreads, 1) window_attention_tc_kernel(Attn
         tc::tmem_ld8(tlane + kAtColO0 + 16, l0);
         tc::tmem_ld16(tlane + kAtColO1, o1);
         tc::tmem_ld8(tlane + kAtColO1 + 16, l1);
+        const float m0 = s_hmax[((it & 1) * 2 + 0) * 128 + row], m1 = m;
         tc::tmem_ld_wait();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(o_empty);
         const int r = t.rt * 128 + row;
         if (r < n) {
-          const float mm = fmaxf(mh[0], mh[1]);
+          const float mm = fmaxf(m0, m1);
           float a0, a1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(mh[0] - mm));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(mh[1] - mm));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(m0 - mm));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(m1 - mm));
           const float inv = 1.f / (a0 * __uint_as_float(l0[0]) + a1 * __uint_as_float(l1[0]));
           a0 *= inv; a1 *= inv;
           __half* ob = p.out + (long long)t.b * p.C8 * T * 8 + ((long long)t.w * n + r) * 8;

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(Cin1Cfg<KS, STRIDE, NT, BD>::kThreads, 1) conv
   uint64_t* a_full = bars;               // [2], 128 producer arrivals
   uint64_t* a_empty = bars + 2;          // [2], tcgen05.commit
   uint64_t* acc_full = bars + 4;         // [2]
-  uint64_t* acc_empty = bars + 6;        // [2], 128 epilogue arrivals
+  uint64_t* acc_empty = bars + 6;        // [2], one arrival per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_stats = reinterpret_cast<float*>(bars + 32);          // [4][2*NT]
 
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(Cin1Cfg<KS, STRIDE, NT, BD>::kThreads, 1) conv
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1);
-      tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128 * Cfg::kEG);
+      tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4 * Cfg::kEG);
     }
     tc::fence_barrier_init();
   }

@@ -39,7 +39,7 @@ __device__ __forceinline__ ConvTile conv_tile(const ConvEpiP& p, long long t) {
 
 // Run by EG groups of four epilogue warps (each group: four warps whose ids cover the residues mod 4 -- warp w reads TMEM lanes
 // 32*(w & 3) ..); group `eg` handles the planes sub = eg, eg + EG, ... of every tile.  acc_full[b] is completed by tcgen05.commit
-// of the MMA warp, acc_empty[b] expects 128 * EG arrivals.  s_stats: shared memory, 4 * EG warp-private rows of 2*NT floats,
+// of the MMA warp, acc_empty[b] expects 4 * EG arrivals (one per epilogue warp).  s_stats: shared memory, 4 * EG warp-private rows of 2*NT floats,
 // zero-initialised by the caller.  (One group suffices while the MMAs of a tile take longer than its epilogue -- conv_tc.cu; the
 // store-bound stems of conv_cin1_tc.cu run four groups.)
 template <int NT, int BD, int NB, int EG = 1>
@@ -117,9 +117,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_b
         }
       }
     }
-    // this thread's TMEM reads of the set are complete: hand it back to the MMA warp
+    // this thread's TMEM reads of the set are complete: hand it back to the MMA warp (one arrival per warp)
     tc::fence_before_sync();
-    tc::mbar_arrive(&acc_empty[buf]);
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
   }
   if (p.sp.buf && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, slot, lane, 0, NT);
 }
@@ -129,7 +130,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_b
 // keeps their InstanceNorm sums in REGISTERS: the cross-lane transpose-reduce (64 of the ~100 instructions a (row, chunk) cost
 // in conv_epilogue -- ncu: FSEL + FADD + SHFL = 40 % of the stem's instruction stream, issue-bound at 74 %) runs once per batch
 // item instead of once per (tile, plane, chunk).  The order of the additions is fixed (tile order), so the sums stay
-// deterministic.  acc_empty expects 128 * EG arrivals; s_stats holds 4 * EG zero-initialised rows of 2 * NT floats.
+// deterministic.  acc_empty expects 4 * EG arrivals (one per warp); s_stats holds 4 * EG zero-initialised rows of 2 * NT floats.
 template <int NT, int BD, int NB, int EG>
 __device__ __forceinline__ void conv_epilogue_cg(const ConvEpiP& p, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty,
                                                  float* s_stats, int warp, int lane, int eg) {
@@ -219,7 +220,8 @@ __device__ __forceinline__ void conv_epilogue_cg(const ConvEpiP& p, uint32_t tme
       }
     }
     tc::fence_before_sync();
-    tc::mbar_arrive(&acc_empty[buf]);
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
   }
   if (p.sp.buf && group >= 0) flush(group);
 }

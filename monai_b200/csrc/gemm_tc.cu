@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 32 * kGemmEpiWarps); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], kGemmEpiWarps); }
     tc::fence_barrier_init();
   }
   if (STATS)
@@ -305,9 +305,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(GemmTcParams p
           process(vb, rb0, rb1, c16 + 1);
         }
       }
-      // this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp
+      // this thread's TMEM reads of the buffer are complete: hand it back to the MMA warp (one arrival per warp: 512 per-thread
+      // arrivals per tile serialise on one shared-memory word)
       tc::fence_before_sync();
-      tc::mbar_arrive(&acc_empty[buf]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
     }
     if (STATS && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, q, lane, c_lo * 16, c_hi * 16);
   }
