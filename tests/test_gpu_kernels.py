@@ -1,4 +1,6 @@
 """GPU parity of the individual CUDA kernels (through the C ABI) against plain torch fp32 references."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -165,3 +167,41 @@ def test_errors_surface_as_python_exceptions():
         K.conv3x3x3_tc_pack_weight(torch.zeros(8, 8, 3, 3, 3, device=DEV))
     with pytest.raises(TypeError):
         K.instnorm_stats(torch.zeros(1, 1, 4, 4, 4, device=DEV, dtype=torch.float64))
+
+
+def test_tiled_resampler_is_bit_identical_to_the_gather_kernel(tmp_path):
+    """resample_affine_tiled_kernel stages the source box of an 8 x 8 x 32 output tile in shared memory and runs the gather kernel's
+    arithmetic on the copy: same bits.  The gather kernel is selected per process (B200_RESAMPLE_GATHER=1), hence the subprocess."""
+    import subprocess
+    import sys
+
+    script = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from monai_b200 import _kernels as K
+g = torch.Generator().manual_seed(9)
+src = torch.randn((2, 37, 45, 52), generator=g).cuda()
+cases = []
+th = 0.2
+rot = [[0.9, -0.15, 0.1, 3.0], [0.2, 1.05, -0.1, -2.0], [-0.1, 0.12, 0.95, 1.5]]
+for mat, out, pad in (([0.8, 0, 0, -0.1, 0, 0.8, 0, -0.1, 0, 0, 0.8, -0.1], (46, 56, 65), 1),
+                      ([0.8, 0, 0, -0.1, 0, 0.8, 0, -0.1, 0, 0, 0.8, -0.1], (46, 56, 65), 0),
+                      ([v for r in rot for v in r], (41, 50, 57), 1), ([v for r in rot for v in r], (41, 50, 57), 0),
+                      ([3.0, 0, 0, 0, 0, 3.0, 0, 0, 0, 0, 3.0, 0], (12, 15, 17), 0),          # strong down-sampling: source box too large to stage
+                      ([1, 0, 0, -5.5, 0, 1, 0, 40.25, 0, 0, 1, 60.0], (20, 24, 40), 0)):     # mostly outside the volume
+    for dt in (torch.float32, torch.float16):
+        y = K.resample_affine(src.to(dt), out, mat, 1, pad, False, out_dtype=torch.float32)
+        cases.append(y.cpu().numpy())
+np.savez(sys.argv[2], *cases)
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, env in (("tiled", {}), ("gather", {"B200_RESAMPLE_GATHER": "1"})):
+        path = str(tmp_path / f"{tag}.npz")
+        r = subprocess.run([sys.executable, "-c", script, root, path], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(path))
+    assert len(outs[0].files) == len(outs[1].files) == 12
+    for k in outs[0].files:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+        assert np.isfinite(outs[0][k]).all()
