@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(256) resample_affine_kernel(ResampleP p) {
   }
 }
 
-// Shared-memory tiled form of the trilinear / zeros (MODE 0) and border (MODE 3) paths.
+// Shared-memory tiled form of the trilinear / zeros (MODE 0) and border (MODE 3) paths -- an EXPERIMENT that did not pay off (see
+// the dispatcher); kept opt-in because it is bit-identical and documents the result.
 //
 // The gather kernel above issues eight scalar global loads per output voxel (130 instructions per voxel, 0.10 of the HBM
 // bandwidth on the C4 shapes).  Here a block owns an 8 (d) x 8 (h) x 32 (w) OUTPUT tile: the source coordinates of a tile are an
@@ -211,9 +212,13 @@ __global__ void __launch_bounds__(256) resample_affine_tiled_kernel(ResampleP p)
     const TI* s = src + ch * in_cs;
     if (staged) {
       if (ch > 0) __syncthreads();          // every thread has finished reading the previous channel's box
-      for (int e = threadIdx.x; e < (int)nbox; e += 256) {
-        const int c = e % nc, r = e / nc, b = r % nb, a = r / nb;
-        s_box[e] = io<TI>::ld(s + ((long long)(la + a) * p.Hi + (lb + b)) * p.Wi + (lc + c));
+      // a warp copies whole source rows (one division per row, lanes along W: coalesced); a per-element index decomposition cost more
+      // instructions than the interpolation itself
+      for (int r = threadIdx.x >> 5; r < na * nb; r += 8) {
+        const int a = r / nb, b = r - a * nb;
+        const TI* row = s + ((long long)(la + a) * p.Hi + (lb + b)) * p.Wi + lc;
+        float* drow = s_box + r * nc;
+        for (int c = threadIdx.x & 31; c < nc; c += 32) drow[c] = io<TI>::ld(row + c);
       }
       __syncthreads();
     }
@@ -424,9 +429,12 @@ extern "C" int b200_resample_affine(const void* src, int src_dtype, int C, int D
   p.interp = interp; p.pad = pad; p.align = align_corners;
   dim3 block(32, 8), grid(ceil_div(Wo, 32 * kRsVox), ceil_div(Ho, 8), Do);
   cudaStream_t st = (cudaStream_t)stream;
-  // trilinear with zeros / border padding: the shared-memory tiled kernel (B200_RESAMPLE_GATHER=1 keeps the gather kernel: A/B runs)
-  static const bool gather_only = std::getenv("B200_RESAMPLE_GATHER") != nullptr;
-  const bool tiled = !gather_only && interp == 1 && pad != 2 && ceil_div(Do, kRtD) <= 65535 && ceil_div(Ho, kRtH) <= 65535;
+  // B200_RESAMPLE_TILED=1 selects the shared-memory tiled kernel for trilinear + zeros / border.  It is OFF by default: measured on
+  // the C4 shapes it is SLOWER than the gather kernel (Spacing 256^3 -> 320^3: 0.356 vs 0.246 ms; rotated 320^3: 0.66 vs 0.43 ms) --
+  // the gather's eight loads per voxel hit L1 / L2 (neighbouring voxels share corners), while the tile pays a block-wide copy, two
+  // barriers per channel and 48 KB of shared memory per block (4 blocks per SM) for the same DRAM traffic.
+  static const bool want_tiled = std::getenv("B200_RESAMPLE_TILED") != nullptr;
+  const bool tiled = want_tiled && interp == 1 && pad != 2 && ceil_div(Do, kRtD) <= 65535 && ceil_div(Ho, kRtH) <= 65535;
   dim3 tgrid(ceil_div(Wo, kRtW), ceil_div(Ho, kRtH), ceil_div(Do, kRtD));
 #define LR(TI, TO) do { if (interp == 0) resample_affine_kernel<TI, TO, 2><<<grid, block, 0, st>>>(p); \
                        else if (pad == 2) resample_affine_kernel<TI, TO, 1><<<grid, block, 0, st>>>(p); \

@@ -171,7 +171,8 @@ def test_errors_surface_as_python_exceptions():
 
 def test_tiled_resampler_is_bit_identical_to_the_gather_kernel(tmp_path):
     """resample_affine_tiled_kernel stages the source box of an 8 x 8 x 32 output tile in shared memory and runs the gather kernel's
-    arithmetic on the copy: same bits.  The gather kernel is selected per process (B200_RESAMPLE_GATHER=1), hence the subprocess."""
+    arithmetic on the copy: same bits.  The tiled kernel is opt-in per process (B200_RESAMPLE_TILED=1: it measured slower), hence the
+    subprocesses."""
     import subprocess
     import sys
 
@@ -196,7 +197,7 @@ np.savez(sys.argv[2], *cases)
 """
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for tag, env in (("tiled", {}), ("gather", {"B200_RESAMPLE_GATHER": "1"})):
+    for tag, env in (("tiled", {"B200_RESAMPLE_TILED": "1"}), ("gather", {})):
         path = str(tmp_path / f"{tag}.npz")
         r = subprocess.run([sys.executable, "-c", script, root, path], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
