@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-echo "=== resample tests"; timeout -k 5 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_transforms.py -q -m gpu --timeout 300 --timeout-method=thread 2>&1 | tail -3
-echo "=== resample times (tiled)"; timeout -k 5 300 python profiles/run_resample.py 2>&1 | tail -2
-echo "=== resample times (gather)"; B200_RESAMPLE_GATHER=1 timeout -k 5 300 python profiles/run_resample.py 2>&1 | tail -2
+echo "=== gemm conv3 shape, batch 25"; timeout -k 5 300 python profiles/run_gemm_tc.py 25 10; timeout -k 5 300 python profiles/run_gemm_tc.py 25 11; timeout -k 5 300 python profiles/run_gemm_tc.py 25 0
+echo "=== ncu of the stats gemm"; timeout -k 5 300 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" --launch-skip 5 --launch-count 1 -f -o gpurun_out/r02_gemm_conv3_stats python profiles/run_gemm_tc.py 8 11 > gpurun_out/r02_gemm_conv3_ncu.log 2>&1; tail -1 gpurun_out/r02_gemm_conv3_ncu.log

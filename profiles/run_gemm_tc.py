@@ -22,6 +22,7 @@ SHAPES = [  # name, rows per batch item, K, N, act, residual
     ("stage4.fc1 384->1536 gelu", 6**3, 384, 1536, L.ACT_GELU, False),
     ("decoder1.up 48->8x48", 48**3, 48, 8 * 48, 0, False),
     ("decoder1.conv3 1x1 96->48 @96^3", 96**3, 96, 48, 0, False),
+    ("decoder1.conv3 1x1 96->48 @96^3 + InstanceNorm statistics (as the network runs it)", 96**3, 96, 48, 0, False, True),
 ]
 
 
@@ -32,7 +33,8 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm = peaks.get("hbm_gbs", 6650.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for idx, (name, S, Kd, N, act, res) in enumerate(SHAPES):
+    for idx, (name, S, Kd, N, act, res, *rest) in enumerate(SHAPES):
+        stats = bool(rest and rest[0])
         if only >= 0 and idx != only:
             continue
         x = K.NC8(batch, Kd, (1, 1, S), dev)
@@ -44,14 +46,14 @@ def main():
         if r is not None:
             r.buf.normal_()
         for _ in range(3):
-            K.gemm_tc(x, w, Kd, N, bias=bias, out=out, res=r, act=act)
+            K.gemm_tc(x, w, Kd, N, bias=None if stats else bias, out=out, res=r, act=act, want_stats=stats)
         torch.cuda.synchronize()
         ms = []
         for _ in range(8):
             flush.fill_(0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            K.gemm_tc(x, w, Kd, N, bias=bias, out=out, res=r, act=act)
+            K.gemm_tc(x, w, Kd, N, bias=None if stats else bias, out=out, res=r, act=act, want_stats=stats)
             e1.record()
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
