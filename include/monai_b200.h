@@ -174,6 +174,15 @@ typedef struct b200_conv_tc_desc {
   float in_eps;
   int in_act;               /* 0 none, 1 leaky-relu (in_slope), 3 relu */
   float in_slope;
+  /* Folded 1x1x1 residual convolution (round 2; res_w == NULL = off; exclusive with in_stats; Cout <= 128): UnetResBlock.conv3
+   * (dynunet_block.py:75-87, 104-108) reads the same input as conv1, so res_y = conv1x1x1(x, W3) is produced by the same launch
+   * (one extra MMA per output plane and K slice on the centre view of the staged halo tile).  res_w = b200_gemm_tc_pack_weight image
+   * of W3 [Cout, Cin]; res_y = NC8 destination (channel slice res_coff of res_ctot); res_stats (optional) = its {sum, sumsq}
+   * per (n, cout), deterministic; the workspace of b200_conv3x3x3_tc_workspace_bytes(desc) covers both outputs. */
+  const void* res_w;
+  void* res_y;
+  int res_ctot, res_coff;
+  float* res_stats;
 } b200_conv_tc_desc;
 
 /* 3x3x3, stride 1, zero padding 1 implicit-GEMM convolution on tcgen05 tensor cores: halo tile staged once

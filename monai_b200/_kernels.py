@@ -447,16 +447,25 @@ def conv3x3x3_tc_pack_weight(weight: torch.Tensor) -> torch.Tensor:
 def conv3x3x3_tc(
     x: NC8, packed_w: torch.Tensor, Cin: int, Cout: int, in_coff: int = 0, bias: torch.Tensor | None = None,
     out: NC8 | None = None, out_coff: int = 0, want_stats: bool = False,
-    in_norm: tuple[torch.Tensor, float, int, float] | None = None,
-) -> tuple[NC8, torch.Tensor | None]:
+    in_norm: tuple[torch.Tensor, float, int, float] | None = None, res_w: torch.Tensor | None = None,
+):
     """3x3x3 / stride 1 / pad 1 convolution.  `in_norm` = (stats, eps, act, slope): x is the RAW output of the previous
-    convolution and InstanceNorm + activation are applied on the operand load (no norm_act pass in between)."""
+    convolution and InstanceNorm + activation are applied on the operand load (no norm_act pass in between).
+    `res_w` = gemm_tc_pack_weight image of a 1x1x1 convolution [Cout, Cin] of the SAME input: it is computed by the same launch
+    and the call returns (out, stats, res_out, res_stats) instead of (out, stats)."""
     if out is None:
         out = NC8(x.N, Cout, x.sp, x.buf.device)
     dev = x.buf.device
     stats = torch.empty((x.N * Cout, 2), device=dev, dtype=torch.float32) if want_stats else None
     b32 = _f32c(bias)
-    d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff, None, 0.0, 0, 0.0)
+    d = L.ConvTcDesc(x.N, Cin, Cout, x.sp[0], x.sp[1], x.sp[2], x.C, in_coff, out.C, out_coff, None, 0.0, 0, 0.0, None, None, 0, 0, None)
+    res_out = res_stats = None
+    if res_w is not None:
+        if in_norm is not None or Cout > 128:
+            raise ValueError("conv3x3x3_tc: the folded 1x1x1 convolution needs Cout <= 128 and no in_norm")
+        res_out = NC8(x.N, Cout, x.sp, dev)
+        res_stats = torch.empty((x.N * Cout, 2), device=dev, dtype=torch.float32) if want_stats else None
+        d.res_w, d.res_y, d.res_ctot, d.res_coff, d.res_stats = L.ptr(res_w), L.ptr(res_out.buf), res_out.C, 0, L.ptr(res_stats)
     if in_norm is not None:
         st, eps, act, slope = in_norm
         if st.dtype != torch.float32 or st.numel() != x.N * Cin * 2 or not st.is_contiguous() or st.device != dev:
@@ -464,7 +473,10 @@ def conv3x3x3_tc(
         d.in_stats, d.in_eps, d.in_act, d.in_slope = L.ptr(st), float(eps), int(act), float(slope)
     ws = _ws(L.load().b200_conv3x3x3_tc_workspace_bytes(C.byref(d)), dev) if want_stats else None
     _call("conv3x3x3_tc", C.byref(d), L.ptr(x.buf), L.ptr(packed_w), L.ptr(b32), L.ptr(out.buf), L.ptr(stats), L.ptr(ws), L.stream_ptr(dev),
-          flops=2.0 * x.N * x.S * Cin * Cout * 27, nbytes=float(x.N * x.S * (Cin + Cout) * 2) + _nb(packed_w))
+          flops=2.0 * x.N * x.S * Cin * Cout * (28 if res_w is not None else 27),
+          nbytes=float(x.N * x.S * (Cin + Cout * (2 if res_w is not None else 1)) * 2) + _nb(packed_w))
+    if res_w is not None:
+        return out, stats, res_out, res_stats
     return out, stats
 
 
@@ -551,6 +563,7 @@ def gemm_tc(
     return out, stats
 
 
+RES_FOLD = os.environ.get("B200_RES_UNFOLDED", "") == ""   # B200_RES_UNFOLDED=1: the 1x1x1 residual convolution as its own gemm_tc launch
 NORM_ON_LOAD = os.environ.get("B200_NORM_UNFUSED", "") == ""   # B200_NORM_UNFUSED=1: norm_act_nc8 pass between conv1 and conv2 (A/B measurements)
 MLP_FUSED = os.environ.get("B200_MLP_UNFUSED", "") == ""   # B200_MLP_UNFUSED=1: layernorm_nc8 + two gemm_tc (A/B measurements)
 

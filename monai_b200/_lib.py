@@ -51,6 +51,7 @@ class ConvTcDesc(C.Structure):
         ("N", i32), ("Cin", i32), ("Cout", i32), ("D", i32), ("H", i32), ("W", i32),
         ("in_ctot", i32), ("in_coff", i32), ("out_ctot", i32), ("out_coff", i32),
         ("in_stats", vp), ("in_eps", f32), ("in_act", i32), ("in_slope", f32),
+        ("res_w", vp), ("res_y", vp), ("res_ctot", i32), ("res_coff", i32), ("res_stats", vp),
     ]
 
 

@@ -125,6 +125,108 @@ __device__ __forceinline__ void conv_epilogue(const ConvEpiP& p, uint32_t tmem_b
   if (p.sp.buf && group >= 0) stats_flush(p.sp, ws, 2 * NT, group, slot, lane, 0, NT);
 }
 
+// Two-output variant for conv3x3x3_tc with the folded 1x1x1 residual branch (conv_tc.cu, RES): the accumulator set holds the BD
+// planes of the 3x3x3 result at columns [0, BD*NT) and the BD planes of the 1x1x1 result at [BD*NT, 2*BD*NT).  `p` describes the main
+// output, `r` the residual output (its own tensor and statistics partials; no bias).
+// At NT = 48, BD = 4 only ONE accumulator set fits in TMEM, so the epilogue is on the critical path; two measures shorten it:
+//   * EG = 2 groups of four warps split the planes (group eg drains planes eg, eg + 2, ...);
+//   * the MAIN block is drained first and handed back through acc_empty -- the next tile's 3x3x3 MMAs only write the main block
+//     until the residual MMAs at the end of its first K slice -- then the residual block is drained and handed back through
+//     res_empty, which the MMA warp waits on right before those residual MMAs.
+// s_stats: 2 x 4 * EG warp-private rows of 2*NT floats (main rows first).  Both barriers expect 4 * EG arrivals (one per warp).
+template <int NT, int BD, int NB, int EG>
+__device__ __forceinline__ void conv_epilogue_res(const ConvEpiP& p, const ConvEpiP& r, uint32_t tmem_base, uint64_t* acc_full,
+                                                  uint64_t* acc_empty, uint64_t* res_empty, float* s_stats, int warp, int lane, int eg) {
+  constexpr int kSubs = (BD + EG - 1) / EG;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int slot = eg * 4 + q;
+  const long long S = (long long)p.D * p.H * p.W;
+  const long long sp_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d;
+  float* ws_m = s_stats + slot * (2 * NT);
+  float* ws_r = s_stats + (4 * EG + slot) * (2 * NT);
+  long long group = -1;
+  int it = 0;
+  for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    const ConvTile c = conv_tile<BD>(p, t);
+    const long long g = t / sp_tiles;
+    if (g != group) {
+      if (group >= 0) {
+        if (p.sp.buf) stats_flush(p.sp, ws_m, 2 * NT, group, slot, lane, 0, NT);
+        if (r.sp.buf) stats_flush(r.sp, ws_r, 2 * NT, group, slot, lane, 0, NT);
+      }
+      group = g;
+    }
+    const int buf = it % NB;
+    const uint32_t aph = (uint32_t)((it / NB) & 1);
+    const int h = c.h0 + (row >> 3), w = c.w0 + (row & 7);
+    const bool hw_ok = h < p.H && w < p.W;
+    const int co0 = c.nt * NT;
+    tc::mbar_wait(&acc_full[buf], aph);
+    tc::fence_after_sync();
+    const uint32_t tq0 = tmem_base + buf * (2 * BD * NT) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const ConvEpiP& o = which ? r : p;
+      float* ws = which ? ws_r : ws_m;
+      const uint32_t tq = tq0 + which * (BD * NT);
+      __half* ybase = o.y + (((long long)c.n * (o.out_ctot / 8) + (o.out_coff + co0) / 8) * S) * 8;
+      uint32_t vn[8];
+      tc::tmem_ld8(tq + eg * NT, vn);
+#pragma unroll 1
+      for (int cc = 0; cc < NT / 8; ++cc) {
+        float bsum[8], bsq[8], bias8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = o.bias ? o.bias[co0 + cc * 8 + j] : 0.f; }
+#pragma unroll
+        for (int si = 0; si < kSubs; ++si) {
+          const int sub = eg + si * EG;
+          uint32_t v[8];
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = vn[j];
+          {
+            const int nsub = si + 1 < kSubs ? sub + EG : eg, ncc = si + 1 < kSubs ? cc : cc + 1;
+            if (ncc < NT / 8 && nsub < BD) tc::tmem_ld8(tq + nsub * NT + ncc * 8, vn);
+          }
+          const int dz = c.d0 + sub;
+          const bool ok = hw_ok && sub < BD && dz < p.D;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[j] = __uint_as_float(v[j]) + bias8[j];
+            if (ok) { bsum[j] += f[j]; bsq[j] = fmaf(f[j], f[j], bsq[j]); }
+          }
+          if (ok) {
+            uint4 hv;
+            __half2* hp = reinterpret_cast<__half2*>(&hv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hp[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>(ybase + ((long long)cc * S + ((long long)dz * p.H + h) * p.W + w) * 8) = hv;
+          }
+        }
+        if (o.sp.buf) {
+          float a1, b1;
+          transpose_reduce8(bsum, bsq, lane, a1, b1);
+          if ((lane & 3) == 0) {
+            const int col = cc * 8 + transpose_reduce8_col(lane);
+            ws[2 * col] += a1;
+            ws[2 * col + 1] += b1;
+          }
+        }
+      }
+      // this block of the set is drained: hand it back (one arrival per warp)
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(which ? &res_empty[buf] : &acc_empty[buf]);
+    }
+  }
+  if (group >= 0) {
+    if (p.sp.buf) stats_flush(p.sp, ws_m, 2 * NT, group, slot, lane, 0, NT);
+    if (r.sp.buf) stats_flush(r.sp, ws_r, 2 * NT, group, slot, lane, 0, NT);
+  }
+}
+
 // Channel-grouped variant for the store-bound stems (conv_cin1_tc.cu).  EG groups of four epilogue warps; group `eg` owns the
 // 8-channel chunks cc = eg, eg + EG, ... of EVERY plane of every tile, so a thread meets the same channels tile after tile and
 // keeps their InstanceNorm sums in REGISTERS: the cross-lane transpose-reduce (64 of the ~100 instructions a (row, chunk) cost

@@ -117,7 +117,7 @@ __global__ void conv_tc_pack_weight_kernel(const float* __restrict__ w, __half* 
 // ----------------------------------------------------------------------------------------------------------
 constexpr int kHH = kTH + 2, kHW = kTW + 2;      // halo patch (kTH x kTW output patch: conv_epi.cuh)
 
-template <int NT, int BD>
+template <int NT, int BD, bool RES = false>
 struct ConvTcCfg {
   static constexpr int kPlanes = BD + 2;
   static constexpr int kChunkBytes = kPlanes * kHH * kHW * 16;   // one 8-channel chunk of the halo tile
@@ -128,11 +128,18 @@ struct ConvTcCfg {
   static constexpr int kSB = (45056 / kBTapBytes) > 9 ? 9 : ((45056 / kBTapBytes) < 3 ? 3 : (45056 / kBTapBytes));
   static constexpr int kSA = 4;                                  // halo tiles in flight (one CTA per SM owns the whole shared memory)
   static constexpr int kKdGroup = (3 * NT <= 256) ? 3 : ((2 * NT <= 256) ? 2 : 1);   // kd taps fused into one MMA (UMMA N <= 256)
-  static constexpr int kAccBufs = (2 * BD * NT <= 512) ? 2 : 1;  // accumulator sets: 2 lets the epilogue of tile i overlap the MMAs of tile i+1
-  static constexpr int kAccCols = kAccBufs * BD * NT;
+  // RES: the 1x1x1 residual convolution of UnetResBlock is folded in (see the kernel): a second block of BD planes x NT columns per set
+  static constexpr int kAccSet = (RES ? 2 : 1) * BD * NT;        // TMEM columns of one accumulator set
+  static constexpr int kAccBufs = (2 * kAccSet <= 512) ? 2 : 1;  // accumulator sets: 2 lets the epilogue of tile i overlap the MMAs of tile i+1
+  static constexpr int kAccCols = kAccBufs * kAccSet;
   static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + 384 /*barriers*/ + 4 * 2 * NT * 4 /*warp-private stats rows*/ + 128 /*align slack*/;
-  static_assert(BD * NT <= 512, "accumulators exceed TMEM");
+  static constexpr int kRBytes = NT * 32;                        // RES: the 1x1x1 weights of one K slice (NT x 16 fp16), 2 stages
+  static constexpr int kSR = 2;
+  static constexpr int kResEG = BD >= 2 ? 2 : 1;                 // RES: epilogue warp groups (they split the planes of a tile)
+  static constexpr int kThreads = RES ? 64 + 128 * kResEG : 192; // (+ 256 transform threads with NORM, see the kernel)
+  static constexpr int kSmemBytes = kSA * kABytes + kSB * kBTapBytes + (RES ? kSR * kRBytes : 0) + 384 /*barriers*/ +
+                                    (RES ? 8 * kResEG : 4) * 2 * NT * 4 /*warp-private stats rows*/ + 128 /*align slack*/;
+  static_assert(kAccSet <= 512, "accumulators exceed TMEM");
   static_assert(NT % 16 == 0 && NT >= 16 && NT <= 256, "invalid UMMA N");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -142,6 +149,8 @@ struct ConvTcParams {
   const __half* w;      // packed
   ConvEpiP e;           // output stage (conv_epi.cuh)
   const float* in_stats;   // NORM: {sum, sumsq} per (n, input channel) of the raw input (see b200_conv_tc_desc.in_stats)
+  ConvEpiP r;              // RES: output stage of the folded 1x1x1 residual convolution
+  const __half* res_w;     // RES: packed 1x1x1 weights (gemm_tc image: [nt][k16][khalf][NT/8][8][8])
 };
 
 // Persistent, warp-specialised (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
@@ -154,15 +163,23 @@ struct ConvTcParams {
 // norm_act_nc8_kernel, so the MMAs consume bit-identical fp16 operands -- between the TMA completion (full_a) and the MMAs
 // (ready_a).  Voxels outside the volume keep the TMA's zero fill: the convolution pads the NORMALISED tensor with zeros.
 // This removes one read and one write of the activation tensor per residual block (norm_act_nc8: 102 ms per C3 step).
-template <int NT, int BD, bool NORM>
-__global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
-  using Cfg = ConvTcCfg<NT, BD>;
+//
+// RES: the 1x1x1 convolution of the residual branch (UnetResBlock.conv3, dynunet_block.py:75-87, 104-108) reads the SAME input as
+// conv1, so it is folded into this kernel: per K slice one extra MMA per output plane multiplies the centre view of the staged
+// halo tile (kh = kw = 1 of input plane o + 1) with the 1x1x1 weights into a second accumulator block, and the epilogue stores
+// both tensors with their statistics (conv_epilogue_res).  This deletes a launch that re-read the 2 x C input tensor
+// (decoder1 of SwinUNETR: 6.4 GB per 25 windows, 2.3 ms at 2.8 TB/s); the price is a single accumulator set at NT = 48, BD = 4.
+template <int NT, int BD, bool NORM, bool RES>
+__global__ void __launch_bounds__(NORM ? 448 : ConvTcCfg<NT, BD, RES>::kThreads, 1) conv3x3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, ConvTcParams p) {
+  using Cfg = ConvTcCfg<NT, BD, RES>;
+  static_assert(!(NORM && RES), "the residual fold is used by conv1, the operand normalisation by conv2");
   constexpr int kSA = Cfg::kSA, kSB = Cfg::kSB, kNB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = tc::align_smem128(smem_raw);   // keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSA * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSB * Cfg::kBTapBytes);
+  uint8_t* smem_r = smem_b + kSB * Cfg::kBTapBytes;                   // RES: [kSR] 1x1x1 weight slices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_r + (RES ? Cfg::kSR * Cfg::kRBytes : 0));
   uint64_t* full_a = bars;              // [kSA]
   uint64_t* empty_a = bars + kSA;       // [kSA]
   uint64_t* full_b = bars + 2 * kSA;    // [kSB]
@@ -170,8 +187,11 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
   uint64_t* acc_full = empty_b + kSB;   // [2]
   uint64_t* acc_empty = acc_full + 2;   // [2]
   uint64_t* ready_a = acc_empty + 2;    // [kSA] NORM: 8 arrivals (one per transform warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_a + kSA);
-  static_assert(3 * kSA + 2 * kSB + 4 + 1 <= 48, "barrier block");
+  uint64_t* full_r = ready_a + kSA;     // [2] RES
+  uint64_t* empty_r = full_r + 2;       // [2] RES
+  uint64_t* res_empty = empty_r + 2;    // [2] RES: the residual accumulator block has been drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
+  static_assert(3 * kSA + 2 * kSB + 4 + 6 + 1 <= 48, "barrier block");
   float* s_stats = reinterpret_cast<float*>(bars + 48);  // [4][2*NT]
 
   const b200_conv_tc_desc& d = p.d;
@@ -181,10 +201,13 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSA; ++i) { tc::mbar_init(&full_a[i], 1); tc::mbar_init(&empty_a[i], 1); tc::mbar_init(&ready_a[i], 8); }
     for (int i = 0; i < kSB; ++i) { tc::mbar_init(&full_b[i], 1); tc::mbar_init(&empty_b[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], RES ? 4 * Cfg::kResEG : 4);
+      tc::mbar_init(&full_r[i], 1); tc::mbar_init(&empty_r[i], 1); tc::mbar_init(&res_empty[i], 4 * Cfg::kResEG);
+    }
     tc::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 4 * 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < (RES ? 8 * Cfg::kResEG : 4) * 2 * NT; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc::fence_before_sync();
   __syncthreads();
@@ -195,7 +218,7 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
     // ===================== TMA producer =====================
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmap);
-      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      int sa = 0, sb = 0, sr = 0; uint32_t pa = 0, pb = 0, pr = 0;
       for (long long t = blockIdx.x; t < p.e.total_tiles; t += gridDim.x) {
         const ConvTile c = conv_tile<BD>(p.e, t);
         const __half* wbase = p.w + (long long)c.nt * num_kc * 9 * (Cfg::kBTapBytes / 2);
@@ -205,6 +228,12 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
           tc::tma_load_5d(smem_a + sa * Cfg::kABytes, &tmap, &full_a[sa], (c.w0 - 1) * 8, c.h0 - 1, c.d0 - 1,
                           (d.in_coff + kc * 16) / 8, c.n);
           if (++sa == kSA) { sa = 0; pa ^= 1; }
+          if constexpr (RES) {
+            tc::mbar_wait(&empty_r[sr], pr ^ 1);
+            tc::mbar_arrive_expect_tx(&full_r[sr], Cfg::kRBytes);
+            tc::bulk_load(smem_r + sr * Cfg::kRBytes, p.res_w + ((long long)c.nt * num_kc + kc) * (Cfg::kRBytes / 2), Cfg::kRBytes, &full_r[sr]);
+            if (++sr == Cfg::kSR) { sr = 0; pr ^= 1; }
+          }
           for (int t9 = 0; t9 < 9; ++t9) {
             tc::mbar_wait(&empty_b[sb], pb ^ 1);
             tc::mbar_arrive_expect_tx(&full_b[sb], Cfg::kBTapBytes);
@@ -224,8 +253,23 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
       constexpr int G = Cfg::kKdGroup;
       const bool leader = tc::elect_one();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      int sa = 0, sb = 0, sr = 0; uint32_t pa = 0, pb = 0, pr = 0;
       uint32_t a_base = 0, tacc = 0;
+      // RES: D_res[plane o] (+)= centre view of input plane o + 1 x W3 slice; FIRST (first K slice) initialises the accumulators
+      auto residual = [&](auto first_c) {
+        constexpr bool FIRST = decltype(first_c)::value;
+        tc::mbar_wait(&full_r[sr], pr);
+        tc::fence_after_sync();
+        const uint64_t bdesc = tc::make_desc_kmajor_noswz(tc::smem_u32(smem_r + sr * Cfg::kRBytes), NT * 16, 128);
+#pragma unroll
+        for (int o = 0; o < BD; ++o) {
+          const uint64_t adesc = tc::make_desc_kmajor_noswz(a_base + (((o + 1) * kHH + 1) * kHW + 1) * 16, Cfg::kChunkBytes, kHW * 16);
+          if (leader) tc::mma_f16_ss(tacc + BD * NT + o * NT, adesc, bdesc, tc::make_idesc_f16(128, NT), FIRST ? 0u : 1u);
+        }
+        if (leader) tc::mma_commit(&empty_r[sr]);
+        __syncwarp();
+        if (++sr == Cfg::kSR) { sr = 0; pr ^= 1; }
+      };
       // One (kh, kw) tap of one K-slice: every input plane ip of the halo tile feeds output planes ip - kd.  FIRST is the
       // very first tap of the tile: it initialises the accumulators, so it issues one MMA per (plane, kd) with a
       // static accumulate flag; every other tap fuses the kd range of a plane into one MMA.  (Kept as two separately
@@ -268,7 +312,7 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
         const uint32_t aph = (uint32_t)((it / kNB) & 1);
         tc::mbar_wait(&acc_empty[buf], aph ^ 1);   // the epilogue has drained this accumulator set
         tc::fence_after_sync();
-        tacc = tmem_u + buf * (BD * NT);
+        tacc = tmem_u + buf * Cfg::kAccSet;
         for (int kc = 0; kc < num_kc; ++kc) {
           tc::mbar_wait(NORM ? &ready_a[sa] : &full_a[sa], pa);
           tc::fence_after_sync();
@@ -277,6 +321,15 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
           else tap(std::false_type{}, 0, 0);
 #pragma unroll
           for (int t9 = 1; t9 < 9; ++t9) tap(std::false_type{}, t9 / 3, t9 % 3);
+          if constexpr (RES) {
+            if (kc == 0) {
+              tc::mbar_wait(&res_empty[buf], aph ^ 1);   // the epilogue has drained the residual block of this set
+              tc::fence_after_sync();
+              residual(std::true_type{});
+            } else {
+              residual(std::false_type{});
+            }
+          }
           if (leader) tc::mma_commit(&empty_a[sa]);
           __syncwarp();
           if (++sa == kSA) { sa = 0; pa ^= 1; }
@@ -286,9 +339,10 @@ __global__ void __launch_bounds__(NORM ? 448 : 192, 1) conv3x3x3_tc_kernel(const
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5) =====================
-    conv_epilogue<NT, BD, kNB>(p.e, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
+  } else if (warp < (RES ? 2 + 4 * Cfg::kResEG : 6)) {
+    // ===================== epilogue (warps 2..5; RES: warps 2..9 in two groups) =====================
+    if constexpr (RES) conv_epilogue_res<NT, BD, kNB, Cfg::kResEG>(p.e, p.r, tmem_base, acc_full, acc_empty, res_empty, s_stats, warp, lane, (warp - 2) >> 2);
+    else conv_epilogue<NT, BD, kNB>(p.e, tmem_base, acc_full, acc_empty, s_stats, warp, lane);
   } else if constexpr (NORM) {
     // ===================== operand transform (warps 6..13): InstanceNorm + activation in place =====================
     // 256 threads: 128 per 8-channel chunk; four vectors are loaded before the first is converted (one warp per scheduler with
@@ -477,15 +531,17 @@ struct ConvTcGeom {
 // what a launch needs beyond the operands: mode 0 = run, mode 1 = only report the statistics workspace size
 struct ConvTcCall { const void* x; const void* w; const float* bias; void* y; float* stats; void* ws; cudaStream_t st; long long ws_bytes; int query; };
 
-template <int NT, int BD, bool NORM>
+template <int NT, int BD, bool NORM, bool RES = false>
 static int launch_conv_tc(const b200_conv_tc_desc& d, ConvTcCall& c) {
-  using Cfg = ConvTcCfg<NT, BD>;
+  using Cfg = ConvTcCfg<NT, BD, RES>;
   ConvTcParams p;
   p.d = d; p.w = (const __half*)c.w; p.in_stats = (const float*)d.in_stats;
   ConvTcGeom<NT, BD>::fill(d, p.e);
   const long long sp_tiles = (long long)p.e.tiles_w * p.e.tiles_h * p.e.tiles_d, groups = (long long)d.N * p.e.n_tiles;
   const int R = stats_rows(sp_tiles, p.e.total_tiles);
-  c.ws_bytes = stats_partial_bytes(groups, R, NT);
+  constexpr int kRows = RES ? 4 * Cfg::kResEG : 4;                 // partial rows a CTA writes per group
+  const long long one = stats_partial_bytes(groups, R, NT, kRows);
+  c.ws_bytes = RES ? 2 * one : one;     // RES: main partials, then the residual's
   if (c.query) return B200_OK;
   EncodeTiledFn enc = get_encode_tiled();
   B200_REQUIRE(enc != nullptr, "conv3x3x3_tc: cuTensorMapEncodeTiled entry point unavailable");
@@ -500,15 +556,34 @@ static int launch_conv_tc(const b200_conv_tc_desc& d, ConvTcCall& c) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "conv3x3x3_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   p.e.y = (__half*)c.y; p.e.bias = c.bias;
-  p.e.sp.buf = c.stats ? (float*)c.ws : nullptr; p.e.sp.R = R; p.e.sp.tiles_per_group = sp_tiles; p.e.sp.rows_per_cta = 4;
+  p.e.sp.buf = c.stats ? (float*)c.ws : nullptr; p.e.sp.R = R; p.e.sp.tiles_per_group = sp_tiles; p.e.sp.rows_per_cta = kRows;
+  p.r = p.e; p.res_w = nullptr;
+  if (RES) {
+    p.r.y = (__half*)d.res_y; p.r.bias = nullptr; p.r.out_ctot = d.res_ctot; p.r.out_coff = d.res_coff;
+    p.r.sp.buf = d.res_stats ? (float*)((char*)c.ws + one) : nullptr;
+    p.res_w = (const __half*)d.res_w;
+  }
   dim3 grid((unsigned)std::min<long long>(p.e.total_tiles, num_sms()));
-  auto kern = conv3x3x3_tc_kernel<NT, BD, NORM>;
+  auto kern = conv3x3x3_tc_kernel<NT, BD, NORM, RES>;
   // per-device attribute: set on every call (cheap), so a second GPU in the same process works
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  kern<<<grid, NORM ? 448 : 192, Cfg::kSmemBytes, c.st>>>(tmap, p);
+  kern<<<grid, NORM ? 448 : Cfg::kThreads, Cfg::kSmemBytes, c.st>>>(tmap, p);
   B200_LAUNCH_CHECK("conv3x3x3_tc_kernel");
-  if (c.stats) return launch_stats_finish((const float*)c.ws, groups, R * 4, NT, p.e.n_tiles, d.Cout, c.stats, c.st);
+  if (c.stats) {
+    const int rc = launch_stats_finish((const float*)c.ws, groups, R * kRows, NT, p.e.n_tiles, d.Cout, c.stats, c.st);
+    if (rc) return rc;
+  }
+  if (RES && d.res_stats) return launch_stats_finish((const float*)((const char*)c.ws + one), groups, R * kRows, NT, p.e.n_tiles, d.Cout, d.res_stats, c.st);
   return B200_OK;
+}
+
+template <int NT, int BD>
+static int launch_variant(const b200_conv_tc_desc& d, ConvTcCall& c) {
+  if (d.in_stats) return launch_conv_tc<NT, BD, true>(d, c);
+  if constexpr (NT <= 128) {
+    if (d.res_w) return launch_conv_tc<NT, BD, false, true>(d, c);
+  }
+  return launch_conv_tc<NT, BD, false>(d, c);
 }
 
 template <int NT>
@@ -516,12 +591,12 @@ static int dispatch_bd(const b200_conv_tc_desc& d, ConvTcCall& c) {
   // deeper CTA tiles amortise the halo and fuse more kd taps per MMA; two accumulator sets (2*BD*NT <= 512 TMEM columns)
   // let the epilogue overlap the next tile, which is worth more than depth for the wide-N layers
   if constexpr (2 * NT * 4 <= 512) {
-    if (d.D % 4 == 0 || d.D >= 16) return d.in_stats ? launch_conv_tc<NT, 4, true>(d, c) : launch_conv_tc<NT, 4, false>(d, c);
+    if (d.D % 4 == 0 || d.D >= 16) return launch_variant<NT, 4>(d, c);
   }
   if constexpr (NT * 2 <= 512) {
-    if (d.D >= 2) return d.in_stats ? launch_conv_tc<NT, 2, true>(d, c) : launch_conv_tc<NT, 2, false>(d, c);
+    if (d.D >= 2) return launch_variant<NT, 2>(d, c);
   }
-  return d.in_stats ? launch_conv_tc<NT, 1, true>(d, c) : launch_conv_tc<NT, 1, false>(d, c);
+  return launch_variant<NT, 1>(d, c);
 }
 
 static int conv_tc_dispatch(const b200_conv_tc_desc& d, ConvTcCall& c) {
@@ -532,6 +607,12 @@ static int conv_tc_dispatch(const b200_conv_tc_desc& d, ConvTcCall& c) {
   B200_REQUIRE(d.out_ctot % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + d.Cout <= d.out_ctot, "conv3x3x3_tc: bad output channel slice");
   B200_REQUIRE(!d.in_stats || d.in_act == 0 || d.in_act == 1 || d.in_act == 3, "conv3x3x3_tc: in_act must be none, leaky-relu or relu");
   B200_REQUIRE(!d.in_stats || d.in_act != 1 || (d.in_slope >= 0.f && d.in_slope <= 1.f), "conv3x3x3_tc: in_slope must lie in [0, 1] (got %g)", (double)d.in_slope);
+  if (d.res_w) {
+    B200_REQUIRE(!d.in_stats, "conv3x3x3_tc: the folded residual convolution and the operand normalisation are exclusive");
+    B200_REQUIRE(d.res_y && d.Cout <= 128, "conv3x3x3_tc: the folded residual convolution needs res_y and Cout <= 128 (got %d)", d.Cout);
+    B200_REQUIRE(d.res_ctot % 8 == 0 && d.res_coff % 8 == 0 && d.res_coff + d.Cout <= d.res_ctot, "conv3x3x3_tc: bad residual output channel slice");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(d.res_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.res_y) & 15) == 0, "conv3x3x3_tc: residual pointers must be 16-byte aligned");
+  }
   switch (conv_tc_nt(d.Cout)) {
     case 16: return dispatch_bd<16>(d, c);
     case 32: return dispatch_bd<32>(d, c);
@@ -555,7 +636,7 @@ extern "C" long long b200_conv3x3x3_tc_workspace_bytes(const b200_conv_tc_desc* 
 extern "C" int b200_conv3x3x3_tc(const b200_conv_tc_desc* desc, const void* x, const void* packed_w, const float* bias,
                                  void* y, float* stats, void* workspace, void* stream) {
   B200_REQUIRE(desc && x && packed_w && y, "conv3x3x3_tc: null pointer");
-  B200_REQUIRE(!stats || workspace, "conv3x3x3_tc: statistics need the workspace of b200_conv3x3x3_tc_workspace_bytes()");
+  B200_REQUIRE(!(stats || (desc && desc->res_stats)) || workspace, "conv3x3x3_tc: statistics need the workspace of b200_conv3x3x3_tc_workspace_bytes()");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(packed_w) & 15) == 0, "conv3x3x3_tc: pointers must be 16-byte aligned");
   ConvTcCall c{x, packed_w, bias, y, stats, workspace, (cudaStream_t)stream, 0, 0};

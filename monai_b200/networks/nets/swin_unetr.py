@@ -405,8 +405,14 @@ class SwinUNETR(GraphedForward, nn.Module):
         With `defer_tail` the final norm2 + residual + lrelu is NOT applied: the pieces (y2, stats2, res, res_coff,
         res_stats) are returned so that the consumer (the output head) applies them on its operand load."""
         cout = blk.conv1.conv.out_channels
+        folded = None
         if x_in_raw is not None:  # single input channel: direct stem kernels read the raw NCDHW window
             y1, st1 = K.conv_cin1_nc8(x_in_raw, blk.conv1.conv.weight, None, 3, 1, 1, want_stats=True)
+        elif K.RES_FOLD and hasattr(blk, "conv3") and cout <= 128 and cin_pad is None and blk.conv3.conv.bias is None:
+            # conv3 (1x1x1 residual branch) reads the same input as conv1: one launch produces both tensors and both statistics
+            y1, st1, y3f, st3f = K.conv3x3x3_tc(x, self._w3(blk.conv1.conv, key + ".c1", cin_pad), cin, cout, in_coff=in_coff, want_stats=True,
+                                                res_w=self._wlin(blk.conv3.conv.weight, key + ".c3", cin_pad))
+            folded = (y3f, st3f)
         else:
             y1, st1 = K.conv3x3x3_tc(x, self._w3(blk.conv1.conv, key + ".c1", cin_pad), cin, cout, in_coff=in_coff, want_stats=True)
         if K.NORM_ON_LOAD:
@@ -423,7 +429,9 @@ class SwinUNETR(GraphedForward, nn.Module):
                 K.norm_act_cin1res_nc8(y2, cout, st2, x_in_raw, K.instnorm_stats(x_in_raw), blk.conv3.conv.weight, act=L.ACT_LEAKY, slope=0.01,
                                        out=out, out_coff=out_coff)
                 return out
-            if x_in_raw is not None:
+            if folded is not None:
+                y3, st3 = folded
+            elif x_in_raw is not None:
                 y3, st3 = K.conv_cin1_nc8(x_in_raw, blk.conv3.conv.weight, None, 1, 1, 0, want_stats=True)
             else:
                 y3, st3 = K.gemm_tc(x, self._wlin(blk.conv3.conv.weight, key + ".c3", cin_pad), cin, cout, in_coff=in_coff, want_stats=True)

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-echo "=== gemm conv3 shape, batch 25"; timeout -k 5 300 python profiles/run_gemm_tc.py 25 10; timeout -k 5 300 python profiles/run_gemm_tc.py 25 11; timeout -k 5 300 python profiles/run_gemm_tc.py 25 0
-echo "=== ncu of the stats gemm"; timeout -k 5 300 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" --launch-skip 5 --launch-count 1 -f -o gpurun_out/r02_gemm_conv3_stats python profiles/run_gemm_tc.py 8 11 > gpurun_out/r02_gemm_conv3_ncu.log 2>&1; tail -1 gpurun_out/r02_gemm_conv3_ncu.log
+echo "=== conv tests"; timeout -k 5 600 python -m pytest tests/test_gpu_conv_tc.py -q -m gpu --timeout 120 --timeout-method=thread 2>&1 | tail -4
+echo "=== swin tests"; timeout -k 5 600 python -m pytest tests/test_gpu_swin.py -q -m gpu --timeout 200 --timeout-method=thread -k "swin_unetr or deterministic" 2>&1 | tail -3
+echo "=== bench folded"; timeout -k 5 500 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_p.json 2> gpurun_out/r02_bench_p.err; tail -3 gpurun_out/r02_bench_p.err; python -c "
+import json;d=json.loads(open('gpurun_out/r02_bench_p.json').read().strip().splitlines()[-1]);print(d['ms_per_step'],d['kernels'])"

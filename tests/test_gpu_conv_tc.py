@@ -97,3 +97,36 @@ def test_conv3x3x3_tc_instance_norm_on_the_operand_load(N, Cin, Cout, sp):
     nrm = F.leaky_relu(F.instance_norm(xf, eps=1e-5), 0.01)
     assert (K.unpack_nc8(xn, dtype=torch.float32).cpu() - nrm).abs().max().item() < 2e-2
     assert not (S == 0)
+
+
+@pytest.mark.parametrize(
+    "N,Cin,Cout,sp",
+    [
+        (2, 96, 48, (8, 32, 16)),     # decoder1 / decoder2 of SwinUNETR: single accumulator set (BD = 4, 2 x 192 columns)
+        (1, 32, 16, (5, 19, 11)),     # ragged edges, two accumulator sets
+        (3, 48, 96, (6, 12, 12)),     # BD = 2, wider N, batch > 1
+        (1, 192, 128, (3, 6, 6)),     # many K slices, BD = 1
+    ],
+)
+def test_conv3x3x3_tc_with_the_folded_residual_convolution(N, Cin, Cout, sp):
+    """UnetResBlock.conv1 and .conv3 (1x1x1, same input; monai/networks/blocks/dynunet_block.py:75-87, 104-108) from ONE launch: the
+    3x3x3 output and its statistics are bit-identical to the plain launch, the 1x1x1 output matches gemm_tc and torch."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn((N, Cin, *sp), generator=g).half()
+    w = (torch.randn((Cout, Cin, 3, 3, 3), generator=g) / (27 * Cin) ** 0.5).half()
+    w3 = (torch.randn((Cout, Cin), generator=g) / Cin**0.5).half()
+    pw = K.conv3x3x3_tc_pack_weight(w.float().to(DEV))
+    pw3 = K.gemm_tc_pack_weight(w3.float().to(DEV))
+    xr = K.pack_nc8(x.to(DEV))
+    y, st, y3, st3 = K.conv3x3x3_tc(xr, pw, Cin, Cout, want_stats=True, res_w=pw3)
+    y_plain, st_plain = K.conv3x3x3_tc(xr, pw, Cin, Cout, want_stats=True)
+    assert torch.equal(y.buf, y_plain.buf) and torch.equal(st, st_plain)
+    g3, gst3 = K.gemm_tc(xr, pw3, Cin, Cout, want_stats=True)
+    a, b = K.unpack_nc8(y3, dtype=torch.float32), K.unpack_nc8(g3, dtype=torch.float32)
+    assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max())
+    torch.testing.assert_close(st3, gst3, rtol=2e-3, atol=2e-3 * float(gst3.abs().max()))
+    ref3 = F.conv3d(x.float(), w3.float().reshape(Cout, Cin, 1, 1, 1))
+    assert float((a.cpu() - ref3).abs().max()) <= 2e-3 * float(ref3.abs().max()) + 1e-3
+    # deterministic
+    y_b, st_b, y3_b, st3_b = K.conv3x3x3_tc(xr, pw, Cin, Cout, want_stats=True, res_w=pw3)
+    assert torch.equal(y3.buf, y3_b.buf) and torch.equal(st3, st3_b)

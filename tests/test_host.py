@@ -67,7 +67,7 @@ def test_struct_layouts_match_header_sizes():
     # sanity: ctypes mirrors must be at least as large as the packed field sum and 8-byte aligned
     assert ctypes.sizeof(_lib.BlendDesc) % 8 == 0
     assert ctypes.sizeof(_lib.ConvDesc) == 21 * 4 + 4 + 16
-    assert ctypes.sizeof(_lib.ConvTcDesc) == 64   # 10 ints, the in_stats pointer (offset 40), eps, act, slope, tail padding
+    assert ctypes.sizeof(_lib.ConvTcDesc) == 96   # 10 ints, in_stats (offset 40), eps, act, slope, pad; res_w, res_y, res_ctot, res_coff, res_stats
 
 
 def test_argument_validation_matches_reference():
