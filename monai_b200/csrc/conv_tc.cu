@@ -590,8 +590,10 @@ template <int NT>
 static int dispatch_bd(const b200_conv_tc_desc& d, ConvTcCall& c) {
   // deeper CTA tiles amortise the halo and fuse more kd taps per MMA; two accumulator sets (2*BD*NT <= 512 TMEM columns)
   // let the epilogue overlap the next tile, which is worth more than depth for the wide-N layers
+  // A/B switch: B200_RES_BD2=1 runs the folded-residual variant with two planes per tile (two accumulator sets fit again)
+  static const bool res_bd2 = std::getenv("B200_RES_BD2") != nullptr;
   if constexpr (2 * NT * 4 <= 512) {
-    if (d.D % 4 == 0 || d.D >= 16) return launch_variant<NT, 4>(d, c);
+    if ((d.D % 4 == 0 || d.D >= 16) && !(res_bd2 && d.res_w)) return launch_variant<NT, 4>(d, c);
   }
   if constexpr (NT * 2 <= 512) {
     if (d.D >= 2) return launch_variant<NT, 2>(d, c);

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-echo "=== conv tests"; timeout -k 5 600 python -m pytest tests/test_gpu_conv_tc.py -q -m gpu --timeout 120 --timeout-method=thread 2>&1 | tail -4
-echo "=== swin tests"; timeout -k 5 600 python -m pytest tests/test_gpu_swin.py -q -m gpu --timeout 200 --timeout-method=thread -k "swin_unetr or deterministic" 2>&1 | tail -3
-echo "=== bench folded"; timeout -k 5 500 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-secondary > gpurun_out/r02_bench_p.json 2> gpurun_out/r02_bench_p.err; tail -3 gpurun_out/r02_bench_p.err; python -c "
-import json;d=json.loads(open('gpurun_out/r02_bench_p.json').read().strip().splitlines()[-1]);print(d['ms_per_step'],d['kernels'])"
+echo "=== breakdown folded BD=4"; timeout -k 5 300 python profiles/run_breakdown.py --batch 25 --reps 3 2>&1 | grep "conv3x3x3_tc\|total" | head -8
+echo "=== breakdown folded BD=2"; B200_RES_BD2=1 timeout -k 5 300 python profiles/run_breakdown.py --batch 25 --reps 3 2>&1 | grep "conv3x3x3_tc\|total" | head -8
+echo "=== breakdown unfolded"; B200_RES_UNFOLDED=1 timeout -k 5 300 python profiles/run_breakdown.py --batch 25 --reps 3 2>&1 | grep "conv3x3x3_tc\|total" | head -8
