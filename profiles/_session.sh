@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-echo "=== breakdown folded BD=4"; timeout -k 5 300 python profiles/run_breakdown.py --batch 25 --reps 3 2>&1 | grep "conv3x3x3_tc\|total" | head -8
-echo "=== breakdown folded BD=2"; B200_RES_BD2=1 timeout -k 5 300 python profiles/run_breakdown.py --batch 25 --reps 3 2>&1 | grep "conv3x3x3_tc\|total" | head -8
-echo "=== breakdown unfolded"; B200_RES_UNFOLDED=1 timeout -k 5 300 python profiles/run_breakdown.py --batch 25 --reps 3 2>&1 | grep "conv3x3x3_tc\|total" | head -8
+echo "=== full GPU test suite"; timeout -k 5 1500 python -m pytest tests -q -m gpu --timeout 300 --timeout-method=thread 2>&1 | tail -15

@@ -110,7 +110,7 @@ def test_conv3x3x3_tc_instance_norm_on_the_operand_load(N, Cin, Cout, sp):
 )
 def test_conv3x3x3_tc_with_the_folded_residual_convolution(N, Cin, Cout, sp):
     """UnetResBlock.conv1 and .conv3 (1x1x1, same input; monai/networks/blocks/dynunet_block.py:75-87, 104-108) from ONE launch: the
-    3x3x3 output and its statistics are bit-identical to the plain launch, the 1x1x1 output matches gemm_tc and torch."""
+    3x3x3 output is bit-identical to the plain launch (its statistics to fp32 round-off), the 1x1x1 output matches gemm_tc and torch."""
     g = torch.Generator().manual_seed(21)
     x = torch.randn((N, Cin, *sp), generator=g).half()
     w = (torch.randn((Cout, Cin, 3, 3, 3), generator=g) / (27 * Cin) ** 0.5).half()
@@ -120,7 +120,9 @@ def test_conv3x3x3_tc_with_the_folded_residual_convolution(N, Cin, Cout, sp):
     xr = K.pack_nc8(x.to(DEV))
     y, st, y3, st3 = K.conv3x3x3_tc(xr, pw, Cin, Cout, want_stats=True, res_w=pw3)
     y_plain, st_plain = K.conv3x3x3_tc(xr, pw, Cin, Cout, want_stats=True)
-    assert torch.equal(y.buf, y_plain.buf) and torch.equal(st, st_plain)
+    assert torch.equal(y.buf, y_plain.buf)
+    # same fp32 values, but two epilogue groups split the planes: the partial sums associate differently (fp64 finish)
+    torch.testing.assert_close(st, st_plain, rtol=2e-6, atol=1e-6 * float(st_plain.abs().max()))
     g3, gst3 = K.gemm_tc(xr, pw3, Cin, Cout, want_stats=True)
     a, b = K.unpack_nc8(y3, dtype=torch.float32), K.unpack_nc8(g3, dtype=torch.float32)
     assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max())
