@@ -256,6 +256,18 @@ int b200_mlp_fused_tc(const void* x, int x_ctot, int Nb, int S, int C, int hidde
                       const void* packed_w2, const float* b2, const float* gamma, const float* beta, float eps, void* y,
                       int y_ctot, void* stream);
 
+/* Channels-first transformer pieces of the ViT encoder (UNETR; generic fp32-faithful forms, tokens [N, C, S]):
+ * LayerNorm over the channel axis of every token (nn.LayerNorm(C): transformerblock.py:94-99, vit.py:128), gamma / beta may be NULL. */
+int b200_layernorm_cf(const void* x, int dtype, int N, int C, long long S, const float* gamma, const float* beta, float eps,
+                      void* y, void* stream);
+/* Non-overlapping patches as channels: x [N, C, D, H, W] -> y [N, C*pd*ph*pw, (D/pd)*(H/ph)*(W/pw)] (channel = (c, a, b, e) row-major,
+ * token = patch grid row-major), so that the patch projection of PatchEmbeddingBlock (patchembedding.py:104-108) is a Linear. */
+int b200_patchify(const void* x, int dtype, int N, int C, int D, int H, int W, int pd, int ph, int pw, void* y, void* stream);
+/* Multi-head self-attention softmax(q k^T * scale) v (SABlock.forward, selfattention.py:170-217, no mask / relative positions).
+ * qkv [N, 3*heads*dim_head, S]: channels ordered (q|k|v, head, dim) as produced by the combined projection; out [N, heads*dim_head, S]
+ * with channels (head, dim).  dim_head in {8, 16, 24, 32, 48, 64}. */
+int b200_mhsa_cf(const void* qkv, int dtype, int N, int heads, int dim_head, long long S, float scale, void* out, void* stream);
+
 /* LayerNorm over channels of NC8 tokens with an optional row gather (window partition + cyclic shift + zero pad of
  * swin_unetr.py:596-625): y[n, :, r] = LN(x[n, :, src[r]]) (src[r] < 0 -> zeros; src == NULL -> identity).
  * gamma/beta NULL = no affine (SwinTransformer.proj_out, swin_unetr.py:1040-1053).  src is shared by all batch items. */

@@ -201,6 +201,40 @@ def norm_act(
     return out
 
 
+def layernorm_cf(x: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | None, eps: float = 1e-5) -> torch.Tensor:
+    """nn.LayerNorm over the channel axis of channels-first tokens x[N, C, S]."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    N, Cc, S = x.shape
+    out = torch.empty_like(x)
+    _call("layernorm_cf", L.ptr(x), L.dt(x), N, Cc, S, L.ptr(_f32c(gamma)), L.ptr(_f32c(beta)), float(eps), L.ptr(out), L.stream_ptr(x.device), nbytes=_nb(x, out))
+    return out
+
+
+def patchify(x: torch.Tensor, patch: Sequence[int]) -> torch.Tensor:
+    """x [N, C, D, H, W] -> [N, C*pd*ph*pw, n_patches]: non-overlapping patches flattened into the channel axis."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    N, Cc, D, H, W = x.shape
+    pd, ph, pw = (int(v) for v in patch)
+    out = torch.empty((N, Cc * pd * ph * pw, (D // pd) * (H // ph) * (W // pw)), device=x.device, dtype=x.dtype)
+    _call("patchify", L.ptr(x), L.dt(x), N, Cc, D, H, W, pd, ph, pw, L.ptr(out), L.stream_ptr(x.device), nbytes=_nb(x, out))
+    return out
+
+
+def mhsa_cf(qkv: torch.Tensor, heads: int, dim_head: int, scale: float) -> torch.Tensor:
+    """softmax(q k^T * scale) v per head; qkv [N, 3*heads*dim_head, S] with channels (q|k|v, head, dim) -> [N, heads*dim_head, S]."""
+    L.require_cuda(qkv)
+    qkv = qkv.contiguous()
+    N, C3, S = qkv.shape
+    if C3 != 3 * heads * dim_head:
+        raise ValueError(f"mhsa_cf: {C3} channels for {heads} heads of {dim_head}")
+    out = torch.empty((N, heads * dim_head, S), device=qkv.device, dtype=qkv.dtype)
+    _call("mhsa_cf", L.ptr(qkv), L.dt(qkv), N, heads, dim_head, S, float(scale), L.ptr(out), L.stream_ptr(qkv.device),
+          flops=4.0 * N * heads * S * S * dim_head, nbytes=_nb(qkv, out))
+    return out
+
+
 def maxpool3d_2(x: torch.Tensor) -> torch.Tensor:
     L.require_cuda(x)
     N, Cc, D, H, W = x.shape

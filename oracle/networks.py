@@ -305,3 +305,89 @@ def segresnet_forward(sd: dict, x: torch.Tensor, blocks_down=(1, 2, 2, 4), block
             x = _seg_resblock(x, sd, f"up_layers.{i}.{j}", groups, slope)
     x = _seg_norm_act(x, sd, "conv_final.0", groups, slope)
     return F.conv3d(x, sd["conv_final.2.conv.weight"], sd["conv_final.2.conv.bias"])
+
+
+# ---------------------------------------------------------------------------------------------------------- UNETR
+def _vit_forward(sd, x, heads, prefix="vit"):
+    """ViT.forward with classification=False (monai/networks/nets/vit.py:118-133): conv patch embedding + position embeddings
+    (blocks/patchembedding.py:172-184), TransformerBlocks (blocks/transformerblock.py:91-99, selfattention.py:170-217), final LayerNorm."""
+    pe = prefix + ".patch_embedding"
+    p = sd[pe + ".patch_embeddings.weight"].shape[2:]
+    t = F.conv3d(x, sd[pe + ".patch_embeddings.weight"], sd[pe + ".patch_embeddings.bias"], stride=tuple(p))
+    t = t.flatten(2).transpose(-1, -2) + sd[pe + ".position_embeddings"]
+    hidden = []
+    i = 0
+    while f"{prefix}.blocks.{i}.norm1.weight" in sd:
+        b = f"{prefix}.blocks.{i}"
+        C = t.shape[-1]
+        d = C // heads
+        h = F.layer_norm(t, (C,), sd[b + ".norm1.weight"], sd[b + ".norm1.bias"], 1e-5)
+        qkv = F.linear(h, sd[b + ".attn.qkv.weight"], sd.get(b + ".attn.qkv.bias"))
+        B_, S_ = qkv.shape[:2]
+        qkv = qkv.reshape(B_, S_, 3, heads, d).permute(2, 0, 3, 1, 4)          # "b h (qkv l d) -> qkv b l h d"
+        att = torch.softmax(torch.einsum("blxd,blyd->blxy", qkv[0], qkv[1]) * d**-0.5, dim=-1)
+        o = torch.einsum("bhxy,bhyd->bhxd", att, qkv[2]).permute(0, 2, 1, 3).reshape(B_, S_, C)   # "b l h d -> b h (l d)"
+        t = t + F.linear(o, sd[b + ".attn.out_proj.weight"], sd[b + ".attn.out_proj.bias"])
+        h = F.layer_norm(t, (C,), sd[b + ".norm2.weight"], sd[b + ".norm2.bias"], 1e-5)
+        m = F.linear(F.gelu(F.linear(h, sd[b + ".mlp.linear1.weight"], sd[b + ".mlp.linear1.bias"])), sd[b + ".mlp.linear2.weight"], sd[b + ".mlp.linear2.bias"])
+        t = t + m
+        hidden.append(t)
+        i += 1
+    C = t.shape[-1]
+    return F.layer_norm(t, (C,), sd[prefix + ".norm.weight"], sd[prefix + ".norm.bias"], 1e-5), hidden
+
+
+def _unetr_norm(x, sd, prefix):
+    if (prefix + ".running_mean") in sd:   # norm_name="batch" in eval mode
+        return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd.get(prefix + ".weight"), sd.get(prefix + ".bias"), False, 0.0, 1e-5)
+    return F.instance_norm(x, weight=sd.get(prefix + ".weight"), bias=sd.get(prefix + ".bias"), eps=1e-5)
+
+
+def _unetr_conv_block(x, sd, prefix, res):
+    """UnetResBlock / UnetBasicBlock with kernel 3, stride 1 (blocks/dynunet_block.py:25-177)."""
+    out = F.leaky_relu(_unetr_norm(F.conv3d(x, sd[prefix + ".conv1.conv.weight"], None, padding=1), sd, prefix + ".norm1"), 0.01)
+    out = _unetr_norm(F.conv3d(out, sd[prefix + ".conv2.conv.weight"], None, padding=1), sd, prefix + ".norm2")
+    if res:
+        r = x
+        if (prefix + ".conv3.conv.weight") in sd:
+            r = _unetr_norm(F.conv3d(x, sd[prefix + ".conv3.conv.weight"], None), sd, prefix + ".norm3")
+        out = out + r
+    return F.leaky_relu(out, 0.01)
+
+
+def unetr_forward(sd: dict, x: torch.Tensor, num_heads: int, res_block: bool = True, conv_block: bool = True) -> torch.Tensor:
+    """UNETR.forward (monai/networks/nets/unetr.py:196-213) with UnetrPrUpBlock / UnetrUpBlock / UnetrBasicBlock
+    (blocks/unetr_block.py:22-259)."""
+    tok, hidden = _vit_forward(sd, x, num_heads)
+    p = sd["vit.patch_embedding.patch_embeddings.weight"].shape[2:]
+    feat = tuple(s // k for s, k in zip(x.shape[2:], p))
+
+    def proj_feat(t):
+        return t.reshape(t.shape[0], *feat, t.shape[-1]).permute(0, 4, 1, 2, 3).contiguous()
+
+    def pr_up(t, prefix):
+        t = F.conv_transpose3d(t, sd[prefix + ".transp_conv_init.conv.weight"], None, stride=2)
+        i = 0
+        while True:
+            if conv_block and f"{prefix}.blocks.{i}.0.conv.weight" in sd:
+                t = F.conv_transpose3d(t, sd[f"{prefix}.blocks.{i}.0.conv.weight"], None, stride=2)
+                t = _unetr_conv_block(t, sd, f"{prefix}.blocks.{i}.1", res_block)
+            elif not conv_block and f"{prefix}.blocks.{i}.conv.weight" in sd:
+                t = F.conv_transpose3d(t, sd[f"{prefix}.blocks.{i}.conv.weight"], None, stride=2)
+            else:
+                return t
+            i += 1
+
+    def up(t, skip, prefix):
+        t = F.conv_transpose3d(t, sd[prefix + ".transp_conv.conv.weight"], None, stride=2)
+        return _unetr_conv_block(torch.cat((t, skip), dim=1), sd, prefix + ".conv_block", res_block)
+
+    enc1 = _unetr_conv_block(x, sd, "encoder1.layer", res_block)
+    enc2 = pr_up(proj_feat(hidden[3]), "encoder2")
+    enc3 = pr_up(proj_feat(hidden[6]), "encoder3")
+    enc4 = pr_up(proj_feat(hidden[9]), "encoder4")
+    dec3 = up(proj_feat(tok), enc4, "decoder5")
+    dec2 = up(dec3, enc3, "decoder4")
+    dec1 = up(dec2, enc2, "decoder3")
+    out = up(dec1, enc1, "decoder2")
+    return F.conv3d(out, sd["out.conv.conv.weight"], sd["out.conv.conv.bias"])

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-echo "=== full GPU test suite"; timeout -k 5 1500 python -m pytest tests -q -m gpu --timeout 300 --timeout-method=thread 2>&1 | tail -15
+echo "=== unetr tests"; timeout -k 5 600 python -m pytest tests/test_gpu_unetr.py -q -m gpu --timeout 300 --timeout-method=thread 2>&1 | tail -25

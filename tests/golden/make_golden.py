@@ -209,6 +209,26 @@ def segresnet():
         json.dump(keys, f)
 
 
+def unetr():
+    """UNETR (eval mode) of the real reference on name-keyed deterministic weights: outputs and state_dict key / shape lists."""
+    import json
+
+    from monai.networks.nets import UNETR
+    from unetr_cases import UNETR_CASES
+
+    out, keys = {}, {}
+    for i, (kw, _, shape, seed) in enumerate(UNETR_CASES):
+        net = _load_named(UNETR(**kw), seed)
+        x = torch.randn(shape, generator=torch.Generator().manual_seed(70 + i))
+        with torch.no_grad():
+            y = net(x)
+        out[f"c{i}.x"], out[f"c{i}.y"] = x.numpy(), y.numpy()
+        keys[f"c{i}"] = {k: list(v.shape) for k, v in net.state_dict().items()}
+    save("unetr.npz", **out)
+    with open(os.path.join(HERE, "unetr_state_dict_keys.json"), "w") as f:
+        json.dump(keys, f)
+
+
 def buffered():
     """Window order / batching the predictor observes in the reference's buffered mode (with_coord=True), plus the result."""
     out = {}
@@ -520,6 +540,6 @@ def unit_goldens():
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "dynunet", "segresnet", "buffered", "resampler", "grid_pull_ref", "lazy_inverse", "transforms", "post", "patch", "unit_goldens"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "dynunet", "segresnet", "unetr", "buffered", "resampler", "grid_pull_ref", "lazy_inverse", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

@@ -240,3 +240,25 @@ def test_segresnet_oracle_and_module_tree_match_the_reference(golden_dir):
         net.load_state_dict(fill_state_dict(net.state_dict(), seed))
         y = onet.segresnet_forward(net.state_dict(), torch.from_numpy(g[f"c{i}.x"]), **okw)
         np.testing.assert_allclose(y.numpy(), g[f"c{i}.y"], rtol=1e-4, atol=1e-4)
+
+
+def test_unetr_oracle_and_module_tree_match_the_reference(golden_dir):
+    """f4: oracle.networks.unetr_forward (ViT encoder + UNETR decoder) against outputs of the real reference UNETR
+    (tests/golden/unetr.npz), and the product's UNETR has the reference's state_dict keys and shapes -- including the cross-attention
+    containers every reference TransformerBlock registers."""
+    import importlib.util
+    import json
+
+    from monai_b200.networks.nets import UNETR
+
+    spec = importlib.util.spec_from_file_location("_unetr_cases", os.path.join(golden_dir, "unetr_cases.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(golden_dir, "unetr.npz"))
+    want = json.load(open(os.path.join(golden_dir, "unetr_state_dict_keys.json")))
+    for i, (kw, okw, shape, seed) in enumerate(mod.UNETR_CASES):
+        net = UNETR(**kw)
+        assert {k: list(v.shape) for k, v in net.state_dict().items()} == want[f"c{i}"], i
+        net.load_state_dict(fill_state_dict(net.state_dict(), seed))
+        y = onet.unetr_forward(net.state_dict(), torch.from_numpy(g[f"c{i}.x"]), **okw)
+        np.testing.assert_allclose(y.numpy(), g[f"c{i}.y"], rtol=1e-4, atol=1e-4)
