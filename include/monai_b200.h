@@ -263,10 +263,18 @@ int b200_layernorm_cf(const void* x, int dtype, int N, int C, long long S, const
 /* Non-overlapping patches as channels: x [N, C, D, H, W] -> y [N, C*pd*ph*pw, (D/pd)*(H/ph)*(W/pw)] (channel = (c, a, b, e) row-major,
  * token = patch grid row-major), so that the patch projection of PatchEmbeddingBlock (patchembedding.py:104-108) is a Linear. */
 int b200_patchify(const void* x, int dtype, int N, int C, int D, int H, int W, int pd, int ph, int pw, void* y, void* stream);
-/* Multi-head self-attention softmax(q k^T * scale) v (SABlock.forward, selfattention.py:170-217, no mask / relative positions).
+/* Multi-head self-attention softmax(q k^T * scale [+ bias] [+ mask]) v on channels-first tokens.
+ * win == 0: global attention (SABlock.forward, selfattention.py:170-217).  win > 0: the token axis holds S / win windows of `win` tokens
+ * and a query attends to its own window (WindowAttention.forward, swin_unetr.py:509-532); bias (optional) = float32 device
+ * [heads][win][win] relative-position bias; region (optional) = int32 device [S / win][win] labels of compute_mask (swin_unetr.py:
+ * 779-816): pairs with different labels get -100.
  * qkv [N, 3*heads*dim_head, S]: channels ordered (q|k|v, head, dim) as produced by the combined projection; out [N, heads*dim_head, S]
  * with channels (head, dim).  dim_head in {8, 16, 24, 32, 48, 64}. */
-int b200_mhsa_cf(const void* qkv, int dtype, int N, int heads, int dim_head, long long S, float scale, void* out, void* stream);
+int b200_mhsa_cf(const void* qkv, int dtype, int N, int heads, int dim_head, long long S, float scale, int win, const float* bias,
+                 const int32_t* region, void* out, void* stream);
+/* y[n, c, r] = src[r] >= 0 ? x[n, c, src[r]] : 0 on channels-first tokens: window partition / reverse with cyclic shift and zero
+ * padding through an index table (swin_unetr.py:596-648). */
+int b200_gather_cf(const void* x, int dtype, int N, int C, long long S_in, const int32_t* src, long long S_out, void* y, void* stream);
 
 /* LayerNorm over channels of NC8 tokens with an optional row gather (window partition + cyclic shift + zero pad of
  * swin_unetr.py:596-625): y[n, :, r] = LN(x[n, :, src[r]]) (src[r] < 0 -> zeros; src == NULL -> identity).

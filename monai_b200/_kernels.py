@@ -222,16 +222,34 @@ def patchify(x: torch.Tensor, patch: Sequence[int]) -> torch.Tensor:
     return out
 
 
-def mhsa_cf(qkv: torch.Tensor, heads: int, dim_head: int, scale: float) -> torch.Tensor:
-    """softmax(q k^T * scale) v per head; qkv [N, 3*heads*dim_head, S] with channels (q|k|v, head, dim) -> [N, heads*dim_head, S]."""
+def mhsa_cf(qkv: torch.Tensor, heads: int, dim_head: int, scale: float, win: int = 0, bias: torch.Tensor | None = None,
+            region: torch.Tensor | None = None) -> torch.Tensor:
+    """softmax(q k^T * scale [+ bias] [+ shift mask]) v per head; qkv [N, 3*heads*dim_head, S] with channels (q|k|v, head, dim) ->
+    [N, heads*dim_head, S].  win > 0: S holds windows of `win` tokens, bias float32 [heads, win, win], region int32 [S // win, win]."""
     L.require_cuda(qkv)
     qkv = qkv.contiguous()
     N, C3, S = qkv.shape
     if C3 != 3 * heads * dim_head:
         raise ValueError(f"mhsa_cf: {C3} channels for {heads} heads of {dim_head}")
+    if bias is not None and (bias.dtype != torch.float32 or tuple(bias.shape) != (heads, win, win) or not bias.is_contiguous()):
+        raise ValueError("mhsa_cf: bias must be a contiguous float32 [heads, win, win] tensor")
+    if region is not None and (region.dtype != torch.int32 or region.numel() != S or not region.is_contiguous()):
+        raise ValueError("mhsa_cf: region must be a contiguous int32 tensor with one label per token")
     out = torch.empty((N, heads * dim_head, S), device=qkv.device, dtype=qkv.dtype)
-    _call("mhsa_cf", L.ptr(qkv), L.dt(qkv), N, heads, dim_head, S, float(scale), L.ptr(out), L.stream_ptr(qkv.device),
-          flops=4.0 * N * heads * S * S * dim_head, nbytes=_nb(qkv, out))
+    keys = win if win > 0 else S
+    _call("mhsa_cf", L.ptr(qkv), L.dt(qkv), N, heads, dim_head, S, float(scale), int(win), L.ptr(bias), L.ptr(region), L.ptr(out), L.stream_ptr(qkv.device),
+          flops=4.0 * N * heads * S * keys * dim_head, nbytes=_nb(qkv, out))
+    return out
+
+
+def gather_cf(x: torch.Tensor, src: torch.Tensor, s_out: int | None = None) -> torch.Tensor:
+    """y[n, c, r] = x[n, c, src[r]] (zeros where src[r] < 0) on channels-first tokens x[N, C, S]; src int32 on the device."""
+    L.require_cuda(x, src)
+    x = x.contiguous()
+    N, Cc, S = x.shape
+    s_out = int(src.numel()) if s_out is None else int(s_out)
+    out = torch.empty((N, Cc, s_out), device=x.device, dtype=x.dtype)
+    _call("gather_cf", L.ptr(x), L.dt(x), N, Cc, S, L.ptr(src), s_out, L.ptr(out), L.stream_ptr(x.device), nbytes=_nb(x, out))
     return out
 
 

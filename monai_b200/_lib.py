@@ -104,7 +104,8 @@ SIGNATURES = {
     "b200_mlp_fused_tc": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f32, vp, i32, vp]),
     "b200_layernorm_cf": (i32, [vp, i32, i32, i32, i64, vp, vp, f32, vp, vp]),
     "b200_patchify": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
-    "b200_mhsa_cf": (i32, [vp, i32, i32, i32, i32, i64, f32, vp, vp]),
+    "b200_mhsa_cf": (i32, [vp, i32, i32, i32, i32, i64, f32, i32, vp, vp, vp, vp]),
+    "b200_gather_cf": (i32, [vp, i32, i32, i32, i64, vp, i64, vp, vp]),
     "b200_layernorm_nc8": (i32, [vp, i32, i32, i64, vp, i64, vp, vp, f32, vp, vp]),
     "b200_patch_merge_ln_nc8": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp]),
     "b200_window_attention_nc8": (i32, [vp, i32, i32, i32, i32, i32, f32, vp, i32, i32, i32, vp, vp, vp]),

@@ -57,13 +57,30 @@ constexpr int kMhsaKC = 32;   // keys staged per step
 
 // block = (query tile, head, batch item); thread = one query with q[D] and the output accumulator in registers; K / V chunks of 32 keys
 // are staged in shared memory as fp32 [D][32] and read as broadcasts; online softmax in the natural-exponent domain.
+// Windowed form (win > 0; WindowAttention.forward, monai/networks/nets/swin_unetr.py:509-532): the token axis holds nW windows of
+// `win` tokens, a query attends to the keys of its window only, `bias[head][i][j]` (window-local i, j; the gathered relative position
+// bias) is added to the scaled scores, and with `region` ([nW][win] labels of compute_mask, swin_unetr.py:779-816) pairs from
+// different regions get -100 (the shifted-window mask).  blockIdx.x = window * tiles_per_window + tile.
 template <typename T, int D>
-__global__ void __launch_bounds__(kMhsaQ) mhsa_cf_kernel(const T* __restrict__ qkv, T* __restrict__ out, int heads, long long S, float scale) {
+__global__ void __launch_bounds__(kMhsaQ) mhsa_cf_kernel(const T* __restrict__ qkv, T* __restrict__ out, int heads, long long S, float scale, int win,
+                                                         const float* __restrict__ bias, const int32_t* __restrict__ region) {
   __shared__ float s_k[D][kMhsaKC];
   __shared__ float s_v[D][kMhsaKC];
+  __shared__ int s_reg[kMhsaKC];
   const int head = blockIdx.y, n = blockIdx.z;
-  const long long qi = (long long)blockIdx.x * kMhsaQ + threadIdx.x;
-  const bool live = qi < S;
+  long long k_lo = 0, k_hi = S, qi;
+  int w = 0, qloc;
+  if (win > 0) {
+    const int tiles = (win + kMhsaQ - 1) / kMhsaQ;
+    w = blockIdx.x / tiles;
+    qloc = (blockIdx.x % tiles) * kMhsaQ + threadIdx.x;
+    k_lo = (long long)w * win; k_hi = k_lo + win;
+    qi = k_lo + qloc;
+  } else {
+    qi = (long long)blockIdx.x * kMhsaQ + threadIdx.x;
+    qloc = (int)qi;
+  }
+  const bool live = win > 0 ? qloc < win : qi < S;
   const long long HD = (long long)heads * D;
   const T* qp = qkv + ((long long)n * 3 * HD + (long long)head * D) * S;
   const T* kp = qp + HD * S;
@@ -71,21 +88,26 @@ __global__ void __launch_bounds__(kMhsaQ) mhsa_cf_kernel(const T* __restrict__ q
   float q[D], acc[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) { q[d] = live ? io<T>::ld(qp + (long long)d * S + qi) * scale : 0.f; acc[d] = 0.f; }
+  const float* brow = (bias && live) ? bias + ((long long)head * win + qloc) * win : nullptr;
+  const int myreg = (region && live) ? region[(long long)w * win + qloc] : 0;
   float m = -INFINITY, l = 0.f;
-  for (long long j0 = 0; j0 < S; j0 += kMhsaKC) {
+  for (long long j0 = k_lo; j0 < k_hi; j0 += kMhsaKC) {
     __syncthreads();
     for (int e = threadIdx.x; e < D * kMhsaKC; e += kMhsaQ) {
       const int d = e / kMhsaKC, jj = e % kMhsaKC;
-      const bool ok = j0 + jj < S;
+      const bool ok = j0 + jj < k_hi;
       s_k[d][jj] = ok ? io<T>::ld(kp + (long long)d * S + j0 + jj) : 0.f;
       s_v[d][jj] = ok ? io<T>::ld(vp + (long long)d * S + j0 + jj) : 0.f;
     }
+    if (region && threadIdx.x < kMhsaKC) s_reg[threadIdx.x] = j0 + threadIdx.x < k_hi ? region[j0 + threadIdx.x] : 0;   // region is [nW][win]: index = w*win + local
     __syncthreads();
-    const int nk = (int)min((long long)kMhsaKC, S - j0);
+    const int nk = (int)min((long long)kMhsaKC, k_hi - j0);
     for (int jj = 0; jj < nk; ++jj) {
       float sc = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) sc = fmaf(q[d], s_k[d][jj], sc);
+      if (brow) sc += brow[(int)(j0 - k_lo) + jj];
+      if (region && s_reg[jj] != myreg) sc += -100.f;
       const float mn = fmaxf(m, sc);
       const float corr = __expf(m - mn), p = __expf(sc - mn);
       l = l * corr + p;
@@ -99,6 +121,20 @@ __global__ void __launch_bounds__(kMhsaQ) mhsa_cf_kernel(const T* __restrict__ q
     T* op = out + ((long long)n * HD + (long long)head * D) * S + qi;
 #pragma unroll
     for (int d = 0; d < D; ++d) io<T>::st(op + (long long)d * S, acc[d] * inv);
+  }
+}
+
+// out[n, c, r] = src[r] >= 0 ? x[n, c, src[r]] : 0: window partition + cyclic shift + zero padding of SwinTransformerBlock
+// (swin_unetr.py:596-625) and, with the inverse table, window_reverse + roll back + crop (:626-648), on channels-first tokens.
+template <typename T>
+__global__ void __launch_bounds__(256) gather_cf_kernel(const T* __restrict__ x, T* __restrict__ y, int C, long long S_in, long long S_out,
+                                                        const int32_t* __restrict__ src) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const T* xs = x + ((long long)n * C + c) * S_in;
+  T* ys = y + ((long long)n * C + c) * S_out;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < S_out; r += (long long)gridDim.x * blockDim.x) {
+    const int s = src[r];
+    ys[r] = s >= 0 ? xs[s] : T(0.f);
   }
 }
 
@@ -132,14 +168,19 @@ extern "C" int b200_patchify(const void* x, int dtype, int N, int C, int D, int 
   return B200_OK;
 }
 
-extern "C" int b200_mhsa_cf(const void* qkv, int dtype, int N, int heads, int dim_head, long long S, float scale, void* out, void* stream) {
+extern "C" int b200_mhsa_cf(const void* qkv, int dtype, int N, int heads, int dim_head, long long S, float scale, int win, const float* bias,
+                            const int32_t* region, void* out, void* stream) {
   B200_REQUIRE(qkv && out, "mhsa_cf: null pointer");
   B200_REQUIRE(N > 0 && heads > 0 && S > 0 && N <= 65535 && heads <= 65535, "mhsa_cf: bad sizes");
   B200_REQUIRE(dtype == B200_DT_F32 || dtype == B200_DT_F16, "mhsa_cf: bad dtype");
-  dim3 grid((unsigned)ceil_div(S, kMhsaQ), heads, N);
+  B200_REQUIRE(win >= 0 && (win == 0 || S % win == 0), "mhsa_cf: the token count %lld is not a multiple of the window %d", S, win);
+  B200_REQUIRE(win > 0 || (!bias && !region), "mhsa_cf: bias / region need a window size");
+  const long long blocks_x = win > 0 ? (S / win) * ceil_div(win, kMhsaQ) : ceil_div(S, kMhsaQ);
+  B200_REQUIRE(blocks_x <= 2147483647LL, "mhsa_cf: too many query tiles");
+  dim3 grid((unsigned)blocks_x, heads, N);
   cudaStream_t st = (cudaStream_t)stream;
-#define LM(D) do { if (dtype == B200_DT_F32) mhsa_cf_kernel<float, D><<<grid, kMhsaQ, 0, st>>>((const float*)qkv, (float*)out, heads, S, scale); \
-                   else mhsa_cf_kernel<__half, D><<<grid, kMhsaQ, 0, st>>>((const __half*)qkv, (__half*)out, heads, S, scale); } while (0)
+#define LM(D) do { if (dtype == B200_DT_F32) mhsa_cf_kernel<float, D><<<grid, kMhsaQ, 0, st>>>((const float*)qkv, (float*)out, heads, S, scale, win, bias, region); \
+                   else mhsa_cf_kernel<__half, D><<<grid, kMhsaQ, 0, st>>>((const __half*)qkv, (__half*)out, heads, S, scale, win, bias, region); } while (0)
   switch (dim_head) {
     case 8: LM(8); break;
     case 16: LM(16); break;
@@ -151,5 +192,17 @@ extern "C" int b200_mhsa_cf(const void* qkv, int dtype, int N, int heads, int di
   }
 #undef LM
   B200_LAUNCH_CHECK("mhsa_cf_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_gather_cf(const void* x, int dtype, int N, int C, long long S_in, const int32_t* src, long long S_out, void* y, void* stream) {
+  B200_REQUIRE(x && y && src, "gather_cf: null pointer");
+  B200_REQUIRE(N > 0 && C > 0 && S_in > 0 && S_out > 0 && N <= 65535 && C <= 65535, "gather_cf: bad sizes");
+  dim3 grid((unsigned)std::min<long long>(ceil_div(S_out, 256), 1024), C, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_DT_F32) gather_cf_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, C, S_in, S_out, src);
+  else if (dtype == B200_DT_F16) gather_cf_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, C, S_in, S_out, src);
+  else return set_err(B200_ERR_INVALID, "gather_cf: bad dtype");
+  B200_LAUNCH_CHECK("gather_cf_kernel");
   return B200_OK;
 }

@@ -31,7 +31,8 @@ import torch.nn as nn
 from ... import _kernels as K
 from ... import _lib as L
 from .._graph import GraphedForward
-from ..blocks.convolutions import Convolution
+from ..blocks.acti_norm import norm_act_from_modules
+from ..blocks.convolutions import Convolution, run_conv_module
 
 __all__ = ["SwinUNETR", "PatchMerging", "PatchMergingV2", "window_plan"]
 
@@ -292,10 +293,13 @@ class SwinUNETR(GraphedForward, nn.Module):
             raise ValueError("feature_size should be divisible by 12.")
         if spatial_dims != 3:
             raise NotImplementedError("monai_b200 SwinUNETR implements spatial_dims=3")
-        if feature_size % 48 != 0:
-            raise NotImplementedError("monai_b200 SwinUNETR needs feature_size % 48 == 0 (tensor-core tiles need 16-channel multiples)")
-        if any((feature_size * 2**i) // h != 16 for i, h in enumerate(num_heads)):
-            raise NotImplementedError("monai_b200 window attention is specialised for head_dim 16 (num_heads = feature_size/16 * 2**stage)")
+        # The tensor-core path needs 16-channel multiples (feature_size % 48 == 0) and head_dim 16; every other configuration of the
+        # reference (e.g. its default feature_size = 24: head_dim 8) runs on the generic fp32-faithful kernels (_forward_direct).
+        head_dims = [(feature_size * 2**i) // h for i, h in enumerate(num_heads)]
+        if any((feature_size * 2**i) % h for i, h in enumerate(num_heads)) or any(d not in (8, 16, 24, 32, 48, 64) for d in head_dims):
+            raise NotImplementedError(f"monai_b200 window attention supports head dimensions 8, 16, 24, 32, 48, 64 (got {head_dims})")
+        self._tc_ok = feature_size % 48 == 0 and all(d == 16 for d in head_dims)
+        self.fp32_faithful = False   # set True (or B200_SWIN_FP32=1) to run fp32-storage generic kernels: <= 1e-3 of the fp32 reference
         nn_name = norm_name if isinstance(norm_name, str) else norm_name[0]
         if str(nn_name).lower() != "instance" or (not isinstance(norm_name, str) and norm_name[1].get("affine")):
             raise NotImplementedError("monai_b200 SwinUNETR implements norm_name='instance' (non-affine)")
@@ -503,17 +507,146 @@ class SwinUNETR(GraphedForward, nn.Module):
             raise ValueError(f"expected {self.in_channels} input channel(s), got {x_in.shape[1]}")
         if x_in.dtype not in (torch.float16, torch.float32):
             raise TypeError(f"SwinUNETR takes float16/float32 inputs, got {x_in.dtype}")
+        if not self._tc_ok or self.fp32_faithful or os.environ.get("B200_SWIN_FP32"):
+            return self._forward_direct(x_in)
         if x_in.dtype == torch.float32 and not getattr(self, "_warned_fp32", False):
             import warnings
 
             # no silent degradation: the tensor-core path stores activations in fp16 (fp32 accumulation everywhere); an fp32
             # input gets fp32 logits of that fp16-storage computation (measured ~5e-3 of the output scale)
             warnings.warn("monai_b200.SwinUNETR computes with fp16 activation storage (fp32 accumulation); float32 inputs are converted. "
-                          "Expect ~1e-2 relative agreement with an fp32 reference, not 1e-3.")
+                          "Expect ~1e-2 relative agreement with an fp32 reference, not 1e-3 (set net.fp32_faithful = True for the fp32 path).")
             self._warned_fp32 = True
         if self._graph_ok():
             return self._forward_graphed(x_in, self._forward_impl)
         return self._forward_impl(x_in)
+
+    # --------------------------------------------------------------------------- fp32-faithful generic path
+    def _plan_direct(self, dims, ws, ss, dev):
+        """window_plan tables on the device + the inverse table (token -> row of the windowed tensor) for window_reverse."""
+        key = ("plan_direct", tuple(dims), tuple(ws), tuple(ss), dev)
+        hit = self._cache.store.get(key)
+        if hit is None:
+            src, region, nW, n = window_plan(dims, ws, ss)
+            inv = np.full(int(np.prod(dims)), -1, dtype=np.int32)
+            rows = np.nonzero(src >= 0)[0]
+            inv[src[rows]] = rows.astype(np.int32)
+            hit = (torch.from_numpy(src).to(dev), None if region is None else torch.from_numpy(np.ascontiguousarray(region)).to(dev),
+                   torch.from_numpy(inv).to(dev), nW, n)
+            self._cache.store[key] = hit
+        return hit
+
+    def _dense_bias(self, attn: WindowAttention, n: int, key):
+        """relative_position_bias_table[relative_position_index[:n, :n]] as float32 [heads, n, n] (swin_unetr.py:514-518)."""
+        def build():
+            idx = attn.relative_position_index[:n, :n].reshape(-1)
+            return attn.relative_position_bias_table.detach().float()[idx].reshape(n, n, -1).permute(2, 0, 1).contiguous()
+
+        return self._cache.get(("dense_bias", key, n, attn.relative_position_bias_table.device), [attn.relative_position_bias_table], build)
+
+    def _merge_params(self, ds, C: int, key):
+        """PatchMerging on the patchified tensor: b200_patchify orders the 8C channels (c, offset a*4 + b*2 + e), the reference
+        concatenates offset-major in its slice order (swin_unetr.py:726-773); permute LayerNorm affine and reduction columns once."""
+        def build():
+            order = list(itertools.product(range(2), range(2), range(2))) if ds.v2 else \
+                [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)]
+            ref_of_pat = np.empty(8 * C, dtype=np.int64)       # reference channel index of every patchified channel
+            for k, (a, b, e) in enumerate(order):
+                for c in range(C):
+                    ref_of_pat[c * 8 + a * 4 + b * 2 + e] = k * C + c
+            idx = torch.from_numpy(ref_of_pat).to(ds.norm.weight.device)
+            return (ds.norm.weight.detach().float()[idx].contiguous(), ds.norm.bias.detach().float()[idx].contiguous(),
+                    ds.reduction.weight.detach().float()[:, idx].contiguous())
+
+        return self._cache.get(("merge", key, C, ds.norm.weight.device), [ds.norm.weight, ds.norm.bias, ds.reduction.weight], build)
+
+    @staticmethod
+    def _lin(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+        """nn.Linear over the channel axis of channels-first tokens [N, Cin, S] (a 1x1x1 convolution with fp32 accumulation)."""
+        N, Cin, S = x.shape
+        return K.conv3d_direct(x.reshape(N, Cin, 1, 1, S), weight.reshape(weight.shape[0], Cin, 1, 1, 1), bias).reshape(N, weight.shape[0], S)
+
+    @staticmethod
+    def _res_block_direct(x: torch.Tensor, blk: UnetResBlock) -> torch.Tensor:
+        """UnetResBlock.forward (dynunet_block.py:97-111) on NCDHW tensors."""
+        out = norm_act_from_modules(run_conv_module(blk.conv1.conv, x), blk.norm1, blk.lrelu)
+        out = run_conv_module(blk.conv2.conv, out)
+        res = x
+        if hasattr(blk, "conv3"):
+            res = norm_act_from_modules(run_conv_module(blk.conv3.conv, x), blk.norm3, None)
+        return norm_act_from_modules(out, blk.norm2, blk.lrelu, res=res)
+
+    def _swin_stage_direct(self, t: torch.Tensor, layer: BasicLayer, key: str, pre: UnetrBasicBlock | None) -> torch.Tensor:
+        """BasicLayer.forward (swin_unetr.py:819-916) on a channels-first [N, C, d, h, w] tensor."""
+        if pre is not None:
+            t = self._res_block_direct(t, pre.layer)
+        N, C = t.shape[:2]
+        dims = tuple(int(v) for v in t.shape[2:])
+        S = dims[0] * dims[1] * dims[2]
+        x = t.reshape(N, C, S)
+        add = lambda a, b: K.norm_act(a, None, res=b, act=L.ACT_NONE)   # noqa: E731
+        for bi, blk in enumerate(layer.blocks):
+            ws, ss = _get_window_size(dims, blk.window_size, blk.shift_size)
+            src, region, inv, nW, n = self._plan_direct(dims, ws, ss, t.device)
+            h = K.layernorm_cf(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+            hw = K.gather_cf(h, src)                                                       # pad + roll + window_partition
+            qkv = self._lin(hw, blk.attn.qkv.weight, blk.attn.qkv.bias)
+            att = K.mhsa_cf(qkv, blk.num_heads, C // blk.num_heads, blk.attn.scale, win=n, bias=self._dense_bias(blk.attn, n, f"{key}.b{bi}"),
+                            region=region.reshape(-1) if (region is not None and any(s_ > 0 for s_ in ss)) else None)
+            o = self._lin(att, blk.attn.proj.weight, blk.attn.proj.bias)
+            x = add(K.gather_cf(o, inv), x)                                                # window_reverse + roll back + crop, shortcut
+            h2 = K.layernorm_cf(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+            m = K.norm_act(self._lin(h2, blk.mlp.linear1.weight, blk.mlp.linear1.bias), None, act=L.ACT_GELU)
+            x = add(self._lin(m, blk.mlp.linear2.weight, blk.mlp.linear2.bias), x)
+        t = x.reshape(N, C, *dims)
+        if layer.downsample is not None:
+            if any(d % 2 for d in dims):
+                raise NotImplementedError("monai_b200 SwinUNETR (generic path): odd token grids in PatchMerging are not implemented")
+            g, b, w = self._merge_params(layer.downsample, C, key)
+            cols = K.patchify(t, (2, 2, 2))                                                # [N, 8C, S / 8]
+            cols = K.layernorm_cf(cols, g, b, layer.downsample.norm.eps)
+            t = self._lin(cols, w, None).reshape(N, 2 * C, *(d // 2 for d in dims))
+        return t
+
+    def _forward_direct(self, x_in: torch.Tensor) -> torch.Tensor:
+        """SwinUNETR.forward (swin_unetr.py:316-330) on the generic kernels: activations keep the input's dtype (float32: the
+        reference's arithmetic to <= 1e-3), every product accumulates in fp32.  Any feature_size / head dimension of the reference."""
+        with torch.no_grad():
+            x_in = x_in.contiguous()
+            vit = self.swinViT
+            pe = vit.patch_embed
+
+            def proj_out(t):
+                if not self.normalize:
+                    return t
+                N, C = t.shape[:2]
+                return K.layernorm_cf(t.reshape(N, C, -1), None, None, 1e-5).reshape(t.shape)
+
+            t0 = run_conv_module(pe.proj, x_in)
+            if pe.norm is not None:
+                N, C = t0.shape[:2]
+                t0 = K.layernorm_cf(t0.reshape(N, C, -1), pe.norm.weight, pe.norm.bias, pe.norm.eps).reshape(t0.shape)
+            v2 = (lambda i: getattr(vit, f"layers{i}c")[0]) if self.use_v2 else (lambda i: None)
+            hs = [proj_out(t0)]
+            t = t0
+            for i in range(1, 5):
+                t = self._swin_stage_direct(t, getattr(vit, f"layers{i}")[0], f"d{i}", v2(i))
+                hs.append(proj_out(t))
+            enc0 = self._res_block_direct(x_in, self.encoder1.layer)
+            enc1 = self._res_block_direct(hs[0], self.encoder2.layer)
+            enc2 = self._res_block_direct(hs[1], self.encoder3.layer)
+            enc3 = self._res_block_direct(hs[2], self.encoder4.layer)
+            dec4 = self._res_block_direct(hs[4], self.encoder10.layer)
+
+            def up(inp, skip, block: UnetrUpBlock):
+                return self._res_block_direct(K.cat_channels([block.transp_conv(inp), skip]), block.conv_block)
+
+            dec3 = up(dec4, hs[3], self.decoder5)
+            dec2 = up(dec3, enc3, self.decoder4)
+            dec1 = up(dec2, enc2, self.decoder3)
+            dec0 = up(dec1, enc1, self.decoder2)
+            out = up(dec0, enc0, self.decoder1)
+            return self.out.conv(out)
 
     def _forward_impl(self, x_in: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():

@@ -230,3 +230,29 @@ def test_kernels_follow_the_tensors_device_not_the_current_one():
     assert got.device == x.device
     torch.testing.assert_close(got, x * 3.0, rtol=1e-5, atol=1e-5)
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("tag,ctor,seed", [
+    ("fs24_64", dict(in_channels=1, out_channels=2, feature_size=24), 5),                      # the reference's DEFAULT feature size: head_dim 8
+    ("fs48_in4_v2_64", dict(in_channels=4, out_channels=3, feature_size=48, use_v2=True), 6),
+    ("fs48_96", dict(in_channels=1, out_channels=2, feature_size=48), 4),                      # the C3 / C5 window
+])
+def test_swin_unetr_fp32_faithful_path_meets_1e3_of_the_real_reference(golden_dir, tag, ctor, seed):
+    """SwinUNETR on the generic fp32-storage kernels (`net.fp32_faithful = True`; the only path for feature sizes the tensor-core
+    kernels do not tile, e.g. the reference's default 24): <= 1e-3 of the real reference's fp32 output (north star's bar for fp32
+    paths), hidden state 0 and the deepest hidden state included."""
+    g = np.load(os.path.join(golden_dir, f"swin_unetr_{tag}.npz"))
+    net = _build(lambda: SwinUNETR(**ctor), seed)
+    if ctor["feature_size"] % 48 == 0:
+        assert net._tc_ok
+        net.fp32_faithful = True
+    else:
+        assert not net._tc_ok
+    x = torch.from_numpy(g["x"]).to(DEV).float()
+    y = net(x)
+    assert y.dtype == torch.float32
+    ref = g["y_sub"]
+    got = y.cpu().numpy()[..., ::4, ::4, ::4]
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    assert err < 1e-3, f"{tag}: max rel err {err:.3e}"
+    assert abs(float(y.double().mean()) - float(g["y_mean"])) < 1e-4 * max(1.0, float(g["y_absmean"]))
