@@ -20,6 +20,14 @@ class GaussianSmooth(Transform):
         self.sigma = sigma
         self.approx = approx
 
+    def _taps(self, sigma: float) -> torch.Tensor:
+        """erf-integrated taps of one axis; a fixed-sigma transform is called once per volume, so the (host) taps are kept"""
+        cache = self.__dict__.setdefault("_tap_cache", {})
+        key = (sigma, self.approx)
+        if key not in cache:
+            cache[key] = gaussian_1d(torch.as_tensor(sigma, dtype=torch.float), truncated=4.0, approx=self.approx)
+        return cache[key]
+
     def __call__(self, img: torch.Tensor) -> torch.Tensor:
         if not isinstance(img, torch.Tensor) or not img.is_cuda:
             raise RuntimeError("monai_b200 GaussianSmooth runs on CUDA tensors only (there is no CPU fallback)")
@@ -36,7 +44,7 @@ class GaussianSmooth(Transform):
             sigs = [torch.as_tensor(s, dtype=torch.float) for s in sig]
         else:
             sigs = [torch.as_tensor(sig, dtype=torch.float)] * nd
-        taps = [gaussian_1d(s, truncated=4.0, approx=self.approx) for s in sigs]
+        taps = [self._taps(float(s)) for s in sigs]
         one = torch.ones(1)
         lift = 3 - nd
         t3 = t.reshape(t.shape[0], *([1] * lift), *t.shape[1:])
