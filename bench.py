@@ -585,7 +585,7 @@ def secondary_lines() -> dict:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", key, "--no-secondary", *extra], capture_output=True, text=True, timeout=600)
             js = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             d = json.loads(js[-1])
-            out[key] = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "roofline", "cpu_baseline", "gpu_launches", "kernels")}
+            out[key] = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "roofline", "cpu_baseline", "gpu_launches", "kernels", "lazy") if k in d}
         except Exception as e:  # pragma: no cover - the headline line must survive a failing side measurement
             out[key] = {"error": f"{type(e).__name__}: {e}"}
     return out
