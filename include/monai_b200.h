@@ -143,6 +143,23 @@ int b200_grid_pull(const void* src, int src_dtype, int B, int C, int X, int Y, i
                    const double* scale3, const double* shift3, const int* bound3, const int* order3, int extrapolate,
                    int nearest_half_even, void* out, int out_dtype, void* stream);
 
+/* monai._C.grid_push / grid_count (monai/csrc/ext.cpp:66-74 -> csrc/resample/pushpull.h:112-216; python wrappers
+ * monai/networks/layers/spatial_transforms.py:135-311): the adjoint of b200_grid_pull.  Every voxel of input [B,C,Xi,Yi,Zi] is
+ * splatted with the same weights / bounds at the voxel coordinate grid[b, :, voxel] into out [B,C,X,Y,Z] (float32, zeroed by the
+ * call).  input == NULL computes grid_count (C must be 1): the splat of ones.  Float atomics: equal to the reference to rounding. */
+int b200_grid_push(const void* input, int in_dtype, int B, int C, int Xi, int Yi, int Zi, const void* grid, int grid_dtype,
+                   long long grid_stride_b, long long grid_stride_c, long long grid_stride_v, int X, int Y, int Z,
+                   const double* scale3, const double* shift3, const int* bound3, const int* order3, int extrapolate,
+                   void* out, void* stream);
+
+/* monai._C.grid_grad (csrc/resample/pushpull.h:218-270; python wrapper monai/networks/layers/spatial_transforms.py:314-408): spatial
+ * gradients of the interpolated volume at the grid's coordinates, out [B,C,Xo,Yo,Zo,3] (last axis: d/dx0, d/dx1, d/dx2 in voxels).
+ * Arguments as b200_grid_pull. */
+int b200_grid_grad(const void* src, int src_dtype, int B, int C, int X, int Y, int Z, const void* grid, int grid_dtype,
+                   long long grid_stride_b, long long grid_stride_c, long long grid_stride_v, int Xo, int Yo, int Zo,
+                   const double* scale3, const double* shift3, const int* bound3, const int* order3, int extrapolate,
+                   void* out, int out_dtype, void* stream);
+
 /* zero-padded separable 3-D filter (GaussianFilter, monai/networks/layers/simplelayers.py:170-249, 542-595):
  * taps_* are float32 device arrays of odd length n_*; src/dst [C,D,H,W]; tmp is a float32 scratch buffer of
  * 2*C*D*H*W elements (the two intermediate passes stay fp32). */

@@ -395,6 +395,56 @@ def grid_pull(src: torch.Tensor, grid: torch.Tensor, bound: Sequence[int], order
     return out
 
 
+def grid_push(inp: torch.Tensor | None, grid: torch.Tensor, shape: Sequence[int], bound: Sequence[int], order: Sequence[int],
+              extrapolate: bool = True) -> torch.Tensor:
+    """The adjoint of grid_pull: inp [B,C,Xi,Yi,Zi] (None = grid_count, the splat of ones) is scattered to out [B,C,*shape] (float32)
+    at the voxel coordinates grid [B,Xi,Yi,Zi,3].  See b200_grid_push."""
+    L.require_cuda(grid) if inp is None else L.require_cuda(inp, grid)
+    grid = grid.contiguous()
+    if grid.dtype not in (torch.float32, torch.float64):
+        grid = grid.float()
+    Bn, Xi, Yi, Zi, ncomp = grid.shape
+    if ncomp != 3:
+        raise ValueError(f"grid must be [B, Xi, Yi, Zi, 3], got {tuple(grid.shape)}")
+    Cc = 1
+    if inp is not None:
+        inp = inp.contiguous()
+        if inp.dtype not in (torch.float16, torch.float32):
+            inp = inp.float()
+        if inp.shape[0] != Bn or tuple(inp.shape[2:]) != (Xi, Yi, Zi):
+            raise ValueError(f"input {tuple(inp.shape)} does not match the grid {tuple(grid.shape)}")
+        Cc = inp.shape[1]
+    X, Y, Z = (int(v) for v in shape)
+    out = torch.empty((Bn, Cc, X, Y, Z), device=grid.device, dtype=torch.float32)
+    int3 = C.c_int * 3
+    _call("grid_push", L.ptr(inp) if inp is not None else None, L.dt(inp) if inp is not None else 0, Bn, Cc, Xi, Yi, Zi, L.ptr(grid),
+          2 if grid.dtype == torch.float64 else 0, Xi * Yi * Zi * 3, 1, 3, X, Y, Z, None, None, int3(*[int(b) for b in bound]),
+          int3(*[int(o) for o in order]), int(bool(extrapolate)), L.ptr(out), L.stream_ptr(grid.device),
+          nbytes=_nb(out) + (_nb(inp) if inp is not None else 0) + float(grid.numel() * grid.element_size()))
+    return out
+
+
+def grid_grad(src: torch.Tensor, grid: torch.Tensor, bound: Sequence[int], order: Sequence[int], extrapolate: bool = True) -> torch.Tensor:
+    """src [B,C,X,Y,Z]; grid [B,Xo,Yo,Zo,3] voxel coordinates -> spatial gradients [B,C,Xo,Yo,Zo,3].  See b200_grid_grad."""
+    L.require_cuda(src, grid)
+    src = src.contiguous()
+    if src.dtype not in (torch.float16, torch.float32):
+        src = src.float()
+    grid = grid.contiguous()
+    if grid.dtype not in (torch.float32, torch.float64):
+        grid = grid.float()
+    Bn, Cc, X, Y, Z = src.shape
+    _, Xo, Yo, Zo, ncomp = grid.shape
+    if ncomp != 3 or grid.shape[0] != Bn:
+        raise ValueError(f"grid must be [B, Xo, Yo, Zo, 3] with B = {Bn}, got {tuple(grid.shape)}")
+    out = torch.empty((Bn, Cc, Xo, Yo, Zo, 3), device=src.device, dtype=src.dtype)
+    int3 = C.c_int * 3
+    _call("grid_grad", L.ptr(src), L.dt(src), Bn, Cc, X, Y, Z, L.ptr(grid), 2 if grid.dtype == torch.float64 else 0, Xo * Yo * Zo * 3, 1, 3,
+          Xo, Yo, Zo, None, None, int3(*[int(b) for b in bound]), int3(*[int(o) for o in order]), int(bool(extrapolate)), L.ptr(out), L.dt(out),
+          L.stream_ptr(src.device), nbytes=_nb(src, out) + float(grid.numel() * grid.element_size()))
+    return out
+
+
 def separable_filter3d(src: torch.Tensor, taps: Sequence[torch.Tensor]) -> torch.Tensor:
     """src [C,D,H,W]; taps = three float32 device vectors of odd length; zero padding."""
     L.require_cuda(src)

@@ -85,6 +85,10 @@ SIGNATURES = {
     "b200_resample_affine": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, C.POINTER(C.c_double), i32, i32, i32, vp]),
     "b200_grid_pull": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, i64, i64, i64, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                        C.POINTER(C.c_int), C.POINTER(C.c_int), i32, i32, vp, i32, vp]),
+    "b200_grid_push": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, i64, i64, i64, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                       C.POINTER(C.c_int), C.POINTER(C.c_int), i32, vp, vp]),
+    "b200_grid_grad": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, i64, i64, i64, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                       C.POINTER(C.c_int), C.POINTER(C.c_int), i32, vp, i32, vp]),
     "b200_separable_filter3d": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp]),
     "b200_pack_nc8": (i32, [vp, i32, i32, i32, i64, vp, i32, i32, vp]),
     "b200_unpack_nc8": (i32, [vp, i32, i32, i32, i32, i64, vp, i32, vp]),

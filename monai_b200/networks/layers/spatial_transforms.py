@@ -9,7 +9,7 @@ import torch
 
 from ... import _kernels as K
 
-__all__ = ["grid_pull"]
+__all__ = ["grid_pull", "grid_push", "grid_count", "grid_grad"]
 
 
 def _codes(v, table: dict, what: str, n: int) -> list[int]:
@@ -67,5 +67,79 @@ def grid_pull(input: torch.Tensor, grid: torch.Tensor, interpolation="linear", b
     if type(like) is not torch.Tensor and hasattr(like, "copy_meta_from"):
         wrapped = type(like)(out)
         wrapped.copy_meta_from(like, copy_attr=False)
+        return wrapped
+    return out
+
+
+def _push_args(grid: torch.Tensor, interpolation, bound, what: str):
+    if not grid.is_cuda:
+        raise RuntimeError(f"monai_b200.{what} runs on CUDA tensors only (there is no CPU fallback)")
+    nd = grid.shape[-1]
+    if nd not in (1, 2, 3) or grid.dim() != nd + 2:
+        raise ValueError(f"{what} expects a grid (B, *{nd} spatial, {nd}); got {tuple(grid.shape)}")
+    order = _codes(interpolation, K.ORDERS, "interpolation", nd)
+    if nd == 3:
+        order = [order[0], order[1], order[1]]      # the reference's interpolation2 = interpolation1 quirk, as in grid_pull
+    bnd = _codes(bound, K.BOUNDS, "bound", nd)
+    if any(b == 6 for b in bnd):
+        raise NotImplementedError("bound 'sliding' (deformation fields) is not implemented")
+    g = grid.as_subclass(torch.Tensor) if type(grid) is not torch.Tensor else grid
+    if g.dtype not in (torch.float32, torch.float64):
+        g = g.float()
+    lift = 3 - nd
+    g3 = g.reshape(g.shape[0], *g.shape[1:-1], *([1] * lift), nd)
+    if lift:
+        g3 = torch.cat([g3, torch.zeros((*g3.shape[:-1], lift), dtype=g3.dtype, device=g3.device)], dim=-1)
+    return nd, lift, order + [0] * lift, bnd + [0] * lift, g3.detach()
+
+
+def grid_push(input: torch.Tensor, grid: torch.Tensor, shape=None, interpolation="linear", bound="zero", extrapolate: bool = True) -> torch.Tensor:  # noqa: A002
+    """Splat `input` (B, C, Wi[, Hi[, Di]]) at the voxel coordinates `grid` (B, Wi[, Hi[, Di]], 1|2|3) into a volume of spatial
+    `shape` (default: the input's): the adjoint of grid_pull (monai/networks/layers/spatial_transforms.py:160-235 -> monai._C.grid_push).
+    Same `interpolation` / `bound` / `extrapolate` vocabulary as grid_pull.  Float32 output; forward only."""
+    nd, lift, order, bnd, g3 = _push_args(grid, interpolation, bound, "grid_push")
+    if input.dim() != nd + 2:
+        raise ValueError(f"grid_push expects input (B, C, *{nd} spatial); got {tuple(input.shape)}")
+    x = input.as_subclass(torch.Tensor) if type(input) is not torch.Tensor else input
+    if shape is None:
+        shape = tuple(x.shape[2:])
+    shape = [int(v) for v in shape]
+    out = K.grid_push(x.detach().reshape(*x.shape, *([1] * lift)), g3, shape + [1] * lift, bnd, order, extrapolate=extrapolate)
+    out = out.reshape(x.shape[0], x.shape[1], *shape).to(x.dtype if x.dtype.is_floating_point else torch.float32)
+    if type(input) is not torch.Tensor and hasattr(input, "copy_meta_from"):
+        wrapped = type(input)(out)
+        wrapped.copy_meta_from(input, copy_attr=False)
+        return wrapped
+    return out
+
+
+def grid_count(grid: torch.Tensor, shape=None, interpolation="linear", bound="zero", extrapolate: bool = True) -> torch.Tensor:
+    """grid_push of an image of ones: how much every voxel of the `shape` volume receives (B, 1, *shape)
+    (monai/networks/layers/spatial_transforms.py:262-311 -> monai._C.grid_count).  `shape` defaults to the grid's spatial shape."""
+    nd, lift, order, bnd, g3 = _push_args(grid, interpolation, bound, "grid_count")
+    if shape is None:
+        shape = tuple(grid.shape[1:-1])
+    shape = [int(v) for v in shape]
+    out = K.grid_push(None, g3, shape + [1] * lift, bnd, order, extrapolate=extrapolate)
+    out = out.reshape(grid.shape[0], 1, *shape).to(grid.dtype if grid.dtype.is_floating_point else torch.float32)
+    if type(grid) is not torch.Tensor and hasattr(grid, "copy_meta_from"):
+        wrapped = type(grid)(out)
+        wrapped.copy_meta_from(grid, copy_attr=False)
+        return wrapped
+    return out
+
+
+def grid_grad(input: torch.Tensor, grid: torch.Tensor, interpolation="linear", bound="zero", extrapolate: bool = True) -> torch.Tensor:  # noqa: A002
+    """Spatial gradients of `input` (B, C, Wi[, Hi[, Di]]) sampled at the voxel coordinates `grid` (B, Wo[, Ho[, Do]], 1|2|3):
+    (B, C, Wo[, Ho[, Do]], 1|2|3) (monai/networks/layers/spatial_transforms.py:345-408 -> monai._C.grid_grad).  Forward only."""
+    nd, lift, order, bnd, g3 = _push_args(grid, interpolation, bound, "grid_grad")
+    if input.dim() != nd + 2:
+        raise ValueError(f"grid_grad expects input (B, C, *{nd} spatial); got {tuple(input.shape)}")
+    x = input.as_subclass(torch.Tensor) if type(input) is not torch.Tensor else input
+    out = K.grid_grad(x.detach().reshape(*x.shape, *([1] * lift)), g3, bnd, order, extrapolate=extrapolate)
+    out = out.reshape(x.shape[0], x.shape[1], *grid.shape[1:-1], 3)[..., :nd].to(x.dtype if x.dtype.is_floating_point else torch.float32)
+    if type(input) is not torch.Tensor and hasattr(input, "copy_meta_from"):
+        wrapped = type(input)(out)
+        wrapped.copy_meta_from(input, copy_attr=False)
         return wrapped
     return out

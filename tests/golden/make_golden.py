@@ -328,6 +328,50 @@ def grid_pull_ref():
     save("grid_pull.npz", **out)
 
 
+def grid_push_ref():
+    """monai._C.grid_push / grid_count of the REAL reference (oracle/_ref, CPU): random coordinates reaching outside the field of
+    view, the seven bounds, orders 0-3, extrapolate on / off; the numpy restatement (oracle/resample.py) is checked on all 56
+    combinations while the subset stored here keeps the fixture small."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import build_ref, resample as orr
+
+    C = build_ref.load()
+    assert C is not None, "run python oracle/build_ref.py first"
+    rng = np.random.default_rng(3)
+    out, n = {}, 0
+    shape = (6, 5, 8)
+    for bound in (0, 1, 2, 3, 4, 5, 7):
+        for order in (0, 1, 2, 3):
+            for extrap in (True, False):
+                x = rng.standard_normal((1, 2, 5, 6, 7)).astype(np.float32)
+                grid = (rng.random((1, 5, 6, 7, 3)) * np.array(shape) * 1.4 - 1.2).astype(np.float32)
+                r = C.grid_push(torch.from_numpy(x), torch.from_numpy(grid), list(shape), [C.BoundType(bound)] * 3, [C.InterpolationType(order)] * 3, extrap).numpy()
+                np.testing.assert_allclose(orr.grid_push(x, grid, shape, [bound] * 3, [order] * 3, extrap), r, rtol=1e-5, atol=2e-6)
+                if order in (1, 3) or (order == 0 and bound in (0, 7)):
+                    out[f"c{n}.x"], out[f"c{n}.grid"], out[f"c{n}.y"] = x, grid, r
+                    out[f"c{n}.cfg"] = np.array([bound, order, int(extrap), *shape], dtype=np.int64)
+                    n += 1
+    g = (rng.random((2, 4, 5, 6, 3)) * np.array((5, 6, 7)) * 1.2 - 0.5).astype(np.float32)
+    out["count.grid"] = g
+    out["count.y"] = C.grid_count(torch.from_numpy(g), [5, 6, 7], [C.BoundType(2)] * 3, [C.InterpolationType(1)] * 3, True).numpy()
+    out["n"] = np.array(n)
+    # monai._C.grid_grad: all 7 bounds x 8 orders x extrapolate checked against the restatement, a subset stored
+    m = 0
+    for bound in (0, 1, 2, 3, 4, 5, 7):
+        for order in range(8):
+            for extrap in (True, False):
+                x = rng.standard_normal((1, 2, 6, 5, 7)).astype(np.float32)
+                grid = (rng.random((1, 4, 5, 6, 3)) * np.array((6, 5, 7)) * 1.4 - 1.2).astype(np.float32)
+                r = C.grid_grad(torch.from_numpy(x), torch.from_numpy(grid), [C.BoundType(bound)] * 3, [C.InterpolationType(order)] * 3, extrap).numpy()
+                np.testing.assert_allclose(orr.grid_grad(x, grid, [bound] * 3, [order] * 3, extrap), r, rtol=1e-4, atol=1e-5)
+                if (extrap and order in (1, 2, 3, 5)) or (not extrap and order == 1) or (order in (0, 7) and bound == 2):
+                    out[f"g{m}.x"], out[f"g{m}.grid"], out[f"g{m}.y"] = x, grid, r
+                    out[f"g{m}.cfg"] = np.array([bound, order, int(extrap)], dtype=np.int64)
+                    m += 1
+    out["n_grad"] = np.array(m)
+    save("grid_push.npz", **out)
+
+
 def lazy_inverse():
     """Lazy resampling (Compose(lazy=True): Spacingd o RandAffined composed into one resample) and the inversion of Spacingd through
     Invertd, both from the real reference."""
@@ -540,6 +584,6 @@ def unit_goldens():
 
 if __name__ == "__main__":
     print("reference monai", monai.__version__, "torch", torch.__version__)
-    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "dynunet", "segresnet", "unetr", "buffered", "resampler", "grid_pull_ref", "lazy_inverse", "transforms", "post", "patch", "unit_goldens"]
+    which = sys.argv[1:] or ["planner", "sliding", "nets", "nets_r2", "dynunet", "segresnet", "unetr", "buffered", "resampler", "grid_pull_ref", "grid_push_ref", "lazy_inverse", "transforms", "post", "patch", "unit_goldens"]
     for w in which:
         globals()[w]()

@@ -61,3 +61,59 @@ def test_dense_grid_resample_matches_the_real_reference(golden_dir):
             assert (diff > 1e-5).mean() < 5e-3, (i, mode, pad, align, norm)
         else:
             assert diff.max() < 1e-5, (i, mode, pad, align, norm, diff.max())
+
+
+def test_grid_push_and_count_match_the_compiled_reference(golden_dir):
+    """b200_grid_push against monai._C.grid_push / grid_count of the reference's C++ (fixtures of make_golden.py grid_push_ref).
+    The kernel scatters with float atomics, so the comparison is to rounding (1e-5), not bit for bit."""
+    from monai_b200.networks.layers import grid_count, grid_push
+
+    g = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    names = {0: "replicate", 1: "dct1", 2: "dct2", 3: "dst1", 4: "dst2", 5: "dft", 7: "zero"}
+    for i in range(int(g["n"])):
+        bound, order, extrap, *shape = (int(v) for v in g[f"c{i}.cfg"])
+        x, grid = torch.from_numpy(g[f"c{i}.x"]).cuda(), torch.from_numpy(g[f"c{i}.grid"]).cuda()
+        got = grid_push(x, grid, shape, interpolation=order, bound=names[bound], extrapolate=bool(extrap)).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"c{i}.y"], rtol=1e-5, atol=4e-6, err_msg=f"case {i}: bound {bound} order {order} extrapolate {extrap}")
+    cg = torch.from_numpy(g["count.grid"]).cuda()
+    np.testing.assert_allclose(grid_count(cg, (5, 6, 7), interpolation="linear", bound="dct2").cpu().numpy(), g["count.y"], rtol=1e-5, atol=4e-6)
+    np.testing.assert_allclose(grid_count(cg.double(), (5, 6, 7), interpolation="linear", bound="dct2").cpu().numpy(), g["count.y"], rtol=1e-5, atol=4e-6)
+    # adjointness, at a size the fixture does not cover: <push(x), y> == <x, pull(y)>
+    from monai_b200.networks.layers import grid_pull
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((2, 3, 40, 36, 44), device="cuda", generator=gen)
+    y = torch.randn((2, 3, 48, 40, 32), device="cuda", generator=gen)
+    grid = torch.rand((2, 40, 36, 44, 3), device="cuda", generator=gen) * torch.tensor([52.0, 44.0, 36.0], device="cuda") - 2.0
+    for order, bound in ((1, "zero"), (3, "dct2"), (2, "dst1"), (0, "dft")):
+        lhs = (grid_push(x, grid, y.shape[2:], interpolation=order, bound=bound).double() * y.double()).sum().item()
+        rhs = (x.double() * grid_pull(y, grid, interpolation=order, bound=bound).double()).sum().item()
+        assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(rhs)) + 0.05, (order, bound, lhs, rhs)
+    with pytest.raises(ValueError):
+        grid_push(x, grid[:, :, :, :5], y.shape[2:])
+
+
+def test_grid_grad_matches_the_compiled_reference(golden_dir):
+    """b200_grid_grad against monai._C.grid_grad of the reference's C++, plus a finite-difference check of grid_pull at a larger size."""
+    from monai_b200.networks.layers import grid_grad
+
+    g = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    names = {0: "replicate", 1: "dct1", 2: "dct2", 3: "dst1", 4: "dst2", 5: "dft", 7: "zero"}
+    for i in range(int(g["n_grad"])):
+        bound, order, extrap = (int(v) for v in g[f"g{i}.cfg"])
+        x, grid = torch.from_numpy(g[f"g{i}.x"]).cuda(), torch.from_numpy(g[f"g{i}.grid"]).cuda()
+        got = grid_grad(x, grid, interpolation=order, bound=names[bound], extrapolate=bool(extrap)).cpu().numpy()
+        assert got.shape == g[f"g{i}.y"].shape
+        np.testing.assert_allclose(got, g[f"g{i}.y"], rtol=1e-4, atol=2e-5, err_msg=f"case {i}: bound {bound} order {order} extrapolate {extrap}")
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((1, 2, 24, 20, 28), device="cuda", generator=gen)
+    grid = (torch.rand((1, 16, 18, 14, 3), device="cuda", generator=gen) * torch.tensor([20.0, 16.0, 24.0], device="cuda") + 1.5).double()
+    got = grid_grad(x, grid, interpolation="cubic", bound="dct2")
+    h = 1e-3
+    for d in range(3):
+        e = torch.zeros(3, device="cuda", dtype=torch.float64)
+        e[d] = h
+        fd = (grid_pull(x, grid + e, interpolation="cubic", bound="dct2") - grid_pull(x, grid - e, interpolation="cubic", bound="dct2")) / (2 * h)
+        assert (fd - got[..., d]).abs().max().item() < 5e-2 * max(1.0, got[..., d].abs().max().item())
+    # 2-D: the lifted axis is dropped from the result
+    x2, g2 = x[:, :, :, :, 0], grid[:, :, :, 0, :2].float()
+    assert grid_grad(x2, g2, interpolation="linear", bound="zero").shape == (1, 2, 16, 18, 2)

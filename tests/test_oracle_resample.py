@@ -48,3 +48,23 @@ def test_compiled_reference_loads_when_present():
     grid = (rng.random((1, 3, 4, 5, 3)) * 9 - 2).astype(np.float32)
     ref = C.grid_pull(torch.from_numpy(x), torch.from_numpy(grid), [C.BoundType(4)] * 3, [C.InterpolationType(3)] * 3, True).numpy()
     np.testing.assert_allclose(ors.grid_pull(x, grid, [4] * 3, [3] * 3), ref, rtol=2e-4, atol=2e-5)
+
+
+def test_oracle_push_and_count_match_the_compiled_reference(golden_dir):
+    """monai._C.grid_push / grid_count outputs of the reference's own C++ (tests/golden/make_golden.py grid_push_ref)."""
+    g = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    for i in range(int(g["n"])):
+        bound, order, extrap, *shape = (int(v) for v in g[f"c{i}.cfg"])
+        got = ors.grid_push(g[f"c{i}.x"], g[f"c{i}.grid"], shape, [bound] * 3, [order] * 3, bool(extrap))
+        np.testing.assert_allclose(got, g[f"c{i}.y"], rtol=1e-5, atol=2e-6, err_msg=f"case {i}: bound {bound} order {order} extrapolate {extrap}")
+    np.testing.assert_allclose(ors.grid_count(g["count.grid"], (5, 6, 7), [2] * 3, [1] * 3), g["count.y"], rtol=1e-5, atol=2e-6)
+
+
+def test_oracle_grad_matches_the_compiled_reference(golden_dir):
+    """monai._C.grid_grad outputs of the reference's own C++ (make_golden.py grid_push_ref)."""
+    g = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    assert int(g["n_grad"]) >= 30
+    for i in range(int(g["n_grad"])):
+        bound, order, extrap = (int(v) for v in g[f"g{i}.cfg"])
+        got = ors.grid_grad(g[f"g{i}.x"], g[f"g{i}.grid"], [bound] * 3, [order] * 3, bool(extrap))
+        np.testing.assert_allclose(got, g[f"g{i}.y"], rtol=1e-4, atol=1e-5, err_msg=f"case {i}: bound {bound} order {order} extrapolate {extrap}")
