@@ -21,10 +21,11 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only-tc", action="store_true")
+    ap.add_argument("--stages", type=int, default=4, help="time the first k stages only")
     a = ap.parse_args()
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, dims, heads in (("stage1 48^3", (48, 48, 48), 3), ("stage2 24^3", (24, 24, 24), 6), ("stage3 12^3", (12, 12, 12), 12), ("stage4 6^3", (6, 6, 6), 24)):
+    for name, dims, heads in (("stage1 48^3", (48, 48, 48), 3), ("stage2 24^3", (24, 24, 24), 6), ("stage3 12^3", (12, 12, 12), 12), ("stage4 6^3", (6, 6, 6), 24))[:a.stages]:
         C = heads * 16
         for shifted in (False, True):
             ss = (3, 3, 3) if shifted else (0, 0, 0)
