@@ -369,6 +369,20 @@ def grid_push_ref():
                     out[f"g{m}.cfg"] = np.array([bound, order, int(extrap)], dtype=np.int64)
                     m += 1
     out["n_grad"] = np.array(m)
+    # tests/testing_data/1D_BP_bwd.txt: gradients of grid_pull(arange(10), arange(20) + 0.5).sum() (tests/networks/layers/test_grid_pull.py).
+    # d/d input is grid_push of ones (= grid_count into the input's shape), d/d grid is grid_grad of the input: the 30-value rows
+    # (input and grid both require grad) are golden vectors for exactly these operators.  Transcribed mechanically, keyed by label.
+    rows, labels = [], []
+    for line in open("/root/reference/tests/testing_data/1D_BP_bwd.txt"):
+        if "#" not in line:
+            continue
+        vals, lab = line.split("#")
+        v = [float(t) for t in vals.split(",") if t.strip()]
+        if len(v) == 30:
+            rows.append(v)
+            labels.append(lab.strip())
+    assert len(rows) == 56, len(rows)
+    out["bp1d_bwd.rows"], out["bp1d_bwd.labels"] = np.asarray(rows, dtype=np.float64), np.asarray(labels)
     save("grid_push.npz", **out)
 
 

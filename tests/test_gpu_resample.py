@@ -117,3 +117,25 @@ def test_grid_grad_matches_the_compiled_reference(golden_dir):
     # 2-D: the lifted axis is dropped from the result
     x2, g2 = x[:, :, :, :, 0], grid[:, :, :, 0, :2].float()
     assert grid_grad(x2, g2, interpolation="linear", bound="zero").shape == (1, 2, 16, 18, 2)
+
+
+def test_grid_count_and_grad_reproduce_1d_bp_bwd_rows(golden_dir):
+    """tests/testing_data/1D_BP_bwd.txt (the gradient rows of tests/networks/layers/test_grid_pull.py): d/d input of
+    grid_pull(...).sum() is grid_count into the input's shape, d/d grid is grid_grad -- 7 bounds x 8 spline orders, 1-D."""
+    from monai_b200.networks.layers import grid_count, grid_grad, grid_push
+
+    g = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    x = torch.arange(10, dtype=torch.float32, device="cuda").reshape(1, 1, 10)
+    grid = (torch.arange(20, dtype=torch.float32, device="cuda") + 0.5).reshape(1, 20, 1)
+    assert len(g["bp1d_bwd.labels"]) == 56
+    for row, lab in zip(g["bp1d_bwd.rows"], g["bp1d_bwd.labels"]):
+        it, bt = str(lab).split()
+        kw = dict(interpolation=it.split(".")[1], bound=bt.split(".")[1])
+        cnt = grid_count(grid, (10,), **kw)
+        assert cnt.shape == (1, 1, 10)
+        np.testing.assert_allclose(cnt.cpu().numpy().reshape(-1), row[:10], rtol=1e-4, atol=1e-4, err_msg=f"count {lab}")
+        psh = grid_push(torch.ones((1, 1, 20), device="cuda"), grid, (10,), **kw)
+        np.testing.assert_allclose(psh.cpu().numpy().reshape(-1), row[:10], rtol=1e-4, atol=1e-4, err_msg=f"push {lab}")
+        grd = grid_grad(x, grid, **kw)
+        assert grd.shape == (1, 1, 20, 1)
+        np.testing.assert_allclose(grd.cpu().numpy().reshape(-1), row[10:], rtol=1e-4, atol=1e-4, err_msg=f"grad {lab}")

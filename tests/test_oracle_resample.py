@@ -68,3 +68,21 @@ def test_oracle_grad_matches_the_compiled_reference(golden_dir):
         bound, order, extrap = (int(v) for v in g[f"g{i}.cfg"])
         got = ors.grid_grad(g[f"g{i}.x"], g[f"g{i}.grid"], [bound] * 3, [order] * 3, bool(extrap))
         np.testing.assert_allclose(got, g[f"g{i}.y"], rtol=1e-4, atol=1e-5, err_msg=f"case {i}: bound {bound} order {order} extrapolate {extrap}")
+
+
+def test_oracle_count_and_grad_reproduce_1d_bp_bwd_rows(golden_dir):
+    """tests/testing_data/1D_BP_bwd.txt: the gradients of grid_pull(arange(10), arange(20) + 0.5).sum() that
+    tests/networks/layers/test_grid_pull.py checks.  d/d input = grid_count of the grid into the input's shape (grid_push of ones),
+    d/d grid = grid_grad of the input: 56 golden rows (7 bounds x 8 orders) for the push / count / grad restatements."""
+    g = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    x = np.arange(10, dtype=np.float32).reshape(1, 1, 10, 1, 1)
+    grid = np.zeros((1, 20, 1, 1, 3), dtype=np.float32)
+    grid[0, :, 0, 0, 0] = np.arange(20, dtype=np.float32) + 0.5
+    assert len(g["bp1d_bwd.labels"]) == 56
+    for row, lab in zip(g["bp1d_bwd.rows"], g["bp1d_bwd.labels"]):
+        it, bt = str(lab).split()
+        o, b = INTERP.index(it.split(".")[1]), ors.BOUNDS[bt.split(".")[1]]
+        cnt = ors.grid_count(grid, (10, 1, 1), [b, 0, 0], [o, 0, 0]).reshape(-1)
+        np.testing.assert_allclose(cnt, row[:10], rtol=1e-4, atol=1e-4, err_msg=f"count {lab}")
+        grd = ors.grid_grad(x, grid, [b, 0, 0], [o, 0, 0])[..., 0].reshape(-1)
+        np.testing.assert_allclose(grd, row[10:], rtol=1e-4, atol=1e-4, err_msg=f"grad {lab}")
