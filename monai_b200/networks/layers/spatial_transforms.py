@@ -5,11 +5,12 @@ from __future__ import annotations
 
 from typing import Sequence
 
+import numpy as np
 import torch
 
 from ... import _kernels as K
 
-__all__ = ["grid_pull", "grid_push", "grid_count", "grid_grad"]
+__all__ = ["AffineTransform", "grid_pull", "grid_push", "grid_count", "grid_grad"]
 
 
 def _codes(v, table: dict, what: str, n: int) -> list[int]:
@@ -143,3 +144,86 @@ def grid_grad(input: torch.Tensor, grid: torch.Tensor, interpolation="linear", b
         wrapped.copy_meta_from(input, copy_attr=False)
         return wrapped
     return out
+
+
+class AffineTransform(torch.nn.Module):
+    """Apply a batch of affine matrices to a batch of images (monai/networks/layers/spatial_transforms.py:439-592): the same constructor,
+    `forward(src, theta, spatial_size=None)`, argument checks and conventions (`normalized`, `reverse_indexing`, `zero_centered`,
+    `align_corners`, bilinear / nearest, zeros / border / reflection).  The reference builds a dense F.affine_grid and calls
+    F.grid_sample; here the whole chain is folded into ONE output-index -> source-index matrix per batch item on the host
+    (monai_b200.transforms.utils.affine_transform_matrix, float64) and b200_resample_affine evaluates it per voxel, no grid in memory.
+    Forward only: `theta` is read on the host (one small device-to-host copy when it lives on the GPU)."""
+
+    def __init__(self, spatial_size=None, normalized: bool = False, mode: str = "bilinear", padding_mode: str = "zeros",
+                 align_corners: bool = True, reverse_indexing: bool = True, zero_centered: bool | None = None) -> None:
+        super().__init__()
+        if spatial_size is not None and not isinstance(spatial_size, (list, tuple)):
+            spatial_size = (spatial_size,)
+        self.spatial_size = tuple(int(s) for s in spatial_size) if spatial_size is not None else None
+        self.normalized = normalized
+        mode = str(getattr(mode, "value", mode)).lower()
+        padding_mode = str(getattr(padding_mode, "value", padding_mode)).lower()
+        if mode not in ("bilinear", "nearest", "bicubic"):
+            raise ValueError(f"unsupported mode {mode!r}; options: bilinear, nearest, bicubic")
+        if mode == "bicubic":
+            raise NotImplementedError("monai_b200 AffineTransform implements bilinear and nearest interpolation")
+        if padding_mode not in ("zeros", "border", "reflection"):
+            raise ValueError(f"unsupported padding_mode {padding_mode!r}; options: zeros, border, reflection")
+        self.mode, self.padding_mode = mode, padding_mode
+        self.align_corners = align_corners
+        self.reverse_indexing = reverse_indexing
+        if zero_centered is not None and self.normalized:
+            raise ValueError("`normalized=True` is not compatible with the `zero_centered` option.")
+        self.zero_centered = zero_centered if zero_centered is not None else False
+
+    def forward(self, src: torch.Tensor, theta: torch.Tensor, spatial_size=None) -> torch.Tensor:
+        from ...transforms import utils as U
+        from ...transforms.spatial import _resample
+
+        if not isinstance(theta, torch.Tensor):
+            raise TypeError(f"theta must be torch.Tensor but is {type(theta).__name__}.")
+        if theta.dim() not in (2, 3):
+            raise ValueError(f"theta must be Nxdxd or dxd, got {theta.shape}.")
+        if theta.dim() == 2:
+            theta = theta[None]
+        tshape = tuple(theta.shape[1:])
+        if tshape not in ((2, 3), (3, 4), (3, 3), (4, 4)):
+            raise ValueError(f"theta must be Nx3x3 or Nx4x4, got {theta.shape}.")
+        if not torch.is_floating_point(theta):
+            raise ValueError(f"theta must be floating point data, got {theta.dtype}")
+        if not isinstance(src, torch.Tensor):
+            raise TypeError(f"src must be torch.Tensor but is {type(src).__name__}.")
+        sr = src.dim() - 2
+        if sr not in (2, 3):
+            raise ValueError(f"Unsupported src dimension: {sr}, available options are [2, 3].")
+        if tshape[1] != sr + 1:
+            raise ValueError(f"theta {tuple(theta.shape)} does not match the {sr} spatial dims of src {tuple(src.shape)}")
+        if not torch.is_floating_point(src):
+            raise RuntimeError(f"src must be floating point data (as F.grid_sample requires), got {src.dtype}")
+        if theta.dtype != src.dtype:
+            raise RuntimeError(f"src and theta must share a dtype (as F.grid_sample requires), got {src.dtype} and {theta.dtype}")
+        if not src.is_cuda:
+            raise RuntimeError("monai_b200.AffineTransform runs on CUDA tensors only (there is no CPU fallback)")
+        dst_spatial = tuple(src.shape[2:])
+        if self.spatial_size is not None:
+            dst_spatial = self.spatial_size
+        if spatial_size is not None:
+            dst_spatial = tuple(int(s) for s in (spatial_size if isinstance(spatial_size, (list, tuple)) else (spatial_size,)))
+        if len(dst_spatial) != sr:
+            raise ValueError(f"spatial_size {dst_spatial} does not match the {sr} spatial dims of src")
+        th = theta.detach().to(device="cpu", dtype=torch.float64).numpy()
+        if tshape[0] == sr:      # pad to homogeneous form
+            bottom = np.zeros((th.shape[0], 1, sr + 1))
+            bottom[:, 0, -1] = 1.0
+            th = np.concatenate([th, bottom], axis=1)
+        if th.shape[0] == 1 and src.shape[0] > 1:
+            th = np.repeat(th, src.shape[0], axis=0)
+        if th.shape[0] != src.shape[0]:
+            raise ValueError(f"affine and image batch dimension must match, got affine={th.shape[0]} image={src.shape[0]}.")
+        x = src.as_subclass(torch.Tensor) if type(src) is not torch.Tensor else src
+        out = []
+        for b in range(x.shape[0]):
+            m = U.affine_transform_matrix(th[b], tuple(x.shape[2:]), dst_spatial, self.normalized, self.reverse_indexing,
+                                          bool(self.align_corners), self.zero_centered)
+            out.append(_resample(x[b].detach(), m, sr, dst_spatial, self.mode, self.padding_mode, bool(self.align_corners)))
+        return torch.stack(out, dim=0).to(src.dtype)

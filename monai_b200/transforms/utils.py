@@ -243,3 +243,44 @@ def lift_to_3d(m: np.ndarray, r: int) -> np.ndarray:
     out[lift:, lift:3] = m[:r, :r]
     out[lift:, 3] = m[:r, r]
     return out
+
+
+def _normalize_matrix(shape, align_corners: bool, zero_centered: bool) -> np.ndarray:
+    """normalize_transform (monai/networks/utils.py:243-286): voxel index -> [-1, 1] for the four (align_corners, zero_centered) cases."""
+    shape = np.asarray(shape, dtype=np.float64)
+    norm = shape.copy()
+    r = len(shape)
+    m = np.eye(r + 1)
+    with np.errstate(divide="ignore"):   # a unit-size axis with zero_centered gives 2 / 0 = inf, as the reference's torch code does
+        if align_corners:
+            norm[norm <= 1.0] = 2.0
+            m[np.arange(r), np.arange(r)] = 2.0 / (norm if zero_centered else norm - 1.0)
+            if not zero_centered:
+                m[:-1, -1] = -1.0
+        else:
+            norm[norm <= 0.0] = 2.0
+            m[np.arange(r), np.arange(r)] = 2.0 / (norm - 1.0 if zero_centered else norm)
+            if not zero_centered:
+                m[:-1, -1] = 1.0 / shape - 1.0
+    return m
+
+
+def affine_transform_matrix(theta, src_shape, dst_shape, normalized: bool, reverse_indexing: bool, align_corners: bool,
+                            zero_centered: bool = False) -> np.ndarray:
+    """The output-index -> source-index matrix of AffineTransform.forward (monai/networks/layers/spatial_transforms.py:556-592) for one
+    homogeneous (r+1)x(r+1) `theta`, in the image's own (i, j, k) axis order:
+      * normalized=False: theta is taken to normalised coordinates by to_norm_affine(align_corners=False, zero_centered)
+        (networks/utils.py:289-326: norm(src) @ theta @ inv(norm(dst)));
+      * reverse_indexing=True flips rows / columns so that affine_grid's (x, y, z) = (k, j, i) convention sees an (i, j, k) theta --
+        in (i, j, k) order that is the identity; with reverse_indexing=False theta is GIVEN in (x, y, z) order and is flipped here;
+      * affine_grid's base coordinates and grid_sample's un-normalisation with the layer's align_corners close the chain."""
+    t = np.asarray(_np(theta), dtype=np.float64)
+    r = len(src_shape)
+    if t.shape != (r + 1, r + 1):
+        raise ValueError(f"theta must be {(r + 1, r + 1)} for {r} spatial dims, got {t.shape}")
+    if not normalized:
+        t = _normalize_matrix(src_shape, False, zero_centered) @ t @ np.linalg.inv(_normalize_matrix(dst_shape, False, zero_centered))
+    if not reverse_indexing:
+        rev = list(range(r - 1, -1, -1)) + [r]
+        t = t[rev][:, rev]
+    return _unnormalize(src_shape, align_corners) @ t @ _base_grid(dst_shape, align_corners)

@@ -278,3 +278,37 @@ def as_discrete(img: torch.Tensor, argmax: bool = False, to_onehot: int | None =
     if rounding is not None:
         t = torch.round(t)
     return t.float()
+
+
+def affine_transform(src: torch.Tensor, theta: torch.Tensor, spatial_size=None, normalized: bool = False, mode: str = "bilinear",
+                     padding_mode: str = "zeros", align_corners: bool = True, reverse_indexing: bool = True, zero_centered: bool = False):
+    """AffineTransform.forward (monai/networks/layers/spatial_transforms.py:502-592) restated: theta padded to homogeneous form,
+    to_norm_affine (networks/utils.py:289-326) when it is not normalised, the (i, j, k) -> (x, y, z) flip, F.affine_grid + F.grid_sample."""
+    if theta.dim() == 2:
+        theta = theta[None]
+    theta = theta.clone()
+    sr = src.dim() - 2
+    if tuple(theta.shape[1:]) in ((2, 3), (3, 4)):
+        pad = torch.zeros((theta.shape[0], 1, sr + 1), dtype=theta.dtype)
+        pad[:, 0, -1] = 1
+        theta = torch.cat([theta, pad], dim=1)
+    src_size = tuple(src.shape)
+    dst_size = src_size if spatial_size is None else src_size[:2] + tuple(spatial_size)
+    if not normalized:
+        def norm(shape):   # normalize_transform(align_corners=False, zero_centered)
+            s = torch.tensor(shape, dtype=torch.float64)
+            n = s.clone()
+            n[n <= 0.0] = 2.0
+            m = torch.diag(torch.cat((2.0 / (n - 1.0 if zero_centered else n), torch.ones(1, dtype=torch.float64))))
+            if not zero_centered:
+                m[:-1, -1] = 1.0 / s - 1.0
+            return m.to(theta.dtype)[None]
+        theta = norm(src_size[2:]) @ theta @ torch.linalg.inv(norm(dst_size[2:]))
+    if reverse_indexing:
+        rev = list(range(sr - 1, -1, -1))
+        theta[:, :sr] = theta[:, rev]
+        theta[:, :, :sr] = theta[:, :, rev]
+    if theta.shape[0] == 1 and src_size[0] > 1:
+        theta = theta.repeat(src_size[0], 1, 1)
+    grid = F.affine_grid(theta[:, :sr], list(dst_size), align_corners=align_corners)
+    return F.grid_sample(src.contiguous(), grid, mode=mode, padding_mode=padding_mode, align_corners=align_corners)

@@ -174,3 +174,131 @@ def test_lazy_compose_runs_one_resample_and_matches_the_reference_affine(monkeyp
     y2 = pipe(False)({"image": MetaTensor(torch.from_numpy(g["x"]), affine=torch.as_tensor(g["x_affine"]))})["image"]
     assert len(calls) == 2
     np.testing.assert_allclose(y2.affine.numpy(), g["eager.affine"], atol=1e-6)
+
+
+# ---- AffineTransform (monai/networks/layers/spatial_transforms.py:439-592): reference unit goldens, tests/networks/layers/test_affine_transform.py
+_T3 = np.pi / 3
+_ROT2 = [[np.cos(_T3), -np.sin(_T3), 0], [np.sin(_T3), np.cos(_T3), 0], [0, 0, 1]]
+_ROT3 = [[1, 0, 0, 0], [0.0, np.cos(_T3), -np.sin(_T3), 0], [0, np.sin(_T3), np.cos(_T3), 0], [0, 0, 0, 1]]
+_IMG34 = [[[[4.0, 1.0, 3.0, 2.0], [7.0, 6.0, 8.0, 5.0], [3.0, 5.0, 3.0, 6.0]]]]
+AFFINE_TRANSFORM_GOLDENS = [   # (init kwargs, image, theta, call spatial_size, expected, atol)   lines 131-262 of the reference test
+    (dict(align_corners=False), _IMG34, [[1.0, 0.0, 0.0], [0.0, 1.0, -1.0]], None, [[[[0, 4, 1, 3], [0, 7, 6, 8], [0, 3, 5, 3]]]], 1e-5),
+    (dict(align_corners=False), _IMG34, [[1.0, 0.0, -1.0], [0.0, 1.0, -1.0]], None, [[[[0, 0, 0, 0], [0, 4, 1, 3], [0, 7, 6, 8]]]], 1e-5),
+    (dict(align_corners=False), _IMG34, [[1.0, 0.0, -1.0], [0.0, 1.0, 0.0]], None, [[[[0, 0, 0, 0], [4, 1, 3, 2], [7, 6, 8, 5]]]], 1e-5),
+    (dict(spatial_size=(3, 2), align_corners=False), np.arange(1.0, 13.0).reshape(1, 1, 3, 4), [[1.0, 0.0, 0.0], [0.0, 2.0, 0.0]], None,
+     [[[[1, 3], [5, 7], [9, 11]]]], 1e-5),
+    (dict(), np.arange(1.0, 13.0).reshape(1, 1, 3, 4), [[2.0, 0.0, 0.0], [0.0, 1.0, 0.0]], (1, 4), [[[[2.333333, 3.333333, 4.333333, 5.333333]]]], 1e-4),
+    (dict(spatial_size=(1, 2)), np.arange(1.0, 13.0).reshape(1, 1, 3, 4), [[2.0, 0.0, 0.0], [0.0, 2.0, 0.0]], None, [[[[1.458333, 4.958333]]]], 1e-5),
+    (dict(spatial_size=(1, 2), zero_centered=True), np.arange(1.0, 13.0).reshape(1, 1, 3, 4), [[2.0, 0.0, 0.0], [0.0, 2.0, 0.0]], None, [[[[5.5, 7.5]]]], 1e-5),
+    (dict(align_corners=False), np.arange(24.0).reshape(1, 1, 4, 6), _ROT2, None,
+     [[[[0.0, 0.06698727, 0.0, 0.0, 0.0, 0.0], [3.8660254, 0.86602557, 0.0, 0.0, 0.0, 0.0], [7.732051, 3.035899, 0.73205125, 0.0, 0.0, 0.0],
+        [11.598076, 6.901923, 2.7631402, 0.0, 0.0, 0.0]]]], 1e-3),
+    (dict(spatial_size=(3, 4), padding_mode="border", align_corners=False, mode="bilinear"), np.arange(24.0).reshape(1, 1, 4, 6), _ROT2, None,
+     [[[[7.1525574e-07, 4.9999994e-01, 1.0, 1.4999999], [3.8660259, 1.3660253, 1.8660252, 2.3660252], [7.7320518, 3.0358994, 2.7320509, 3.2320507]]]], 1e-3),
+    (dict(spatial_size=(3, 4, 2), padding_mode="border", align_corners=False, mode="bilinear"), np.arange(48.0).reshape(2, 1, 4, 2, 3), _ROT3, None,
+     [[[[[0.00000006, 0.5000001], [2.3660254, 1.3660254], [4.732051, 2.4019241], [5.0, 3.9019237]],
+        [[6.0, 6.5], [8.366026, 7.3660254], [10.732051, 8.401924], [11.0, 9.901924]],
+        [[12.0, 12.5], [14.366026, 13.366025], [16.732052, 14.401924], [17.0, 15.901923]]]],
+      [[[[24.0, 24.5], [26.366024, 25.366024], [28.732052, 26.401924], [29.0, 27.901924]],
+        [[30.0, 30.5], [32.366028, 31.366026], [34.732048, 32.401924], [35.0, 33.901924]],
+        [[36.0, 36.5], [38.366024, 37.366024], [40.73205, 38.401924], [41.0, 39.901924]]]]], 1e-4),
+]
+
+
+def _sample_with_index_matrix(img, m, out_shape, mode, padding_mode, align):
+    """CPU stand-in for b200_resample_affine (test helper): evaluates an output-index -> source-index matrix with F.grid_sample."""
+    r = len(out_shape)
+    idx = np.stack(np.meshgrid(*[np.arange(d, dtype=np.float64) for d in out_shape], indexing="ij"), -1)
+    coords = idx @ m[:r, :r].T + m[:r, r]
+    s = np.asarray(img.shape[1:], dtype=np.float64)
+    g = (coords / np.where(s > 1, s - 1, 1.0) * 2 - 1) if align else ((coords * 2 + 1) / s - 1)
+    grid = torch.from_numpy(g[..., ::-1].copy())[None]
+    return F.grid_sample(img[None].double(), grid, mode=mode, padding_mode=padding_mode, align_corners=align)[0]
+
+
+@pytest.mark.parametrize("case", range(len(AFFINE_TRANSFORM_GOLDENS)))
+def test_affine_transform_reference_unit_goldens(case):
+    """The oracle restatement AND the host matrix of monai_b200.AffineTransform reproduce every golden of the reference's unit test."""
+    init, image, theta, call_size, expected, atol = AFFINE_TRANSFORM_GOLDENS[case]
+    image = torch.as_tensor(np.asarray(image), dtype=torch.float32)
+    theta_t = torch.as_tensor(np.asarray(theta), dtype=torch.float32)
+    kw = dict(normalized=False, mode="bilinear", padding_mode="zeros", align_corners=True, reverse_indexing=True, zero_centered=False)
+    kw.update({k: v for k, v in init.items() if k != "spatial_size"})
+    size = call_size if call_size is not None else init.get("spatial_size")
+    got = otr.affine_transform(image, theta_t, spatial_size=size, **kw).numpy()
+    np.testing.assert_allclose(got, np.asarray(expected), atol=atol, rtol=1e-4)
+    # host matrix: one per batch item, evaluated by the CPU stand-in of the resampling kernel
+    sr = image.dim() - 2
+    dst = tuple(size) if size is not None else tuple(image.shape[2:])
+    th = np.asarray(theta, dtype=np.float64)
+    if th.shape[0] == sr:
+        th = np.vstack([th, np.eye(sr + 1)[-1]])
+    m = U.affine_transform_matrix(th, tuple(image.shape[2:]), dst, kw["normalized"], kw["reverse_indexing"], kw["align_corners"], kw["zero_centered"])
+    for b in range(image.shape[0]):
+        out = _sample_with_index_matrix(image[b], m, dst, kw["mode"], kw["padding_mode"], kw["align_corners"]).numpy()
+        np.testing.assert_allclose(out, np.asarray(expected)[b], atol=atol, rtol=1e-4)
+
+
+@pytest.mark.parametrize("normalized,reverse,align,zero", [(False, True, True, False), (False, True, False, True), (False, False, False, False),
+                                                           (True, False, False, False), (True, True, True, False), (False, False, True, True)])
+@pytest.mark.parametrize("sr", [2, 3])
+def test_affine_transform_matrix_equals_the_dense_grid_of_the_reference_chain(normalized, reverse, align, zero, sr):
+    """All convention switches, random theta, output size != input size: the matrix equals affine_grid + grid_sample of the restated
+    reference chain on a random image (bilinear, border) to float32 round-off; test_forward_2d / 3d of the reference (normalized=True,
+    reverse_indexing=False == plain F.affine_grid + F.grid_sample) are the (True, False, False, False) rows."""
+    rng = np.random.default_rng(sr * 10 + normalized + 2 * reverse)
+    src = (5, 7, 6)[:sr]
+    dst = (6, 4, 8)[:sr]
+    th = np.eye(sr + 1)
+    th[:sr, :sr] += rng.normal(0, 0.25, (sr, sr))
+    th[:sr, sr] = rng.normal(0, 0.3 if normalized else 1.0, sr)
+    img = torch.from_numpy(rng.standard_normal((2, 3, *src))).float()
+    want = otr.affine_transform(img.double(), torch.from_numpy(th), spatial_size=dst, normalized=normalized, mode="bilinear", padding_mode="border",
+                                align_corners=align, reverse_indexing=reverse, zero_centered=zero).numpy()
+    m = U.affine_transform_matrix(th, src, dst, normalized, reverse, align, zero)
+    for b in range(2):
+        got = _sample_with_index_matrix(img[b], m, dst, "bilinear", "border", align).numpy()
+        np.testing.assert_allclose(got, want[b], rtol=1e-9, atol=1e-9)
+    if normalized and not reverse:   # the reference's test_forward_2d / test_forward_3d identity
+        grid = F.affine_grid(torch.from_numpy(th[None, :sr]).repeat(2, 1, 1), [2, 3, *dst], align_corners=align)
+        np.testing.assert_allclose(F.grid_sample(img.double(), grid, padding_mode="border", align_corners=align).numpy(), want, rtol=1e-12, atol=1e-12)
+
+
+def test_affine_transform_argument_errors_follow_the_reference():
+    """test_ill_affine_transform of the reference (test_affine_transform.py:264-330): the same exception types, raised before any launch."""
+    from monai_b200.networks.layers import AffineTransform
+
+    rot3 = torch.as_tensor(_ROT3, dtype=torch.float32)
+    x5 = torch.arange(48.0).view(2, 1, 4, 2, 3)
+    with pytest.raises(ValueError):   # image too small
+        AffineTransform((3, 4, 2), padding_mode="border", align_corners=False)(torch.as_tensor([1.0, 2.0, 3.0]), rot3)
+    with pytest.raises(ValueError):   # output shape too small
+        AffineTransform((3, 4), padding_mode="border", align_corners=False)(x5.cuda() if torch.cuda.is_available() else _FakeCuda(x5), rot3)
+    with pytest.raises(ValueError):   # incorrect affine
+        AffineTransform((2, 3, 4))(x5, rot3[None, None])
+    with pytest.raises(ValueError):   # batch doesn't match
+        AffineTransform((2, 3, 4))(x5.cuda() if torch.cuda.is_available() else _FakeCuda(x5), rot3[None].repeat(3, 1, 1))
+    with pytest.raises(RuntimeError):  # integer image
+        AffineTransform((2, 3, 4), normalized=True)(x5.int(), rot3[None].repeat(2, 1, 1))
+    with pytest.raises(ValueError):   # wrong affine
+        AffineTransform((2, 3, 4))(x5, torch.as_tensor([[1, 0, 0, 0], [0, 0, 0, 1]]))
+    with pytest.raises(RuntimeError):  # dtype doesn't match
+        AffineTransform((1, 2))(torch.arange(1.0, 13.0).view(1, 1, 3, 4), torch.as_tensor([[2.0, 0.0, 0.0], [0.0, 2.0, 0.0]], dtype=torch.float64))
+    with pytest.raises(TypeError):
+        AffineTransform()(x5, np.eye(4))
+    with pytest.raises(ValueError):
+        AffineTransform(normalized=True, zero_centered=True)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        AffineTransform((2, 3, 4))(x5, rot3)
+
+
+class _FakeCuda(torch.Tensor):
+    """A CPU tensor that reports is_cuda, so that checks placed after the device test can be reached without a GPU."""
+
+    @staticmethod
+    def __new__(cls, t):
+        return torch.Tensor._make_subclass(cls, t)
+
+    @property
+    def is_cuda(self):
+        return True
