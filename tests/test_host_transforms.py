@@ -302,3 +302,39 @@ class _FakeCuda(torch.Tensor):
     @property
     def is_cuda(self):
         return True
+
+
+def test_normalize_transform_and_to_norm_affine_goldens_of_the_reference_unit_test():
+    """tests/networks/layers/test_affine_transform.py:27-130: every TEST_NORM_CASES / TEST_TO_NORM_AFFINE_CASES row (the zero-centred ones
+    included) and the ill-formed inputs, through monai_b200.networks.utils."""
+    from monai_b200.networks.utils import normalize_transform, to_norm_affine
+
+    norm_cases = [
+        ((4, 5), True, [[[0.666667, 0, -1], [0, 0.5, -1], [0, 0, 1]]], False),
+        ((4, 5), True, [[[0.5, 0, 0], [0, 0.4, 0], [0, 0, 1]]], True),
+        ((2, 4, 5), True, [[[2.0, 0.0, 0.0, -1.0], [0.0, 0.6666667, 0.0, -1.0], [0.0, 0.0, 0.5, -1.0], [0.0, 0.0, 0.0, 1.0]]], False),
+        ((4, 5), False, [[[0.5, 0.0, -0.75], [0.0, 0.4, -0.8], [0.0, 0.0, 1.0]]], False),
+        ((4, 5), False, [[[0.6666667, 0.0, 0.0], [0.0, 0.5, 0.0], [0.0, 0.0, 1.0]]], True),
+        ((2, 4, 5), False, [[[1.0, 0.0, 0.0, -0.5], [0.0, 0.5, 0.0, -0.75], [0.0, 0.0, 0.4, -0.8], [0.0, 0.0, 0.0, 1.0]]], False),
+    ]
+    for shape, align, expected, zero in norm_cases:
+        got = normalize_transform(shape, device=torch.device("cpu:0"), dtype=torch.float32, align_corners=align, zero_centered=zero)
+        assert got.dtype == torch.float32 and tuple(got.shape) == (1, len(shape) + 1, len(shape) + 1)
+        np.testing.assert_allclose(got.numpy(), np.asarray(expected), atol=1e-6)
+    eye3, eye4 = [[[1, 0, 0], [0, 1, 0], [0, 0, 1]]], [[[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]]
+    to_norm_cases = [
+        (eye3, (4, 6), (5, 3), True, [[[1.3333334, 0.0, 0.33333337], [0.0, 0.4, -0.6], [0.0, 0.0, 1.0]]], False),
+        (eye3, (4, 6), (5, 3), False, [[[1.25, 0.0, 0.25], [0.0, 0.5, -0.5], [0.0, 0.0, 1.0]]], False),
+        (eye4, (2, 4, 6), (3, 5, 3), True, [[[2.0, 0.0, 0.0, 1.0], [0.0, 1.3333334, 0.0, 0.33333337], [0.0, 0.0, 0.4, -0.6], [0.0, 0.0, 0.0, 1.0]]], False),
+        (eye4, (2, 4, 6), (3, 5, 3), False, [[[1.5, 0.0, 0.0, 0.5], [0.0, 1.25, 0.0, 0.25], [0.0, 0.0, 0.5, -0.5], [0.0, 0.0, 0.0, 1.0]]], False),
+        (eye4, (2, 4, 6), (3, 5, 3), False, [[[2.0, 0.0, 0.0, 0.0], [0.0, 1.3333334, 0.0, 0.0], [0.0, 0.0, 0.4, 0.0], [0.0, 0.0, 0.0, 1.0]]], True),
+    ]
+    for affine, src, dst, align, expected, zero in to_norm_cases:
+        got = to_norm_affine(torch.as_tensor(affine, dtype=torch.float32), src, dst, align, zero)
+        np.testing.assert_allclose(got.numpy(), np.asarray(expected), atol=1e-6)
+    for affine, src, dst, align in [(eye3, (3, 4, 6), (3, 5, 3), False), (eye4, (4, 6), (3, 5, 3), True),
+                                    ([[[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]]], (4, 6), (3, 5, 3), True)]:
+        with pytest.raises(TypeError):
+            to_norm_affine(affine, src, dst, align)
+        with pytest.raises(ValueError):
+            to_norm_affine(torch.as_tensor(affine, dtype=torch.float32), src, dst, align)
