@@ -1,6 +1,7 @@
 """`grid_pull` with the reference's call contract (monai/networks/layers/spatial_transforms.py:35-132), backed by the CUDA
 kernel b200_grid_pull (no monai._C needed): spline orders 0-7, the seven boundary conditions of the discrete transforms,
-per-axis settings given in the reference's [W, H, D] order (= the order of the grid's last dimension).  Inference only."""
+per-axis settings given in the reference's [W, H, D] order (= the order of the grid's last dimension).  grid_pull / grid_push /
+grid_count are differentiable (their backward passes are compositions of the same four forward kernels); grid_grad is forward only."""
 from __future__ import annotations
 
 from typing import Sequence
@@ -32,13 +33,82 @@ def _codes(v, table: dict, what: str, n: int) -> list[int]:
     return out[:n]
 
 
+class _GridPull(torch.autograd.Function):
+    """grid_pull with the gradients of monai._C.grid_pull_backward, composed from the forward kernels of the adjoint operators:
+    d/d input = grid_push(grad) into the input's shape; d/d grid = sum_c grad * grid_grad(input) (pushpull_cpu.cpp, do_push / do_grad
+    branches; checked against the compiled reference's backward entry points and its 1D_BP_bwd.txt rows)."""
+
+    @staticmethod
+    def forward(ctx, x3, g3, bnd, order, extrapolate):
+        ctx.opt = (bnd, order, extrapolate)
+        ctx.save_for_backward(x3, g3)
+        return K.grid_pull(x3, g3, bnd, order, extrapolate=extrapolate, channel_last=True)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x3, g3 = ctx.saved_tensors
+        bnd, order, extrapolate = ctx.opt
+        grad = grad.contiguous()
+        gi = gg = None
+        if ctx.needs_input_grad[0]:
+            gi = K.grid_push(grad, g3, x3.shape[2:], bnd, order, extrapolate=extrapolate).to(x3.dtype)
+        if ctx.needs_input_grad[1]:
+            gg = (K.grid_grad(x3, g3, bnd, order, extrapolate=extrapolate).float() * grad.float().unsqueeze(-1)).sum(1).to(g3.dtype)
+        return gi, gg, None, None, None
+
+
+class _GridPush(torch.autograd.Function):
+    """grid_push; backward (monai._C.grid_push_backward): d/d input = grid_pull(grad), d/d grid = sum_c input * grid_grad(grad)."""
+
+    @staticmethod
+    def forward(ctx, x3, g3, shape3, bnd, order, extrapolate):
+        ctx.opt = (bnd, order, extrapolate)
+        ctx.save_for_backward(x3, g3)
+        return K.grid_push(x3, g3, shape3, bnd, order, extrapolate=extrapolate)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x3, g3 = ctx.saved_tensors
+        bnd, order, extrapolate = ctx.opt
+        grad = grad.contiguous()
+        gi = gg = None
+        if ctx.needs_input_grad[0]:
+            gi = K.grid_pull(grad, g3, bnd, order, extrapolate=extrapolate, channel_last=True).to(x3.dtype)
+        if ctx.needs_input_grad[1]:
+            gg = (K.grid_grad(grad, g3, bnd, order, extrapolate=extrapolate).float() * x3.float().unsqueeze(-1)).sum(1).to(g3.dtype)
+        return gi, gg, None, None, None, None
+
+
+class _GridCount(torch.autograd.Function):
+    """grid_count; backward (monai._C.grid_count_backward): d/d grid = grid_grad(grad) of the single channel."""
+
+    @staticmethod
+    def forward(ctx, g3, shape3, bnd, order, extrapolate):
+        ctx.opt = (bnd, order, extrapolate)
+        ctx.save_for_backward(g3)
+        return K.grid_push(None, g3, shape3, bnd, order, extrapolate=extrapolate)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (g3,) = ctx.saved_tensors
+        bnd, order, extrapolate = ctx.opt
+        gg = None
+        if ctx.needs_input_grad[0]:
+            gg = K.grid_grad(grad.contiguous(), g3, bnd, order, extrapolate=extrapolate)[:, 0].to(g3.dtype)
+        return gg, None, None, None, None
+
+
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def grid_pull(input: torch.Tensor, grid: torch.Tensor, interpolation="linear", bound="zero", extrapolate: bool = True) -> torch.Tensor:  # noqa: A002
     """Sample `input` (B, C, Wi[, Hi[, Di]]) at the voxel coordinates `grid` (B, Wo[, Ho[, Do]], 1|2|3).
 
     interpolation: 0-7 or 'nearest' | 'linear' | 'quadratic' | 'cubic' | 'fourth' | 'fifth' | 'sixth' | 'seventh' (or a list, one per
     dimension); bound: 0 'replicate'/'nearest'/'border', 1 'dct1'/'mirror', 2 'dct2'/'reflect', 3 'dst1'/'antimirror',
     4 'dst2'/'antireflect', 5 'dft'/'wrap', 7 'zero'/'zeros' (or a list); extrapolate=False zeroes samples outside the field of view.
-    'sliding' (flow fields only) is not implemented."""
+    'sliding' (flow fields only) is not implemented.  Differentiable in `input` and `grid` (the reference's _GridPull)."""
     if not input.is_cuda:
         raise RuntimeError("monai_b200.grid_pull runs on CUDA tensors only (there is no CPU fallback)")
     nd = grid.shape[-1]
@@ -63,7 +133,10 @@ def grid_pull(input: torch.Tensor, grid: torch.Tensor, interpolation="linear", b
     g3 = g.reshape(g.shape[0], *g.shape[1:-1], *([1] * lift), nd)
     if lift:
         g3 = torch.cat([g3, torch.zeros((*g3.shape[:-1], lift), dtype=g3.dtype, device=g3.device)], dim=-1)
-    out = K.grid_pull(x3.detach(), g3.detach(), bnd + [0] * lift, order + [0] * lift, extrapolate=extrapolate, channel_last=True)
+    if _wants_grad(x3, g3):   # x3 / g3 are differentiable views of the caller's tensors: the gradients flow back through them
+        out = _GridPull.apply(x3.contiguous(), g3.contiguous(), bnd + [0] * lift, order + [0] * lift, extrapolate)
+    else:
+        out = K.grid_pull(x3.detach(), g3.detach(), bnd + [0] * lift, order + [0] * lift, extrapolate=extrapolate, channel_last=True)
     out = out.reshape(x.shape[0], x.shape[1], *g.shape[1:-1])
     if type(like) is not torch.Tensor and hasattr(like, "copy_meta_from"):
         wrapped = type(like)(out)
@@ -91,13 +164,13 @@ def _push_args(grid: torch.Tensor, interpolation, bound, what: str):
     g3 = g.reshape(g.shape[0], *g.shape[1:-1], *([1] * lift), nd)
     if lift:
         g3 = torch.cat([g3, torch.zeros((*g3.shape[:-1], lift), dtype=g3.dtype, device=g3.device)], dim=-1)
-    return nd, lift, order + [0] * lift, bnd + [0] * lift, g3.detach()
+    return nd, lift, order + [0] * lift, bnd + [0] * lift, g3
 
 
 def grid_push(input: torch.Tensor, grid: torch.Tensor, shape=None, interpolation="linear", bound="zero", extrapolate: bool = True) -> torch.Tensor:  # noqa: A002
     """Splat `input` (B, C, Wi[, Hi[, Di]]) at the voxel coordinates `grid` (B, Wi[, Hi[, Di]], 1|2|3) into a volume of spatial
     `shape` (default: the input's): the adjoint of grid_pull (monai/networks/layers/spatial_transforms.py:160-235 -> monai._C.grid_push).
-    Same `interpolation` / `bound` / `extrapolate` vocabulary as grid_pull.  Float32 output; forward only."""
+    Same `interpolation` / `bound` / `extrapolate` vocabulary as grid_pull.  Float32 accumulation; differentiable in `input` and `grid`."""
     nd, lift, order, bnd, g3 = _push_args(grid, interpolation, bound, "grid_push")
     if input.dim() != nd + 2:
         raise ValueError(f"grid_push expects input (B, C, *{nd} spatial); got {tuple(input.shape)}")
@@ -105,7 +178,11 @@ def grid_push(input: torch.Tensor, grid: torch.Tensor, shape=None, interpolation
     if shape is None:
         shape = tuple(x.shape[2:])
     shape = [int(v) for v in shape]
-    out = K.grid_push(x.detach().reshape(*x.shape, *([1] * lift)), g3, shape + [1] * lift, bnd, order, extrapolate=extrapolate)
+    x3 = x.reshape(*x.shape, *([1] * lift))
+    if _wants_grad(x3, g3):
+        out = _GridPush.apply(x3.contiguous(), g3.contiguous(), shape + [1] * lift, bnd, order, extrapolate)
+    else:
+        out = K.grid_push(x3.detach(), g3.detach(), shape + [1] * lift, bnd, order, extrapolate=extrapolate)
     out = out.reshape(x.shape[0], x.shape[1], *shape).to(x.dtype if x.dtype.is_floating_point else torch.float32)
     if type(input) is not torch.Tensor and hasattr(input, "copy_meta_from"):
         wrapped = type(input)(out)
@@ -116,12 +193,16 @@ def grid_push(input: torch.Tensor, grid: torch.Tensor, shape=None, interpolation
 
 def grid_count(grid: torch.Tensor, shape=None, interpolation="linear", bound="zero", extrapolate: bool = True) -> torch.Tensor:
     """grid_push of an image of ones: how much every voxel of the `shape` volume receives (B, 1, *shape)
-    (monai/networks/layers/spatial_transforms.py:262-311 -> monai._C.grid_count).  `shape` defaults to the grid's spatial shape."""
+    (monai/networks/layers/spatial_transforms.py:262-311 -> monai._C.grid_count).  `shape` defaults to the grid's spatial shape.
+    Differentiable in `grid`."""
     nd, lift, order, bnd, g3 = _push_args(grid, interpolation, bound, "grid_count")
     if shape is None:
         shape = tuple(grid.shape[1:-1])
     shape = [int(v) for v in shape]
-    out = K.grid_push(None, g3, shape + [1] * lift, bnd, order, extrapolate=extrapolate)
+    if _wants_grad(g3):
+        out = _GridCount.apply(g3.contiguous(), shape + [1] * lift, bnd, order, extrapolate)
+    else:
+        out = K.grid_push(None, g3.detach(), shape + [1] * lift, bnd, order, extrapolate=extrapolate)
     out = out.reshape(grid.shape[0], 1, *shape).to(grid.dtype if grid.dtype.is_floating_point else torch.float32)
     if type(grid) is not torch.Tensor and hasattr(grid, "copy_meta_from"):
         wrapped = type(grid)(out)
@@ -137,7 +218,10 @@ def grid_grad(input: torch.Tensor, grid: torch.Tensor, interpolation="linear", b
     if input.dim() != nd + 2:
         raise ValueError(f"grid_grad expects input (B, C, *{nd} spatial); got {tuple(input.shape)}")
     x = input.as_subclass(torch.Tensor) if type(input) is not torch.Tensor else input
-    out = K.grid_grad(x.detach().reshape(*x.shape, *([1] * lift)), g3, bnd, order, extrapolate=extrapolate)
+    if _wants_grad(x, g3):
+        raise NotImplementedError("monai_b200.grid_grad is forward only (its backward needs the spline Hessians); call it under torch.no_grad() "
+                                  "or on tensors that do not require grad")
+    out = K.grid_grad(x.detach().reshape(*x.shape, *([1] * lift)), g3.detach(), bnd, order, extrapolate=extrapolate)
     out = out.reshape(x.shape[0], x.shape[1], *grid.shape[1:-1], 3)[..., :nd].to(x.dtype if x.dtype.is_floating_point else torch.float32)
     if type(input) is not torch.Tensor and hasattr(input, "copy_meta_from"):
         wrapped = type(input)(out)

@@ -383,6 +383,48 @@ def grid_push_ref():
             labels.append(lab.strip())
     assert len(rows) == 56, len(rows)
     out["bp1d_bwd.rows"], out["bp1d_bwd.labels"] = np.asarray(rows, dtype=np.float64), np.asarray(labels)
+    # all 224 rows in file order (per (bound, interpolation): input+grid, input only, grid only, none), ragged -> padded with NaN
+    allrows, alllabels = [], []
+    for line in open("/root/reference/tests/testing_data/1D_BP_bwd.txt"):
+        if "#" not in line:
+            continue
+        vals, lab = line.split("#")
+        v = [float(t) for t in vals.split(",") if t.strip()]
+        allrows.append(v + [np.nan] * (30 - len(v)))
+        alllabels.append(lab.strip())
+    assert len(allrows) == 224
+    out["bp1d_bwd.all_rows"], out["bp1d_bwd.all_labels"] = np.asarray(allrows, dtype=np.float64), np.asarray(alllabels)
+    # monai._C.grid_pull_backward / grid_push_backward / grid_count_backward of the compiled reference on 3-D data: the backward passes of
+    # monai_b200's grid_pull / grid_push / grid_count are compositions of the forward operators (checked here on all bounds x orders 0-3 x
+    # extrapolate; a subset stored)
+    k = 0
+    for bound in (0, 1, 2, 3, 4, 5, 7):
+        for order in (0, 1, 2, 3):
+            for extrap in (True, False):
+                B_, I_ = [C.BoundType(bound)] * 3, [C.InterpolationType(order)] * 3
+                x = rng.standard_normal((1, 2, 6, 5, 7)).astype(np.float32)
+                grid = (rng.random((1, 4, 5, 6, 3)) * np.array((6, 5, 7)) * 1.3 - 1.0).astype(np.float32)
+                gout = rng.standard_normal((1, 2, 4, 5, 6)).astype(np.float32)
+                xin = rng.standard_normal((1, 2, 4, 5, 6)).astype(np.float32)
+                gvol = rng.standard_normal((1, 2, 6, 5, 7)).astype(np.float32)
+                gcnt = rng.standard_normal((1, 1, 6, 5, 7)).astype(np.float32)
+                tg = lambda a: torch.from_numpy(a).requires_grad_()   # noqa: E731
+                pb = C.grid_pull_backward(torch.from_numpy(gout), tg(x), tg(grid), B_, I_, extrap)
+                sb = C.grid_push_backward(torch.from_numpy(gvol), tg(xin), tg(grid), B_, I_, extrap)
+                cb = C.grid_count_backward(torch.from_numpy(gcnt), tg(grid), B_, I_, extrap)
+                bb, oo = [bound] * 3, [order] * 3
+                np.testing.assert_allclose(orr.grid_push(gout, grid, x.shape[2:], bb, oo, extrap), pb[0].numpy(), rtol=1e-4, atol=1e-5)
+                np.testing.assert_allclose((orr.grid_grad(x, grid, bb, oo, extrap) * gout[..., None]).sum(1), pb[1].numpy(), rtol=1e-4, atol=1e-5)
+                np.testing.assert_allclose(orr.grid_pull(gvol, grid, bb, oo, extrap), sb[0].numpy(), rtol=1e-4, atol=1e-5)
+                np.testing.assert_allclose((orr.grid_grad(gvol, grid, bb, oo, extrap) * xin[..., None]).sum(1), sb[1].numpy(), rtol=1e-4, atol=1e-5)
+                np.testing.assert_allclose(orr.grid_grad(gcnt, grid, bb, oo, extrap)[:, 0], cb.numpy(), rtol=1e-4, atol=1e-5)
+                if order in (1, 3) and (extrap or bound == 7):
+                    for name, val in (("x", x), ("grid", grid), ("gout", gout), ("xin", xin), ("gvol", gvol), ("gcnt", gcnt), ("pull_dx", pb[0].numpy()),
+                                      ("pull_dg", pb[1].numpy()), ("push_dx", sb[0].numpy()), ("push_dg", sb[1].numpy()), ("count_dg", cb.numpy())):
+                        out[f"b{k}.{name}"] = val
+                    out[f"b{k}.cfg"] = np.array([bound, order, int(extrap)], dtype=np.int64)
+                    k += 1
+    out["n_bwd"] = np.array(k)
     save("grid_push.npz", **out)
 
 

@@ -86,3 +86,21 @@ def test_oracle_count_and_grad_reproduce_1d_bp_bwd_rows(golden_dir):
         np.testing.assert_allclose(cnt, row[:10], rtol=1e-4, atol=1e-4, err_msg=f"count {lab}")
         grd = ors.grid_grad(x, grid, [b, 0, 0], [o, 0, 0])[..., 0].reshape(-1)
         np.testing.assert_allclose(grd, row[10:], rtol=1e-4, atol=1e-4, err_msg=f"grad {lab}")
+
+
+def test_backward_compositions_match_the_compiled_reference(golden_dir):
+    """monai._C.grid_pull_backward / grid_push_backward / grid_count_backward (fixtures of make_golden.py grid_push_ref): the backward
+    passes monai_b200 attaches to grid_pull / grid_push / grid_count are compositions of the FORWARD operators --
+    pull: (push(grad), sum_c grad * grad_op(input)); push: (pull(grad), sum_c input * grad_op(grad)); count: grad_op(grad)."""
+    g = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    assert int(g["n_bwd"]) >= 16
+    for i in range(int(g["n_bwd"])):
+        bound, order, extrap = (int(v) for v in g[f"b{i}.cfg"])
+        bb, oo, ex = [bound] * 3, [order] * 3, bool(extrap)
+        x, grid, gout, xin, gvol, gcnt = (g[f"b{i}.{k}"] for k in ("x", "grid", "gout", "xin", "gvol", "gcnt"))
+        tol = dict(rtol=1e-4, atol=1e-5, err_msg=f"case {i}: bound {bound} order {order} extrapolate {extrap}")
+        np.testing.assert_allclose(ors.grid_push(gout, grid, x.shape[2:], bb, oo, ex), g[f"b{i}.pull_dx"], **tol)
+        np.testing.assert_allclose((ors.grid_grad(x, grid, bb, oo, ex) * gout[..., None]).sum(1), g[f"b{i}.pull_dg"], **tol)
+        np.testing.assert_allclose(ors.grid_pull(gvol, grid, bb, oo, ex), g[f"b{i}.push_dx"], **tol)
+        np.testing.assert_allclose((ors.grid_grad(gvol, grid, bb, oo, ex) * xin[..., None]).sum(1), g[f"b{i}.push_dg"], **tol)
+        np.testing.assert_allclose(ors.grid_grad(gcnt, grid, bb, oo, ex)[:, 0], g[f"b{i}.count_dg"], **tol)
