@@ -9,6 +9,7 @@ from __future__ import annotations
 import copy
 from typing import Any
 
+import numpy as np
 import torch
 
 __all__ = ["MetaTensor", "is_meta", "get_affine", "rewrap"]
@@ -112,7 +113,9 @@ def _copy_tree(x):
         return [_copy_tree(v) for v in x] if type(x) is list else copy.deepcopy(x)
     if isinstance(x, tuple):
         return tuple(_copy_tree(v) for v in x) if type(x) is tuple else copy.deepcopy(x)
-    return copy.deepcopy(x)   # numpy arrays, user objects
+    if type(x) is np.ndarray and x.dtype != object:
+        return x.copy()
+    return copy.deepcopy(x)   # object arrays, numpy scalars, user objects
 
 
 def is_meta(x) -> bool:
@@ -131,8 +134,13 @@ def rewrap(out: torch.Tensor, like, affine=None, applied=None):
     """Wrap `out` with the metadata of `like` (same class as `like`), optionally replacing the affine."""
     if not is_meta(like):
         return out
-    w = type(like)(out)
-    w.copy_meta_from(like, copy_attr=True)
+    if type(like) is MetaTensor:
+        # same result as MetaTensor(out) + copy_meta_from, without building the default affine that copy_meta_from replaces at once
+        w = (out.as_subclass(torch.Tensor) if type(out) is not torch.Tensor else out).as_subclass(MetaTensor)
+        w.copy_meta_from(like, copy_attr=True)
+    else:
+        w = type(like)(out)
+        w.copy_meta_from(like, copy_attr=True)
     if affine is not None:
         w.affine = torch.as_tensor(affine, dtype=torch.float64)
     if applied is not None:

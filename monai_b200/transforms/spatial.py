@@ -86,6 +86,7 @@ class SpatialResample(Transform):
     def __init__(self, mode="bilinear", padding_mode="border", align_corners: bool = False, dtype=np.float64, lazy: bool = False):
         self.mode, self.padding_mode, self.align_corners, self.dtype, self.lazy = mode, padding_mode, align_corners, dtype, lazy
         self._trace = True
+        self._algebra_cache: dict = {}
 
     def inverse(self, data):
         """Resample back to the grid the forward call started from (spatial/array.py:238-253)."""
@@ -105,22 +106,37 @@ class SpatialResample(Transform):
         rank = min(len(img.shape) - 1, src_affine_full.shape[0] - 1, 3)
         if (not isinstance(spatial_size, int) or spatial_size != -1) and spatial_size is not None:
             rank = min(len(tuple(spatial_size)), 3)
-        src_affine = U.to_affine_nd(rank, src_affine_full)
-        dst = U.to_affine_nd(rank, dst_affine) if dst_affine is not None else src_affine
-        in_size = np.asarray(original_shape[:rank])
-        if isinstance(spatial_size, int) and spatial_size == -1:
-            spatial_size = in_size
-        elif spatial_size is None and rank > 1:
-            spatial_size, _ = U.compute_shape_offset(in_size, src_affine, dst)
-        sp = np.asarray([int(s) if s >= 0 else int(d) for s, d in zip(tuple(spatial_size)[:rank], in_size)])
-        try:
-            xform = np.eye(rank + 1) if rank < 2 else np.linalg.solve(src_affine, dst)
-        except np.linalg.LinAlgError as e:
-            raise ValueError(f"src affine is not invertible {src_affine}, {dst}.") from e
-        xform = U.to_affine_nd(rank, xform)
-        unchanged = (np.allclose(src_affine, dst, atol=U.AFFINE_TOL) and np.allclose(sp, in_size)) or (
-            np.allclose(xform, np.eye(len(xform)), atol=U.AFFINE_TOL) and np.allclose(sp, in_size)
-        )
+        # The affine algebra below depends on (source affine, destination affine, shapes) only: a dataset resampled to one spacing
+        # repeats it volume after volume, and at 1-2 us per numpy call it -- not the kernel -- set the pace of the C4 pipeline.
+        src_np = src_affine_full.numpy() if isinstance(src_affine_full, torch.Tensor) else np.asarray(src_affine_full)
+        dst_np = None if dst_affine is None else (dst_affine.detach().cpu().numpy() if isinstance(dst_affine, torch.Tensor) else np.asarray(dst_affine))
+        size_key = spatial_size if (spatial_size is None or isinstance(spatial_size, int)) else tuple(int(v) for v in spatial_size)
+        key = (src_np.shape, src_np.astype(np.float64).tobytes(), None if dst_np is None else (dst_np.shape, dst_np.astype(np.float64).tobytes()),
+               original_shape, size_key, rank)
+        hit = self._algebra_cache.get(key)
+        if hit is None:
+            src_affine = U.to_affine_nd(rank, src_affine_full)
+            dst = U.to_affine_nd(rank, dst_affine) if dst_affine is not None else src_affine
+            in_size = np.asarray(original_shape[:rank])
+            if isinstance(spatial_size, int) and spatial_size == -1:
+                spatial_size = in_size
+            elif spatial_size is None and rank > 1:
+                spatial_size, _ = U.compute_shape_offset(in_size, src_affine, dst)
+            sp = np.asarray([int(s) if s >= 0 else int(d) for s, d in zip(tuple(spatial_size)[:rank], in_size)])
+            try:
+                xform = np.eye(rank + 1) if rank < 2 else np.linalg.solve(src_affine, dst)
+            except np.linalg.LinAlgError as e:
+                raise ValueError(f"src affine is not invertible {src_affine}, {dst}.") from e
+            xform = U.to_affine_nd(rank, xform)
+            unchanged = bool((np.allclose(src_affine, dst, atol=U.AFFINE_TOL) and np.allclose(sp, in_size)) or (
+                np.allclose(xform, np.eye(len(xform)), atol=U.AFFINE_TOL) and np.allclose(sp, in_size)
+            ))
+            if len(self._algebra_cache) >= 64:
+                self._algebra_cache.clear()
+            self._algebra_cache[key] = (src_affine, sp, xform, unchanged)
+        else:
+            src_affine, sp, xform, unchanged = hit
+        src_affine, sp, xform = src_affine.copy(), sp.copy(), xform.copy()    # callers keep / edit these (applied_operations, lazy)
         info = {"class": type(self).__name__, "orig_size": original_shape, "extra_info": {"src_affine": src_affine, "align_corners": align,
                 "mode": getattr(mode or self.mode, "value", mode or self.mode), "padding_mode": getattr(padding_mode or self.padding_mode, "value", padding_mode or self.padding_mode)}}
         if not self._trace:
@@ -139,7 +155,11 @@ class SpatialResample(Transform):
         if unchanged:
             out = (img.as_subclass(torch.Tensor) if type(img) is not torch.Tensor else img).to(torch.float32)
             return rewrap(out, img, new_affine, info)
-        mat = U.sample_matrix_from_xform(xform, original_shape[:rank], sp, align)
+        mkey = (key, bool(align))
+        mat = self._algebra_cache.get(mkey)
+        if mat is None:
+            mat = U.sample_matrix_from_xform(xform, original_shape[:rank], sp, align)
+            self._algebra_cache[mkey] = mat
         out = _resample(img, mat, rank, tuple(int(s) for s in sp), mode or self.mode, padding_mode or self.padding_mode, align)
         return rewrap(out, img, new_affine, info)
 
@@ -161,6 +181,7 @@ class Spacing(Transform):
             if (not np.isnan(mn)) and (not np.isnan(mx)) and ((mx < mn) or (mn < 0)):
                 raise ValueError(f"min_pixdim {self.min_pixdim} must be positive, smaller than max {self.max_pixdim}.")
         self.sp_resample = SpatialResample(mode=mode, padding_mode=padding_mode, align_corners=align_corners, dtype=dtype, lazy=lazy)
+        self._algebra_cache: dict = {}     # (input affine, shape, scale_extent) -> (affine, new affine, output shape); see SpatialResample
 
     def inverse(self, data):
         """spatial/array.py:545-546: the inverse of the SpatialResample this transform ran."""
@@ -177,6 +198,15 @@ class Spacing(Transform):
 
             warnings.warn("`data_array` is not of type MetaTensor, assuming affine to be identity.")
             input_affine = np.eye(sr + 1, dtype=np.float64)
+        scale_extent = self.scale_extent if scale_extent is None else scale_extent
+        in_np = input_affine.numpy() if isinstance(input_affine, torch.Tensor) else np.asarray(input_affine)
+        ckey = (in_np.shape, in_np.astype(np.float64).tobytes(), original_shape, bool(scale_extent), self.pixdim.tobytes(), self.min_pixdim.tobytes(),
+                self.max_pixdim.tobytes(), bool(self.diagonal))
+        chit = self._algebra_cache.get(ckey)
+        if chit is not None:
+            affine_, new_affine, output_shape = chit[0].copy(), chit[1].copy(), list(chit[2])
+            return self._finish(data_array, affine_, new_affine, output_shape, original_shape, mode, padding_mode, align_corners, dtype,
+                                output_spatial_shape, lazy)
         affine_ = U.to_affine_nd(sr, input_affine)
         out_d = self.pixdim[:sr].copy()
         if out_d.size < sr:
@@ -192,9 +222,15 @@ class Spacing(Transform):
                 raise ValueError(f"min_pixdim is larger than max_pixdim at dim {idx}: min {mn} max {mx} out {target}.")
             out_d[idx] = _d if (mn - U.AFFINE_TOL) <= _d <= (mx + U.AFFINE_TOL) else target
         new_affine = U.zoom_affine(affine_, out_d, diagonal=self.diagonal)
-        scale_extent = self.scale_extent if scale_extent is None else scale_extent
         output_shape, offset = U.compute_shape_offset(original_shape, affine_, new_affine, scale_extent)
         new_affine[:sr, -1] = offset[:sr]
+        if len(self._algebra_cache) >= 64:
+            self._algebra_cache.clear()
+        self._algebra_cache[ckey] = (np.array(affine_, copy=True), np.array(new_affine, copy=True), [int(v) for v in output_shape])
+        return self._finish(data_array, affine_, new_affine, output_shape, original_shape, mode, padding_mode, align_corners, dtype,
+                            output_spatial_shape, lazy)
+
+    def _finish(self, data_array, affine_, new_affine, output_shape, original_shape, mode, padding_mode, align_corners, dtype, output_spatial_shape, lazy):
         actual_shape = list(output_shape) if output_spatial_shape is None else output_spatial_shape
         lazy_ = bool(getattr(self.sp_resample, "lazy", False)) if lazy is None else bool(lazy)
         kw = {"lazy": True} if lazy_ else {}
