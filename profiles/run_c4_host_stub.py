@@ -46,4 +46,4 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(20):
     for v in vols: y = pipe({"image": mk(v)})["image"]
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(40)
+pstats.Stats(pr).sort_stats("tottime").print_stats(30)
