@@ -1,3 +1,5 @@
+# HISTORICAL: this session ran on an intermediate state of csrc/attn_tc.cu (between commits e2d23aa and a37a933) in which the variants were
+# selectable at run time (B200_ATTN_POLY / B200_ATTN_PT / B200_ATTN_PREFETCH); the committed kernel keeps only the winner.
 # anti-phase control (B200_ATTN_PHASE = cycles per 32 keys) and L2 prefetch (B200_ATTN_PREFETCH) on the P-in-TMEM kernel
 mkdir -p gpurun_out; rm -f gpurun_out/r02_attention_phase.jsonl
 for cfg in "0 0" "0 1" "140 1" "175 1" "210 1" "175 0" "250 1"; do

@@ -1,3 +1,5 @@
+# HISTORICAL: this session ran on an intermediate state of csrc/attn_tc.cu (between commits e2d23aa and a37a933) in which the variants were
+# selectable at run time (B200_ATTN_POLY / B200_ATTN_PT / B200_ATTN_PREFETCH); the committed kernel keeps only the winner.
 # A/B of the FMA-pipe exponential share in window_attention_tc (B200_ATTN_POLY = 0 | 2 | 3), parity under 3, ncu of 0 and 3.
 mkdir -p gpurun_out
 for P in 0 2 3; do

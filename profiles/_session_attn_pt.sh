@@ -1,3 +1,5 @@
+# HISTORICAL: this session ran on an intermediate state of csrc/attn_tc.cu (between commits e2d23aa and a37a933) in which the variants were
+# selectable at run time (B200_ATTN_POLY / B200_ATTN_PT / B200_ATTN_PREFETCH); the committed kernel keeps only the winner.
 # P kept in TMEM (B200_ATTN_PT=1): parity, A/B timing, phase timeline
 mkdir -p gpurun_out
 echo "=== parity with PT=1"; B200_ATTN_PT=1 timeout -k 5 200 python -m pytest tests/test_gpu_swin.py -x -q -k "attention_tcgen05 or swin_unetr" 2>&1 | tail -8
