@@ -338,3 +338,56 @@ def test_normalize_transform_and_to_norm_affine_goldens_of_the_reference_unit_te
             to_norm_affine(affine, src, dst, align)
         with pytest.raises(ValueError):
             to_norm_affine(torch.as_tensor(affine, dtype=torch.float32), src, dst, align)
+
+
+def _stand_in_resample(img, mat, r, out_shape, mode, padding_mode, align):
+    """numerically real CPU stand-in for spatial._resample (F.grid_sample evaluates the index matrix)"""
+    mode = {"bilinear": "bilinear", "linear": "bilinear", "trilinear": "bilinear", "nearest": "nearest", 1: "bilinear", 0: "nearest"}[getattr(mode, "value", mode)]
+    pad = {"zeros": "zeros", "constant": "zeros", "border": "border", "nearest": "border", "reflection": "reflection", "reflect": "reflection"}[str(getattr(padding_mode, "value", padding_mode))]
+    t = img.as_subclass(torch.Tensor) if type(img) is not torch.Tensor else img
+    return _sample_with_index_matrix(t, np.asarray(mat, dtype=np.float64), tuple(int(s) for s in out_shape), mode, pad, bool(align)).float()
+
+
+def test_host_path_with_a_stand_in_kernel_reproduces_the_real_reference_fixtures(monkeypatch, golden_dir):
+    """The shipped host code of Spacing / Spacingd / RandAffined / Compose(lazy) -- including the memoised affine algebra: every
+    transform object is called twice -- with only the resampling kernel replaced by a CPU evaluation of the SAME index matrix:
+    values, shapes and affines of the real-reference fixtures the GPU tests use (tests/golden/transforms.npz, lazy_inverse.npz)."""
+    import ast
+    import os
+
+    import monai_b200.transforms.spatial as S
+    from monai_b200.data import MetaTensor
+    from monai_b200.transforms import Compose, RandAffined, Spacing, Spacingd
+
+    monkeypatch.setattr(S, "_resample", _stand_in_resample)
+    g = np.load(os.path.join(golden_dir, "transforms.npz"))
+    for tag in ("s0", "s1", "s2", "s3", "s4"):
+        kw = ast.literal_eval(str(g[f"{tag}.kw"]))
+        sp = Spacing(pixdim=tuple(g[f"{tag}.pixdim"]), **kw)
+        for rep in range(2):     # the second call takes the cached algebra
+            r = sp(MetaTensor(torch.from_numpy(g["img"]), affine=torch.as_tensor(g[f"{tag}.affine"])))
+            assert tuple(r.shape) == g[f"{tag}.y"].shape, (tag, rep)
+            np.testing.assert_allclose(r.affine.numpy(), g[f"{tag}.new_affine"], rtol=1e-9, atol=1e-9, err_msg=f"{tag} call {rep}")
+            if kw.get("mode") == "nearest":
+                assert (r.numpy() != g[f"{tag}.y"]).mean() < 2e-3, tag
+            else:
+                np.testing.assert_allclose(r.numpy(), g[f"{tag}.y"], rtol=1e-3, atol=1e-4, err_msg=f"{tag} call {rep}")
+    for tag in ("r0", "r1", "r2"):
+        kw = ast.literal_eval(str(g[f"{tag}.kw"]))
+        t = RandAffined(keys=["image"], **kw)
+        t.set_random_state(seed=0)
+        r = t({"image": MetaTensor(torch.from_numpy(g["img2"]), affine=torch.eye(4))})["image"]
+        assert tuple(r.shape) == g[f"{tag}.y"].shape, tag
+        if kw["mode"] != "nearest":
+            np.testing.assert_allclose(r.numpy(), g[f"{tag}.y"], rtol=1e-3, atol=2e-4, err_msg=tag)
+        np.testing.assert_allclose(r.affine.numpy(), g[f"{tag}.new_affine"], rtol=1e-5, atol=1e-5, err_msg=tag)
+    li = np.load(os.path.join(golden_dir, "lazy_inverse.npz"))
+    for tag, lazy in (("eager", False), ("lazy", True)):
+        c = Compose([Spacingd(keys=["image"], pixdim=(1.0, 1.0, 1.0), mode="bilinear"),
+                     RandAffined(keys=["image"], prob=1.0, rotate_range=(0.2,) * 3, scale_range=(0.1,) * 3, translate_range=(5,) * 3, mode="bilinear", padding_mode="border")],
+                    lazy=lazy)
+        for rep in range(2):
+            c.transforms[1].set_random_state(seed=0)
+            y = c({"image": MetaTensor(torch.from_numpy(li["x"]), affine=torch.as_tensor(li["x_affine"]))})["image"]
+            np.testing.assert_allclose(y.numpy(), li[f"{tag}.y"], rtol=1e-4, atol=1e-4, err_msg=f"{tag} call {rep}")
+            np.testing.assert_allclose(np.asarray(y.affine), li[f"{tag}.affine"], atol=1e-6)
