@@ -391,3 +391,83 @@ def test_host_path_with_a_stand_in_kernel_reproduces_the_real_reference_fixtures
             y = c({"image": MetaTensor(torch.from_numpy(li["x"]), affine=torch.as_tensor(li["x_affine"]))})["image"]
             np.testing.assert_allclose(y.numpy(), li[f"{tag}.y"], rtol=1e-4, atol=1e-4, err_msg=f"{tag} call {rep}")
             np.testing.assert_allclose(np.asarray(y.affine), li[f"{tag}.affine"], atol=1e-6)
+
+
+def test_grid_autograd_glue_with_oracle_backed_kernels_reproduces_the_reference_gradient_rows(monkeypatch, golden_dir):
+    """The autograd Functions of grid_pull / grid_push / grid_count (networks/layers/spatial_transforms.py) with the four kernel wrappers
+    replaced by the numpy restatements: the reference's test_grid_pull gradient check, all 224 rows of 1D_BP_bwd.txt, plus the 3-D backward
+    fixtures of the compiled reference.  (The same assertions run against the real kernels in tests/test_gpu_zz_grid_autograd.py.)"""
+    import os
+
+    import monai_b200.networks.layers.spatial_transforms as ST
+    from oracle import resample as orr
+
+    def k_pull(x, g, b, o, extrapolate=True, channel_last=True, **kw):
+        return torch.from_numpy(orr.grid_pull(x.detach().numpy(), g.detach().numpy(), b, o, extrapolate))
+
+    def k_push(x, g, shape, b, o, extrapolate=True):
+        if x is None:
+            return torch.from_numpy(orr.grid_count(g.detach().numpy(), shape, b, o, extrapolate))
+        return torch.from_numpy(orr.grid_push(x.detach().numpy(), g.detach().numpy(), shape, b, o, extrapolate))
+
+    def k_grad(x, g, b, o, extrapolate=True):
+        return torch.from_numpy(orr.grid_grad(x.detach().numpy(), g.detach().numpy(), b, o, extrapolate))
+
+    monkeypatch.setattr(ST.K, "grid_pull", k_pull)
+    monkeypatch.setattr(ST.K, "grid_push", k_push)
+    monkeypatch.setattr(ST.K, "grid_grad", k_grad)
+    fake = lambda t, g=False: _FakeCuda(t).requires_grad_(g)   # noqa: E731
+    gp = np.load(os.path.join(golden_dir, "grid_push.npz"))
+    rows, labels = gp["bp1d_bwd.all_rows"], gp["bp1d_bwd.all_labels"]
+    for i in range(0, 224, 4):
+        it, bt = str(labels[i]).split()
+        for j, (input_g, grid_g) in enumerate(((True, True), (True, False), (False, True), (False, False))):
+            want = rows[i + j][~np.isnan(rows[i + j])]
+            x = fake(torch.arange(10, dtype=torch.float32).reshape(1, 1, 10), input_g)
+            base = fake(torch.arange(20, dtype=torch.float32).reshape(1, 20, 1), grid_g)
+            res = ST.grid_pull(x, base + 0.5, interpolation=it.split(".")[1], bound=bt.split(".")[1])
+            grads = []
+            if input_g or grid_g:
+                res.sum().backward()
+            if input_g:
+                grads.append(x.grad.as_subclass(torch.Tensor).view(-1))
+            if grid_g:
+                grads.append(base.grad.as_subclass(torch.Tensor).view(-1))
+            got = torch.cat(grads).numpy() if grads else np.zeros(1)
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4, err_msg=f"{labels[i]} input_g={input_g} grid_g={grid_g}")
+    names = {0: "replicate", 1: "dct1", 2: "dct2", 3: "dst1", 4: "dst2", 5: "dft", 7: "zero"}
+    for i in range(int(gp["n_bwd"])):
+        bound, order, extrap = (int(v) for v in gp[f"b{i}.cfg"])
+        kw = dict(interpolation=order, bound=names[bound], extrapolate=bool(extrap))
+        tol = dict(rtol=1e-4, atol=2e-5, err_msg=f"case {i}")
+        t = lambda k, g=False: fake(torch.from_numpy(gp[f"b{i}.{k}"]), g)   # noqa: E731
+        pl = lambda a: a.as_subclass(torch.Tensor).numpy()   # noqa: E731
+        x, grid = t("x", True), t("grid", True)
+        ST.grid_pull(x, grid, **kw).backward(torch.from_numpy(gp[f"b{i}.gout"]))
+        np.testing.assert_allclose(pl(x.grad), gp[f"b{i}.pull_dx"], **tol)
+        np.testing.assert_allclose(pl(grid.grad), gp[f"b{i}.pull_dg"], **tol)
+        xin, grid = t("xin", True), t("grid", True)
+        ST.grid_push(xin, grid, (6, 5, 7), **kw).backward(torch.from_numpy(gp[f"b{i}.gvol"]))
+        np.testing.assert_allclose(pl(xin.grad), gp[f"b{i}.push_dx"], **tol)
+        np.testing.assert_allclose(pl(grid.grad), gp[f"b{i}.push_dg"], **tol)
+        grid = t("grid", True)
+        ST.grid_count(grid, (6, 5, 7), **kw).backward(torch.from_numpy(gp[f"b{i}.gcnt"]))
+        np.testing.assert_allclose(pl(grid.grad), gp[f"b{i}.count_dg"], **tol)
+    with pytest.raises(NotImplementedError):
+        ST.grid_grad(fake(torch.zeros(1, 1, 4, 4, 4), True), fake(torch.zeros(1, 2, 2, 2, 3)))
+
+
+@pytest.mark.parametrize("case", range(len(AFFINE_TRANSFORM_GOLDENS)))
+def test_affine_transform_layer_with_a_stand_in_kernel_reproduces_the_reference_goldens(monkeypatch, case):
+    """monai_b200.networks.layers.AffineTransform as shipped (argument handling, per-item matrices, stacking, dtype) with the resampling
+    kernel replaced by its CPU stand-in: the goldens of the reference's unit test.  The GPU twin is tests/test_gpu_zz_affine_transform.py."""
+    import monai_b200.transforms.spatial as S
+    from monai_b200.networks.layers import AffineTransform
+
+    monkeypatch.setattr(S, "_resample", _stand_in_resample)
+    init, image, theta, call_size, expected, atol = AFFINE_TRANSFORM_GOLDENS[case]
+    image = _FakeCuda(torch.as_tensor(np.asarray(image), dtype=torch.float32))
+    theta = torch.as_tensor(np.asarray(theta), dtype=torch.float32)
+    out = AffineTransform(**init)(image, theta, call_size)
+    assert out.dtype == torch.float32
+    np.testing.assert_allclose(out.as_subclass(torch.Tensor).numpy(), np.asarray(expected), atol=max(atol, 1e-4), rtol=1e-4)
